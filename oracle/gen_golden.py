@@ -1,0 +1,196 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED reference on CPU.
+
+(ORACLE - test infrastructure.  Runs only in the build container: needs /root/reference.)
+
+    python -m oracle.gen_golden            # writes tests/golden/ref_*.npz
+
+What is executed is the reference's own code:
+  * asr.modeling.decoders.rnn_transducer.RNNTDecoder.forward (rnn_transducer.py:81-145) with
+    the warp_rnnt shim (oracle/warp_rnnt_shim.py; warp_rnnt itself is CUDA-only and absent),
+  * asr.modeling.decoders.ctc.CTCDecoder.forward (ctc.py:87-174).
+For each case the file stores the inputs, every parameter of the decoder (state_dict), the loss
+values the reference returned and the gradients autograd produced for eouts and all parameters.
+The two in-tree smoke inputs (rnnt_aligner.py:201-208, ctc_aligner.py:225-233) and the upstream
+warp-transducer known-answer vector are frozen as fixtures as well.
+"""
+import os
+import sys
+from collections import namedtuple
+
+import numpy as np
+import torch
+
+REF = os.environ.get("EMOASR_REFERENCE", "/root/reference")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "golden")
+
+
+def _params(**kw):
+    base = dict(
+        dec_num_layers=1, dec_hidden_size=16, embedding_size=8, joint_hidden_size=16,
+        enc_hidden_size=12, vocab_size=11, eos_id=2, blank_id=0, mtl_ctc_weight=0.0,
+        kd_weight=0, dropout_emb_rate=0.0, dropout_dec_rate=0.0,
+    )
+    base.update(kw)
+    return namedtuple("Params", base.keys())(**base)
+
+
+def _labels(g, B, U, V, ulens, eos):
+    # labels drawn from {1} u [4,V) (specials per corpora/utils/spm_train.py:7-9), eos padded
+    pool = torch.tensor([1] + list(range(4, V)))
+    ys = pool[torch.randint(len(pool), (B, U), generator=g)]
+    for b in range(B):
+        ys[b, ulens[b]:] = eos
+    return ys
+
+
+def _np(t):
+    return t.detach().cpu().numpy()
+
+
+def rnnt_case(name, seed, B, T, U, p, tlens, ulens, mtl_ctc_weight=0.0):
+    from asr.modeling.decoders.rnn_transducer import RNNTDecoder
+
+    p = p._replace(mtl_ctc_weight=mtl_ctc_weight)
+    torch.manual_seed(seed)
+    g = torch.Generator().manual_seed(seed)
+    dec = RNNTDecoder(p, phase="test")
+    dec.train()
+    eouts = torch.randn(B, T, p.enc_hidden_size, generator=g).requires_grad_()
+    elens = torch.tensor(tlens, dtype=torch.long)
+    ylens = torch.tensor(ulens, dtype=torch.long)
+    ys = _labels(g, B, U, p.vocab_size, ulens, p.eos_id)
+    eos = torch.full((B, 1), p.eos_id, dtype=torch.long)
+    ys_in = torch.cat([eos, ys], dim=1)          # datasets.py:160-173
+    ys_out = torch.cat([ys, eos], dim=1)
+    loss, loss_dict, logits = dec(eouts, elens, None, ys, ylens, ys_in, ys_out)
+    loss.backward()
+    out = {
+        "eouts": _np(eouts), "elens": _np(elens), "ys": _np(ys), "ylens": _np(ylens),
+        "ys_in": _np(ys_in), "ys_out": _np(ys_out),
+        "loss_total": _np(loss), "grad_eouts": _np(eouts.grad), "logits": _np(logits),
+        "meta_mtl_ctc_weight": np.float64(mtl_ctc_weight),
+    }
+    for k, v in loss_dict.items():
+        out["lossdict." + k] = _np(v)
+    for k, v in dec.state_dict().items():
+        out["param." + k] = _np(v)
+    for k, v in dec.named_parameters():
+        out["grad." + k] = _np(v.grad) if v.grad is not None else np.zeros(0)
+    for k, v in p._asdict().items():
+        out["hp." + k] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, float(loss))
+
+
+def ctc_case(name, seed, B, T, U, V, He, tlens, ulens):
+    from asr.modeling.decoders.ctc import CTCDecoder
+
+    p = _params(enc_hidden_size=He, vocab_size=V)
+    torch.manual_seed(seed)
+    g = torch.Generator().manual_seed(seed)
+    dec = CTCDecoder(p)
+    eouts = torch.randn(B, T, He, generator=g).requires_grad_()
+    elens = torch.tensor(tlens, dtype=torch.long)
+    ylens = torch.tensor(ulens, dtype=torch.long)
+    ys = _labels(g, B, U, V, ulens, p.eos_id)
+    loss, loss_dict, logits = dec(eouts, elens, None, ys, ylens)
+    loss.backward()
+    out = {
+        "eouts": _np(eouts), "elens": _np(elens), "ys": _np(ys), "ylens": _np(ylens),
+        "loss_total": _np(loss), "grad_eouts": _np(eouts.grad), "logits": _np(logits),
+    }
+    for k, v in dec.state_dict().items():
+        out["param." + k] = _np(v)
+    for k, v in dec.named_parameters():
+        out["grad." + k] = _np(v.grad)
+    for k, v in p._asdict().items():
+        out["hp." + k] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, float(loss))
+
+
+def smoke_fixtures():
+    """Freeze the reference's two in-tree __main__ smoke inputs and what its CPU-runnable loss
+    functions give on them, plus the warp-transducer known-answer vector."""
+    import warp_rnnt  # the shim
+
+    # rnnt_aligner.py:201-208 (seed 1, (2,10,6,5))
+    torch.manual_seed(1)
+    lp = torch.randn((2, 10, 6, 5)).log_softmax(dim=-1).requires_grad_()
+    labels = torch.tensor([[1, 2, 1, 2, 0], [1, 2, 1, 2, 3]], dtype=torch.int32)
+    T = torch.tensor([8, 10], dtype=torch.int32)
+    U = torch.tensor([4, 5], dtype=torch.int32)
+    costs = warp_rnnt.rnnt_loss(lp, labels, T, U, reduction=None, blank=0)
+    costs.sum().backward()
+    np.savez_compressed(
+        os.path.join(OUT, "ref_rnnt_aligner_smoke.npz"),
+        log_probs=_np(lp), labels=_np(labels), T=_np(T), U=_np(U), costs=_np(costs), grad=_np(lp.grad),
+    )
+    print("ref_rnnt_aligner_smoke", _np(costs))
+
+    # ctc_aligner.py:225-233 (seed 1, (2,8,3))
+    torch.manual_seed(1)
+    logits = (torch.rand((2, 8, 3)) * 10.0).requires_grad_()
+    elens = torch.tensor([7, 8])
+    ys = torch.tensor([[1, 2, 0], [1, 2, 1]])
+    ylens = torch.tensor([2, 3])
+    fn = torch.nn.CTCLoss(blank=0, reduction="sum", zero_infinity=True)   # ctc.py:36-38
+    loss = fn(logits.transpose(1, 0).log_softmax(dim=2), ys, elens, ylens) / logits.size(0)
+    loss.backward()
+    np.savez_compressed(
+        os.path.join(OUT, "ref_ctc_aligner_smoke.npz"),
+        logits=_np(logits), elens=_np(elens), ys=_np(ys), ylens=_np(ylens), loss=_np(loss),
+        grad=_np(logits.grad),
+    )
+    print("ref_ctc_aligner_smoke", float(loss))
+
+    # warp-transducer known answer: acts are *logits*
+    acts = torch.tensor(
+        [[[[0.1, 0.6, 0.1, 0.1, 0.1], [0.1, 0.1, 0.6, 0.1, 0.1], [0.1, 0.1, 0.2, 0.8, 0.1]],
+          [[0.1, 0.6, 0.1, 0.1, 0.1], [0.1, 0.1, 0.2, 0.1, 0.1], [0.7, 0.1, 0.2, 0.1, 0.1]]]],
+        requires_grad=True)
+    lp = acts.log_softmax(-1)
+    cost = warp_rnnt.rnnt_loss(lp, torch.tensor([[1, 2]], dtype=torch.int32),
+                               torch.tensor([2], dtype=torch.int32), torch.tensor([2], dtype=torch.int32),
+                               reduction=None, blank=0)
+    cost.sum().backward()
+    np.savez_compressed(
+        os.path.join(OUT, "known_answer_warp_transducer.npz"),
+        acts=_np(acts), labels=np.array([[1, 2]], np.int32), T=np.array([2], np.int32),
+        U=np.array([2], np.int32), cost_published=np.float64(4.495666),
+        grad_row_000_published=np.array([-0.13116688, -0.3999269, 0.17703125, 0.17703125, 0.17703125]),
+        grad_row_012_published=np.array([-0.6925882, 0.16871116, 0.18645467, 0.16871116, 0.16871116]),
+        cost_here=_np(cost), grad_here=_np(acts.grad),
+    )
+    print("known_answer", _np(cost))
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from oracle import warp_rnnt_shim
+
+    warp_rnnt_shim.install()
+    sys.path.insert(0, REF)
+    torch.set_num_threads(4)
+
+    smoke_fixtures()
+    p = _params()
+    rnnt_case("ref_rnnt_small_full", 0, B=3, T=9, U=5, p=p, tlens=[9, 9, 9], ulens=[5, 5, 5])
+    rnnt_case("ref_rnnt_small_ragged", 1, B=4, T=12, U=6, p=p, tlens=[12, 10, 7, 1], ulens=[6, 3, 0, 2])
+    rnnt_case("ref_rnnt_small_auxctc", 2, B=3, T=14, U=4, p=p, tlens=[14, 11, 9], ulens=[4, 4, 2],
+              mtl_ctc_weight=0.3)
+    pm = _params(dec_num_layers=2, dec_hidden_size=40, embedding_size=24, joint_hidden_size=64,
+                 enc_hidden_size=48, vocab_size=131)
+    rnnt_case("ref_rnnt_medium_ragged", 3, B=5, T=37, U=17, p=pm,
+              tlens=[37, 33, 30, 22, 15], ulens=[17, 17, 9, 12, 3])
+    ctc_case("ref_ctc_small_full", 4, B=3, T=10, U=4, V=7, He=12, tlens=[10, 10, 10], ulens=[4, 4, 4])
+    # includes an infeasible utterance (T_b < U_b: zero_infinity) and an empty label sequence
+    ctc_case("ref_ctc_small_ragged", 5, B=5, T=13, U=6, V=9, He=12,
+             tlens=[13, 9, 4, 13, 1], ulens=[6, 4, 6, 0, 1])
+    ctc_case("ref_ctc_medium_ragged", 6, B=6, T=61, U=20, V=203, He=32,
+             tlens=[61, 55, 50, 41, 30, 22], ulens=[20, 18, 20, 7, 11, 10])
+
+
+if __name__ == "__main__":
+    main()
