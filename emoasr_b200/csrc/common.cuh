@@ -1,0 +1,103 @@
+// Shared helpers for the emoasr_b200 kernels (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/emoasr_b200.h"
+
+namespace emo {
+
+// thread-local error text behind emo_last_error_string()
+void set_error(const char* fmt, ...);
+
+#define EMO_REQUIRE(cond, status, ...)      \
+    do {                                    \
+        if (!(cond)) {                      \
+            ::emo::set_error(__VA_ARGS__);  \
+            return (status);                \
+        }                                   \
+    } while (0)
+
+#define EMO_CHECK_LAUNCH(what)                                                          \
+    do {                                                                                \
+        cudaError_t e__ = cudaGetLastError();                                           \
+        if (e__ != cudaSuccess) {                                                       \
+            ::emo::set_error("%s: %s (%s)", what, cudaGetErrorName(e__),                \
+                             cudaGetErrorString(e__));                                  \
+            return EMO_LAUNCH_FAILURE;                                                  \
+        }                                                                               \
+    } while (0)
+
+#define EMO_CUDA(call)                                                                  \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            ::emo::set_error("%s: %s (%s)", #call, cudaGetErrorName(e__),               \
+                             cudaGetErrorString(e__));                                  \
+            return EMO_LAUNCH_FAILURE;                                                  \
+        }                                                                               \
+    } while (0)
+
+constexpr float kNegInf = -INFINITY;
+
+// log(exp(a)+exp(b)), exact-ish fp32, -inf safe
+__device__ __forceinline__ float log_add_exp(float a, float b) {
+    float m = fmaxf(a, b);
+    if (m == kNegInf) return kNegInf;
+    return m + log1pf(expf(-fabsf(a - b)));
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// online (max, sum exp) pair merge
+__device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2) {
+    float mn = fmaxf(m, m2);
+    if (mn == kNegInf) { m = mn; s = 0.f; return; }
+    s = s * expf(m - mn) + s2 * expf(m2 - mn);
+    m = mn;
+}
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+int sm_count();  // SMs of the current device (cached per device)
+
+// ---- entry points implemented across translation units ----
+int rnnt_lattice_launch(const float* lp2, const int* tlen, const int* ulen, int B, int T, int U1,
+                        float* alpha_ws, float* beta_ws, float* cost, float* gamma2,
+                        cudaStream_t st);
+
+int joint_fwd_f32(const float* enc_proj, const float* dec_proj, const float* w_out,
+                  const float* b_out, const int* labels, const int* tlen, const int* ulen, int B,
+                  int T, int U1, int J, int V, int blank, float* lp2, float* lse, void* ws,
+                  size_t ws_bytes, cudaStream_t st);
+int joint_bwd_f32(const float* enc_proj, const float* dec_proj, const float* w_out,
+                  const float* b_out, const int* labels, const int* tlen, const int* ulen,
+                  const float* lse, const float* gamma2, const float* grad_cost, int B, int T,
+                  int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
+                  float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t joint_f32_workspace(int op, int B, int T, int U1, int J, int V);
+
+int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
+                   const float* b_out, const int* labels, const int* tlen, const int* ulen, int B,
+                   int T, int U1, int J, int V, int blank, float* lp2, float* lse, void* ws,
+                   size_t ws_bytes, cudaStream_t st);
+int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
+                   const float* b_out, const int* labels, const int* tlen, const int* ulen,
+                   const float* lse, const float* gamma2, const float* grad_cost, int B, int T,
+                   int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
+                   float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st);
+size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V);
+
+}  // namespace emo

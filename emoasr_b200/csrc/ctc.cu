@@ -1,0 +1,359 @@
+// CTC forward-backward over the blank-extended label sequence, fused with the log_softmax that
+// precedes it in the reference (asr/modeling/decoders/ctc.py:109-113):
+//     nn.CTCLoss(blank, reduction="sum", zero_infinity=True)(logits.transpose(1,0).log_softmax(2), ...)
+// The kernels read raw logits (B,T,V) once in the forward (row log-sum-exp) and once in the
+// backward (softmax - occupancy), never materialising the (T,B,V) log-prob tensor.
+//
+//   ctc_row_lse_kernel   HBM-bound: one warp-group per (b,t) row, float4 loads, online (max,sum).
+//   ctc_lattice_kernel<false>  alpha: one CTA per utterance, thread s owns extended state s; serial
+//                        over t, previous frame in double-buffered shared memory; gathered logits
+//                        are prefetched kPrefetch frames ahead in registers.
+//   ctc_lattice_kernel<true>   beta, same backwards; writes the state posterior occ_t(s) in place
+//                        of beta.
+//   ctc_grad_kernel      HBM-bound: per row, scatter the <= S posteriors into a shared-memory
+//                        vocabulary accumulator, then stream softmax - occ with float4 stores.
+#include "common.cuh"
+
+namespace emo {
+namespace {
+
+constexpr int kPrefetch = 4;
+constexpr int kRowThreads = 256;
+
+__device__ __forceinline__ float block_reduce_lse(float m, float s, float* sm_m, float* sm_s) {
+    // warp then block reduce of (max, sumexp); returns lse to all threads
+    for (int o = 16; o > 0; o >>= 1) {
+        float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+        float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        lse_merge(m, s, m2, s2);
+    }
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) { sm_m[warp] = m; sm_s[warp] = s; }
+    __syncthreads();
+    int nw = blockDim.x >> 5;
+    m = lane < nw ? sm_m[lane] : kNegInf;
+    s = lane < nw ? sm_s[lane] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) {
+        float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+        float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+        lse_merge(m, s, m2, s2);
+    }
+    __syncthreads();
+    return m + logf(s);
+}
+
+// grid-stride over rows r = b*T + t
+__global__ void __launch_bounds__(kRowThreads)
+ctc_row_lse_kernel(const float* __restrict__ logits, const long long* __restrict__ tlen, int B,
+                   int T, int V, float* __restrict__ lse) {
+    __shared__ float sm_m[32], sm_s[32];
+    const int rows = B * T;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        int b = r / T, t = r - b * T;
+        long long T_b = tlen[b];
+        if (t >= T_b) {
+            if (threadIdx.x == 0) lse[r] = 0.f;
+            continue;  // uniform
+        }
+        const float* row = logits + (size_t)r * V;
+        float m = kNegInf, s = 0.f;
+        if ((V & 3) == 0) {
+            const float4* row4 = reinterpret_cast<const float4*>(row);
+            int n4 = V >> 2;
+            for (int i = threadIdx.x; i < n4; i += kRowThreads) {
+                float4 x = __ldg(row4 + i);
+                float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
+                float mn = fmaxf(m, mx);
+                if (mn > kNegInf) {
+                    s = s * expf(m - mn) + expf(x.x - mn) + expf(x.y - mn) + expf(x.z - mn) +
+                        expf(x.w - mn);
+                    m = mn;
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < V; i += kRowThreads) {
+                float x = __ldg(row + i);
+                float mn = fmaxf(m, x);
+                if (mn > kNegInf) {
+                    s = s * expf(m - mn) + expf(x - mn);
+                    m = mn;
+                }
+            }
+        }
+        float l = block_reduce_lse(m, s, sm_m, sm_s);
+        if (threadIdx.x == 0) lse[r] = l;
+    }
+}
+
+struct Ext {
+    int label;   // l'_s
+    bool skip;   // transition s-2 -> s allowed
+};
+
+__device__ __forceinline__ Ext ext_state(const long long* __restrict__ y, int s, int S_b, int blank,
+                                         int V) {
+    Ext e;
+    e.label = blank;
+    e.skip = false;
+    if (s < S_b && (s & 1)) {
+        long long l = y[s >> 1];
+        l = l < 0 ? 0 : (l >= V ? V - 1 : l);
+        e.label = (int)l;
+        if (s >= 2) e.skip = e.label != blank && l != y[(s >> 1) - 1];
+    }
+    return e;
+}
+
+// One CTA per utterance; blockDim.x = S rounded up to a warp.  Thread s owns extended state s.
+// alpha_t / beta_t of the previous frame live in a double-buffered shared array padded by two
+// -inf guards on each side, so the three-way recursion is three shared loads and one barrier.
+template <bool kBackward>
+__global__ void __launch_bounds__(1024, 1)
+ctc_lattice_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
+                   const long long* __restrict__ tlen, const long long* __restrict__ ulen,
+                   const float* __restrict__ lse, int T, int V, int Umax, int blank,
+                   int zero_infinity, float* __restrict__ alpha_ws /* fwd: out; bwd: in */,
+                   float* __restrict__ nll /* fwd: out */, float* __restrict__ occ_ws /* bwd: out */) {
+    __shared__ float buf[2][1024 + 4];
+    __shared__ float sm_ll;
+    const int b = blockIdx.x;
+    const int S = 2 * Umax + 1;
+    const int s = threadIdx.x;
+    long long T_bl = tlen[b], U_bl = ulen[b];
+    const int T_b = (int)(T_bl < 1 ? 1 : (T_bl > T ? T : T_bl));
+    const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
+    const int S_b = 2 * U_b + 1;
+    const long long* y = labels + (size_t)b * Umax;
+    const Ext me = ext_state(y, s, S_b, blank, V);
+    const bool jump = kBackward ? ext_state(y, s + 2, S_b, blank, V).skip : me.skip;
+    const bool valid = s < S_b;
+    const float* lg_b = logits + (size_t)b * T * V;
+    const float* lse_b = lse + (size_t)b * T;
+    float* alpha_b = alpha_ws + (size_t)b * T * S;
+    float* occ_b = kBackward ? occ_ws + (size_t)b * T * S : nullptr;
+
+    for (int i = threadIdx.x; i < 2 * (1024 + 4); i += blockDim.x) (&buf[0][0])[i] = kNegInf;
+
+    auto frame = [&](int i) { return kBackward ? T_b - 1 - i : i; };
+    auto load = [&](int i) -> float {
+        if (valid && i < T_b) {
+            int t = frame(i);
+            return __ldg(lg_b + (size_t)t * V + me.label) - __ldg(lse_b + t);
+        }
+        return kNegInf;
+    };
+
+    float ll = 0.f;
+    if (kBackward) {
+        if (s == 0) {
+            float a1 = alpha_b[(size_t)(T_b - 1) * S + S_b - 1];
+            float a2 = S_b > 1 ? alpha_b[(size_t)(T_b - 1) * S + S_b - 2] : kNegInf;
+            sm_ll = log_add_exp(a1, a2);
+        }
+    }
+    __syncthreads();
+    if (kBackward) ll = sm_ll;
+    const bool feasible = ll > kNegInf && ll == ll && ll < INFINITY;
+
+    auto load_alpha = [&](int i) -> float {
+        if (kBackward && valid && i < T_b) return alpha_b[(size_t)frame(i) * S + s];
+        return kNegInf;
+    };
+    float ring[kPrefetch], ring_a[kPrefetch];
+#pragma unroll
+    for (int k = 0; k < kPrefetch; ++k) { ring[k] = load(k); ring_a[k] = load_alpha(k); }
+
+    for (int i0 = 0; i0 < T_b; i0 += kPrefetch) {
+#pragma unroll
+        for (int k = 0; k < kPrefetch; ++k) {
+            const int i = i0 + k;
+            if (i >= T_b) break;  // uniform
+            const float lp = ring[k];
+            const float a_t = ring_a[k];
+            ring[k] = load(i + kPrefetch);
+            ring_a[k] = load_alpha(i + kPrefetch);
+            const int t = frame(i);
+            const float* prev = buf[(i + 1) & 1] + 2;  // previous frame, index by state
+            float val = kNegInf;
+            if (valid) {
+                if (i == 0) {
+                    // forward: alpha_0(0), alpha_0(1); backward: beta_{T-1}(S-1), beta_{T-1}(S-2)
+                    bool init = kBackward ? (s >= S_b - 2) : (s < 2);
+                    val = init ? lp : kNegInf;
+                } else {
+                    float a = prev[s];
+                    float n1 = kBackward ? prev[s + 1] : prev[s - 1];
+                    float n2 = jump ? (kBackward ? prev[s + 2] : prev[s - 2]) : kNegInf;
+                    float m = fmaxf(fmaxf(a, n1), n2);
+                    if (m > kNegInf) val = m + logf(expf(a - m) + expf(n1 - m) + expf(n2 - m)) + lp;
+                }
+                if (!kBackward) {
+                    alpha_b[(size_t)t * S + s] = val;
+                } else {
+                    // state posterior: alpha and beta both contain the emission at t
+                    float o = 0.f;
+                    if (feasible && a_t > kNegInf && val > kNegInf && lp > kNegInf)
+                        o = expf(a_t + val - lp - ll);
+                    occ_b[(size_t)t * S + s] = o;
+                }
+            }
+            buf[i & 1][2 + s] = val;
+            __syncthreads();
+        }
+    }
+    if (!kBackward && s == 0) {
+        const float* last = buf[(T_b - 1) & 1] + 2;
+        float l = log_add_exp(last[S_b - 1], S_b > 1 ? last[S_b - 2] : kNegInf);
+        float v = -l;
+        if (!(l > kNegInf) || l != l) v = zero_infinity ? 0.f : INFINITY;
+        nll[b] = v;
+    }
+}
+
+// Persistent CTAs, grid-stride over rows (b,t).  acc[V] in dynamic shared memory stays zero
+// between rows: only the touched entries are cleared again.
+__global__ void __launch_bounds__(kRowThreads)
+ctc_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
+                const long long* __restrict__ tlen, const long long* __restrict__ ulen,
+                const float* __restrict__ lse, const float* __restrict__ alpha_ws,
+                const float* __restrict__ occ_ws, const float* __restrict__ grad_nll, int B, int T,
+                int V, int Umax, int blank, float* __restrict__ grad) {
+    extern __shared__ float acc[];  // V floats
+    const int S = 2 * Umax + 1;
+    for (int v = threadIdx.x; v < V; v += kRowThreads) acc[v] = 0.f;
+    __syncthreads();
+    const int rows = B * T;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        int b = r / T, t = r - b * T;
+        long long T_bl = tlen[b], U_bl = ulen[b];
+        const int T_b = (int)(T_bl < 1 ? 1 : (T_bl > T ? T : T_bl));
+        const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
+        const int S_b = 2 * U_b + 1;
+        float* grow = grad + (size_t)r * V;
+        // feasibility of the utterance from the last alphas (same test as the forward kernel)
+        const float* alast = alpha_ws + ((size_t)b * T + (T_b - 1)) * S;
+        float l = log_add_exp(alast[S_b - 1], S_b > 1 ? alast[S_b - 2] : kNegInf);
+        bool feasible = l > kNegInf && l == l && l < INFINITY;
+        if (t >= T_b || !feasible) {  // uniform over the CTA
+            if ((V & 3) == 0) {
+                float4* g4 = reinterpret_cast<float4*>(grow);
+                for (int i = threadIdx.x; i < (V >> 2); i += kRowThreads)
+                    g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+            } else {
+                for (int i = threadIdx.x; i < V; i += kRowThreads) grow[i] = 0.f;
+            }
+            continue;
+        }
+        const long long* y = labels + (size_t)b * Umax;
+        const float* occ = occ_ws + (size_t)r * S;
+        for (int s = threadIdx.x; s < S_b; s += kRowThreads) {
+            int lab = blank;
+            if (s & 1) {
+                long long ll_ = y[s >> 1];
+                lab = (int)(ll_ < 0 ? 0 : (ll_ >= V ? V - 1 : ll_));
+            }
+            atomicAdd(&acc[lab], occ[s]);
+        }
+        __syncthreads();
+        const float g = grad_nll[b];
+        const float row_lse = lse[r];
+        const float* row = logits + (size_t)r * V;
+        if ((V & 3) == 0) {
+            const float4* row4 = reinterpret_cast<const float4*>(row);
+            float4* g4 = reinterpret_cast<float4*>(grow);
+            const float4* a4 = reinterpret_cast<const float4*>(acc);
+            for (int i = threadIdx.x; i < (V >> 2); i += kRowThreads) {
+                float4 x = __ldg(row4 + i);
+                float4 a = a4[i];
+                float4 o;
+                o.x = g * (expf(x.x - row_lse) - a.x);
+                o.y = g * (expf(x.y - row_lse) - a.y);
+                o.z = g * (expf(x.z - row_lse) - a.z);
+                o.w = g * (expf(x.w - row_lse) - a.w);
+                g4[i] = o;
+            }
+        } else {
+            for (int i = threadIdx.x; i < V; i += kRowThreads)
+                grow[i] = g * (expf(__ldg(row + i) - row_lse) - acc[i]);
+        }
+        __syncthreads();
+        for (int s = threadIdx.x; s < S_b; s += kRowThreads) {
+            int lab = blank;
+            if (s & 1) {
+                long long ll_ = y[s >> 1];
+                lab = (int)(ll_ < 0 ? 0 : (ll_ >= V ? V - 1 : ll_));
+            }
+            acc[lab] = 0.f;
+        }
+        __syncthreads();
+    }
+}
+
+int check_ctc_args(const void* logits, const void* labels, const void* tlen, const void* ulen,
+                   int B, int T, int V, int Umax, int blank) {
+    EMO_REQUIRE(logits && labels && tlen && ulen, EMO_BAD_ARG, "ctc: null pointer");
+    EMO_REQUIRE(B > 0 && T > 0 && V > 0 && Umax >= 0, EMO_BAD_ARG, "ctc: bad sizes");
+    EMO_REQUIRE(blank >= 0 && blank < V, EMO_BAD_ARG, "ctc: blank %d outside [0,%d)", blank, V);
+    EMO_REQUIRE(2 * Umax + 1 <= 1024, EMO_UNSUPPORTED_SHAPE,
+                "ctc: 2*Umax+1 = %d exceeds 1024 extended states", 2 * Umax + 1);
+    EMO_REQUIRE((size_t)V * sizeof(float) <= 200 * 1024, EMO_UNSUPPORTED_SHAPE,
+                "ctc: vocabulary %d does not fit the shared-memory accumulator", V);
+    return EMO_OK;
+}
+
+}  // namespace
+}  // namespace emo
+
+using namespace emo;
+
+extern "C" int emo_ctc_fwd(const float* logits, const long long* labels, const long long* tlen,
+                           const long long* ulen, int B, int T, int V, int Umax, int blank,
+                           int zero_infinity, float* lse, float* alpha_ws, float* nll,
+                           void* stream) {
+    int rc = check_ctc_args(logits, labels, tlen, ulen, B, T, V, Umax, blank);
+    if (rc) return rc;
+    EMO_REQUIRE(lse && alpha_ws && nll, EMO_BAD_ARG, "ctc_fwd: null output pointer");
+    cudaStream_t st = (cudaStream_t)stream;
+    int rows = B * T;
+    int grid = min(rows, sm_count() * 8);
+    ctc_row_lse_kernel<<<grid, kRowThreads, 0, st>>>(logits, tlen, B, T, V, lse);
+    EMO_CHECK_LAUNCH("ctc_row_lse_kernel");
+    int S = 2 * Umax + 1;
+    int threads = (S + 31) / 32 * 32;
+    ctc_lattice_kernel<false><<<B, threads, 0, st>>>(logits, labels, tlen, ulen, lse, T, V, Umax,
+                                                     blank, zero_infinity, alpha_ws, nll, nullptr);
+    EMO_CHECK_LAUNCH("ctc_lattice_kernel<fwd>");
+    return EMO_OK;
+}
+
+extern "C" int emo_ctc_bwd(const float* logits, const long long* labels, const long long* tlen,
+                           const long long* ulen, const float* lse, const float* alpha_ws,
+                           const float* nll, const float* grad_nll, int B, int T, int V, int Umax,
+                           int blank, int zero_infinity, float* beta_ws, float* grad_logits,
+                           void* stream) {
+    int rc = check_ctc_args(logits, labels, tlen, ulen, B, T, V, Umax, blank);
+    if (rc) return rc;
+    EMO_REQUIRE(lse && alpha_ws && nll && grad_nll && beta_ws && grad_logits, EMO_BAD_ARG,
+                "ctc_bwd: null pointer");
+    (void)zero_infinity;  // infeasible utterances get zero gradient either way (their nll is 0 or
+                          // inf; torch yields NaN for inf without zero_infinity, we return 0)
+    cudaStream_t st = (cudaStream_t)stream;
+    int S = 2 * Umax + 1;
+    int threads = (S + 31) / 32 * 32;
+    ctc_lattice_kernel<true><<<B, threads, 0, st>>>(logits, labels, tlen, ulen, lse, T, V, Umax,
+                                                    blank, zero_infinity,
+                                                    const_cast<float*>(alpha_ws), nullptr, beta_ws);
+    EMO_CHECK_LAUNCH("ctc_lattice_kernel<bwd>");
+    size_t smem = (size_t)V * sizeof(float);
+    if (smem > 48 * 1024)
+        EMO_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)smem));
+    int rows = B * T;
+    int per_sm = (int)max((size_t)1, min((size_t)8, (size_t)(200 * 1024) / max(smem, (size_t)1)));
+    int grid = min(rows, sm_count() * per_sm);
+    ctc_grad_kernel<<<grid, kRowThreads, smem, st>>>(logits, labels, tlen, ulen, lse, alpha_ws,
+                                                     beta_ws, grad_nll, B, T, V, Umax, blank,
+                                                     grad_logits);
+    EMO_CHECK_LAUNCH("ctc_grad_kernel");
+    return EMO_OK;
+}

@@ -1,0 +1,170 @@
+"""Drop-in RNN-T / CTC decoders: same constructor, sub-module names (hence state_dict keys),
+``forward`` signature and return values as asr/modeling/decoders/rnn_transducer.py:24-156 and
+asr/modeling/decoders/ctc.py:26-174, with the loss path routed through the fused CUDA ops.
+
+Two ways to use them:
+  * stand-alone (``RNNTDecoder(params)``, ``CTCDecoder(params)``) -- training-time surface only
+    (forward / joint / recurrency); this is what bench.py and the GPU tests drive.
+  * ``emoasr_b200.dropin.install()`` mixes the ``Fused*Forward`` classes over the reference's own
+    decoder classes, so decode / beam search / KD keep the reference's code.
+"""
+import torch
+import torch.nn as nn
+
+from . import functional as F
+from .criteria import CTCLoss
+
+
+def _opt(params, name, default=0):
+    return getattr(params, name) if hasattr(params, name) else default
+
+
+class FusedCTCForward:
+    """forward() of ctc.py:87-174 with every ``ctc_loss_fn(logits.transpose(1,0).log_softmax(2), ...)
+    / B`` site (:109-113, :139-141, :152-154) replaced by the fused op on raw logits."""
+
+    def _fused_ctc(self, logits, ys, elens, ylens):
+        nll = F.ctc_loss(logits, ys, elens, ylens, blank=self.blank_id, zero_infinity=True)
+        return nll.sum() / logits.size(0)   # reduction="sum", then "/ B" (ctc.py:111-113)
+
+    def forward(self, eouts, elens, eouts_inter=None, ys=None, ylens=None, ys_in=None, ys_out=None,
+                soft_labels=None, ps=None, plens=None):
+        wants_kd = self.kd_weight > 0 and soft_labels is not None
+        if wants_kd or _opt(self, "inter_kd_weight") > 0:
+            # KD needs dense log-probs + the forced aligner: the reference's own path
+            base = super()
+            if not hasattr(base, "forward") or type(self).__mro__[1] is nn.Module:
+                raise NotImplementedError("knowledge distillation needs the reference decoder "
+                                          "(use emoasr_b200.dropin.install())")
+            return base.forward(eouts, elens, eouts_inter, ys, ylens, ys_in, ys_out, soft_labels, ps, plens)
+        loss = 0
+        loss_dict = {}
+        logits = self.output(eouts)  # (B, T, vocab)
+        if ys is None:
+            return logits
+        loss_ctc = self._fused_ctc(logits, ys, elens, ylens)
+        loss += loss_ctc
+        loss_dict["loss_ctc"] = loss_ctc
+        if self.mtl_phone_ctc_weight > 0:
+            logits_phone = self.phone_output(eouts_inter if self.hie_mtl_phone else eouts)
+            loss_phone_ctc = self._fused_ctc(logits_phone, ps, elens, plens)
+            loss += self.mtl_phone_ctc_weight * loss_phone_ctc
+            key = "loss_phone_ctc(inter)" if self.hie_mtl_phone else "loss_phone_ctc"
+            loss_dict[key] = loss_phone_ctc
+        if self.mtl_inter_ctc_weight > 0:
+            logits_inter = self.output(eouts_inter)
+            loss_inter_ctc = self._fused_ctc(logits_inter, ys, elens, ylens)
+            loss_dict["loss_inter_ctc"] = loss_inter_ctc
+            loss += self.mtl_inter_ctc_weight * loss_inter_ctc
+        loss_dict["loss_total"] = loss
+        return loss, loss_dict, logits
+
+
+class FusedRNNTForward:
+    """forward() of rnn_transducer.py:81-145 with joint -> log_softmax -> warp_rnnt.rnnt_loss
+    (:101-115) replaced by one fused op.  The third return value is None (the (B,T,U+1,V) logits
+    are never formed; the only caller, asr/modeling/asr.py:65, discards it)."""
+
+    fused_precision = "bf16"
+
+    def forward(self, eouts, elens, eouts_inter=None, ys=None, ylens=None, ys_in=None, ys_out=None,
+                soft_labels=None, ps=None, plens=None):
+        if self.kd_weight > 0 and soft_labels is not None:
+            base = super()
+            if type(self).__mro__[1] is nn.Module or not hasattr(base, "forward"):
+                raise NotImplementedError("knowledge distillation needs the dense logits: use the "
+                                          "reference decoder (emoasr_b200.dropin.install())")
+            return base.forward(eouts, elens, eouts_inter, ys, ylens, ys_in, ys_out, soft_labels, ps, plens)
+        loss = 0
+        loss_dict = {}
+        douts, _ = self.recurrency(ys_in, dstate=None)
+        enc_proj = self.w_enc(eouts)   # (B, T, J)
+        dec_proj = self.w_dec(douts)   # (B, L+1, J)
+        assert dec_proj.size(1) == ys.size(1) + 1
+        loss_rnnt = F.rnnt_joint_loss(enc_proj, dec_proj, self.output.weight, self.output.bias,
+                                      ys, elens, ylens, blank=self.blank_id, reduction="mean",
+                                      precision=self.fused_precision)
+        loss += loss_rnnt
+        loss_dict["loss_rnnt"] = loss_rnnt
+        if self.mtl_ctc_weight > 0:
+            loss_ctc, _, _ = self.ctc(eouts=eouts, elens=elens, ys=ys, ylens=ylens, soft_labels=None)
+            loss += self.mtl_ctc_weight * loss_ctc
+            loss_dict["loss_ctc"] = loss_ctc
+        loss_dict["loss_total"] = loss
+        return loss, loss_dict, None
+
+
+class CTCDecoder(FusedCTCForward, nn.Module):
+    """Stand-alone equivalent of asr/modeling/decoders/ctc.py:26-85 (constructor) for training."""
+
+    def __init__(self, params):
+        nn.Module.__init__(self)
+        self.blank_id = params.blank_id
+        self.eos_id = params.eos_id
+        self.vocab_size = params.vocab_size
+        self.output = nn.Linear(params.enc_hidden_size, self.vocab_size)
+        self.ctc_loss_fn = CTCLoss(blank=self.blank_id, reduction="sum", zero_infinity=True)
+        self.mtl_phone_ctc_weight = _opt(params, "mtl_phone_ctc_weight")
+        self.mtl_inter_ctc_weight = _opt(params, "mtl_inter_ctc_weight")
+        self.kd_weight = params.kd_weight
+        if self.mtl_phone_ctc_weight > 0:
+            self.hie_mtl_phone = params.hie_mtl_phone
+            self.phone_output = nn.Linear(params.enc_hidden_size, params.phone_vocab_size)
+
+    def decode(self, *args, **kwargs):
+        raise NotImplementedError("decoding is outside the loss hot path: use the reference "
+                                  "decoder via emoasr_b200.dropin.install()")
+
+
+class RNNTDecoder(FusedRNNTForward, nn.Module):
+    """Stand-alone equivalent of asr/modeling/decoders/rnn_transducer.py:24-79 (constructor),
+    :147-156 (joint) and :158-192 (recurrency) for training."""
+
+    def __init__(self, params, phase="train"):
+        nn.Module.__init__(self)
+        self.dec_num_layers = params.dec_num_layers
+        self.dec_hidden_size = params.dec_hidden_size
+        self.eos_id = params.eos_id
+        self.blank_id = params.blank_id
+        self.max_seq_len = 256
+        self.mtl_ctc_weight = params.mtl_ctc_weight
+        self.kd_weight = params.kd_weight
+        self.embed = nn.Embedding(params.vocab_size, params.embedding_size)
+        self.dropout_emb = nn.Dropout(p=params.dropout_emb_rate)
+        self.dropout = nn.Dropout(p=params.dropout_dec_rate)
+        self.rnns = nn.ModuleList()
+        input_size = params.embedding_size
+        for _ in range(self.dec_num_layers):
+            self.rnns += [nn.LSTM(input_size=input_size, hidden_size=params.dec_hidden_size,
+                                  num_layers=1, batch_first=True)]
+            input_size = params.dec_hidden_size
+        self.w_enc = nn.Linear(params.enc_hidden_size, params.joint_hidden_size)
+        self.w_dec = nn.Linear(params.dec_hidden_size, params.joint_hidden_size)
+        self.output = nn.Linear(params.joint_hidden_size, params.vocab_size)
+        if self.mtl_ctc_weight > 0:
+            self.ctc = CTCDecoder(params)
+
+    def joint(self, eouts, douts):
+        """Dense joint, kept for decoding-style callers: (B,T,He),(B,L,Hd) -> (B,T,L,V)."""
+        out = torch.tanh(self.w_enc(eouts.unsqueeze(2)) + self.w_dec(douts.unsqueeze(1)))
+        return self.output(out)
+
+    def recurrency(self, ys_in, dstate):
+        ys_emb = self.dropout_emb(self.embed(ys_in))
+        bs = ys_emb.size(0)
+        if dstate is None:
+            zeros = torch.zeros(self.dec_num_layers, bs, self.dec_hidden_size, device=ys_in.device)
+            dstate = {"hs": zeros, "cs": zeros.clone()}
+        new_hs, new_cs = [], []
+        for layer_id in range(self.dec_num_layers):
+            self.rnns[layer_id].flatten_parameters()
+            ys_emb, (h, c) = self.rnns[layer_id](
+                ys_emb, hx=(dstate["hs"][layer_id:layer_id + 1], dstate["cs"][layer_id:layer_id + 1]))
+            new_hs.append(h)
+            new_cs.append(c)
+            ys_emb = self.dropout(ys_emb)
+        return ys_emb, {"hs": torch.cat(new_hs, dim=0), "cs": torch.cat(new_cs, dim=0)}
+
+    def decode(self, *args, **kwargs):
+        raise NotImplementedError("decoding is outside the loss hot path: use the reference "
+                                  "decoder via emoasr_b200.dropin.install()")

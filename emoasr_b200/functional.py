@@ -1,0 +1,272 @@
+"""Autograd functions over the C ABI (include/emoasr_b200.h).  CUDA tensors only; no fallback.
+
+rnnt_loss        warp_rnnt.rnnt_loss signature (asr/modeling/decoders/rnn_transducer.py:106-115)
+rnnt_joint_loss  joint + log_softmax + transducer loss fused (rnn_transducer.py:101-115, 147-156)
+ctc_loss         log_softmax + nn.CTCLoss(reduction="none") fused (asr/modeling/decoders/ctc.py:109-113)
+"""
+import ctypes
+
+import torch
+
+from . import _lib
+
+_PRECISIONS = {"fp32": _lib.PREC_FP32, "bf16": _lib.PREC_BF16, 0: 0, 1: 1}
+
+
+def _p(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(*tensors):
+    for t in tensors:
+        if not t.is_cuda:
+            raise RuntimeError(
+                "emoasr_b200 ops run on CUDA tensors only (there is no CPU fallback); got a "
+                f"{t.device} tensor")
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def _i32c(t, device):
+    return t.detach().to(device=device, dtype=torch.int32).contiguous()
+
+
+def _i64c(t, device):
+    return t.detach().to(device=device, dtype=torch.int64).contiguous()
+
+
+# ----------------------------------------------------------------------------------------------
+class _RNNTLattice(torch.autograd.Function):
+    """cost(B) from gathered pairs lp2 (B,T,U1,2); d cost/d lp2 = -gamma2."""
+
+    @staticmethod
+    def forward(ctx, lp2, tlen, ulen):
+        _require_cuda(lp2)
+        lib = _lib.load()
+        lp2c = _f32c(lp2)
+        B, T, U1, two = lp2c.shape
+        assert two == 2
+        dev = lp2c.device
+        tlen, ulen = _i32c(tlen, dev), _i32c(ulen, dev)
+        with torch.cuda.device(dev):
+            alpha = torch.empty(B, T, U1, device=dev)
+            beta = torch.empty(B, T, U1, device=dev)
+            cost = torch.empty(B, device=dev)
+            gamma2 = torch.empty(B, T, U1, 2, device=dev)
+            _lib.check(lib.emo_rnnt_lattice_fwd_bwd(_p(lp2c), _p(tlen), _p(ulen), B, T, U1, _p(alpha),
+                                                    _p(beta), _p(cost), _p(gamma2), _stream()),
+                       "emo_rnnt_lattice_fwd_bwd")
+        ctx.save_for_backward(gamma2)
+        return cost
+
+    @staticmethod
+    def backward(ctx, grad_cost):
+        (gamma2,) = ctx.saved_tensors
+        return -gamma2 * grad_cost.view(-1, 1, 1, 1), None, None
+
+
+class _RNNTDense(torch.autograd.Function):
+    """warp_rnnt contract: dense log-probs in, sparse gradient out."""
+
+    @staticmethod
+    def forward(ctx, log_probs, labels, tlen, ulen, blank):
+        _require_cuda(log_probs)
+        lib = _lib.load()
+        lp = _f32c(log_probs)
+        B, T, U1, V = lp.shape
+        dev = lp.device
+        labels, tlen, ulen = _i32c(labels, dev), _i32c(tlen, dev), _i32c(ulen, dev)
+        if labels.dim() != 2 or labels.size(0) != B or labels.size(1) != U1 - 1:
+            raise RuntimeError(f"labels must be (B, U) = ({B}, {U1 - 1}); got {tuple(labels.shape)}")
+        with torch.cuda.device(dev):
+            lp2 = torch.empty(B, T, U1, 2, device=dev)
+            alpha = torch.empty(B, T, U1, device=dev)
+            beta = torch.empty(B, T, U1, device=dev)
+            cost = torch.empty(B, device=dev)
+            gamma2 = torch.empty(B, T, U1, 2, device=dev)
+            _lib.check(lib.emo_rnnt_dense_fwd(_p(lp), _p(labels), _p(tlen), _p(ulen), B, T, U1, V, blank,
+                                              _p(lp2), _p(alpha), _p(beta), _p(cost), _p(gamma2), _stream()),
+                       "emo_rnnt_dense_fwd")
+        ctx.save_for_backward(gamma2, labels, tlen, ulen)
+        ctx.dims = (B, T, U1, V, blank)
+        return cost
+
+    @staticmethod
+    def backward(ctx, grad_cost):
+        gamma2, labels, tlen, ulen = ctx.saved_tensors
+        B, T, U1, V, blank = ctx.dims
+        lib = _lib.load()
+        dev = gamma2.device
+        with torch.cuda.device(dev):
+            g = _f32c(grad_cost)
+            grad = torch.empty(B, T, U1, V, device=dev)
+            _lib.check(lib.emo_rnnt_dense_bwd(_p(gamma2), _p(labels), _p(tlen), _p(ulen), _p(g), B, T, U1, V,
+                                              blank, _p(grad), _stream()), "emo_rnnt_dense_bwd")
+        return grad, None, None, None, None
+
+
+def _reduce(costs, reduction):
+    if reduction is None or reduction == "none":
+        return costs
+    if reduction == "mean":
+        return costs.mean()
+    if reduction == "sum":
+        return costs.sum()
+    raise ValueError(f"unknown reduction {reduction!r}")
+
+
+def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=False,
+              reduction=None, blank=0, gather=False):
+    """Drop-in for ``warp_rnnt.rnnt_loss`` as called at rnn_transducer.py:106-115.
+
+    log_probs (B,T,U+1,V) fp32 log-softmax output (or (B,T,U+1,2) = {blank,label} pairs when
+    ``gather=True``), labels (B,U) int, lengths (B,) int.  Gradient w.r.t. log_probs has two
+    non-zeros per valid lattice cell, exactly like warp_rnnt.
+    """
+    if gather:
+        costs = _RNNTLattice.apply(log_probs, frames_lengths, labels_lengths)
+    else:
+        costs = _RNNTDense.apply(log_probs, labels, frames_lengths, labels_lengths, int(blank))
+    if average_frames:
+        costs = costs / frames_lengths.to(costs)
+    return _reduce(costs, reduction)
+
+
+# ----------------------------------------------------------------------------------------------
+class _RNNTJoint(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, blank, precision):
+        _require_cuda(enc_proj, dec_proj, w_out, b_out)
+        lib = _lib.load()
+        enc, dec, w, bo = _f32c(enc_proj), _f32c(dec_proj), _f32c(w_out), _f32c(b_out)
+        B, T, J = enc.shape
+        U1 = dec.size(1)
+        V = w.size(0)
+        if dec.size(0) != B or dec.size(2) != J or w.size(1) != J or bo.numel() != V:
+            raise RuntimeError("rnnt_joint_loss: inconsistent shapes "
+                               f"enc {tuple(enc.shape)} dec {tuple(dec.shape)} w_out {tuple(w.shape)}")
+        dev = enc.device
+        labels, tlen, ulen = _i32c(labels, dev), _i32c(tlen, dev), _i32c(ulen, dev)
+        if U1 > 1:
+            if labels.dim() != 2 or labels.size(0) != B or labels.size(1) < U1 - 1:
+                raise RuntimeError(f"labels must be (B, >= U) = ({B}, {U1 - 1}); got {tuple(labels.shape)}")
+            if labels.size(1) != U1 - 1:
+                labels = labels[:, : U1 - 1].contiguous()
+        else:
+            labels = torch.zeros(B, 1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            nbytes = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_FWD, precision, B, T, U1, J, V)
+            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+            lp2 = torch.empty(B, T, U1, 2, device=dev)
+            lse = torch.empty(B, T, U1, device=dev)
+            _lib.check(lib.emo_rnnt_joint_fwd(_p(enc), _p(dec), _p(w), _p(bo), _p(labels), _p(tlen), _p(ulen),
+                                              B, T, U1, J, V, blank, precision, _p(lp2), _p(lse),
+                                              _p(ws), ws.numel(), _stream()), "emo_rnnt_joint_fwd")
+            alpha = torch.empty(B, T, U1, device=dev)
+            beta = torch.empty(B, T, U1, device=dev)
+            cost = torch.empty(B, device=dev)
+            gamma2 = torch.empty(B, T, U1, 2, device=dev)
+            _lib.check(lib.emo_rnnt_lattice_fwd_bwd(_p(lp2), _p(tlen), _p(ulen), B, T, U1, _p(alpha),
+                                                    _p(beta), _p(cost), _p(gamma2), _stream()),
+                       "emo_rnnt_lattice_fwd_bwd")
+        ctx.save_for_backward(enc, dec, w, bo, labels, tlen, ulen, lse, gamma2)
+        ctx.cfg = (blank, precision)
+        return cost
+
+    @staticmethod
+    def backward(ctx, grad_cost):
+        enc, dec, w, bo, labels, tlen, ulen, lse, gamma2 = ctx.saved_tensors
+        blank, precision = ctx.cfg
+        lib = _lib.load()
+        B, T, J = enc.shape
+        U1, V = dec.size(1), w.size(0)
+        dev = enc.device
+        with torch.cuda.device(dev):
+            g = _f32c(grad_cost)
+            nbytes = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_BWD, precision, B, T, U1, J, V)
+            ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
+            d_enc = torch.empty_like(enc)
+            d_dec = torch.empty_like(dec)
+            d_w = torch.empty_like(w)
+            d_b = torch.empty_like(bo)
+            _lib.check(lib.emo_rnnt_joint_bwd(_p(enc), _p(dec), _p(w), _p(bo), _p(labels), _p(tlen), _p(ulen),
+                                              _p(lse), _p(gamma2), _p(g), B, T, U1, J, V, blank, precision,
+                                              _p(d_enc), _p(d_dec), _p(d_w), _p(d_b), _p(ws), ws.numel(),
+                                              _stream()), "emo_rnnt_joint_bwd")
+        return d_enc, d_dec, d_w, d_b, None, None, None, None, None
+
+
+def rnnt_joint_loss(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths, labels_lengths,
+                    blank=0, reduction=None, precision="bf16"):
+    """Per-utterance transducer cost straight from the two projected streams.
+
+    enc_proj (B,T,J) = w_enc(eouts)+b, dec_proj (B,U+1,J) = w_dec(douts)+b, w_out (V,J), b_out (V).
+    Equivalent to ``rnnt_loss(log_softmax(output(tanh(enc_proj[:,:,None]+dec_proj[:,None]))), ...)``
+    (rnn_transducer.py:101-115,147-156) without ever forming the (B,T,U+1,V) tensors.
+    """
+    costs = _RNNTJoint.apply(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths,
+                             labels_lengths, int(blank), _PRECISIONS[precision])
+    return _reduce(costs, reduction)
+
+
+# ----------------------------------------------------------------------------------------------
+class _CTC(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, labels, tlen, ulen, blank, zero_infinity):
+        _require_cuda(logits)
+        lib = _lib.load()
+        z = _f32c(logits)
+        B, T, V = z.shape
+        dev = z.device
+        labels, tlen, ulen = _i64c(labels, dev), _i64c(tlen, dev), _i64c(ulen, dev)
+        if labels.dim() != 2 or labels.size(0) != B:
+            raise RuntimeError(f"labels must be (B, Umax); got {tuple(labels.shape)}")
+        Umax = labels.size(1)
+        if Umax == 0:
+            labels = torch.zeros(B, 1, dtype=torch.int64, device=dev)
+            Umax = 1
+        S = 2 * Umax + 1
+        with torch.cuda.device(dev):
+            lse = torch.empty(B, T, device=dev)
+            alpha = torch.empty(B, T, S, device=dev)
+            nll = torch.empty(B, device=dev)
+            _lib.check(lib.emo_ctc_fwd(_p(z), _p(labels), _p(tlen), _p(ulen), B, T, V, Umax, blank,
+                                       int(zero_infinity), _p(lse), _p(alpha), _p(nll), _stream()),
+                       "emo_ctc_fwd")
+        ctx.save_for_backward(z, labels, tlen, ulen, lse, alpha, nll)
+        ctx.cfg = (blank, int(zero_infinity))
+        return nll
+
+    @staticmethod
+    def backward(ctx, grad_nll):
+        z, labels, tlen, ulen, lse, alpha, nll = ctx.saved_tensors
+        blank, zero_infinity = ctx.cfg
+        lib = _lib.load()
+        B, T, V = z.shape
+        Umax = labels.size(1)
+        dev = z.device
+        with torch.cuda.device(dev):
+            g = _f32c(grad_nll)
+            occ = torch.empty(B, T, 2 * Umax + 1, device=dev)
+            grad = torch.empty_like(z)
+            _lib.check(lib.emo_ctc_bwd(_p(z), _p(labels), _p(tlen), _p(ulen), _p(lse), _p(alpha), _p(nll),
+                                       _p(g), B, T, V, Umax, blank, zero_infinity, _p(occ), _p(grad),
+                                       _stream()), "emo_ctc_bwd")
+        return grad, None, None, None, None, None
+
+
+def ctc_loss(logits, labels, input_lengths, label_lengths, blank=0, reduction=None, zero_infinity=True):
+    """Per-utterance CTC negative log-likelihood from RAW logits (B,T,V).
+
+    Equivalent to ``nn.CTCLoss(blank, reduction="none", zero_infinity)(logits.transpose(1,0)
+    .log_softmax(2), labels, input_lengths, label_lengths)`` (ctc.py:109-113); the log_softmax is
+    fused.  Feeding log-probs instead of logits gives the same value and torch's gradient.
+    """
+    nll = _CTC.apply(logits, labels, input_lengths, label_lengths, int(blank), bool(zero_infinity))
+    return _reduce(nll, reduction)

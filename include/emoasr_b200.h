@@ -1,0 +1,146 @@
+/* emoasr_b200 -- C ABI of the B200 (sm_100a) sequence-loss hot path of emoASR.
+ *
+ * Drop-in boundary: the reference is pure Python; the calls that leave it on this path are
+ *   warp_rnnt.rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, ...)
+ *                          asr/modeling/decoders/rnn_transducer.py:106-115   (third-party CUDA ext)
+ *   RNNTDecoder.joint + torch.log_softmax
+ *                          asr/modeling/decoders/rnn_transducer.py:101-102, 147-156
+ *   nn.CTCLoss(blank, reduction="sum", zero_infinity=True)(log_probs(T,B,V), ys, elens, ylens)
+ *                          asr/modeling/decoders/ctc.py:36-38, 109-113, 139-141, 152-154 (ATen)
+ * This library is what a maintainer binds instead (ctypes stub in INTEGRATION.md and
+ * emoasr_b200/_lib.py).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless marked host.
+ *   - `stream` is a cudaStream_t passed as void*; all work is enqueued on it, nothing
+ *     synchronises, allocates or reads lengths back to the host.
+ *   - the device is the current CUDA device of the calling thread; no global mutable state
+ *     besides a thread-local error string, so DataParallel-style threads may call concurrently.
+ *   - every function returns 0 on success, an emo_status otherwise; emo_last_error_string()
+ *     explains the last failure on the calling thread.
+ *   - numerically impossible utterances give cost = +inf (RNN-T, as warp_rnnt) or are zeroed
+ *     (CTC with zero_infinity, as torch); kernels never trap.
+ *   - lengths: 1 <= tlen[b] <= T, 0 <= ulen[b] <= U1-1.  Cells with t >= tlen[b] or u > ulen[b]
+ *     are never read and receive zero gradient.
+ */
+#ifndef EMOASR_B200_H
+#define EMOASR_B200_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define EMO_ABI_VERSION 1
+
+enum emo_status {
+    EMO_OK = 0,
+    EMO_BAD_ARG = 1,           /* null pointer / non-positive size / misaligned pointer */
+    EMO_UNSUPPORTED_SHAPE = 2, /* shape outside what the requested precision path supports */
+    EMO_WORKSPACE_TOO_SMALL = 3,
+    EMO_LAUNCH_FAILURE = 4,    /* cudaGetLastError() != cudaSuccess after a launch */
+    EMO_NO_DEVICE = 5
+};
+
+/* arithmetic of the joint's vocabulary projection */
+enum emo_precision {
+    EMO_PREC_FP32 = 0, /* fp32 FFMA, slab-streamed; parity mode (1e-5 / 1e-4 vs the reference) */
+    EMO_PREC_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM; LSE, lattice,
+                          occupancies and all reductions stay fp32 */
+};
+
+enum emo_op {
+    EMO_OP_RNNT_JOINT_FWD = 0,
+    EMO_OP_RNNT_JOINT_BWD = 1,
+    EMO_OP_CTC = 2
+};
+
+int emo_abi_version(void);
+const char* emo_last_error_string(void); /* host pointer, thread-local storage */
+
+/* Bytes of scratch the op needs for these sizes and precision (host call, no CUDA work). */
+size_t emo_workspace_bytes(int op, int precision, int B, int T, int U1, int J, int V);
+
+/* ---- RNN-T lattice on gathered pairs ---------------------------------------------------------
+ * Replaces the alpha/beta/grad kernels of warp_rnnt.rnnt_loss (rnn_transducer.py:106-115).
+ * lp2      (B,T,U1,2)  {log p(blank | t,u), log p(y_{u+1} | t,u)}
+ * tlen,ulen (B)        int32 (the reference casts with .int(), rnn_transducer.py:108-110)
+ * alpha_ws, beta_ws (B,T,U1) scratch, overwritten
+ * cost     (B)         -log P(y_b | x_b)                       (no reduction, no normalisation)
+ * gamma2   (B,T,U1,2)  {-d cost/d lp_blank, -d cost/d lp_label} = transition posteriors; zero
+ *                      outside the valid region.
+ */
+int emo_rnnt_lattice_fwd_bwd(const float* lp2, const int* tlen, const int* ulen,
+                             int B, int T, int U1,
+                             float* alpha_ws, float* beta_ws,
+                             float* cost, float* gamma2, void* stream);
+
+/* ---- warp_rnnt module seam: dense log-probs in, sparse gradient out --------------------------
+ * Same contract as warp_rnnt.rnnt_loss(log_probs, labels, frames_lengths, labels_lengths,
+ * average_frames=False, reduction=None, blank, gather=False).
+ * log_probs (B,T,U1,V) fp32 contiguous; labels (B,U1-1) int32.
+ * lp2_ws/gamma2_ws (B,T,U1,2), alpha_ws/beta_ws (B,T,U1) scratch.
+ * emo_rnnt_dense_fwd gathers, runs the lattice and leaves gamma2_ws for the backward call.
+ * emo_rnnt_dense_bwd writes grad_log_probs (B,T,U1,V) = -grad_cost[b] * gamma at the blank and
+ * label entries and 0 elsewhere (the whole tensor is written). */
+int emo_rnnt_dense_fwd(const float* log_probs, const int* labels, const int* tlen, const int* ulen,
+                       int B, int T, int U1, int V, int blank,
+                       float* lp2_ws, float* alpha_ws, float* beta_ws,
+                       float* cost, float* gamma2_ws, void* stream);
+int emo_rnnt_dense_bwd(const float* gamma2_ws, const int* labels, const int* tlen, const int* ulen,
+                       const float* grad_cost, int B, int T, int U1, int V, int blank,
+                       float* grad_log_probs, void* stream);
+
+/* ---- fused joint (rnn_transducer.py:147-156 + :102) -----------------------------------------
+ * enc_proj (B,T,J)  = w_enc(eouts) + b_enc      dec_proj (B,U1,J) = w_dec(douts) + b_dec
+ * w_out (V,J) fp32 row-major (torch Linear weight), b_out (V)
+ * For every valid cell: h = tanh(enc_proj[b,t] + dec_proj[b,u]); z = w_out h + b_out;
+ *   lse[b,t,u] = logsumexp_v z;  lp2[b,t,u] = {z[blank]-lse, z[labels[b,u]]-lse (u < ulen[b])}.
+ * The (B,T,U1,V) logits are never written to memory in EMO_PREC_BF16; EMO_PREC_FP32 streams
+ * them through a bounded slab inside `ws`.
+ */
+int emo_rnnt_joint_fwd(const float* enc_proj, const float* dec_proj,
+                       const float* w_out, const float* b_out,
+                       const int* labels, const int* tlen, const int* ulen,
+                       int B, int T, int U1, int J, int V, int blank, int precision,
+                       float* lp2, float* lse,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* Backward of cost (B) w.r.t. enc_proj, dec_proj, w_out, b_out given grad_cost (B):
+ *   dz[b,t,u,v] = grad_cost[b] * ((g_blank+g_label) * exp(z[v]-lse) - g_blank 1[v=blank]
+ *                                  - g_label 1[v=labels[b,u]])
+ * recomputed tile by tile and contracted on the fly:
+ *   d_w_out (V,J) = sum dz^T h ; d_b_out (V) = sum dz ; dh = dz w_out ;
+ *   dpre = dh (1-h^2) ; d_enc_proj[b,t] = sum_u dpre ; d_dec_proj[b,u] = sum_t dpre.
+ * All four outputs are overwritten (not accumulated into). */
+int emo_rnnt_joint_bwd(const float* enc_proj, const float* dec_proj,
+                       const float* w_out, const float* b_out,
+                       const int* labels, const int* tlen, const int* ulen,
+                       const float* lse, const float* gamma2, const float* grad_cost,
+                       int B, int T, int U1, int J, int V, int blank, int precision,
+                       float* d_enc_proj, float* d_dec_proj, float* d_w_out, float* d_b_out,
+                       void* ws, size_t ws_bytes, void* stream);
+
+/* ---- CTC (ctc.py:109-113; torch.nn.CTCLoss semantics) ----------------------------------------
+ * logits (B,T,V) fp32 contiguous -- the log_softmax of ctc.py:110 is fused: the kernels read raw
+ * logits.  labels (B,Umax) int64 padded arbitrarily; tlen, ulen (B) int64 (as the reference
+ * passes them).  S = 2*Umax+1.
+ * emo_ctc_fwd:  lse (B,T), alpha_ws (B,T,S) scratch kept for backward,
+ *               nll (B): -log P(y|x), or 0 when infeasible and zero_infinity != 0 (else +inf).
+ * emo_ctc_bwd:  grad_logits (B,T,V) = grad_nll[b] * (softmax(z)[t,v] - occ[t,v]) for t < tlen[b],
+ *               0 for padded frames and for infeasible utterances (whole tensor written).
+ *               beta_ws (B,T,S) scratch.
+ */
+int emo_ctc_fwd(const float* logits, const long long* labels, const long long* tlen,
+                const long long* ulen, int B, int T, int V, int Umax, int blank, int zero_infinity,
+                float* lse, float* alpha_ws, float* nll, void* stream);
+int emo_ctc_bwd(const float* logits, const long long* labels, const long long* tlen,
+                const long long* ulen, const float* lse, const float* alpha_ws, const float* nll,
+                const float* grad_nll, int B, int T, int V, int Umax, int blank, int zero_infinity,
+                float* beta_ws, float* grad_logits, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* EMOASR_B200_H */

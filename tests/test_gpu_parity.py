@@ -1,0 +1,241 @@
+"""GPU parity tests: CUDA path (through the C ABI) vs the oracle and the reference's golden vectors.
+
+Tolerances (north star): fp32 mode loss <= 1e-5 relative, gradients <= 1e-4 relative (norm-wise).
+"""
+from collections import namedtuple
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden, rel_err
+
+pytestmark = pytest.mark.gpu
+
+LOSS_RTOL = 1e-5
+GRAD_RTOL = 1e-4
+
+
+def dev():
+    return torch.device("cuda:0")
+
+
+def T_(a, dtype=None):
+    t = torch.as_tensor(np.asarray(a)).to(dev())
+    return t.to(dtype) if dtype is not None else t
+
+
+# ---------------------------------------------------------------- RNN-T lattice / warp_rnnt seam
+def test_known_answer_vector():
+    import emoasr_b200 as E
+    g = load_golden("known_answer_warp_transducer")
+    acts = T_(g["acts"]).requires_grad_()
+    cost = E.rnnt_loss(acts.log_softmax(-1), T_(g["labels"]), T_(g["T"]), T_(g["U"]), blank=0)
+    cost.sum().backward()
+    assert abs(float(cost[0]) - float(g["cost_published"])) < 1e-5 * 4.5
+    grad = acts.grad.cpu().numpy()
+    assert np.abs(grad[0, 0, 0] - g["grad_row_000_published"]).max() < 1e-6
+    assert np.abs(grad[0, 1, 2] - g["grad_row_012_published"]).max() < 1e-6
+
+
+def test_aligner_smoke_fixture():
+    import emoasr_b200 as E
+    g = load_golden("ref_rnnt_aligner_smoke")
+    lp = T_(g["log_probs"]).requires_grad_()
+    costs = E.rnnt_loss(lp, T_(g["labels"]), T_(g["T"]), T_(g["U"]), blank=0)
+    costs.sum().backward()
+    assert np.abs(costs.detach().cpu().numpy() - g["costs"]).max() <= LOSS_RTOL * np.abs(g["costs"]).max()
+    assert rel_err(lp.grad.cpu().numpy(), g["grad"]) < GRAD_RTOL
+    # sparse contract: exactly the blank/label entries are non-zero, padded cells are zero
+    assert np.all(lp.grad.cpu().numpy()[0, 8:] == 0)
+
+
+@pytest.mark.parametrize("B,T,U,V,seed", [(4, 23, 7, 11, 0), (3, 70, 33, 40, 1), (2, 5, 40, 9, 2), (5, 64, 1, 6, 3)])
+def test_dense_seam_vs_dp_random_ragged(B, T, U, V, seed):
+    import emoasr_b200 as E
+    from oracle import rnnt_dp
+    rng = np.random.default_rng(seed)
+    lp = rnnt_dp.log_softmax(rng.standard_normal((B, T, U + 1, V)) * 2).astype(np.float32)
+    ys = rng.integers(1, V, (B, U))
+    tl = rng.integers(1, T + 1, B); tl[0] = T
+    ul = rng.integers(0, U + 1, B); ul[0] = U
+    costs_ref, grad_ref = rnnt_dp.rnnt_loss_dense(lp, ys, tl, ul, blank=0)
+    x = T_(lp).requires_grad_()
+    w = torch.arange(1, B + 1, device=dev(), dtype=torch.float32)
+    costs = E.rnnt_loss(x, T_(ys), T_(tl), T_(ul), blank=0)
+    (costs * w).sum().backward()
+    assert np.abs(costs.detach().cpu().numpy() - costs_ref).max() <= LOSS_RTOL * np.abs(costs_ref).max()
+    assert rel_err(x.grad.cpu().numpy(), grad_ref * np.arange(1, B + 1)[:, None, None, None]) < GRAD_RTOL
+    # gather=True variant (pairs in, pairs out)
+    lp2 = np.zeros((B, T, U + 1, 2), np.float32)
+    lp2[..., 0] = lp[..., 0]
+    for b in range(B):
+        lp2[b, :, :U, 1] = lp[b][:, np.arange(U), ys[b]]
+    x2 = T_(lp2).requires_grad_()
+    c2 = E.rnnt_loss(x2, T_(ys), T_(tl), T_(ul), blank=0, gather=True, reduction="mean")
+    c2.backward()
+    assert abs(float(c2) - costs_ref.mean()) <= LOSS_RTOL * abs(costs_ref.mean())
+
+
+def test_lattice_occupancy_properties_full_size():
+    """Size-independent properties at the BASELINE cfg-3 lattice size: expected number of label
+    emissions = U_b, expected number of blank emissions = T_b, cost from alpha == cost from beta."""
+    import emoasr_b200 as E
+    B, T, U = 32, 250, 100
+    gen = torch.Generator(device="cpu").manual_seed(0)
+    lp2 = (torch.rand(B, T, U + 1, 2, generator=gen) * 3 + 0.2).neg().to(dev()).requires_grad_()
+    r = torch.linspace(1.0, 0.6, B)
+    tl = (T * r).long().clamp(min=1)
+    ul = (U * r).long()
+    costs = E.rnnt_loss(lp2, None, tl, ul, gather=True)
+    costs.sum().backward()
+    g = -lp2.grad
+    assert torch.isfinite(costs).all()
+    assert torch.allclose(g[..., 1].sum((1, 2)).cpu(), ul.float(), rtol=1e-4, atol=1e-3)
+    assert torch.allclose(g[..., 0].sum((1, 2)).cpu(), tl.float(), rtol=1e-4, atol=1e-3)
+    for b in (0, B - 1):
+        assert float(g[b, int(tl[b]):].abs().sum()) == 0.0
+        assert float(g[b, :, int(ul[b]) + 1:].abs().sum()) == 0.0
+
+
+# ---------------------------------------------------------------- fused joint, fp32 parity mode
+def _params_from_golden(g):
+    keys = ["dec_num_layers", "dec_hidden_size", "embedding_size", "joint_hidden_size", "enc_hidden_size",
+            "vocab_size", "eos_id", "blank_id", "mtl_ctc_weight", "kd_weight", "dropout_emb_rate",
+            "dropout_dec_rate"]
+    d = {k: g["hp." + k].item() for k in keys}
+    return namedtuple("Params", d.keys())(**d)
+
+
+RNNT_CASES = ["ref_rnnt_small_full", "ref_rnnt_small_ragged", "ref_rnnt_small_auxctc", "ref_rnnt_medium_ragged"]
+
+
+@pytest.mark.parametrize("name", RNNT_CASES)
+def test_rnnt_decoder_fp32_vs_reference_golden(name):
+    """Drop-in RNNTDecoder (fused, fp32 mode) loaded with the reference's state_dict must give the
+    reference's loss and gradients on the reference's inputs."""
+    from emoasr_b200.decoders import RNNTDecoder
+    g = load_golden(name)
+    p = _params_from_golden(g)
+    dec = RNNTDecoder(p, phase="test")
+    dec.fused_precision = "fp32"
+    dec.load_state_dict({k[len("param."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")})
+    dec = dec.to(dev()).train()
+    eouts = T_(g["eouts"]).requires_grad_()
+    loss, loss_dict, logits = dec(eouts, T_(g["elens"]), None, T_(g["ys"]), T_(g["ylens"]), T_(g["ys_in"]), T_(g["ys_out"]))
+    loss.backward()
+    assert logits is None
+    assert abs(float(loss) - float(g["loss_total"])) <= LOSS_RTOL * abs(float(g["loss_total"]))
+    assert abs(float(loss_dict["loss_rnnt"]) - float(g["lossdict.loss_rnnt"])) <= LOSS_RTOL * abs(float(g["lossdict.loss_rnnt"]))
+    assert rel_err(eouts.grad.cpu().numpy(), g["grad_eouts"]) < GRAD_RTOL
+    for k, v in dec.named_parameters():
+        ref = g["grad." + k]
+        if ref.size == 0:
+            continue
+        assert rel_err(v.grad.cpu().numpy(), ref) < GRAD_RTOL, k
+
+
+@pytest.mark.parametrize("B,T,U,V,J,seed", [(3, 11, 4, 13, 8, 0), (2, 33, 17, 100, 72, 1), (4, 20, 9, 260, 40, 2)])
+def test_joint_fp32_vs_dp_random(B, T, U, V, J, seed):
+    import emoasr_b200 as E
+    from oracle import rnnt_dp
+    rng = np.random.default_rng(seed)
+    f = lambda *s: rng.standard_normal(s).astype(np.float32)
+    enc, dec_ = f(B, T, J), f(B, U + 1, J)
+    w_out, b_out = f(V, J) * 0.3, f(V) * 0.1
+    ys = rng.integers(1, V, (B, U))
+    tl = rng.integers(1, T + 1, B); tl[0] = T
+    ul = rng.integers(0, U + 1, B); ul[0] = U
+    # oracle on the projected streams: identity projections
+    eye = np.eye(J, dtype=np.float32)
+    r = rnnt_dp.joint_loss_and_grads(enc, dec_, eye, np.zeros(J), eye, np.zeros(J), w_out, b_out, ys, tl, ul)
+    te = [T_(a).requires_grad_() for a in (enc, dec_, w_out, b_out)]
+    loss = E.rnnt_joint_loss(*te, T_(ys), T_(tl), T_(ul), blank=0, reduction="mean", precision="fp32")
+    loss.backward()
+    assert abs(float(loss) - r["loss"]) <= LOSS_RTOL * abs(r["loss"])
+    for t, k in zip(te, ["d_enc_proj", "d_dec_proj", "d_w_out", "d_b_out"]):
+        assert rel_err(t.grad.cpu().numpy(), r[k]) < GRAD_RTOL, k
+    assert abs(float(te[3].grad.sum())) < 1e-4          # dz rows sum to zero
+
+
+# ---------------------------------------------------------------- CTC
+CTC_CASES = ["ref_ctc_small_full", "ref_ctc_small_ragged", "ref_ctc_medium_ragged"]
+
+
+@pytest.mark.parametrize("name", CTC_CASES)
+def test_ctc_decoder_vs_reference_golden(name):
+    from emoasr_b200.decoders import CTCDecoder
+    g = load_golden(name)
+    d = dict(enc_hidden_size=int(g["hp.enc_hidden_size"]), vocab_size=int(g["hp.vocab_size"]),
+             eos_id=int(g["hp.eos_id"]), blank_id=int(g["hp.blank_id"]), kd_weight=0)
+    dec = CTCDecoder(namedtuple("Params", d.keys())(**d))
+    dec.load_state_dict({k[len("param."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")})
+    dec = dec.to(dev())
+    eouts = T_(g["eouts"]).requires_grad_()
+    loss, loss_dict, logits = dec(eouts, T_(g["elens"]), None, T_(g["ys"]), T_(g["ylens"]))
+    loss.backward()
+    assert abs(float(loss) - float(g["loss_total"])) <= LOSS_RTOL * abs(float(g["loss_total"]))
+    assert rel_err(logits.detach().cpu().numpy(), g["logits"]) < 1e-5
+    assert rel_err(eouts.grad.cpu().numpy(), g["grad_eouts"]) < GRAD_RTOL
+    assert rel_err(dec.output.weight.grad.cpu().numpy(), g["grad.output.weight"]) < GRAD_RTOL
+    assert rel_err(dec.output.bias.grad.cpu().numpy(), g["grad.output.bias"]) < GRAD_RTOL
+
+
+def test_ctc_aligner_smoke_fixture_and_module_seam():
+    import emoasr_b200 as E
+    g = load_golden("ref_ctc_aligner_smoke")
+    logits = T_(g["logits"]).requires_grad_()
+    fn = E.CTCLoss(blank=0, reduction="sum", zero_infinity=True)     # nn.CTCLoss-shaped call (ctc.py:109-110)
+    loss = fn(logits.transpose(1, 0).log_softmax(dim=2), T_(g["ys"]), T_(g["elens"]), T_(g["ylens"])) / 2
+    loss.backward()
+    assert abs(float(loss) - float(g["loss"])) <= LOSS_RTOL * float(g["loss"])
+    assert rel_err(logits.grad.cpu().numpy(), g["grad"]) < GRAD_RTOL
+
+
+@pytest.mark.parametrize("B,T,U,V,seed", [(4, 30, 8, 17, 0), (3, 50, 20, 101, 1), (6, 12, 5, 4, 2), (2, 40, 0, 8, 3)])
+def test_ctc_vs_dp_random_with_repeats_and_edges(B, T, U, V, seed):
+    import emoasr_b200 as E
+    from oracle import ctc_dp
+    rng = np.random.default_rng(seed)
+    logits = (rng.standard_normal((B, T, V)) * 2).astype(np.float32)
+    ys = rng.integers(1, min(V, 4), (B, max(U, 1)))            # tiny alphabet: many repeated labels
+    tl = rng.integers(1, T + 1, B); tl[0] = T
+    ul = rng.integers(0, U + 1, B); ul[0] = U
+    if B > 2:
+        tl[1], ul[1] = 1, min(U, 1)                              # single frame
+        tl[2], ul[2] = min(T, max(U, 1)), U                      # possibly infeasible with repeats
+    loss_ref, nll_ref, grad_ref = ctc_dp.ctc_loss_and_grad(logits, ys, tl, ul, blank=0)
+    x = T_(logits).requires_grad_()
+    nll = E.ctc_loss(x, T_(ys), T_(tl), T_(ul), blank=0)
+    (nll.sum() / B).backward()
+    assert np.abs(nll.detach().cpu().numpy() - nll_ref).max() <= LOSS_RTOL * max(np.abs(nll_ref).max(), 1.0)
+    assert rel_err(x.grad.cpu().numpy(), grad_ref) < GRAD_RTOL
+    assert np.abs(x.grad.cpu().numpy().sum(-1)).max() < 1e-5    # rows sum to zero
+
+
+def test_ctc_properties_full_size():
+    """BASELINE cfg-2 shape (B=64, T=374, V=5000): per-frame occupancies sum to one, so every valid
+    gradient row sums to zero; padded frames and infeasible utterances are exactly zero."""
+    import emoasr_b200 as E
+    B, T, V, U = 64, 374, 5000, 80
+    gen = torch.Generator().manual_seed(0)
+    logits = torch.randn(B, T, V, generator=gen).to(dev()).requires_grad_()
+    ys = torch.randint(4, V, (B, U), generator=gen)
+    r = torch.linspace(1.0, 0.6, B)
+    tl = (T * r).long()
+    ul = torch.randint(40, U + 1, (B,), generator=gen)
+    tl[-1], ul[-1] = 30, 60                                      # infeasible -> zero_infinity
+    nll = E.ctc_loss(logits, ys, tl, ul, blank=0)
+    nll.sum().backward()
+    g = logits.grad
+    assert float(nll[-1]) == 0.0 and float(g[-1].abs().sum()) == 0.0
+    assert torch.isfinite(nll).all() and (nll[:-1] > 0).all()
+    assert float(g.sum(-1).abs().max()) < 1e-4
+    assert float(g[5, int(tl[5]):].abs().sum()) == 0.0
+    # torch's own CUDA ctc_loss as a second opinion at full size
+    x2 = logits.detach().clone().requires_grad_()
+    ref = torch.nn.functional.ctc_loss(x2.transpose(0, 1).log_softmax(2), ys.to(dev()), tl.to(dev()), ul.to(dev()),
+                                       blank=0, reduction="none", zero_infinity=True)
+    ref.sum().backward()
+    assert torch.allclose(nll, ref, rtol=1e-5, atol=1e-3)
+    assert float((g - x2.grad).norm() / x2.grad.norm()) < GRAD_RTOL
