@@ -1,17 +1,409 @@
-// placeholder until the tcgen05 path lands (replaced in the next milestone)
+// EMO_PREC_BF16: fused joint on the 5th-gen tensor cores.
+//
+//   z[cell, v] = sum_j tanh(enc[b,t,j] + dec[b,u,j]) * w_out[v,j] + b_out[v]
+//   lse[cell]  = log sum_v exp z ;  lp2[cell] = { z[blank]-lse, z[label]-lse }
+// (asr/modeling/decoders/rnn_transducer.py:147-156 + :102) without writing z anywhere.
+//
+// Persistent, warp-specialised CTAs, one 128-cell tile at a time (cells of one utterance,
+// flattened over its VALID (t,u) region, so padding costs nothing):
+//   warp 0      TMA producer   w_out (bf16, [V][J]) tiles [256 v x 64 j], 128B swizzle, ring of
+//                              kNumBStages, mbarrier complete_tx
+//   warp 1      MMA issuer     tcgen05.mma kind::f16, M=128, N<=256, K=16; accumulators in TMEM,
+//                              two 256-column buffers so the epilogue of vocab chunk n overlaps the
+//                              MMAs of chunk n+1
+//   warp 2      TMEM allocator
+//   warps 4-7   epilogue       tcgen05.ld 32 columns at a time (thread == lattice cell), bias add,
+//                              online (max, sum-exp) over the vocab chunks, capture of the blank and
+//                              label logits
+//   warps 8-11  A producers    h = tanh(enc+dec) -> bf16 -> shared memory in the canonical K-major
+//                              128B-swizzle layout, one 64-wide K block at a time so the MMAs of
+//                              the next tile start as soon as block 0 is rewritten
+// The h tile (128 x J bf16) stays resident in shared memory for all vocab chunks of the tile.
 #include "common.cuh"
+#include "tc_common.cuh"
+
 namespace emo {
-size_t joint_bf16_workspace(int, int, int, int, int, int) { return 256; }
-int joint_fwd_bf16(const float*, const float*, const float*, const float*, const int*, const int*,
-                   const int*, int, int, int, int, int, int, float*, float*, void*, size_t,
-                   cudaStream_t) {
-    set_error("joint_fwd(bf16): not built");
-    return EMO_UNSUPPORTED_SHAPE;
+namespace {
+
+using namespace tc;
+
+constexpr int kTileM = 128;          // cells per tile
+constexpr int kBlockK = 64;          // bf16 elements per 128-byte swizzle row
+constexpr int kChunkN = 256;         // vocab columns per accumulator buffer
+constexpr int kMaxKBlocks = 8;       // J <= 512
+constexpr int kMaxBStages = 4;
+constexpr int kABlockBytes = kTileM * kBlockK * 2;    // 16 KiB
+constexpr int kBStageBytes = kChunkN * kBlockK * 2;   // 32 KiB
+constexpr int kThreads = 384;
+constexpr int kSmemLimit = 232448;                    // 227 KiB opt-in maximum per CTA
+constexpr float kLog2e = 1.4426950408889634f;
+constexpr float kLn2 = 0.6931471805599453f;
+
+struct __align__(16) Barriers {
+    uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
+    uint64_t a_full[kMaxKBlocks], a_empty[kMaxKBlocks];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+struct TileInfo {
+    int b, first_cell, n_cells, U1b;  // n_cells = valid cells of the utterance
+};
+
+__device__ __forceinline__ bool tile_info(int tile, int tiles_per_utt, const int* tlen,
+                                          const int* ulen, int T, int U1, TileInfo& ti) {
+    ti.b = tile / tiles_per_utt;
+    int i = tile - ti.b * tiles_per_utt;
+    int T_b = min(max(__ldg(tlen + ti.b), 1), T);
+    ti.U1b = min(max(__ldg(ulen + ti.b), 0), U1 - 1) + 1;
+    ti.n_cells = T_b * ti.U1b;
+    ti.first_cell = i * kTileM;
+    return ti.first_cell < ti.n_cells;
 }
-int joint_bwd_bf16(const float*, const float*, const float*, const float*, const int*, const int*,
-                   const int*, const float*, const float*, const float*, int, int, int, int, int,
-                   int, float*, float*, float*, float*, void*, size_t, cudaStream_t) {
-    set_error("joint_bwd(bf16): not built");
-    return EMO_UNSUPPORTED_SHAPE;
+
+__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
+                                   size_t n) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        float4 v = *reinterpret_cast<const float4*>(src + i);
+        uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
+        *reinterpret_cast<uint2*>(dst + i) = o;
+    } else {
+        for (; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
+    }
 }
+
+__global__ void __launch_bounds__(kThreads, 1)
+joint_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ enc,
+                      const float* __restrict__ dec, const float* __restrict__ b_out,
+                      const int* __restrict__ labels, const int* __restrict__ tlen,
+                      const int* __restrict__ ulen, int B, int T, int U1, int J, int V, int blank,
+                      int num_b_stages, uint32_t b_stage_tx, float* __restrict__ lp2, float* __restrict__ lse_out) {
+    // 1024-byte alignment is required by the 128B swizzle atoms; the kernel has no static shared
+    // memory, so the dynamic window starts at the CTA's (1 KiB-granular) shared-memory base.
+    extern __shared__ __align__(1024) uint8_t smem[];
+    if ((smem_u32(smem) & 1023u) != 0) {  // uniform; never expected
+        if (threadIdx.x == 0 && blockIdx.x == 0) printf("emoasr_b200: shared memory base misaligned\n");
+        return;
+    }
+    const int KB = J / kBlockK;
+    const int NC = (V + kChunkN - 1) / kChunkN;
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + (size_t)KB * kABlockBytes;
+    Barriers* bars = reinterpret_cast<Barriers*>(sB + (size_t)num_b_stages * kBStageBytes);
+    float* s_bias = reinterpret_cast<float*>(bars + 1);  // [2][kChunkN]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int tiles_per_utt = (T * U1 + kTileM - 1) / kTileM;
+    const int total_tiles = B * tiles_per_utt;
+
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kMaxBStages; ++i) {
+            mbar_init(smem_u32(&bars->b_full[i]), 1);
+            mbar_init(smem_u32(&bars->b_empty[i]), 1);
+        }
+        for (int i = 0; i < kMaxKBlocks; ++i) {
+            mbar_init(smem_u32(&bars->a_full[i]), 128);
+            mbar_init(smem_u32(&bars->a_empty[i]), 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&bars->acc_full[i]), 1);
+            mbar_init(smem_u32(&bars->acc_empty[i]), 128);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_w);
+    if (warp == 2) {
+        tmem_alloc(smem_u32(&bars->tmem_base), 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA producer =====================
+        if (lane == 0) {
+            uint32_t it = 0;
+            TileInfo ti;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                if (!tile_info(tile, tiles_per_utt, tlen, ulen, T, U1, ti)) continue;
+                for (int nc = 0; nc < NC; ++nc)
+                    for (int kb = 0; kb < KB; ++kb, ++it) {
+                        uint32_t s = it % num_b_stages, ph = (it / num_b_stages) & 1;
+                        mbar_wait(smem_u32(&bars->b_empty[s]), ph ^ 1);
+                        uint32_t full = smem_u32(&bars->b_full[s]);
+                        mbar_arrive_expect_tx(full, b_stage_tx);
+                        tma_load_2d(smem_u32(sB + (size_t)s * kBStageBytes), &tmap_w, kb * kBlockK,
+                                    nc * kChunkN, full);
+                    }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t it = 0, cc = 0, tl = 0;
+            TileInfo ti;
+            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                if (!tile_info(tile, tiles_per_utt, tlen, ulen, T, U1, ti)) continue;
+                for (int nc = 0; nc < NC; ++nc, ++cc) {
+                    const uint32_t buf = cc & 1;
+                    mbar_wait(smem_u32(&bars->acc_empty[buf]), ((cc >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    const int n = min(kChunkN, V - nc * kChunkN);
+                    const uint32_t idesc = umma_idesc_bf16(kTileM, n);
+                    const uint32_t d_tmem = tmem_base + buf * kChunkN;
+                    for (int kb = 0; kb < KB; ++kb, ++it) {
+                        if (nc == 0) mbar_wait(smem_u32(&bars->a_full[kb]), tl & 1);
+                        uint32_t s = it % num_b_stages, ph = (it / num_b_stages) & 1;
+                        mbar_wait(smem_u32(&bars->b_full[s]), ph);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(sA + (size_t)kb * kABlockBytes);
+                        const uint32_t b_addr = smem_u32(sB + (size_t)s * kBStageBytes);
+#pragma unroll
+                        for (int k16 = 0; k16 < kBlockK / 16; ++k16) {
+                            umma_bf16(d_tmem, umma_desc_k_sw128(a_addr + k16 * 32),
+                                      umma_desc_k_sw128(b_addr + k16 * 32), idesc,
+                                      (kb | k16) != 0);
+                        }
+                        umma_commit(smem_u32(&bars->b_empty[s]));
+                        if (nc == NC - 1) umma_commit(smem_u32(&bars->a_empty[kb]));
+                    }
+                    umma_commit(smem_u32(&bars->acc_full[buf]));
+                }
+                ++tl;
+            }
+        }
+    } else if (warp >= 4 && warp < 8) {
+        // ===================== epilogue: online LSE over vocab chunks =====================
+        const int q = warp & 3;
+        const int row = q * 32 + lane;
+        const int etid = threadIdx.x - 128;  // 0..127
+        uint32_t cc = 0;
+        TileInfo ti;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            if (!tile_info(tile, tiles_per_utt, tlen, ulen, T, U1, ti)) continue;
+            const int m = ti.first_cell + row;
+            const bool valid = m < ti.n_cells;
+            const int t = valid ? m / ti.U1b : 0;
+            const int u = valid ? m - t * ti.U1b : 0;
+            int lab = -1;
+            if (valid && u < ti.U1b - 1)
+                lab = min(max(__ldg(labels + (size_t)ti.b * (U1 - 1) + u), 0), V - 1);
+            float run_m = kNegInf, run_s = 0.f, zb = 0.f, zl = 0.f;
+            for (int nc = 0; nc < NC; ++nc, ++cc) {
+                const uint32_t buf = cc & 1;
+                const int n = min(kChunkN, V - nc * kChunkN);
+                // stage this chunk's bias (double-buffered with the accumulator buffer)
+                float* bias = s_bias + buf * kChunkN;
+                for (int i = etid; i < n; i += 128) bias[i] = __ldg(b_out + nc * kChunkN + i);
+                named_bar_sync(1, 128);
+                mbar_wait(smem_u32(&bars->acc_full[buf]), (cc >> 1) & 1);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kChunkN;
+                for (int g = 0; g < n / 32; ++g) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(taddr + g * 32, r);
+                    tmem_wait_ld();
+                    const int v0 = nc * kChunkN + g * 32;
+                    float x[32];
+                    float gmax = kNegInf;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4) {
+                        float4 bv = *reinterpret_cast<const float4*>(bias + g * 32 + i);
+                        x[i + 0] = __uint_as_float(r[i + 0]) + bv.x;
+                        x[i + 1] = __uint_as_float(r[i + 1]) + bv.y;
+                        x[i + 2] = __uint_as_float(r[i + 2]) + bv.z;
+                        x[i + 3] = __uint_as_float(r[i + 3]) + bv.w;
+                        gmax = fmaxf(gmax, fmaxf(fmaxf(x[i], x[i + 1]), fmaxf(x[i + 2], x[i + 3])));
+                    }
+                    const float new_m = fmaxf(run_m, gmax);
+                    const float neg_m2 = -new_m * kLog2e;
+                    float acc = 0.f;
+                    const int dl = lab - v0;
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        acc += ex2_approx(fmaf(x[i], kLog2e, neg_m2));
+                        zl = (i == dl) ? x[i] : zl;
+                    }
+                    if (blank >= v0 && blank < v0 + 32) {  // warp-uniform
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) zb = (i == blank - v0) ? x[i] : zb;
+                    }
+                    run_s = run_s * ex2_approx((run_m - new_m) * kLog2e) + acc;
+                    run_m = new_m;
+                }
+                tc_fence_before();
+                mbar_arrive(smem_u32(&bars->acc_empty[buf]));
+            }
+            if (valid) {
+                const float l = run_m + kLn2 * log2f(run_s);
+                const size_t cell = ((size_t)ti.b * T + t) * U1 + u;
+                reinterpret_cast<float2*>(lp2)[cell] = make_float2(zb - l, lab >= 0 ? zl - l : 0.f);
+                lse_out[cell] = l;
+            }
+        }
+    } else if (warp >= 8) {
+        // ===================== A producers: h = tanh(enc + dec) -> bf16, swizzled =====================
+        const int pw = warp - 8;
+        const int c = lane & 7;        // 16-byte chunk (8 bf16) inside the 128-byte row
+        const int rsub = lane >> 3;    // 4 rows per warp pass
+        uint32_t tl = 0;
+        TileInfo ti;
+        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+            if (!tile_info(tile, tiles_per_utt, tlen, ulen, T, U1, ti)) continue;
+            uint32_t eoff[8], doff[8];  // element offsets of this lane's 8 rows
+#pragma unroll
+            for (int p = 0; p < 8; ++p) {
+                int row = pw * 32 + p * 4 + rsub;
+                int m = min(ti.first_cell + row, ti.n_cells - 1);  // clamp padding rows
+                int t = m / ti.U1b, u = m - t * ti.U1b;
+                eoff[p] = (uint32_t)(((size_t)ti.b * T + t) * J) + c * 8;
+                doff[p] = (uint32_t)(((size_t)ti.b * U1 + u) * J) + c * 8;
+            }
+            for (int kb = 0; kb < KB; ++kb) {
+                mbar_wait(smem_u32(&bars->a_empty[kb]), (tl & 1) ^ 1);
+                uint8_t* blk = sA + (size_t)kb * kABlockBytes;
+#pragma unroll
+                for (int half = 0; half < 2; ++half) {
+                    float4 e0[4], e1[4], d0[4], d1[4];
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const float* ep = enc + eoff[half * 4 + p] + kb * kBlockK;
+                        const float* dp = dec + doff[half * 4 + p] + kb * kBlockK;
+                        e0[p] = __ldg(reinterpret_cast<const float4*>(ep));
+                        e1[p] = __ldg(reinterpret_cast<const float4*>(ep) + 1);
+                        d0[p] = __ldg(reinterpret_cast<const float4*>(dp));
+                        d1[p] = __ldg(reinterpret_cast<const float4*>(dp) + 1);
+                    }
+#pragma unroll
+                    for (int p = 0; p < 4; ++p) {
+                        const int row = pw * 32 + (half * 4 + p) * 4 + rsub;
+                        uint4 o;
+                        o.x = pack_bf16x2(tanh_approx(e0[p].x + d0[p].x), tanh_approx(e0[p].y + d0[p].y));
+                        o.y = pack_bf16x2(tanh_approx(e0[p].z + d0[p].z), tanh_approx(e0[p].w + d0[p].w));
+                        o.z = pack_bf16x2(tanh_approx(e1[p].x + d1[p].x), tanh_approx(e1[p].y + d1[p].y));
+                        o.w = pack_bf16x2(tanh_approx(e1[p].z + d1[p].z), tanh_approx(e1[p].w + d1[p].w));
+                        // canonical K-major SW128: 16-byte chunk index XOR (row mod 8)
+                        uint8_t* dst = blk + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+                        *reinterpret_cast<uint4*>(dst) = o;
+                    }
+                }
+                fence_proxy_async_smem();
+                mbar_arrive(smem_u32(&bars->a_full[kb]));
+            }
+            ++tl;
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// ---- host side ----
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
+                      uint32_t box_inner, uint32_t box_outer) {
+    cuuint64_t dims[2] = {inner, outer};
+    cuuint64_t strides[1] = {inner * sizeof(__nv_bfloat16)};
+    cuuint32_t box[2] = {box_inner, box_outer};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
+                                        const_cast<void*>(base), dims, strides, box, estr,
+                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        const char* s = nullptr;
+        cuGetErrorString(r, &s);
+        set_error("cuTensorMapEncodeTiled failed: %s", s ? s : "?");
+        return EMO_LAUNCH_FAILURE;
+    }
+    return EMO_OK;
+}
+
+int check_bf16_shape(int B, int T, int U1, int J, int V, int blank) {
+    EMO_REQUIRE(B > 0 && T > 0 && U1 > 0 && J > 0 && V > 0, EMO_BAD_ARG, "joint(bf16): bad sizes");
+    EMO_REQUIRE(blank >= 0 && blank < V, EMO_BAD_ARG, "joint(bf16): blank %d outside [0,%d)", blank, V);
+    EMO_REQUIRE(J % kBlockK == 0 && J <= kMaxKBlocks * kBlockK, EMO_UNSUPPORTED_SHAPE,
+                "joint(bf16): joint_hidden_size %d must be a multiple of 64 and <= 512 "
+                "(use precision fp32 for other sizes)", J);
+    EMO_REQUIRE(V % 32 == 0, EMO_UNSUPPORTED_SHAPE,
+                "joint(bf16): vocab %d must be a multiple of 32 (use precision fp32)", V);
+    EMO_REQUIRE((long long)B * T * J < (1ll << 31) && (long long)B * U1 * J < (1ll << 31),
+                EMO_UNSUPPORTED_SHAPE, "joint(bf16): projected streams exceed 2^31 elements");
+    return EMO_OK;
+}
+
+}  // namespace
+
+size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V) {
+    size_t w = align_up((size_t)V * J * sizeof(__nv_bfloat16), 256);
+    if (op == EMO_OP_RNNT_JOINT_BWD) return w + joint_f32_workspace(op, B, T, U1, J, V);
+    return w;
+}
+
+int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
+                   const float* b_out, const int* labels, const int* tlen, const int* ulen, int B,
+                   int T, int U1, int J, int V, int blank, float* lp2, float* lse, void* ws,
+                   size_t ws_bytes, cudaStream_t st) {
+    EMO_REQUIRE(enc_proj && dec_proj && w_out && b_out && labels && tlen && ulen && lp2 && lse && ws,
+                EMO_BAD_ARG, "joint_fwd(bf16): null pointer");
+    int rc = check_bf16_shape(B, T, U1, J, V, blank);
+    if (rc) return rc;
+    EMO_REQUIRE(ws_bytes >= joint_bf16_workspace(EMO_OP_RNNT_JOINT_FWD, B, T, U1, J, V),
+                EMO_WORKSPACE_TOO_SMALL, "joint_fwd(bf16): workspace too small");
+    EMO_REQUIRE(((uintptr_t)ws & 255) == 0 && ((uintptr_t)enc_proj & 15) == 0 &&
+                    ((uintptr_t)dec_proj & 15) == 0 && ((uintptr_t)w_out & 15) == 0,
+                EMO_BAD_ARG, "joint_fwd(bf16): pointers must be 16-byte (workspace 256-byte) aligned");
+    __nv_bfloat16* w_bf16 = reinterpret_cast<__nv_bfloat16*>(ws);
+    size_t nw = (size_t)V * J;
+    f32_to_bf16_kernel<<<ceil_div(nw, 4 * 256), 256, 0, st>>>(w_out, w_bf16, nw);
+    EMO_CHECK_LAUNCH("f32_to_bf16_kernel");
+
+    CUtensorMap tmap;
+    rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, (uint32_t)min(kChunkN, V));
+    if (rc) return rc;
+
+    const int KB = J / kBlockK;
+    const size_t a_bytes = (size_t)KB * kABlockBytes;
+    const size_t fixed = sizeof(Barriers) + 2 * kChunkN * sizeof(float);
+    int stages = (int)min((size_t)kMaxBStages, (kSmemLimit - a_bytes - fixed) / kBStageBytes);
+    EMO_REQUIRE(stages >= 2, EMO_UNSUPPORTED_SHAPE, "joint_fwd(bf16): not enough shared memory");
+    const size_t smem = a_bytes + (size_t)stages * kBStageBytes + fixed;
+    EMO_CUDA(cudaFuncSetAttribute(joint_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)smem));
+    const int tiles = B * ceil_div((size_t)T * U1, kTileM);
+    const int grid = min(tiles, sm_count());
+    joint_fwd_bf16_kernel<<<grid, kThreads, smem, st>>>(tmap, enc_proj, dec_proj, b_out, labels, tlen,
+                                                        ulen, B, T, U1, J, V, blank, stages,
+                                                        (uint32_t)(min(kChunkN, V) * kBlockK * 2), lp2, lse);
+    EMO_CHECK_LAUNCH("joint_fwd_bf16_kernel");
+    return EMO_OK;
+}
+
+// Interim: the bf16 backward still runs the fp32 slab path (tcgen05 backward is the next milestone).
+int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
+                   const float* b_out, const int* labels, const int* tlen, const int* ulen,
+                   const float* lse, const float* gamma2, const float* grad_cost, int B, int T,
+                   int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
+                   float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    size_t w = align_up((size_t)V * J * sizeof(__nv_bfloat16), 256);
+    EMO_REQUIRE(ws && ws_bytes >= joint_bf16_workspace(EMO_OP_RNNT_JOINT_BWD, B, T, U1, J, V),
+                EMO_WORKSPACE_TOO_SMALL, "joint_bwd(bf16): workspace too small");
+    return joint_bwd_f32(enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, lse, gamma2,
+                         grad_cost, B, T, U1, J, V, blank, d_enc_proj, d_dec_proj, d_w_out, d_b_out,
+                         (char*)ws + w, ws_bytes - w, st);
+}
+
 }  // namespace emo
