@@ -21,6 +21,7 @@ _SIGNATURES = {
     "emo_abi_version": (_I, []),
     "emo_last_error_string": (_c.c_char_p, []),
     "emo_workspace_bytes": (_SZ, [_I] * 7),
+    "emo_launch_count": (_I, [_I] * 7),
     "emo_rnnt_lattice_fwd_bwd": (_I, [_P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "emo_rnnt_dense_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "emo_rnnt_dense_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
@@ -66,3 +67,7 @@ def check(status, what):
 
 def workspace_bytes(op, precision, B, T, U1, J, V):
     return int(load().emo_workspace_bytes(op, precision, B, T, U1, J, V))
+
+
+def launch_count(op, precision, B, T, U1, J, V):
+    return int(load().emo_launch_count(op, precision, B, T, U1, J, V))

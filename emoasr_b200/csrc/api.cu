@@ -48,6 +48,22 @@ extern "C" size_t emo_workspace_bytes(int op, int precision, int B, int T, int U
     }
 }
 
+extern "C" int emo_launch_count(int op, int precision, int B, int T, int U1, int J, int V) {
+    if (B <= 0 || T <= 0) return 0;
+    switch (op) {
+        case EMO_OP_RNNT_JOINT_FWD:
+            return (precision == EMO_PREC_BF16 ? joint_bf16_launches(op, B, T, U1, J, V)
+                                               : joint_f32_launches(op, B, T, U1, J, V)) + 2;
+        case EMO_OP_RNNT_JOINT_BWD:
+            return precision == EMO_PREC_BF16 ? joint_bf16_launches(op, B, T, U1, J, V)
+                                              : joint_f32_launches(op, B, T, U1, J, V);
+        case EMO_OP_CTC:
+            return 4;  // row lse, alpha, beta/occupancy, gradient
+        default:
+            return 0;
+    }
+}
+
 extern "C" int emo_rnnt_joint_fwd(const float* enc_proj, const float* dec_proj, const float* w_out,
                                   const float* b_out, const int* labels, const int* tlen,
                                   const int* ulen, int B, int T, int U1, int J, int V, int blank,

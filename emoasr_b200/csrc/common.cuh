@@ -88,6 +88,7 @@ int joint_bwd_f32(const float* enc_proj, const float* dec_proj, const float* w_o
                   int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
                   float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t joint_f32_workspace(int op, int B, int T, int U1, int J, int V);
+int joint_f32_launches(int op, int B, int T, int U1, int J, int V);
 
 int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
                    const float* b_out, const int* labels, const int* tlen, const int* ulen, int B,
@@ -99,5 +100,6 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
                    int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
                    float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V);
+int joint_bf16_launches(int op, int B, int T, int U1, int J, int V);
 
 }  // namespace emo

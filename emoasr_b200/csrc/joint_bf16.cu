@@ -318,15 +318,24 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
     cuuint64_t strides[1] = {inner * sizeof(__nv_bfloat16)};
     cuuint32_t box[2] = {box_inner, box_outer};
     cuuint32_t estr[2] = {1, 1};
-    CUresult r = cuTensorMapEncodeTiled(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2,
-                                        const_cast<void*>(base), dims, strides, box, estr,
-                                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    // libcuda is reached through the runtime (no link-time dependency on libcuda.so.1, so the
+    // library also loads on a machine without a driver)
+    static PFN_encodeTiled encode = nullptr;
+    if (!encode) {
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
+            set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorName(e));
+            return EMO_NO_DEVICE;
+        }
+        encode = (PFN_encodeTiled)fn;
+    }
+    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
+                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
-        const char* s = nullptr;
-        cuGetErrorString(r, &s);
-        set_error("cuTensorMapEncodeTiled failed: %s", s ? s : "?");
+        set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
         return EMO_LAUNCH_FAILURE;
     }
     return EMO_OK;
@@ -351,6 +360,11 @@ size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V) {
     size_t w = align_up((size_t)V * J * sizeof(__nv_bfloat16), 256);
     if (op == EMO_OP_RNNT_JOINT_BWD) return w + joint_f32_workspace(op, B, T, U1, J, V);
     return w;
+}
+
+int joint_bf16_launches(int op, int B, int T, int U1, int J, int V) {
+    if (op == EMO_OP_RNNT_JOINT_BWD) return joint_f32_launches(op, B, T, U1, J, V);
+    return 2;  // weight cast + fused joint
 }
 
 int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,

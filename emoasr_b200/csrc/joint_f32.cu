@@ -261,6 +261,13 @@ size_t joint_f32_workspace(int op, int B, int T, int U1, int J, int V) {
     return bytes;
 }
 
+int joint_f32_launches(int op, int B, int T, int U1, int J, int V) {
+    (void)J; (void)V;
+    int R = min(slab_rows_for(U1), B * T);
+    int slabs = (B * T + R - 1) / R;
+    return slabs * (op == EMO_OP_RNNT_JOINT_BWD ? 7 : 3);
+}
+
 int joint_fwd_f32(const float* enc_proj, const float* dec_proj, const float* w_out,
                   const float* b_out, const int* labels, const int* tlen, const int* ulen, int B,
                   int T, int U1, int J, int V, int blank, float* lp2, float* lse, void* ws,

@@ -62,6 +62,12 @@ const char* emo_last_error_string(void); /* host pointer, thread-local storage *
 /* Bytes of scratch the op needs for these sizes and precision (host call, no CUDA work). */
 size_t emo_workspace_bytes(int op, int precision, int B, int T, int U1, int J, int V);
 
+/* Number of kernel launches one call of the op enqueues for these sizes (host call; lets a harness
+ * report how many of this library's kernels ran).  EMO_OP_RNNT_JOINT_FWD counts emo_rnnt_joint_fwd
+ * plus the emo_rnnt_lattice_fwd_bwd that follows it; EMO_OP_CTC counts emo_ctc_fwd + emo_ctc_bwd
+ * (J is ignored). */
+int emo_launch_count(int op, int precision, int B, int T, int U1, int J, int V);
+
 /* ---- RNN-T lattice on gathered pairs ---------------------------------------------------------
  * Replaces the alpha/beta/grad kernels of warp_rnnt.rnnt_loss (rnn_transducer.py:106-115).
  * lp2      (B,T,U1,2)  {log p(blank | t,u), log p(y_{u+1} | t,u)}
