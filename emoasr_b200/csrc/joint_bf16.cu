@@ -19,6 +19,8 @@
 //                              128B-swizzle layout, one 64-wide K block at a time so the MMAs of
 //                              the next tile start as soon as block 0 is rewritten
 // The h tile (128 x J bf16) stays resident in shared memory for all vocab chunks of the tile.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "tc_common.cuh"
 
@@ -31,35 +33,29 @@ constexpr int kTileM = 128;          // cells per tile
 constexpr int kBlockK = 64;          // bf16 elements per 128-byte swizzle row
 constexpr int kChunkN = 256;         // vocab columns per accumulator buffer
 constexpr int kMaxKBlocks = 8;       // J <= 512
-constexpr int kMaxBStages = 4;
 constexpr int kABlockBytes = kTileM * kBlockK * 2;    // 16 KiB
-constexpr int kBStageBytes = kChunkN * kBlockK * 2;   // 32 KiB
 constexpr int kThreads = 384;
 constexpr int kSmemLimit = 232448;                    // 227 KiB opt-in maximum per CTA
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
-struct __align__(16) Barriers {
-    uint64_t b_full[kMaxBStages], b_empty[kMaxBStages];
-    uint64_t a_full[kMaxKBlocks], a_empty[kMaxKBlocks];
-    uint64_t acc_full[2], acc_empty[2];
-    uint32_t tmem_base;
-    uint32_t pad;
-};
-
 struct TileInfo {
     int b, first_cell, n_cells, U1b;  // n_cells = valid cells of the utterance
 };
 
-__device__ __forceinline__ bool tile_info(int tile, int tiles_per_utt, const int* tlen,
+// kCtas = 1: one CTA per 128-cell tile.  kCtas = 2: a CTA pair (cluster of 2, cta_group::2) per
+// 256-cell tile, 128 cells per CTA; `rank` selects this CTA's half.  Both CTAs of a pair get the
+// same answer.
+template <int kCtas>
+__device__ __forceinline__ bool tile_info(int tile, int tiles_per_utt, uint32_t rank, const int* tlen,
                                           const int* ulen, int T, int U1, TileInfo& ti) {
     ti.b = tile / tiles_per_utt;
     int i = tile - ti.b * tiles_per_utt;
     int T_b = min(max(__ldg(tlen + ti.b), 1), T);
     ti.U1b = min(max(__ldg(ulen + ti.b), 0), U1 - 1) + 1;
     ti.n_cells = T_b * ti.U1b;
-    ti.first_cell = i * kTileM;
-    return ti.first_cell < ti.n_cells;
+    ti.first_cell = i * (kCtas * kTileM) + (int)rank * kTileM;
+    return i * (kCtas * kTileM) < ti.n_cells;
 }
 
 __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
@@ -74,104 +70,248 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
     }
 }
 
+// ---- per-variant constants ----
+template <int kCtas> struct Cfg;
+template <> struct Cfg<1> {
+    static constexpr int kBStages = 3;
+    static constexpr int kBRows = kChunkN;            // vocab rows of a w_out tile held by this CTA
+};
+template <> struct Cfg<2> {
+    static constexpr int kBStages = 6;
+    static constexpr int kBRows = kChunkN / 2;
+};
+
+template <int kCtas>
+struct __align__(16) FwdBarriers {
+    uint64_t b_full[Cfg<kCtas>::kBStages], b_empty[Cfg<kCtas>::kBStages];
+    uint64_t a_full[kMaxKBlocks], a_empty[kMaxKBlocks];
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad[3];
+};
+
+// A-operand producer shared by the forward and backward kernels: this warp's 32 rows of the
+// 128-row tile, K block kb.  h = tanh(enc + dec) -> bf16 -> canonical K-major SW128 layout
+// (16-byte chunk index XOR (row mod 8)).
+__device__ __forceinline__ void produce_h_block(const float* __restrict__ enc,
+                                                const float* __restrict__ dec,
+                                                const uint32_t (&eoff)[8], const uint32_t (&doff)[8],
+                                                int kb, int pw, int rsub, int c, uint8_t* blk) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        float4 e0[4], e1[4], d0[4], d1[4];
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const float* ep = enc + eoff[half * 4 + p] + kb * kBlockK;
+            const float* dp = dec + doff[half * 4 + p] + kb * kBlockK;
+            e0[p] = __ldg(reinterpret_cast<const float4*>(ep));
+            e1[p] = __ldg(reinterpret_cast<const float4*>(ep) + 1);
+            d0[p] = __ldg(reinterpret_cast<const float4*>(dp));
+            d1[p] = __ldg(reinterpret_cast<const float4*>(dp) + 1);
+        }
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+            const int row = pw * 32 + (half * 4 + p) * 4 + rsub;
+            uint4 o;
+            o.x = pack_bf16x2(tanh_approx(e0[p].x + d0[p].x), tanh_approx(e0[p].y + d0[p].y));
+            o.y = pack_bf16x2(tanh_approx(e0[p].z + d0[p].z), tanh_approx(e0[p].w + d0[p].w));
+            o.z = pack_bf16x2(tanh_approx(e1[p].x + d1[p].x), tanh_approx(e1[p].y + d1[p].y));
+            o.w = pack_bf16x2(tanh_approx(e1[p].z + d1[p].z), tanh_approx(e1[p].w + d1[p].w));
+            uint8_t* dst = blk + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+            *reinterpret_cast<uint4*>(dst) = o;
+        }
+    }
+}
+
+// x[d] for a per-thread d in [0,32) without dynamic register indexing: five select levels
+__device__ __forceinline__ float mux32(const float (&x)[32], int d) {
+    float a[16], b[8], c[4], e[2];
+    const bool s4 = d & 16, s3 = d & 8, s2 = d & 4, s1 = d & 2, s0 = d & 1;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) a[i] = s4 ? x[i + 16] : x[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) b[i] = s3 ? a[i + 8] : a[i];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) c[i] = s2 ? b[i + 4] : b[i];
+#pragma unroll
+    for (int i = 0; i < 2; ++i) e[i] = s1 ? c[i + 2] : c[i];
+    return s0 ? e[1] : e[0];
+}
+
+// One 32-column group of logits of this thread's row: bias add, online (max, sum exp2), capture of
+// the blank / label logit.
+__device__ __forceinline__ void lse_group(const uint32_t (&r)[32], const float* __restrict__ bias,
+                                          int v0, int lab, int blank, float& run_m, float& run_s,
+                                          float& zb, float& zl) {
+    float x[32];
+    float m0 = kNegInf, m1 = kNegInf, m2 = kNegInf, m3 = kNegInf;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        const float4 bv = *reinterpret_cast<const float4*>(bias + i);
+        x[i + 0] = __uint_as_float(r[i + 0]) + bv.x;
+        x[i + 1] = __uint_as_float(r[i + 1]) + bv.y;
+        x[i + 2] = __uint_as_float(r[i + 2]) + bv.z;
+        x[i + 3] = __uint_as_float(r[i + 3]) + bv.w;
+        m0 = fmaxf(m0, x[i + 0]);
+        m1 = fmaxf(m1, x[i + 1]);
+        m2 = fmaxf(m2, x[i + 2]);
+        m3 = fmaxf(m3, x[i + 3]);
+    }
+    const float new_m = fmaxf(run_m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
+    const float neg_m2 = -new_m * kLog2e;
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        s0 += ex2_approx(fmaf(x[i + 0], kLog2e, neg_m2));
+        s1 += ex2_approx(fmaf(x[i + 1], kLog2e, neg_m2));
+        s2 += ex2_approx(fmaf(x[i + 2], kLog2e, neg_m2));
+        s3 += ex2_approx(fmaf(x[i + 3], kLog2e, neg_m2));
+    }
+    run_s = run_s * ex2_approx((run_m - new_m) * kLog2e) + ((s0 + s1) + (s2 + s3));
+    run_m = new_m;
+    const int dl = lab - v0;
+    const bool mine = dl >= 0 && dl < 32;
+    if (__any_sync(0xffffffffu, mine)) {
+        const float v = mux32(x, dl & 31);
+        zl = mine ? v : zl;
+    }
+    if (blank >= v0 && blank < v0 + 32) zb = mux32(x, blank - v0);  // warp-uniform branch
+}
+
+// =================================================================================================
+// Fused joint forward.  See the file header for the role layout.  kCtas = 2 is the CTA-pair
+// (cta_group::2) version: the leader CTA issues M=256 MMAs over both CTAs' h tiles, and each CTA
+// stages only half (128 vocab rows) of every w_out tile.  Barrier topology for the pair:
+//   b_full / a_full / acc_empty live in the LEADER (arrivals from both CTAs, TMA bytes from both),
+//   b_empty / a_empty / acc_full are signalled in BOTH CTAs by a multicast tcgen05.commit.
+template <int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
-joint_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ enc,
-                      const float* __restrict__ dec, const float* __restrict__ b_out,
-                      const int* __restrict__ labels, const int* __restrict__ tlen,
-                      const int* __restrict__ ulen, int B, int T, int U1, int J, int V, int blank,
-                      int num_b_stages, uint32_t b_stage_tx, float* __restrict__ lp2, float* __restrict__ lse_out) {
+joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ enc,
+                 const float* __restrict__ dec, const float* __restrict__ b_out,
+                 const int* __restrict__ labels, const int* __restrict__ tlen,
+                 const int* __restrict__ ulen, int B, int T, int U1, int J, int V, int blank,
+                 float* __restrict__ lp2, float* __restrict__ lse_out) {
+    constexpr bool kPair = kCtas == 2;
+    constexpr int kBStages = Cfg<kCtas>::kBStages;
+    constexpr int kBBytes = Cfg<kCtas>::kBRows * kBlockK * 2;
+    using Bars = FwdBarriers<kCtas>;
     // 1024-byte alignment is required by the 128B swizzle atoms; the kernel has no static shared
     // memory, so the dynamic window starts at the CTA's (1 KiB-granular) shared-memory base.
     extern __shared__ __align__(1024) uint8_t smem[];
-    if ((smem_u32(smem) & 1023u) != 0) {  // uniform; never expected
-        if (threadIdx.x == 0 && blockIdx.x == 0) printf("emoasr_b200: shared memory base misaligned\n");
-        return;
-    }
     const int KB = J / kBlockK;
     const int NC = (V + kChunkN - 1) / kChunkN;
     uint8_t* sA = smem;
     uint8_t* sB = sA + (size_t)KB * kABlockBytes;
-    Barriers* bars = reinterpret_cast<Barriers*>(sB + (size_t)num_b_stages * kBStageBytes);
+    Bars* bars = reinterpret_cast<Bars*>(sB + (size_t)kBStages * kBBytes);
     float* s_bias = reinterpret_cast<float*>(bars + 1);  // [2][kChunkN]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int tiles_per_utt = (T * U1 + kTileM - 1) / kTileM;
+    const uint32_t rank = kPair ? cluster_ctarank() : 0;
+    const bool leader = rank == 0;
+    const int tiles_per_utt = (T * U1 + kCtas * kTileM - 1) / (kCtas * kTileM);
     const int total_tiles = B * tiles_per_utt;
+    const int tile0 = blockIdx.x / kCtas, tile_stride = gridDim.x / kCtas;
+    constexpr uint32_t kArrivals = 128 * kCtas;
 
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < kMaxBStages; ++i) {
-            mbar_init(smem_u32(&bars->b_full[i]), 1);
+        for (int i = 0; i < kBStages; ++i) {
+            mbar_init(smem_u32(&bars->b_full[i]), kCtas);
             mbar_init(smem_u32(&bars->b_empty[i]), 1);
         }
         for (int i = 0; i < kMaxKBlocks; ++i) {
-            mbar_init(smem_u32(&bars->a_full[i]), 128);
+            mbar_init(smem_u32(&bars->a_full[i]), kArrivals);
             mbar_init(smem_u32(&bars->a_empty[i]), 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->acc_full[i]), 1);
-            mbar_init(smem_u32(&bars->acc_empty[i]), 128);
+            mbar_init(smem_u32(&bars->acc_empty[i]), kArrivals);
         }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_w);
     if (warp == 2) {
-        tmem_alloc(smem_u32(&bars->tmem_base), 512);
-        tmem_relinquish();
+        if (kPair) { tmem_alloc_pair(smem_u32(&bars->tmem_base), 512); tmem_relinquish_pair(); }
+        else       { tmem_alloc(smem_u32(&bars->tmem_base), 512); tmem_relinquish(); }
     }
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
 
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
-            uint32_t it = 0;
+            uint32_t stage = 0, phase = 0;
             TileInfo ti;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                if (!tile_info(tile, tiles_per_utt, tlen, ulen, T, U1, ti)) continue;
-                for (int nc = 0; nc < NC; ++nc)
-                    for (int kb = 0; kb < KB; ++kb, ++it) {
-                        uint32_t s = it % num_b_stages, ph = (it / num_b_stages) & 1;
-                        mbar_wait(smem_u32(&bars->b_empty[s]), ph ^ 1);
-                        uint32_t full = smem_u32(&bars->b_full[s]);
-                        mbar_arrive_expect_tx(full, b_stage_tx);
-                        tma_load_2d(smem_u32(sB + (size_t)s * kBStageBytes), &tmap_w, kb * kBlockK,
-                                    nc * kChunkN, full);
+            for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+                if (!tile_info<kCtas>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
+                for (int nc = 0; nc < NC; ++nc) {
+                    const int n = min(kChunkN, V - nc * kChunkN);
+                    const int y = nc * kChunkN + (kPair ? (int)rank * (n >> 1) : 0);
+                    for (int kb = 0; kb < KB; ++kb) {
+                        mbar_wait(smem_u32(&bars->b_empty[stage]), phase ^ 1);
+                        const uint32_t full = smem_u32(&bars->b_full[stage]);
+                        const uint32_t dst = smem_u32(sB + (size_t)stage * kBBytes);
+                        if (kPair) {
+                            mbar_arrive_expect_tx_cluster(mapa_shared(full, 0), kBBytes);
+                            tma_load_2d_pair(dst, &tmap_w, kb * kBlockK, y, full);
+                        } else {
+                            mbar_arrive_expect_tx(full, kBBytes);
+                            tma_load_2d(dst, &tmap_w, kb * kBlockK, y, full);
+                        }
+                        if (++stage == kBStages) { stage = 0; phase ^= 1; }
                     }
+                }
             }
         }
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
-        if (lane == 0) {
-            uint32_t it = 0, cc = 0, tl = 0;
+        // ===================== MMA issuer (whole warp loops, one elected lane issues) =====================
+        if (leader) {
+            uint32_t stage = 0, phase = 0, cc = 0, tl = 0;
+            constexpr uint32_t kDescHi = (1024u >> 4) | (1u << 14) | (2u << 29);
+            const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
+            const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
             TileInfo ti;
-            for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                if (!tile_info(tile, tiles_per_utt, tlen, ulen, T, U1, ti)) continue;
+            for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+                if (!tile_info<kCtas>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
                 for (int nc = 0; nc < NC; ++nc, ++cc) {
                     const uint32_t buf = cc & 1;
-                    mbar_wait(smem_u32(&bars->acc_empty[buf]), ((cc >> 1) & 1) ^ 1);
-                    tc_fence_after();
+                    if (kPair) mbar_wait_cluster(smem_u32(&bars->acc_empty[buf]), ((cc >> 1) & 1) ^ 1);
+                    else       mbar_wait(smem_u32(&bars->acc_empty[buf]), ((cc >> 1) & 1) ^ 1);
                     const int n = min(kChunkN, V - nc * kChunkN);
-                    const uint32_t idesc = umma_idesc_bf16(kTileM, n);
+                    const uint32_t idesc = umma_idesc_bf16(kCtas * kTileM, n);
                     const uint32_t d_tmem = tmem_base + buf * kChunkN;
-                    for (int kb = 0; kb < KB; ++kb, ++it) {
-                        if (nc == 0) mbar_wait(smem_u32(&bars->a_full[kb]), tl & 1);
-                        uint32_t s = it % num_b_stages, ph = (it / num_b_stages) & 1;
-                        mbar_wait(smem_u32(&bars->b_full[s]), ph);
-                        tc_fence_after();
-                        const uint32_t a_addr = smem_u32(sA + (size_t)kb * kABlockBytes);
-                        const uint32_t b_addr = smem_u32(sB + (size_t)s * kBStageBytes);
-#pragma unroll
-                        for (int k16 = 0; k16 < kBlockK / 16; ++k16) {
-                            umma_bf16(d_tmem, umma_desc_k_sw128(a_addr + k16 * 32),
-                                      umma_desc_k_sw128(b_addr + k16 * 32), idesc,
-                                      (kb | k16) != 0);
+                    for (int kb = 0; kb < KB; ++kb) {
+                        if (nc == 0) {
+                            if (kPair) mbar_wait_cluster(smem_u32(&bars->a_full[kb]), tl & 1);
+                            else       mbar_wait(smem_u32(&bars->a_full[kb]), tl & 1);
                         }
-                        umma_commit(smem_u32(&bars->b_empty[s]));
-                        if (nc == NC - 1) umma_commit(smem_u32(&bars->a_empty[kb]));
+                        if (kPair) mbar_wait_cluster(smem_u32(&bars->b_full[stage]), phase);
+                        else       mbar_wait(smem_u32(&bars->b_full[stage]), phase);
+                        tc_fence_after();
+                        if (elect_one_sync()) {
+                            const uint32_t a_lo = a_lo0 + kb * (kABlockBytes >> 4);
+                            const uint32_t b_lo = b_lo0 + stage * (kBBytes >> 4);
+#pragma unroll
+                            for (int k16 = 0; k16 < kBlockK / 16; ++k16) {
+                                const uint64_t ad = ((uint64_t)kDescHi << 32) | (a_lo + 2 * k16);
+                                const uint64_t bd = ((uint64_t)kDescHi << 32) | (b_lo + 2 * k16);
+                                if (kPair) umma_bf16_pair(d_tmem, ad, bd, idesc, (kb | k16) != 0);
+                                else       umma_bf16(d_tmem, ad, bd, idesc, (kb | k16) != 0);
+                            }
+                            if (kPair) {
+                                umma_commit_pair(smem_u32(&bars->b_empty[stage]));
+                                if (nc == NC - 1) umma_commit_pair(smem_u32(&bars->a_empty[kb]));
+                                if (kb == KB - 1) umma_commit_pair(smem_u32(&bars->acc_full[buf]));
+                            } else {
+                                umma_commit(smem_u32(&bars->b_empty[stage]));
+                                if (nc == NC - 1) umma_commit(smem_u32(&bars->a_empty[kb]));
+                                if (kb == KB - 1) umma_commit(smem_u32(&bars->acc_full[buf]));
+                            }
+                        }
+                        __syncwarp();
+                        if (++stage == kBStages) { stage = 0; phase ^= 1; }
                     }
-                    umma_commit(smem_u32(&bars->acc_full[buf]));
                 }
                 ++tl;
             }
@@ -180,11 +320,17 @@ joint_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* _
         // ===================== epilogue: online LSE over vocab chunks =====================
         const int q = warp & 3;
         const int row = q * 32 + lane;
-        const int etid = threadIdx.x - 128;  // 0..127
+        const int etid = threadIdx.x - 128;
         uint32_t cc = 0;
         TileInfo ti;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            if (!tile_info(tile, tiles_per_utt, tlen, ulen, T, U1, ti)) continue;
+        uint32_t acc_empty_addr[2];
+        acc_empty_addr[0] = kPair ? mapa_shared(smem_u32(&bars->acc_empty[0]), 0) : smem_u32(&bars->acc_empty[0]);
+        acc_empty_addr[1] = kPair ? mapa_shared(smem_u32(&bars->acc_empty[1]), 0) : smem_u32(&bars->acc_empty[1]);
+        // bias of the first chunk of the first tile
+        float nb0 = etid < V ? __ldg(b_out + etid) : 0.f;
+        float nb1 = etid + 128 < V ? __ldg(b_out + etid + 128) : 0.f;
+        for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+            if (!tile_info<kCtas>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
             const int m = ti.first_cell + row;
             const bool valid = m < ti.n_cells;
             const int t = valid ? m / ti.U1b : 0;
@@ -196,47 +342,36 @@ joint_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* _
             for (int nc = 0; nc < NC; ++nc, ++cc) {
                 const uint32_t buf = cc & 1;
                 const int n = min(kChunkN, V - nc * kChunkN);
-                // stage this chunk's bias (double-buffered with the accumulator buffer)
                 float* bias = s_bias + buf * kChunkN;
-                for (int i = etid; i < n; i += 128) bias[i] = __ldg(b_out + nc * kChunkN + i);
+                bias[etid] = nb0;
+                bias[etid + 128] = nb1;
+                {   // prefetch the next chunk's bias (wraps to chunk 0 for the next tile)
+                    const int nn = (nc + 1 == NC) ? 0 : nc + 1;
+                    const int i0 = nn * kChunkN + etid;
+                    nb0 = i0 < V ? __ldg(b_out + i0) : 0.f;
+                    nb1 = i0 + 128 < V ? __ldg(b_out + i0 + 128) : 0.f;
+                }
                 named_bar_sync(1, 128);
                 mbar_wait(smem_u32(&bars->acc_full[buf]), (cc >> 1) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kChunkN;
-                for (int g = 0; g < n / 32; ++g) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(taddr + g * 32, r);
+                const int G = n >> 5;
+                uint32_t ra[32], rb[32];
+                tmem_ld_32x32b_x32(taddr, ra);
+                for (int g = 0; g < G; g += 2) {
                     tmem_wait_ld();
-                    const int v0 = nc * kChunkN + g * 32;
-                    float x[32];
-                    float gmax = kNegInf;
-#pragma unroll
-                    for (int i = 0; i < 32; i += 4) {
-                        float4 bv = *reinterpret_cast<const float4*>(bias + g * 32 + i);
-                        x[i + 0] = __uint_as_float(r[i + 0]) + bv.x;
-                        x[i + 1] = __uint_as_float(r[i + 1]) + bv.y;
-                        x[i + 2] = __uint_as_float(r[i + 2]) + bv.z;
-                        x[i + 3] = __uint_as_float(r[i + 3]) + bv.w;
-                        gmax = fmaxf(gmax, fmaxf(fmaxf(x[i], x[i + 1]), fmaxf(x[i + 2], x[i + 3])));
+                    if (g + 1 < G) tmem_ld_32x32b_x32(taddr + (g + 1) * 32, rb);
+                    lse_group(ra, bias + g * 32, nc * kChunkN + g * 32, lab, blank, run_m, run_s, zb, zl);
+                    if (g + 1 < G) {
+                        tmem_wait_ld();
+                        if (g + 2 < G) tmem_ld_32x32b_x32(taddr + (g + 2) * 32, ra);
+                        lse_group(rb, bias + (g + 1) * 32, nc * kChunkN + (g + 1) * 32, lab, blank, run_m,
+                                  run_s, zb, zl);
                     }
-                    const float new_m = fmaxf(run_m, gmax);
-                    const float neg_m2 = -new_m * kLog2e;
-                    float acc = 0.f;
-                    const int dl = lab - v0;
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) {
-                        acc += ex2_approx(fmaf(x[i], kLog2e, neg_m2));
-                        zl = (i == dl) ? x[i] : zl;
-                    }
-                    if (blank >= v0 && blank < v0 + 32) {  // warp-uniform
-#pragma unroll
-                        for (int i = 0; i < 32; ++i) zb = (i == blank - v0) ? x[i] : zb;
-                    }
-                    run_s = run_s * ex2_approx((run_m - new_m) * kLog2e) + acc;
-                    run_m = new_m;
                 }
                 tc_fence_before();
-                mbar_arrive(smem_u32(&bars->acc_empty[buf]));
+                if (kPair) mbar_arrive_cluster(acc_empty_addr[buf]);
+                else       mbar_arrive(acc_empty_addr[buf]);
             }
             if (valid) {
                 const float l = run_m + kLn2 * log2f(run_s);
@@ -246,14 +381,14 @@ joint_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* _
             }
         }
     } else if (warp >= 8) {
-        // ===================== A producers: h = tanh(enc + dec) -> bf16, swizzled =====================
+        // ===================== A producers =====================
         const int pw = warp - 8;
         const int c = lane & 7;        // 16-byte chunk (8 bf16) inside the 128-byte row
         const int rsub = lane >> 3;    // 4 rows per warp pass
         uint32_t tl = 0;
         TileInfo ti;
-        for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            if (!tile_info(tile, tiles_per_utt, tlen, ulen, T, U1, ti)) continue;
+        for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+            if (!tile_info<kCtas>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
             uint32_t eoff[8], doff[8];  // element offsets of this lane's 8 rows
 #pragma unroll
             for (int p = 0; p < 8; ++p) {
@@ -265,44 +400,20 @@ joint_fwd_bf16_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* _
             }
             for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(smem_u32(&bars->a_empty[kb]), (tl & 1) ^ 1);
-                uint8_t* blk = sA + (size_t)kb * kABlockBytes;
-#pragma unroll
-                for (int half = 0; half < 2; ++half) {
-                    float4 e0[4], e1[4], d0[4], d1[4];
-#pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        const float* ep = enc + eoff[half * 4 + p] + kb * kBlockK;
-                        const float* dp = dec + doff[half * 4 + p] + kb * kBlockK;
-                        e0[p] = __ldg(reinterpret_cast<const float4*>(ep));
-                        e1[p] = __ldg(reinterpret_cast<const float4*>(ep) + 1);
-                        d0[p] = __ldg(reinterpret_cast<const float4*>(dp));
-                        d1[p] = __ldg(reinterpret_cast<const float4*>(dp) + 1);
-                    }
-#pragma unroll
-                    for (int p = 0; p < 4; ++p) {
-                        const int row = pw * 32 + (half * 4 + p) * 4 + rsub;
-                        uint4 o;
-                        o.x = pack_bf16x2(tanh_approx(e0[p].x + d0[p].x), tanh_approx(e0[p].y + d0[p].y));
-                        o.y = pack_bf16x2(tanh_approx(e0[p].z + d0[p].z), tanh_approx(e0[p].w + d0[p].w));
-                        o.z = pack_bf16x2(tanh_approx(e1[p].x + d1[p].x), tanh_approx(e1[p].y + d1[p].y));
-                        o.w = pack_bf16x2(tanh_approx(e1[p].z + d1[p].z), tanh_approx(e1[p].w + d1[p].w));
-                        // canonical K-major SW128: 16-byte chunk index XOR (row mod 8)
-                        uint8_t* dst = blk + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
-                        *reinterpret_cast<uint4*>(dst) = o;
-                    }
-                }
+                produce_h_block(enc, dec, eoff, doff, kb, pw, rsub, c, sA + (size_t)kb * kABlockBytes);
                 fence_proxy_async_smem();
-                mbar_arrive(smem_u32(&bars->a_full[kb]));
+                if (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->a_full[kb]), 0));
+                else       mbar_arrive(smem_u32(&bars->a_full[kb]));
             }
             ++tl;
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (kPair) cluster_sync_all(); else __syncthreads();
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        if (kPair) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -385,24 +496,44 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     f32_to_bf16_kernel<<<ceil_div(nw, 4 * 256), 256, 0, st>>>(w_out, w_bf16, nw);
     EMO_CHECK_LAUNCH("f32_to_bf16_kernel");
 
-    CUtensorMap tmap;
-    rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, (uint32_t)min(kChunkN, V));
-    if (rc) return rc;
-
     const int KB = J / kBlockK;
     const size_t a_bytes = (size_t)KB * kABlockBytes;
-    const size_t fixed = sizeof(Barriers) + 2 * kChunkN * sizeof(float);
-    int stages = (int)min((size_t)kMaxBStages, (kSmemLimit - a_bytes - fixed) / kBStageBytes);
-    EMO_REQUIRE(stages >= 2, EMO_UNSUPPORTED_SHAPE, "joint_fwd(bf16): not enough shared memory");
-    const size_t smem = a_bytes + (size_t)stages * kBStageBytes + fixed;
-    EMO_CUDA(cudaFuncSetAttribute(joint_fwd_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  (int)smem));
+    static const bool use_single = getenv("EMO_FWD_SINGLE_CTA") != nullptr;  // A/B switch while tuning
+    CUtensorMap tmap;
+    if (!use_single) {
+        rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, Cfg<2>::kBRows);
+        if (rc) return rc;
+        const size_t smem = a_bytes + (size_t)Cfg<2>::kBStages * Cfg<2>::kBRows * kBlockK * 2 +
+                            sizeof(FwdBarriers<2>) + 2 * kChunkN * sizeof(float);
+        EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_fwd(bf16): shared memory");
+        EMO_CUDA(cudaFuncSetAttribute(joint_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int ptiles = B * ceil_div((size_t)T * U1, 2 * kTileM);
+        const int pairs = min(ptiles, sm_count() / 2);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        EMO_CUDA(cudaLaunchKernelEx(&cfg, joint_fwd_kernel<2>, tmap, enc_proj, dec_proj, b_out, labels, tlen,
+                                    ulen, B, T, U1, J, V, blank, lp2, lse));
+        EMO_CHECK_LAUNCH("joint_fwd_kernel<pair>");
+        return EMO_OK;
+    }
+    rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, Cfg<1>::kBRows);
+    if (rc) return rc;
+    const size_t smem = a_bytes + (size_t)Cfg<1>::kBStages * Cfg<1>::kBRows * kBlockK * 2 +
+                        sizeof(FwdBarriers<1>) + 2 * kChunkN * sizeof(float);
+    EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_fwd(bf16): shared memory");
+    EMO_CUDA(cudaFuncSetAttribute(joint_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = B * ceil_div((size_t)T * U1, kTileM);
-    const int grid = min(tiles, sm_count());
-    joint_fwd_bf16_kernel<<<grid, kThreads, smem, st>>>(tmap, enc_proj, dec_proj, b_out, labels, tlen,
-                                                        ulen, B, T, U1, J, V, blank, stages,
-                                                        (uint32_t)(min(kChunkN, V) * kBlockK * 2), lp2, lse);
-    EMO_CHECK_LAUNCH("joint_fwd_bf16_kernel");
+    joint_fwd_kernel<1><<<min(tiles, sm_count()), kThreads, smem, st>>>(tmap, enc_proj, dec_proj, b_out, labels,
+                                                                        tlen, ulen, B, T, U1, J, V, blank, lp2, lse);
+    EMO_CHECK_LAUNCH("joint_fwd_kernel<single>");
     return EMO_OK;
 }
 
