@@ -19,56 +19,10 @@
 //                              128B-swizzle layout, one 64-wide K block at a time so the MMAs of
 //                              the next tile start as soon as block 0 is rewritten
 // The h tile (128 x J bf16) stays resident in shared memory for all vocab chunks of the tile.
-#include <stdlib.h>
-
-#include "common.cuh"
-#include "tc_common.cuh"
+#include "joint_tc.cuh"
 
 namespace emo {
 namespace {
-
-using namespace tc;
-
-constexpr int kTileM = 128;          // cells per tile
-constexpr int kBlockK = 64;          // bf16 elements per 128-byte swizzle row
-constexpr int kChunkN = 256;         // vocab columns per accumulator buffer
-constexpr int kMaxKBlocks = 8;       // J <= 512
-constexpr int kABlockBytes = kTileM * kBlockK * 2;    // 16 KiB
-constexpr int kThreads = 384;
-constexpr int kSmemLimit = 232448;                    // 227 KiB opt-in maximum per CTA
-constexpr float kLog2e = 1.4426950408889634f;
-constexpr float kLn2 = 0.6931471805599453f;
-
-struct TileInfo {
-    int b, first_cell, n_cells, U1b;  // n_cells = valid cells of the utterance
-};
-
-// kCtas = 1: one CTA per 128-cell tile.  kCtas = 2: a CTA pair (cluster of 2, cta_group::2) per
-// 256-cell tile, 128 cells per CTA; `rank` selects this CTA's half.  Both CTAs of a pair get the
-// same answer.
-template <int kCtas>
-__device__ __forceinline__ bool tile_info(int tile, int tiles_per_utt, uint32_t rank, const int* tlen,
-                                          const int* ulen, int T, int U1, TileInfo& ti) {
-    ti.b = tile / tiles_per_utt;
-    int i = tile - ti.b * tiles_per_utt;
-    int T_b = min(max(__ldg(tlen + ti.b), 1), T);
-    ti.U1b = min(max(__ldg(ulen + ti.b), 0), U1 - 1) + 1;
-    ti.n_cells = T_b * ti.U1b;
-    ti.first_cell = i * (kCtas * kTileM) + (int)rank * kTileM;
-    return i * (kCtas * kTileM) < ti.n_cells;
-}
-
-__global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst,
-                                   size_t n) {
-    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i + 3 < n) {
-        float4 v = *reinterpret_cast<const float4*>(src + i);
-        uint2 o = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-        *reinterpret_cast<uint2*>(dst + i) = o;
-    } else {
-        for (; i < n; ++i) dst[i] = __float2bfloat16_rn(src[i]);
-    }
-}
 
 // ---- per-variant constants ----
 template <int kCtas> struct Cfg;
@@ -89,54 +43,6 @@ struct __align__(16) FwdBarriers {
     uint32_t tmem_base;
     uint32_t pad[3];
 };
-
-// A-operand producer shared by the forward and backward kernels: this warp's 32 rows of the
-// 128-row tile, K block kb.  h = tanh(enc + dec) -> bf16 -> canonical K-major SW128 layout
-// (16-byte chunk index XOR (row mod 8)).
-__device__ __forceinline__ void produce_h_block(const float* __restrict__ enc,
-                                                const float* __restrict__ dec,
-                                                const uint32_t (&eoff)[8], const uint32_t (&doff)[8],
-                                                int kb, int pw, int rsub, int c, uint8_t* blk) {
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        float4 e0[4], e1[4], d0[4], d1[4];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const float* ep = enc + eoff[half * 4 + p] + kb * kBlockK;
-            const float* dp = dec + doff[half * 4 + p] + kb * kBlockK;
-            e0[p] = __ldg(reinterpret_cast<const float4*>(ep));
-            e1[p] = __ldg(reinterpret_cast<const float4*>(ep) + 1);
-            d0[p] = __ldg(reinterpret_cast<const float4*>(dp));
-            d1[p] = __ldg(reinterpret_cast<const float4*>(dp) + 1);
-        }
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int row = pw * 32 + (half * 4 + p) * 4 + rsub;
-            uint4 o;
-            o.x = pack_bf16x2(tanh_approx(e0[p].x + d0[p].x), tanh_approx(e0[p].y + d0[p].y));
-            o.y = pack_bf16x2(tanh_approx(e0[p].z + d0[p].z), tanh_approx(e0[p].w + d0[p].w));
-            o.z = pack_bf16x2(tanh_approx(e1[p].x + d1[p].x), tanh_approx(e1[p].y + d1[p].y));
-            o.w = pack_bf16x2(tanh_approx(e1[p].z + d1[p].z), tanh_approx(e1[p].w + d1[p].w));
-            uint8_t* dst = blk + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
-            *reinterpret_cast<uint4*>(dst) = o;
-        }
-    }
-}
-
-// x[d] for a per-thread d in [0,32) without dynamic register indexing: five select levels
-__device__ __forceinline__ float mux32(const float (&x)[32], int d) {
-    float a[16], b[8], c[4], e[2];
-    const bool s4 = d & 16, s3 = d & 8, s2 = d & 4, s1 = d & 2, s0 = d & 1;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) a[i] = s4 ? x[i + 16] : x[i];
-#pragma unroll
-    for (int i = 0; i < 8; ++i) b[i] = s3 ? a[i + 8] : a[i];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) c[i] = s2 ? b[i + 4] : b[i];
-#pragma unroll
-    for (int i = 0; i < 2; ++i) e[i] = s1 ? c[i + 2] : c[i];
-    return s0 ? e[1] : e[0];
-}
 
 // One 32-column group of logits of this thread's row: bias add, online (max, sum exp2), capture of
 // the blank / label logit.
@@ -417,66 +323,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __rest
     }
 }
 
-// ---- host side ----
-typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
-                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
-                                    const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64_t outer,
-                      uint32_t box_inner, uint32_t box_outer) {
-    cuuint64_t dims[2] = {inner, outer};
-    cuuint64_t strides[1] = {inner * sizeof(__nv_bfloat16)};
-    cuuint32_t box[2] = {box_inner, box_outer};
-    cuuint32_t estr[2] = {1, 1};
-    // libcuda is reached through the runtime (no link-time dependency on libcuda.so.1, so the
-    // library also loads on a machine without a driver)
-    static PFN_encodeTiled encode = nullptr;
-    if (!encode) {
-        void* fn = nullptr;
-        cudaDriverEntryPointQueryResult qres;
-        cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
-        if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn) {
-            set_error("cuTensorMapEncodeTiled entry point unavailable (%s)", cudaGetErrorName(e));
-            return EMO_NO_DEVICE;
-        }
-        encode = (PFN_encodeTiled)fn;
-    }
-    CUresult r = encode(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims,
-                        strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                        CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) {
-        set_error("cuTensorMapEncodeTiled failed: CUresult %d", (int)r);
-        return EMO_LAUNCH_FAILURE;
-    }
-    return EMO_OK;
-}
-
-int check_bf16_shape(int B, int T, int U1, int J, int V, int blank) {
-    EMO_REQUIRE(B > 0 && T > 0 && U1 > 0 && J > 0 && V > 0, EMO_BAD_ARG, "joint(bf16): bad sizes");
-    EMO_REQUIRE(blank >= 0 && blank < V, EMO_BAD_ARG, "joint(bf16): blank %d outside [0,%d)", blank, V);
-    EMO_REQUIRE(J % kBlockK == 0 && J <= kMaxKBlocks * kBlockK, EMO_UNSUPPORTED_SHAPE,
-                "joint(bf16): joint_hidden_size %d must be a multiple of 64 and <= 512 "
-                "(use precision fp32 for other sizes)", J);
-    EMO_REQUIRE(V % 32 == 0, EMO_UNSUPPORTED_SHAPE,
-                "joint(bf16): vocab %d must be a multiple of 32 (use precision fp32)", V);
-    EMO_REQUIRE((long long)B * T * J < (1ll << 31) && (long long)B * U1 * J < (1ll << 31),
-                EMO_UNSUPPORTED_SHAPE, "joint(bf16): projected streams exceed 2^31 elements");
-    return EMO_OK;
-}
-
 }  // namespace
-
-size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V) {
-    size_t w = align_up((size_t)V * J * sizeof(__nv_bfloat16), 256);
-    if (op == EMO_OP_RNNT_JOINT_BWD) return w + joint_f32_workspace(op, B, T, U1, J, V);
-    return w;
-}
-
-int joint_bf16_launches(int op, int B, int T, int U1, int J, int V) {
-    if (op == EMO_OP_RNNT_JOINT_BWD) return joint_f32_launches(op, B, T, U1, J, V);
-    return 2;  // weight cast + fused joint
-}
 
 int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
                    const float* b_out, const int* labels, const int* tlen, const int* ulen, int B,
@@ -535,20 +382,6 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
                                                                         tlen, ulen, B, T, U1, J, V, blank, lp2, lse);
     EMO_CHECK_LAUNCH("joint_fwd_kernel<single>");
     return EMO_OK;
-}
-
-// Interim: the bf16 backward still runs the fp32 slab path (tcgen05 backward is the next milestone).
-int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
-                   const float* b_out, const int* labels, const int* tlen, const int* ulen,
-                   const float* lse, const float* gamma2, const float* grad_cost, int B, int T,
-                   int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
-                   float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st) {
-    size_t w = align_up((size_t)V * J * sizeof(__nv_bfloat16), 256);
-    EMO_REQUIRE(ws && ws_bytes >= joint_bf16_workspace(EMO_OP_RNNT_JOINT_BWD, B, T, U1, J, V),
-                EMO_WORKSPACE_TOO_SMALL, "joint_bwd(bf16): workspace too small");
-    return joint_bwd_f32(enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, lse, gamma2,
-                         grad_cost, B, T, U1, J, V, blank, d_enc_proj, d_dec_proj, d_w_out, d_b_out,
-                         (char*)ws + w, ws_bytes - w, st);
 }
 
 }  // namespace emo
