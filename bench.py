@@ -169,13 +169,15 @@ def run_ours_rnnt(args, w, rank, world, dev):
         ws = torch.empty(_lib.workspace_bytes(0, 1, B, T, U1, J, V), dtype=torch.uint8, device=dev)
         lp2 = torch.empty(B, T, U1, 2, device=dev)
         lse = torch.empty(B, T, U1, device=dev)
+        hc = torch.empty(_lib.workspace_bytes(_lib.OP_RNNT_JOINT_HCACHE, 1, B, T, U1, J, V), dtype=torch.uint8, device=dev)
         wo, bo = wl.output.weight.detach().contiguous(), wl.output.bias.detach().contiguous()
         p = lambda t: ctypes.c_void_p(t.data_ptr())
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
         def call():
             rc = lib.emo_rnnt_joint_fwd(p(enc_proj), p(dec_proj), p(wo), p(bo), p(resident[2]), p(resident[3]),
-                                        p(resident[4]), B, T, U1, J, V, 0, 1, p(lp2), p(lse), p(ws), ws.numel(), st)
+                                        p(resident[4]), B, T, U1, J, V, 0, 1, p(lp2), p(lse), p(hc), hc.numel(),
+                                        p(ws), ws.numel(), st)
             _lib.check(rc, "emo_rnnt_joint_fwd")
         for _ in range(3):
             call()

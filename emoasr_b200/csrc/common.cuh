@@ -92,11 +92,12 @@ int joint_f32_launches(int op, int B, int T, int U1, int J, int V);
 
 int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
                    const float* b_out, const int* labels, const int* tlen, const int* ulen, int B,
-                   int T, int U1, int J, int V, int blank, float* lp2, float* lse, void* ws,
-                   size_t ws_bytes, cudaStream_t st);
+                   int T, int U1, int J, int V, int blank, float* lp2, float* lse, void* hcache,
+                   size_t hcache_bytes, void* ws, size_t ws_bytes, cudaStream_t st);
 int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
                    const float* b_out, const int* labels, const int* tlen, const int* ulen,
-                   const float* lse, const float* gamma2, const float* grad_cost, int B, int T,
+                   const float* lse, const float* gamma2, const float* grad_cost,
+                   const void* hcache, size_t hcache_bytes, int B, int T,
                    int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
                    float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V);

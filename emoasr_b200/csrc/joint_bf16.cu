@@ -39,6 +39,7 @@ template <int kCtas>
 struct __align__(16) FwdBarriers {
     uint64_t b_full[Cfg<kCtas>::kBStages], b_empty[Cfg<kCtas>::kBStages];
     uint64_t a_full[kMaxKBlocks], a_empty[kMaxKBlocks];
+    uint64_t h_ready[kMaxKBlocks];  // local: this CTA's 128 producer threads have written block kb
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     uint32_t pad[3];
@@ -92,7 +93,8 @@ __device__ __forceinline__ void lse_group(const uint32_t (&r)[32], const float* 
 //   b_empty / a_empty / acc_full are signalled in BOTH CTAs by a multicast tcgen05.commit.
 template <int kCtas>
 __global__ void __launch_bounds__(kThreads, 1)
-joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ enc,
+joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
+                 int store_h, const float* __restrict__ enc,
                  const float* __restrict__ dec, const float* __restrict__ b_out,
                  const int* __restrict__ labels, const int* __restrict__ tlen,
                  const int* __restrict__ ulen, int B, int T, int U1, int J, int V, int blank,
@@ -126,7 +128,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __rest
         }
         for (int i = 0; i < kMaxKBlocks; ++i) {
             mbar_init(smem_u32(&bars->a_full[i]), kArrivals);
-            mbar_init(smem_u32(&bars->a_empty[i]), 1);
+            mbar_init(smem_u32(&bars->a_empty[i]), store_h ? 2 : 1);  // MMA commit (+ h store done)
+            mbar_init(smem_u32(&bars->h_ready[i]), 128);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->acc_full[i]), 1);
@@ -134,7 +137,10 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __rest
         }
         fence_barrier_init();
     }
-    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_w);
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_h);
+    }
     if (warp == 2) {
         if (kPair) { tmem_alloc_pair(smem_u32(&bars->tmem_base), 512); tmem_relinquish_pair(); }
         else       { tmem_alloc(smem_u32(&bars->tmem_base), 512); tmem_relinquish(); }
@@ -222,6 +228,26 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __rest
                 ++tl;
             }
         }
+    } else if (warp == 3) {
+        // ===================== h-cache writer: TMA store of every finished h block =====================
+        if (store_h && lane == 0) {
+            const int tpu = tiles128_per_utt(T, U1);
+            uint32_t tl = 0;
+            TileInfo ti;
+            for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+                if (!tile_info<kCtas>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
+                const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(smem_u32(&bars->h_ready[kb]), tl & 1);
+                    tma_store_2d(&tmap_h, smem_u32(sA + (size_t)kb * kABlockBytes), kb * kBlockK, row0);
+                    tma_store_commit();
+                    tma_store_wait_read<0>();
+                    mbar_arrive(smem_u32(&bars->a_empty[kb]));
+                }
+                ++tl;
+            }
+            tma_store_wait_all<0>();
+        }
     } else if (warp >= 4 && warp < 8) {
         // ===================== epilogue: online LSE over vocab chunks =====================
         const int q = warp & 3;
@@ -308,6 +334,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __rest
                 mbar_wait(smem_u32(&bars->a_empty[kb]), (tl & 1) ^ 1);
                 produce_h_block(enc, dec, eoff, doff, kb, pw, rsub, c, sA + (size_t)kb * kABlockBytes);
                 fence_proxy_async_smem();
+                if (store_h) mbar_arrive(smem_u32(&bars->h_ready[kb]));
                 if (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->a_full[kb]), 0));
                 else       mbar_arrive(smem_u32(&bars->a_full[kb]));
             }
@@ -327,8 +354,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __rest
 
 int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
                    const float* b_out, const int* labels, const int* tlen, const int* ulen, int B,
-                   int T, int U1, int J, int V, int blank, float* lp2, float* lse, void* ws,
-                   size_t ws_bytes, cudaStream_t st) {
+                   int T, int U1, int J, int V, int blank, float* lp2, float* lse, void* hcache,
+                   size_t hcache_bytes, void* ws, size_t ws_bytes, cudaStream_t st) {
     EMO_REQUIRE(enc_proj && dec_proj && w_out && b_out && labels && tlen && ulen && lp2 && lse && ws,
                 EMO_BAD_ARG, "joint_fwd(bf16): null pointer");
     int rc = check_bf16_shape(B, T, U1, J, V, blank);
@@ -346,7 +373,15 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     const int KB = J / kBlockK;
     const size_t a_bytes = (size_t)KB * kABlockBytes;
     static const bool use_single = getenv("EMO_FWD_SINGLE_CTA") != nullptr;  // A/B switch while tuning
-    CUtensorMap tmap;
+    CUtensorMap tmap, tmap_h;
+    const int store_h = hcache != nullptr;
+    if (store_h) {
+        EMO_REQUIRE(hcache_bytes >= hcache_bytes_for(B, T, U1, J) && ((uintptr_t)hcache & 255) == 0,
+                    EMO_WORKSPACE_TOO_SMALL, "joint_fwd(bf16): h cache too small or misaligned");
+        rc = make_tmap_bf16_2d(&tmap_h, hcache, (uint64_t)J,
+                               (uint64_t)B * tiles128_per_utt(T, U1) * kTileM, kBlockK, kTileM);
+        if (rc) return rc;
+    }
     if (!use_single) {
         rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, Cfg<2>::kBRows);
         if (rc) return rc;
@@ -366,8 +401,9 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        EMO_CUDA(cudaLaunchKernelEx(&cfg, joint_fwd_kernel<2>, tmap, enc_proj, dec_proj, b_out, labels, tlen,
-                                    ulen, B, T, U1, J, V, blank, lp2, lse));
+        if (!store_h) tmap_h = tmap;
+        EMO_CUDA(cudaLaunchKernelEx(&cfg, joint_fwd_kernel<2>, tmap, tmap_h, store_h, enc_proj, dec_proj, b_out,
+                                    labels, tlen, ulen, B, T, U1, J, V, blank, lp2, lse));
         EMO_CHECK_LAUNCH("joint_fwd_kernel<pair>");
         return EMO_OK;
     }
@@ -378,8 +414,10 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_fwd(bf16): shared memory");
     EMO_CUDA(cudaFuncSetAttribute(joint_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = B * ceil_div((size_t)T * U1, kTileM);
-    joint_fwd_kernel<1><<<min(tiles, sm_count()), kThreads, smem, st>>>(tmap, enc_proj, dec_proj, b_out, labels,
-                                                                        tlen, ulen, B, T, U1, J, V, blank, lp2, lse);
+    if (!store_h) tmap_h = tmap;
+    joint_fwd_kernel<1><<<min(tiles, sm_count()), kThreads, smem, st>>>(tmap, tmap_h, store_h, enc_proj, dec_proj,
+                                                                        b_out, labels, tlen, ulen, B, T, U1, J, V,
+                                                                        blank, lp2, lse);
     EMO_CHECK_LAUNCH("joint_fwd_kernel<single>");
     return EMO_OK;
 }

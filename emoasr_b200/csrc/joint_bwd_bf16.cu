@@ -3,22 +3,26 @@
 // The dense gradient of the logits
 //     dz[cell,v] = g_b * (gamma * softmax(z)[v] - gamma_blank 1[v=blank] - gamma_label 1[v=label])
 // is recomputed tile by tile from (h, w_out, lse) and consumed straight from shared memory by the
-// MMAs that need it; it never reaches global memory.  Two kernels share one skeleton:
+// MMAs that need it; it never reaches global memory.  h = tanh(enc+dec) comes from the bf16 h
+// cache the forward kernel wrote (TMA loads, no tanh / fp32 gathers here).  Two kernels:
 //
-//   kDW = false  "dh kernel", cell-stationary like the forward: for a 128-cell tile and one
-//                J-part (<= 256 hidden units) at a time, loop over 128-wide vocab chunks:
-//                  z = h W_c^T -> dz (bf16, smem) -> dh_part += dz W_c[:, part]
-//                then dpre = dh (1 - h^2) is written as bf16 (B,T,U1,J) for the two axis
-//                reductions (d_enc_proj = sum_u, d_dec_proj = sum_t) done by small kernels.
-//   kDW = true   "dW kernel", one (vocab chunk, J-part) role per CTA, persistent over cell tiles:
-//                  z = h W_c^T -> dz -> dW[c, part] += dz^T h[:, part]      (accumulates in TMEM
-//                over ALL tiles of the CTA, flushed once with red.global.add.v4.f32); the same
-//                CTAs produce d_b_out = column sums of dz.
+//   dh kernel   cell-stationary CTA PAIR (cluster of 2, tcgen05 cta_group::2, 256 cells per pair
+//               tile).  Per J-part (<= 256 hidden units) loop over 128-wide vocab chunks:
+//                  z = h W_c^T (M=256) -> dz (bf16, smem) -> dh_part += dz W_c[:, part]
+//               then dpre = dh (1 - h^2) is written as bf16 (B,T,U1,J) for the two axis reductions
+//               (d_enc_proj = sum_u, d_dec_proj = sum_t) done by small kernels.  The pair halves
+//               the w_out traffic per cell and the shared-memory operand traffic per MMA.
+//   dW kernel   one (vocab chunk, J-part) role per CTA, persistent over 128-cell tiles:
+//                  z = h W_c^T -> dz -> dW[c, part] += dz^T h[:, part]
+//               (accumulates in TMEM over ALL tiles of the CTA, flushed once with
+//               red.global.add.v4.f32); the same CTAs produce d_b_out = column sums of dz.
 //
-// Operand layouts: the h tile and the dz tile are stored once, rows = cells, 128-byte rows of 64
-// bf16, 128B swizzle.  Read as K-major they feed z = h W^T and dh = dz W; read as MN-major (same
-// bytes, different descriptor) they feed dW = dz^T h.  w_out tiles [128 v x 64 j] arrive by TMA and
-// are K-major B for z and MN-major B for dh.
+// Operand layouts: h and dz tiles are stored once, rows = cells, 128-byte rows of 64 bf16, 128B
+// swizzle.  Read as K-major they feed z = h W^T and dh = dz W; read as MN-major (same bytes,
+// different descriptor) they feed dW = dz^T h.  w_out tiles arrive by TMA and are K-major B for z
+// and MN-major B for dh.
+// Both kernels: warp 0 TMA producer, warp 1 MMA issuer, warp 2 TMEM allocator, warps 4-11 epilogue
+// (two warps per TMEM lane quadrant, each owning half of the columns of a chunk).
 // TMEM: columns [0,256) two z buffers of 128, columns [256,512) the dh / dW accumulator.
 #include "joint_tc.cuh"
 
@@ -26,21 +30,13 @@ namespace emo {
 namespace {
 
 constexpr int kBwdChunk = 128;                 // vocab columns per z chunk
-constexpr int kBwdStages = 4;                  // TMA ring
-constexpr int kBwdTileBytes = 128 * kBlockK * 2;   // [128 v x 64 j] bf16 = 16 KiB
+constexpr int kSlotBytes = 16384;              // one ring slot = one [128 x 64] bf16 tile
+constexpr int kDhSlots = 4;                    // dh kernel: w_out ring
+constexpr int kDwSlots = 4;                    // dW kernel: w_out ring
 constexpr int kDzBytes = 2 * kABlockBytes;     // [128 cells x 128 v] bf16 = 32 KiB
 constexpr int kPartBlocks = 4;                 // J-part = up to 4 K blocks = 256 hidden units
+constexpr int kEpiThreads = 256;
 constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO=1024, v1, SW128
-
-struct __align__(16) BwdBarriers {
-    uint64_t b_full[kBwdStages], b_empty[kBwdStages];
-    uint64_t a_full[kMaxKBlocks], a_empty[kMaxKBlocks];
-    uint64_t z_full[2], z_empty[2];
-    uint64_t dz_full, dz_empty;
-    uint64_t acc2_full, acc2_empty;
-    uint32_t tmem_base;
-    uint32_t pad[3];
-};
 
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
     return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
@@ -78,58 +74,470 @@ struct RowCtx {
     int lab;
 };
 
-template <bool kDW>
+__device__ __forceinline__ void load_row_ctx(RowCtx& rc, const TileInfo& ti, int row, int T, int U1,
+                                             int V, const int* __restrict__ labels,
+                                             const float* __restrict__ lse,
+                                             const float* __restrict__ gamma2,
+                                             const float* __restrict__ grad_cost) {
+    const int m = ti.first_cell + row;
+    rc.valid = m < ti.n_cells;
+    const int t = rc.valid ? m / ti.U1b : 0;
+    const int u = rc.valid ? m - t * ti.U1b : 0;
+    rc.cell = ((size_t)ti.b * T + t) * U1 + u;
+    rc.lab = -1;
+    rc.c2 = 0.f; rc.gg = 0.f; rc.corr_b = 0.f; rc.corr_l = 0.f;
+    if (rc.valid) {
+        const float g = __ldg(grad_cost + ti.b);
+        const float2 gm = __ldg(reinterpret_cast<const float2*>(gamma2) + rc.cell);
+        rc.c2 = -__ldg(lse + rc.cell) * kLog2e;
+        rc.gg = g * (gm.x + gm.y);
+        rc.corr_b = g * gm.x;
+        rc.corr_l = g * gm.y;
+        if (u < ti.U1b - 1)
+            rc.lab = min(max(__ldg(labels + (size_t)ti.b * (U1 - 1) + u), 0), V - 1);
+    }
+}
+
+// One z chunk (TMEM, this thread's row) -> dz (bf16) for the two 32-column groups this thread owns
+// (column half `hf` of the 128-wide chunk), written into the shared dz tile [128 cells x 128 v]
+// (two K-major SW128 atoms).  kColSum: also accumulate the per-column sums (d_b_out).
+template <bool kColSum>
+__device__ __forceinline__ void dz_from_z(uint32_t taddr, const float* __restrict__ bias, int n, int v0c,
+                                          int hf, int row, int lane, const RowCtx& rc, int blank,
+                                          uint8_t* sDz, uint32_t dz_empty_bar, uint32_t dz_empty_parity,
+                                          float (&colsum)[2], float* __restrict__ d_b_out) {
+    const int g0 = hf * 2;
+    if (g0 * 32 >= n) return;
+    const bool two = (g0 + 1) * 32 < n;
+    uint32_t r0[32], r1[32];
+    tmem_ld_32x32b_x32(taddr + g0 * 32, r0);
+    if (two) tmem_ld_32x32b_x32(taddr + g0 * 32 + 32, r1);
+    tmem_wait_ld();
+    uint8_t* rowp = sDz + hf * kABlockBytes + (row >> 3) * 1024 + (row & 7) * 128;
+    bool dz_free = false;
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi) {
+        if (gi == 1 && !two) break;
+        const uint32_t(&r)[32] = gi == 0 ? r0 : r1;
+        const int v0 = v0c + (g0 + gi) * 32;
+        const float* bs = bias + (g0 + gi) * 32;
+        float d[32];
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            const float4 bv = *reinterpret_cast<const float4*>(bs + i);
+            d[i + 0] = rc.gg * ex2_approx(fmaf(__uint_as_float(r[i + 0]) + bv.x, kLog2e, rc.c2));
+            d[i + 1] = rc.gg * ex2_approx(fmaf(__uint_as_float(r[i + 1]) + bv.y, kLog2e, rc.c2));
+            d[i + 2] = rc.gg * ex2_approx(fmaf(__uint_as_float(r[i + 2]) + bv.z, kLog2e, rc.c2));
+            d[i + 3] = rc.gg * ex2_approx(fmaf(__uint_as_float(r[i + 3]) + bv.w, kLog2e, rc.c2));
+        }
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(d[2 * i], d[2 * i + 1]);
+        if (!dz_free) {  // the previous dz tile must have been consumed by its MMAs
+            mbar_wait(dz_empty_bar, dz_empty_parity);
+            dz_free = true;
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int chunk = (gi * 4 + j) ^ (row & 7);
+            *reinterpret_cast<uint4*>(rowp + (chunk << 4)) =
+                make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+        }
+        // sparse part of dz: patch the (at most two) affected elements of this row in place
+        const int dl = rc.lab - v0;
+        const bool lab_here = dl >= 0 && dl < 32;
+        const bool blank_here = blank >= v0 && blank < v0 + 32;  // warp-uniform
+        auto patch = [&](int col, float corr) {
+            const int chunk = (gi * 4 + (col >> 3)) ^ (row & 7);
+            __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(rowp + (chunk << 4)) + (col & 7);
+            *e = __float2bfloat16_rn(__bfloat162float(*e) - corr);
+        };
+        if (lab_here) patch(dl, rc.corr_l);
+        if (blank_here) patch(blank - v0, rc.corr_b);
+        if (kColSum) {
+            float cs = warp_transpose_reduce(d, lane);   // dense part, lane == column
+            if (blank_here) {
+                const float sb = warp_sum(rc.corr_b);
+                if (lane == blank - v0) cs -= sb;
+            }
+            colsum[gi] += cs;
+            if (lab_here && rc.corr_l != 0.f) atomicAdd(d_b_out + rc.lab, -rc.corr_l);
+        }
+    }
+}
+
+// dpre = dacc (1 - h^2) for one 32-column group of this thread's row; h from the resident h tile
+__device__ __forceinline__ void dpre_group(const uint32_t (&r)[32], const uint8_t* hrow, int half32, int row,
+                                           uint32_t (&pk)[16]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int chunk = (half32 * 4 + j) ^ (row & 7);
+        const uint4 hv = *reinterpret_cast<const uint4*>(hrow + (chunk << 4));
+        const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const float h0 = __uint_as_float(hw[e] << 16);
+            const float h1 = __uint_as_float(hw[e] & 0xffff0000u);
+            const float d0 = __uint_as_float(r[j * 8 + e * 2]) * fmaf(-h0, h0, 1.f);
+            const float d1 = __uint_as_float(r[j * 8 + e * 2 + 1]) * fmaf(-h1, h1, 1.f);
+            pk[j * 4 + e] = pack_bf16x2(d0, d1);
+        }
+    }
+}
+
+// =================================================================================================
+// dh kernel (CTA pair).  Barrier topology: *_full barriers fed by TMA and the barriers the MMA issuer
+// waits on (z_empty, dz_full, acc_empty) live in the LEADER; barriers signalled by tcgen05.commit
+// (w_empty, z_full, dz_empty, acc_full, h_empty) are multicast to BOTH CTAs.
+struct __align__(16) DhBarriers {
+    uint64_t w_full[kDhSlots], w_empty[kDhSlots];
+    uint64_t h_full[kMaxKBlocks];
+    uint64_t h_empty;
+    uint64_t z_full[2], z_empty[2];
+    uint64_t dz_full, dz_empty;
+    uint64_t acc_full, acc_empty;
+    uint32_t tmem_base;
+    uint32_t pad[3];
+};
+
 __global__ void __launch_bounds__(kThreads, 1)
-joint_bwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __restrict__ enc,
-                 const float* __restrict__ dec, const float* __restrict__ b_out,
-                 const int* __restrict__ labels, const int* __restrict__ tlen,
-                 const int* __restrict__ ulen, const float* __restrict__ lse,
-                 const float* __restrict__ gamma2, const float* __restrict__ grad_cost, int B, int T,
-                 int U1, int J, int V, int blank, int num_splits,
-                 __nv_bfloat16* __restrict__ dpre_out,   // !kDW: (B,T,U1,J)
-                 float* __restrict__ d_w_out,            //  kDW: (V,J), pre-zeroed
-                 float* __restrict__ d_b_out) {          //  kDW: (V), pre-zeroed
+joint_dh_kernel(const __grid_constant__ CUtensorMap tmap_wz,   // w_out bf16, box [64 j x 64 v]
+                const __grid_constant__ CUtensorMap tmap_wd,   // w_out bf16, box [64 j x 128 v]
+                const __grid_constant__ CUtensorMap tmap_h,    // h cache, box [64 j x 128 cells]
+                const float* __restrict__ b_out, const int* __restrict__ labels,
+                const int* __restrict__ tlen, const int* __restrict__ ulen,
+                const float* __restrict__ lse, const float* __restrict__ gamma2,
+                const float* __restrict__ grad_cost, int B, int T, int U1, int J, int V, int blank,
+                __nv_bfloat16* __restrict__ dpre_out) {   // (B,T,U1,J)
     extern __shared__ __align__(1024) uint8_t smem[];
     const int KB = J / kBlockK;
     const int NCH = (V + kBwdChunk - 1) / kBwdChunk;
     const int NPART = (KB + kPartBlocks - 1) / kPartBlocks;
-    uint8_t* sA = smem;
-    uint8_t* sDz = sA + (size_t)KB * kABlockBytes;
-    uint8_t* sB = sDz + kDzBytes;
-    BwdBarriers* bars = reinterpret_cast<BwdBarriers*>(sB + (size_t)kBwdStages * kBwdTileBytes);
+    const int ZS = (KB + 1) / 2;  // ring slots per z chunk (two K blocks of [64 v x 64 j] per slot)
+    uint8_t* sH = smem;
+    uint8_t* sDz = sH + (size_t)KB * kABlockBytes;
+    uint8_t* sW = sDz + kDzBytes;
+    DhBarriers* bars = reinterpret_cast<DhBarriers*>(sW + (size_t)kDhSlots * kSlotBytes);
     float* s_bias = reinterpret_cast<float*>(bars + 1);  // [2][kBwdChunk]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int tiles_per_utt = (T * U1 + 2 * kTileM - 1) / (2 * kTileM);
+    const int total_tiles = B * tiles_per_utt;
+    const int tile0 = blockIdx.x / 2, tile_stride = gridDim.x / 2;
+    const int tpu = tiles128_per_utt(T, U1);
+    auto chunk_cols = [&](int c) { return min(kBwdChunk, V - c * kBwdChunk); };
+    auto part_cols = [&](int p) { return min(kPartBlocks * kBlockK, J - p * kPartBlocks * kBlockK); };
+
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kDhSlots; ++i) {
+            mbar_init(smem_u32(&bars->w_full[i]), 2);
+            mbar_init(smem_u32(&bars->w_empty[i]), 1);
+        }
+        for (int i = 0; i < kMaxKBlocks; ++i) mbar_init(smem_u32(&bars->h_full[i]), 2);
+        mbar_init(smem_u32(&bars->h_empty), 1 + kEpiThreads);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&bars->z_full[i]), 1);
+            mbar_init(smem_u32(&bars->z_empty[i]), 2 * kEpiThreads);
+        }
+        mbar_init(smem_u32(&bars->dz_full), 2 * kEpiThreads);
+        mbar_init(smem_u32(&bars->dz_empty), 1);
+        mbar_init(smem_u32(&bars->acc_full), 1);
+        mbar_init(smem_u32(&bars->acc_empty), 2 * kEpiThreads);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_wz);
+        tma_prefetch_desc(&tmap_wd);
+        tma_prefetch_desc(&tmap_h);
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(smem_u32(&bars->tmem_base), 512);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t tmem_acc2 = tmem_base + 2 * kBwdChunk;
+
+    if (warp == 0) {
+        // ===================== TMA producer (both CTAs; same order as the MMA issuer consumes) =====
+        if (lane == 0) {
+            uint32_t slot = 0, sphase = 0, tl = 0;
+            uint32_t full = 0;
+            auto acquire = [&](uint32_t bytes) -> uint32_t {
+                mbar_wait(smem_u32(&bars->w_empty[slot]), sphase ^ 1);
+                full = smem_u32(&bars->w_full[slot]);
+                mbar_arrive_expect_tx_cluster(mapa_shared(full, 0), bytes);
+                const uint32_t dst = smem_u32(sW + (size_t)slot * kSlotBytes);
+                if (++slot == kDhSlots) { slot = 0; sphase ^= 1; }
+                return dst;
+            };
+            auto zloads = [&](int c) {
+                const int y = c * kBwdChunk + (int)rank * (chunk_cols(c) >> 1);
+                for (int s = 0; s < ZS; ++s) {
+                    const int nkb = min(2, KB - 2 * s);
+                    const uint32_t dst = acquire(nkb * (kSlotBytes / 2));
+                    for (int i = 0; i < nkb; ++i)
+                        tma_load_2d_pair(dst + i * (kSlotBytes / 2), &tmap_wz, (2 * s + i) * kBlockK, y, full);
+                }
+            };
+            auto dhloads = [&](int p, int c) {
+                const int half = part_cols(p) >> 1;
+                for (int t = 0; t < half / kBlockK; ++t) {
+                    const uint32_t dst = acquire(kSlotBytes);
+                    tma_load_2d_pair(dst, &tmap_wd, p * kPartBlocks * kBlockK + (int)rank * half + t * kBlockK,
+                                     c * kBwdChunk, full);
+                }
+            };
+            TileInfo ti;
+            for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+                if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
+                const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM;
+                mbar_wait(smem_u32(&bars->h_empty), (tl & 1) ^ 1);
+                for (int kb = 0; kb < KB; ++kb) {
+                    const uint32_t hf = smem_u32(&bars->h_full[kb]);
+                    mbar_arrive_expect_tx_cluster(mapa_shared(hf, 0), kABlockBytes);
+                    tma_load_2d_pair(smem_u32(sH + (size_t)kb * kABlockBytes), &tmap_h, kb * kBlockK, row0, hf);
+                }
+                for (int p = 0; p < NPART; ++p) {
+                    zloads(0);
+                    for (int c = 0; c < NCH; ++c) {
+                        if (c + 1 < NCH) zloads(c + 1);
+                        dhloads(p, c);
+                    }
+                }
+                ++tl;
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA; one elected lane issues) =====================
+        if (leader) {
+            uint32_t slot = 0, sphase = 0, zc = 0, dc = 0, ac = 0, tl = 0;
+            const uint32_t h_lo0 = desc_lo(smem_u32(sH), 16);
+            const uint32_t w_lo0 = desc_lo(smem_u32(sW), 16);
+            const uint32_t dz_lo0 = desc_lo(smem_u32(sDz), 16);
+            const uint32_t w_mn_lo0 = desc_lo(smem_u32(sW), kSlotBytes);
+            auto advance = [&]() { if (++slot == kDhSlots) { slot = 0; sphase ^= 1; } };
+
+            // z[256 x n] = h W_c^T into z buffer zc&1
+            auto z_mma = [&](int c, bool wait_h, bool release_h) {
+                const uint32_t zb = zc & 1;
+                mbar_wait(smem_u32(&bars->z_empty[zb]), ((zc >> 1) & 1) ^ 1);
+                const uint32_t idesc = umma_idesc_bf16(2 * kTileM, chunk_cols(c));
+                const uint32_t d_tmem = tmem_base + zb * kBwdChunk;
+                for (int s = 0; s < ZS; ++s) {
+                    const int nkb = min(2, KB - 2 * s);
+                    if (wait_h)
+                        for (int i = 0; i < nkb; ++i) mbar_wait(smem_u32(&bars->h_full[2 * s + i]), tl & 1);
+                    mbar_wait(smem_u32(&bars->w_full[slot]), sphase);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        for (int i = 0; i < nkb; ++i) {
+                            const uint32_t a_lo = h_lo0 + (2 * s + i) * (kABlockBytes >> 4);
+                            const uint32_t b_lo = w_lo0 + slot * (kSlotBytes >> 4) + i * (kSlotBytes >> 5);
+#pragma unroll
+                            for (int k16 = 0; k16 < kBlockK / 16; ++k16)
+                                umma_bf16_pair(d_tmem, mk_desc(a_lo + 2 * k16), mk_desc(b_lo + 2 * k16), idesc,
+                                               (s | i | k16) != 0);
+                        }
+                        umma_commit_pair(smem_u32(&bars->w_empty[slot]));
+                        if (s == ZS - 1) {
+                            umma_commit_pair(smem_u32(&bars->z_full[zb]));
+                            if (release_h) umma_commit_pair(smem_u32(&bars->h_empty));
+                        }
+                    }
+                    __syncwarp();
+                    advance();
+                }
+                ++zc;
+            };
+            // dh_part[256 x part] += dz W_c[:, part]; one N=128 MMA group per w_out tile (64 j per CTA)
+            auto dh_mma = [&](int p, int c) {
+                const int n = chunk_cols(c);
+                const int nt = (part_cols(p) >> 1) / kBlockK;
+                if (c == 0) mbar_wait(smem_u32(&bars->acc_empty), (ac & 1) ^ 1);
+                mbar_wait(smem_u32(&bars->dz_full), dc & 1);
+                const uint32_t idesc = umma_idesc_bf16(2 * kTileM, 2 * kBlockK, 0, 1);
+                for (int t = 0; t < nt; ++t) {
+                    mbar_wait(smem_u32(&bars->w_full[slot]), sphase);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t b_lo = w_mn_lo0 + slot * (kSlotBytes >> 4);
+                        for (int kk = 0; kk < n / 16; ++kk)
+                            umma_bf16_pair(tmem_acc2 + t * 2 * kBlockK,
+                                           mk_desc(dz_lo0 + (kk >> 2) * (kABlockBytes >> 4) + (kk & 3) * 2),
+                                           mk_desc(b_lo + kk * (2048 >> 4)), idesc, (c > 0 || kk > 0) ? 1u : 0u);
+                        umma_commit_pair(smem_u32(&bars->w_empty[slot]));
+                        if (t == nt - 1) {
+                            umma_commit_pair(smem_u32(&bars->dz_empty));
+                            if (c == NCH - 1) umma_commit_pair(smem_u32(&bars->acc_full));
+                        }
+                    }
+                    __syncwarp();
+                    advance();
+                }
+                ++dc;
+            };
+
+            TileInfo ti;
+            for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+                if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
+                for (int p = 0; p < NPART; ++p) {
+                    const bool lastp = p == NPART - 1;
+                    z_mma(0, p == 0, lastp && NCH == 1);
+                    for (int c = 0; c < NCH; ++c) {
+                        if (c + 1 < NCH) z_mma(c + 1, false, lastp && c + 1 == NCH - 1);
+                        dh_mma(p, c);
+                    }
+                    ++ac;
+                }
+                ++tl;
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (8 warps) =====================
+        const int e = threadIdx.x - 128;
+        const int q = warp & 3, hf = (warp - 4) >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        uint32_t zc = 0, dc = 0, ac = 0;
+        float colsum[2] = {0.f, 0.f};
+        const uint32_t z_empty_addr[2] = {mapa_shared(smem_u32(&bars->z_empty[0]), 0),
+                                          mapa_shared(smem_u32(&bars->z_empty[1]), 0)};
+        const uint32_t dz_full_addr = mapa_shared(smem_u32(&bars->dz_full), 0);
+        const uint32_t acc_empty_addr = mapa_shared(smem_u32(&bars->acc_empty), 0);
+        TileInfo ti;
+        for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+            if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
+            RowCtx rc;
+            load_row_ctx(rc, ti, row, T, U1, V, labels, lse, gamma2, grad_cost);
+            for (int p = 0; p < NPART; ++p) {
+                for (int c = 0; c < NCH; ++c) {
+                    const uint32_t zb = zc & 1;
+                    const int n = chunk_cols(c);
+                    float* bias = s_bias + zb * kBwdChunk;
+                    if (e < n) bias[e] = __ldg(b_out + c * kBwdChunk + e);
+                    named_bar_sync(1, kEpiThreads);
+                    mbar_wait(smem_u32(&bars->z_full[zb]), (zc >> 1) & 1);
+                    tc_fence_after();
+                    dz_from_z<false>(tmem_base + lane_base + zb * kBwdChunk, bias, n, c * kBwdChunk, hf, row, lane,
+                                     rc, blank, sDz, smem_u32(&bars->dz_empty), (dc & 1) ^ 1, colsum, nullptr);
+                    tc_fence_before();
+                    mbar_arrive_cluster(z_empty_addr[zb]);
+                    fence_proxy_async_smem();
+                    mbar_arrive_cluster(dz_full_addr);
+                    ++zc;
+                    ++dc;
+                }
+                // ---- dh_part -> dpre = dh (1 - h^2) -> bf16 (B,T,U1,J).  Accumulator columns of the
+                // part: [t*128 + r*64 + jj] <-> j = p*256 + r*half + t*64 + jj  (r = CTA that staged it)
+                const int half = part_cols(p) >> 1;
+                const int G = part_cols(p) >> 5;  // 32-column groups
+                mbar_wait(smem_u32(&bars->acc_full), ac & 1);
+                tc_fence_after();
+                for (int gi = hf * (G >> 1); gi < (hf + 1) * (G >> 1); ++gi) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tmem_acc2 + lane_base + gi * 32, r);
+                    tmem_wait_ld();
+                    const int j0 = p * kPartBlocks * kBlockK + ((gi >> 1) & 1) * half + (gi >> 2) * kBlockK + (gi & 1) * 32;
+                    const int kb = j0 / kBlockK;
+                    const uint8_t* hrow = sH + (size_t)kb * kABlockBytes + (row >> 3) * 1024 + (row & 7) * 128;
+                    uint32_t pk[16];
+                    dpre_group(r, hrow, gi & 1, row, pk);
+                    if (rc.valid) {
+                        uint4* dst = reinterpret_cast<uint4*>(dpre_out + rc.cell * J + j0);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j)
+                            dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive_cluster(acc_empty_addr);
+                ++ac;
+            }
+            mbar_arrive(smem_u32(&bars->h_empty));
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+// =================================================================================================
+// dW kernel (single CTA per role, cta_group::1).
+struct __align__(16) DwBarriers {
+    uint64_t w_full[kDwSlots], w_empty[kDwSlots];
+    uint64_t h_full[kMaxKBlocks], h_empty[kMaxKBlocks];
+    uint64_t z_full[2], z_empty[2];
+    uint64_t dz_full, dz_empty;
+    uint64_t acc_full;
+    uint32_t tmem_base;
+    uint32_t pad[3];
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+joint_dw_kernel(const __grid_constant__ CUtensorMap tmap_w,    // w_out bf16, box [64 j x 128 v]
+                const __grid_constant__ CUtensorMap tmap_h,    // h cache, box [64 j x 128 cells]
+                const float* __restrict__ b_out, const int* __restrict__ labels,
+                const int* __restrict__ tlen, const int* __restrict__ ulen,
+                const float* __restrict__ lse, const float* __restrict__ gamma2,
+                const float* __restrict__ grad_cost, int B, int T, int U1, int J, int V, int blank,
+                int num_splits,
+                float* __restrict__ d_w_out,    // (V,J), pre-zeroed
+                float* __restrict__ d_b_out) {  // (V), pre-zeroed
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int KB = J / kBlockK;
+    const int NCH = (V + kBwdChunk - 1) / kBwdChunk;
+    const int NPART = (KB + kPartBlocks - 1) / kPartBlocks;
+    uint8_t* sH = smem;                                   // h tile: KB blocks [128 cells x 64 j]
+    uint8_t* sDz = sH + (size_t)KB * kABlockBytes;
+    uint8_t* sW = sDz + kDzBytes;                         // ring of W_c blocks [128 v x 64 j]
+    DwBarriers* bars = reinterpret_cast<DwBarriers*>(sW + (size_t)kDwSlots * kSlotBytes);
+    float* s_bias = reinterpret_cast<float*>(bars + 1);   // [kBwdChunk]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int tiles_per_utt = (T * U1 + kTileM - 1) / kTileM;
     const int total_tiles = B * tiles_per_utt;
-    // kDW: role = (vocab chunk, J-part), `num_splits` CTAs per role share the cell tiles
-    const int role = kDW ? (int)blockIdx.x % (NCH * NPART) : 0;
+    const int tpu = tiles128_per_utt(T, U1);
+    // role = (vocab chunk, J-part); `num_splits` CTAs per role share the cell tiles
+    const int role = (int)blockIdx.x % (NCH * NPART);
     const int role_c = role / NPART, role_p = role % NPART;
-    const int tile0 = kDW ? (int)blockIdx.x / (NCH * NPART) : (int)blockIdx.x;
-    const int tile_stride = kDW ? num_splits : (int)gridDim.x;
-    auto part_blocks = [&](int p) { return min(kPartBlocks, KB - p * kPartBlocks); };
-    auto chunk_cols = [&](int c) { return min(kBwdChunk, V - c * kBwdChunk); };
+    const int tile0 = (int)blockIdx.x / (NCH * NPART);
+    const int n = min(kBwdChunk, V - role_c * kBwdChunk);            // vocab rows of the role
+    const int pb = min(kPartBlocks, KB - role_p * kPartBlocks);      // K blocks of the role's J-part
+    const int kb_part0 = role_p * kPartBlocks;
+    // K order of the z MMAs: the blocks outside the part first (their h slots are recycled early)
+    auto korder = [&](int i) { return i < KB - pb ? (i < kb_part0 ? i : i + pb) : kb_part0 + (i - (KB - pb)); };
 
     if (warp == 1 && lane == 0) {
-        for (int i = 0; i < kBwdStages; ++i) {
-            mbar_init(smem_u32(&bars->b_full[i]), 1);
-            mbar_init(smem_u32(&bars->b_empty[i]), 1);
+        for (int i = 0; i < kDwSlots; ++i) {
+            mbar_init(smem_u32(&bars->w_full[i]), 1);
+            mbar_init(smem_u32(&bars->w_empty[i]), 1);
         }
         for (int i = 0; i < kMaxKBlocks; ++i) {
-            mbar_init(smem_u32(&bars->a_full[i]), 128);
-            mbar_init(smem_u32(&bars->a_empty[i]), kDW ? 1 : 129);  // !kDW: + epilogue readers of h
+            mbar_init(smem_u32(&bars->h_full[i]), 1);
+            mbar_init(smem_u32(&bars->h_empty[i]), 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->z_full[i]), 1);
-            mbar_init(smem_u32(&bars->z_empty[i]), 128);
+            mbar_init(smem_u32(&bars->z_empty[i]), kEpiThreads);
         }
-        mbar_init(smem_u32(&bars->dz_full), 128);
+        mbar_init(smem_u32(&bars->dz_full), kEpiThreads);
         mbar_init(smem_u32(&bars->dz_empty), 1);
-        mbar_init(smem_u32(&bars->acc2_full), 1);
-        mbar_init(smem_u32(&bars->acc2_empty), 128);
+        mbar_init(smem_u32(&bars->acc_full), 1);
         fence_barrier_init();
     }
-    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_w);
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_h);
+    }
     if (warp == 2) {
         tmem_alloc(smem_u32(&bars->tmem_base), 512);
         tmem_relinquish();
@@ -141,307 +549,143 @@ joint_bwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __rest
     const uint32_t tmem_acc2 = tmem_base + 2 * kBwdChunk;
 
     if (warp == 0) {
-        // ===================== TMA producer: same order as the MMA issuer consumes =====================
+        // ===================== TMA producer =====================
         if (lane == 0) {
-            uint32_t stage = 0, phase = 0;
-            auto load = [&](int x, int y) {
-                mbar_wait(smem_u32(&bars->b_empty[stage]), phase ^ 1);
-                const uint32_t full = smem_u32(&bars->b_full[stage]);
-                mbar_arrive_expect_tx(full, kBwdTileBytes);
-                tma_load_2d(smem_u32(sB + (size_t)stage * kBwdTileBytes), &tmap_w, x, y, full);
-                if (++stage == kBwdStages) { stage = 0; phase ^= 1; }
-            };
+            uint32_t tl = 0, slot = 0, sphase = 0;
             TileInfo ti;
-            for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+            for (int tile = tile0; tile < total_tiles; tile += num_splits) {
                 if (!tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) continue;
-                if (kDW) {
-                    for (int kb = 0; kb < KB; ++kb) load(kb * kBlockK, role_c * kBwdChunk);
-                } else {
-                    for (int p = 0; p < NPART; ++p) {
-                        const int pb = part_blocks(p);
-                        for (int c = 0; c <= NCH; ++c) {
-                            if (c < NCH)
-                                for (int kb = 0; kb < KB; ++kb) load(kb * kBlockK, c * kBwdChunk);
-                            if (c > 0)
-                                for (int jb = 0; jb < pb; ++jb)
-                                    load((p * kPartBlocks + jb) * kBlockK, (c - 1) * kBwdChunk);
-                        }
-                    }
+                const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM;
+                for (int i = 0; i < KB; ++i) {
+                    const int kb = korder(i);
+                    mbar_wait(smem_u32(&bars->h_empty[kb]), (tl & 1) ^ 1);
+                    const uint32_t hf = smem_u32(&bars->h_full[kb]);
+                    mbar_arrive_expect_tx(hf, kABlockBytes);
+                    tma_load_2d(smem_u32(sH + (size_t)kb * kABlockBytes), &tmap_h, kb * kBlockK, row0, hf);
+                    mbar_wait(smem_u32(&bars->w_empty[slot]), sphase ^ 1);
+                    const uint32_t wf = smem_u32(&bars->w_full[slot]);
+                    mbar_arrive_expect_tx(wf, kSlotBytes);
+                    tma_load_2d(smem_u32(sW + (size_t)slot * kSlotBytes), &tmap_w, kb * kBlockK, role_c * kBwdChunk, wf);
+                    if (++slot == kDwSlots) { slot = 0; sphase ^= 1; }
                 }
+                ++tl;
             }
         }
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        uint32_t stage = 0, phase = 0, zc = 0, dc = 0, ac = 0, tl = 0;
-        const uint32_t a_lo0 = desc_lo(smem_u32(sA), 16);
-        const uint32_t b_lo0 = desc_lo(smem_u32(sB), 16);
-        const uint32_t dz_lo0 = desc_lo(smem_u32(sDz), 16);
-        // MN-major views (LBO = 16 KiB between 64-element atoms along M/N)
-        const uint32_t a_mn_lo0 = desc_lo(smem_u32(sA), kABlockBytes);
-        const uint32_t b_mn_lo0 = desc_lo(smem_u32(sB), kBwdTileBytes);
+        uint32_t zc = 0, dc = 0, slot = 0, sphase = 0;
+        const uint32_t h_lo0 = desc_lo(smem_u32(sH), 16);
+        const uint32_t w_lo0 = desc_lo(smem_u32(sW), 16);
+        const uint32_t h_mn_lo0 = desc_lo(smem_u32(sH), kABlockBytes);
         const uint32_t dz_mn_lo0 = desc_lo(smem_u32(sDz), kABlockBytes);
-        auto advance = [&]() { if (++stage == kBwdStages) { stage = 0; phase ^= 1; } };
-
-        // z[128 x n] = h W_c^T into z buffer zc&1
-        auto z_mma = [&](int n, bool wait_a, int release_a_mask) {
+        const uint32_t idesc_z = umma_idesc_bf16(kTileM, n);
+        const uint32_t idesc_dw = umma_idesc_bf16(kTileM, pb * kBlockK, 1, 1);
+        // z MMAs over K blocks korder(i0..i1) of the tile with parity `par`; z buffer zc&1
+        auto z_part = [&](int i0, int i1, uint32_t par, bool first, bool last) {
             const uint32_t zb = zc & 1;
-            mbar_wait(smem_u32(&bars->z_empty[zb]), ((zc >> 1) & 1) ^ 1);
-            const uint32_t idesc = umma_idesc_bf16(kTileM, n);
+            if (first) mbar_wait(smem_u32(&bars->z_empty[zb]), ((zc >> 1) & 1) ^ 1);
             const uint32_t d_tmem = tmem_base + zb * kBwdChunk;
-            for (int kb = 0; kb < KB; ++kb) {
-                if (wait_a) mbar_wait(smem_u32(&bars->a_full[kb]), tl & 1);
-                mbar_wait(smem_u32(&bars->b_full[stage]), phase);
+            for (int i = i0; i < i1; ++i) {
+                const int kb = korder(i);
+                mbar_wait(smem_u32(&bars->h_full[kb]), par);
+                mbar_wait(smem_u32(&bars->w_full[slot]), sphase);
                 tc_fence_after();
                 if (elect_one_sync()) {
-                    const uint32_t a_lo = a_lo0 + kb * (kABlockBytes >> 4);
-                    const uint32_t b_lo = b_lo0 + stage * (kBwdTileBytes >> 4);
+                    const uint32_t a_lo = h_lo0 + kb * (kABlockBytes >> 4);
+                    const uint32_t b_lo = w_lo0 + slot * (kSlotBytes >> 4);
 #pragma unroll
                     for (int k16 = 0; k16 < kBlockK / 16; ++k16)
-                        umma_bf16(d_tmem, mk_desc(a_lo + 2 * k16), mk_desc(b_lo + 2 * k16), idesc,
-                                  (kb | k16) != 0);
-                    umma_commit(smem_u32(&bars->b_empty[stage]));
-                    if ((release_a_mask >> kb) & 1) umma_commit(smem_u32(&bars->a_empty[kb]));
-                    if (kb == KB - 1) umma_commit(smem_u32(&bars->z_full[zb]));
+                        umma_bf16(d_tmem, mk_desc(a_lo + 2 * k16), mk_desc(b_lo + 2 * k16), idesc_z,
+                                  (i | k16) != 0);
+                    umma_commit(smem_u32(&bars->w_empty[slot]));
+                    if (i < KB - pb) umma_commit(smem_u32(&bars->h_empty[kb]));  // outside the part: free now
+                    if (last && i == i1 - 1) umma_commit(smem_u32(&bars->z_full[zb]));
                 }
                 __syncwarp();
-                advance();
+                if (++slot == kDwSlots) { slot = 0; sphase ^= 1; }
             }
-            ++zc;
+            if (last) ++zc;
+        };
+        // dW[c, part] += dz^T h[:, part]   (M = 128 vocab rows, N = 64 pb, K = 128 cells)
+        auto dw_mma = [&](bool accumulate) {
+            mbar_wait(smem_u32(&bars->dz_full), dc & 1);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint32_t hb_lo = h_mn_lo0 + kb_part0 * (kABlockBytes >> 4);
+#pragma unroll
+                for (int kk = 0; kk < kTileM / 16; ++kk)
+                    umma_bf16(tmem_acc2, mk_desc(dz_mn_lo0 + kk * (2048 >> 4)), mk_desc(hb_lo + kk * (2048 >> 4)),
+                              idesc_dw, (accumulate || kk) ? 1u : 0u);
+                umma_commit(smem_u32(&bars->dz_empty));
+                for (int jb = 0; jb < pb; ++jb) umma_commit(smem_u32(&bars->h_empty[kb_part0 + jb]));
+            }
+            __syncwarp();
+            ++dc;
         };
 
+        // software pipeline over the CTA's valid tiles: zA(next) is issued before dW(cur) so the
+        // tensor pipe has work while the epilogue turns z(cur) into dz(cur)
         TileInfo ti;
-        bool any_tile = false;
-        for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+        uint32_t tl = 0;
+        bool have_cur = false;
+        for (int tile = tile0; tile < total_tiles; tile += num_splits) {
             if (!tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) continue;
-            if (kDW) {
-                const int pb = part_blocks(role_p);
-                const int part_mask = ((1 << pb) - 1) << (role_p * kPartBlocks);
-                z_mma(chunk_cols(role_c), true, ((1 << KB) - 1) & ~part_mask);
-                // dW[c, part] += dz^T h[:, part]   (M = 128 vocab rows, N = 64 pb, K = 128 cells)
-                mbar_wait(smem_u32(&bars->dz_full), dc & 1);
-                tc_fence_after();
-                if (elect_one_sync()) {
-                    const uint32_t idesc = umma_idesc_bf16(kTileM, pb * kBlockK, 1, 1);
-                    const uint32_t hb_lo = a_mn_lo0 + (role_p * kPartBlocks) * (kABlockBytes >> 4);
-#pragma unroll
-                    for (int kk = 0; kk < kTileM / 16; ++kk)
-                        umma_bf16(tmem_acc2, mk_desc(dz_mn_lo0 + kk * (2048 >> 4)),
-                                  mk_desc(hb_lo + kk * (2048 >> 4)), idesc, (any_tile || kk) ? 1u : 0u);
-                    umma_commit(smem_u32(&bars->dz_empty));
-                    for (int jb = 0; jb < pb; ++jb)
-                        umma_commit(smem_u32(&bars->a_empty[role_p * kPartBlocks + jb]));
-                }
-                __syncwarp();
-                ++dc;
-            } else {
-                for (int p = 0; p < NPART; ++p) {
-                    const int pb = part_blocks(p);
-                    for (int c = 0; c <= NCH; ++c) {
-                        if (c < NCH) {
-                            const bool last_use = (p == NPART - 1) && (c == NCH - 1);
-                            z_mma(chunk_cols(c), p == 0 && c == 0, last_use ? (1 << KB) - 1 : 0);
-                        }
-                        if (c > 0) {
-                            // dh_part += dz W_{c-1}[:, part]   (M = 128 cells, N = 64 per tile, K = n)
-                            const int n = chunk_cols(c - 1);
-                            if (c == 1) mbar_wait(smem_u32(&bars->acc2_empty), (ac & 1) ^ 1);
-                            mbar_wait(smem_u32(&bars->dz_full), dc & 1);
-                            const uint32_t idesc = umma_idesc_bf16(kTileM, kBlockK, 0, 1);
-                            for (int jb = 0; jb < pb; ++jb) {
-                                mbar_wait(smem_u32(&bars->b_full[stage]), phase);
-                                tc_fence_after();
-                                if (elect_one_sync()) {
-                                    const uint32_t b_lo = b_mn_lo0 + stage * (kBwdTileBytes >> 4);
-                                    for (int kk = 0; kk < n / 16; ++kk)
-                                        umma_bf16(tmem_acc2 + jb * kBlockK,
-                                                  mk_desc(dz_lo0 + (kk >> 2) * (kABlockBytes >> 4) + (kk & 3) * 2),
-                                                  mk_desc(b_lo + kk * (2048 >> 4)), idesc,
-                                                  (c > 1 || kk) ? 1u : 0u);
-                                    umma_commit(smem_u32(&bars->b_empty[stage]));
-                                    if (jb == pb - 1) {
-                                        umma_commit(smem_u32(&bars->dz_empty));
-                                        if (c == NCH) umma_commit(smem_u32(&bars->acc2_full));
-                                    }
-                                }
-                                __syncwarp();
-                                advance();
-                            }
-                            ++dc;
-                        }
-                    }
-                    ++ac;
-                }
-            }
-            any_tile = true;
+            // `tile` is the next valid tile (index tl); the current one (tl-1) still owes its dW
+            z_part(0, KB - pb, tl & 1, true, false);
+            if (have_cur) dw_mma(tl > 1);
+            z_part(KB - pb, KB, tl & 1, KB - pb == 0, true);
+            have_cur = true;
             ++tl;
         }
-        if (kDW && any_tile) {
-            if (elect_one_sync()) umma_commit(smem_u32(&bars->acc2_full));
+        if (have_cur) {
+            dw_mma(tl > 1);
+            if (elect_one_sync()) umma_commit(smem_u32(&bars->acc_full));
             __syncwarp();
         }
-    } else if (warp >= 4 && warp < 8) {
-        // ===================== epilogue =====================
-        const int q = warp & 3;
+    } else if (warp >= 4) {
+        // ===================== epilogue (8 warps) =====================
+        const int e = threadIdx.x - 128;
+        const int q = warp & 3, hf = (warp - 4) >> 2;
         const int row = q * 32 + lane;
-        const int etid = threadIdx.x - 128;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        uint32_t zc = 0, dc = 0, ac = 0, tl = 0;
-        float colsum[kBwdChunk / 32] = {0.f, 0.f, 0.f, 0.f};
+        uint32_t zc = 0, dc = 0;
+        float colsum[2] = {0.f, 0.f};
         bool any_tile = false;
+        if (e < n) s_bias[e] = __ldg(b_out + role_c * kBwdChunk + e);
+        named_bar_sync(1, kEpiThreads);
         TileInfo ti;
-
-        // z chunk -> dz (bf16) into the shared dz tile; returns after signalling dz_full
-        auto epi1 = [&](int c, const RowCtx& rc) {
+        for (int tile = tile0; tile < total_tiles; tile += num_splits) {
+            if (!tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) continue;
+            RowCtx rc;
+            load_row_ctx(rc, ti, row, T, U1, V, labels, lse, gamma2, grad_cost);
             const uint32_t zb = zc & 1;
-            const int n = chunk_cols(c);
-            float* bias = s_bias + zb * kBwdChunk;
-            if (etid < n) bias[etid] = __ldg(b_out + c * kBwdChunk + etid);
-            named_bar_sync(1, 128);
             mbar_wait(smem_u32(&bars->z_full[zb]), (zc >> 1) & 1);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + lane_base + zb * kBwdChunk;
-            bool dz_free = false;
-#pragma unroll
-            for (int g = 0; g < kBwdChunk / 32; ++g) {
-                if (g >= (n >> 5)) break;
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(taddr + g * 32, r);
-                tmem_wait_ld();
-                const int v0 = c * kBwdChunk + g * 32;
-                float d[32];
-#pragma unroll
-                for (int i = 0; i < 32; i += 4) {
-                    const float4 bv = *reinterpret_cast<const float4*>(bias + g * 32 + i);
-                    d[i + 0] = rc.gg * ex2_approx(fmaf(__uint_as_float(r[i + 0]) + bv.x, kLog2e, rc.c2));
-                    d[i + 1] = rc.gg * ex2_approx(fmaf(__uint_as_float(r[i + 1]) + bv.y, kLog2e, rc.c2));
-                    d[i + 2] = rc.gg * ex2_approx(fmaf(__uint_as_float(r[i + 2]) + bv.z, kLog2e, rc.c2));
-                    d[i + 3] = rc.gg * ex2_approx(fmaf(__uint_as_float(r[i + 3]) + bv.w, kLog2e, rc.c2));
-                }
-                uint32_t pk[16];
-#pragma unroll
-                for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(d[2 * i], d[2 * i + 1]);
-                if (!dz_free) {  // the previous dz tile must have been consumed by its MMAs
-                    mbar_wait(smem_u32(&bars->dz_empty), (dc & 1) ^ 1);
-                    dz_free = true;
-                }
-                uint8_t* rowp = sDz + (g >> 1) * kABlockBytes + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const int chunk = ((g & 1) * 4 + j) ^ (row & 7);
-                    *reinterpret_cast<uint4*>(rowp + (chunk << 4)) =
-                        make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                }
-                // sparse part of dz: patch the (at most two) affected elements of this row in place
-                const int dl = rc.lab - v0;
-                const bool lab_here = dl >= 0 && dl < 32;
-                const bool blank_here = blank >= v0 && blank < v0 + 32;  // warp-uniform
-                auto patch = [&](int col, float corr) {
-                    const int chunk = ((g & 1) * 4 + (col >> 3)) ^ (row & 7);
-                    __nv_bfloat16* e = reinterpret_cast<__nv_bfloat16*>(rowp + (chunk << 4)) + (col & 7);
-                    *e = __float2bfloat16_rn(__bfloat162float(*e) - corr);
-                };
-                if (lab_here) patch(dl, rc.corr_l);
-                if (blank_here) patch(blank - v0, rc.corr_b);
-                if (kDW && role_p == 0) {
-                    float cs = warp_transpose_reduce(d, lane);   // dense part, lane == column
-                    if (blank_here) {
-                        const float sb = warp_sum(rc.corr_b);
-                        if (lane == blank - v0) cs -= sb;
-                    }
-                    colsum[g] += cs;
-                    if (lab_here && rc.corr_l != 0.f) atomicAdd(d_b_out + rc.lab, -rc.corr_l);
-                }
-            }
+            if (role_p == 0)
+                dz_from_z<true>(tmem_base + lane_base + zb * kBwdChunk, s_bias, n, role_c * kBwdChunk, hf, row, lane,
+                                rc, blank, sDz, smem_u32(&bars->dz_empty), (dc & 1) ^ 1, colsum, d_b_out);
+            else
+                dz_from_z<false>(tmem_base + lane_base + zb * kBwdChunk, s_bias, n, role_c * kBwdChunk, hf, row, lane,
+                                 rc, blank, sDz, smem_u32(&bars->dz_empty), (dc & 1) ^ 1, colsum, d_b_out);
             tc_fence_before();
             mbar_arrive(smem_u32(&bars->z_empty[zb]));
             fence_proxy_async_smem();
             mbar_arrive(smem_u32(&bars->dz_full));
             ++zc;
             ++dc;
-        };
-
-        for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
-            if (!tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) continue;
-            RowCtx rc;
-            {
-                const int m = ti.first_cell + row;
-                rc.valid = m < ti.n_cells;
-                const int t = rc.valid ? m / ti.U1b : 0;
-                const int u = rc.valid ? m - t * ti.U1b : 0;
-                rc.cell = ((size_t)ti.b * T + t) * U1 + u;
-                rc.lab = -1;
-                rc.c2 = 0.f; rc.gg = 0.f; rc.corr_b = 0.f; rc.corr_l = 0.f;
-                if (rc.valid) {
-                    const float g = __ldg(grad_cost + ti.b);
-                    const float2 gm = __ldg(reinterpret_cast<const float2*>(gamma2) + rc.cell);
-                    rc.c2 = -__ldg(lse + rc.cell) * kLog2e;
-                    rc.gg = g * (gm.x + gm.y);
-                    rc.corr_b = g * gm.x;
-                    rc.corr_l = g * gm.y;
-                    if (u < ti.U1b - 1)
-                        rc.lab = min(max(__ldg(labels + (size_t)ti.b * (U1 - 1) + u), 0), V - 1);
-                }
-            }
-            if (kDW) {
-                epi1(role_c, rc);
-            } else {
-                for (int p = 0; p < NPART; ++p) {
-                    const int pb = part_blocks(p);
-                    for (int c = 0; c < NCH; ++c) epi1(c, rc);
-                    // ---- dh_part -> dpre = dh (1 - h^2) -> bf16 (B,T,U1,J)
-                    if (p == 0)
-                        for (int kb = 0; kb < KB; ++kb) mbar_wait(smem_u32(&bars->a_full[kb]), tl & 1);
-                    mbar_wait(smem_u32(&bars->acc2_full), ac & 1);
-                    tc_fence_after();
-                    for (int g = 0; g < pb * 2; ++g) {
-                        uint32_t r[32];
-                        tmem_ld_32x32b_x32(tmem_acc2 + lane_base + g * 32, r);
-                        tmem_wait_ld();
-                        const int kb = p * kPartBlocks + (g >> 1);
-                        const uint8_t* hrow = sA + (size_t)kb * kABlockBytes + (row >> 3) * 1024 + (row & 7) * 128;
-                        uint32_t pk[16];
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const int chunk = ((g & 1) * 4 + j) ^ (row & 7);
-                            const uint4 hv = *reinterpret_cast<const uint4*>(hrow + (chunk << 4));
-                            const uint32_t hw[4] = {hv.x, hv.y, hv.z, hv.w};
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float h0 = __uint_as_float(hw[e] << 16);
-                                const float h1 = __uint_as_float(hw[e] & 0xffff0000u);
-                                const float d0 = __uint_as_float(r[j * 8 + e * 2]) * fmaf(-h0, h0, 1.f);
-                                const float d1 = __uint_as_float(r[j * 8 + e * 2 + 1]) * fmaf(-h1, h1, 1.f);
-                                pk[j * 4 + e] = pack_bf16x2(d0, d1);
-                            }
-                        }
-                        if (rc.valid) {
-                            uint4* dst = reinterpret_cast<uint4*>(dpre_out + rc.cell * J + kb * kBlockK + (g & 1) * 32);
-#pragma unroll
-                            for (int j = 0; j < 4; ++j)
-                                dst[j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                        }
-                    }
-                    tc_fence_before();
-                    mbar_arrive(smem_u32(&bars->acc2_empty));
-                    ++ac;
-                }
-                for (int kb = 0; kb < KB; ++kb) mbar_arrive(smem_u32(&bars->a_empty[kb]));
-            }
             any_tile = true;
-            ++tl;
         }
-        if (kDW && any_tile) {
+        if (any_tile) {
             // ---- flush dW[c, part] (rows = vocab) and the column sums of dz
-            const int pb = part_blocks(role_p);
-            const int n = chunk_cols(role_c);
-            mbar_wait(smem_u32(&bars->acc2_full), 0);
+            mbar_wait(smem_u32(&bars->acc_full), 0);
             tc_fence_after();
-            for (int g = 0; g < pb * 2; ++g) {
+            const int G = pb * 2;  // 32-column groups of the part
+            for (int g = hf * (G >> 1); g < (hf + 1) * (G >> 1); ++g) {
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_acc2 + lane_base + g * 32, r);
                 tmem_wait_ld();
                 if (row < n) {
-                    float* dst = d_w_out + (size_t)(role_c * kBwdChunk + row) * J + role_p * kPartBlocks * kBlockK + g * 32;
+                    float* dst = d_w_out + (size_t)(role_c * kBwdChunk + row) * J + kb_part0 * kBlockK + g * 32;
 #pragma unroll
                     for (int i = 0; i < 32; i += 4)
                         red_add_v4(dst + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]),
@@ -450,37 +694,11 @@ joint_bwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const float* __rest
             }
             if (role_p == 0) {
 #pragma unroll
-                for (int g = 0; g < kBwdChunk / 32; ++g) {
-                    const int v = role_c * kBwdChunk + g * 32 + lane;
-                    if (g * 32 < n && v < V) atomicAdd(d_b_out + v, colsum[g]);
+                for (int gi = 0; gi < 2; ++gi) {
+                    const int col = (hf * 2 + gi) * 32 + lane;
+                    if (col < n) atomicAdd(d_b_out + role_c * kBwdChunk + col, colsum[gi]);
                 }
             }
-        }
-    } else if (warp >= 8) {
-        // ===================== A producers =====================
-        const int pw = warp - 8;
-        const int c = lane & 7;
-        const int rsub = lane >> 3;
-        uint32_t tl = 0;
-        TileInfo ti;
-        for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
-            if (!tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) continue;
-            uint32_t eoff[8], doff[8];
-#pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                int row = pw * 32 + p * 4 + rsub;
-                int m = min(ti.first_cell + row, ti.n_cells - 1);
-                int t = m / ti.U1b, u = m - t * ti.U1b;
-                eoff[p] = (uint32_t)(((size_t)ti.b * T + t) * J) + c * 8;
-                doff[p] = (uint32_t)(((size_t)ti.b * U1 + u) * J) + c * 8;
-            }
-            for (int kb = 0; kb < KB; ++kb) {
-                mbar_wait(smem_u32(&bars->a_empty[kb]), (tl & 1) ^ 1);
-                produce_h_block(enc, dec, eoff, doff, kb, pw, rsub, c, sA + (size_t)kb * kABlockBytes);
-                fence_proxy_async_smem();
-                mbar_arrive(smem_u32(&bars->a_full[kb]));
-            }
-            ++tl;
         }
     }
 
@@ -535,14 +753,19 @@ __global__ void reduce_over_t_kernel(const __nv_bfloat16* __restrict__ dpre, con
     }
 }
 
-size_t bwd_smem_bytes(int J) {
-    return (size_t)(J / kBlockK) * kABlockBytes + kDzBytes + (size_t)kBwdStages * kBwdTileBytes +
-           sizeof(BwdBarriers) + 2 * kBwdChunk * sizeof(float);
+size_t dh_smem_bytes(int J) {
+    return (size_t)(J / kBlockK) * kABlockBytes + kDzBytes + (size_t)kDhSlots * kSlotBytes + sizeof(DhBarriers) +
+           2 * kBwdChunk * sizeof(float);
+}
+size_t dw_smem_bytes(int J) {
+    return (size_t)(J / kBlockK) * kABlockBytes + kDzBytes + (size_t)kDwSlots * kSlotBytes + sizeof(DwBarriers) +
+           kBwdChunk * sizeof(float);
 }
 
 }  // namespace
 
 size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V) {
+    if (op == EMO_OP_RNNT_JOINT_HCACHE) return align_up(hcache_bytes_for(B, T, U1, J), 256);
     size_t w = align_up((size_t)V * J * sizeof(__nv_bfloat16), 256);
     if (op == EMO_OP_RNNT_JOINT_BWD)
         return w + align_up((size_t)B * T * U1 * J * sizeof(__nv_bfloat16), 256);
@@ -557,19 +780,22 @@ int joint_bf16_launches(int op, int B, int T, int U1, int J, int V) {
 
 int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
                    const float* b_out, const int* labels, const int* tlen, const int* ulen,
-                   const float* lse, const float* gamma2, const float* grad_cost, int B, int T,
+                   const float* lse, const float* gamma2, const float* grad_cost,
+                   const void* hcache, size_t hcache_bytes, int B, int T,
                    int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
                    float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st) {
-    EMO_REQUIRE(enc_proj && dec_proj && w_out && b_out && labels && tlen && ulen && lse && gamma2 &&
-                    grad_cost && d_enc_proj && d_dec_proj && d_w_out && d_b_out && ws,
+    (void)enc_proj; (void)dec_proj;
+    EMO_REQUIRE(w_out && b_out && labels && tlen && ulen && lse && gamma2 && grad_cost && d_enc_proj &&
+                    d_dec_proj && d_w_out && d_b_out && ws,
                 EMO_BAD_ARG, "joint_bwd(bf16): null pointer");
+    EMO_REQUIRE(hcache, EMO_BAD_ARG, "joint_bwd(bf16): the h cache written by emo_rnnt_joint_fwd is required");
     int rc = check_bf16_shape(B, T, U1, J, V, blank);
     if (rc) return rc;
+    EMO_REQUIRE(hcache_bytes >= hcache_bytes_for(B, T, U1, J) && ((uintptr_t)hcache & 255) == 0,
+                EMO_WORKSPACE_TOO_SMALL, "joint_bwd(bf16): h cache too small or misaligned");
     EMO_REQUIRE(ws_bytes >= joint_bf16_workspace(EMO_OP_RNNT_JOINT_BWD, B, T, U1, J, V),
                 EMO_WORKSPACE_TOO_SMALL, "joint_bwd(bf16): workspace too small");
-    EMO_REQUIRE(((uintptr_t)ws & 255) == 0 && ((uintptr_t)enc_proj & 15) == 0 &&
-                    ((uintptr_t)dec_proj & 15) == 0 && ((uintptr_t)w_out & 15) == 0 &&
-                    ((uintptr_t)d_w_out & 15) == 0,
+    EMO_REQUIRE(((uintptr_t)ws & 255) == 0 && ((uintptr_t)w_out & 15) == 0 && ((uintptr_t)d_w_out & 15) == 0,
                 EMO_BAD_ARG, "joint_bwd(bf16): pointers must be 16-byte (workspace 256-byte) aligned");
     const int KB = J / kBlockK;
     const int NCH = ceil_div(V, kBwdChunk), NPART = ceil_div(KB, kPartBlocks);
@@ -584,32 +810,54 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     EMO_CUDA(cudaMemsetAsync(d_w_out, 0, nw * sizeof(float), st));
     EMO_CUDA(cudaMemsetAsync(d_b_out, 0, (size_t)V * sizeof(float), st));
 
-    CUtensorMap tmap;
-    rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, 128);
+    CUtensorMap tmap_wz, tmap_wd, tmap_h;
+    rc = make_tmap_bf16_2d(&tmap_wz, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, 64);
     if (rc) return rc;
-    const size_t smem = bwd_smem_bytes(J);
-    EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_bwd(bf16): shared memory");
-    EMO_CUDA(cudaFuncSetAttribute(joint_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    EMO_CUDA(cudaFuncSetAttribute(joint_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int tiles = B * ceil_div((size_t)T * U1, kTileM);
+    rc = make_tmap_bf16_2d(&tmap_wd, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, 128);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tmap_h, hcache, (uint64_t)J, (uint64_t)B * tiles128_per_utt(T, U1) * kTileM, kBlockK,
+                           kTileM);
+    if (rc) return rc;
 
-    // dh kernel + the two axis reductions
-    joint_bwd_kernel<false><<<min(tiles, sm_count()), kThreads, smem, st>>>(
-        tmap, enc_proj, dec_proj, b_out, labels, tlen, ulen, lse, gamma2, grad_cost, B, T, U1, J, V,
-        blank, 1, dpre, nullptr, nullptr);
-    EMO_CHECK_LAUNCH("joint_bwd_kernel<dh>");
+    // ---- dh kernel (CTA pairs) + the two axis reductions
+    {
+        const size_t smem = dh_smem_bytes(J);
+        EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_bwd(bf16): shared memory (dh)");
+        EMO_CUDA(cudaFuncSetAttribute(joint_dh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int ptiles = B * ceil_div((size_t)T * U1, 2 * kTileM);
+        const int pairs = max(1, min(ptiles, sm_count() / 2));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * pairs);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        EMO_CUDA(cudaLaunchKernelEx(&cfg, joint_dh_kernel, tmap_wz, tmap_wd, tmap_h, b_out, labels, tlen, ulen, lse,
+                                    gamma2, grad_cost, B, T, U1, J, V, blank, dpre));
+        EMO_CHECK_LAUNCH("joint_dh_kernel");
+    }
     reduce_over_u_kernel<<<B * T, 128, 0, st>>>(dpre, tlen, ulen, T, U1, J, d_enc_proj);
     EMO_CHECK_LAUNCH("reduce_over_u_kernel");
     reduce_over_t_kernel<<<B * U1, 128, 0, st>>>(dpre, tlen, ulen, T, U1, J, d_dec_proj);
     EMO_CHECK_LAUNCH("reduce_over_t_kernel");
 
-    // dW kernel: one (vocab chunk, J-part) role per CTA, num_splits CTAs per role
-    const int roles = NCH * NPART;
-    const int splits = max(1, min(sm_count() / roles, tiles));
-    joint_bwd_kernel<true><<<roles * splits, kThreads, smem, st>>>(
-        tmap, enc_proj, dec_proj, b_out, labels, tlen, ulen, lse, gamma2, grad_cost, B, T, U1, J, V,
-        blank, splits, nullptr, d_w_out, d_b_out);
-    EMO_CHECK_LAUNCH("joint_bwd_kernel<dW>");
+    // ---- dW kernel: one (vocab chunk, J-part) role per CTA, num_splits CTAs per role
+    {
+        const size_t smem = dw_smem_bytes(J);
+        EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_bwd(bf16): shared memory (dW)");
+        EMO_CUDA(cudaFuncSetAttribute(joint_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int tiles = B * ceil_div((size_t)T * U1, kTileM);
+        const int roles = NCH * NPART;
+        const int splits = max(1, min(sm_count() / roles, tiles));
+        joint_dw_kernel<<<roles * splits, kThreads, smem, st>>>(tmap_wd, tmap_h, b_out, labels, tlen, ulen, lse,
+                                                                gamma2, grad_cost, B, T, U1, J, V, blank, splits,
+                                                                d_w_out, d_b_out);
+        EMO_CHECK_LAUNCH("joint_dw_kernel");
+    }
     return EMO_OK;
 }
 

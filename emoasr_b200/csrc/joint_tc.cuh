@@ -24,6 +24,14 @@ struct TileInfo {
     int b, first_cell, n_cells, U1b;  // n_cells = valid cells of the utterance
 };
 
+// h cache: tanh output of every valid cell in bf16, written by the forward kernel and read by the
+// backward kernels.  Layout [B * tiles128_per_utt * 128, J], row = (b * tiles128_per_utt +
+// first_cell / 128) * 128 + row-in-tile; tiles128_per_utt is even so a CTA pair always owns two slots.
+__host__ __device__ inline int tiles128_per_utt(int T, int U1) { return 2 * ((T * U1 + 255) / 256); }
+inline size_t hcache_bytes_for(int B, int T, int U1, int J) {
+    return (size_t)B * tiles128_per_utt(T, U1) * kTileM * J * sizeof(__nv_bfloat16);
+}
+
 // kCtas = 1: one CTA per 128-cell tile.  kCtas = 2: a CTA pair (cluster of 2, cta_group::2) per
 // 256-cell tile, 128 cells per CTA; `rank` selects this CTA's half.  Both CTAs of a pair get the
 // same answer.
@@ -137,8 +145,8 @@ int make_tmap_bf16_2d(CUtensorMap* map, const void* base, uint64_t inner, uint64
 int check_bf16_shape(int B, int T, int U1, int J, int V, int blank) {
     EMO_REQUIRE(B > 0 && T > 0 && U1 > 0 && J > 0 && V > 0, EMO_BAD_ARG, "joint(bf16): bad sizes");
     EMO_REQUIRE(blank >= 0 && blank < V, EMO_BAD_ARG, "joint(bf16): blank %d outside [0,%d)", blank, V);
-    EMO_REQUIRE(J % kBlockK == 0 && J <= kMaxKBlocks * kBlockK, EMO_UNSUPPORTED_SHAPE,
-                "joint(bf16): joint_hidden_size %d must be a multiple of 64 and <= 512 "
+    EMO_REQUIRE(J % 128 == 0 && J <= kMaxKBlocks * kBlockK, EMO_UNSUPPORTED_SHAPE,
+                "joint(bf16): joint_hidden_size %d must be a multiple of 128 and <= 512 "
                 "(use precision fp32 for other sizes)", J);
     EMO_REQUIRE(V % 32 == 0, EMO_UNSUPPORTED_SHAPE,
                 "joint(bf16): vocab %d must be a multiple of 32 (use precision fp32)", V);

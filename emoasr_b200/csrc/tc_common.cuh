@@ -62,6 +62,25 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
         : "memory");
 }
 
+// 2D tile store shared -> global (bulk async-group completion)
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int x, int y) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
+                 "r"(src_smem), "r"(x), "r"(y)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+// all but the newest N store groups have finished READING shared memory
+template <int N>
+__device__ __forceinline__ void tma_store_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+template <int N>
+__device__ __forceinline__ void tma_store_wait_all() {
+    asm volatile("cp.async.bulk.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---------------- TMEM ----------------
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
@@ -196,26 +215,19 @@ __device__ __forceinline__ uint32_t mapa_shared(uint32_t addr, uint32_t rank) {
     return r;
 }
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr)
-                 : "memory");
+    // default .release.cta semantics (as CUTLASS' ClusterBarrier::arrive(cta_id)): a cluster-scope
+    // release would cost a MEMBAR.ALL.GPU per arrive
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_addr, uint32_t bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(
-                     cluster_addr),
+    asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_addr),
                  "r"(bytes)
                  : "memory");
 }
+// waits on a LOCAL barrier that peer-CTA threads also arrive on; default acquire.cta (a
+// cluster-scope acquire would invalidate L1 on every probe)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    while (!ok) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-    }
+    mbar_wait(bar, parity);
 }
 // TMA tile load executed by either CTA of a pair; completion bytes go to the LEADER's mbarrier
 __device__ __forceinline__ void tma_load_2d_pair(uint32_t dst_smem, const CUtensorMap* m, int x,

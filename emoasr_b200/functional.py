@@ -165,8 +165,13 @@ class _RNNTJoint(torch.autograd.Function):
             ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
             lp2 = torch.empty(B, T, U1, 2, device=dev)
             lse = torch.empty(B, T, U1, device=dev)
+            # bf16 mode: tanh output of every valid cell, written by the forward kernel for the backward
+            hbytes = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HCACHE, precision, B, T, U1, J, V)
+            need_h = hbytes > 0 and any(ctx.needs_input_grad[:4])
+            hcache = torch.empty(hbytes, dtype=torch.uint8, device=dev) if need_h else None
             _lib.check(lib.emo_rnnt_joint_fwd(_p(enc), _p(dec), _p(w), _p(bo), _p(labels), _p(tlen), _p(ulen),
                                               B, T, U1, J, V, blank, precision, _p(lp2), _p(lse),
+                                              _p(hcache), hbytes if need_h else 0,
                                               _p(ws), ws.numel(), _stream()), "emo_rnnt_joint_fwd")
             alpha = torch.empty(B, T, U1, device=dev)
             beta = torch.empty(B, T, U1, device=dev)
@@ -176,6 +181,7 @@ class _RNNTJoint(torch.autograd.Function):
                                                     _p(beta), _p(cost), _p(gamma2), _stream()),
                        "emo_rnnt_lattice_fwd_bwd")
         ctx.save_for_backward(enc, dec, w, bo, labels, tlen, ulen, lse, gamma2)
+        ctx.hcache = hcache
         ctx.cfg = (blank, precision)
         return cost
 
@@ -195,10 +201,14 @@ class _RNNTJoint(torch.autograd.Function):
             d_dec = torch.empty_like(dec)
             d_w = torch.empty_like(w)
             d_b = torch.empty_like(bo)
+            hcache = ctx.hcache
             _lib.check(lib.emo_rnnt_joint_bwd(_p(enc), _p(dec), _p(w), _p(bo), _p(labels), _p(tlen), _p(ulen),
-                                              _p(lse), _p(gamma2), _p(g), B, T, U1, J, V, blank, precision,
+                                              _p(lse), _p(gamma2), _p(g), _p(hcache),
+                                              hcache.numel() if hcache is not None else 0,
+                                              B, T, U1, J, V, blank, precision,
                                               _p(d_enc), _p(d_dec), _p(d_w), _p(d_b), _p(ws), ws.numel(),
                                               _stream()), "emo_rnnt_joint_bwd")
+            ctx.hcache = None
         return d_enc, d_dec, d_w, d_b, None, None, None, None, None
 
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define EMO_ABI_VERSION 1
+#define EMO_ABI_VERSION 2
 
 enum emo_status {
     EMO_OK = 0,
@@ -53,7 +53,8 @@ enum emo_precision {
 enum emo_op {
     EMO_OP_RNNT_JOINT_FWD = 0,
     EMO_OP_RNNT_JOINT_BWD = 1,
-    EMO_OP_CTC = 2
+    EMO_OP_CTC = 2,
+    EMO_OP_RNNT_JOINT_HCACHE = 3 /* emo_workspace_bytes only: size of the h cache shared by fwd and bwd */
 };
 
 int emo_abi_version(void);
@@ -105,12 +106,16 @@ int emo_rnnt_dense_bwd(const float* gamma2_ws, const int* labels, const int* tle
  *   lse[b,t,u] = logsumexp_v z;  lp2[b,t,u] = {z[blank]-lse, z[labels[b,u]]-lse (u < ulen[b])}.
  * The (B,T,U1,V) logits are never written to memory in EMO_PREC_BF16; EMO_PREC_FP32 streams
  * them through a bounded slab inside `ws`.
+ * hcache (EMO_PREC_BF16 only; emo_workspace_bytes(EMO_OP_RNNT_JOINT_HCACHE, ...) bytes, 256-byte
+ * aligned): receives h in bf16 for every valid cell, tile-major; the caller keeps it until
+ * emo_rnnt_joint_bwd.  May be NULL for a forward-only call (inference / validation); ignored
+ * (may be NULL, 0) in EMO_PREC_FP32.
  */
 int emo_rnnt_joint_fwd(const float* enc_proj, const float* dec_proj,
                        const float* w_out, const float* b_out,
                        const int* labels, const int* tlen, const int* ulen,
                        int B, int T, int U1, int J, int V, int blank, int precision,
-                       float* lp2, float* lse,
+                       float* lp2, float* lse, void* hcache, size_t hcache_bytes,
                        void* ws, size_t ws_bytes, void* stream);
 
 /* Backward of cost (B) w.r.t. enc_proj, dec_proj, w_out, b_out given grad_cost (B):
@@ -119,11 +124,13 @@ int emo_rnnt_joint_fwd(const float* enc_proj, const float* dec_proj,
  * recomputed tile by tile and contracted on the fly:
  *   d_w_out (V,J) = sum dz^T h ; d_b_out (V) = sum dz ; dh = dz w_out ;
  *   dpre = dh (1-h^2) ; d_enc_proj[b,t] = sum_u dpre ; d_dec_proj[b,u] = sum_t dpre.
- * All four outputs are overwritten (not accumulated into). */
+ * All four outputs are overwritten (not accumulated into).  hcache: what emo_rnnt_joint_fwd wrote
+ * for the same inputs (required in EMO_PREC_BF16). */
 int emo_rnnt_joint_bwd(const float* enc_proj, const float* dec_proj,
                        const float* w_out, const float* b_out,
                        const int* labels, const int* tlen, const int* ulen,
                        const float* lse, const float* gamma2, const float* grad_cost,
+                       const void* hcache, size_t hcache_bytes,
                        int B, int T, int U1, int J, int V, int blank, int precision,
                        float* d_enc_proj, float* d_dec_proj, float* d_w_out, float* d_b_out,
                        void* ws, size_t ws_bytes, void* stream);

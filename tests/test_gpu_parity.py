@@ -282,8 +282,10 @@ def _joint_fwd_raw(enc, dec_, w_out, b_out, ys, tl, ul, precision):
     lp2 = torch.zeros(B, T, U1, 2, device=dev())
     lse = torch.zeros(B, T, U1, device=dev())
     p = lambda t: ctypes.c_void_p(t.data_ptr())
+    hb = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HCACHE, precision, B, T, U1, J, V)
+    hc = torch.empty(max(hb, 256), dtype=torch.uint8, device=dev())
     rc = lib.emo_rnnt_joint_fwd(p(te[0]), p(te[1]), p(te[2]), p(te[3]), p(lab), p(tlen), p(ulen), B, T, U1, J, V,
-                                0, precision, p(lp2), p(lse), p(ws), ws.numel(),
+                                0, precision, p(lp2), p(lse), p(hc) if hb else None, hb, p(ws), ws.numel(),
                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "emo_rnnt_joint_fwd")
     torch.cuda.synchronize()
@@ -292,8 +294,9 @@ def _joint_fwd_raw(enc, dec_, w_out, b_out, ys, tl, ul, precision):
 
 BF16_SHAPES = [
     # B, T, U, V, J
-    (1, 8, 7, 32, 64),        # one tile, one vocab chunk, one K block
-    (2, 16, 7, 256, 64),      # exactly one full chunk
+    (1, 8, 7, 32, 128),       # one tile, one vocab chunk, one J-part of two K blocks
+    (2, 16, 7, 256, 128),     # exactly one full chunk
+    (2, 9, 5, 160, 384),      # J = 384: a full and a half J-part, odd number of slot pairs
     (2, 20, 12, 288, 128),    # partial last vocab chunk (TMA out-of-bounds rows), 2 K blocks
     (3, 40, 15, 1024, 512),   # cfg-3 vocabulary / joint width, several tiles per CTA
     (2, 150, 30, 512, 256),   # many tiles
