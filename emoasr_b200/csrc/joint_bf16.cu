@@ -91,8 +91,45 @@ __device__ __forceinline__ void lse_group(const uint32_t (&r)[32], const float* 
 // stages only half (128 vocab rows) of every w_out tile.  Barrier topology for the pair:
 //   b_full / a_full / acc_empty live in the LEADER (arrivals from both CTAs, TMA bytes from both),
 //   b_empty / a_empty / acc_full are signalled in BOTH CTAs by a multicast tcgen05.commit.
+constexpr int kFwdThreads = 512;  // 4 control warps, 4 epilogue warps, 8 A-producer warps
+template <int N> __device__ __forceinline__ void reg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N> __device__ __forceinline__ void reg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+// A-operand producer: this warp's 16 rows of the 128-row tile, K block kb.
+// h = tanh(enc + dec) -> bf16 -> canonical K-major SW128 layout (16-byte chunk index XOR (row mod 8)).
+// All 16 loads of the block are issued before the first use (one latency per block).
+__device__ __forceinline__ void produce_h_block16(const float* __restrict__ enc, const float* __restrict__ dec,
+                                                  const uint32_t (&eoff)[4], const uint32_t (&doff)[4], int kb,
+                                                  int pw, int rsub, int c, uint8_t* blk) {
+    float4 e0[4], e1[4], d0[4], d1[4];
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const float* ep = enc + eoff[p] + kb * kBlockK;
+        const float* dp = dec + doff[p] + kb * kBlockK;
+        e0[p] = __ldg(reinterpret_cast<const float4*>(ep));
+        e1[p] = __ldg(reinterpret_cast<const float4*>(ep) + 1);
+        d0[p] = __ldg(reinterpret_cast<const float4*>(dp));
+        d1[p] = __ldg(reinterpret_cast<const float4*>(dp) + 1);
+    }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int row = pw * 16 + p * 4 + rsub;
+        uint4 o;
+        o.x = pack_bf16x2(tanh_approx(e0[p].x + d0[p].x), tanh_approx(e0[p].y + d0[p].y));
+        o.y = pack_bf16x2(tanh_approx(e0[p].z + d0[p].z), tanh_approx(e0[p].w + d0[p].w));
+        o.z = pack_bf16x2(tanh_approx(e1[p].x + d1[p].x), tanh_approx(e1[p].y + d1[p].y));
+        o.w = pack_bf16x2(tanh_approx(e1[p].z + d1[p].z), tanh_approx(e1[p].w + d1[p].w));
+        uint8_t* dst = blk + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = o;
+    }
+}
+
 template <int kCtas>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFwdThreads, 1)
 joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
                  int store_h, const float* __restrict__ enc,
                  const float* __restrict__ dec, const float* __restrict__ b_out,
@@ -119,7 +156,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     const int tiles_per_utt = (T * U1 + kCtas * kTileM - 1) / (kCtas * kTileM);
     const int total_tiles = B * tiles_per_utt;
     const int tile0 = blockIdx.x / kCtas, tile_stride = gridDim.x / kCtas;
-    constexpr uint32_t kArrivals = 128 * kCtas;
+    constexpr uint32_t kArrivals = 128 * kCtas;   // epilogue threads of the pair
+    constexpr uint32_t kProducers = 256;          // A-producer threads per CTA
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kBStages; ++i) {
@@ -127,9 +165,9 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             mbar_init(smem_u32(&bars->b_empty[i]), 1);
         }
         for (int i = 0; i < kMaxKBlocks; ++i) {
-            mbar_init(smem_u32(&bars->a_full[i]), kArrivals);
+            mbar_init(smem_u32(&bars->a_full[i]), kProducers * kCtas);
             mbar_init(smem_u32(&bars->a_empty[i]), store_h ? 2 : 1);  // MMA commit (+ h store done)
-            mbar_init(smem_u32(&bars->h_ready[i]), 128);
+            mbar_init(smem_u32(&bars->h_ready[i]), kProducers);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->acc_full[i]), 1);
@@ -149,7 +187,9 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     if (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
-
+    // register budget per warpgroup: control 56, epilogue 216, producers 104 (x128 threads: 61440 <= 64K)
+    if (warp < 4) {
+    reg_dec<56>();
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -248,7 +288,9 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             }
             tma_store_wait_all<0>();
         }
-    } else if (warp >= 4 && warp < 8) {
+    }
+    } else if (warp < 8) {
+        reg_inc<216>();
         // ===================== epilogue: online LSE over vocab chunks =====================
         const int q = warp & 3;
         const int row = q * 32 + lane;
@@ -312,19 +354,20 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 lse_out[cell] = l;
             }
         }
-    } else if (warp >= 8) {
+    } else {
+        reg_dec<104>();
         // ===================== A producers =====================
-        const int pw = warp - 8;
+        const int pw = warp - 8;       // 8 producer warps, 16 rows each
         const int c = lane & 7;        // 16-byte chunk (8 bf16) inside the 128-byte row
         const int rsub = lane >> 3;    // 4 rows per warp pass
         uint32_t tl = 0;
         TileInfo ti;
         for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
             if (!tile_info<kCtas>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
-            uint32_t eoff[8], doff[8];  // element offsets of this lane's 8 rows
+            uint32_t eoff[4], doff[4];  // element offsets of this lane's 4 rows
 #pragma unroll
-            for (int p = 0; p < 8; ++p) {
-                int row = pw * 32 + p * 4 + rsub;
+            for (int p = 0; p < 4; ++p) {
+                int row = pw * 16 + p * 4 + rsub;
                 int m = min(ti.first_cell + row, ti.n_cells - 1);  // clamp padding rows
                 int t = m / ti.U1b, u = m - t * ti.U1b;
                 eoff[p] = (uint32_t)(((size_t)ti.b * T + t) * J) + c * 8;
@@ -332,7 +375,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             }
             for (int kb = 0; kb < KB; ++kb) {
                 mbar_wait(smem_u32(&bars->a_empty[kb]), (tl & 1) ^ 1);
-                produce_h_block(enc, dec, eoff, doff, kb, pw, rsub, c, sA + (size_t)kb * kABlockBytes);
+                produce_h_block16(enc, dec, eoff, doff, kb, pw, rsub, c, sA + (size_t)kb * kABlockBytes);
                 fence_proxy_async_smem();
                 if (store_h) mbar_arrive(smem_u32(&bars->h_ready[kb]));
                 if (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->a_full[kb]), 0));
@@ -393,7 +436,7 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
         const int pairs = min(ptiles, sm_count() / 2);
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(2 * pairs);
-        cfg.blockDim = dim3(kThreads);
+        cfg.blockDim = dim3(kFwdThreads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
@@ -415,7 +458,7 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     EMO_CUDA(cudaFuncSetAttribute(joint_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = B * ceil_div((size_t)T * U1, kTileM);
     if (!store_h) tmap_h = tmap;
-    joint_fwd_kernel<1><<<min(tiles, sm_count()), kThreads, smem, st>>>(tmap, tmap_h, store_h, enc_proj, dec_proj,
+    joint_fwd_kernel<1><<<min(tiles, sm_count()), kFwdThreads, smem, st>>>(tmap, tmap_h, store_h, enc_proj, dec_proj,
                                                                         b_out, labels, tlen, ulen, B, T, U1, J, V,
                                                                         blank, lp2, lse);
     EMO_CHECK_LAUNCH("joint_fwd_kernel<single>");
