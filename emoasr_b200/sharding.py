@@ -1,0 +1,83 @@
+"""Batch sharding + gradient all-reduce for the process-per-GPU data-parallel mode.
+
+Replaces the reference's single-process ``nn.DataParallel`` (asr/train_asr.py:237-240): rank r takes
+utterances [r*B_local, (r+1)*B_local) of the global batch, runs the whole path locally (no data-path
+collective: every utterance's joint tiles and lattice are independent) and only the parameter
+gradients are summed over ranks -- NCCL over NVLink on GPUs, gloo in the CPU tests.
+
+Loss semantics kept from the reference (train_asr.py:67-71): mean over the local batch, then mean
+over replicas -> gradients are all-reduced with SUM and divided by the world size.
+"""
+import torch
+import torch.distributed as dist
+
+BATCH_KEYS = ("xs", "xlens", "ys", "ylens", "ys_in", "ys_out", "ps", "plens")
+
+
+def shard_range(global_batch, rank, world):
+    """[lo, hi) of the utterances rank `rank` owns; shards differ by at most one utterance."""
+    base, rem = divmod(global_batch, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(batch, rank, world):
+    """Slice every per-utterance tensor of a reference-style batch dict (asr/datasets.py:146-186)."""
+    B = next(v for v in batch.values() if torch.is_tensor(v)).size(0)
+    lo, hi = shard_range(B, rank, world)
+    return {k: (v[lo:hi] if torch.is_tensor(v) and v.dim() > 0 and v.size(0) == B else v) for k, v in batch.items()}
+
+
+class GradBuckets:
+    """Flat gradient buckets (default ~25 MB) all-reduced asynchronously, then averaged.
+
+    ``start()`` launches one all-reduce per bucket (they overlap with whatever the caller enqueues
+    next, e.g. the encoder backward); ``finish()`` waits, divides by the world size and scatters the
+    result back into ``p.grad``.
+    """
+
+    def __init__(self, params, bucket_bytes=25 << 20, group=None):
+        self.params = [p for p in params if p.requires_grad]
+        self.group = group
+        self.buckets, cur, size = [], [], 0
+        for p in self.params:
+            n = p.numel() * p.element_size()
+            if cur and size + n > bucket_bytes:
+                self.buckets.append(cur)
+                cur, size = [], 0
+            cur.append(p)
+            size += n
+        if cur:
+            self.buckets.append(cur)
+        self._pending = []
+
+    def start(self):
+        self._pending = []
+        for bucket in self.buckets:
+            grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
+            flat = torch._utils._flatten_dense_tensors(grads)
+            work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+            self._pending.append((bucket, grads, flat, work))
+
+    def finish(self):
+        world = dist.get_world_size(self.group)
+        for bucket, grads, flat, work in self._pending:
+            work.wait()
+            flat.div_(world)
+            for p, g, r in zip(bucket, grads, torch._utils._unflatten_dense_tensors(flat, grads)):
+                if p.grad is None:
+                    p.grad = r.clone()
+                else:
+                    p.grad.copy_(r)
+        self._pending = []
+
+    def allreduce(self):
+        self.start()
+        self.finish()
+
+
+def mean_over_replicas(value, group=None):
+    """Logging-only scalar: mean of the per-replica values (train_asr.py:67-71)."""
+    t = value.detach().clone()
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t / dist.get_world_size(group)

@@ -1,0 +1,88 @@
+"""World-size-2 gloo tests (CPU) of the batch-sharded data-parallel host logic
+(emoasr_b200/sharding.py): shard ranges, bucketed gradient all-reduce, mean-of-replica-means
+normalisation (asr/train_asr.py:67-71).  The per-rank loss is the oracle's CPU restatement of the
+path -- on the GPU box the same host logic drives the CUDA kernels (bench.py --gpus N)."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from emoasr_b200 import sharding
+
+
+def test_shard_ranges_cover_batch_exactly_once():
+    for B in (1, 7, 8, 32, 33):
+        for world in (1, 2, 3, 8):
+            spans = [sharding.shard_range(B, r, world) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == B
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_batch_slices_only_per_utterance_tensors():
+    batch = {"xs": torch.arange(24.).view(4, 3, 2), "xlens": torch.tensor([3, 3, 2, 1]), "utt_ids": ["a", "b", "c", "d"],
+             "scalar": torch.tensor(5)}
+    s = sharding.shard_batch(batch, 1, 2)
+    assert s["xs"].shape == (2, 3, 2) and torch.equal(s["xlens"], torch.tensor([2, 1]))
+    assert s["utt_ids"] == ["a", "b", "c", "d"] and int(s["scalar"]) == 5
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _make_problem():
+    g = torch.Generator().manual_seed(0)
+    B, T, U, V, He, Hd, J = 4, 9, 4, 13, 6, 5, 8
+    eouts = torch.randn(B, T, He, generator=g)
+    douts = torch.tanh(torch.randn(B, U + 1, Hd, generator=g))
+    ys = torch.randint(1, V, (B, U), generator=g)
+    tl = torch.tensor([9, 8, 9, 7])
+    ul = torch.tensor([4, 3, 4, 2])
+    torch.manual_seed(7)
+    lin = torch.nn.ModuleList([torch.nn.Linear(He, J), torch.nn.Linear(Hd, J), torch.nn.Linear(J, V)])
+    return eouts, douts, ys, tl, ul, lin
+
+
+def _loss(lin, eouts, douts, ys, tl, ul):
+    from oracle import torch_path
+    return torch_path.rnnt_joint_loss(eouts, douts, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias,
+                                      lin[2].weight, lin[2].bias, ys, tl, ul, blank=0)
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    eouts, douts, ys, tl, ul, lin = _make_problem()
+    batch = sharding.shard_batch({"eouts": eouts, "douts": douts, "ys": ys, "tl": tl, "ul": ul}, rank, world)
+    loss = _loss(lin, batch["eouts"], batch["douts"], batch["ys"], batch["tl"], batch["ul"])
+    loss.backward()
+    buckets = sharding.GradBuckets(lin.parameters(), bucket_bytes=256)   # tiny buckets: several all-reduces
+    assert len(buckets.buckets) > 1
+    buckets.start()
+    buckets.finish()
+    mean_loss = sharding.mean_over_replicas(loss)
+    if rank == 0:
+        torch.save({"loss": mean_loss, "grads": [p.grad.clone() for p in lin.parameters()]}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharded_step_matches_single_process(tmp_path):
+    out = str(tmp_path / "rank0.pt")
+    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    eouts, douts, ys, tl, ul, lin = _make_problem()
+    loss = _loss(lin, eouts, douts, ys, tl, ul)      # global mean over the 4 utterances
+    loss.backward()
+    assert abs(float(got["loss"]) - float(loss)) < 1e-5 * abs(float(loss))
+    for p, g in zip(lin.parameters(), got["grads"]):
+        assert np.allclose(g.numpy(), p.grad.numpy(), rtol=1e-4, atol=1e-6)
