@@ -27,8 +27,8 @@ _SIGNATURES = {
     "emo_rnnt_dense_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "emo_rnnt_joint_fwd": (_I, [_P] * 7 + [_I] * 7 + [_P, _P, _P, _SZ, _P, _SZ, _P]),
     "emo_rnnt_joint_bwd": (_I, [_P] * 10 + [_P, _SZ] + [_I] * 7 + [_P, _P, _P, _P, _P, _SZ, _P]),
-    "emo_ctc_fwd": (_I, [_P] * 4 + [_I] * 6 + [_P, _P, _P, _P]),
-    "emo_ctc_bwd": (_I, [_P] * 8 + [_I] * 6 + [_P, _P, _P]),
+    "emo_ctc_fwd": (_I, [_P] * 4 + [_I] * 6 + [_P, _P, _P, _P, _P]),
+    "emo_ctc_bwd": (_I, [_P] * 8 + [_I] * 6 + [_P, _I, _P, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -61,7 +61,7 @@ extern "C" int emo_launch_count(int op, int precision, int B, int T, int U1, int
             return precision == EMO_PREC_BF16 ? joint_bf16_launches(op, B, T, U1, J, V)
                                               : joint_f32_launches(op, B, T, U1, J, V);
         case EMO_OP_CTC:
-            return 4;  // row lse, alpha, beta/occupancy, gradient
+            return 3;  // row lse + emission gather, alpha || beta lattices, gradient
         default:
             return 0;
     }

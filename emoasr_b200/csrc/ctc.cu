@@ -17,7 +17,7 @@
 namespace emo {
 namespace {
 
-constexpr int kPrefetch = 4;
+constexpr int kPrefetch = 8;
 constexpr int kRowThreads = 256;
 
 __device__ __forceinline__ float block_reduce_lse(float m, float s, float* sm_m, float* sm_s) {
@@ -42,49 +42,6 @@ __device__ __forceinline__ float block_reduce_lse(float m, float s, float* sm_m,
     return m + logf(s);
 }
 
-// grid-stride over rows r = b*T + t
-__global__ void __launch_bounds__(kRowThreads)
-ctc_row_lse_kernel(const float* __restrict__ logits, const long long* __restrict__ tlen, int B,
-                   int T, int V, float* __restrict__ lse) {
-    __shared__ float sm_m[32], sm_s[32];
-    const int rows = B * T;
-    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-        int b = r / T, t = r - b * T;
-        long long T_b = tlen[b];
-        if (t >= T_b) {
-            if (threadIdx.x == 0) lse[r] = 0.f;
-            continue;  // uniform
-        }
-        const float* row = logits + (size_t)r * V;
-        float m = kNegInf, s = 0.f;
-        if ((V & 3) == 0) {
-            const float4* row4 = reinterpret_cast<const float4*>(row);
-            int n4 = V >> 2;
-            for (int i = threadIdx.x; i < n4; i += kRowThreads) {
-                float4 x = __ldg(row4 + i);
-                float mx = fmaxf(fmaxf(x.x, x.y), fmaxf(x.z, x.w));
-                float mn = fmaxf(m, mx);
-                if (mn > kNegInf) {
-                    s = s * expf(m - mn) + expf(x.x - mn) + expf(x.y - mn) + expf(x.z - mn) +
-                        expf(x.w - mn);
-                    m = mn;
-                }
-            }
-        } else {
-            for (int i = threadIdx.x; i < V; i += kRowThreads) {
-                float x = __ldg(row + i);
-                float mn = fmaxf(m, x);
-                if (mn > kNegInf) {
-                    s = s * expf(m - mn) + expf(x - mn);
-                    m = mn;
-                }
-            }
-        }
-        float l = block_reduce_lse(m, s, sm_m, sm_s);
-        if (threadIdx.x == 0) lse[r] = l;
-    }
-}
-
 struct Ext {
     int label;   // l'_s
     bool skip;   // transition s-2 -> s allowed
@@ -104,19 +61,90 @@ __device__ __forceinline__ Ext ext_state(const long long* __restrict__ y, int s,
     return e;
 }
 
-// One CTA per utterance; blockDim.x = S rounded up to a warp.  Thread s owns extended state s.
-// alpha_t / beta_t of the previous frame live in a double-buffered shared array padded by two
-// -inf guards on each side, so the three-way recursion is three shared loads and one barrier.
-template <bool kBackward>
+constexpr int kRowVec = 12;  // float4 per thread held in registers (rows up to 12288 logits in one pass)
+
+// grid-stride over rows r = b*T + t.  One pass over the row (held in registers): max, sum exp, then
+// the gather of the S_b = 2 U_b + 1 emission log-probs lp_ext[r][s] = z[l'_s] - lse, written where
+// the alpha (and beta) recursion will find them -- the lattice kernels never touch the logits.
+__global__ void __launch_bounds__(kRowThreads)
+ctc_row_lse_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
+                   const long long* __restrict__ tlen, const long long* __restrict__ ulen, int B, int T,
+                   int V, int Umax, int blank, float* __restrict__ lse, float* __restrict__ lp_a,
+                   float* __restrict__ lp_b) {
+    __shared__ float sm_m[32], sm_s[32];
+    const int rows = B * T;
+    const int S = 2 * Umax + 1;
+    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
+        int b = r / T, t = r - b * T;
+        long long T_b = tlen[b];
+        if (t >= T_b) {
+            if (threadIdx.x == 0) lse[r] = 0.f;
+            continue;  // uniform
+        }
+        const float* row = logits + (size_t)r * V;
+        float m = kNegInf, s = 0.f;
+        if ((V & 3) == 0) {
+            const float4* row4 = reinterpret_cast<const float4*>(row);
+            const int n4 = V >> 2;
+            for (int base = 0; base < n4; base += kRowVec * kRowThreads) {
+                float4 x[kRowVec];
+#pragma unroll
+                for (int k = 0; k < kRowVec; ++k) {
+                    const int i = base + k * kRowThreads + threadIdx.x;
+                    x[k] = i < n4 ? __ldg(row4 + i) : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+                }
+                float mx = kNegInf;
+#pragma unroll
+                for (int k = 0; k < kRowVec; ++k)
+                    mx = fmaxf(mx, fmaxf(fmaxf(x[k].x, x[k].y), fmaxf(x[k].z, x[k].w)));
+                const float mn = fmaxf(m, mx);
+                if (mn > kNegInf) {
+                    float acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < kRowVec; ++k)
+                        acc += __expf(x[k].x - mn) + __expf(x[k].y - mn) + __expf(x[k].z - mn) + __expf(x[k].w - mn);
+                    s = s * __expf(m - mn) + acc;
+                    m = mn;
+                }
+            }
+        } else {
+            for (int i = threadIdx.x; i < V; i += kRowThreads) {
+                float x = __ldg(row + i);
+                float mn = fmaxf(m, x);
+                if (mn > kNegInf) {
+                    s = s * expf(m - mn) + expf(x - mn);
+                    m = mn;
+                }
+            }
+        }
+        float l = block_reduce_lse(m, s, sm_m, sm_s);
+        if (threadIdx.x == 0) lse[r] = l;
+        // gather the emissions of the blank-extended label sequence (the row is L1/L2-hot)
+        long long U_bl = ulen[b];
+        const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
+        const int S_b = 2 * U_b + 1;
+        const long long* y = labels + (size_t)b * Umax;
+        for (int st = threadIdx.x; st < S_b; st += kRowThreads) {
+            const float v = __ldg(row + ext_state(y, st, S_b, blank, V).label) - l;
+            lp_a[(size_t)r * S + st] = v;
+            if (lp_b) lp_b[(size_t)r * S + st] = v;
+        }
+    }
+}
+
+// grid (B, 2): y = 0 alpha, y = 1 beta; blockDim.x = S rounded up to a warp.  Thread s owns extended
+// state s.  The previous frame lives in a double-buffered shared array padded by -inf guards, so the
+// three-way recursion is three shared loads and one barrier per frame.  Emissions lp_ext[t][s] are
+// read from the slot the result is written to (prefetched kPrefetch frames ahead, so the read of a
+// slot always precedes its overwrite).  alpha_t and beta_t both include the emission at t.
 __global__ void __launch_bounds__(1024, 1)
-ctc_lattice_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
-                   const long long* __restrict__ tlen, const long long* __restrict__ ulen,
-                   const float* __restrict__ lse, int T, int V, int Umax, int blank,
-                   int zero_infinity, float* __restrict__ alpha_ws /* fwd: out; bwd: in */,
-                   float* __restrict__ nll /* fwd: out */, float* __restrict__ occ_ws /* bwd: out */) {
+ctc_lattice_kernel(const long long* __restrict__ labels, const long long* __restrict__ tlen,
+                   const long long* __restrict__ ulen, int T, int V, int Umax, int blank,
+                   int zero_infinity, int first_dir, float* __restrict__ alpha_ws,
+                   float* __restrict__ beta_ws, float* __restrict__ nll) {
     __shared__ float buf[2][1024 + 4];
-    __shared__ float sm_ll;
     const int b = blockIdx.x;
+    const bool backward = (int)blockIdx.y + first_dir == 1;
     const int S = 2 * Umax + 1;
     const int s = threadIdx.x;
     long long T_bl = tlen[b], U_bl = ulen[b];
@@ -124,44 +152,21 @@ ctc_lattice_kernel(const float* __restrict__ logits, const long long* __restrict
     const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
     const int S_b = 2 * U_b + 1;
     const long long* y = labels + (size_t)b * Umax;
-    const Ext me = ext_state(y, s, S_b, blank, V);
-    const bool jump = kBackward ? ext_state(y, s + 2, S_b, blank, V).skip : me.skip;
+    const bool jump = backward ? ext_state(y, s + 2, S_b, blank, V).skip : ext_state(y, s, S_b, blank, V).skip;
     const bool valid = s < S_b;
-    const float* lg_b = logits + (size_t)b * T * V;
-    const float* lse_b = lse + (size_t)b * T;
-    float* alpha_b = alpha_ws + (size_t)b * T * S;
-    float* occ_b = kBackward ? occ_ws + (size_t)b * T * S : nullptr;
+    float* io = (backward ? beta_ws : alpha_ws) + (size_t)b * T * S;
+    const int nb = backward ? 1 : -1;  // neighbour direction in state space
 
     for (int i = threadIdx.x; i < 2 * (1024 + 4); i += blockDim.x) (&buf[0][0])[i] = kNegInf;
-
-    auto frame = [&](int i) { return kBackward ? T_b - 1 - i : i; };
-    auto load = [&](int i) -> float {
-        if (valid && i < T_b) {
-            int t = frame(i);
-            return __ldg(lg_b + (size_t)t * V + me.label) - __ldg(lse_b + t);
-        }
-        return kNegInf;
-    };
-
-    float ll = 0.f;
-    if (kBackward) {
-        if (s == 0) {
-            float a1 = alpha_b[(size_t)(T_b - 1) * S + S_b - 1];
-            float a2 = S_b > 1 ? alpha_b[(size_t)(T_b - 1) * S + S_b - 2] : kNegInf;
-            sm_ll = log_add_exp(a1, a2);
-        }
-    }
     __syncthreads();
-    if (kBackward) ll = sm_ll;
-    const bool feasible = ll > kNegInf && ll == ll && ll < INFINITY;
 
-    auto load_alpha = [&](int i) -> float {
-        if (kBackward && valid && i < T_b) return alpha_b[(size_t)frame(i) * S + s];
-        return kNegInf;
+    auto frame = [&](int i) { return backward ? T_b - 1 - i : i; };
+    auto load = [&](int i) -> float {
+        return (valid && i < T_b) ? io[(size_t)frame(i) * S + s] : kNegInf;
     };
-    float ring[kPrefetch], ring_a[kPrefetch];
+    float ring[kPrefetch];
 #pragma unroll
-    for (int k = 0; k < kPrefetch; ++k) { ring[k] = load(k); ring_a[k] = load_alpha(k); }
+    for (int k = 0; k < kPrefetch; ++k) ring[k] = load(k);
 
     for (int i0 = 0; i0 < T_b; i0 += kPrefetch) {
 #pragma unroll
@@ -169,39 +174,28 @@ ctc_lattice_kernel(const float* __restrict__ logits, const long long* __restrict
             const int i = i0 + k;
             if (i >= T_b) break;  // uniform
             const float lp = ring[k];
-            const float a_t = ring_a[k];
             ring[k] = load(i + kPrefetch);
-            ring_a[k] = load_alpha(i + kPrefetch);
-            const int t = frame(i);
             const float* prev = buf[(i + 1) & 1] + 2;  // previous frame, index by state
             float val = kNegInf;
             if (valid) {
                 if (i == 0) {
                     // forward: alpha_0(0), alpha_0(1); backward: beta_{T-1}(S-1), beta_{T-1}(S-2)
-                    bool init = kBackward ? (s >= S_b - 2) : (s < 2);
+                    const bool init = backward ? (s >= S_b - 2) : (s < 2);
                     val = init ? lp : kNegInf;
                 } else {
-                    float a = prev[s];
-                    float n1 = kBackward ? prev[s + 1] : prev[s - 1];
-                    float n2 = jump ? (kBackward ? prev[s + 2] : prev[s - 2]) : kNegInf;
-                    float m = fmaxf(fmaxf(a, n1), n2);
+                    const float a = prev[s];
+                    const float n1 = prev[s + nb];
+                    const float n2 = jump ? prev[s + 2 * nb] : kNegInf;
+                    const float m = fmaxf(fmaxf(a, n1), n2);
                     if (m > kNegInf) val = m + logf(expf(a - m) + expf(n1 - m) + expf(n2 - m)) + lp;
                 }
-                if (!kBackward) {
-                    alpha_b[(size_t)t * S + s] = val;
-                } else {
-                    // state posterior: alpha and beta both contain the emission at t
-                    float o = 0.f;
-                    if (feasible && a_t > kNegInf && val > kNegInf && lp > kNegInf)
-                        o = expf(a_t + val - lp - ll);
-                    occ_b[(size_t)t * S + s] = o;
-                }
+                io[(size_t)frame(i) * S + s] = val;
             }
             buf[i & 1][2 + s] = val;
             __syncthreads();
         }
     }
-    if (!kBackward && s == 0) {
+    if (!backward && s == 0) {
         const float* last = buf[(T_b - 1) & 1] + 2;
         float l = log_add_exp(last[S_b - 1], S_b > 1 ? last[S_b - 2] : kNegInf);
         float v = -l;
@@ -211,12 +205,13 @@ ctc_lattice_kernel(const float* __restrict__ logits, const long long* __restrict
 }
 
 // Persistent CTAs, grid-stride over rows (b,t).  acc[V] in dynamic shared memory stays zero
-// between rows: only the touched entries are cleared again.
+// between rows: only the touched entries are cleared again.  The state posteriors
+// occ_t(s) = exp(alpha_t(s) + beta_t(s) - lp_t(l'_s) - ll) are formed here from the two lattices.
 __global__ void __launch_bounds__(kRowThreads)
 ctc_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
                 const long long* __restrict__ tlen, const long long* __restrict__ ulen,
                 const float* __restrict__ lse, const float* __restrict__ alpha_ws,
-                const float* __restrict__ occ_ws, const float* __restrict__ grad_nll, int B, int T,
+                const float* __restrict__ beta_ws, const float* __restrict__ grad_nll, int B, int T,
                 int V, int Umax, int blank, float* __restrict__ grad) {
     extern __shared__ float acc[];  // V floats
     const int S = 2 * Umax + 1;
@@ -232,8 +227,8 @@ ctc_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ 
         float* grow = grad + (size_t)r * V;
         // feasibility of the utterance from the last alphas (same test as the forward kernel)
         const float* alast = alpha_ws + ((size_t)b * T + (T_b - 1)) * S;
-        float l = log_add_exp(alast[S_b - 1], S_b > 1 ? alast[S_b - 2] : kNegInf);
-        bool feasible = l > kNegInf && l == l && l < INFINITY;
+        const float l = log_add_exp(alast[S_b - 1], S_b > 1 ? alast[S_b - 2] : kNegInf);
+        const bool feasible = l > kNegInf && l == l && l < INFINITY;
         if (t >= T_b || !feasible) {  // uniform over the CTA
             if ((V & 3) == 0) {
                 float4* g4 = reinterpret_cast<float4*>(grow);
@@ -245,19 +240,20 @@ ctc_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ 
             continue;
         }
         const long long* y = labels + (size_t)b * Umax;
-        const float* occ = occ_ws + (size_t)r * S;
+        const float row_lse = lse[r];
+        const float* row = logits + (size_t)r * V;
+        const float* al = alpha_ws + (size_t)r * S;
+        const float* be = beta_ws + (size_t)r * S;
         for (int s = threadIdx.x; s < S_b; s += kRowThreads) {
-            int lab = blank;
-            if (s & 1) {
-                long long ll_ = y[s >> 1];
-                lab = (int)(ll_ < 0 ? 0 : (ll_ >= V ? V - 1 : ll_));
+            const int lab = ext_state(y, s, S_b, blank, V).label;
+            const float a = al[s], bt = be[s];
+            if (a > kNegInf && bt > kNegInf) {
+                const float lp = __ldg(row + lab) - row_lse;
+                atomicAdd(&acc[lab], expf(a + bt - lp - l));
             }
-            atomicAdd(&acc[lab], occ[s]);
         }
         __syncthreads();
         const float g = grad_nll[b];
-        const float row_lse = lse[r];
-        const float* row = logits + (size_t)r * V;
         if ((V & 3) == 0) {
             const float4* row4 = reinterpret_cast<const float4*>(row);
             float4* g4 = reinterpret_cast<float4*>(grow);
@@ -277,15 +273,28 @@ ctc_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ 
                 grow[i] = g * (expf(__ldg(row + i) - row_lse) - acc[i]);
         }
         __syncthreads();
-        for (int s = threadIdx.x; s < S_b; s += kRowThreads) {
-            int lab = blank;
-            if (s & 1) {
-                long long ll_ = y[s >> 1];
-                lab = (int)(ll_ < 0 ? 0 : (ll_ >= V ? V - 1 : ll_));
-            }
-            acc[lab] = 0.f;
-        }
+        for (int s = threadIdx.x; s < S_b; s += kRowThreads)
+            acc[ext_state(y, s, S_b, blank, V).label] = 0.f;
         __syncthreads();
+    }
+}
+
+// lp_ext gather alone (backward called without a forward that staged beta)
+__global__ void ctc_gather_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
+                                  const long long* __restrict__ tlen, const long long* __restrict__ ulen,
+                                  const float* __restrict__ lse, int B, int T, int V, int Umax, int blank,
+                                  float* __restrict__ lp_out) {
+    const int S = 2 * Umax + 1;
+    const size_t n = (size_t)B * T * S;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int st = (int)(idx % S);
+        const size_t r = idx / S;
+        const int b = (int)(r / T), t = (int)(r % T);
+        long long U_bl = ulen[b];
+        const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
+        const int S_b = 2 * U_b + 1;
+        if (t < tlen[b] && st < S_b)
+            lp_out[idx] = __ldg(logits + r * V + ext_state(labels + (size_t)b * Umax, st, S_b, blank, V).label) - lse[r];
     }
 }
 
@@ -308,7 +317,7 @@ using namespace emo;
 
 extern "C" int emo_ctc_fwd(const float* logits, const long long* labels, const long long* tlen,
                            const long long* ulen, int B, int T, int V, int Umax, int blank,
-                           int zero_infinity, float* lse, float* alpha_ws, float* nll,
+                           int zero_infinity, float* lse, float* alpha_ws, float* beta_ws, float* nll,
                            void* stream) {
     int rc = check_ctc_args(logits, labels, tlen, ulen, B, T, V, Umax, blank);
     if (rc) return rc;
@@ -316,21 +325,23 @@ extern "C" int emo_ctc_fwd(const float* logits, const long long* labels, const l
     cudaStream_t st = (cudaStream_t)stream;
     int rows = B * T;
     int grid = min(rows, sm_count() * 8);
-    ctc_row_lse_kernel<<<grid, kRowThreads, 0, st>>>(logits, tlen, B, T, V, lse);
+    ctc_row_lse_kernel<<<grid, kRowThreads, 0, st>>>(logits, labels, tlen, ulen, B, T, V, Umax, blank, lse,
+                                                     alpha_ws, beta_ws);
     EMO_CHECK_LAUNCH("ctc_row_lse_kernel");
     int S = 2 * Umax + 1;
     int threads = (S + 31) / 32 * 32;
-    ctc_lattice_kernel<false><<<B, threads, 0, st>>>(logits, labels, tlen, ulen, lse, T, V, Umax,
-                                                     blank, zero_infinity, alpha_ws, nll, nullptr);
-    EMO_CHECK_LAUNCH("ctc_lattice_kernel<fwd>");
+    // alpha and (when the caller will differentiate) beta run side by side
+    ctc_lattice_kernel<<<dim3(B, beta_ws ? 2 : 1), threads, 0, st>>>(labels, tlen, ulen, T, V, Umax, blank,
+                                                                      zero_infinity, 0, alpha_ws, beta_ws, nll);
+    EMO_CHECK_LAUNCH("ctc_lattice_kernel");
     return EMO_OK;
 }
 
 extern "C" int emo_ctc_bwd(const float* logits, const long long* labels, const long long* tlen,
                            const long long* ulen, const float* lse, const float* alpha_ws,
                            const float* nll, const float* grad_nll, int B, int T, int V, int Umax,
-                           int blank, int zero_infinity, float* beta_ws, float* grad_logits,
-                           void* stream) {
+                           int blank, int zero_infinity, float* beta_ws, int beta_valid,
+                           float* grad_logits, void* stream) {
     int rc = check_ctc_args(logits, labels, tlen, ulen, B, T, V, Umax, blank);
     if (rc) return rc;
     EMO_REQUIRE(lse && alpha_ws && nll && grad_nll && beta_ws && grad_logits, EMO_BAD_ARG,
@@ -339,11 +350,16 @@ extern "C" int emo_ctc_bwd(const float* logits, const long long* labels, const l
                           // inf; torch yields NaN for inf without zero_infinity, we return 0)
     cudaStream_t st = (cudaStream_t)stream;
     int S = 2 * Umax + 1;
-    int threads = (S + 31) / 32 * 32;
-    ctc_lattice_kernel<true><<<B, threads, 0, st>>>(logits, labels, tlen, ulen, lse, T, V, Umax,
-                                                    blank, zero_infinity,
-                                                    const_cast<float*>(alpha_ws), nullptr, beta_ws);
-    EMO_CHECK_LAUNCH("ctc_lattice_kernel<bwd>");
+    if (!beta_valid) {  // the forward did not stage beta: gather the emissions and run the beta lattice now
+        size_t n = (size_t)B * T * S;
+        ctc_gather_kernel<<<(int)min((size_t)sm_count() * 16, (n + 255) / 256), 256, 0, st>>>(
+            logits, labels, tlen, ulen, lse, B, T, V, Umax, blank, beta_ws);
+        EMO_CHECK_LAUNCH("ctc_gather_kernel");
+        int threads = (S + 31) / 32 * 32;
+        ctc_lattice_kernel<<<dim3(B, 1), threads, 0, st>>>(labels, tlen, ulen, T, V, Umax, blank, zero_infinity, 1,
+                                                           nullptr, beta_ws, nullptr);
+        EMO_CHECK_LAUNCH("ctc_lattice_kernel<beta>");
+    }
     size_t smem = (size_t)V * sizeof(float);
     if (smem > 48 * 1024)
         EMO_CUDA(cudaFuncSetAttribute(ctc_grad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

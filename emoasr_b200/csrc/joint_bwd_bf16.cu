@@ -710,46 +710,68 @@ joint_dw_kernel(const __grid_constant__ CUtensorMap tmap_w,    // w_out bf16, bo
     }
 }
 
-// d_enc_proj[b,t,j] = sum_{u <= U_b} dpre[b,t,u,j]   (0 for t >= T_b)
-__global__ void reduce_over_u_kernel(const __nv_bfloat16* __restrict__ dpre, const int* __restrict__ tlen,
-                                     const int* __restrict__ ulen, int T, int U1, int J,
-                                     float* __restrict__ d_enc) {
-    const int r = blockIdx.x;  // b*T + t
-    const int b = r / T, t = r - b * T;
+// Both axis reductions of dpre (B,T,U1,J) bf16 in ONE pass over the tensor:
+//   d_enc_proj[b,t,j] = sum_{u <= U_b} dpre[b,t,u,j]   (0 for t >= T_b)        written directly
+//   d_dec_proj[b,u,j] = sum_{t <  T_b} dpre[b,t,u,j]   (0 for u >  U_b)        pre-zeroed, atomicAdd
+// Block = (64-column slice, group of kRedTG frames, utterance); warp w owns the rows u = w mod 8, so
+// its shared-memory partial sums over t need no atomics; one red per (u, column) per block at the end.
+constexpr int kRedTG = 25;
+constexpr int kRedWarps = 8;
+__global__ void __launch_bounds__(kRedWarps * 32)
+reduce_dpre_kernel(const __nv_bfloat16* __restrict__ dpre, const int* __restrict__ tlen,
+                   const int* __restrict__ ulen, int T, int U1, int J, float* __restrict__ d_enc,
+                   float* __restrict__ d_dec) {
+    extern __shared__ float s_red[];               // [U1][64] partial d_dec, then [kRedWarps][64] for d_enc
+    float* s_dec = s_red;
+    float* s_enc = s_red + (size_t)U1 * 64;
+    const int b = blockIdx.z, j0 = blockIdx.x * 64;
+    const int t0 = blockIdx.y * kRedTG, t1 = min(t0 + kRedTG, T);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T_b = min(max(tlen[b], 1), T), U1b = min(max(ulen[b], 0), U1 - 1) + 1;
-    for (int j2 = threadIdx.x; j2 < J / 2; j2 += blockDim.x) {
-        float a0 = 0.f, a1 = 0.f;
+    for (int i = threadIdx.x; i < U1 * 64; i += blockDim.x) s_dec[i] = 0.f;
+    __syncthreads();
+    for (int t = t0; t < t1; ++t) {
+        float e0 = 0.f, e1 = 0.f;
         if (t < T_b) {
-            const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(dpre + (size_t)r * U1 * J) + j2;
-            for (int u = 0; u < U1b; ++u) {
-                const float2 v = __bfloat1622float2(p[(size_t)u * (J / 2)]);
-                a0 += v.x;
-                a1 += v.y;
+            const __nv_bfloat162* base =
+                reinterpret_cast<const __nv_bfloat162*>(dpre + (((size_t)b * T + t) * U1) * J + j0) + lane;
+            int u = warp;
+            for (; u + 3 * kRedWarps < U1b; u += 4 * kRedWarps) {
+                __nv_bfloat162 v[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) v[k] = base[(size_t)(u + k * kRedWarps) * (J / 2)];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 f = __bfloat1622float2(v[k]);
+                    e0 += f.x; e1 += f.y;
+                    float2* d = reinterpret_cast<float2*>(s_dec + (size_t)(u + k * kRedWarps) * 64) + lane;
+                    float2 acc = *d;
+                    acc.x += f.x; acc.y += f.y;
+                    *d = acc;
+                }
+            }
+            for (; u < U1b; u += kRedWarps) {
+                const float2 f = __bfloat1622float2(base[(size_t)u * (J / 2)]);
+                e0 += f.x; e1 += f.y;
+                float2* d = reinterpret_cast<float2*>(s_dec + (size_t)u * 64) + lane;
+                float2 acc = *d;
+                acc.x += f.x; acc.y += f.y;
+                *d = acc;
             }
         }
-        reinterpret_cast<float2*>(d_enc + (size_t)r * J)[j2] = make_float2(a0, a1);
+        reinterpret_cast<float2*>(s_enc + warp * 64)[lane] = make_float2(e0, e1);
+        __syncthreads();
+        if (threadIdx.x < 64) {
+            float a = 0.f;
+#pragma unroll
+            for (int w = 0; w < kRedWarps; ++w) a += s_enc[w * 64 + threadIdx.x];
+            d_enc[((size_t)b * T + t) * J + j0 + threadIdx.x] = a;
+        }
+        __syncthreads();
     }
-}
-
-// d_dec_proj[b,u,j] = sum_{t < T_b} dpre[b,t,u,j]   (0 for u > U_b)
-__global__ void reduce_over_t_kernel(const __nv_bfloat16* __restrict__ dpre, const int* __restrict__ tlen,
-                                     const int* __restrict__ ulen, int T, int U1, int J,
-                                     float* __restrict__ d_dec) {
-    const int r = blockIdx.x;  // b*U1 + u
-    const int b = r / U1, u = r - b * U1;
-    const int T_b = min(max(tlen[b], 1), T), U1b = min(max(ulen[b], 0), U1 - 1) + 1;
-    for (int j2 = threadIdx.x; j2 < J / 2; j2 += blockDim.x) {
-        float a0 = 0.f, a1 = 0.f;
-        if (u < U1b) {
-            const __nv_bfloat162* p =
-                reinterpret_cast<const __nv_bfloat162*>(dpre + ((size_t)b * T * U1 + u) * J) + j2;
-            for (int t = 0; t < T_b; ++t) {
-                const float2 v = __bfloat1622float2(p[(size_t)t * U1 * (J / 2)]);
-                a0 += v.x;
-                a1 += v.y;
-            }
-        }
-        reinterpret_cast<float2*>(d_dec + (size_t)r * J)[j2] = make_float2(a0, a1);
+    for (int i = threadIdx.x; i < U1b * 64; i += blockDim.x) {
+        const float v = s_dec[i];
+        if (v != 0.f) atomicAdd(d_dec + ((size_t)b * U1 + (i >> 6)) * J + j0 + (i & 63), v);
     }
 }
 
@@ -774,7 +796,7 @@ size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V) {
 
 int joint_bf16_launches(int op, int B, int T, int U1, int J, int V) {
     (void)B; (void)T; (void)U1; (void)J; (void)V;
-    if (op == EMO_OP_RNNT_JOINT_BWD) return 5;  // weight cast, dh kernel, 2 reductions, dW kernel
+    if (op == EMO_OP_RNNT_JOINT_BWD) return 4;  // weight cast, dh kernel, axis reductions, dW kernel
     return 2;                                    // weight cast + fused joint forward
 }
 
@@ -809,6 +831,7 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     EMO_CHECK_LAUNCH("f32_to_bf16_kernel");
     EMO_CUDA(cudaMemsetAsync(d_w_out, 0, nw * sizeof(float), st));
     EMO_CUDA(cudaMemsetAsync(d_b_out, 0, (size_t)V * sizeof(float), st));
+    EMO_CUDA(cudaMemsetAsync(d_dec_proj, 0, (size_t)B * U1 * J * sizeof(float), st));
 
     CUtensorMap tmap_wz, tmap_wd, tmap_h;
     rc = make_tmap_bf16_2d(&tmap_wz, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, 64);
@@ -840,10 +863,14 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
                                     gamma2, grad_cost, B, T, U1, J, V, blank, dpre));
         EMO_CHECK_LAUNCH("joint_dh_kernel");
     }
-    reduce_over_u_kernel<<<B * T, 128, 0, st>>>(dpre, tlen, ulen, T, U1, J, d_enc_proj);
-    EMO_CHECK_LAUNCH("reduce_over_u_kernel");
-    reduce_over_t_kernel<<<B * U1, 128, 0, st>>>(dpre, tlen, ulen, T, U1, J, d_dec_proj);
-    EMO_CHECK_LAUNCH("reduce_over_t_kernel");
+    {
+        const size_t smem = ((size_t)U1 + kRedWarps) * 64 * sizeof(float);
+        EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_bwd(bf16): U+1 = %d too large", U1);
+        EMO_CUDA(cudaFuncSetAttribute(reduce_dpre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        reduce_dpre_kernel<<<dim3(J / 64, ceil_div(T, kRedTG), B), kRedWarps * 32, smem, st>>>(
+            dpre, tlen, ulen, T, U1, J, d_enc_proj, d_dec_proj);
+        EMO_CHECK_LAUNCH("reduce_dpre_kernel");
+    }
 
     // ---- dW kernel: one (vocab chunk, J-part) role per CTA, num_splits CTAs per role
     {

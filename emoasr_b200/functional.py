@@ -245,11 +245,14 @@ class _CTC(torch.autograd.Function):
         with torch.cuda.device(dev):
             lse = torch.empty(B, T, device=dev)
             alpha = torch.empty(B, T, S, device=dev)
+            # training step: the beta lattice runs side by side with alpha inside the forward call
+            beta = torch.empty(B, T, S, device=dev) if ctx.needs_input_grad[0] else None
             nll = torch.empty(B, device=dev)
             _lib.check(lib.emo_ctc_fwd(_p(z), _p(labels), _p(tlen), _p(ulen), B, T, V, Umax, blank,
-                                       int(zero_infinity), _p(lse), _p(alpha), _p(nll), _stream()),
+                                       int(zero_infinity), _p(lse), _p(alpha), _p(beta), _p(nll), _stream()),
                        "emo_ctc_fwd")
         ctx.save_for_backward(z, labels, tlen, ulen, lse, alpha, nll)
+        ctx.beta = beta
         ctx.cfg = (blank, int(zero_infinity))
         return nll
 
@@ -263,11 +266,13 @@ class _CTC(torch.autograd.Function):
         dev = z.device
         with torch.cuda.device(dev):
             g = _f32c(grad_nll)
-            occ = torch.empty(B, T, 2 * Umax + 1, device=dev)
+            beta, beta_valid = ctx.beta, 1
+            if beta is None:
+                beta, beta_valid = torch.empty(B, T, 2 * Umax + 1, device=dev), 0
             grad = torch.empty_like(z)
             _lib.check(lib.emo_ctc_bwd(_p(z), _p(labels), _p(tlen), _p(ulen), _p(lse), _p(alpha), _p(nll),
-                                       _p(g), B, T, V, Umax, blank, zero_infinity, _p(occ), _p(grad),
-                                       _stream()), "emo_ctc_bwd")
+                                       _p(g), B, T, V, Umax, blank, zero_infinity, _p(beta), beta_valid,
+                                       _p(grad), _stream()), "emo_ctc_bwd")
         return grad, None, None, None, None, None
 
 

@@ -140,18 +140,21 @@ int emo_rnnt_joint_bwd(const float* enc_proj, const float* dec_proj,
  * logits.  labels (B,Umax) int64 padded arbitrarily; tlen, ulen (B) int64 (as the reference
  * passes them).  S = 2*Umax+1.
  * emo_ctc_fwd:  lse (B,T), alpha_ws (B,T,S) scratch kept for backward,
+ *               beta_ws (B,T,S) or NULL: when given, the beta lattice runs side by side with alpha
+ *               (what a training step wants); NULL = forward only.
  *               nll (B): -log P(y|x), or 0 when infeasible and zero_infinity != 0 (else +inf).
  * emo_ctc_bwd:  grad_logits (B,T,V) = grad_nll[b] * (softmax(z)[t,v] - occ[t,v]) for t < tlen[b],
  *               0 for padded frames and for infeasible utterances (whole tensor written).
- *               beta_ws (B,T,S) scratch.
+ *               beta_ws (B,T,S): beta from emo_ctc_fwd (beta_valid != 0) or scratch the beta lattice
+ *               is computed into first (beta_valid == 0).
  */
 int emo_ctc_fwd(const float* logits, const long long* labels, const long long* tlen,
                 const long long* ulen, int B, int T, int V, int Umax, int blank, int zero_infinity,
-                float* lse, float* alpha_ws, float* nll, void* stream);
+                float* lse, float* alpha_ws, float* beta_ws, float* nll, void* stream);
 int emo_ctc_bwd(const float* logits, const long long* labels, const long long* tlen,
                 const long long* ulen, const float* lse, const float* alpha_ws, const float* nll,
                 const float* grad_nll, int B, int T, int V, int Umax, int blank, int zero_infinity,
-                float* beta_ws, float* grad_logits, void* stream);
+                float* beta_ws, int beta_valid, float* grad_logits, void* stream);
 
 #ifdef __cplusplus
 }

@@ -350,3 +350,34 @@ def test_joint_bf16_loss_and_grads(B, T, U, V, J):
     assert abs(float(loss) - r["loss"]) <= BF16_LOSS_RTOL * abs(r["loss"])
     for t, k in zip(te, ["d_enc_proj", "d_dec_proj", "d_w_out", "d_b_out"]):
         assert rel_err(t.grad.cpu().numpy(), r[k]) < BF16_GRAD_RTOL, k
+
+
+def test_ctc_backward_without_staged_beta_matches_training_path():
+    """C ABI: emo_ctc_fwd(beta_ws=NULL) + emo_ctc_bwd(beta_valid=0) (forward-only caller that later wants the
+    gradient) must give the same gradient as the training path where beta runs beside alpha."""
+    import ctypes
+    import emoasr_b200 as E
+    from emoasr_b200 import _lib
+    lib = _lib.load()
+    gen = torch.Generator().manual_seed(5)
+    B, T, U, V = 5, 37, 9, 64
+    logits = torch.randn(B, T, V, generator=gen).to(dev())
+    ys = torch.randint(1, V, (B, U), generator=gen).to(dev())
+    tl = torch.tensor([37, 30, 22, 37, 12], device=dev())
+    ul = torch.tensor([9, 9, 4, 0, 7], device=dev())
+    x = logits.clone().requires_grad_()
+    nll = E.ctc_loss(x, ys, tl, ul, blank=0)
+    nll.sum().backward()
+    S = 2 * U + 1
+    lse = torch.empty(B, T, device=dev()); alpha = torch.empty(B, T, S, device=dev())
+    beta = torch.empty(B, T, S, device=dev()); nll2 = torch.empty(B, device=dev())
+    grad = torch.empty_like(logits); g = torch.ones(B, device=dev())
+    p = lambda t: ctypes.c_void_p(t.data_ptr())
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    _lib.check(lib.emo_ctc_fwd(p(logits), p(ys), p(tl), p(ul), B, T, V, U, 0, 1, p(lse), p(alpha), None, p(nll2), st),
+               "emo_ctc_fwd")
+    _lib.check(lib.emo_ctc_bwd(p(logits), p(ys), p(tl), p(ul), p(lse), p(alpha), p(nll2), p(g), B, T, V, U, 0, 1,
+                               p(beta), 0, p(grad), st), "emo_ctc_bwd")
+    torch.cuda.synchronize()
+    assert torch.allclose(nll2, nll.detach(), rtol=1e-6, atol=1e-6)
+    assert torch.allclose(grad, x.grad, rtol=1e-5, atol=1e-6)
