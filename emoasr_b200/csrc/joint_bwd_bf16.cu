@@ -710,6 +710,328 @@ joint_dw_kernel(const __grid_constant__ CUtensorMap tmap_w,    // w_out bf16, bo
     }
 }
 
+// =================================================================================================
+// dW kernel, transposed CTA-pair version ("dWt").  Role of a pair = (256-wide vocab range, 256-wide J
+// group); both CTAs work on the SAME 128-cell tile and the epilogue thread is a VOCAB row:
+//   z^T [256 v x 128 cells] = W_range (A: this CTA's 128 vocab rows, RESIDENT in shared memory)
+//                             . h^T   (B: the h tile, split by cells across the pair -> 64 cells x J per
+//                                         CTA, streamed through a small ring)
+//   dz^T[v, cell] (bf16)  rows = vocab, 128 cells contiguous  ->  K-major B operand of
+//   dW^T [256 j x 256 v] += h^T (A: MN-major view of this CTA's [128 cells x 128 j] block of the h tile)
+//                           . dz (B: dz^T rows, split by vocab across the pair)        K = 128 cells
+// accumulated in TMEM over ALL tiles of the pair and flushed once.  Per tile a CTA pulls 96 KiB of h
+// from L2 and nothing else (w_out never streams), and the h block used by dW^T is loaded separately
+// from the ring that feeds z^T, so no operand is held across the epilogue.
+constexpr int kHzSlots = 4;
+constexpr int kHzBytes = 64 * kBlockK * 2;   // [64 cells x 64 j] bf16 = 8 KiB
+
+struct __align__(16) DwtBarriers {
+    uint64_t w_full;
+    uint64_t hz_full[kHzSlots], hz_empty[kHzSlots];
+    uint64_t hd_full, hd_empty;
+    uint64_t z_full[2], z_empty[2];
+    uint64_t dz_full, dz_empty;
+    uint64_t acc_full;
+    uint32_t tmem_base;
+    uint32_t pad[3];
+};
+
+__global__ void __launch_bounds__(kThreads, 1)
+joint_dwt_kernel(const __grid_constant__ CUtensorMap tmap_w,    // w_out bf16, box [64 j x 128 v]
+                 const __grid_constant__ CUtensorMap tmap_hz,   // h cache, box [64 j x 64 cells]
+                 const __grid_constant__ CUtensorMap tmap_hd,   // h cache, box [64 j x 128 cells]
+                 const float* __restrict__ b_out, const int* __restrict__ labels,
+                 const int* __restrict__ tlen, const int* __restrict__ ulen,
+                 const float* __restrict__ lse, const float* __restrict__ gamma2,
+                 const float* __restrict__ grad_cost, int B, int T, int U1, int J, int V, int blank,
+                 int num_splits,
+                 float* __restrict__ d_w_out,    // (V,J), pre-zeroed
+                 float* __restrict__ d_b_out) {  // (V), pre-zeroed
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int KB = J / kBlockK;
+    const int G = (J + 255) / 256;                        // J groups
+    uint8_t* sW = smem;                                   // resident: KB blocks [128 v x 64 j]
+    uint8_t* sHz = sW + (size_t)KB * kABlockBytes;        // ring of [64 cells x 64 j] blocks (z^T B operand)
+    uint8_t* sHd = sHz + (size_t)kHzSlots * kHzBytes;     // [128 cells x 128 j] (dW^T A operand), 2 x 16 KiB
+    uint8_t* sDz = sHd + 2 * kABlockBytes;                // dz^T [128 v x 128 cells], 2 K-atoms x 16 KiB
+    DwtBarriers* bars = reinterpret_cast<DwtBarriers*>(sDz + kDzBytes);
+    float* s_c2 = reinterpret_cast<float*>(bars + 1);     // per-cell scalars of the current tile
+    float* s_gg = s_c2 + kTileM;
+    float* s_cb = s_gg + kTileM;
+    float* s_cl = s_cb + kTileM;
+    int* s_lab = reinterpret_cast<int*>(s_cl + kTileM);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int tiles_per_utt = (T * U1 + kTileM - 1) / kTileM;
+    const int total_tiles = B * tiles_per_utt;
+    const int tpu = tiles128_per_utt(T, U1);
+    const int pair = blockIdx.x >> 1;
+    const int roles = G * ((V + 255) / 256);
+    const int role = pair % roles, tile0 = pair / roles;
+    const int g = role % G, range = role / G;
+    const int v0 = range * 256, v0_r = v0 + (int)rank * kTileM;       // first vocab row of the pair / this CTA
+    const bool full_group = J - g * 256 >= 256;                      // 128-wide last group: both CTAs duplicate it
+    const int j0_r = g * 256 + (full_group ? (int)rank * kTileM : 0);
+    const bool flush_dw = full_group || leader;
+
+    if (warp == 1 && lane == 0) {
+        mbar_init(smem_u32(&bars->w_full), 2);
+        for (int i = 0; i < kHzSlots; ++i) {
+            mbar_init(smem_u32(&bars->hz_full[i]), 2);
+            mbar_init(smem_u32(&bars->hz_empty[i]), 1);
+        }
+        mbar_init(smem_u32(&bars->hd_full), 2);
+        mbar_init(smem_u32(&bars->hd_empty), 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&bars->z_full[i]), 1);
+            mbar_init(smem_u32(&bars->z_empty[i]), 2 * kEpiThreads);
+        }
+        mbar_init(smem_u32(&bars->dz_full), 2 * kEpiThreads);
+        mbar_init(smem_u32(&bars->dz_empty), 1);
+        mbar_init(smem_u32(&bars->acc_full), 1);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_hz);
+        tma_prefetch_desc(&tmap_hd);
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(smem_u32(&bars->tmem_base), 512);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    const uint32_t tmem_acc2 = tmem_base + 2 * kBwdChunk;
+
+    if (warp == 0) {
+        // ===================== TMA: resident W, then the h ring feeding z^T =====================
+        if (lane == 0) {
+            const uint32_t wf = smem_u32(&bars->w_full);
+            mbar_arrive_expect_tx_cluster(mapa_shared(wf, 0), KB * kABlockBytes);
+            for (int kb = 0; kb < KB; ++kb)
+                tma_load_2d_pair(smem_u32(sW + (size_t)kb * kABlockBytes), &tmap_w, kb * kBlockK, v0_r, wf);
+            uint32_t slot = 0, sphase = 0;
+            TileInfo ti;
+            for (int tile = tile0; tile < total_tiles; tile += num_splits) {
+                if (!tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) continue;
+                const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM + (int)rank * 64;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(smem_u32(&bars->hz_empty[slot]), sphase ^ 1);
+                    const uint32_t full = smem_u32(&bars->hz_full[slot]);
+                    mbar_arrive_expect_tx_cluster(mapa_shared(full, 0), kHzBytes);
+                    tma_load_2d_pair(smem_u32(sHz + (size_t)slot * kHzBytes), &tmap_hz, kb * kBlockK, row0, full);
+                    if (++slot == kHzSlots) { slot = 0; sphase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== TMA: the [128 cells x 128 j] h block of dW^T (own thread, so it never
+        // delays the ring above) =====================
+        if (lane == 0) {
+            uint32_t tl = 0;
+            TileInfo ti;
+            for (int tile = tile0; tile < total_tiles; tile += num_splits) {
+                if (!tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) continue;
+                const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM;
+                mbar_wait(smem_u32(&bars->hd_empty), (tl & 1) ^ 1);
+                const uint32_t full = smem_u32(&bars->hd_full);
+                mbar_arrive_expect_tx_cluster(mapa_shared(full, 0), 2 * kABlockBytes);
+                for (int t = 0; t < 2; ++t)
+                    tma_load_2d_pair(smem_u32(sHd + (size_t)t * kABlockBytes), &tmap_hd, j0_r + t * kBlockK, row0, full);
+                ++tl;
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA) =====================
+        if (leader) {
+            uint32_t slot = 0, sphase = 0, zc = 0, dc = 0;
+            const uint32_t w_lo0 = desc_lo(smem_u32(sW), 16);
+            const uint32_t hz_lo0 = desc_lo(smem_u32(sHz), 16);
+            const uint32_t hd_mn_lo0 = desc_lo(smem_u32(sHd), kABlockBytes);
+            const uint32_t dz_lo0 = desc_lo(smem_u32(sDz), 16);
+            const uint32_t idesc_z = umma_idesc_bf16(2 * kTileM, kTileM);
+            const uint32_t idesc_dw = umma_idesc_bf16(2 * kTileM, 2 * kTileM, 1, 0);
+            auto z_mma = [&]() {
+                const uint32_t zb = zc & 1;
+                mbar_wait(smem_u32(&bars->z_empty[zb]), ((zc >> 1) & 1) ^ 1);
+                const uint32_t d_tmem = tmem_base + zb * kBwdChunk;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(smem_u32(&bars->hz_full[slot]), sphase);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t a_lo = w_lo0 + kb * (kABlockBytes >> 4);
+                        const uint32_t b_lo = hz_lo0 + slot * (kHzBytes >> 4);
+#pragma unroll
+                        for (int k16 = 0; k16 < kBlockK / 16; ++k16)
+                            umma_bf16_pair(d_tmem, mk_desc(a_lo + 2 * k16), mk_desc(b_lo + 2 * k16), idesc_z,
+                                           (kb | k16) != 0);
+                        umma_commit_pair(smem_u32(&bars->hz_empty[slot]));
+                        if (kb == KB - 1) umma_commit_pair(smem_u32(&bars->z_full[zb]));
+                    }
+                    __syncwarp();
+                    if (++slot == kHzSlots) { slot = 0; sphase ^= 1; }
+                }
+                ++zc;
+            };
+            auto dw_mma = [&]() {
+                mbar_wait(smem_u32(&bars->dz_full), dc & 1);
+                mbar_wait(smem_u32(&bars->hd_full), dc & 1);
+                tc_fence_after();
+                if (elect_one_sync()) {
+#pragma unroll
+                    for (int kk = 0; kk < kTileM / 16; ++kk)
+                        umma_bf16_pair(tmem_acc2, mk_desc(hd_mn_lo0 + kk * (2048 >> 4)),
+                                       mk_desc(dz_lo0 + (kk >> 2) * (kABlockBytes >> 4) + (kk & 3) * 2), idesc_dw,
+                                       (dc || kk) ? 1u : 0u);
+                    umma_commit_pair(smem_u32(&bars->dz_empty));
+                    umma_commit_pair(smem_u32(&bars->hd_empty));
+                }
+                __syncwarp();
+                ++dc;
+            };
+            mbar_wait(smem_u32(&bars->w_full), 0);
+            bool have_cur = false;
+            TileInfo ti;
+            for (int tile = tile0; tile < total_tiles; tile += num_splits) {
+                if (!tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) continue;
+                z_mma();                    // z^T of this tile runs while the epilogue works on the previous one
+                if (have_cur) dw_mma();     // dW^T of the previous tile
+                have_cur = true;
+            }
+            if (have_cur) {
+                dw_mma();
+                if (elect_one_sync()) umma_commit_pair(smem_u32(&bars->acc_full));
+                __syncwarp();
+            }
+        }
+    } else if (warp >= 4) {
+        // ===================== epilogue (8 warps): thread = vocab row, half of the cells =====================
+        const int e = threadIdx.x - 128;
+        const int q = warp & 3, hf = (warp - 4) >> 2;
+        const int row = q * 32 + lane;                    // vocab row inside this CTA (TMEM lane)
+        const int v = v0_r + row;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const float bias2 = (v < V ? __ldg(b_out + v) : 0.f) * kLog2e;
+        const bool is_blank = v == blank;
+        const uint32_t z_empty_addr[2] = {mapa_shared(smem_u32(&bars->z_empty[0]), 0),
+                                          mapa_shared(smem_u32(&bars->z_empty[1]), 0)};
+        const uint32_t dz_full_addr = mapa_shared(smem_u32(&bars->dz_full), 0);
+        uint8_t* rowp = sDz + hf * kABlockBytes + (row >> 3) * 1024 + (row & 7) * 128;
+        uint32_t zc = 0;
+        float rowsum = 0.f;
+        bool any_tile = false;
+        TileInfo ti;
+        for (int tile = tile0; tile < total_tiles; tile += num_splits) {
+            if (!tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) continue;
+            // ---- per-cell scalars of the tile
+            if (e < kTileM) {
+                RowCtx rc;
+                load_row_ctx(rc, ti, e, T, U1, V, labels, lse, gamma2, grad_cost);
+                s_c2[e] = rc.c2; s_gg[e] = rc.gg; s_cb[e] = rc.corr_b; s_cl[e] = rc.corr_l; s_lab[e] = rc.lab;
+            }
+            named_bar_sync(1, kEpiThreads);
+            const uint32_t zb = zc & 1;
+            mbar_wait(smem_u32(&bars->z_full[zb]), (zc >> 1) & 1);
+            tc_fence_after();
+            uint32_t r0[32], r1[32];
+            const uint32_t taddr = tmem_base + lane_base + zb * kBwdChunk + hf * 64;
+            tmem_ld_32x32b_x32(taddr, r0);
+            tmem_ld_32x32b_x32(taddr + 32, r1);
+            tmem_wait_ld();
+            bool dz_free = false;
+#pragma unroll
+            for (int gi = 0; gi < 2; ++gi) {
+                const uint32_t(&r)[32] = gi == 0 ? r0 : r1;
+                const int c0 = hf * 64 + gi * 32;
+                uint32_t pk[16];
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) {
+                    const float4 c2 = *reinterpret_cast<const float4*>(s_c2 + c0 + i);
+                    const float4 gg = *reinterpret_cast<const float4*>(s_gg + c0 + i);
+                    float d0 = gg.x * ex2_approx(fmaf(__uint_as_float(r[i + 0]), kLog2e, bias2 + c2.x));
+                    float d1 = gg.y * ex2_approx(fmaf(__uint_as_float(r[i + 1]), kLog2e, bias2 + c2.y));
+                    float d2 = gg.z * ex2_approx(fmaf(__uint_as_float(r[i + 2]), kLog2e, bias2 + c2.z));
+                    float d3 = gg.w * ex2_approx(fmaf(__uint_as_float(r[i + 3]), kLog2e, bias2 + c2.w));
+                    if (is_blank) {
+                        const float4 cb = *reinterpret_cast<const float4*>(s_cb + c0 + i);
+                        d0 -= cb.x; d1 -= cb.y; d2 -= cb.z; d3 -= cb.w;
+                    }
+                    rowsum += (d0 + d1) + (d2 + d3);
+                    pk[i >> 1] = pack_bf16x2(d0, d1);
+                    pk[(i >> 1) + 1] = pack_bf16x2(d2, d3);
+                }
+                if (!dz_free) {  // dW^T of the previous tile must have consumed dz^T
+                    mbar_wait(smem_u32(&bars->dz_empty), (zc & 1) ^ 1);
+                    dz_free = true;
+                }
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const int chunk = (gi * 4 + j) ^ (row & 7);
+                    *reinterpret_cast<uint4*>(rowp + (chunk << 4)) =
+                        make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                }
+            }
+            named_bar_sync(2, kEpiThreads);   // dense dz^T complete in this CTA
+            // ---- sparse part: cell e subtracts its label term from row (lab - v0_r) if this CTA owns it
+            if (e < kTileM) {
+                const int lab = s_lab[e];
+                const float cl = s_cl[e];
+                const int vv = lab - v0_r;
+                if (lab >= 0 && cl != 0.f && vv >= 0 && vv < kTileM) {
+                    const int c64 = e & 63;
+                    __nv_bfloat16* p = reinterpret_cast<__nv_bfloat16*>(
+                        sDz + (e >> 6) * kABlockBytes + (vv >> 3) * 1024 + (vv & 7) * 128 +
+                        (((c64 >> 3) ^ (vv & 7)) << 4)) + (c64 & 7);
+                    *p = __float2bfloat16_rn(__bfloat162float(*p) - cl);
+                    if (g == 0) atomicAdd(d_b_out + lab, -cl);
+                }
+            }
+            tc_fence_before();
+            mbar_arrive_cluster(z_empty_addr[zb]);
+            fence_proxy_async_smem();
+            mbar_arrive_cluster(dz_full_addr);
+            ++zc;
+            any_tile = true;
+        }
+        if (any_tile) {
+            // ---- flush dW^T: TMEM lane = j row, columns = the pair's 256 vocab rows
+            mbar_wait(smem_u32(&bars->acc_full), 0);
+            tc_fence_after();
+            const int j = j0_r + row;
+            for (int gi = hf * 4; gi < hf * 4 + 4; ++gi) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_acc2 + lane_base + gi * 32, r);
+                tmem_wait_ld();
+                if (flush_dw) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) {
+                        const int vv = v0 + gi * 32 + i;
+                        if (vv < V) atomicAdd(d_w_out + (size_t)vv * J + j, __uint_as_float(r[i]));
+                    }
+                }
+            }
+            if (g == 0 && v < V) atomicAdd(d_b_out + v, rowsum);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+size_t dwt_smem_bytes(int J) {
+    return (size_t)(J / kBlockK) * kABlockBytes + (size_t)kHzSlots * kHzBytes + 2 * kABlockBytes + kDzBytes +
+           sizeof(DwtBarriers) + 5 * kTileM * sizeof(float);
+}
+
 // Both axis reductions of dpre (B,T,U1,J) bf16 in ONE pass over the tensor:
 //   d_enc_proj[b,t,j] = sum_{u <= U_b} dpre[b,t,u,j]   (0 for t >= T_b)        written directly
 //   d_dec_proj[b,u,j] = sum_{t <  T_b} dpre[b,t,u,j]   (0 for u >  U_b)        pre-zeroed, atomicAdd
@@ -872,8 +1194,33 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
         EMO_CHECK_LAUNCH("reduce_dpre_kernel");
     }
 
-    // ---- dW kernel: one (vocab chunk, J-part) role per CTA, num_splits CTAs per role
-    {
+    // ---- dW kernel
+    static const bool use_dw_v1 = getenv("EMO_DW_V1") != nullptr;  // A/B switch: per-CTA roles, streamed W
+    if (!use_dw_v1 && dwt_smem_bytes(J) <= (size_t)kSmemLimit) {
+        // transposed CTA-pair roles (256 vocab rows x 256 hidden units), W resident
+        CUtensorMap tmap_hz;
+        rc = make_tmap_bf16_2d(&tmap_hz, hcache, (uint64_t)J, (uint64_t)B * tiles128_per_utt(T, U1) * kTileM,
+                               kBlockK, 64);
+        if (rc) return rc;
+        const size_t smem = dwt_smem_bytes(J);
+        EMO_CUDA(cudaFuncSetAttribute(joint_dwt_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const int tiles = B * ceil_div((size_t)T * U1, kTileM);
+        const int roles = ceil_div(J, 256) * ceil_div(V, 256);
+        const int splits = max(1, min((sm_count() / 2) / roles, tiles));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(2 * roles * splits);
+        cfg.blockDim = dim3(kThreads);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        EMO_CUDA(cudaLaunchKernelEx(&cfg, joint_dwt_kernel, tmap_wd, tmap_hz, tmap_h, b_out, labels, tlen, ulen, lse,
+                                    gamma2, grad_cost, B, T, U1, J, V, blank, splits, d_w_out, d_b_out));
+        EMO_CHECK_LAUNCH("joint_dwt_kernel");
+    } else {
         const size_t smem = dw_smem_bytes(J);
         EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_bwd(bf16): shared memory (dW)");
         EMO_CUDA(cudaFuncSetAttribute(joint_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
