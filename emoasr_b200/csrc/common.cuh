@@ -49,6 +49,14 @@ __device__ __forceinline__ float log_add_exp(float a, float b) {
     return m + log1pf(expf(-fabsf(a - b)));
 }
 
+// same with the hardware ex2/lg2 approximations: absolute error ~1e-7, used inside the serial lattice
+// recursions where the full-precision expf/log1pf latency is the critical path
+__device__ __forceinline__ float log_add_exp_fast(float a, float b) {
+    float m = fmaxf(a, b);
+    if (m == kNegInf) return kNegInf;
+    return m + __logf(1.f + __expf(-fabsf(a - b)));
+}
+
 __device__ __forceinline__ float warp_max(float v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));

@@ -61,36 +61,40 @@ __device__ __forceinline__ Ext ext_state(const long long* __restrict__ y, int s,
     return e;
 }
 
-constexpr int kRowVec = 12;  // float4 per thread held in registers (rows up to 12288 logits in one pass)
+constexpr int kRowVec = 8;   // float4 per lane in flight (one 4 KiB slab of the row per warp pass)
+constexpr int kLseWarps = 8;
 
-// grid-stride over rows r = b*T + t.  One pass over the row (held in registers): max, sum exp, then
-// the gather of the S_b = 2 U_b + 1 emission log-probs lp_ext[r][s] = z[l'_s] - lse, written where
-// the alpha (and beta) recursion will find them -- the lattice kernels never touch the logits.
-__global__ void __launch_bounds__(kRowThreads)
+// One WARP per row r = b*T + t (grid-stride), no block-level synchronisation: the row streams through
+// registers in slabs of 32 lanes x kRowVec float4 with an online (max, sum exp); then the warp
+// gathers the S_b = 2 U_b + 1 emission log-probs lp_ext[r][s] = z[l'_s] - lse (the row is L2-hot) and
+// writes them where the alpha (and beta) recursion will find them -- the lattice kernels never
+// touch the logits.
+__global__ void __launch_bounds__(kLseWarps * 32)
 ctc_row_lse_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
                    const long long* __restrict__ tlen, const long long* __restrict__ ulen, int B, int T,
                    int V, int Umax, int blank, float* __restrict__ lse, float* __restrict__ lp_a,
                    float* __restrict__ lp_b) {
-    __shared__ float sm_m[32], sm_s[32];
     const int rows = B * T;
     const int S = 2 * Umax + 1;
-    for (int r = blockIdx.x; r < rows; r += gridDim.x) {
-        int b = r / T, t = r - b * T;
-        long long T_b = tlen[b];
-        if (t >= T_b) {
-            if (threadIdx.x == 0) lse[r] = 0.f;
-            continue;  // uniform
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kLseWarps + (threadIdx.x >> 5);
+    const int warp_stride = gridDim.x * kLseWarps;
+    for (int r = warp_global; r < rows; r += warp_stride) {
+        const int b = r / T, t = r - b * T;
+        if (t >= tlen[b]) {
+            if (lane == 0) lse[r] = 0.f;
+            continue;  // warp-uniform
         }
         const float* row = logits + (size_t)r * V;
         float m = kNegInf, s = 0.f;
         if ((V & 3) == 0) {
             const float4* row4 = reinterpret_cast<const float4*>(row);
             const int n4 = V >> 2;
-            for (int base = 0; base < n4; base += kRowVec * kRowThreads) {
+            for (int base = 0; base < n4; base += kRowVec * 32) {
                 float4 x[kRowVec];
 #pragma unroll
                 for (int k = 0; k < kRowVec; ++k) {
-                    const int i = base + k * kRowThreads + threadIdx.x;
+                    const int i = base + k * 32 + lane;
                     x[k] = i < n4 ? __ldg(row4 + i) : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
                 }
                 float mx = kNegInf;
@@ -108,23 +112,29 @@ ctc_row_lse_kernel(const float* __restrict__ logits, const long long* __restrict
                 }
             }
         } else {
-            for (int i = threadIdx.x; i < V; i += kRowThreads) {
-                float x = __ldg(row + i);
-                float mn = fmaxf(m, x);
+            for (int i = lane; i < V; i += 32) {
+                const float x = __ldg(row + i);
+                const float mn = fmaxf(m, x);
                 if (mn > kNegInf) {
-                    s = s * expf(m - mn) + expf(x - mn);
+                    s = s * __expf(m - mn) + __expf(x - mn);
                     m = mn;
                 }
             }
         }
-        float l = block_reduce_lse(m, s, sm_m, sm_s);
-        if (threadIdx.x == 0) lse[r] = l;
-        // gather the emissions of the blank-extended label sequence (the row is L1/L2-hot)
-        long long U_bl = ulen[b];
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
+            const float s2 = __shfl_xor_sync(0xffffffffu, s, o);
+            lse_merge(m, s, m2, s2);
+        }
+        const float l = m + logf(s);
+        if (lane == 0) lse[r] = l;
+        // gather the emissions of the blank-extended label sequence
+        const long long U_bl = ulen[b];
         const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
         const int S_b = 2 * U_b + 1;
         const long long* y = labels + (size_t)b * Umax;
-        for (int st = threadIdx.x; st < S_b; st += kRowThreads) {
+        for (int st = lane; st < S_b; st += 32) {
             const float v = __ldg(row + ext_state(y, st, S_b, blank, V).label) - l;
             lp_a[(size_t)r * S + st] = v;
             if (lp_b) lp_b[(size_t)r * S + st] = v;
@@ -187,7 +197,7 @@ ctc_lattice_kernel(const long long* __restrict__ labels, const long long* __rest
                     const float n1 = prev[s + nb];
                     const float n2 = jump ? prev[s + 2 * nb] : kNegInf;
                     const float m = fmaxf(fmaxf(a, n1), n2);
-                    if (m > kNegInf) val = m + logf(expf(a - m) + expf(n1 - m) + expf(n2 - m)) + lp;
+                    if (m > kNegInf) val = m + __logf(__expf(a - m) + __expf(n1 - m) + __expf(n2 - m)) + lp;
                 }
                 io[(size_t)frame(i) * S + s] = val;
             }
@@ -324,8 +334,8 @@ extern "C" int emo_ctc_fwd(const float* logits, const long long* labels, const l
     EMO_REQUIRE(lse && alpha_ws && nll, EMO_BAD_ARG, "ctc_fwd: null output pointer");
     cudaStream_t st = (cudaStream_t)stream;
     int rows = B * T;
-    int grid = min(rows, sm_count() * 8);
-    ctc_row_lse_kernel<<<grid, kRowThreads, 0, st>>>(logits, labels, tlen, ulen, B, T, V, Umax, blank, lse,
+    int grid = min(ceil_div(rows, kLseWarps), sm_count() * 8);
+    ctc_row_lse_kernel<<<grid, kLseWarps * 32, 0, st>>>(logits, labels, tlen, ulen, B, T, V, Umax, blank, lse,
                                                      alpha_ws, beta_ws);
     EMO_CHECK_LAUNCH("ctc_row_lse_kernel");
     int S = 2 * Umax + 1;

@@ -66,7 +66,7 @@ __device__ __forceinline__ void wavefront(const float2* __restrict__ lp2_b, int 
             if (active) {
                 if (!kBackward) {
                     // alpha(t,u) = lse(alpha(t-1,u)+blank(t-1,u), alpha(t,u-1)+label(t,u-1))
-                    val = (t == 0 && u == 0) ? 0.f : log_add_exp(keep, u > 0 ? nb : kNegInf);
+                    val = (t == 0 && u == 0) ? 0.f : log_add_exp_fast(keep, u > 0 ? nb : kNegInf);
                     out_b[(size_t)t * U1 + u] = val;
                     keep = val + lp.x;
                     give = (u < U_b) ? val + lp.y : kNegInf;
@@ -78,7 +78,7 @@ __device__ __forceinline__ void wavefront(const float2* __restrict__ lp2_b, int 
                     } else {
                         float ne = (t < T_b - 1) ? keep + lp.x : kNegInf;
                         float em = (u < U_b) ? nb + lp.y : kNegInf;
-                        val = log_add_exp(ne, em);
+                        val = log_add_exp_fast(ne, em);
                     }
                     out_b[(size_t)t * U1 + u] = val;
                     keep = val;

@@ -380,4 +380,5 @@ def test_ctc_backward_without_staged_beta_matches_training_path():
                                p(beta), 0, p(grad), st), "emo_ctc_bwd")
     torch.cuda.synchronize()
     assert torch.allclose(nll2, nll.detach(), rtol=1e-6, atol=1e-6)
-    assert torch.allclose(grad, x.grad, rtol=1e-5, atol=1e-6)
+    # the two routes may differ by an ulp of beta (~1.5e-5 at |beta| ~ 130), i.e. ~1e-5 on a posterior
+    assert torch.allclose(grad, x.grad, rtol=GRAD_RTOL, atol=2e-5)
