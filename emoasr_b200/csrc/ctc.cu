@@ -171,13 +171,17 @@ ctc_lattice_kernel(const long long* __restrict__ labels, const long long* __rest
     __syncthreads();
 
     auto frame = [&](int i) { return backward ? T_b - 1 - i : i; };
-    auto load = [&](int i) -> float {
-        return (valid && i < T_b) ? io[(size_t)frame(i) * S + s] : kNegInf;
-    };
+    // always a valid address (clamped), no select on the loaded value: the load must stay in flight
+    // for kPrefetch frames, a select right behind it would stall the thread until it lands
+    const int s_ld = valid ? s : 0;
+    auto load = [&](int i) -> float { return io[(size_t)frame(min(i, T_b - 1)) * S + s_ld]; };
     float ring[kPrefetch];
 #pragma unroll
     for (int k = 0; k < kPrefetch; ++k) ring[k] = load(k);
 
+    // results are kept in registers and written kPrefetch frames at a time: a global store in front of
+    // every per-frame barrier would put one store round trip on the serial chain
+    float vals[kPrefetch];
     for (int i0 = 0; i0 < T_b; i0 += kPrefetch) {
 #pragma unroll
         for (int k = 0; k < kPrefetch; ++k) {
@@ -199,10 +203,15 @@ ctc_lattice_kernel(const long long* __restrict__ labels, const long long* __rest
                     const float m = fmaxf(fmaxf(a, n1), n2);
                     if (m > kNegInf) val = m + __logf(__expf(a - m) + __expf(n1 - m) + __expf(n2 - m)) + lp;
                 }
-                io[(size_t)frame(i) * S + s] = val;
             }
+            vals[k] = val;
             buf[i & 1][2 + s] = val;
             __syncthreads();
+        }
+        if (valid) {
+#pragma unroll
+            for (int k = 0; k < kPrefetch; ++k)
+                if (i0 + k < T_b) io[(size_t)frame(i0 + k) * S + s] = vals[k];
         }
     }
     if (!backward && s == 0) {

@@ -1034,66 +1034,63 @@ size_t dwt_smem_bytes(int J) {
 
 // Both axis reductions of dpre (B,T,U1,J) bf16 in ONE pass over the tensor:
 //   d_enc_proj[b,t,j] = sum_{u <= U_b} dpre[b,t,u,j]   (0 for t >= T_b)        written directly
-//   d_dec_proj[b,u,j] = sum_{t <  T_b} dpre[b,t,u,j]   (0 for u >  U_b)        pre-zeroed, atomicAdd
-// Block = (64-column slice, group of kRedTG frames, utterance); warp w owns the rows u = w mod 8, so
-// its shared-memory partial sums over t need no atomics; one red per (u, column) per block at the end.
-constexpr int kRedTG = 25;
+//   d_dec_proj[b,u,j] = sum_{t <  T_b} dpre[b,t,u,j]   (0 for u >  U_b)        pre-zeroed, red.add.v4
+// Block = (128-column slice, kRedTG frames, utterance).  Warp w owns the rows u = w mod 8: for each
+// of its u it loads the kRedTG frames at once (8-byte loads, next u prefetched), sums them in
+// registers for d_dec (one vector red per (u, lane)) and keeps per-frame partials for d_enc, which
+// are combined across the 8 warps through shared memory once at the end.  No barrier in the loop.
+constexpr int kRedTG = 8;
 constexpr int kRedWarps = 8;
+constexpr int kRedCols = 128;   // columns per block: 4 per lane (one 8-byte load of 4 bf16)
 __global__ void __launch_bounds__(kRedWarps * 32)
 reduce_dpre_kernel(const __nv_bfloat16* __restrict__ dpre, const int* __restrict__ tlen,
                    const int* __restrict__ ulen, int T, int U1, int J, float* __restrict__ d_enc,
                    float* __restrict__ d_dec) {
-    extern __shared__ float s_red[];               // [U1][64] partial d_dec, then [kRedWarps][64] for d_enc
-    float* s_dec = s_red;
-    float* s_enc = s_red + (size_t)U1 * 64;
-    const int b = blockIdx.z, j0 = blockIdx.x * 64;
-    const int t0 = blockIdx.y * kRedTG, t1 = min(t0 + kRedTG, T);
+    __shared__ float4 s_enc[kRedWarps][kRedTG][32];
+    const int b = blockIdx.z, j0 = blockIdx.x * kRedCols;
+    const int t0 = blockIdx.y * kRedTG;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int T_b = min(max(tlen[b], 1), T), U1b = min(max(ulen[b], 0), U1 - 1) + 1;
-    for (int i = threadIdx.x; i < U1 * 64; i += blockDim.x) s_dec[i] = 0.f;
-    __syncthreads();
-    for (int t = t0; t < t1; ++t) {
-        float e0 = 0.f, e1 = 0.f;
-        if (t < T_b) {
-            const __nv_bfloat162* base =
-                reinterpret_cast<const __nv_bfloat162*>(dpre + (((size_t)b * T + t) * U1) * J + j0) + lane;
-            int u = warp;
-            for (; u + 3 * kRedWarps < U1b; u += 4 * kRedWarps) {
-                __nv_bfloat162 v[4];
+    const int nt = max(0, min(kRedTG, T_b - t0));          // valid frames of this block
+    const size_t rs = (size_t)J / 4;                        // row stride in uint2
+    const uint2* base = reinterpret_cast<const uint2*>(dpre + (((size_t)b * T + t0) * U1) * J + j0) + lane;
+    float e[kRedTG][4];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) v[k] = base[(size_t)(u + k * kRedWarps) * (J / 2)];
+    for (int k = 0; k < kRedTG; ++k) e[k][0] = e[k][1] = e[k][2] = e[k][3] = 0.f;
+    auto load_u = [&](int u, uint2 (&v)[kRedTG]) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
-                    const float2 f = __bfloat1622float2(v[k]);
-                    e0 += f.x; e1 += f.y;
-                    float2* d = reinterpret_cast<float2*>(s_dec + (size_t)(u + k * kRedWarps) * 64) + lane;
-                    float2 acc = *d;
-                    acc.x += f.x; acc.y += f.y;
-                    *d = acc;
-                }
-            }
-            for (; u < U1b; u += kRedWarps) {
-                const float2 f = __bfloat1622float2(base[(size_t)u * (J / 2)]);
-                e0 += f.x; e1 += f.y;
-                float2* d = reinterpret_cast<float2*>(s_dec + (size_t)u * 64) + lane;
-                float2 acc = *d;
-                acc.x += f.x; acc.y += f.y;
-                *d = acc;
-            }
+        for (int k = 0; k < kRedTG; ++k)
+            v[k] = (k < nt && u < U1b) ? __ldg(base + ((size_t)k * U1 + u) * rs) : make_uint2(0u, 0u);
+    };
+    uint2 cur[kRedTG], nxt[kRedTG];
+    load_u(warp, cur);
+    for (int u = warp; u < U1b; u += kRedWarps) {
+        load_u(u + kRedWarps, nxt);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kRedTG; ++k) {
+            const float f0 = __uint_as_float(cur[k].x << 16), f1 = __uint_as_float(cur[k].x & 0xffff0000u);
+            const float f2 = __uint_as_float(cur[k].y << 16), f3 = __uint_as_float(cur[k].y & 0xffff0000u);
+            a0 += f0; a1 += f1; a2 += f2; a3 += f3;
+            e[k][0] += f0; e[k][1] += f1; e[k][2] += f2; e[k][3] += f3;
         }
-        reinterpret_cast<float2*>(s_enc + warp * 64)[lane] = make_float2(e0, e1);
-        __syncthreads();
-        if (threadIdx.x < 64) {
-            float a = 0.f;
+        if (nt > 0) red_add_v4(d_dec + ((size_t)b * U1 + u) * J + j0 + lane * 4, a0, a1, a2, a3);
 #pragma unroll
-            for (int w = 0; w < kRedWarps; ++w) a += s_enc[w * 64 + threadIdx.x];
-            d_enc[((size_t)b * T + t) * J + j0 + threadIdx.x] = a;
-        }
-        __syncthreads();
+        for (int k = 0; k < kRedTG; ++k) cur[k] = nxt[k];
     }
-    for (int i = threadIdx.x; i < U1b * 64; i += blockDim.x) {
-        const float v = s_dec[i];
-        if (v != 0.f) atomicAdd(d_dec + ((size_t)b * U1 + (i >> 6)) * J + j0 + (i & 63), v);
+#pragma unroll
+    for (int k = 0; k < kRedTG; ++k) s_enc[warp][k][lane] = make_float4(e[k][0], e[k][1], e[k][2], e[k][3]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kRedTG * 32; i += blockDim.x) {
+        const int k = i >> 5, l = i & 31;
+        if (t0 + k >= T) continue;
+        float4 a = s_enc[0][k][l];
+#pragma unroll
+        for (int w = 1; w < kRedWarps; ++w) {
+            const float4 x = s_enc[w][k][l];
+            a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+        }
+        reinterpret_cast<float4*>(d_enc + ((size_t)b * T + t0 + k) * J + j0)[l] = a;
     }
 }
 
@@ -1186,10 +1183,7 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
         EMO_CHECK_LAUNCH("joint_dh_kernel");
     }
     {
-        const size_t smem = ((size_t)U1 + kRedWarps) * 64 * sizeof(float);
-        EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_bwd(bf16): U+1 = %d too large", U1);
-        EMO_CUDA(cudaFuncSetAttribute(reduce_dpre_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        reduce_dpre_kernel<<<dim3(J / 64, ceil_div(T, kRedTG), B), kRedWarps * 32, smem, st>>>(
+        reduce_dpre_kernel<<<dim3(J / kRedCols, ceil_div(T, kRedTG), B), kRedWarps * 32, 0, st>>>(
             dpre, tlen, ulen, T, U1, J, d_enc_proj, d_dec_proj);
         EMO_CHECK_LAUNCH("reduce_dpre_kernel");
     }

@@ -32,11 +32,12 @@ __device__ __forceinline__ void wavefront(const float2* __restrict__ lp2_b, int 
 
     // my cell on diagonal index i (processing order): forward d=i, backward d=n_diag-1-i
     auto cell_t = [&](int i) { return (kBackward ? (n_diag - 1 - i) : i) - u; };
+    // clamped address, no select on the loaded pair (it is only consumed when the cell is active):
+    // a select right behind the load would stall the thread until it lands and defeat the prefetch
+    const int u_ld = col_valid ? u : 0;
     auto load = [&](int i) -> float2 {
-        int t = cell_t(i);
-        if (col_valid && i < n_diag && t >= 0 && t < T_b)
-            return __ldg(&lp2_b[(size_t)t * U1 + u]);
-        return make_float2(kNegInf, kNegInf);
+        const int t = min(max(cell_t(min(i, n_diag - 1)), 0), T_b - 1);
+        return __ldg(&lp2_b[(size_t)t * U1 + u_ld]);
     };
 
     float2 ring[kPrefetch];
