@@ -408,7 +408,10 @@ def main():
         if rank != 0:
             return
         cores = os.cpu_count() or 1
-        threads = torch.get_num_threads()
+        # all host threads (torchrun exports OMP_NUM_THREADS=1, which would handicap the CPU arm)
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else cores
+        torch.set_num_threads(threads)
+        config = dict(config, parallelism=f"host CPU, {threads} threads (rank 0 only)")
         sample = 2 if w["kind"] == "rnnt" else w["B"]
         steps = max(1, min(args.steps, 2 if w["kind"] == "rnnt" else 5))
         warm = 1 if args.warmup > 0 else 0
@@ -453,7 +456,8 @@ def main():
             out["step_frac_of_sustained_peak"] = round(step_tf / (peaks["tf_sust"] or peaks["tf_burst"]), 4)
         if not args.no_cpu_baseline and world == 1:
             sample = 2 if w["kind"] == "rnnt" else min(w["B"], 16)
-            rate, sec = cpu_reference_rate(w, sample, 1, 1)
+            nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+            rate, sec = cpu_reference_rate(w, sample, 1, 1, threads=nthreads)
             out["cpu_baseline"] = {"value": round(rate, 4), "unit": "utt/s", "cores": torch.get_num_threads(),
                                    "kind": "port", "host_cpus": os.cpu_count(),
                                    "sample": f"{sample} utterances of the same shape, 1 warm-up + 1 timed step "
