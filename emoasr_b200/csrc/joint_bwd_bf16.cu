@@ -36,6 +36,7 @@ constexpr int kDwSlots = 4;                    // dW kernel: w_out ring
 constexpr int kDzBytes = 2 * kABlockBytes;     // [128 cells x 128 v] bf16 = 32 KiB
 constexpr int kPartBlocks = 4;                 // J-part = up to 4 K blocks = 256 hidden units
 constexpr int kEpiThreads = 256;
+constexpr int kEpiWarps = kEpiThreads / 32;
 constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO=1024, v1, SW128
 
 __device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
@@ -239,12 +240,12 @@ joint_dh_kernel(const __grid_constant__ CUtensorMap tmap_wz,   // w_out bf16, bo
         mbar_init(smem_u32(&bars->h_empty), 1 + kEpiThreads);
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->z_full[i]), 1);
-            mbar_init(smem_u32(&bars->z_empty[i]), 2 * kEpiThreads);
+            mbar_init(smem_u32(&bars->z_empty[i]), 2 * kEpiWarps);   // one arrive per epilogue warp
         }
-        mbar_init(smem_u32(&bars->dz_full), 2 * kEpiThreads);
+        mbar_init(smem_u32(&bars->dz_full), 2 * kEpiWarps);
         mbar_init(smem_u32(&bars->dz_empty), 1);
         mbar_init(smem_u32(&bars->acc_full), 1);
-        mbar_init(smem_u32(&bars->acc_empty), 2 * kEpiThreads);
+        mbar_init(smem_u32(&bars->acc_empty), 2 * kEpiWarps);
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) {
@@ -425,10 +426,15 @@ joint_dh_kernel(const __grid_constant__ CUtensorMap tmap_wz,   // w_out bf16, bo
                     tc_fence_after();
                     dz_from_z<false>(tmem_base + lane_base + zb * kBwdChunk, bias, n, c * kBwdChunk, hf, row, lane,
                                      rc, blank, sDz, smem_u32(&bars->dz_empty), (dc & 1) ^ 1, colsum, nullptr);
+                    // every lane orders its own TMEM reads / shared-memory writes, then ONE lane per warp
+                    // arrives (512 single-word arrivals per chunk would serialise on the barrier)
                     tc_fence_before();
-                    mbar_arrive_cluster(z_empty_addr[zb]);
                     fence_proxy_async_smem();
-                    mbar_arrive_cluster(dz_full_addr);
+                    __syncwarp();
+                    if (lane == 0) {
+                        mbar_arrive_cluster(z_empty_addr[zb]);
+                        mbar_arrive_cluster(dz_full_addr);
+                    }
                     ++zc;
                     ++dc;
                 }
@@ -455,7 +461,8 @@ joint_dh_kernel(const __grid_constant__ CUtensorMap tmap_wz,   // w_out bf16, bo
                     }
                 }
                 tc_fence_before();
-                mbar_arrive_cluster(acc_empty_addr);
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty_addr);
                 ++ac;
             }
             mbar_arrive(smem_u32(&bars->h_empty));
@@ -786,9 +793,9 @@ joint_dwt_kernel(const __grid_constant__ CUtensorMap tmap_w,    // w_out bf16, b
         mbar_init(smem_u32(&bars->hd_empty), 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->z_full[i]), 1);
-            mbar_init(smem_u32(&bars->z_empty[i]), 2 * kEpiThreads);
+            mbar_init(smem_u32(&bars->z_empty[i]), 2 * kEpiWarps);   // one arrive per epilogue warp
         }
-        mbar_init(smem_u32(&bars->dz_full), 2 * kEpiThreads);
+        mbar_init(smem_u32(&bars->dz_full), 2 * kEpiWarps);
         mbar_init(smem_u32(&bars->dz_empty), 1);
         mbar_init(smem_u32(&bars->acc_full), 1);
         fence_barrier_init();
@@ -992,9 +999,12 @@ joint_dwt_kernel(const __grid_constant__ CUtensorMap tmap_w,    // w_out bf16, b
                 }
             }
             tc_fence_before();
-            mbar_arrive_cluster(z_empty_addr[zb]);
             fence_proxy_async_smem();
-            mbar_arrive_cluster(dz_full_addr);
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive_cluster(z_empty_addr[zb]);
+                mbar_arrive_cluster(dz_full_addr);
+            }
             ++zc;
             any_tile = true;
         }
