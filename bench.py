@@ -100,6 +100,9 @@ def run_ours_rnnt(args, w, rank, world, dev):
     import emoasr_b200 as E
     from emoasr_b200 import _lib, sharding
 
+    # tensor-core mode: the two small projection GEMMs around the fused op (plain cuBLAS Linear, as in the
+    # reference's joint) run in TF32 instead of SIMT fp32; fp32 mode keeps them in true fp32
+    torch.backends.cuda.matmul.allow_tf32 = args.precision == "bf16"
     wl = RNNTWorkload(w, seed=rank, regime=args.lengths)
     mods = torch.nn.ModuleList([wl.w_enc, wl.w_dec, wl.output]).to(dev)
     params = list(mods.parameters())
@@ -402,7 +405,8 @@ def main():
     config = {"workload": w["desc"], "name": args.workload, "lengths": args.lengths,
               "per_gpu_batch": w["B"], "global_batch": w["B"] * world,
               "parallelism": f"batch-sharded x{world}, NCCL all-reduce of the path's parameter grads" if world > 1 else "single GPU",
-              "l2": "L2 flushed (256 MiB write, untimed) between timed steps"}
+              "l2": "L2 flushed (256 MiB write, untimed) between timed steps",
+              "projections": "w_enc/w_dec Linear via cuBLAS, " + ("TF32" if args.precision == "bf16" else "fp32")}
 
     if args.impl == "reference":
         if rank != 0:
