@@ -66,15 +66,19 @@ __device__ __forceinline__ void lse_group(const uint32_t (&r)[32], const float* 
     }
     const float new_m = fmaxf(run_m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
     const float neg_m2 = -new_m * kLog2e;
-    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    // exp2 of two logits per MUFU op (ex2.approx.f16x2): the special-function unit, shared with the
+    // tanh of the A producers, is the scarce pipe of this kernel.  Arguments are <= 0, results in (0,1];
+    // four packed accumulators keep each half-precision sum to four terms before it is widened.
+    uint32_t h0 = 0u, h1 = 0u, h2 = 0u, h3 = 0u;   // half2 zeros
 #pragma unroll
-    for (int i = 0; i < 32; i += 4) {
-        s0 += ex2_approx(fmaf(x[i + 0], kLog2e, neg_m2));
-        s1 += ex2_approx(fmaf(x[i + 1], kLog2e, neg_m2));
-        s2 += ex2_approx(fmaf(x[i + 2], kLog2e, neg_m2));
-        s3 += ex2_approx(fmaf(x[i + 3], kLog2e, neg_m2));
+    for (int i = 0; i < 32; i += 8) {
+        h0 = hadd2_u32(h0, ex2_f16x2(pack_f16x2(fmaf(x[i + 0], kLog2e, neg_m2), fmaf(x[i + 1], kLog2e, neg_m2))));
+        h1 = hadd2_u32(h1, ex2_f16x2(pack_f16x2(fmaf(x[i + 2], kLog2e, neg_m2), fmaf(x[i + 3], kLog2e, neg_m2))));
+        h2 = hadd2_u32(h2, ex2_f16x2(pack_f16x2(fmaf(x[i + 4], kLog2e, neg_m2), fmaf(x[i + 5], kLog2e, neg_m2))));
+        h3 = hadd2_u32(h3, ex2_f16x2(pack_f16x2(fmaf(x[i + 6], kLog2e, neg_m2), fmaf(x[i + 7], kLog2e, neg_m2))));
     }
-    run_s = run_s * ex2_approx((run_m - new_m) * kLog2e) + ((s0 + s1) + (s2 + s3));
+    const float2 f0 = unpack_f16x2(h0), f1 = unpack_f16x2(h1), f2 = unpack_f16x2(h2), f3 = unpack_f16x2(h3);
+    run_s = run_s * ex2_approx((run_m - new_m) * kLog2e) + (((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y)));
     run_m = new_m;
     const int dl = lab - v0;
     const bool mine = dl >= 0 && dl < 32;
@@ -99,40 +103,33 @@ template <int N> __device__ __forceinline__ void reg_inc() {
     asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
 }
 
-// A-operand producer: this warp's 16 rows of the 128-row tile, K block kb.
-// h = tanh(enc + dec) -> bf16 -> canonical K-major SW128 layout (16-byte chunk index XOR (row mod 8)).
-// All 16 loads of the block are issued before the first use (one latency per block).
-__device__ __forceinline__ void produce_h_block16(const float* __restrict__ enc, const float* __restrict__ dec,
-                                                  const uint32_t (&eoff)[4], const uint32_t (&doff)[4], int kb,
-                                                  int pw, int rsub, int c, uint8_t* blk) {
-    float4 e0[4], e1[4], d0[4], d1[4];
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        const float* ep = enc + eoff[p] + kb * kBlockK;
-        const float* dp = dec + doff[p] + kb * kBlockK;
-        e0[p] = __ldg(reinterpret_cast<const float4*>(ep));
-        e1[p] = __ldg(reinterpret_cast<const float4*>(ep) + 1);
-        d0[p] = __ldg(reinterpret_cast<const float4*>(dp));
-        d1[p] = __ldg(reinterpret_cast<const float4*>(dp) + 1);
-    }
+// A-operand producer: this warp's 16 rows of the 128-row tile, one 64-wide K block.
+// enc / dec arrive as fp16 (one 16-byte load = 8 hidden units per row and stream), h = tanh(enc + dec)
+// with packed-half add and tanh.approx.f16x2, rounded to bf16 into the canonical K-major SW128 layout
+// (16-byte chunk index XOR (row mod 8)).
+__device__ __forceinline__ void produce_h_block16(const uint4 (&re)[4], const uint4 (&rd)[4], int pw, int rsub,
+                                                  int c, uint8_t* blk) {
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         const int row = pw * 16 + p * 4 + rsub;
-        uint4 o;
-        o.x = pack_bf16x2(tanh_approx(e0[p].x + d0[p].x), tanh_approx(e0[p].y + d0[p].y));
-        o.y = pack_bf16x2(tanh_approx(e0[p].z + d0[p].z), tanh_approx(e0[p].w + d0[p].w));
-        o.z = pack_bf16x2(tanh_approx(e1[p].x + d1[p].x), tanh_approx(e1[p].y + d1[p].y));
-        o.w = pack_bf16x2(tanh_approx(e1[p].z + d1[p].z), tanh_approx(e1[p].w + d1[p].w));
+        const uint32_t e[4] = {re[p].x, re[p].y, re[p].z, re[p].w};
+        const uint32_t d[4] = {rd[p].x, rd[p].y, rd[p].z, rd[p].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 f = unpack_f16x2(tanh_f16x2(hadd2_u32(e[q], d[q])));
+            o[q] = pack_bf16x2(f.x, f.y);
+        }
         uint8_t* dst = blk + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
-        *reinterpret_cast<uint4*>(dst) = o;
+        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
     }
 }
 
 template <int kCtas>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
-                 int store_h, const float* __restrict__ enc,
-                 const float* __restrict__ dec, const float* __restrict__ b_out,
+                 int store_h, const __half* __restrict__ enc,
+                 const __half* __restrict__ dec, const float* __restrict__ b_out,
                  const int* __restrict__ labels, const int* __restrict__ tlen,
                  const int* __restrict__ ulen, int B, int T, int U1, int J, int V, int blank,
                  float* __restrict__ lp2, float* __restrict__ lse_out) {
@@ -358,30 +355,57 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         reg_dec<104>();
         // ===================== A producers =====================
         const int pw = warp - 8;       // 8 producer warps, 16 rows each
-        const int c = lane & 7;        // 16-byte chunk (8 bf16) inside the 128-byte row
+        const int c = lane & 7;        // 16-byte chunk (8 hidden units) inside the 64-wide K block
         const int rsub = lane >> 3;    // 4 rows per warp pass
-        uint32_t tl = 0;
-        TileInfo ti;
-        for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
-            if (!tile_info<kCtas>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
-            uint32_t eoff[4], doff[4];  // element offsets of this lane's 4 rows
+        // Flattened (tile, K block) sequence with TWO blocks of loads in flight: the loads of block n+2
+        // are issued right after block n has been written, so an L2 round trip is hidden behind two
+        // block periods (and, across tiles, behind the wait for the MMAs to release the slot).
+        int ltile = tile0 - tile_stride, lkb = KB;   // load cursor
+        uint32_t eoff[4], doff[4];
+        auto issue = [&](uint4 (&re)[4], uint4 (&rd)[4]) -> bool {
+            if (lkb == KB) {
+                TileInfo ti;
+                do {
+                    ltile += tile_stride;
+                    if (ltile >= total_tiles) { ltile = total_tiles; return false; }
+                } while (!tile_info<kCtas>(ltile, tiles_per_utt, rank, tlen, ulen, T, U1, ti));
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const int row = pw * 16 + p * 4 + rsub;
+                    const int m = min(ti.first_cell + row, ti.n_cells - 1);  // clamp padding rows
+                    const int t = m / ti.U1b, u = m - t * ti.U1b;
+                    eoff[p] = (uint32_t)(((size_t)ti.b * T + t) * J) + c * 8;
+                    doff[p] = (uint32_t)(((size_t)ti.b * U1 + u) * J) + c * 8;
+                }
+                lkb = 0;
+            }
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
-                int row = pw * 16 + p * 4 + rsub;
-                int m = min(ti.first_cell + row, ti.n_cells - 1);  // clamp padding rows
-                int t = m / ti.U1b, u = m - t * ti.U1b;
-                eoff[p] = (uint32_t)(((size_t)ti.b * T + t) * J) + c * 8;
-                doff[p] = (uint32_t)(((size_t)ti.b * U1 + u) * J) + c * 8;
+                re[p] = __ldg(reinterpret_cast<const uint4*>(enc + eoff[p] + lkb * kBlockK));
+                rd[p] = __ldg(reinterpret_cast<const uint4*>(dec + doff[p] + lkb * kBlockK));
             }
-            for (int kb = 0; kb < KB; ++kb) {
-                mbar_wait(smem_u32(&bars->a_empty[kb]), (tl & 1) ^ 1);
-                produce_h_block16(enc, dec, eoff, doff, kb, pw, rsub, c, sA + (size_t)kb * kABlockBytes);
-                fence_proxy_async_smem();
-                if (store_h) mbar_arrive(smem_u32(&bars->h_ready[kb]));
-                if (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->a_full[kb]), 0));
-                else       mbar_arrive(smem_u32(&bars->a_full[kb]));
-            }
-            ++tl;
+            ++lkb;
+            return true;
+        };
+        uint32_t wkb = 0, wtl = 0;                   // work cursor: same sequence, KB blocks per valid tile
+        auto work = [&](const uint4 (&re)[4], const uint4 (&rd)[4]) {
+            mbar_wait(smem_u32(&bars->a_empty[wkb]), (wtl & 1) ^ 1);
+            produce_h_block16(re, rd, pw, rsub, c, sA + (size_t)wkb * kABlockBytes);
+            fence_proxy_async_smem();
+            if (store_h) mbar_arrive(smem_u32(&bars->h_ready[wkb]));
+            if (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->a_full[wkb]), 0));
+            else       mbar_arrive(smem_u32(&bars->a_full[wkb]));
+            if (++wkb == (uint32_t)KB) { wkb = 0; ++wtl; }
+        };
+        uint4 e0[4], d0[4], e1[4], d1[4];
+        bool v0 = issue(e0, d0);
+        bool v1 = v0 && issue(e1, d1);
+        while (v0) {
+            work(e0, d0);
+            v0 = v1 && issue(e0, d0);
+            if (!v1) break;
+            work(e1, d1);
+            v1 = v0 && issue(e1, d1);
         }
     }
 
@@ -412,6 +436,13 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     size_t nw = (size_t)V * J;
     f32_to_bf16_kernel<<<ceil_div(nw, 4 * 256), 256, 0, st>>>(w_out, w_bf16, nw);
     EMO_CHECK_LAUNCH("f32_to_bf16_kernel");
+    // fp16 copies of the two projected streams (11-bit mantissa, half the gather bytes of fp32)
+    const size_t ne = (size_t)B * T * J, nd = (size_t)B * U1 * J;
+    __half* enc_h = reinterpret_cast<__half*>((char*)ws + align_up(nw * sizeof(__nv_bfloat16), 256));
+    __half* dec_h = reinterpret_cast<__half*>((char*)enc_h + align_up(ne * sizeof(__half), 256));
+    f32_to_f16_kernel<<<ceil_div(ne, 4 * 256), 256, 0, st>>>(enc_proj, enc_h, ne);
+    f32_to_f16_kernel<<<ceil_div(nd, 4 * 256), 256, 0, st>>>(dec_proj, dec_h, nd);
+    EMO_CHECK_LAUNCH("f32_to_f16_kernel");
 
     const int KB = J / kBlockK;
     const size_t a_bytes = (size_t)KB * kABlockBytes;
@@ -445,7 +476,7 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         if (!store_h) tmap_h = tmap;
-        EMO_CUDA(cudaLaunchKernelEx(&cfg, joint_fwd_kernel<2>, tmap, tmap_h, store_h, enc_proj, dec_proj, b_out,
+        EMO_CUDA(cudaLaunchKernelEx(&cfg, joint_fwd_kernel<2>, tmap, tmap_h, store_h, enc_h, dec_h, b_out,
                                     labels, tlen, ulen, B, T, U1, J, V, blank, lp2, lse));
         EMO_CHECK_LAUNCH("joint_fwd_kernel<pair>");
         return EMO_OK;
@@ -458,7 +489,7 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     EMO_CUDA(cudaFuncSetAttribute(joint_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = B * ceil_div((size_t)T * U1, kTileM);
     if (!store_h) tmap_h = tmap;
-    joint_fwd_kernel<1><<<min(tiles, sm_count()), kFwdThreads, smem, st>>>(tmap, tmap_h, store_h, enc_proj, dec_proj,
+    joint_fwd_kernel<1><<<min(tiles, sm_count()), kFwdThreads, smem, st>>>(tmap, tmap_h, store_h, enc_h, dec_h,
                                                                         b_out, labels, tlen, ulen, B, T, U1, J, V,
                                                                         blank, lp2, lse);
     EMO_CHECK_LAUNCH("joint_fwd_kernel<single>");

@@ -1120,13 +1120,14 @@ size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V) {
     size_t w = align_up((size_t)V * J * sizeof(__nv_bfloat16), 256);
     if (op == EMO_OP_RNNT_JOINT_BWD)
         return w + align_up((size_t)B * T * U1 * J * sizeof(__nv_bfloat16), 256);
-    return w;
+    // forward: + fp16 copies of enc_proj and dec_proj
+    return w + align_up((size_t)B * T * J * sizeof(__half), 256) + align_up((size_t)B * U1 * J * sizeof(__half), 256);
 }
 
 int joint_bf16_launches(int op, int B, int T, int U1, int J, int V) {
     (void)B; (void)T; (void)U1; (void)J; (void)V;
     if (op == EMO_OP_RNNT_JOINT_BWD) return 4;  // weight cast, dh kernel, axis reductions, dW kernel
-    return 2;                                    // weight cast + fused joint forward
+    return 4;                                    // weight cast, 2 stream casts, fused joint forward
 }
 
 int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,

@@ -59,6 +59,17 @@ __global__ void f32_to_bf16_kernel(const float* __restrict__ src, __nv_bfloat16*
     }
 }
 
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, size_t n) {
+    size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i + 3 < n) {
+        float4 v = *reinterpret_cast<const float4*>(src + i);
+        uint2 o = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
+        *reinterpret_cast<uint2*>(dst + i) = o;
+    } else {
+        for (; i < n; ++i) dst[i] = __float2half_rn(src[i]);
+    }
+}
+
 // A-operand producer shared by the forward and backward kernels: this warp's 32 rows of the
 // 128-row tile, K block kb.  h = tanh(enc + dec) -> bf16 -> canonical K-major SW128 layout
 // (16-byte chunk index XOR (row mod 8)).

@@ -4,6 +4,7 @@
 #pragma once
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace emo {
@@ -180,6 +181,34 @@ __device__ __forceinline__ float tanh_approx(float x) {
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
     asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// ---- packed half helpers (two fp16 values in a 32-bit register, low half = first element) ----
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float2 unpack_f16x2(uint32_t v) {
+    float2 f;
+    asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %2;\n\tcvt.f32.f16 %0, lo;\n\tcvt.f32.f16 %1, hi;\n\t}"
+        : "=f"(f.x), "=f"(f.y)
+        : "r"(v));
+    return f;
+}
+__device__ __forceinline__ uint32_t hadd2_u32(uint32_t a, uint32_t b) {
+    uint32_t r;
+    asm("add.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+    return r;
+}
+__device__ __forceinline__ uint32_t ex2_f16x2(uint32_t x) {
+    uint32_t y;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+    return y;
+}
+__device__ __forceinline__ uint32_t tanh_f16x2(uint32_t x) {
+    uint32_t y;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
     return y;
 }
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
