@@ -76,6 +76,14 @@ __device__ __forceinline__ void lse_merge(float& m, float& s, float m2, float s2
     m = mn;
 }
 
+// same, with exp2 of log2e-scaled differences (matches the kernels' ex2.approx arithmetic)
+__device__ __forceinline__ void lse_merge_exp2(float& m, float& s, float m2, float s2) {
+    const float mn = fmaxf(m, m2);
+    if (mn == kNegInf) { m = mn; s = 0.f; return; }
+    s = s * exp2f((m - mn) * 1.4426950408889634f) + s2 * exp2f((m2 - mn) * 1.4426950408889634f);
+    m = mn;
+}
+
 inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

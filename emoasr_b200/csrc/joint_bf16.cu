@@ -27,11 +27,11 @@ namespace {
 // ---- per-variant constants ----
 template <int kCtas> struct Cfg;
 template <> struct Cfg<1> {
-    static constexpr int kBStages = 3;
+    static constexpr int kBStages = 2;                // (tuning switch only; the pair kernel is the product path)
     static constexpr int kBRows = kChunkN;            // vocab rows of a w_out tile held by this CTA
 };
 template <> struct Cfg<2> {
-    static constexpr int kBStages = 6;
+    static constexpr int kBStages = 5;
     static constexpr int kBRows = kChunkN / 2;
 };
 
@@ -39,7 +39,7 @@ template <int kCtas>
 struct __align__(16) FwdBarriers {
     uint64_t b_full[Cfg<kCtas>::kBStages], b_empty[Cfg<kCtas>::kBStages];
     uint64_t a_full[kMaxKBlocks], a_empty[kMaxKBlocks];
-    uint64_t h_ready[kMaxKBlocks];  // local: this CTA's 128 producer threads have written block kb
+    uint64_t h_ready[kMaxKBlocks];  // local: this CTA's producer threads have written block kb
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     uint32_t pad[3];
@@ -95,7 +95,8 @@ __device__ __forceinline__ void lse_group(const uint32_t (&r)[32], const float* 
 // stages only half (128 vocab rows) of every w_out tile.  Barrier topology for the pair:
 //   b_full / a_full / acc_empty live in the LEADER (arrivals from both CTAs, TMA bytes from both),
 //   b_empty / a_empty / acc_full are signalled in BOTH CTAs by a multicast tcgen05.commit.
-constexpr int kFwdThreads = 512;  // 4 control warps, 4 epilogue warps, 8 A-producer warps
+constexpr int kFwdThreads = 512;  // 4 control warps, 8 epilogue warps, 4 A-producer warps
+constexpr int kFwdEpiThreads = 256;
 template <int N> __device__ __forceinline__ void reg_dec() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
@@ -146,6 +147,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     uint8_t* sB = sA + (size_t)KB * kABlockBytes;
     Bars* bars = reinterpret_cast<Bars*>(sB + (size_t)kBStages * kBBytes);
     float* s_bias = reinterpret_cast<float*>(bars + 1);  // [2][kChunkN]
+    float4* s_part = reinterpret_cast<float4*>(s_bias + 2 * kChunkN);  // [kTileM] partial LSE state of column half 1
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = kPair ? cluster_ctarank() : 0;
@@ -153,8 +155,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     const int tiles_per_utt = (T * U1 + kCtas * kTileM - 1) / (kCtas * kTileM);
     const int total_tiles = B * tiles_per_utt;
     const int tile0 = blockIdx.x / kCtas, tile_stride = gridDim.x / kCtas;
-    constexpr uint32_t kArrivals = 128 * kCtas;   // epilogue threads of the pair
-    constexpr uint32_t kProducers = 256;          // A-producer threads per CTA
+    constexpr uint32_t kArrivals = (kFwdEpiThreads / 32) * kCtas;   // epilogue WARPS of the pair (one arrive each)
+    constexpr uint32_t kProducers = 128;                            // A-producer threads per CTA
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kBStages; ++i) {
@@ -184,9 +186,10 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     if (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
-    // register budget per warpgroup: control 56, epilogue 216, producers 104 (x128 threads: 61440 <= 64K)
+    // register budget per warpgroup (x128 threads): control 40, two epilogue groups 184, producers 104
+    // -> 5120 + 2 * 23552 + 13312 = 65536
     if (warp < 4) {
-    reg_dec<56>();
+    reg_dec<40>();
     if (warp == 0) {
         // ===================== TMA producer =====================
         if (lane == 0) {
@@ -286,20 +289,21 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             tma_store_wait_all<0>();
         }
     }
-    } else if (warp < 8) {
-        reg_inc<216>();
+    } else if (warp < 12) {
+        reg_inc<184>();
         // ===================== epilogue: online LSE over vocab chunks =====================
-        const int q = warp & 3;
+        // Two warps per TMEM lane quadrant: warp (q, hf) owns columns [128 hf, 128 hf + 128) of every 256-wide
+        // chunk for the rows of quadrant q.  The two partial (max, sum, blank, label) states of a row are
+        // merged through shared memory once per tile.
+        const int q = warp & 3, hf = (warp - 4) >> 2;
         const int row = q * 32 + lane;
-        const int etid = threadIdx.x - 128;
+        const int etid = threadIdx.x - 128;   // 0..255
         uint32_t cc = 0;
         TileInfo ti;
         uint32_t acc_empty_addr[2];
         acc_empty_addr[0] = kPair ? mapa_shared(smem_u32(&bars->acc_empty[0]), 0) : smem_u32(&bars->acc_empty[0]);
         acc_empty_addr[1] = kPair ? mapa_shared(smem_u32(&bars->acc_empty[1]), 0) : smem_u32(&bars->acc_empty[1]);
-        // bias of the first chunk of the first tile
-        float nb0 = etid < V ? __ldg(b_out + etid) : 0.f;
-        float nb1 = etid + 128 < V ? __ldg(b_out + etid + 128) : 0.f;
+        float nb = etid < V ? __ldg(b_out + etid) : 0.f;   // bias of the first chunk of the first tile
         for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
             if (!tile_info<kCtas>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
             const int m = ti.first_cell + row;
@@ -314,37 +318,47 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 const uint32_t buf = cc & 1;
                 const int n = min(kChunkN, V - nc * kChunkN);
                 float* bias = s_bias + buf * kChunkN;
-                bias[etid] = nb0;
-                bias[etid + 128] = nb1;
+                bias[etid] = nb;
                 {   // prefetch the next chunk's bias (wraps to chunk 0 for the next tile)
                     const int nn = (nc + 1 == NC) ? 0 : nc + 1;
                     const int i0 = nn * kChunkN + etid;
-                    nb0 = i0 < V ? __ldg(b_out + i0) : 0.f;
-                    nb1 = i0 + 128 < V ? __ldg(b_out + i0 + 128) : 0.f;
+                    nb = i0 < V ? __ldg(b_out + i0) : 0.f;
                 }
-                named_bar_sync(1, 128);
+                named_bar_sync(1, kFwdEpiThreads);
                 mbar_wait(smem_u32(&bars->acc_full[buf]), (cc >> 1) & 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + buf * kChunkN;
-                const int G = n >> 5;
-                uint32_t ra[32], rb[32];
-                tmem_ld_32x32b_x32(taddr, ra);
-                for (int g = 0; g < G; g += 2) {
-                    tmem_wait_ld();
-                    if (g + 1 < G) tmem_ld_32x32b_x32(taddr + (g + 1) * 32, rb);
-                    lse_group(ra, bias + g * 32, nc * kChunkN + g * 32, lab, blank, run_m, run_s, zb, zl);
-                    if (g + 1 < G) {
+                const int g0 = hf * 4, g1 = min(hf * 4 + 4, n >> 5);   // my 32-column groups of the chunk
+                if (g0 < g1) {
+                    uint32_t ra[32], rb[32];
+                    tmem_ld_32x32b_x32(taddr + g0 * 32, ra);
+                    for (int g = g0; g < g1; g += 2) {
                         tmem_wait_ld();
-                        if (g + 2 < G) tmem_ld_32x32b_x32(taddr + (g + 2) * 32, ra);
-                        lse_group(rb, bias + (g + 1) * 32, nc * kChunkN + (g + 1) * 32, lab, blank, run_m,
-                                  run_s, zb, zl);
+                        if (g + 1 < g1) tmem_ld_32x32b_x32(taddr + (g + 1) * 32, rb);
+                        lse_group(ra, bias + g * 32, nc * kChunkN + g * 32, lab, blank, run_m, run_s, zb, zl);
+                        if (g + 1 < g1) {
+                            tmem_wait_ld();
+                            if (g + 2 < g1) tmem_ld_32x32b_x32(taddr + (g + 2) * 32, ra);
+                            lse_group(rb, bias + (g + 1) * 32, nc * kChunkN + (g + 1) * 32, lab, blank, run_m,
+                                      run_s, zb, zl);
+                        }
                     }
                 }
                 tc_fence_before();
-                if (kPair) mbar_arrive_cluster(acc_empty_addr[buf]);
-                else       mbar_arrive(acc_empty_addr[buf]);
+                __syncwarp();
+                if (lane == 0) {
+                    if (kPair) mbar_arrive_cluster(acc_empty_addr[buf]);
+                    else       mbar_arrive(acc_empty_addr[buf]);
+                }
             }
-            if (valid) {
+            // ---- merge the two column halves of the row (half 1 -> shared memory -> half 0)
+            if (hf == 1) s_part[row] = make_float4(run_m, run_s, zb, zl);
+            named_bar_sync(2, kFwdEpiThreads);
+            if (hf == 0 && valid) {
+                const float4 o = s_part[row];
+                lse_merge_exp2(run_m, run_s, o.x, o.y);
+                if (((blank % kChunkN) >> 7) == 1) zb = o.z;
+                if (lab >= 0 && ((lab % kChunkN) >> 7) == 1) zl = o.w;
                 const float l = run_m + kLn2 * log2f(run_s);
                 const size_t cell = ((size_t)ti.b * T + t) * U1 + u;
                 reinterpret_cast<float2*>(lp2)[cell] = make_float2(zb - l, lab >= 0 ? zl - l : 0.f);
@@ -354,48 +368,60 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     } else {
         reg_dec<104>();
         // ===================== A producers =====================
-        const int pw = warp - 8;       // 8 producer warps, 16 rows each
+        const int pw = warp - 12;      // 4 producer warps, 32 rows each, produced as two 16-row halves
         const int c = lane & 7;        // 16-byte chunk (8 hidden units) inside the 64-wide K block
         const int rsub = lane >> 3;    // 4 rows per warp pass
-        // Flattened (tile, K block) sequence with TWO blocks of loads in flight: the loads of block n+2
-        // are issued right after block n has been written, so an L2 round trip is hidden behind two
-        // block periods (and, across tiles, behind the wait for the MMAs to release the slot).
-        int ltile = tile0 - tile_stride, lkb = KB;   // load cursor
-        uint32_t eoff[4], doff[4];
+        // Flattened (tile, K block, half) sequence with TWO units of loads in flight: the loads of unit n+2
+        // are issued right after unit n has been written, so an L2 round trip is hidden behind two
+        // unit periods (and, across tiles, behind the wait for the MMAs to release the slot).
+        int ltile = tile0 - tile_stride, lunit = 2 * KB;   // load cursor; unit = 2 * kb + half
+        uint32_t eoff[8], doff[8];
         auto issue = [&](uint4 (&re)[4], uint4 (&rd)[4]) -> bool {
-            if (lkb == KB) {
+            if (lunit == 2 * KB) {
                 TileInfo ti;
                 do {
                     ltile += tile_stride;
                     if (ltile >= total_tiles) { ltile = total_tiles; return false; }
                 } while (!tile_info<kCtas>(ltile, tiles_per_utt, rank, tlen, ulen, T, U1, ti));
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    const int row = pw * 16 + p * 4 + rsub;
+                for (int p = 0; p < 8; ++p) {
+                    const int row = pw * 32 + p * 4 + rsub;
                     const int m = min(ti.first_cell + row, ti.n_cells - 1);  // clamp padding rows
                     const int t = m / ti.U1b, u = m - t * ti.U1b;
                     eoff[p] = (uint32_t)(((size_t)ti.b * T + t) * J) + c * 8;
                     doff[p] = (uint32_t)(((size_t)ti.b * U1 + u) * J) + c * 8;
                 }
-                lkb = 0;
+                lunit = 0;
             }
+            const int lkb = lunit >> 1;
+            if (lunit & 1) {
 #pragma unroll
-            for (int p = 0; p < 4; ++p) {
-                re[p] = __ldg(reinterpret_cast<const uint4*>(enc + eoff[p] + lkb * kBlockK));
-                rd[p] = __ldg(reinterpret_cast<const uint4*>(dec + doff[p] + lkb * kBlockK));
+                for (int p = 0; p < 4; ++p) {
+                    re[p] = __ldg(reinterpret_cast<const uint4*>(enc + eoff[4 + p] + lkb * kBlockK));
+                    rd[p] = __ldg(reinterpret_cast<const uint4*>(dec + doff[4 + p] + lkb * kBlockK));
+                }
+            } else {
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    re[p] = __ldg(reinterpret_cast<const uint4*>(enc + eoff[p] + lkb * kBlockK));
+                    rd[p] = __ldg(reinterpret_cast<const uint4*>(dec + doff[p] + lkb * kBlockK));
+                }
             }
-            ++lkb;
+            ++lunit;
             return true;
         };
-        uint32_t wkb = 0, wtl = 0;                   // work cursor: same sequence, KB blocks per valid tile
+        uint32_t wunit = 0, wtl = 0;                 // work cursor: same sequence, 2 * KB units per valid tile
         auto work = [&](const uint4 (&re)[4], const uint4 (&rd)[4]) {
-            mbar_wait(smem_u32(&bars->a_empty[wkb]), (wtl & 1) ^ 1);
-            produce_h_block16(re, rd, pw, rsub, c, sA + (size_t)wkb * kABlockBytes);
-            fence_proxy_async_smem();
-            if (store_h) mbar_arrive(smem_u32(&bars->h_ready[wkb]));
-            if (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->a_full[wkb]), 0));
-            else       mbar_arrive(smem_u32(&bars->a_full[wkb]));
-            if (++wkb == (uint32_t)KB) { wkb = 0; ++wtl; }
+            const uint32_t wkb = wunit >> 1, half = wunit & 1;
+            if (!half) mbar_wait(smem_u32(&bars->a_empty[wkb]), (wtl & 1) ^ 1);
+            produce_h_block16(re, rd, 2 * pw + (int)half, rsub, c, sA + (size_t)wkb * kABlockBytes);
+            if (half) {
+                fence_proxy_async_smem();
+                if (store_h) mbar_arrive(smem_u32(&bars->h_ready[wkb]));
+                if (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->a_full[wkb]), 0));
+                else       mbar_arrive(smem_u32(&bars->a_full[wkb]));
+            }
+            if (++wunit == 2u * (uint32_t)KB) { wunit = 0; ++wtl; }
         };
         uint4 e0[4], d0[4], e1[4], d1[4];
         bool v0 = issue(e0, d0);
@@ -460,7 +486,7 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
         rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, Cfg<2>::kBRows);
         if (rc) return rc;
         const size_t smem = a_bytes + (size_t)Cfg<2>::kBStages * Cfg<2>::kBRows * kBlockK * 2 +
-                            sizeof(FwdBarriers<2>) + 2 * kChunkN * sizeof(float);
+                            sizeof(FwdBarriers<2>) + 2 * kChunkN * sizeof(float) + kTileM * sizeof(float4);
         EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_fwd(bf16): shared memory");
         EMO_CUDA(cudaFuncSetAttribute(joint_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const int ptiles = B * ceil_div((size_t)T * U1, 2 * kTileM);
@@ -484,7 +510,7 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, Cfg<1>::kBRows);
     if (rc) return rc;
     const size_t smem = a_bytes + (size_t)Cfg<1>::kBStages * Cfg<1>::kBRows * kBlockK * 2 +
-                        sizeof(FwdBarriers<1>) + 2 * kChunkN * sizeof(float);
+                        sizeof(FwdBarriers<1>) + 2 * kChunkN * sizeof(float) + kTileM * sizeof(float4);
     EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_fwd(bf16): shared memory");
     EMO_CUDA(cudaFuncSetAttribute(joint_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int tiles = B * ceil_div((size_t)T * U1, kTileM);
