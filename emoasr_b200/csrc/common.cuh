@@ -49,12 +49,31 @@ __device__ __forceinline__ float log_add_exp(float a, float b) {
     return m + log1pf(expf(-fabsf(a - b)));
 }
 
-// same with the hardware ex2/lg2 approximations: absolute error ~1e-7, used inside the serial lattice
-// recursions where the full-precision expf/log1pf latency is the critical path
+// ---- single-instruction ex2 / lg2 (MUFU) and branch-free log-sum-exp built on them.  Used inside the
+// serial lattice recursions, where the expansions of expf/logf (range fix-ups, branches) are the
+// critical path.  Absolute error of a log-add ~1e-7.  -inf safe: the pivot is clamped to -1e30 so
+// that (-inf) - pivot stays -inf (no NaN); an all -inf input gives lg2(0) = -inf.
+__device__ __forceinline__ float ex2_ftz(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float lg2_ftz(float x) {
+    float y;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+constexpr float kLog2eF = 1.4426950408889634f;
+constexpr float kLn2F = 0.6931471805599453f;
 __device__ __forceinline__ float log_add_exp_fast(float a, float b) {
-    float m = fmaxf(a, b);
-    if (m == kNegInf) return kNegInf;
-    return m + __logf(1.f + __expf(-fabsf(a - b)));
+    const float m = fmaxf(fmaxf(a, b), -1e30f);
+    const float s = ex2_ftz((a - m) * kLog2eF) + ex2_ftz((b - m) * kLog2eF);
+    return fmaf(lg2_ftz(s), kLn2F, m);
+}
+__device__ __forceinline__ float log_add_exp3_fast(float a, float b, float c) {
+    const float m = fmaxf(fmaxf(fmaxf(a, b), c), -1e30f);
+    const float s = ex2_ftz((a - m) * kLog2eF) + ex2_ftz((b - m) * kLog2eF) + ex2_ftz((c - m) * kLog2eF);
+    return fmaf(lg2_ftz(s), kLn2F, m);
 }
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -200,8 +200,7 @@ ctc_lattice_kernel(const long long* __restrict__ labels, const long long* __rest
                     const float a = prev[s];
                     const float n1 = prev[s + nb];
                     const float n2 = jump ? prev[s + 2 * nb] : kNegInf;
-                    const float m = fmaxf(fmaxf(a, n1), n2);
-                    if (m > kNegInf) val = m + __logf(__expf(a - m) + __expf(n1 - m) + __expf(n2 - m)) + lp;
+                    val = log_add_exp3_fast(a, n1, n2) + lp;
                 }
             }
             vals[k] = val;
