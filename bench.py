@@ -44,6 +44,13 @@ WORKLOADS = {
 }
 
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch, from profiles/r1c_ncu_full_metrics.txt
+# (bwd = joint_dh_kernel + reduce_dpre_kernel + joint_dwt_kernel; algorithmic: h cache read twice,
+# dpre written once and read once = 3.3 GB)
+NCU_DRAM_BYTES = {"rnnt_cfg3": {"fwd": 24.1e6 + 781.9e6,
+                                "bwd": (842.4e6 + 776.5e6) + (834.2e6 + 21.9e6) + (844.1e6 + 4.5e6)}}
+
+
 def load_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -226,7 +233,11 @@ def run_ours_rnnt(args, w, rank, world, dev):
                         2 * unit, b_ms, {"executed_flops_per_launch": 6 * unit,
                                          "note": "algorithmic = dh and dW GEMMs (2 x 2*N*J*V); z is recomputed "
                                                  "per J-part in both kernels (6 GEMM units executed)"})
-        roof["forward"] = roofline("joint_fwd_kernel (+ weight cast)", unit, f_ms, {})
+        roof["forward"] = roofline("joint_fwd_kernel (+ weight / stream casts)", unit, f_ms, {})
+        # DRAM bytes per launch from the ncu --set full capture of this workload (profiles/, cfg 3 only)
+        if args.workload == "rnnt_cfg3" and args.lengths == "full":
+            roof["traffic"] = NCU_DRAM_BYTES["rnnt_cfg3"]["bwd"]
+            roof["forward"]["traffic"] = NCU_DRAM_BYTES["rnnt_cfg3"]["fwd"]
 
     prec = 1 if args.precision == "bf16" else 0
     per_step = (_lib.launch_count(_lib.OP_RNNT_JOINT_FWD, prec, w["B"], w["T"], w["U"] + 1, w["J"], w["V"]) +

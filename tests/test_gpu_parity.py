@@ -382,3 +382,35 @@ def test_ctc_backward_without_staged_beta_matches_training_path():
     assert torch.allclose(nll2, nll.detach(), rtol=1e-6, atol=1e-6)
     # the two routes may differ by an ulp of beta (~1.5e-5 at |beta| ~ 130), i.e. ~1e-5 on a posterior
     assert torch.allclose(grad, x.grad, rtol=GRAD_RTOL, atol=2e-5)
+
+
+def test_joint_bf16_properties_full_size_cfg3():
+    """BASELINE cfg 3 at full size (B=32,T=250,U=100,V=1024,J=512; the oracle would need 3.3 GB tensors):
+    size-independent properties of the fused tensor-core path.
+      * every dz row sums to zero (softmax - two one-hots)        =>  sum(d_b_out) ~ 0
+      * d_enc_proj and d_dec_proj are two marginals of one tensor  =>  sum_t d_enc[b,t,:] == sum_u d_dec[b,u,:]
+      * padded frames / labels get exactly zero gradient
+      * the loss agrees with the fp32 FFMA mode on the same inputs within the stated bf16 tolerance."""
+    import emoasr_b200 as E
+    gen = torch.Generator().manual_seed(11)
+    B, T, U, V, J = 32, 250, 100, 1024, 512
+    enc = torch.randn(B, T, J, generator=gen).to(dev())
+    dec_ = torch.randn(B, U + 1, J, generator=gen).to(dev())
+    w = (torch.randn(V, J, generator=gen) / J ** 0.5).to(dev())
+    bo = (0.1 * torch.randn(V, generator=gen)).to(dev())
+    ys = torch.randint(1, V, (B, U), generator=gen).to(dev())
+    r = torch.linspace(1.0, 0.6, B)
+    tl, ul = (T * r).long().to(dev()), (U * r).long().to(dev())
+    te = [t.clone().requires_grad_() for t in (enc, dec_, w, bo)]
+    loss = E.rnnt_joint_loss(*te, ys, tl, ul, blank=0, reduction="mean", precision="bf16")
+    loss.backward()
+    d_enc, d_dec, d_w, d_b = [t.grad for t in te]
+    assert torch.isfinite(loss) and all(torch.isfinite(g).all() for g in (d_enc, d_dec, d_w, d_b))
+    assert abs(float(d_b.sum())) < 2e-2 * float(d_b.abs().sum())
+    m_enc, m_dec = d_enc.sum(1), d_dec.sum(1)                      # (B, J) each
+    assert float((m_enc - m_dec).norm() / m_enc.norm()) < 1e-2      # dpre is stored in bf16 between the two sums
+    b = B - 1
+    assert float(d_enc[b, int(tl[b]):].abs().sum()) == 0.0 and float(d_dec[b, int(ul[b]) + 1:].abs().sum()) == 0.0
+    with torch.no_grad():
+        loss32 = E.rnnt_joint_loss(enc, dec_, w, bo, ys, tl, ul, blank=0, reduction="mean", precision="fp32")
+    assert abs(float(loss) - float(loss32)) <= BF16_LOSS_RTOL * abs(float(loss32))
