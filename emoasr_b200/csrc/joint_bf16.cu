@@ -66,19 +66,15 @@ __device__ __forceinline__ void lse_group(const uint32_t (&r)[32], const float* 
     }
     const float new_m = fmaxf(run_m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
     const float neg_m2 = -new_m * kLog2e;
-    // exp2 of two logits per MUFU op (ex2.approx.f16x2): the special-function unit, shared with the
-    // tanh of the A producers, is the scarce pipe of this kernel.  Arguments are <= 0, results in (0,1];
-    // four packed accumulators keep each half-precision sum to four terms before it is widened.
-    uint32_t h0 = 0u, h1 = 0u, h2 = 0u, h3 = 0u;   // half2 zeros
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-    for (int i = 0; i < 32; i += 8) {
-        h0 = hadd2_u32(h0, ex2_f16x2(pack_f16x2(fmaf(x[i + 0], kLog2e, neg_m2), fmaf(x[i + 1], kLog2e, neg_m2))));
-        h1 = hadd2_u32(h1, ex2_f16x2(pack_f16x2(fmaf(x[i + 2], kLog2e, neg_m2), fmaf(x[i + 3], kLog2e, neg_m2))));
-        h2 = hadd2_u32(h2, ex2_f16x2(pack_f16x2(fmaf(x[i + 4], kLog2e, neg_m2), fmaf(x[i + 5], kLog2e, neg_m2))));
-        h3 = hadd2_u32(h3, ex2_f16x2(pack_f16x2(fmaf(x[i + 6], kLog2e, neg_m2), fmaf(x[i + 7], kLog2e, neg_m2))));
+    for (int i = 0; i < 32; i += 4) {
+        s0 += ex2_approx(fmaf(x[i + 0], kLog2e, neg_m2));
+        s1 += ex2_approx(fmaf(x[i + 1], kLog2e, neg_m2));
+        s2 += ex2_approx(fmaf(x[i + 2], kLog2e, neg_m2));
+        s3 += ex2_approx(fmaf(x[i + 3], kLog2e, neg_m2));
     }
-    const float2 f0 = unpack_f16x2(h0), f1 = unpack_f16x2(h1), f2 = unpack_f16x2(h2), f3 = unpack_f16x2(h3);
-    run_s = run_s * ex2_approx((run_m - new_m) * kLog2e) + (((f0.x + f0.y) + (f1.x + f1.y)) + ((f2.x + f2.y) + (f3.x + f3.y)));
+    run_s = run_s * ex2_approx((run_m - new_m) * kLog2e) + ((s0 + s1) + (s2 + s3));
     run_m = new_m;
     const int dl = lab - v0;
     const bool mine = dl >= 0 && dl < 32;
