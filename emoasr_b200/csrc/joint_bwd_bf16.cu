@@ -411,6 +411,7 @@ joint_dh_kernel(const __grid_constant__ CUtensorMap tmap_wz,   // w_out bf16, bo
         const uint32_t dz_full_addr = mapa_shared(smem_u32(&bars->dz_full), 0);
         const uint32_t acc_empty_addr = mapa_shared(smem_u32(&bars->acc_empty), 0);
         TileInfo ti;
+        float nb = e < chunk_cols(0) ? __ldg(b_out + e) : 0.f;   // bias of the next chunk, one chunk ahead
         for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
             if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
             RowCtx rc;
@@ -420,7 +421,11 @@ joint_dh_kernel(const __grid_constant__ CUtensorMap tmap_wz,   // w_out bf16, bo
                     const uint32_t zb = zc & 1;
                     const int n = chunk_cols(c);
                     float* bias = s_bias + zb * kBwdChunk;
-                    if (e < n) bias[e] = __ldg(b_out + c * kBwdChunk + e);
+                    if (e < kBwdChunk) bias[e] = nb;
+                    {
+                        const int cn = c + 1 == NCH ? 0 : c + 1;
+                        nb = e < chunk_cols(cn) ? __ldg(b_out + cn * kBwdChunk + e) : 0.f;
+                    }
                     named_bar_sync(1, kEpiThreads);
                     mbar_wait(smem_u32(&bars->z_full[zb]), (zc >> 1) & 1);
                     tc_fence_after();
@@ -933,15 +938,28 @@ joint_dwt_kernel(const __grid_constant__ CUtensorMap tmap_w,    // w_out bf16, b
         float rowsum = 0.f;
         bool any_tile = false;
         TileInfo ti;
+        // per-cell scalars are fetched ONE TILE AHEAD into registers of the 128 staging threads: their
+        // dependent global loads (labels, lse, gamma) would otherwise sit on the z -> dz -> dW chain
+        int ntile = tile0 - num_splits;
+        RowCtx rc_next;
+        auto fetch_next = [&]() {
+            TileInfo ni;
+            do {
+                ntile += num_splits;
+                if (ntile >= total_tiles) { ntile = total_tiles; return; }
+            } while (!tile_info<1>(ntile, tiles_per_utt, 0, tlen, ulen, T, U1, ni));
+            if (e < kTileM) load_row_ctx(rc_next, ni, e, T, U1, V, labels, lse, gamma2, grad_cost);
+        };
+        fetch_next();
         for (int tile = tile0; tile < total_tiles; tile += num_splits) {
             if (!tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) continue;
-            // ---- per-cell scalars of the tile
+            // ---- per-cell scalars of the tile (loaded during the previous tile)
             if (e < kTileM) {
-                RowCtx rc;
-                load_row_ctx(rc, ti, e, T, U1, V, labels, lse, gamma2, grad_cost);
-                s_c2[e] = rc.c2; s_gg[e] = rc.gg; s_cb[e] = rc.corr_b; s_cl[e] = rc.corr_l; s_lab[e] = rc.lab;
+                s_c2[e] = rc_next.c2; s_gg[e] = rc_next.gg; s_cb[e] = rc_next.corr_b; s_cl[e] = rc_next.corr_l;
+                s_lab[e] = rc_next.lab;
             }
             named_bar_sync(1, kEpiThreads);
+            fetch_next();
             const uint32_t zb = zc & 1;
             mbar_wait(smem_u32(&bars->z_full[zb]), (zc >> 1) & 1);
             tc_fence_after();
