@@ -787,6 +787,11 @@ joint_dwt_kernel(const __grid_constant__ CUtensorMap tmap_w,    // w_out bf16, b
     const bool full_group = J - g * 256 >= 256;                      // 128-wide last group: both CTAs duplicate it
     const int j0_r = g * 256 + (full_group ? (int)rank * kTileM : 0);
     const bool flush_dw = full_group || leader;
+    // The pairs of one split walk the same tile list; each role starts at a different point of it, so the
+    // 2 * roles CTAs do not all pull the same h tile out of the same L2 lines at the same moment.
+    const int n_seq = tile0 < total_tiles ? (total_tiles - tile0 + num_splits - 1) / num_splits : 0;
+    const int seq_off = n_seq > 0 ? (role * 5) % n_seq : 0;
+    auto tile_at = [&](int sk) { int i = sk + seq_off; if (i >= n_seq) i -= n_seq; return tile0 + i * num_splits; };
 
     if (warp == 1 && lane == 0) {
         mbar_init(smem_u32(&bars->w_full), 2);
@@ -829,7 +834,8 @@ joint_dwt_kernel(const __grid_constant__ CUtensorMap tmap_w,    // w_out bf16, b
                 tma_load_2d_pair(smem_u32(sW + (size_t)kb * kABlockBytes), &tmap_w, kb * kBlockK, v0_r, wf);
             uint32_t slot = 0, sphase = 0;
             TileInfo ti;
-            for (int tile = tile0; tile < total_tiles; tile += num_splits) {
+            for (int sk = 0; sk < n_seq; ++sk) {
+            const int tile = tile_at(sk);
                 if (!tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) continue;
                 const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM + (int)rank * 64;
                 for (int kb = 0; kb < KB; ++kb) {
@@ -847,7 +853,8 @@ joint_dwt_kernel(const __grid_constant__ CUtensorMap tmap_w,    // w_out bf16, b
         if (lane == 0) {
             uint32_t tl = 0;
             TileInfo ti;
-            for (int tile = tile0; tile < total_tiles; tile += num_splits) {
+            for (int sk = 0; sk < n_seq; ++sk) {
+            const int tile = tile_at(sk);
                 if (!tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) continue;
                 const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM;
                 mbar_wait(smem_u32(&bars->hd_empty), (tl & 1) ^ 1);
@@ -909,7 +916,8 @@ joint_dwt_kernel(const __grid_constant__ CUtensorMap tmap_w,    // w_out bf16, b
             mbar_wait(smem_u32(&bars->w_full), 0);
             bool have_cur = false;
             TileInfo ti;
-            for (int tile = tile0; tile < total_tiles; tile += num_splits) {
+            for (int sk = 0; sk < n_seq; ++sk) {
+            const int tile = tile_at(sk);
                 if (!tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) continue;
                 z_mma();                    // z^T of this tile runs while the epilogue works on the previous one
                 if (have_cur) dw_mma();     // dW^T of the previous tile
@@ -940,18 +948,18 @@ joint_dwt_kernel(const __grid_constant__ CUtensorMap tmap_w,    // w_out bf16, b
         TileInfo ti;
         // per-cell scalars are fetched ONE TILE AHEAD into registers of the 128 staging threads: their
         // dependent global loads (labels, lse, gamma) would otherwise sit on the z -> dz -> dW chain
-        int ntile = tile0 - num_splits;
+        int nk = -1;
         RowCtx rc_next;
         auto fetch_next = [&]() {
             TileInfo ni;
             do {
-                ntile += num_splits;
-                if (ntile >= total_tiles) { ntile = total_tiles; return; }
-            } while (!tile_info<1>(ntile, tiles_per_utt, 0, tlen, ulen, T, U1, ni));
+                if (++nk >= n_seq) { nk = n_seq; return; }
+            } while (!tile_info<1>(tile_at(nk), tiles_per_utt, 0, tlen, ulen, T, U1, ni));
             if (e < kTileM) load_row_ctx(rc_next, ni, e, T, U1, V, labels, lse, gamma2, grad_cost);
         };
         fetch_next();
-        for (int tile = tile0; tile < total_tiles; tile += num_splits) {
+        for (int sk = 0; sk < n_seq; ++sk) {
+            const int tile = tile_at(sk);
             if (!tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) continue;
             // ---- per-cell scalars of the tile (loaded during the previous tile)
             if (e < kTileM) {
