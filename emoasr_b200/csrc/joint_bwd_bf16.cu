@@ -193,7 +193,7 @@ __device__ __forceinline__ void dpre_group(const uint32_t (&r)[32], const uint8_
 struct __align__(16) DhBarriers {
     uint64_t w_full[kDhSlots], w_empty[kDhSlots];
     uint64_t h_full[kMaxKBlocks];
-    uint64_t h_empty;
+    uint64_t h_empty[kMaxKBlocks];   // per K block: blocks outside the last J-part are free before the last epilogue
     uint64_t z_full[2], z_empty[2];
     uint64_t dz_full, dz_empty;
     uint64_t acc_full, acc_empty;
@@ -237,7 +237,10 @@ joint_dh_kernel(const __grid_constant__ CUtensorMap tmap_wz,   // w_out bf16, bo
             mbar_init(smem_u32(&bars->w_empty[i]), 1);
         }
         for (int i = 0; i < kMaxKBlocks; ++i) mbar_init(smem_u32(&bars->h_full[i]), 2);
-        mbar_init(smem_u32(&bars->h_empty), 1 + kEpiThreads);
+        // a block is free once the last z MMA has read it (commit) and, for the blocks of the LAST J-part,
+        // once the dpre epilogue of that part has read h from it as well (256 threads)
+        for (int i = 0; i < kMaxKBlocks; ++i)
+            mbar_init(smem_u32(&bars->h_empty[i]), i >= (NPART - 1) * kPartBlocks ? 1 + kEpiThreads : 1);
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->z_full[i]), 1);
             mbar_init(smem_u32(&bars->z_empty[i]), 2 * kEpiWarps);   // one arrive per epilogue warp
@@ -296,19 +299,30 @@ joint_dh_kernel(const __grid_constant__ CUtensorMap tmap_wz,   // w_out bf16, bo
             TileInfo ti;
             for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
                 if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
-                const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM;
-                mbar_wait(smem_u32(&bars->h_empty), (tl & 1) ^ 1);
-                for (int kb = 0; kb < KB; ++kb) {
-                    const uint32_t hf = smem_u32(&bars->h_full[kb]);
-                    mbar_arrive_expect_tx_cluster(mapa_shared(hf, 0), kABlockBytes);
-                    tma_load_2d_pair(smem_u32(sH + (size_t)kb * kABlockBytes), &tmap_h, kb * kBlockK, row0, hf);
-                }
                 for (int p = 0; p < NPART; ++p) {
                     zloads(0);
                     for (int c = 0; c < NCH; ++c) {
                         if (c + 1 < NCH) zloads(c + 1);
                         dhloads(p, c);
                     }
+                }
+                ++tl;
+            }
+        }
+    } else if (warp == 3) {
+        // ===================== TMA: the h tile, block by block as the previous tile lets go of it (own thread,
+        // so a block still held by the last epilogue never delays the w_out stream) =====================
+        if (lane == 0) {
+            uint32_t tl = 0;
+            TileInfo ti;
+            for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+                if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
+                const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(smem_u32(&bars->h_empty[kb]), (tl & 1) ^ 1);
+                    const uint32_t hf = smem_u32(&bars->h_full[kb]);
+                    mbar_arrive_expect_tx_cluster(mapa_shared(hf, 0), kABlockBytes);
+                    tma_load_2d_pair(smem_u32(sH + (size_t)kb * kABlockBytes), &tmap_h, kb * kBlockK, row0, hf);
                 }
                 ++tl;
             }
@@ -347,7 +361,8 @@ joint_dh_kernel(const __grid_constant__ CUtensorMap tmap_wz,   // w_out bf16, bo
                         umma_commit_pair(smem_u32(&bars->w_empty[slot]));
                         if (s == ZS - 1) {
                             umma_commit_pair(smem_u32(&bars->z_full[zb]));
-                            if (release_h) umma_commit_pair(smem_u32(&bars->h_empty));
+                            if (release_h)
+                                for (int kb = 0; kb < KB; ++kb) umma_commit_pair(smem_u32(&bars->h_empty[kb]));
                         }
                     }
                     __syncwarp();
@@ -470,7 +485,7 @@ joint_dh_kernel(const __grid_constant__ CUtensorMap tmap_wz,   // w_out bf16, bo
                 if (lane == 0) mbar_arrive_cluster(acc_empty_addr);
                 ++ac;
             }
-            mbar_arrive(smem_u32(&bars->h_empty));
+            for (int kb = (NPART - 1) * kPartBlocks; kb < KB; ++kb) mbar_arrive(smem_u32(&bars->h_empty[kb]));
         }
     }
 
