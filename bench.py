@@ -176,7 +176,10 @@ def run_ours_rnnt(args, w, rank, world, dev):
         ws = torch.empty(_lib.workspace_bytes(0, 1, B, T, U1, J, V), dtype=torch.uint8, device=dev)
         lp2 = torch.empty(B, T, U1, 2, device=dev)
         lse = torch.empty(B, T, U1, device=dev)
-        hc = torch.empty(_lib.workspace_bytes(_lib.OP_RNNT_JOINT_HCACHE, 1, B, T, U1, J, V), dtype=torch.uint8, device=dev)
+        from emoasr_b200.functional import _joint_cache_bytes
+        cache_bytes = _joint_cache_bytes(1, B, T, U1, J, V, dev)       # same policy as the autograd path
+        zc = cache_bytes > _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HCACHE, 1, B, T, U1, J, V)
+        hc = torch.empty(cache_bytes, dtype=torch.uint8, device=dev)
         wo, bo = wl.output.weight.detach().contiguous(), wl.output.bias.detach().contiguous()
         p = lambda t: ctypes.c_void_p(t.data_ptr())
         st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
@@ -229,13 +232,20 @@ def run_ours_rnnt(args, w, rank, world, dev):
             r.update(extra)
             return r
         # dominant by time: the backward call (ncu launch list under profiles/ gives the per-kernel shares)
-        roof = roofline("emo_rnnt_joint_bwd = joint_dh_kernel + joint_dw_kernel (+ weight cast, 2 axis reductions)",
-                        2 * unit, b_ms, {"executed_flops_per_launch": 6 * unit,
-                                         "note": "algorithmic = dh and dW GEMMs (2 x 2*N*J*V); z is recomputed "
-                                                 "per J-part in both kernels (6 GEMM units executed)"})
+        if zc:
+            roof = roofline("emo_rnnt_joint_bwd = joint_dhz_kernel + joint_dwz_kernel (+ weight cast, axis reductions)",
+                            2 * unit, b_ms, {"executed_flops_per_launch": 2 * unit,
+                                             "note": "algorithmic = executed = dh and dW GEMMs (2 x 2*N*J*V); the "
+                                                     "logits come from the fp16 z cache the forward wrote"})
+        else:
+            roof = roofline("emo_rnnt_joint_bwd = joint_dh_kernel + joint_dwt_kernel (+ weight cast, axis reductions)",
+                            2 * unit, b_ms, {"executed_flops_per_launch": 6 * unit,
+                                             "note": "algorithmic = dh and dW GEMMs (2 x 2*N*J*V); z is recomputed "
+                                                     "per J-part in both kernels (6 GEMM units executed)"})
+        roof["z_cache"] = bool(zc)
         roof["forward"] = roofline("joint_fwd_kernel (+ weight / stream casts)", unit, f_ms, {})
         # DRAM bytes per launch from the ncu --set full capture of this workload (profiles/, cfg 3 only)
-        if args.workload == "rnnt_cfg3" and args.lengths == "full":
+        if args.workload == "rnnt_cfg3" and args.lengths == "full" and not zc:
             roof["traffic"] = NCU_DRAM_BYTES["rnnt_cfg3"]["bwd"]
             roof["forward"]["traffic"] = NCU_DRAM_BYTES["rnnt_cfg3"]["fwd"]
 

@@ -8,9 +8,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libemoasr_b200.so")
 
-OP_RNNT_JOINT_FWD, OP_RNNT_JOINT_BWD, OP_CTC, OP_RNNT_JOINT_HCACHE = 0, 1, 2, 3
+OP_RNNT_JOINT_FWD, OP_RNNT_JOINT_BWD, OP_CTC, OP_RNNT_JOINT_HCACHE, OP_RNNT_JOINT_HZCACHE = 0, 1, 2, 3, 4
 PREC_FP32, PREC_BF16 = 0, 1
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 _c = ctypes
 _P = _c.c_void_p

@@ -44,7 +44,8 @@ extern "C" size_t emo_workspace_bytes(int op, int precision, int B, int T, int U
             return precision == EMO_PREC_BF16 ? joint_bf16_workspace(op, B, T, U1, J, V)
                                               : joint_f32_workspace(op, B, T, U1, J, V);
         case EMO_OP_RNNT_JOINT_HCACHE:
-            if (U1 <= 0 || J <= 0) return 0;
+        case EMO_OP_RNNT_JOINT_HZCACHE:
+            if (U1 <= 0 || J <= 0 || (op == EMO_OP_RNNT_JOINT_HZCACHE && V <= 0)) return 0;
             return precision == EMO_PREC_BF16 ? joint_bf16_workspace(op, B, T, U1, J, V) : 0;
         default:
             return 0;  // CTC takes its scratch as explicit arguments

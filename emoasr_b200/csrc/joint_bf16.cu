@@ -49,7 +49,7 @@ struct __align__(16) FwdBarriers {
 // the blank / label logit.
 __device__ __forceinline__ void lse_group(const uint32_t (&r)[32], const float* __restrict__ bias,
                                           int v0, int lab, int blank, float& run_m, float& run_s,
-                                          float& zb, float& zl) {
+                                          float& zb, float& zl, __half* __restrict__ zrow) {
     float x[32];
     float m0 = kNegInf, m1 = kNegInf, m2 = kNegInf, m3 = kNegInf;
 #pragma unroll
@@ -63,6 +63,13 @@ __device__ __forceinline__ void lse_group(const uint32_t (&r)[32], const float* 
         m1 = fmaxf(m1, x[i + 1]);
         m2 = fmaxf(m2, x[i + 2]);
         m3 = fmaxf(m3, x[i + 3]);
+    }
+    if (zrow) {   // z cache: the logits of this row, fp16, for the backward (warp-uniform branch)
+        uint4* dst = reinterpret_cast<uint4*>(zrow + v0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            dst[i] = make_uint4(pack_f16x2(x[8 * i], x[8 * i + 1]), pack_f16x2(x[8 * i + 2], x[8 * i + 3]),
+                                pack_f16x2(x[8 * i + 4], x[8 * i + 5]), pack_f16x2(x[8 * i + 6], x[8 * i + 7]));
     }
     const float new_m = fmaxf(run_m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
     const float neg_m2 = -new_m * kLog2e;
@@ -129,7 +136,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                  const __half* __restrict__ dec, const float* __restrict__ b_out,
                  const int* __restrict__ labels, const int* __restrict__ tlen,
                  const int* __restrict__ ulen, int B, int T, int U1, int J, int V, int blank,
-                 float* __restrict__ lp2, float* __restrict__ lse_out) {
+                 float* __restrict__ lp2, float* __restrict__ lse_out,
+                 __half* __restrict__ zcache) {   // optional (rows of the h cache, V) fp16 logits
     constexpr bool kPair = kCtas == 2;
     constexpr int kBStages = Cfg<kCtas>::kBStages;
     constexpr int kBBytes = Cfg<kCtas>::kBRows * kBlockK * 2;
@@ -310,6 +318,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             if (valid && u < ti.U1b - 1)
                 lab = min(max(__ldg(labels + (size_t)ti.b * (U1 - 1) + u), 0), V - 1);
             float run_m = kNegInf, run_s = 0.f, zb = 0.f, zl = 0.f;
+            __half* zrow = zcache ? zcache + (size_t)((ti.b * tiles128_per_utt(T, U1) + ti.first_cell / kTileM) * kTileM + row) * V
+                                  : nullptr;
             for (int nc = 0; nc < NC; ++nc, ++cc) {
                 const uint32_t buf = cc & 1;
                 const int n = min(kChunkN, V - nc * kChunkN);
@@ -331,12 +341,12 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                     for (int g = g0; g < g1; g += 2) {
                         tmem_wait_ld();
                         if (g + 1 < g1) tmem_ld_32x32b_x32(taddr + (g + 1) * 32, rb);
-                        lse_group(ra, bias + g * 32, nc * kChunkN + g * 32, lab, blank, run_m, run_s, zb, zl);
+                        lse_group(ra, bias + g * 32, nc * kChunkN + g * 32, lab, blank, run_m, run_s, zb, zl, zrow);
                         if (g + 1 < g1) {
                             tmem_wait_ld();
                             if (g + 2 < g1) tmem_ld_32x32b_x32(taddr + (g + 2) * 32, ra);
                             lse_group(rb, bias + (g + 1) * 32, nc * kChunkN + (g + 1) * 32, lab, blank, run_m,
-                                      run_s, zb, zl);
+                                      run_s, zb, zl, zrow);
                         }
                     }
                 }
@@ -471,9 +481,13 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     static const bool use_single = getenv("EMO_FWD_SINGLE_CTA") != nullptr;  // A/B switch while tuning
     CUtensorMap tmap, tmap_h;
     const int store_h = hcache != nullptr;
+    __half* zcache = nullptr;
     if (store_h) {
         EMO_REQUIRE(hcache_bytes >= hcache_bytes_for(B, T, U1, J) && ((uintptr_t)hcache & 255) == 0,
                     EMO_WORKSPACE_TOO_SMALL, "joint_fwd(bf16): h cache too small or misaligned");
+        if (joint_zc_supported(J) &&
+            hcache_bytes >= zcache_offset_for(B, T, U1, J) + zcache_bytes_for(B, T, U1, V))
+            zcache = reinterpret_cast<__half*>((char*)hcache + zcache_offset_for(B, T, U1, J));
         rc = make_tmap_bf16_2d(&tmap_h, hcache, (uint64_t)J,
                                (uint64_t)B * tiles128_per_utt(T, U1) * kTileM, kBlockK, kTileM);
         if (rc) return rc;
@@ -499,7 +513,7 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
         cfg.numAttrs = 1;
         if (!store_h) tmap_h = tmap;
         EMO_CUDA(cudaLaunchKernelEx(&cfg, joint_fwd_kernel<2>, tmap, tmap_h, store_h, enc_h, dec_h, b_out,
-                                    labels, tlen, ulen, B, T, U1, J, V, blank, lp2, lse));
+                                    labels, tlen, ulen, B, T, U1, J, V, blank, lp2, lse, zcache));
         EMO_CHECK_LAUNCH("joint_fwd_kernel<pair>");
         return EMO_OK;
     }
@@ -513,7 +527,7 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     if (!store_h) tmap_h = tmap;
     joint_fwd_kernel<1><<<min(tiles, sm_count()), kFwdThreads, smem, st>>>(tmap, tmap_h, store_h, enc_h, dec_h,
                                                                         b_out, labels, tlen, ulen, B, T, U1, J, V,
-                                                                        blank, lp2, lse);
+                                                                        blank, lp2, lse, zcache);
     EMO_CHECK_LAUNCH("joint_fwd_kernel<single>");
     return EMO_OK;
 }

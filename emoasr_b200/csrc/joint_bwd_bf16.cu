@@ -1158,6 +1158,10 @@ size_t dw_smem_bytes(int J) {
 
 size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V) {
     if (op == EMO_OP_RNNT_JOINT_HCACHE) return align_up(hcache_bytes_for(B, T, U1, J), 256);
+    if (op == EMO_OP_RNNT_JOINT_HZCACHE) {
+        if (!joint_zc_supported(J) || J % 128 != 0 || V % 32 != 0) return 0;
+        return zcache_offset_for(B, T, U1, J) + align_up(zcache_bytes_for(B, T, U1, V), 256);
+    }
     size_t w = align_up((size_t)V * J * sizeof(__nv_bfloat16), 256);
     if (op == EMO_OP_RNNT_JOINT_BWD)
         return w + align_up((size_t)B * T * U1 * J * sizeof(__nv_bfloat16), 256);
@@ -1203,6 +1207,20 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     EMO_CUDA(cudaMemsetAsync(d_w_out, 0, nw * sizeof(float), st));
     EMO_CUDA(cudaMemsetAsync(d_b_out, 0, (size_t)V * sizeof(float), st));
     EMO_CUDA(cudaMemsetAsync(d_dec_proj, 0, (size_t)B * U1 * J * sizeof(float), st));
+
+    // ---- z-cache path: the forward left the logits behind the h cache
+    if (joint_zc_supported(J) &&
+        hcache_bytes >= zcache_offset_for(B, T, U1, J) + zcache_bytes_for(B, T, U1, V)) {
+        const void* zcache = (const char*)hcache + zcache_offset_for(B, T, U1, J);
+        rc = joint_dhz_launch(w_bf16, hcache, zcache, labels, tlen, ulen, lse, gamma2, grad_cost, B, T, U1, J, V,
+                              blank, dpre, st);
+        if (rc) return rc;
+        reduce_dpre_kernel<<<dim3(J / kRedCols, ceil_div(T, kRedTG), B), kRedWarps * 32, 0, st>>>(
+            dpre, tlen, ulen, T, U1, J, d_enc_proj, d_dec_proj);
+        EMO_CHECK_LAUNCH("reduce_dpre_kernel");
+        return joint_dwz_launch(hcache, zcache, labels, tlen, ulen, lse, gamma2, grad_cost, B, T, U1, J, V, blank,
+                                d_w_out, d_b_out, st);
+    }
 
     CUtensorMap tmap_wz, tmap_wd, tmap_h;
     rc = make_tmap_bf16_2d(&tmap_wz, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, 64);

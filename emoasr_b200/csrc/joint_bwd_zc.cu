@@ -1,0 +1,689 @@
+// EMO_PREC_BF16 backward of the fused joint, z-cache version (tcgen05 / TMEM / TMA).
+//
+// When the caller hands emo_rnnt_joint_fwd a cache large enough for the logits (EMO_OP_RNNT_JOINT_HZCACHE),
+// the forward kernel leaves z = h W^T + b of every valid lattice cell in HBM as fp16, tile-major like the
+// h cache.  The backward then needs NO z GEMM: it streams z once per kernel, turns it into
+//     dz[cell,v] = g_b * (gamma * exp(z - lse) - gamma_blank 1[v=blank] - gamma_label 1[v=label])
+// IN PLACE in shared memory (fp16 tile -> bf16 tile of the same shape and swizzle) and feeds the tensor
+// cores with it.  2 executed GEMM units instead of 6, paid for with
+// 2 bytes per (cell, vocab entry) of HBM.
+//
+//   dhz kernel  cell-stationary CTA pair (cta_group::2, 256 cells per pair tile); per 64-wide vocab block:
+//                  z tile [128 cells x 64 v] (TMA) -> dz (8 transform warps) -> dh[256 x J] += dz W[kb]
+//               with the full J-wide accumulator in TMEM (512 columns); dpre = dh (1 - h^2) -> bf16.
+//               The tile, read with v contiguous, is the K-major A operand.
+//   dWz kernel  vocab-stationary CTA pair: role = 256 vocab rows (128 per CTA, TMEM lane == vocab row), all
+//               of J in the 512 TMEM columns, accumulated over ALL cells of the pair's share:
+//                  z tile [64 cells x 128 v] (TMA) -> dz -> dW[256 v x J] += dz^T h[64 cells x J]
+//               The same bytes, read with v contiguous, are now the MN-major A operand (M = vocab, K = cells);
+//               h blocks from the h cache are the MN-major B operand.  d_b_out = column sums of dz, kept in
+//               registers of the transform threads (each owns an 8-wide vocab strip for the whole kernel).
+// Both: warp 0 TMA producer of the second operand (w_out / h), warp 1 MMA issuer, warp 2 TMEM allocator + z TMA
+// producer, warp 3 per-cell scalar stager (dWz), warps 4-11 transform, warps 12-19 accumulator drain / flush.
+#include "joint_tc.cuh"
+
+namespace emo {
+namespace {
+
+constexpr int kZcThreads = 640;
+constexpr int kDhzZStages = 6;
+constexpr int kDwzZStages = 5;
+constexpr int kOpStages = 4;
+constexpr int kZBytes = 16384;                 // one z / dz stage: 128 x 64 (dhz) or 2 x [64 x 64] (dWz) 2-byte elements
+constexpr int kBoxBytes = 8192;                // [64 rows x 128 B]
+constexpr int kXfWarps = 8;
+constexpr int kDrainWarps = 8;
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO=1024, v1, SW128
+
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo) { return ((uint64_t)kDescHiSw128 << 32) | lo; }
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+
+// per-cell scalars of dz
+struct CellSc {
+    float nl2;   // -lse * log2e  (-1e30 for padding rows: exp2 -> 0)
+    float cs;    // g * (gamma_blank + gamma_label)
+    float cb;    // g * gamma_blank
+    float cl;    // g * gamma_label
+    int lab;     // label of the cell's emit transition, -1 if none
+};
+
+__device__ __forceinline__ void load_cell_sc(CellSc& s, const TileInfo& ti, int m, int T, int U1, int V,
+                                             const int* __restrict__ labels, const float* __restrict__ lse,
+                                             const float* __restrict__ gamma2,
+                                             const float* __restrict__ grad_cost) {
+    s.nl2 = -1e30f; s.cs = 0.f; s.cb = 0.f; s.cl = 0.f; s.lab = -1;
+    if (m < ti.n_cells) {
+        const int t = m / ti.U1b, u = m - t * ti.U1b;
+        const size_t cell = ((size_t)ti.b * T + t) * U1 + u;
+        const float g = __ldg(grad_cost + ti.b);
+        const float2 gm = __ldg(reinterpret_cast<const float2*>(gamma2) + cell);
+        s.nl2 = -__ldg(lse + cell) * kLog2e;
+        s.cs = g * (gm.x + gm.y);
+        s.cb = g * gm.x;
+        s.cl = g * gm.y;
+        if (u < ti.U1b - 1) s.lab = min(max(__ldg(labels + (size_t)ti.b * (U1 - 1) + u), 0), V - 1);
+    }
+}
+
+// 8 consecutive vocab entries of one cell: fp16 logits -> bf16 dz.  vb = first vocab index of the strip,
+// db = blank - vb.
+template <bool kColSum>
+__device__ __forceinline__ uint4 dz8(const uint4 zr, const CellSc& s, int vb, int db, float (&colsum)[8]) {
+    const uint32_t w[4] = {zr.x, zr.y, zr.z, zr.w};
+    float d[8];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_f16x2(w[e]);
+        d[2 * e] = s.cs * ex2_approx(fmaf(f.x, kLog2e, s.nl2));
+        d[2 * e + 1] = s.cs * ex2_approx(fmaf(f.y, kLog2e, s.nl2));
+    }
+    const int dl = s.lab - vb;
+    if ((unsigned)dl < 8u) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] -= (e == dl) ? s.cl : 0.f;
+    }
+    if ((unsigned)db < 8u) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) d[e] -= (e == db) ? s.cb : 0.f;
+    }
+    if (kColSum) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) colsum[e] += d[e];
+    }
+    return make_uint4(pack_bf16x2(d[0], d[1]), pack_bf16x2(d[2], d[3]), pack_bf16x2(d[4], d[5]),
+                      pack_bf16x2(d[6], d[7]));
+}
+
+template <int kS>
+struct __align__(16) ZcBarriers {
+    uint64_t z_full[kS];      // local: TMA bytes of the z tile (+ the scalar stager in dWz)
+    uint64_t dz_full[kS];     // leader: transform warps of both CTAs
+    uint64_t dz_empty[kS];    // both CTAs (multicast commit): the MMAs have read the stage
+    uint64_t op_full[kOpStages], op_empty[kOpStages];
+    uint64_t acc_full, acc_empty;
+    uint32_t tmem_base;
+    uint32_t pad[3];
+};
+
+// =================================================================================================
+__global__ void __launch_bounds__(kZcThreads, 1)
+joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,J), box [64 j x 64 v]
+                 const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (rows,V), box [64 v x 128 cells]
+                 const __nv_bfloat16* __restrict__ hcache, const int* __restrict__ labels,
+                 const int* __restrict__ tlen, const int* __restrict__ ulen, const float* __restrict__ lse,
+                 const float* __restrict__ gamma2, const float* __restrict__ grad_cost, int B, int T, int U1,
+                 int J, int V, int blank, __nv_bfloat16* __restrict__ dpre_out) {   // (B,T,U1,J)
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int kS = kDhzZStages;
+    using Bars = ZcBarriers<kS>;
+    const int NKB = (V + kBlockK - 1) / kBlockK;
+    const int NMMA = (J + 255) / 256;
+    const uint32_t op_bytes = (uint32_t)J * 64;      // this CTA's half of a [64 v x J] w_out block
+    uint8_t* sZ = smem;
+    uint8_t* sW = sZ + (size_t)kS * kZBytes;
+    Bars* bars = reinterpret_cast<Bars*>(sW + (size_t)kOpStages * op_bytes);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int tiles_per_utt = (T * U1 + 2 * kTileM - 1) / (2 * kTileM);
+    const int total_tiles = B * tiles_per_utt;
+    const int tile0 = blockIdx.x / 2, tile_stride = gridDim.x / 2;
+    const int tpu = tiles128_per_utt(T, U1);
+
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kS; ++i) {
+            mbar_init(smem_u32(&bars->z_full[i]), 1);
+            mbar_init(smem_u32(&bars->dz_full[i]), 2 * kXfWarps);
+            mbar_init(smem_u32(&bars->dz_empty[i]), 1);
+        }
+        for (int i = 0; i < kOpStages; ++i) {
+            mbar_init(smem_u32(&bars->op_full[i]), 2);
+            mbar_init(smem_u32(&bars->op_empty[i]), 1);
+        }
+        mbar_init(smem_u32(&bars->acc_full), 1);
+        mbar_init(smem_u32(&bars->acc_empty), 2 * kDrainWarps);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_w);
+        tma_prefetch_desc(&tmap_z);
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(smem_u32(&bars->tmem_base), 512);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    if (warp == 0) {
+        // ===================== TMA: w_out blocks [64 v x J/2] (this CTA's half of every MMA's N range) ==========
+        if (lane == 0) {
+            uint32_t slot = 0, ph = 0;
+            TileInfo ti;
+            for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+                if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
+                for (int kb = 0; kb < NKB; ++kb) {
+                    mbar_wait(smem_u32(&bars->op_empty[slot]), ph ^ 1);
+                    const uint32_t full = smem_u32(&bars->op_full[slot]);
+                    mbar_arrive_expect_tx_cluster(mapa_shared(full, 0), op_bytes);
+                    uint32_t dst = smem_u32(sW + (size_t)slot * op_bytes);
+                    for (int n = 0; n < NMMA; ++n) {
+                        const int half = min(256, J - n * 256) >> 1;
+                        for (int b = 0; b < half; b += kBlockK) {
+                            tma_load_2d_pair(dst, &tmap_w, n * 256 + (int)rank * half + b, kb * kBlockK, full);
+                            dst += kBoxBytes;
+                        }
+                    }
+                    if (++slot == kOpStages) { slot = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== TMA: this CTA's z tiles =====================
+        if (lane == 0) {
+            uint32_t zs = 0, zph = 0;
+            TileInfo ti;
+            for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+                if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
+                const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM;
+                for (int kb = 0; kb < NKB; ++kb) {
+                    mbar_wait(smem_u32(&bars->dz_empty[zs]), zph ^ 1);
+                    const uint32_t full = smem_u32(&bars->z_full[zs]);
+                    mbar_arrive_expect_tx(full, kZBytes);
+                    tma_load_2d(smem_u32(sZ + (size_t)zs * kZBytes), &tmap_z, kb * kBlockK, row0, full);
+                    if (++zs == kS) { zs = 0; zph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA) =====================
+        if (leader) {
+            uint32_t zs = 0, zph = 0, slot = 0, ph = 0, tl = 0;
+            const uint32_t z_lo0 = desc_lo(smem_u32(sZ), 16);
+            const uint32_t w_lo0 = desc_lo(smem_u32(sW), kBoxBytes);
+            TileInfo ti;
+            for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+                if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
+                mbar_wait(smem_u32(&bars->acc_empty), (tl & 1) ^ 1);
+                for (int kb = 0; kb < NKB; ++kb) {
+                    mbar_wait(smem_u32(&bars->dz_full[zs]), zph);
+                    mbar_wait(smem_u32(&bars->op_full[slot]), ph);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        const uint32_t a_lo = z_lo0 + zs * (kZBytes >> 4);
+                        const uint32_t b_lo = w_lo0 + slot * (op_bytes >> 4);
+#pragma unroll
+                        for (int k16 = 0; k16 < kBlockK / 16; ++k16) {
+                            for (int n = 0; n < NMMA; ++n) {
+                                const int Nn = min(256, J - n * 256);
+                                umma_bf16_pair(tmem_base + n * 256, mk_desc(a_lo + 2 * k16),
+                                               mk_desc(b_lo + n * (2 * kBoxBytes >> 4) + k16 * (2048 >> 4)),
+                                               umma_idesc_bf16(2 * kTileM, Nn, 0, 1), (kb | k16) != 0);
+                            }
+                        }
+                        umma_commit_pair(smem_u32(&bars->dz_empty[zs]));
+                        umma_commit_pair(smem_u32(&bars->op_empty[slot]));
+                        if (kb == NKB - 1) umma_commit_pair(smem_u32(&bars->acc_full));
+                    }
+                    __syncwarp();
+                    if (++zs == kS) { zs = 0; zph ^= 1; }
+                    if (++slot == kOpStages) { slot = 0; ph ^= 1; }
+                }
+                ++tl;
+            }
+        }
+    } else if (warp >= 4 && warp < 4 + kXfWarps) {
+        // ===================== transform: z (fp16) -> dz (bf16) in place =====================
+        // thread = (16-byte chunk c of the 128-byte row, 4 consecutive rows)
+        const int tt = threadIdx.x - 128;
+        const int c = tt & 7, r0 = (tt >> 3) * 4;
+        const uint32_t dz_full0 = mapa_shared(smem_u32(&bars->dz_full[0]), 0);
+        uint32_t off[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = r0 + i;
+            off[i] = (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+        }
+        float dummy[8];
+        uint32_t zs = 0, zph = 0;
+        // scalars of the NEXT tile are fetched while the current one is transformed
+        int ntile = tile0 - tile_stride;
+        CellSc nxt[4];
+        auto fetch_next = [&]() {
+            TileInfo ni;
+            do {
+                ntile += tile_stride;
+                if (ntile >= total_tiles) return;
+            } while (!tile_info<2>(ntile, tiles_per_utt, rank, tlen, ulen, T, U1, ni));
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                load_cell_sc(nxt[i], ni, ni.first_cell + r0 + i, T, U1, V, labels, lse, gamma2, grad_cost);
+        };
+        fetch_next();
+        TileInfo ti;
+        for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+            if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
+            CellSc cur[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+            fetch_next();
+            for (int kb = 0; kb < NKB; ++kb) {
+                uint8_t* st = sZ + (size_t)zs * kZBytes;
+                mbar_wait(smem_u32(&bars->z_full[zs]), zph);
+                uint4 zr[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) zr[i] = *reinterpret_cast<const uint4*>(st + off[i]);
+                const int vb = kb * kBlockK + c * 8;
+#pragma unroll
+                for (int i = 0; i < 4; ++i)
+                    *reinterpret_cast<uint4*>(st + off[i]) = dz8<false>(zr[i], cur[i], vb, blank - vb, dummy);
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(dz_full0 + zs * 8);
+                if (++zs == kS) { zs = 0; zph ^= 1; }
+            }
+        }
+    } else if (warp >= 4 + kXfWarps) {
+        // ===================== drain: dh -> dpre = dh (1 - h^2) -> bf16 (B,T,U1,J) =====================
+        const int dw = warp - (4 + kXfWarps);
+        const int q = warp & 3, hf = dw >> 2;
+        const int row = q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t acc_empty_addr = mapa_shared(smem_u32(&bars->acc_empty), 0);
+        const int G = J >> 6;              // 32-column groups per column half
+        const int col_base = hf * (J >> 1);
+        uint32_t tl = 0;
+        TileInfo ti;
+        for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
+            if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
+            const int m = ti.first_cell + row;
+            const bool valid = m < ti.n_cells;
+            const int t = valid ? m / ti.U1b : 0;
+            const int u = valid ? m - t * ti.U1b : 0;
+            const size_t cell = ((size_t)ti.b * T + t) * U1 + u;
+            const size_t hrow = (size_t)((ti.b * tpu + ti.first_cell / kTileM) * kTileM + row);
+            const uint4* hp = reinterpret_cast<const uint4*>(hcache + hrow * J + col_base);
+            uint4* dp = reinterpret_cast<uint4*>(dpre_out + cell * J + col_base);
+            uint4 hv[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) hv[j] = __ldg(hp + j);
+            mbar_wait(smem_u32(&bars->acc_full), tl & 1);
+            tc_fence_after();
+            for (int g = 0; g < G; ++g) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + g * 32, r);
+                uint4 hn[4];
+                if (g + 1 < G) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) hn[j] = __ldg(hp + (g + 1) * 4 + j);
+                }
+                tmem_wait_ld();
+                uint32_t pk[16];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    const uint32_t hw[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const float h0 = __uint_as_float(hw[e] << 16);
+                        const float h1 = __uint_as_float(hw[e] & 0xffff0000u);
+                        const float d0 = __uint_as_float(r[j * 8 + e * 2]) * fmaf(-h0, h0, 1.f);
+                        const float d1 = __uint_as_float(r[j * 8 + e * 2 + 1]) * fmaf(-h1, h1, 1.f);
+                        pk[j * 4 + e] = pack_bf16x2(d0, d1);
+                    }
+                }
+                if (valid) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        dp[g * 4 + j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
+                }
+                if (g + 1 < G) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) hv[j] = hn[j];
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty_addr);
+            ++tl;
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+// =================================================================================================
+__global__ void __launch_bounds__(kZcThreads, 1)
+joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (rows,V), box [64 v x 64 cells]
+                 const __grid_constant__ CUtensorMap tmap_h,   // h cache bf16 (rows,J), box [64 j x 64 cells]
+                 const int* __restrict__ labels, const int* __restrict__ tlen, const int* __restrict__ ulen,
+                 const float* __restrict__ lse, const float* __restrict__ gamma2,
+                 const float* __restrict__ grad_cost, int B, int T, int U1, int J, int V, int blank,
+                 int num_splits,
+                 float* __restrict__ d_w_out,    // (V,J), pre-zeroed
+                 float* __restrict__ d_b_out) {  // (V), pre-zeroed
+    extern __shared__ __align__(1024) uint8_t smem[];
+    constexpr int kS = kDwzZStages;
+    using Bars = ZcBarriers<kS>;
+    const int NMMA = (J + 255) / 256;
+    const uint32_t op_bytes = (uint32_t)J * 64;      // this CTA's half of a [64 cells x J] h block
+    uint8_t* sZ = smem;
+    uint8_t* sH = sZ + (size_t)kS * kZBytes;
+    Bars* bars = reinterpret_cast<Bars*>(sH + (size_t)kOpStages * op_bytes);
+    float* s_sc = reinterpret_cast<float*>(bars + 1);   // [kS][5][64] per-cell scalars of each stage
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int tiles_per_utt = (T * U1 + kTileM - 1) / kTileM;
+    const int total_tiles = B * tiles_per_utt;
+    const int tpu = tiles128_per_utt(T, U1);
+    const int pair = blockIdx.x >> 1;
+    const int roles = (V + 255) / 256;
+    const int role = pair % roles, split = pair / roles;
+    const int v0_cta = role * 256 + (int)rank * kTileM;
+
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kS; ++i) {
+            mbar_init(smem_u32(&bars->z_full[i]), 2);               // TMA thread + scalar stager
+            mbar_init(smem_u32(&bars->dz_full[i]), 2 * kXfWarps);
+            mbar_init(smem_u32(&bars->dz_empty[i]), 1);
+        }
+        for (int i = 0; i < kOpStages; ++i) {
+            mbar_init(smem_u32(&bars->op_full[i]), 2);
+            mbar_init(smem_u32(&bars->op_empty[i]), 1);
+        }
+        mbar_init(smem_u32(&bars->acc_full), 1);
+        mbar_init(smem_u32(&bars->acc_empty), 1);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&tmap_z);
+        tma_prefetch_desc(&tmap_h);
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(smem_u32(&bars->tmem_base), 512);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+
+    // every role walks the same sequence of 64-cell K blocks: tiles split, split + num_splits, ...
+    auto for_each_kblock = [&](auto&& body) {
+        TileInfo ti;
+        for (int tile = split; tile < total_tiles; tile += num_splits) {
+            if (!tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) continue;
+            const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM;
+            const int nkh = (ti.n_cells - ti.first_cell > 64) ? 2 : 1;
+            for (int kh = 0; kh < nkh; ++kh) body(ti, row0 + kh * 64, ti.first_cell + kh * 64);
+        }
+    };
+
+    if (warp == 0) {
+        // ===================== TMA: h blocks [64 cells x J/2] =====================
+        if (lane == 0) {
+            uint32_t slot = 0, ph = 0;
+            for_each_kblock([&](const TileInfo& ti, int rowK, int m0) {
+                (void)ti; (void)rowK; (void)m0;
+                mbar_wait(smem_u32(&bars->op_empty[slot]), ph ^ 1);
+                const uint32_t full = smem_u32(&bars->op_full[slot]);
+                mbar_arrive_expect_tx_cluster(mapa_shared(full, 0), op_bytes);
+                uint32_t dst = smem_u32(sH + (size_t)slot * op_bytes);
+                for (int n = 0; n < NMMA; ++n) {
+                    const int half = min(256, J - n * 256) >> 1;
+                    for (int b = 0; b < half; b += kBlockK) {
+                        tma_load_2d_pair(dst, &tmap_h, n * 256 + (int)rank * half + b, rowK, full);
+                        dst += kBoxBytes;
+                    }
+                }
+                if (++slot == kOpStages) { slot = 0; ph ^= 1; }
+            });
+        }
+    } else if (warp == 2) {
+        // ===================== TMA: z blocks [64 cells x 128 v] of this CTA's vocab rows =====================
+        if (lane == 0) {
+            uint32_t zs = 0, zph = 0;
+            for_each_kblock([&](const TileInfo& ti, int rowK, int m0) {
+                (void)ti; (void)rowK; (void)m0;
+                mbar_wait(smem_u32(&bars->dz_empty[zs]), zph ^ 1);
+                const uint32_t full = smem_u32(&bars->z_full[zs]);
+                mbar_arrive_expect_tx(full, kZBytes);
+                const uint32_t dst = smem_u32(sZ + (size_t)zs * kZBytes);
+                tma_load_2d(dst, &tmap_z, v0_cta, rowK, full);
+                tma_load_2d(dst + kBoxBytes, &tmap_z, v0_cta + kBlockK, rowK, full);
+                if (++zs == kS) { zs = 0; zph ^= 1; }
+            });
+        }
+    } else if (warp == 3) {
+        // ===================== per-cell scalars of each stage =====================
+        uint32_t zs = 0, zph = 0;
+        for_each_kblock([&](const TileInfo& ti, int rowK, int m0) {
+                (void)ti; (void)rowK; (void)m0;
+            mbar_wait(smem_u32(&bars->dz_empty[zs]), zph ^ 1);
+            float* sc = s_sc + zs * 5 * 64;
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int ci = lane + 32 * i;
+                CellSc s;
+                load_cell_sc(s, ti, m0 + ci, T, U1, V, labels, lse, gamma2, grad_cost);
+                sc[ci] = s.nl2; sc[64 + ci] = s.cs; sc[128 + ci] = s.cb; sc[192 + ci] = s.cl;
+                reinterpret_cast<int*>(sc)[256 + ci] = s.lab;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->z_full[zs]));
+            if (++zs == kS) { zs = 0; zph ^= 1; }
+        });
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA) =====================
+        if (leader) {
+            uint32_t zs = 0, zph = 0, slot = 0, ph = 0, first = 1;
+            const uint32_t z_lo0 = desc_lo(smem_u32(sZ), kBoxBytes);
+            const uint32_t h_lo0 = desc_lo(smem_u32(sH), kBoxBytes);
+            for_each_kblock([&](const TileInfo& ti, int rowK, int m0) {
+                (void)ti; (void)rowK; (void)m0;
+                mbar_wait(smem_u32(&bars->dz_full[zs]), zph);
+                mbar_wait(smem_u32(&bars->op_full[slot]), ph);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    const uint32_t a_lo = z_lo0 + zs * (kZBytes >> 4);
+                    const uint32_t b_lo = h_lo0 + slot * (op_bytes >> 4);
+#pragma unroll
+                    for (int k16 = 0; k16 < 4; ++k16) {
+                        for (int n = 0; n < NMMA; ++n) {
+                            const int Nn = min(256, J - n * 256);
+                            umma_bf16_pair(tmem_base + n * 256, mk_desc(a_lo + k16 * (2048 >> 4)),
+                                           mk_desc(b_lo + n * (2 * kBoxBytes >> 4) + k16 * (2048 >> 4)),
+                                           umma_idesc_bf16(2 * kTileM, Nn, 1, 1), (first && k16 == 0) ? 0u : 1u);
+                        }
+                    }
+                    umma_commit_pair(smem_u32(&bars->dz_empty[zs]));
+                    umma_commit_pair(smem_u32(&bars->op_empty[slot]));
+                }
+                __syncwarp();
+                first = 0;
+                if (++zs == kS) { zs = 0; zph ^= 1; }
+                if (++slot == kOpStages) { slot = 0; ph ^= 1; }
+            });
+            if (elect_one_sync()) umma_commit_pair(smem_u32(&bars->acc_full));
+            __syncwarp();
+        }
+    } else if (warp >= 4 && warp < 4 + kXfWarps) {
+        // ===================== transform: z (fp16) -> dz (bf16) in place; column sums for d_b_out ==========
+        // thread = (64-wide vocab box, 16-byte chunk c = 8 vocab entries, 4 consecutive cells)
+        const int tt = threadIdx.x - 128;
+        const int box = tt >> 7, t7 = tt & 127;
+        const int c = t7 & 7, r0 = (t7 >> 3) * 4;
+        const int vb = v0_cta + box * kBlockK + c * 8;
+        const int db = blank - vb;
+        const uint32_t dz_full0 = mapa_shared(smem_u32(&bars->dz_full[0]), 0);
+        uint32_t off[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = r0 + i;
+            off[i] = box * kBoxBytes + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+        }
+        float colsum[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) colsum[e] = 0.f;
+        uint32_t zs = 0, zph = 0;
+        for_each_kblock([&](const TileInfo& ti, int rowK, int m0) {
+                (void)ti; (void)rowK; (void)m0;
+            uint8_t* st = sZ + (size_t)zs * kZBytes;
+            const float* sc = s_sc + zs * 5 * 64;
+            mbar_wait(smem_u32(&bars->z_full[zs]), zph);
+            uint4 zr[4];
+            CellSc cs[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                zr[i] = *reinterpret_cast<const uint4*>(st + off[i]);
+                cs[i].nl2 = sc[r0 + i]; cs[i].cs = sc[64 + r0 + i]; cs[i].cb = sc[128 + r0 + i];
+                cs[i].cl = sc[192 + r0 + i];
+                cs[i].lab = reinterpret_cast<const int*>(sc)[256 + r0 + i];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                *reinterpret_cast<uint4*>(st + off[i]) = dz8<true>(zr[i], cs[i], vb, db, colsum);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(dz_full0 + zs * 8);
+            if (++zs == kS) { zs = 0; zph ^= 1; }
+        });
+        // ---- d_b_out: lanes with equal (lane & 7) hold the same vocab strip
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            colsum[e] += __shfl_xor_sync(0xffffffffu, colsum[e], 8);
+            colsum[e] += __shfl_xor_sync(0xffffffffu, colsum[e], 16);
+        }
+        if (lane < 8) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (vb + e < V && colsum[e] != 0.f) atomicAdd(d_b_out + vb + e, colsum[e]);
+        }
+    } else if (warp >= 4 + kXfWarps) {
+        // ===================== flush dW: TMEM lane = vocab row, columns = hidden units =====================
+        bool any = false;
+        for_each_kblock([&](const TileInfo&, int, int) { any = true; });
+        const int dw = warp - (4 + kXfWarps);
+        const int q = warp & 3, hf = dw >> 2;
+        const int v = v0_cta + q * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const int G = J >> 6;
+        const int col_base = hf * (J >> 1);
+        mbar_wait(smem_u32(&bars->acc_full), 0);
+        tc_fence_after();
+        if (any) {
+            for (int g = 0; g < G; ++g) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + g * 32, r);
+                tmem_wait_ld();
+                if (v < V) {
+                    float* dst = d_w_out + (size_t)v * J + col_base + g * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        red_add_v4(dst + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                   __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+size_t dhz_smem_bytes(int J) {
+    return (size_t)kDhzZStages * kZBytes + (size_t)kOpStages * J * 64 + sizeof(ZcBarriers<kDhzZStages>);
+}
+size_t dwz_smem_bytes(int J) {
+    return (size_t)kDwzZStages * kZBytes + (size_t)kOpStages * J * 64 + sizeof(ZcBarriers<kDwzZStages>) +
+           (size_t)kDwzZStages * 5 * 64 * sizeof(float);
+}
+
+int launch_pair_kernel(const void* fn, int ctas, size_t smem, cudaStream_t st, void** args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(kZcThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    EMO_CUDA(cudaLaunchKernelExC(&cfg, fn, args));
+    return EMO_OK;
+}
+
+}  // namespace
+
+bool joint_zc_supported(int J) {
+    return dhz_smem_bytes(J) <= (size_t)kSmemLimit && dwz_smem_bytes(J) <= (size_t)kSmemLimit;
+}
+
+int joint_dhz_launch(const void* w_bf16, const void* hcache, const void* zcache, const int* labels, const int* tlen,
+                     const int* ulen, const float* lse, const float* gamma2, const float* grad_cost, int B, int T,
+                     int U1, int J, int V, int blank, void* dpre, cudaStream_t st) {
+    CUtensorMap tmap_w, tmap_z;
+    const uint64_t rows = (uint64_t)B * tiles128_per_utt(T, U1) * kTileM;
+    int rc = make_tmap_bf16_2d(&tmap_w, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, 64);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tmap_z, zcache, (uint64_t)V, rows, kBlockK, kTileM);
+    if (rc) return rc;
+    const size_t smem = dhz_smem_bytes(J);
+    EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_bwd(bf16): shared memory (dhz)");
+    EMO_CUDA(cudaFuncSetAttribute(joint_dhz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int ptiles = B * ceil_div((size_t)T * U1, 2 * kTileM);
+    const int pairs = max(1, min(ptiles, sm_count() / 2));
+    const __nv_bfloat16* hc = reinterpret_cast<const __nv_bfloat16*>(hcache);
+    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(dpre);
+    void* args[] = {&tmap_w, &tmap_z, &hc, &labels, &tlen, &ulen, &lse, &gamma2, &grad_cost,
+                    &B, &T, &U1, &J, &V, &blank, &dp};
+    rc = launch_pair_kernel((const void*)joint_dhz_kernel, 2 * pairs, smem, st, args);
+    if (rc) return rc;
+    EMO_CHECK_LAUNCH("joint_dhz_kernel");
+    return EMO_OK;
+}
+
+int joint_dwz_launch(const void* hcache, const void* zcache, const int* labels, const int* tlen, const int* ulen,
+                     const float* lse, const float* gamma2, const float* grad_cost, int B, int T, int U1, int J,
+                     int V, int blank, float* d_w_out, float* d_b_out, cudaStream_t st) {
+    CUtensorMap tmap_z, tmap_h;
+    const uint64_t rows = (uint64_t)B * tiles128_per_utt(T, U1) * kTileM;
+    int rc = make_tmap_bf16_2d(&tmap_z, zcache, (uint64_t)V, rows, kBlockK, 64);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tmap_h, hcache, (uint64_t)J, rows, kBlockK, 64);
+    if (rc) return rc;
+    const size_t smem = dwz_smem_bytes(J);
+    EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_bwd(bf16): shared memory (dWz)");
+    EMO_CUDA(cudaFuncSetAttribute(joint_dwz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int tiles = B * ceil_div((size_t)T * U1, kTileM);
+    const int roles = ceil_div(V, 256);
+    int splits = max(1, min((sm_count() / 2) / roles, tiles));
+    void* args[] = {&tmap_z, &tmap_h, &labels, &tlen, &ulen, &lse, &gamma2, &grad_cost,
+                    &B, &T, &U1, &J, &V, &blank, &splits, &d_w_out, &d_b_out};
+    rc = launch_pair_kernel((const void*)joint_dwz_kernel, 2 * roles * splits, smem, st, args);
+    if (rc) return rc;
+    EMO_CHECK_LAUNCH("joint_dwz_kernel");
+    return EMO_OK;
+}
+
+}  // namespace emo

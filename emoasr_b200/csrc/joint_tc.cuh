@@ -35,6 +35,15 @@ inline size_t hcache_bytes_for(int B, int T, int U1, int J) {
 // kCtas = 1: one CTA per 128-cell tile.  kCtas = 2: a CTA pair (cluster of 2, cta_group::2) per
 // 256-cell tile, 128 cells per CTA; `rank` selects this CTA's half.  Both CTAs of a pair get the
 // same answer.
+// z cache (optional, behind the h cache in the same buffer): fp16 logits z = h W^T + b of the same rows,
+// layout [B * tiles128_per_utt * 128, V].
+inline size_t zcache_offset_for(int B, int T, int U1, int J) {
+    return (hcache_bytes_for(B, T, U1, J) + 255) / 256 * 256;
+}
+inline size_t zcache_bytes_for(int B, int T, int U1, int V) {
+    return (size_t)B * tiles128_per_utt(T, U1) * kTileM * V * sizeof(__half);
+}
+
 template <int kCtas>
 __device__ __forceinline__ bool tile_info(int tile, int tiles_per_utt, uint32_t rank, const int* tlen,
                                           const int* ulen, int T, int U1, TileInfo& ti) {

@@ -5,6 +5,7 @@ rnnt_joint_loss  joint + log_softmax + transducer loss fused (rnn_transducer.py:
 ctc_loss         log_softmax + nn.CTCLoss(reduction="none") fused (asr/modeling/decoders/ctc.py:109-113)
 """
 import ctypes
+import os
 
 import torch
 
@@ -139,6 +140,23 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=
 
 
 # ----------------------------------------------------------------------------------------------
+def _joint_cache_bytes(precision, B, T, U1, J, V, dev):
+    """Size of the cache the fused forward leaves for its backward.  Preferred: h (bf16) + logits (fp16),
+    which lets the backward stream z instead of recomputing it (2 GEMMs instead of 6).  Falls back to the
+    h-only cache (recompute path) when the logit cache would not fit comfortably in free HBM, or when
+    EMO_NO_ZCACHE is set (A/B switch)."""
+    hbytes = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HCACHE, precision, B, T, U1, J, V)
+    if hbytes == 0 or os.environ.get("EMO_NO_ZCACHE"):
+        return hbytes
+    hz = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HZCACHE, precision, B, T, U1, J, V)
+    if hz == 0:
+        return hbytes
+    free, _total = torch.cuda.mem_get_info(dev)
+    # the caching allocator may hold freed blocks that can serve the request
+    reusable = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+    return hz if hz <= 0.6 * (free + reusable) else hbytes
+
+
 class _RNNTJoint(torch.autograd.Function):
     @staticmethod
     def forward(ctx, enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, blank, precision):
@@ -166,7 +184,7 @@ class _RNNTJoint(torch.autograd.Function):
             lp2 = torch.empty(B, T, U1, 2, device=dev)
             lse = torch.empty(B, T, U1, device=dev)
             # bf16 mode: tanh output of every valid cell, written by the forward kernel for the backward
-            hbytes = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HCACHE, precision, B, T, U1, J, V)
+            hbytes = _joint_cache_bytes(precision, B, T, U1, J, V, dev)
             need_h = hbytes > 0 and any(ctx.needs_input_grad[:4])
             hcache = torch.empty(hbytes, dtype=torch.uint8, device=dev) if need_h else None
             _lib.check(lib.emo_rnnt_joint_fwd(_p(enc), _p(dec), _p(w), _p(bo), _p(labels), _p(tlen), _p(ulen),

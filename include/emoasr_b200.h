@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define EMO_ABI_VERSION 2
+#define EMO_ABI_VERSION 3
 
 enum emo_status {
     EMO_OK = 0,
@@ -54,7 +54,8 @@ enum emo_op {
     EMO_OP_RNNT_JOINT_FWD = 0,
     EMO_OP_RNNT_JOINT_BWD = 1,
     EMO_OP_CTC = 2,
-    EMO_OP_RNNT_JOINT_HCACHE = 3 /* emo_workspace_bytes only: size of the h cache shared by fwd and bwd */
+    EMO_OP_RNNT_JOINT_HCACHE = 3, /* emo_workspace_bytes only: size of the h cache shared by fwd and bwd */
+    EMO_OP_RNNT_JOINT_HZCACHE = 4 /* emo_workspace_bytes only: h cache + fp16 logit cache (see emo_rnnt_joint_fwd) */
 };
 
 int emo_abi_version(void);
@@ -110,6 +111,11 @@ int emo_rnnt_dense_bwd(const float* gamma2_ws, const int* labels, const int* tle
  * aligned): receives h in bf16 for every valid cell, tile-major; the caller keeps it until
  * emo_rnnt_joint_bwd.  May be NULL for a forward-only call (inference / validation); ignored
  * (may be NULL, 0) in EMO_PREC_FP32.
+ * If hcache_bytes >= emo_workspace_bytes(EMO_OP_RNNT_JOINT_HZCACHE, ...) (non-zero for shapes that support
+ * it) the forward also leaves the logits z of every valid cell behind the h cache as fp16
+ * (2 bytes per cell and vocabulary entry) and emo_rnnt_joint_bwd, given the same buffer and size,
+ * streams them instead of recomputing z = h w_out^T on the tensor cores (2 GEMMs instead of 6).
+ * With the smaller EMO_OP_RNNT_JOINT_HCACHE size both calls use the recompute path.
  */
 int emo_rnnt_joint_fwd(const float* enc_proj, const float* dec_proj,
                        const float* w_out, const float* b_out,

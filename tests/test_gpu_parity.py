@@ -267,7 +267,7 @@ BF16_LOSS_RTOL = 2e-3
 BF16_GRAD_RTOL = 2e-2
 
 
-def _joint_fwd_raw(enc, dec_, w_out, b_out, ys, tl, ul, precision):
+def _joint_fwd_raw(enc, dec_, w_out, b_out, ys, tl, ul, precision, cache_op=None, return_cache=False):
     """Calls emo_rnnt_joint_fwd directly; returns lp2 (B,T,U1,2) and lse (B,T,U1) as numpy."""
     import ctypes
     from emoasr_b200 import _lib
@@ -282,13 +282,15 @@ def _joint_fwd_raw(enc, dec_, w_out, b_out, ys, tl, ul, precision):
     lp2 = torch.zeros(B, T, U1, 2, device=dev())
     lse = torch.zeros(B, T, U1, device=dev())
     p = lambda t: ctypes.c_void_p(t.data_ptr())
-    hb = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HCACHE, precision, B, T, U1, J, V)
+    hb = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HCACHE if cache_op is None else cache_op, precision, B, T, U1, J, V)
     hc = torch.empty(max(hb, 256), dtype=torch.uint8, device=dev())
     rc = lib.emo_rnnt_joint_fwd(p(te[0]), p(te[1]), p(te[2]), p(te[3]), p(lab), p(tlen), p(ulen), B, T, U1, J, V,
                                 0, precision, p(lp2), p(lse), p(hc) if hb else None, hb, p(ws), ws.numel(),
                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "emo_rnnt_joint_fwd")
     torch.cuda.synchronize()
+    if return_cache:
+        return lp2.cpu().numpy(), lse.cpu().numpy(), hc
     return lp2.cpu().numpy(), lse.cpu().numpy()
 
 
@@ -329,11 +331,36 @@ def test_joint_bf16_forward_values(B, T, U, V, J):
     # fp32 mode through the same raw call agrees tightly
     lp2f, lsef = _joint_fwd_raw(enc, dec_, w_out, b_out, ys, tl, ul, precision=0)
     assert np.abs(lsef[0, :, :] - lse_ref[0]).max() < 1e-4
+    # with the larger cache the forward also leaves h (bf16) and the logits (fp16) of every valid cell,
+    # tile-major: row (b * tiles128 + m // 128) * 128 + m % 128 for the flattened valid cell m = t * (U_b+1) + u
+    from emoasr_b200 import _lib
+    lp2z, lsez, hc = _joint_fwd_raw(enc, dec_, w_out, b_out, ys, tl, ul, precision=1,
+                                    cache_op=_lib.OP_RNNT_JOINT_HZCACHE, return_cache=True)
+    assert np.array_equal(lp2z, lp2) and np.array_equal(lsez, lse)
+    U1 = U + 1
+    tpu = 2 * ((T * U1 + 255) // 256)
+    rows = B * tpu * 128
+    hbytes = (rows * J * 2 + 255) // 256 * 256
+    hcache = hc[: rows * J * 2].view(torch.bfloat16).view(rows, J).float().cpu().numpy()
+    zcache = hc[hbytes: hbytes + rows * V * 2].view(torch.float16).view(rows, V).float().cpu().numpy()
+    for b in range(B):
+        Tb, U1b = tl[b], ul[b] + 1
+        m = np.arange(Tb * U1b)
+        t, u = m // U1b, m % U1b
+        r = b * tpu * 128 + m
+        assert np.abs(hcache[r] - np.tanh(enc[b, t] + dec_[b, u])).max() < 2e-2
+        assert np.abs(zcache[r] - z[b, t, u]).max() < 6e-2
 
 
+@pytest.mark.parametrize("zcache", [True, False], ids=["zcache", "recompute"])
 @pytest.mark.parametrize("B,T,U,V,J", BF16_SHAPES)
-def test_joint_bf16_loss_and_grads(B, T, U, V, J):
+def test_joint_bf16_loss_and_grads(B, T, U, V, J, zcache, monkeypatch):
+    """Both backward routes: logits streamed from the fp16 z cache (default) and recomputed from the h cache."""
     import emoasr_b200 as E
+    if zcache:
+        monkeypatch.delenv("EMO_NO_ZCACHE", raising=False)
+    else:
+        monkeypatch.setenv("EMO_NO_ZCACHE", "1")
     from oracle import rnnt_dp
     rng = np.random.default_rng(B * 77 + V)
     f = lambda *s: rng.standard_normal(s).astype(np.float32)
@@ -384,7 +411,8 @@ def test_ctc_backward_without_staged_beta_matches_training_path():
     assert torch.allclose(grad, x.grad, rtol=GRAD_RTOL, atol=2e-5)
 
 
-def test_joint_bf16_properties_full_size_cfg3():
+@pytest.mark.parametrize("zcache", [True, False], ids=["zcache", "recompute"])
+def test_joint_bf16_properties_full_size_cfg3(zcache, monkeypatch):
     """BASELINE cfg 3 at full size (B=32,T=250,U=100,V=1024,J=512; the oracle would need 3.3 GB tensors):
     size-independent properties of the fused tensor-core path.
       * every dz row sums to zero (softmax - two one-hots)        =>  sum(d_b_out) ~ 0
@@ -392,6 +420,10 @@ def test_joint_bf16_properties_full_size_cfg3():
       * padded frames / labels get exactly zero gradient
       * the loss agrees with the fp32 FFMA mode on the same inputs within the stated bf16 tolerance."""
     import emoasr_b200 as E
+    if zcache:
+        monkeypatch.delenv("EMO_NO_ZCACHE", raising=False)
+    else:
+        monkeypatch.setenv("EMO_NO_ZCACHE", "1")
     gen = torch.Generator().manual_seed(11)
     B, T, U, V, J = 32, 250, 100, 1024, 512
     enc = torch.randn(B, T, J, generator=gen).to(dev())
