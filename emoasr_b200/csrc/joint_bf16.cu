@@ -25,19 +25,20 @@ namespace emo {
 namespace {
 
 // ---- per-variant constants ----
-template <int kCtas> struct Cfg;
-template <> struct Cfg<1> {
+template <int kCtas, bool kStoreZ> struct Cfg;
+template <bool kStoreZ> struct Cfg<1, kStoreZ> {
     static constexpr int kBStages = 2;                // (tuning switch only; the pair kernel is the product path)
     static constexpr int kBRows = kChunkN;            // vocab rows of a w_out tile held by this CTA
 };
-template <> struct Cfg<2> {
-    static constexpr int kBStages = 5;
+template <bool kStoreZ> struct Cfg<2, kStoreZ> {
+    static constexpr int kBStages = kStoreZ ? 4 : 5;  // the z staging buffers take one stage's worth of shared memory
     static constexpr int kBRows = kChunkN / 2;
 };
+constexpr int kZStageBytes = 2048;                    // per epilogue warp: [32 cells x 32 v] fp16, 64B swizzle
 
-template <int kCtas>
+template <int kCtas, bool kStoreZ>
 struct __align__(16) FwdBarriers {
-    uint64_t b_full[Cfg<kCtas>::kBStages], b_empty[Cfg<kCtas>::kBStages];
+    uint64_t b_full[Cfg<kCtas, kStoreZ>::kBStages], b_empty[Cfg<kCtas, kStoreZ>::kBStages];
     uint64_t a_full[kMaxKBlocks], a_empty[kMaxKBlocks];
     uint64_t h_ready[kMaxKBlocks];  // local: this CTA's producer threads have written block kb
     uint64_t acc_full[2], acc_empty[2];
@@ -46,10 +47,14 @@ struct __align__(16) FwdBarriers {
 };
 
 // One 32-column group of logits of this thread's row: bias add, online (max, sum exp2), capture of
-// the blank / label logit.
+// the blank / label logit.  kStoreZ: the warp's [32 cells x 32 v] block of logits also goes to the z cache
+// as fp16: staged in this warp's shared-memory buffer (64B swizzle, conflict-free 16-byte stores) and
+// written with one TMA store (per-thread global stores of 64-byte row pieces cost 32 L1 wavefronts each).
+template <bool kStoreZ>
 __device__ __forceinline__ void lse_group(const uint32_t (&r)[32], const float* __restrict__ bias,
                                           int v0, int lab, int blank, float& run_m, float& run_s,
-                                          float& zb, float& zl, __half* __restrict__ zrow) {
+                                          float& zb, float& zl, const CUtensorMap* tmap_z, uint8_t* zbuf,
+                                          int zrow0, int lane) {
     float x[32];
     float m0 = kNegInf, m1 = kNegInf, m2 = kNegInf, m3 = kNegInf;
 #pragma unroll
@@ -64,12 +69,21 @@ __device__ __forceinline__ void lse_group(const uint32_t (&r)[32], const float* 
         m2 = fmaxf(m2, x[i + 2]);
         m3 = fmaxf(m3, x[i + 3]);
     }
-    if (zrow) {   // z cache: the logits of this row, fp16, for the backward (warp-uniform branch)
-        uint4* dst = reinterpret_cast<uint4*>(zrow + v0);
+    if (kStoreZ) {
+        if (lane == 0) tma_store_wait_read<0>();   // the previous block has left the staging buffer
+        __syncwarp();
+        uint8_t* rowp = zbuf + lane * 64;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
-            dst[i] = make_uint4(pack_f16x2(x[8 * i], x[8 * i + 1]), pack_f16x2(x[8 * i + 2], x[8 * i + 3]),
-                                pack_f16x2(x[8 * i + 4], x[8 * i + 5]), pack_f16x2(x[8 * i + 6], x[8 * i + 7]));
+            *reinterpret_cast<uint4*>(rowp + ((i ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(pack_f16x2(x[8 * i], x[8 * i + 1]), pack_f16x2(x[8 * i + 2], x[8 * i + 3]),
+                           pack_f16x2(x[8 * i + 4], x[8 * i + 5]), pack_f16x2(x[8 * i + 6], x[8 * i + 7]));
+        fence_proxy_async_smem();
+        __syncwarp();
+        if (lane == 0) {
+            tma_store_2d(tmap_z, smem_u32(zbuf), v0, zrow0);
+            tma_store_commit();
+        }
     }
     const float new_m = fmaxf(run_m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
     const float neg_m2 = -new_m * kLog2e;
@@ -129,19 +143,19 @@ __device__ __forceinline__ void produce_h_block16(const uint4 (&re)[4], const ui
     }
 }
 
-template <int kCtas>
+template <int kCtas, bool kStoreZ>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
+                 const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (rows,V), box [32 v x 32 cells], 64B swizzle
                  int store_h, const __half* __restrict__ enc,
                  const __half* __restrict__ dec, const float* __restrict__ b_out,
                  const int* __restrict__ labels, const int* __restrict__ tlen,
                  const int* __restrict__ ulen, int B, int T, int U1, int J, int V, int blank,
-                 float* __restrict__ lp2, float* __restrict__ lse_out,
-                 __half* __restrict__ zcache) {   // optional (rows of the h cache, V) fp16 logits
+                 float* __restrict__ lp2, float* __restrict__ lse_out) {
     constexpr bool kPair = kCtas == 2;
-    constexpr int kBStages = Cfg<kCtas>::kBStages;
-    constexpr int kBBytes = Cfg<kCtas>::kBRows * kBlockK * 2;
-    using Bars = FwdBarriers<kCtas>;
+    constexpr int kBStages = Cfg<kCtas, kStoreZ>::kBStages;
+    constexpr int kBBytes = Cfg<kCtas, kStoreZ>::kBRows * kBlockK * 2;
+    using Bars = FwdBarriers<kCtas, kStoreZ>;
     // 1024-byte alignment is required by the 128B swizzle atoms; the kernel has no static shared
     // memory, so the dynamic window starts at the CTA's (1 KiB-granular) shared-memory base.
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -149,7 +163,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     const int NC = (V + kChunkN - 1) / kChunkN;
     uint8_t* sA = smem;
     uint8_t* sB = sA + (size_t)KB * kABlockBytes;
-    Bars* bars = reinterpret_cast<Bars*>(sB + (size_t)kBStages * kBBytes);
+    uint8_t* sZst = sB + (size_t)kBStages * kBBytes;   // kStoreZ: one staging buffer per epilogue warp
+    Bars* bars = reinterpret_cast<Bars*>(sZst + (kStoreZ ? (kFwdEpiThreads / 32) * kZStageBytes : 0));
     float* s_bias = reinterpret_cast<float*>(bars + 1);  // [2][kChunkN]
     float4* s_part = reinterpret_cast<float4*>(s_bias + 2 * kChunkN);  // [kTileM] partial LSE state of column half 1
 
@@ -181,6 +196,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(&tmap_h);
+        if (kStoreZ) tma_prefetch_desc(&tmap_z);
     }
     if (warp == 2) {
         if (kPair) { tmem_alloc_pair(smem_u32(&bars->tmem_base), 512); tmem_relinquish_pair(); }
@@ -318,8 +334,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             if (valid && u < ti.U1b - 1)
                 lab = min(max(__ldg(labels + (size_t)ti.b * (U1 - 1) + u), 0), V - 1);
             float run_m = kNegInf, run_s = 0.f, zb = 0.f, zl = 0.f;
-            __half* zrow = zcache ? zcache + (size_t)((ti.b * tiles128_per_utt(T, U1) + ti.first_cell / kTileM) * kTileM + row) * V
-                                  : nullptr;
+            const int zrow0 = (ti.b * tiles128_per_utt(T, U1) + ti.first_cell / kTileM) * kTileM + q * 32;
+            uint8_t* zbuf = sZst + (warp - 4) * kZStageBytes;
             for (int nc = 0; nc < NC; ++nc, ++cc) {
                 const uint32_t buf = cc & 1;
                 const int n = min(kChunkN, V - nc * kChunkN);
@@ -341,12 +357,13 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                     for (int g = g0; g < g1; g += 2) {
                         tmem_wait_ld();
                         if (g + 1 < g1) tmem_ld_32x32b_x32(taddr + (g + 1) * 32, rb);
-                        lse_group(ra, bias + g * 32, nc * kChunkN + g * 32, lab, blank, run_m, run_s, zb, zl, zrow);
+                        lse_group<kStoreZ>(ra, bias + g * 32, nc * kChunkN + g * 32, lab, blank, run_m, run_s, zb, zl,
+                                           &tmap_z, zbuf, zrow0, lane);
                         if (g + 1 < g1) {
                             tmem_wait_ld();
                             if (g + 2 < g1) tmem_ld_32x32b_x32(taddr + (g + 2) * 32, ra);
-                            lse_group(rb, bias + (g + 1) * 32, nc * kChunkN + (g + 1) * 32, lab, blank, run_m,
-                                      run_s, zb, zl, zrow);
+                            lse_group<kStoreZ>(rb, bias + (g + 1) * 32, nc * kChunkN + (g + 1) * 32, lab, blank,
+                                               run_m, run_s, zb, zl, &tmap_z, zbuf, zrow0, lane);
                         }
                     }
                 }
@@ -371,6 +388,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 lse_out[cell] = l;
             }
         }
+        if (kStoreZ && lane == 0) tma_store_wait_all<0>();
     } else {
         reg_dec<104>();
         // ===================== A producers =====================
@@ -492,44 +510,47 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
                                (uint64_t)B * tiles128_per_utt(T, U1) * kTileM, kBlockK, kTileM);
         if (rc) return rc;
     }
-    if (!use_single) {
-        rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, Cfg<2>::kBRows);
+    CUtensorMap tmap_z;
+    if (zcache) {
+        rc = make_tmap_bf16_2d(&tmap_z, zcache, (uint64_t)V, (uint64_t)B * tiles128_per_utt(T, U1) * kTileM, 32, 32,
+                               CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
-        const size_t smem = a_bytes + (size_t)Cfg<2>::kBStages * Cfg<2>::kBRows * kBlockK * 2 +
-                            sizeof(FwdBarriers<2>) + 2 * kChunkN * sizeof(float) + kTileM * sizeof(float4);
+    }
+    const bool pair = !use_single;
+    const int b_rows = pair ? Cfg<2, false>::kBRows : Cfg<1, false>::kBRows;
+    rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, b_rows);
+    if (rc) return rc;
+    if (!store_h) tmap_h = tmap;
+    if (!zcache) tmap_z = tmap;
+    const int tiles = B * ceil_div((size_t)T * U1, (pair ? 2 : 1) * kTileM);
+    const int ctas = pair ? 2 * min(tiles, sm_count() / 2) : min(tiles, sm_count());
+    auto launch = [&](auto kernel, int stages, size_t bars_bytes, bool store_z) -> int {
+        const size_t smem = a_bytes + (size_t)stages * b_rows * kBlockK * 2 +
+                            (store_z ? (kFwdEpiThreads / 32) * kZStageBytes : 0) + bars_bytes +
+                            2 * kChunkN * sizeof(float) + kTileM * sizeof(float4);
         EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_fwd(bf16): shared memory");
-        EMO_CUDA(cudaFuncSetAttribute(joint_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        const int ptiles = B * ceil_div((size_t)T * U1, 2 * kTileM);
-        const int pairs = min(ptiles, sm_count() / 2);
+        EMO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(2 * pairs);
+        cfg.gridDim = dim3(ctas);
         cfg.blockDim = dim3(kFwdThreads);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
-        if (!store_h) tmap_h = tmap;
-        EMO_CUDA(cudaLaunchKernelEx(&cfg, joint_fwd_kernel<2>, tmap, tmap_h, store_h, enc_h, dec_h, b_out,
-                                    labels, tlen, ulen, B, T, U1, J, V, blank, lp2, lse, zcache));
-        EMO_CHECK_LAUNCH("joint_fwd_kernel<pair>");
+        EMO_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmap, tmap_h, tmap_z, store_h, (const __half*)enc_h,
+                                    (const __half*)dec_h, b_out, labels, tlen, ulen, B, T, U1, J, V, blank, lp2, lse));
+        EMO_CHECK_LAUNCH("joint_fwd_kernel");
         return EMO_OK;
+    };
+    if (pair) {
+        if (zcache) return launch(joint_fwd_kernel<2, true>, Cfg<2, true>::kBStages, sizeof(FwdBarriers<2, true>), true);
+        return launch(joint_fwd_kernel<2, false>, Cfg<2, false>::kBStages, sizeof(FwdBarriers<2, false>), false);
     }
-    rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, Cfg<1>::kBRows);
-    if (rc) return rc;
-    const size_t smem = a_bytes + (size_t)Cfg<1>::kBStages * Cfg<1>::kBRows * kBlockK * 2 +
-                        sizeof(FwdBarriers<1>) + 2 * kChunkN * sizeof(float) + kTileM * sizeof(float4);
-    EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_fwd(bf16): shared memory");
-    EMO_CUDA(cudaFuncSetAttribute(joint_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int tiles = B * ceil_div((size_t)T * U1, kTileM);
-    if (!store_h) tmap_h = tmap;
-    joint_fwd_kernel<1><<<min(tiles, sm_count()), kFwdThreads, smem, st>>>(tmap, tmap_h, store_h, enc_h, dec_h,
-                                                                        b_out, labels, tlen, ulen, B, T, U1, J, V,
-                                                                        blank, lp2, lse, zcache);
-    EMO_CHECK_LAUNCH("joint_fwd_kernel<single>");
-    return EMO_OK;
+    if (zcache) return launch(joint_fwd_kernel<1, true>, Cfg<1, true>::kBStages, sizeof(FwdBarriers<1, true>), true);
+    return launch(joint_fwd_kernel<1, false>, Cfg<1, false>::kBStages, sizeof(FwdBarriers<1, false>), false);
 }
 
 }  // namespace emo

@@ -1163,8 +1163,8 @@ size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V) {
         return zcache_offset_for(B, T, U1, J) + align_up(zcache_bytes_for(B, T, U1, V), 256);
     }
     size_t w = align_up((size_t)V * J * sizeof(__nv_bfloat16), 256);
-    if (op == EMO_OP_RNNT_JOINT_BWD)
-        return w + align_up((size_t)B * T * U1 * J * sizeof(__nv_bfloat16), 256);
+    if (op == EMO_OP_RNNT_JOINT_BWD)   // dpre (B,T,U1,J) (recompute path) or tile-major dh (z-cache path, >= as large)
+        return w + align_up(hcache_bytes_for(B, T, U1, J), 256);
     // forward: + fp16 copies of enc_proj and dec_proj
     return w + align_up((size_t)B * T * J * sizeof(__half), 256) + align_up((size_t)B * U1 * J * sizeof(__half), 256);
 }
@@ -1213,11 +1213,8 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
         hcache_bytes >= zcache_offset_for(B, T, U1, J) + zcache_bytes_for(B, T, U1, V)) {
         const void* zcache = (const char*)hcache + zcache_offset_for(B, T, U1, J);
         rc = joint_dhz_launch(w_bf16, hcache, zcache, labels, tlen, ulen, lse, gamma2, grad_cost, B, T, U1, J, V,
-                              blank, dpre, st);
+                              blank, dpre, d_enc_proj, d_dec_proj, st);
         if (rc) return rc;
-        reduce_dpre_kernel<<<dim3(J / kRedCols, ceil_div(T, kRedTG), B), kRedWarps * 32, 0, st>>>(
-            dpre, tlen, ulen, T, U1, J, d_enc_proj, d_dec_proj);
-        EMO_CHECK_LAUNCH("reduce_dpre_kernel");
         return joint_dwz_launch(hcache, zcache, labels, tlen, ulen, lse, gamma2, grad_cost, B, T, U1, J, V, blank,
                                 d_w_out, d_b_out, st);
     }

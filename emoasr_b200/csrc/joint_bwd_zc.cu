@@ -10,7 +10,8 @@
 //
 //   dhz kernel  cell-stationary CTA pair (cta_group::2, 256 cells per pair tile); per 64-wide vocab block:
 //                  z tile [128 cells x 64 v] (TMA) -> dz (8 transform warps) -> dh[256 x J] += dz W[kb]
-//               with the full J-wide accumulator in TMEM (512 columns); dpre = dh (1 - h^2) -> bf16.
+//               with the full J-wide accumulator in TMEM (512 columns); dh leaves as bf16, tile-major (TMA
+//               stores); reduce_dh_kernel applies (1 - h^2) and forms the two axis sums.
 //               The tile, read with v contiguous, is the K-major A operand.
 //   dWz kernel  vocab-stationary CTA pair: role = 256 vocab rows (128 per CTA, TMEM lane == vocab row), all
 //               of J in the 512 TMEM columns, accumulated over ALL cells of the pair's share:
@@ -22,11 +23,18 @@
 // producer, warp 3 per-cell scalar stager (dWz), warps 4-11 transform, warps 12-19 accumulator drain / flush.
 #include "joint_tc.cuh"
 
+#ifdef EMO_ZC_PROF
+#define EMO_PROF(...) __VA_ARGS__
+#else
+#define EMO_PROF(...)
+#endif
+
 namespace emo {
 namespace {
 
 constexpr int kZcThreads = 640;
-constexpr int kDhzZStages = 6;
+constexpr int kDhzZStages = 5;
+constexpr int kDrainBufBytes = 2048;           // per drain warp: [32 cells x 32 j] bf16, 64B swizzle
 constexpr int kDwzZStages = 5;
 constexpr int kOpStages = 4;
 constexpr int kZBytes = 16384;                 // one z / dz stage: 128 x 64 (dhz) or 2 x [64 x 64] (dWz) 2-byte elements
@@ -53,22 +61,36 @@ struct CellSc {
     int lab;     // label of the cell's emit transition, -1 if none
 };
 
-__device__ __forceinline__ void load_cell_sc(CellSc& s, const TileInfo& ti, int m, int T, int U1, int V,
-                                             const int* __restrict__ labels, const float* __restrict__ lse,
-                                             const float* __restrict__ gamma2,
-                                             const float* __restrict__ grad_cost) {
-    s.nl2 = -1e30f; s.cs = 0.f; s.cb = 0.f; s.cl = 0.f; s.lab = -1;
+// Split in two so that the global loads can stay in flight: load_raw_sc only issues the loads (no instruction
+// consumes their results), finish_sc does the arithmetic one tile / two K blocks later.
+struct RawSc {
+    float g, lse;
+    float2 gm;
+    int lab, valid;
+};
+__device__ __forceinline__ void load_raw_sc(RawSc& r, const TileInfo& ti, int m, int T, int U1,
+                                            const int* __restrict__ labels, const float* __restrict__ lse,
+                                            const float* __restrict__ gamma2,
+                                            const float* __restrict__ grad_cost) {
+    r.g = 0.f; r.lse = 0.f; r.gm = make_float2(0.f, 0.f); r.lab = -1; r.valid = 0;
     if (m < ti.n_cells) {
         const int t = m / ti.U1b, u = m - t * ti.U1b;
         const size_t cell = ((size_t)ti.b * T + t) * U1 + u;
-        const float g = __ldg(grad_cost + ti.b);
-        const float2 gm = __ldg(reinterpret_cast<const float2*>(gamma2) + cell);
-        s.nl2 = -__ldg(lse + cell) * kLog2e;
-        s.cs = g * (gm.x + gm.y);
-        s.cb = g * gm.x;
-        s.cl = g * gm.y;
-        if (u < ti.U1b - 1) s.lab = min(max(__ldg(labels + (size_t)ti.b * (U1 - 1) + u), 0), V - 1);
+        r.valid = 1;
+        r.g = __ldg(grad_cost + ti.b);
+        r.gm = __ldg(reinterpret_cast<const float2*>(gamma2) + cell);
+        r.lse = __ldg(lse + cell);
+        if (u < ti.U1b - 1) r.lab = __ldg(labels + (size_t)ti.b * (U1 - 1) + u);
     }
+}
+__device__ __forceinline__ CellSc finish_sc(const RawSc& r, int V) {
+    CellSc s;
+    s.nl2 = r.valid ? -r.lse * kLog2e : -1e30f;
+    s.cs = r.g * (r.gm.x + r.gm.y);
+    s.cb = r.g * r.gm.x;
+    s.cl = r.g * r.gm.y;
+    s.lab = r.lab < 0 ? -1 : min(r.lab, V - 1);
+    return s;
 }
 
 // 8 consecutive vocab entries of one cell: fp16 logits -> bf16 dz.  vb = first vocab index of the strip,
@@ -115,10 +137,11 @@ struct __align__(16) ZcBarriers {
 __global__ void __launch_bounds__(kZcThreads, 1)
 joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,J), box [64 j x 64 v]
                  const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (rows,V), box [64 v x 128 cells]
-                 const __nv_bfloat16* __restrict__ hcache, const int* __restrict__ labels,
+                 const __grid_constant__ CUtensorMap tmap_d,   // dh out, bf16 (rows,J), box [32 j x 32 cells], 64B swizzle
+                 const int* __restrict__ labels,
                  const int* __restrict__ tlen, const int* __restrict__ ulen, const float* __restrict__ lse,
                  const float* __restrict__ gamma2, const float* __restrict__ grad_cost, int B, int T, int U1,
-                 int J, int V, int blank, __nv_bfloat16* __restrict__ dpre_out) {   // (B,T,U1,J)
+                 int J, int V, int blank) {
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int kS = kDhzZStages;
     using Bars = ZcBarriers<kS>;
@@ -127,7 +150,8 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
     const uint32_t op_bytes = (uint32_t)J * 64;      // this CTA's half of a [64 v x J] w_out block
     uint8_t* sZ = smem;
     uint8_t* sW = sZ + (size_t)kS * kZBytes;
-    Bars* bars = reinterpret_cast<Bars*>(sW + (size_t)kOpStages * op_bytes);
+    uint8_t* sDst = sW + (size_t)kOpStages * op_bytes;        // drain staging, one buffer per drain warp
+    Bars* bars = reinterpret_cast<Bars*>(sDst + kDrainWarps * kDrainBufBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -154,6 +178,7 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&tmap_w);
         tma_prefetch_desc(&tmap_z);
+        tma_prefetch_desc(&tmap_d);
     }
     if (warp == 2) {
         tmem_alloc_pair(smem_u32(&bars->tmem_base), 512);
@@ -211,12 +236,18 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
             const uint32_t z_lo0 = desc_lo(smem_u32(sZ), 16);
             const uint32_t w_lo0 = desc_lo(smem_u32(sW), kBoxBytes);
             TileInfo ti;
+            EMO_PROF(long long p_acc = 0, p_dz = 0, p_op = 0, p_t0 = clock64(), p_c;)
             for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
                 if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
+                EMO_PROF(p_c = clock64();)
                 mbar_wait(smem_u32(&bars->acc_empty), (tl & 1) ^ 1);
+                EMO_PROF(p_acc += clock64() - p_c;)
                 for (int kb = 0; kb < NKB; ++kb) {
+                    EMO_PROF(p_c = clock64();)
                     mbar_wait(smem_u32(&bars->dz_full[zs]), zph);
+                    EMO_PROF(p_dz += clock64() - p_c; p_c = clock64();)
                     mbar_wait(smem_u32(&bars->op_full[slot]), ph);
+                    EMO_PROF(p_op += clock64() - p_c;)
                     tc_fence_after();
                     if (elect_one_sync()) {
                         const uint32_t a_lo = z_lo0 + zs * (kZBytes >> 4);
@@ -240,6 +271,9 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
                 }
                 ++tl;
             }
+            EMO_PROF(if (blockIdx.x == 0 && lane == 0)
+                         printf("dhz issuer: total %lld clk, %u tiles; wait acc_empty %lld dz_full %lld op_full %lld\n",
+                                clock64() - p_t0, tl, p_acc, p_dz, p_op);)
         }
     } else if (warp >= 4 && warp < 4 + kXfWarps) {
         // ===================== transform: z (fp16) -> dz (bf16) in place =====================
@@ -257,7 +291,7 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
         uint32_t zs = 0, zph = 0;
         // scalars of the NEXT tile are fetched while the current one is transformed
         int ntile = tile0 - tile_stride;
-        CellSc nxt[4];
+        RawSc nxt[4];
         auto fetch_next = [&]() {
             TileInfo ni;
             do {
@@ -266,7 +300,7 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
             } while (!tile_info<2>(ntile, tiles_per_utt, rank, tlen, ulen, T, U1, ni));
 #pragma unroll
             for (int i = 0; i < 4; ++i)
-                load_cell_sc(nxt[i], ni, ni.first_cell + r0 + i, T, U1, V, labels, lse, gamma2, grad_cost);
+                load_raw_sc(nxt[i], ni, ni.first_cell + r0 + i, T, U1, labels, lse, gamma2, grad_cost);
         };
         fetch_next();
         TileInfo ti;
@@ -274,7 +308,7 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
             if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
             CellSc cur[4];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) cur[i] = nxt[i];
+            for (int i = 0; i < 4; ++i) cur[i] = finish_sc(nxt[i], V);
             fetch_next();
             for (int kb = 0; kb < NKB; ++kb) {
                 uint8_t* st = sZ + (size_t)zs * kZBytes;
@@ -293,61 +327,53 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
             }
         }
     } else if (warp >= 4 + kXfWarps) {
-        // ===================== drain: dh -> dpre = dh (1 - h^2) -> bf16 (B,T,U1,J) =====================
+        // ===================== drain: dh -> bf16, tile-major (rows of the h cache, J) =====================
+        // Each warp moves its [32 cells x 32 j] blocks through a private shared-memory buffer (64B swizzle,
+        // conflict-free 16-byte stores) and one TMA store per block; the factor (1 - h^2) is applied by the
+        // reduction kernel, which reads h with the same row index.
         const int dw = warp - (4 + kXfWarps);
         const int q = warp & 3, hf = dw >> 2;
-        const int row = q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
         const uint32_t acc_empty_addr = mapa_shared(smem_u32(&bars->acc_empty), 0);
         const int G = J >> 6;              // 32-column groups per column half
         const int col_base = hf * (J >> 1);
+        uint8_t* buf = sDst + dw * kDrainBufBytes;
+        uint8_t* rowp = buf + lane * 64;
+        const int sw = (lane >> 1) & 3;
         uint32_t tl = 0;
         TileInfo ti;
         for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
             if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
-            const int m = ti.first_cell + row;
-            const bool valid = m < ti.n_cells;
-            const int t = valid ? m / ti.U1b : 0;
-            const int u = valid ? m - t * ti.U1b : 0;
-            const size_t cell = ((size_t)ti.b * T + t) * U1 + u;
-            const size_t hrow = (size_t)((ti.b * tpu + ti.first_cell / kTileM) * kTileM + row);
-            const uint4* hp = reinterpret_cast<const uint4*>(hcache + hrow * J + col_base);
-            uint4* dp = reinterpret_cast<uint4*>(dpre_out + cell * J + col_base);
-            uint4 hv[4];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) hv[j] = __ldg(hp + j);
+            const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM + q * 32;
             mbar_wait(smem_u32(&bars->acc_full), tl & 1);
             tc_fence_after();
-            for (int g = 0; g < G; ++g) {
-                uint32_t r[32];
-                tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + g * 32, r);
-                uint4 hn[4];
-                if (g + 1 < G) {
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_base + col_base, ra);
+            auto emit = [&](const uint32_t (&r)[32], int g) {
+                if (lane == 0) tma_store_wait_read<0>();   // the previous block has left the buffer
+                __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) hn[j] = __ldg(hp + (g + 1) * 4 + j);
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(
+                        pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])),
+                        pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
+                        pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
+                        pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmap_d, smem_u32(buf), col_base + g * 32, row0);
+                    tma_store_commit();
                 }
+            };
+            for (int g = 0; g < G; g += 2) {
                 tmem_wait_ld();
-                uint32_t pk[16];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                    const uint32_t hw[4] = {hv[j].x, hv[j].y, hv[j].z, hv[j].w};
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) {
-                        const float h0 = __uint_as_float(hw[e] << 16);
-                        const float h1 = __uint_as_float(hw[e] & 0xffff0000u);
-                        const float d0 = __uint_as_float(r[j * 8 + e * 2]) * fmaf(-h0, h0, 1.f);
-                        const float d1 = __uint_as_float(r[j * 8 + e * 2 + 1]) * fmaf(-h1, h1, 1.f);
-                        pk[j * 4 + e] = pack_bf16x2(d0, d1);
-                    }
-                }
-                if (valid) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        dp[g * 4 + j] = make_uint4(pk[4 * j], pk[4 * j + 1], pk[4 * j + 2], pk[4 * j + 3]);
-                }
+                if (g + 1 < G) tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + (g + 1) * 32, rb);
+                emit(ra, g);
                 if (g + 1 < G) {
-#pragma unroll
-                    for (int j = 0; j < 4; ++j) hv[j] = hn[j];
+                    tmem_wait_ld();
+                    if (g + 2 < G) tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + (g + 2) * 32, ra);
+                    emit(rb, g + 1);
                 }
             }
             tc_fence_before();
@@ -355,6 +381,7 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
             if (lane == 0) mbar_arrive_cluster(acc_empty_addr);
             ++tl;
         }
+        if (lane == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -471,33 +498,64 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
         }
     } else if (warp == 3) {
         // ===================== per-cell scalars of each stage =====================
+        // The global loads (lse, gamma, labels: a DRAM round trip) of K blocks n+1 and n+2 are in flight while
+        // block n is published; nothing consumes a loaded value before its own publish.
         uint32_t zs = 0, zph = 0;
-        for_each_kblock([&](const TileInfo& ti, int rowK, int m0) {
-                (void)ti; (void)rowK; (void)m0;
+        int ltile = split - num_splits, lkh = 1, lnkh = 1;     // load cursor
+        TileInfo lti;
+        auto load_next = [&](RawSc (&q)[2]) -> bool {
+            if (++lkh >= lnkh) {
+                do {
+                    ltile += num_splits;
+                    if (ltile >= total_tiles) { ltile = total_tiles; lkh = lnkh = 1; return false; }
+                } while (!tile_info<1>(ltile, tiles_per_utt, 0, tlen, ulen, T, U1, lti));
+                lkh = 0;
+                lnkh = (lti.n_cells - lti.first_cell > 64) ? 2 : 1;
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                load_raw_sc(q[i], lti, lti.first_cell + lkh * 64 + lane + 32 * i, T, U1, labels, lse, gamma2,
+                            grad_cost);
+            return true;
+        };
+        auto publish = [&](const RawSc (&qr)[2]) {
             mbar_wait(smem_u32(&bars->dz_empty[zs]), zph ^ 1);
             float* sc = s_sc + zs * 5 * 64;
 #pragma unroll
             for (int i = 0; i < 2; ++i) {
                 const int ci = lane + 32 * i;
-                CellSc s;
-                load_cell_sc(s, ti, m0 + ci, T, U1, V, labels, lse, gamma2, grad_cost);
-                sc[ci] = s.nl2; sc[64 + ci] = s.cs; sc[128 + ci] = s.cb; sc[192 + ci] = s.cl;
-                reinterpret_cast<int*>(sc)[256 + ci] = s.lab;
+                const CellSc q = finish_sc(qr[i], V);
+                sc[ci] = q.nl2; sc[64 + ci] = q.cs; sc[128 + ci] = q.cb; sc[192 + ci] = q.cl;
+                reinterpret_cast<int*>(sc)[256 + ci] = q.lab;
             }
             __syncwarp();
             if (lane == 0) mbar_arrive(smem_u32(&bars->z_full[zs]));
             if (++zs == kS) { zs = 0; zph ^= 1; }
-        });
+        };
+        RawSc qa[2], qb[2];
+        bool va = load_next(qa);
+        bool vb = va && load_next(qb);
+        while (va) {
+            publish(qa);
+            va = vb && load_next(qa);
+            if (!vb) break;
+            publish(qb);
+            vb = va && load_next(qb);
+        }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA) =====================
         if (leader) {
             uint32_t zs = 0, zph = 0, slot = 0, ph = 0, first = 1;
             const uint32_t z_lo0 = desc_lo(smem_u32(sZ), kBoxBytes);
             const uint32_t h_lo0 = desc_lo(smem_u32(sH), kBoxBytes);
+            EMO_PROF(long long p_dz = 0, p_op = 0, p_t0 = clock64(), p_c; int p_n = 0;)
             for_each_kblock([&](const TileInfo& ti, int rowK, int m0) {
                 (void)ti; (void)rowK; (void)m0;
+                EMO_PROF(p_c = clock64(); ++p_n;)
                 mbar_wait(smem_u32(&bars->dz_full[zs]), zph);
+                EMO_PROF(p_dz += clock64() - p_c; p_c = clock64();)
                 mbar_wait(smem_u32(&bars->op_full[slot]), ph);
+                EMO_PROF(p_op += clock64() - p_c;)
                 tc_fence_after();
                 if (elect_one_sync()) {
                     const uint32_t a_lo = z_lo0 + zs * (kZBytes >> 4);
@@ -521,6 +579,9 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
             });
             if (elect_one_sync()) umma_commit_pair(smem_u32(&bars->acc_full));
             __syncwarp();
+            EMO_PROF(if (blockIdx.x == 0 && lane == 0)
+                         printf("dwz issuer: total %lld clk, %d K blocks; wait dz_full %lld op_full %lld\n",
+                                clock64() - p_t0, p_n, p_dz, p_op);)
         }
     } else if (warp >= 4 && warp < 4 + kXfWarps) {
         // ===================== transform: z (fp16) -> dz (bf16) in place; column sums for d_b_out ==========
@@ -610,8 +671,82 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
     }
 }
 
+// Both axis reductions of dpre = dh (1 - h^2) in ONE pass over the tile-major dh (bf16, written by the dhz
+// kernel) and h (bf16, the h cache); row of (b,t,u) = b * tiles128 * 128 + t * (U_b+1) + u in both:
+//   d_enc_proj[b,t,j] = sum_{u <= U_b} dpre[b,t,u,j]   (0 for t >= T_b)        written directly
+//   d_dec_proj[b,u,j] = sum_{t <  T_b} dpre[b,t,u,j]   (0 for u >  U_b)        pre-zeroed, red.add.v4
+// Block = (128-column slice, kRedTG frames, utterance).  Warp w owns the rows u = w mod 8: for each of its u
+// it loads the kRedTG frames at once (8-byte loads, next u prefetched), sums them in registers for d_dec
+// (one vector red per (u, lane)) and keeps per-frame partials for d_enc, combined across the 8 warps through
+// shared memory once at the end.  No barrier in the loop.
+constexpr int kRedTG = 8;
+constexpr int kRedWarps = 8;
+constexpr int kRedCols = 128;   // columns per block: 4 per lane (one 8-byte load of 4 bf16)
+__global__ void __launch_bounds__(kRedWarps * 32)
+reduce_dh_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ h,
+                 const int* __restrict__ tlen, const int* __restrict__ ulen, int T, int U1, int J, int tpu,
+                 float* __restrict__ d_enc, float* __restrict__ d_dec) {
+    __shared__ float4 s_enc[kRedWarps][kRedTG][32];
+    const int b = blockIdx.z, j0 = blockIdx.x * kRedCols;
+    const int t0 = blockIdx.y * kRedTG;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int T_b = min(max(tlen[b], 1), T), U1b = min(max(ulen[b], 0), U1 - 1) + 1;
+    const int nt = max(0, min(kRedTG, T_b - t0));          // valid frames of this block
+    const size_t rs = (size_t)J / 4;                        // row stride in uint2
+    const size_t off = (((size_t)b * tpu * kTileM + (size_t)t0 * U1b) * J + j0) / 4 + lane;
+    const uint2* dbase = reinterpret_cast<const uint2*>(dh) + off;
+    const uint2* hbase = reinterpret_cast<const uint2*>(h) + off;
+    float e[kRedTG][4];
+#pragma unroll
+    for (int k = 0; k < kRedTG; ++k) e[k][0] = e[k][1] = e[k][2] = e[k][3] = 0.f;
+    auto load_u = [&](int u, uint2 (&dv)[kRedTG], uint2 (&hv)[kRedTG]) {
+#pragma unroll
+        for (int k = 0; k < kRedTG; ++k) {
+            const bool ok = k < nt && u < U1b;
+            const size_t i = ((size_t)k * U1b + u) * rs;
+            dv[k] = ok ? __ldg(dbase + i) : make_uint2(0u, 0u);
+            hv[k] = ok ? __ldg(hbase + i) : make_uint2(0u, 0u);
+        }
+    };
+    uint2 cd[kRedTG], ch[kRedTG], nd[kRedTG], nh[kRedTG];
+    load_u(warp, cd, ch);
+    for (int u = warp; u < U1b; u += kRedWarps) {
+        load_u(u + kRedWarps, nd, nh);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kRedTG; ++k) {
+            const float h0 = __uint_as_float(ch[k].x << 16), h1 = __uint_as_float(ch[k].x & 0xffff0000u);
+            const float h2 = __uint_as_float(ch[k].y << 16), h3 = __uint_as_float(ch[k].y & 0xffff0000u);
+            const float f0 = __uint_as_float(cd[k].x << 16) * fmaf(-h0, h0, 1.f);
+            const float f1 = __uint_as_float(cd[k].x & 0xffff0000u) * fmaf(-h1, h1, 1.f);
+            const float f2 = __uint_as_float(cd[k].y << 16) * fmaf(-h2, h2, 1.f);
+            const float f3 = __uint_as_float(cd[k].y & 0xffff0000u) * fmaf(-h3, h3, 1.f);
+            a0 += f0; a1 += f1; a2 += f2; a3 += f3;
+            e[k][0] += f0; e[k][1] += f1; e[k][2] += f2; e[k][3] += f3;
+        }
+        if (nt > 0) red_add_v4(d_dec + ((size_t)b * U1 + u) * J + j0 + lane * 4, a0, a1, a2, a3);
+#pragma unroll
+        for (int k = 0; k < kRedTG; ++k) { cd[k] = nd[k]; ch[k] = nh[k]; }
+    }
+#pragma unroll
+    for (int k = 0; k < kRedTG; ++k) s_enc[warp][k][lane] = make_float4(e[k][0], e[k][1], e[k][2], e[k][3]);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kRedTG * 32; i += blockDim.x) {
+        const int k = i >> 5, l = i & 31;
+        if (t0 + k >= T) continue;
+        float4 a = s_enc[0][k][l];
+#pragma unroll
+        for (int w = 1; w < kRedWarps; ++w) {
+            const float4 x = s_enc[w][k][l];
+            a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
+        }
+        reinterpret_cast<float4*>(d_enc + ((size_t)b * T + t0 + k) * J + j0)[l] = a;
+    }
+}
+
 size_t dhz_smem_bytes(int J) {
-    return (size_t)kDhzZStages * kZBytes + (size_t)kOpStages * J * 64 + sizeof(ZcBarriers<kDhzZStages>);
+    return (size_t)kDhzZStages * kZBytes + (size_t)kOpStages * J * 64 + kDrainWarps * kDrainBufBytes +
+           sizeof(ZcBarriers<kDhzZStages>);
 }
 size_t dwz_smem_bytes(int J) {
     return (size_t)kDwzZStages * kZBytes + (size_t)kOpStages * J * 64 + sizeof(ZcBarriers<kDwzZStages>) +
@@ -641,25 +776,31 @@ bool joint_zc_supported(int J) {
 
 int joint_dhz_launch(const void* w_bf16, const void* hcache, const void* zcache, const int* labels, const int* tlen,
                      const int* ulen, const float* lse, const float* gamma2, const float* grad_cost, int B, int T,
-                     int U1, int J, int V, int blank, void* dpre, cudaStream_t st) {
-    CUtensorMap tmap_w, tmap_z;
-    const uint64_t rows = (uint64_t)B * tiles128_per_utt(T, U1) * kTileM;
+                     int U1, int J, int V, int blank, void* dh_ws, float* d_enc_proj, float* d_dec_proj,
+                     cudaStream_t st) {
+    CUtensorMap tmap_w, tmap_z, tmap_d;
+    const int tpu = tiles128_per_utt(T, U1);
+    const uint64_t rows = (uint64_t)B * tpu * kTileM;
     int rc = make_tmap_bf16_2d(&tmap_w, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, 64);
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tmap_z, zcache, (uint64_t)V, rows, kBlockK, kTileM);
+    if (rc) return rc;
+    rc = make_tmap_bf16_2d(&tmap_d, dh_ws, (uint64_t)J, rows, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc) return rc;
     const size_t smem = dhz_smem_bytes(J);
     EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_bwd(bf16): shared memory (dhz)");
     EMO_CUDA(cudaFuncSetAttribute(joint_dhz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ptiles = B * ceil_div((size_t)T * U1, 2 * kTileM);
     const int pairs = max(1, min(ptiles, sm_count() / 2));
-    const __nv_bfloat16* hc = reinterpret_cast<const __nv_bfloat16*>(hcache);
-    __nv_bfloat16* dp = reinterpret_cast<__nv_bfloat16*>(dpre);
-    void* args[] = {&tmap_w, &tmap_z, &hc, &labels, &tlen, &ulen, &lse, &gamma2, &grad_cost,
-                    &B, &T, &U1, &J, &V, &blank, &dp};
+    void* args[] = {&tmap_w, &tmap_z, &tmap_d, &labels, &tlen, &ulen, &lse, &gamma2, &grad_cost,
+                    &B, &T, &U1, &J, &V, &blank};
     rc = launch_pair_kernel((const void*)joint_dhz_kernel, 2 * pairs, smem, st, args);
     if (rc) return rc;
     EMO_CHECK_LAUNCH("joint_dhz_kernel");
+    reduce_dh_kernel<<<dim3(J / kRedCols, ceil_div(T, kRedTG), B), kRedWarps * 32, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dh_ws), reinterpret_cast<const __nv_bfloat16*>(hcache), tlen, ulen, T,
+        U1, J, tpu, d_enc_proj, d_dec_proj);
+    EMO_CHECK_LAUNCH("reduce_dh_kernel");
     return EMO_OK;
 }
 
