@@ -23,20 +23,27 @@
 // producer, warp 3 per-cell scalar stager (dWz), warps 4-11 transform, warps 12-19 accumulator drain / flush.
 #include "joint_tc.cuh"
 
+// -DEMO_ZC_PROF: clock64 accounting of the MMA issuer's mbarrier waits (printf from CTA 0) and the
+// EMO_ZC_DEBUG ablation switches (bit 0: no transform math, bit 1: no MMAs; results are then wrong).
+// tools/gpu_zcprof.sh; never defined in the shipped library.
 #ifdef EMO_ZC_PROF
 #define EMO_PROF(...) __VA_ARGS__
+#define EMO_DBG(flag) (dbg & (flag))
 #else
 #define EMO_PROF(...)
+#define EMO_DBG(flag) false
 #endif
 
 namespace emo {
 namespace {
 
 constexpr int kZcThreads = 640;
-constexpr int kDhzZStages = 5;
-constexpr int kDrainBufBytes = 2048;           // per drain warp: [32 cells x 32 j] bf16, 64B swizzle
+constexpr int kDhzZStages = 6;
+constexpr int kDhzOpStages = 3;                // w_out blocks come from L2: three in flight are enough
+constexpr int kZPrefetch = 8;                  // z K blocks pulled into L2 ahead of the shared-memory ring
+constexpr int kDrainBufBytes = 2048;           // [32 cells x 32 j] bf16, 64B swizzle; two per drain warp
 constexpr int kDwzZStages = 5;
-constexpr int kOpStages = 4;
+constexpr int kDwzOpStages = 4;
 constexpr int kZBytes = 16384;                 // one z / dz stage: 128 x 64 (dhz) or 2 x [64 x 64] (dWz) 2-byte elements
 constexpr int kBoxBytes = 8192;                // [64 rows x 128 B]
 constexpr int kXfWarps = 8;
@@ -122,13 +129,14 @@ __device__ __forceinline__ uint4 dz8(const uint4 zr, const CellSc& s, int vb, in
                       pack_bf16x2(d[6], d[7]));
 }
 
-template <int kS>
+template <int kS, int kOp>
 struct __align__(16) ZcBarriers {
     uint64_t z_full[kS];      // local: TMA bytes of the z tile (+ the scalar stager in dWz)
     uint64_t dz_full[kS];     // leader: transform warps of both CTAs
     uint64_t dz_empty[kS];    // both CTAs (multicast commit): the MMAs have read the stage
-    uint64_t op_full[kOpStages], op_empty[kOpStages];
+    uint64_t op_full[kOp], op_empty[kOp];
     uint64_t acc_full, acc_empty;
+    uint64_t sc_full[2], sc_empty[2];   // dhz: per-tile cell scalars (double-buffered)
     uint32_t tmem_base;
     uint32_t pad[3];
 };
@@ -141,10 +149,11 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
                  const int* __restrict__ labels,
                  const int* __restrict__ tlen, const int* __restrict__ ulen, const float* __restrict__ lse,
                  const float* __restrict__ gamma2, const float* __restrict__ grad_cost, int B, int T, int U1,
-                 int J, int V, int blank) {
+                 int J, int V, int blank, int dbg) {   // dbg: tuning switches (bit 0: no transform math, bit 1: no MMAs)
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int kS = kDhzZStages;
-    using Bars = ZcBarriers<kS>;
+    constexpr int kOpStages = kDhzOpStages;
+    using Bars = ZcBarriers<kS, kOpStages>;
     const int NKB = (V + kBlockK - 1) / kBlockK;
     const int NMMA = (J + 255) / 256;
     const uint32_t op_bytes = (uint32_t)J * 64;      // this CTA's half of a [64 v x J] w_out block
@@ -152,6 +161,7 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
     uint8_t* sW = sZ + (size_t)kS * kZBytes;
     uint8_t* sDst = sW + (size_t)kOpStages * op_bytes;        // drain staging, one buffer per drain warp
     Bars* bars = reinterpret_cast<Bars*>(sDst + kDrainWarps * kDrainBufBytes);
+    float* s_sc = reinterpret_cast<float*>(bars + 1);          // [2][5][128] per-cell scalars of a tile
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = cluster_ctarank();
@@ -173,6 +183,10 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
         }
         mbar_init(smem_u32(&bars->acc_full), 1);
         mbar_init(smem_u32(&bars->acc_empty), 2 * kDrainWarps);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&bars->sc_full[i]), 1);
+            mbar_init(smem_u32(&bars->sc_empty[i]), 2 * kXfWarps);   // every transform warp of this CTA
+        }
         fence_barrier_init();
     }
     if (warp == 0 && lane == 0) {
@@ -217,10 +231,28 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
         if (lane == 0) {
             uint32_t zs = 0, zph = 0;
             TileInfo ti;
+            // L2 prefetch cursor: kZPrefetch K blocks ahead of the loads, so a load is an L2 hit and the shared-memory
+            // ring only has to cover the L2 latency, not a DRAM round trip
+            int pt = tile0 - tile_stride, pkb = NKB, prow0 = 0;
+            auto pf_next = [&]() {
+                if (pt >= total_tiles) return;
+                if (++pkb >= NKB) {
+                    TileInfo ni;
+                    do {
+                        pt += tile_stride;
+                        if (pt >= total_tiles) return;
+                    } while (!tile_info<2>(pt, tiles_per_utt, rank, tlen, ulen, T, U1, ni));
+                    prow0 = (ni.b * tpu + ni.first_cell / kTileM) * kTileM;
+                    pkb = 0;
+                }
+                tma_prefetch_2d(&tmap_z, pkb * kBlockK, prow0);
+            };
+            for (int i = 0; i < kZPrefetch; ++i) pf_next();
             for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
                 if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
                 const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM;
                 for (int kb = 0; kb < NKB; ++kb) {
+                    pf_next();
                     mbar_wait(smem_u32(&bars->dz_empty[zs]), zph ^ 1);
                     const uint32_t full = smem_u32(&bars->z_full[zs]);
                     mbar_arrive_expect_tx(full, kZBytes);
@@ -254,6 +286,7 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
                         const uint32_t b_lo = w_lo0 + slot * (op_bytes >> 4);
 #pragma unroll
                         for (int k16 = 0; k16 < kBlockK / 16; ++k16) {
+                            if (EMO_DBG(2)) break;
                             for (int n = 0; n < NMMA; ++n) {
                                 const int Nn = min(256, J - n * 256);
                                 umma_bf16_pair(tmem_base + n * 256, mk_desc(a_lo + 2 * k16),
@@ -275,10 +308,50 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
                          printf("dhz issuer: total %lld clk, %u tiles; wait acc_empty %lld dz_full %lld op_full %lld\n",
                                 clock64() - p_t0, tl, p_acc, p_dz, p_op);)
         }
-    } else if (warp >= 4 && warp < 4 + kXfWarps) {
-        // ===================== transform: z (fp16) -> dz (bf16) in place =====================
+    } else if (warp == 3) {
+        // ===================== per-cell scalars of each tile -> shared memory =====================
+        // (loads of the NEXT tile are in flight while the current one is published)
+        uint32_t tl = 0;
+        int ntile = tile0 - tile_stride;
+        RawSc nxt[4];
+        bool have = false;
+        auto fetch_next = [&]() {
+            TileInfo ni;
+            have = false;
+            do {
+                ntile += tile_stride;
+                if (ntile >= total_tiles) return;
+            } while (!tile_info<2>(ntile, tiles_per_utt, rank, tlen, ulen, T, U1, ni));
+            have = true;
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                load_raw_sc(nxt[i], ni, ni.first_cell + lane + 32 * i, T, U1, labels, lse, gamma2, grad_cost);
+        };
+        fetch_next();
+        while (have) {
+            mbar_wait(smem_u32(&bars->sc_empty[tl & 1]), ((tl >> 1) & 1) ^ 1);
+            float* sc = s_sc + (tl & 1) * 5 * kTileM;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int ci = lane + 32 * i;
+                const CellSc q = finish_sc(nxt[i], V);
+                sc[ci] = q.nl2; sc[kTileM + ci] = q.cs; sc[2 * kTileM + ci] = q.cb; sc[3 * kTileM + ci] = q.cl;
+                reinterpret_cast<int*>(sc)[4 * kTileM + ci] = q.lab;
+            }
+            fetch_next();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&bars->sc_full[tl & 1]));
+            ++tl;
+        }
+    } else if (warp >= 4) {
+        // ===================== transform: z (fp16) -> dz (bf16) in place; group 1 also drains ==========
+        // Two groups of 8 warps take alternate K blocks (group = kb & 1), so that four warps per scheduler in two
+        // different phases of the LDS -> MUFU -> pack -> STS -> fence chain keep the pipes busy.  Group 1 is also
+        // the drain: its transform work for the next tile starts when the accumulator has been read out, which
+        // is when the MMAs of that tile may start anyway.
         // thread = (16-byte chunk c of the 128-byte row, 4 consecutive rows)
-        const int tt = threadIdx.x - 128;
+        const int grp = (warp - 4) >> 3;
+        const int tt = threadIdx.x - 128 - grp * 256;
         const int c = tt & 7, r0 = (tt >> 3) * 4;
         const uint32_t dz_full0 = mapa_shared(smem_u32(&bars->dz_full[0]), 0);
         uint32_t off[4];
@@ -288,31 +361,40 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
             off[i] = (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
         }
         float dummy[8];
-        uint32_t zs = 0, zph = 0;
-        // scalars of the NEXT tile are fetched while the current one is transformed
-        int ntile = tile0 - tile_stride;
-        RawSc nxt[4];
-        auto fetch_next = [&]() {
-            TileInfo ni;
-            do {
-                ntile += tile_stride;
-                if (ntile >= total_tiles) return;
-            } while (!tile_info<2>(ntile, tiles_per_utt, rank, tlen, ulen, T, U1, ni));
-#pragma unroll
-            for (int i = 0; i < 4; ++i)
-                load_raw_sc(nxt[i], ni, ni.first_cell + r0 + i, T, U1, labels, lse, gamma2, grad_cost);
-        };
-        fetch_next();
+        // drain role (group 1): TMEM lane quadrant q, column half hf
+        const int dw = warp - (4 + kXfWarps);
+        const int q = warp & 3, hf = (dw >> 2) & 1;
+        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
+        const uint32_t acc_empty_addr = mapa_shared(smem_u32(&bars->acc_empty), 0);
+        const int G = J >> 6;              // 32-column groups per column half
+        const int col_base = hf * (J >> 1);
+        uint8_t* buf = sDst + (dw & 7) * kDrainBufBytes;
+        uint8_t* rowp = buf + lane * 64;
+        const int sw = (lane >> 1) & 3;
+        uint32_t tl = 0;
         TileInfo ti;
         for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
             if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
+            // ---- this thread's four cells: scalars from the staged tile block into registers
             CellSc cur[4];
+            {
+                mbar_wait(smem_u32(&bars->sc_full[tl & 1]), (tl >> 1) & 1);
+                const float* sc = s_sc + (tl & 1) * 5 * kTileM;
 #pragma unroll
-            for (int i = 0; i < 4; ++i) cur[i] = finish_sc(nxt[i], V);
-            fetch_next();
-            for (int kb = 0; kb < NKB; ++kb) {
+                for (int i = 0; i < 4; ++i) {
+                    cur[i].nl2 = sc[r0 + i]; cur[i].cs = sc[kTileM + r0 + i]; cur[i].cb = sc[2 * kTileM + r0 + i];
+                    cur[i].cl = sc[3 * kTileM + r0 + i];
+                    cur[i].lab = reinterpret_cast<const int*>(sc)[4 * kTileM + r0 + i];
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&bars->sc_empty[tl & 1]));
+            }
+            for (int kb = grp; kb < NKB; kb += 2) {
+                const uint32_t n = tl * (uint32_t)NKB + kb;          // global K-block counter -> ring stage / phase
+                const uint32_t zs = n % kS, zph = (n / kS) & 1;
                 uint8_t* st = sZ + (size_t)zs * kZBytes;
                 mbar_wait(smem_u32(&bars->z_full[zs]), zph);
+                if (!EMO_DBG(1)) {
                 uint4 zr[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) zr[i] = *reinterpret_cast<const uint4*>(st + off[i]);
@@ -320,68 +402,46 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
 #pragma unroll
                 for (int i = 0; i < 4; ++i)
                     *reinterpret_cast<uint4*>(st + off[i]) = dz8<false>(zr[i], cur[i], vb, blank - vb, dummy);
+                }
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(dz_full0 + zs * 8);
-                if (++zs == kS) { zs = 0; zph ^= 1; }
             }
-        }
-    } else if (warp >= 4 + kXfWarps) {
-        // ===================== drain: dh -> bf16, tile-major (rows of the h cache, J) =====================
-        // Each warp moves its [32 cells x 32 j] blocks through a private shared-memory buffer (64B swizzle,
-        // conflict-free 16-byte stores) and one TMA store per block; the factor (1 - h^2) is applied by the
-        // reduction kernel, which reads h with the same row index.
-        const int dw = warp - (4 + kXfWarps);
-        const int q = warp & 3, hf = dw >> 2;
-        const uint32_t lane_base = (uint32_t)(q * 32) << 16;
-        const uint32_t acc_empty_addr = mapa_shared(smem_u32(&bars->acc_empty), 0);
-        const int G = J >> 6;              // 32-column groups per column half
-        const int col_base = hf * (J >> 1);
-        uint8_t* buf = sDst + dw * kDrainBufBytes;
-        uint8_t* rowp = buf + lane * 64;
-        const int sw = (lane >> 1) & 3;
-        uint32_t tl = 0;
-        TileInfo ti;
-        for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
-            if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
-            const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM + q * 32;
-            mbar_wait(smem_u32(&bars->acc_full), tl & 1);
-            tc_fence_after();
-            uint32_t ra[32], rb[32];
-            tmem_ld_32x32b_x32(tmem_base + lane_base + col_base, ra);
-            auto emit = [&](const uint32_t (&r)[32], int g) {
-                if (lane == 0) tma_store_wait_read<0>();   // the previous block has left the buffer
-                __syncwarp();
-#pragma unroll
-                for (int j = 0; j < 4; ++j)
-                    *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(
-                        pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])),
-                        pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
-                        pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
-                        pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
-                fence_proxy_async_smem();
-                __syncwarp();
-                if (lane == 0) {
-                    tma_store_2d(&tmap_d, smem_u32(buf), col_base + g * 32, row0);
-                    tma_store_commit();
-                }
-            };
-            for (int g = 0; g < G; g += 2) {
-                tmem_wait_ld();
-                if (g + 1 < G) tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + (g + 1) * 32, rb);
-                emit(ra, g);
-                if (g + 1 < G) {
+            if (grp == 1) {
+                // ---- drain: dh -> bf16, tile-major (rows of the h cache, J).  Each warp moves its
+                // [32 cells x 32 j] blocks through a private shared-memory buffer (64B swizzle, conflict-free
+                // 16-byte stores) and one TMA store per block; the factor (1 - h^2) is applied by the reduction
+                // kernel, which reads h with the same row index.
+                const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM + q * 32;
+                mbar_wait(smem_u32(&bars->acc_full), tl & 1);
+                tc_fence_after();
+                for (int g = 0; g < G; ++g) {
+                    uint32_t r[32];
+                    tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + g * 32, r);
                     tmem_wait_ld();
-                    if (g + 2 < G) tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + (g + 2) * 32, ra);
-                    emit(rb, g + 1);
+                    if (lane == 0) tma_store_wait_read<0>();   // the previous block has left the buffer
+                    __syncwarp();
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(
+                            pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])),
+                            pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
+                            pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
+                            pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+                    fence_proxy_async_smem();
+                    __syncwarp();
+                    if (lane == 0) {
+                        tma_store_2d(&tmap_d, smem_u32(buf), col_base + g * 32, row0);
+                        tma_store_commit();
+                    }
                 }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty_addr);
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive_cluster(acc_empty_addr);
             ++tl;
         }
-        if (lane == 0) tma_store_wait_all<0>();
+        if (grp == 1 && lane == 0) tma_store_wait_all<0>();
     }
 
     tc_fence_before();
@@ -401,10 +461,12 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
                  const float* __restrict__ grad_cost, int B, int T, int U1, int J, int V, int blank,
                  int num_splits,
                  float* __restrict__ d_w_out,    // (V,J), pre-zeroed
-                 float* __restrict__ d_b_out) {  // (V), pre-zeroed
+                 float* __restrict__ d_b_out,    // (V), pre-zeroed
+                 int dbg) {                      // tuning switches (bit 0: no transform math, bit 1: no MMAs)
     extern __shared__ __align__(1024) uint8_t smem[];
     constexpr int kS = kDwzZStages;
-    using Bars = ZcBarriers<kS>;
+    constexpr int kOpStages = kDwzOpStages;
+    using Bars = ZcBarriers<kS, kOpStages>;
     const int NMMA = (J + 255) / 256;
     const uint32_t op_bytes = (uint32_t)J * 64;      // this CTA's half of a [64 cells x J] h block
     uint8_t* sZ = smem;
@@ -426,7 +488,7 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kS; ++i) {
             mbar_init(smem_u32(&bars->z_full[i]), 2);               // TMA thread + scalar stager
-            mbar_init(smem_u32(&bars->dz_full[i]), 2 * kXfWarps);
+            mbar_init(smem_u32(&bars->dz_full[i]), 2 * kXfWarps);   // the 8 warps of ONE group, both CTAs
             mbar_init(smem_u32(&bars->dz_empty[i]), 1);
         }
         for (int i = 0; i < kOpStages; ++i) {
@@ -485,8 +547,27 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
         // ===================== TMA: z blocks [64 cells x 128 v] of this CTA's vocab rows =====================
         if (lane == 0) {
             uint32_t zs = 0, zph = 0;
+            // L2 prefetch cursor, kZPrefetch K blocks ahead of the loads (see the dhz kernel)
+            int pt = split - num_splits, pkh = 1, pnkh = 1, prow0 = 0;
+            auto pf_next = [&]() {
+                if (pt >= total_tiles) return;
+                if (++pkh >= pnkh) {
+                    TileInfo ni;
+                    do {
+                        pt += num_splits;
+                        if (pt >= total_tiles) return;
+                    } while (!tile_info<1>(pt, tiles_per_utt, 0, tlen, ulen, T, U1, ni));
+                    prow0 = (ni.b * tpu + ni.first_cell / kTileM) * kTileM;
+                    pkh = 0;
+                    pnkh = (ni.n_cells - ni.first_cell > 64) ? 2 : 1;
+                }
+                tma_prefetch_2d(&tmap_z, v0_cta, prow0 + pkh * 64);
+                tma_prefetch_2d(&tmap_z, v0_cta + kBlockK, prow0 + pkh * 64);
+            };
+            for (int i = 0; i < kZPrefetch; ++i) pf_next();
             for_each_kblock([&](const TileInfo& ti, int rowK, int m0) {
                 (void)ti; (void)rowK; (void)m0;
+                pf_next();
                 mbar_wait(smem_u32(&bars->dz_empty[zs]), zph ^ 1);
                 const uint32_t full = smem_u32(&bars->z_full[zs]);
                 mbar_arrive_expect_tx(full, kZBytes);
@@ -562,6 +643,7 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
                     const uint32_t b_lo = h_lo0 + slot * (op_bytes >> 4);
 #pragma unroll
                     for (int k16 = 0; k16 < 4; ++k16) {
+                        if (EMO_DBG(2)) break;
                         for (int n = 0; n < NMMA; ++n) {
                             const int Nn = min(256, J - n * 256);
                             umma_bf16_pair(tmem_base + n * 256, mk_desc(a_lo + k16 * (2048 >> 4)),
@@ -583,10 +665,13 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
                          printf("dwz issuer: total %lld clk, %d K blocks; wait dz_full %lld op_full %lld\n",
                                 clock64() - p_t0, p_n, p_dz, p_op);)
         }
-    } else if (warp >= 4 && warp < 4 + kXfWarps) {
+    } else {
         // ===================== transform: z (fp16) -> dz (bf16) in place; column sums for d_b_out ==========
+        // Two groups of 8 warps take alternate stages, so that four warps per scheduler in two different phases
+        // of the LDS -> MUFU -> pack -> STS -> fence chain keep the pipes busy.
         // thread = (64-wide vocab box, 16-byte chunk c = 8 vocab entries, 4 consecutive cells)
-        const int tt = threadIdx.x - 128;
+        const int grp = (warp - 4) >> 3;
+        const int tt = threadIdx.x - 128 - grp * 256;
         const int box = tt >> 7, t7 = tt & 127;
         const int c = t7 & 7, r0 = (t7 >> 3) * 4;
         const int vb = v0_cta + box * kBlockK + c * 8;
@@ -601,12 +686,27 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
         float colsum[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) colsum[e] = 0.f;
-        uint32_t zs = 0, zph = 0;
+        uint32_t zs = 0, zph = 0, par = 0;
+        bool any = false;
         for_each_kblock([&](const TileInfo& ti, int rowK, int m0) {
                 (void)ti; (void)rowK; (void)m0;
+            any = true;
+            const bool mine = par == (uint32_t)grp;
+            par ^= 1;
+            if (!mine) {
+                if (++zs == kS) { zs = 0; zph ^= 1; }
+                return;
+            }
             uint8_t* st = sZ + (size_t)zs * kZBytes;
             const float* sc = s_sc + zs * 5 * 64;
             mbar_wait(smem_u32(&bars->z_full[zs]), zph);
+            if (EMO_DBG(1)) {
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(dz_full0 + zs * 8);
+                if (++zs == kS) { zs = 0; zph ^= 1; }
+                return;
+            }
             uint4 zr[4];
             CellSc cs[4];
 #pragma unroll
@@ -635,11 +735,9 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
             for (int e = 0; e < 8; ++e)
                 if (vb + e < V && colsum[e] != 0.f) atomicAdd(d_b_out + vb + e, colsum[e]);
         }
-    } else if (warp >= 4 + kXfWarps) {
+        if (grp == 0) {
         // ===================== flush dW: TMEM lane = vocab row, columns = hidden units =====================
-        bool any = false;
-        for_each_kblock([&](const TileInfo&, int, int) { any = true; });
-        const int dw = warp - (4 + kXfWarps);
+        const int dw = warp - 4;
         const int q = warp & 3, hf = dw >> 2;
         const int v = v0_cta + q * 32 + lane;
         const uint32_t lane_base = (uint32_t)(q * 32) << 16;
@@ -660,6 +758,7 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
                                    __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
                 }
             }
+        }
         }
     }
 
@@ -745,12 +844,18 @@ reduce_dh_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __re
 }
 
 size_t dhz_smem_bytes(int J) {
-    return (size_t)kDhzZStages * kZBytes + (size_t)kOpStages * J * 64 + kDrainWarps * kDrainBufBytes +
-           sizeof(ZcBarriers<kDhzZStages>);
+    return (size_t)kDhzZStages * kZBytes + (size_t)kDhzOpStages * J * 64 + kDrainWarps * kDrainBufBytes +
+           sizeof(ZcBarriers<kDhzZStages, kDhzOpStages>) + 2 * 5 * kTileM * sizeof(float);
 }
 size_t dwz_smem_bytes(int J) {
-    return (size_t)kDwzZStages * kZBytes + (size_t)kOpStages * J * 64 + sizeof(ZcBarriers<kDwzZStages>) +
+    return (size_t)kDwzZStages * kZBytes + (size_t)kDwzOpStages * J * 64 + sizeof(ZcBarriers<kDwzZStages, kDwzOpStages>) +
            (size_t)kDwzZStages * 5 * 64 * sizeof(float);
+}
+
+// EMO_ZC_DEBUG=<flags>: kernel tuning switches (results are then WRONG; never set outside tools/)
+int zc_debug_flags() {
+    static const int flags = getenv("EMO_ZC_DEBUG") ? atoi(getenv("EMO_ZC_DEBUG")) : 0;
+    return flags;
 }
 
 int launch_pair_kernel(const void* fn, int ctas, size_t smem, cudaStream_t st, void** args) {
@@ -792,8 +897,9 @@ int joint_dhz_launch(const void* w_bf16, const void* hcache, const void* zcache,
     EMO_CUDA(cudaFuncSetAttribute(joint_dhz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     const int ptiles = B * ceil_div((size_t)T * U1, 2 * kTileM);
     const int pairs = max(1, min(ptiles, sm_count() / 2));
+    int dbg = zc_debug_flags();
     void* args[] = {&tmap_w, &tmap_z, &tmap_d, &labels, &tlen, &ulen, &lse, &gamma2, &grad_cost,
-                    &B, &T, &U1, &J, &V, &blank};
+                    &B, &T, &U1, &J, &V, &blank, &dbg};
     rc = launch_pair_kernel((const void*)joint_dhz_kernel, 2 * pairs, smem, st, args);
     if (rc) return rc;
     EMO_CHECK_LAUNCH("joint_dhz_kernel");
@@ -819,8 +925,9 @@ int joint_dwz_launch(const void* hcache, const void* zcache, const int* labels, 
     const int tiles = B * ceil_div((size_t)T * U1, kTileM);
     const int roles = ceil_div(V, 256);
     int splits = max(1, min((sm_count() / 2) / roles, tiles));
+    int dbg = zc_debug_flags();
     void* args[] = {&tmap_z, &tmap_h, &labels, &tlen, &ulen, &lse, &gamma2, &grad_cost,
-                    &B, &T, &U1, &J, &V, &blank, &splits, &d_w_out, &d_b_out};
+                    &B, &T, &U1, &J, &V, &blank, &splits, &d_w_out, &d_b_out, &dbg};
     rc = launch_pair_kernel((const void*)joint_dwz_kernel, 2 * roles * splits, smem, st, args);
     if (rc) return rc;
     EMO_CHECK_LAUNCH("joint_dwz_kernel");

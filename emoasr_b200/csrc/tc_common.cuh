@@ -63,6 +63,12 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst_smem, const CUtensorMap
         : "memory");
 }
 
+// 2D tile global -> L2 only (no shared-memory destination, no completion tracking)
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* m, int x, int y) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global.tile [%0, {%1, %2}];" ::"l"(m), "r"(x), "r"(y)
+                 : "memory");
+}
+
 // 2D tile store shared -> global (bulk async-group completion)
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* m, uint32_t src_smem, int x, int y) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(m),
