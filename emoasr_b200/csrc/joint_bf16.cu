@@ -21,6 +21,13 @@
 // The h tile (128 x J bf16) stays resident in shared memory for all vocab chunks of the tile.
 #include "joint_tc.cuh"
 
+// -DEMO_ZC_PROF: clock64 accounting of the MMA issuer's mbarrier waits (printf from CTA 0); tools/gpu_zcprof.sh
+#ifdef EMO_ZC_PROF
+#define EMO_PROF(...) __VA_ARGS__
+#else
+#define EMO_PROF(...)
+#endif
+
 namespace emo {
 namespace {
 
@@ -244,22 +251,28 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
             const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
             TileInfo ti;
+            EMO_PROF(long long p_acc = 0, p_a = 0, p_b = 0, p_t0 = clock64(), p_c;)
             for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
                 if (!tile_info<kCtas>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
                 for (int nc = 0; nc < NC; ++nc, ++cc) {
                     const uint32_t buf = cc & 1;
+                    EMO_PROF(p_c = clock64();)
                     if (kPair) mbar_wait_cluster(smem_u32(&bars->acc_empty[buf]), ((cc >> 1) & 1) ^ 1);
                     else       mbar_wait(smem_u32(&bars->acc_empty[buf]), ((cc >> 1) & 1) ^ 1);
+                    EMO_PROF(p_acc += clock64() - p_c;)
                     const int n = min(kChunkN, V - nc * kChunkN);
                     const uint32_t idesc = umma_idesc_bf16(kCtas * kTileM, n);
                     const uint32_t d_tmem = tmem_base + buf * kChunkN;
                     for (int kb = 0; kb < KB; ++kb) {
+                        EMO_PROF(p_c = clock64();)
                         if (nc == 0) {
                             if (kPair) mbar_wait_cluster(smem_u32(&bars->a_full[kb]), tl & 1);
                             else       mbar_wait(smem_u32(&bars->a_full[kb]), tl & 1);
                         }
+                        EMO_PROF(p_a += clock64() - p_c; p_c = clock64();)
                         if (kPair) mbar_wait_cluster(smem_u32(&bars->b_full[stage]), phase);
                         else       mbar_wait(smem_u32(&bars->b_full[stage]), phase);
+                        EMO_PROF(p_b += clock64() - p_c;)
                         tc_fence_after();
                         if (elect_one_sync()) {
                             const uint32_t a_lo = a_lo0 + kb * (kABlockBytes >> 4);
@@ -287,6 +300,9 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 }
                 ++tl;
             }
+            EMO_PROF(if (blockIdx.x == 0 && lane == 0)
+                         printf("fwd issuer: total %lld clk, %u tiles; wait acc_empty %lld a_full %lld b_full %lld\n",
+                                clock64() - p_t0, tl, p_acc, p_a, p_b);)
         }
     } else if (warp == 3) {
         // ===================== h-cache writer: TMA store of every finished h block =====================

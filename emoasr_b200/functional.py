@@ -140,21 +140,31 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=
 
 
 # ----------------------------------------------------------------------------------------------
+_CACHE_BYTES = {}
+
+
 def _joint_cache_bytes(precision, B, T, U1, J, V, dev):
     """Size of the cache the fused forward leaves for its backward.  Preferred: h (bf16) + logits (fp16),
     which lets the backward stream z instead of recomputing it (2 GEMMs instead of 6).  Falls back to the
     h-only cache (recompute path) when the logit cache would not fit comfortably in free HBM, or when
     EMO_NO_ZCACHE is set (A/B switch)."""
+    no_zc = bool(os.environ.get("EMO_NO_ZCACHE"))
+    key = (precision, B, T, U1, J, V, torch.device(dev).index, no_zc)
+    hit = _CACHE_BYTES.get(key)
+    if hit is not None:
+        return hit
     hbytes = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HCACHE, precision, B, T, U1, J, V)
-    if hbytes == 0 or os.environ.get("EMO_NO_ZCACHE"):
-        return hbytes
-    hz = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HZCACHE, precision, B, T, U1, J, V)
-    if hz == 0:
-        return hbytes
-    free, _total = torch.cuda.mem_get_info(dev)
-    # the caching allocator may hold freed blocks that can serve the request
-    reusable = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
-    return hz if hz <= 0.6 * (free + reusable) else hbytes
+    out = hbytes
+    if hbytes and not no_zc:
+        hz = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HZCACHE, precision, B, T, U1, J, V)
+        if hz:
+            free, _total = torch.cuda.mem_get_info(dev)
+            # the caching allocator may hold freed blocks that can serve the request
+            reusable = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
+            if hz <= 0.6 * (free + reusable):
+                out = hz
+    _CACHE_BYTES[key] = out          # decided once per shape: no driver query on the step path
+    return out
 
 
 class _RNNTJoint(torch.autograd.Function):

@@ -13,7 +13,7 @@ timeout 300 python bench.py --precision fp32 --steps 3 --warmup 3 --no-cpu-basel
 timeout 300 python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_${TAG}_reference_rnnt_cfg3.json 2>/dev/null; echo "reference rc=$?"
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 200 --csv --log-file gpurun_out/launches_${TAG}_rnnt_cfg3.csv python tools/run_path.py --iters 3 > /dev/null 2>&1; echo "ncu launches rc=$?"
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv --log-file gpurun_out/launches_${TAG}_ctc_cfg2.csv python tools/run_path.py --ctc --B 64 --T 374 --U 80 --V 5000 --iters 3 > /dev/null 2>&1; echo "ncu ctc rc=$?"
-timeout 900 ncu --set full --clock-control none --import-source on -k regex:"joint_|reduce_dpre|rnnt_alpha" -s 5 -c 5 -f -o gpurun_out/prof_${TAG} python tools/run_path.py --iters 2 > gpurun_out/ncu_full_${TAG}.log 2>&1; echo "ncu full rc=$?"
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:"joint_|reduce_d|rnnt_alpha" -s 5 -c 5 -f -o gpurun_out/prof_${TAG} python tools/run_path.py --iters 2 > gpurun_out/ncu_full_${TAG}.log 2>&1; echo "ncu full rc=$?"
 timeout 600 ncu --set full --clock-control none -k regex:"ctc_" -s 3 -c 3 -f -o gpurun_out/prof_${TAG}_ctc python tools/run_path.py --ctc --B 64 --T 374 --U 80 --V 5000 --iters 2 > /dev/null 2>&1; echo "ncu ctc full rc=$?"
 for f in gpurun_out/bench_${TAG}_*.json; do python - "$f" <<'PY'
 import json,sys

@@ -1,8 +1,9 @@
 #!/bin/bash
-# issuer-wait instrumentation of the z-cache backward kernels (library built with -DEMO_ZC_PROF);
-# EMO_ZC_DEBUG switches: 1 = no transform math, 2 = no MMAs, 3 = neither (pure data movement)
+# issuer-wait instrumentation of the tcgen05 kernels (library built with EMO_NVCC_EXTRA=-DEMO_ZC_PROF);
+# EMO_ZC_DEBUG switches (backward kernels): 1 = no transform math, 2 = no MMAs, 3 = neither (pure data movement)
 mkdir -p gpurun_out
-for f in 0 1 2 3; do
+for f in ${ZC_FLAGS:-0}; do
   echo "== EMO_ZC_DEBUG=$f"
-  EMO_ZC_DEBUG=$f timeout 120 python tools/run_path.py --iters 2 > gpurun_out/zcprof_$f.log 2>&1; echo "rc=$?"; grep issuer gpurun_out/zcprof_$f.log | tail -2
+  EMO_ZC_DEBUG=$f timeout 120 python tools/run_path.py --iters 2 > gpurun_out/zcprof_$f.log 2>&1; echo "rc=$?"; grep issuer gpurun_out/zcprof_$f.log | tail -3
+  EMO_NO_ZCACHE=1 EMO_ZC_DEBUG=$f timeout 120 python tools/run_path.py --iters 2 > gpurun_out/zcprof_nozc_$f.log 2>&1; echo "rc=$?"; grep issuer gpurun_out/zcprof_nozc_$f.log | tail -1
 done
