@@ -267,10 +267,18 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
             uint32_t zs = 0, zph = 0, slot = 0, ph = 0, tl = 0;
             const uint32_t z_lo0 = desc_lo(smem_u32(sZ), 16);
             const uint32_t w_lo0 = desc_lo(smem_u32(sW), kBoxBytes);
-            TileInfo ti;
+            // number of valid tiles of this pair, counted once by the whole warp: the issue loop itself then
+            // contains no global loads or divisions
+            int n_tiles = 0;
+            {
+                TileInfo ti;
+                for (int tile = tile0 + lane * tile_stride; tile < total_tiles; tile += 32 * tile_stride)
+                    n_tiles += tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti) ? 1 : 0;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) n_tiles += __shfl_xor_sync(0xffffffffu, n_tiles, o);
+            }
             EMO_PROF(long long p_acc = 0, p_dz = 0, p_op = 0, p_t0 = clock64(), p_c;)
-            for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
-                if (!tile_info<2>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
+            for (int ti_n = 0; ti_n < n_tiles; ++ti_n) {
                 EMO_PROF(p_c = clock64();)
                 mbar_wait(smem_u32(&bars->acc_empty), (tl & 1) ^ 1);
                 EMO_PROF(p_acc += clock64() - p_c;)
@@ -522,6 +530,19 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
             for (int kh = 0; kh < nkh; ++kh) body(ti, row0 + kh * 64, ti.first_cell + kh * 64);
         }
     };
+    // Number of K blocks in that sequence, computed once by a whole warp (lanes take tiles round-robin).  The MMA
+    // issuer and the transform warps only need this count: walking the tile list (an integer division and two
+    // dependent loads per tile) inside the issue loop cost ~400 clk per K block on the one thread that feeds the
+    // tensor pipe.
+    auto count_kblocks = [&]() -> int {
+        int n = 0;
+        TileInfo ti;
+        for (int tile = split + lane * num_splits; tile < total_tiles; tile += 32 * num_splits)
+            if (tile_info<1>(tile, tiles_per_utt, 0, tlen, ulen, T, U1, ti)) n += (ti.n_cells - ti.first_cell > 64) ? 2 : 1;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) n += __shfl_xor_sync(0xffffffffu, n, o);
+        return n;
+    };
 
     if (warp == 0) {
         // ===================== TMA: h blocks [64 cells x J/2] =====================
@@ -629,9 +650,9 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
             uint32_t zs = 0, zph = 0, slot = 0, ph = 0, first = 1;
             const uint32_t z_lo0 = desc_lo(smem_u32(sZ), kBoxBytes);
             const uint32_t h_lo0 = desc_lo(smem_u32(sH), kBoxBytes);
+            const int n_kb = count_kblocks();
             EMO_PROF(long long p_dz = 0, p_op = 0, p_t0 = clock64(), p_c; int p_n = 0;)
-            for_each_kblock([&](const TileInfo& ti, int rowK, int m0) {
-                (void)ti; (void)rowK; (void)m0;
+            for (int kbi = 0; kbi < n_kb; ++kbi) {
                 EMO_PROF(p_c = clock64(); ++p_n;)
                 mbar_wait(smem_u32(&bars->dz_full[zs]), zph);
                 EMO_PROF(p_dz += clock64() - p_c; p_c = clock64();)
@@ -658,7 +679,7 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
                 first = 0;
                 if (++zs == kS) { zs = 0; zph ^= 1; }
                 if (++slot == kOpStages) { slot = 0; ph ^= 1; }
-            });
+            }
             if (elect_one_sync()) umma_commit_pair(smem_u32(&bars->acc_full));
             __syncwarp();
             EMO_PROF(if (blockIdx.x == 0 && lane == 0)
@@ -687,15 +708,14 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
 #pragma unroll
         for (int e = 0; e < 8; ++e) colsum[e] = 0.f;
         uint32_t zs = 0, zph = 0, par = 0;
-        bool any = false;
-        for_each_kblock([&](const TileInfo& ti, int rowK, int m0) {
-                (void)ti; (void)rowK; (void)m0;
-            any = true;
+        const int n_kb = count_kblocks();
+        const bool any = n_kb > 0;
+        for (int kbi = 0; kbi < n_kb; ++kbi) {
             const bool mine = par == (uint32_t)grp;
             par ^= 1;
             if (!mine) {
                 if (++zs == kS) { zs = 0; zph ^= 1; }
-                return;
+                continue;
             }
             uint8_t* st = sZ + (size_t)zs * kZBytes;
             const float* sc = s_sc + zs * 5 * 64;
@@ -705,7 +725,7 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
                 __syncwarp();
                 if (lane == 0) mbar_arrive_cluster(dz_full0 + zs * 8);
                 if (++zs == kS) { zs = 0; zph ^= 1; }
-                return;
+                continue;
             }
             uint4 zr[4];
             CellSc cs[4];
@@ -723,7 +743,7 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(dz_full0 + zs * 8);
             if (++zs == kS) { zs = 0; zph ^= 1; }
-        });
+        }
         // ---- d_b_out: lanes with equal (lane & 7) hold the same vocab strip
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
