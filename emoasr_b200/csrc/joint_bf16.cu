@@ -213,8 +213,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     if (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
-    // register budget per warpgroup (x128 threads): control 40, two epilogue groups 184, producers 104
-    // -> 5120 + 2 * 23552 + 13312 = 65536
+    // register budget per warpgroup (x128 threads): control 40, two epilogue groups 152, producers 152 (three units
+    // of gather loads in flight) -> 5120 + 2 * 19456 + 19456 = 63488 of 65536 (an exact fit deadlocks)
     if (warp < 4) {
     reg_dec<40>();
     if (warp == 0) {
@@ -326,7 +326,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         }
     }
     } else if (warp < 12) {
-        reg_inc<184>();
+        reg_inc<152>();
         // ===================== epilogue: online LSE over vocab chunks =====================
         // Two warps per TMEM lane quadrant: warp (q, hf) owns columns [128 hf, 128 hf + 128) of every 256-wide
         // chunk for the rows of quadrant q.  The two partial (max, sum, blank, label) states of a row are
@@ -406,14 +406,14 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         }
         if (kStoreZ && lane == 0) tma_store_wait_all<0>();
     } else {
-        reg_dec<104>();
+        reg_inc<152>();
         // ===================== A producers =====================
         const int pw = warp - 12;      // 4 producer warps, 32 rows each, produced as two 16-row halves
         const int c = lane & 7;        // 16-byte chunk (8 hidden units) inside the 64-wide K block
         const int rsub = lane >> 3;    // 4 rows per warp pass
-        // Flattened (tile, K block, half) sequence with TWO units of loads in flight: the loads of unit n+2
-        // are issued right after unit n has been written, so an L2 round trip is hidden behind two
-        // unit periods (and, across tiles, behind the wait for the MMAs to release the slot).
+        // Flattened (tile, K block, half) sequence with THREE units of loads in flight: the loads of unit n+3
+        // are issued right after unit n has been written, so an L2 round trip (600-1500 clk under load) is hidden
+        // behind three unit periods (and, across tiles, behind the wait for the MMAs to release the slot).
         int ltile = tile0 - tile_stride, lunit = 2 * KB;   // load cursor; unit = 2 * kb + half
         uint32_t eoff[8], doff[8];
         auto issue = [&](uint4 (&re)[4], uint4 (&rd)[4]) -> bool {
@@ -463,15 +463,19 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             }
             if (++wunit == 2u * (uint32_t)KB) { wunit = 0; ++wtl; }
         };
-        uint4 e0[4], d0[4], e1[4], d1[4];
+        uint4 e0[4], d0[4], e1[4], d1[4], e2[4], d2[4];
         bool v0 = issue(e0, d0);
         bool v1 = v0 && issue(e1, d1);
+        bool v2 = v1 && issue(e2, d2);
         while (v0) {
             work(e0, d0);
-            v0 = v1 && issue(e0, d0);
+            v0 = v2 && issue(e0, d0);
             if (!v1) break;
             work(e1, d1);
             v1 = v0 && issue(e1, d1);
+            if (!v2) break;
+            work(e2, d2);
+            v2 = v1 && issue(e2, d2);
         }
     }
 
