@@ -83,8 +83,8 @@ __device__ __forceinline__ void lse_group(const uint32_t (&r)[32], const float* 
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             *reinterpret_cast<uint4*>(rowp + ((i ^ ((lane >> 1) & 3)) << 4)) =
-                make_uint4(pack_f16x2(x[8 * i], x[8 * i + 1]), pack_f16x2(x[8 * i + 2], x[8 * i + 3]),
-                           pack_f16x2(x[8 * i + 4], x[8 * i + 5]), pack_f16x2(x[8 * i + 6], x[8 * i + 7]));
+                make_uint4(pack_f16x2_sat(x[8 * i], x[8 * i + 1]), pack_f16x2_sat(x[8 * i + 2], x[8 * i + 3]),
+                           pack_f16x2_sat(x[8 * i + 4], x[8 * i + 5]), pack_f16x2_sat(x[8 * i + 6], x[8 * i + 7]));
         fence_proxy_async_smem();
         __syncwarp();
         if (lane == 0) {
