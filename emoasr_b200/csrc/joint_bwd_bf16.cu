@@ -1194,10 +1194,6 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
                 EMO_WORKSPACE_TOO_SMALL, "joint_bwd(bf16): workspace too small");
     EMO_REQUIRE(((uintptr_t)ws & 255) == 0 && ((uintptr_t)w_out & 15) == 0 && ((uintptr_t)d_w_out & 15) == 0,
                 EMO_BAD_ARG, "joint_bwd(bf16): pointers must be 16-byte (workspace 256-byte) aligned");
-    const int KB = J / kBlockK;
-    const int NCH = ceil_div(V, kBwdChunk), NPART = ceil_div(KB, kPartBlocks);
-    EMO_REQUIRE(NCH * NPART <= sm_count() * 4, EMO_UNSUPPORTED_SHAPE,
-                "joint_bwd(bf16): vocabulary %d too large for the dW role grid", V);
     __nv_bfloat16* w_bf16 = reinterpret_cast<__nv_bfloat16*>(ws);
     __nv_bfloat16* dpre = reinterpret_cast<__nv_bfloat16*>(
         (char*)ws + align_up((size_t)V * J * sizeof(__nv_bfloat16), 256));
@@ -1219,6 +1215,11 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
                                 d_w_out, d_b_out, st);
     }
 
+    // ---- recompute path (h cache only)
+    const int KB = J / kBlockK;
+    const int NCH = ceil_div(V, kBwdChunk), NPART = ceil_div(KB, kPartBlocks);
+    EMO_REQUIRE(NCH * NPART <= sm_count() * 4, EMO_UNSUPPORTED_SHAPE,
+                "joint_bwd(bf16): vocabulary %d too large for the dW role grid", V);
     CUtensorMap tmap_wz, tmap_wd, tmap_h;
     rc = make_tmap_bf16_2d(&tmap_wz, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, 64);
     if (rc) return rc;

@@ -79,39 +79,6 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restr
     }
 }
 
-// A-operand producer shared by the forward and backward kernels: this warp's 32 rows of the
-// 128-row tile, K block kb.  h = tanh(enc + dec) -> bf16 -> canonical K-major SW128 layout
-// (16-byte chunk index XOR (row mod 8)).
-__device__ __forceinline__ void produce_h_block(const float* __restrict__ enc,
-                                                const float* __restrict__ dec,
-                                                const uint32_t (&eoff)[8], const uint32_t (&doff)[8],
-                                                int kb, int pw, int rsub, int c, uint8_t* blk) {
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        float4 e0[4], e1[4], d0[4], d1[4];
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const float* ep = enc + eoff[half * 4 + p] + kb * kBlockK;
-            const float* dp = dec + doff[half * 4 + p] + kb * kBlockK;
-            e0[p] = __ldg(reinterpret_cast<const float4*>(ep));
-            e1[p] = __ldg(reinterpret_cast<const float4*>(ep) + 1);
-            d0[p] = __ldg(reinterpret_cast<const float4*>(dp));
-            d1[p] = __ldg(reinterpret_cast<const float4*>(dp) + 1);
-        }
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            const int row = pw * 32 + (half * 4 + p) * 4 + rsub;
-            uint4 o;
-            o.x = pack_bf16x2(tanh_approx(e0[p].x + d0[p].x), tanh_approx(e0[p].y + d0[p].y));
-            o.y = pack_bf16x2(tanh_approx(e0[p].z + d0[p].z), tanh_approx(e0[p].w + d0[p].w));
-            o.z = pack_bf16x2(tanh_approx(e1[p].x + d1[p].x), tanh_approx(e1[p].y + d1[p].y));
-            o.w = pack_bf16x2(tanh_approx(e1[p].z + d1[p].z), tanh_approx(e1[p].w + d1[p].w));
-            uint8_t* dst = blk + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
-            *reinterpret_cast<uint4*>(dst) = o;
-        }
-    }
-}
-
 // x[d] for a per-thread d in [0,32) without dynamic register indexing: five select levels
 __device__ __forceinline__ float mux32(const float (&x)[32], int d) {
     float a[16], b[8], c[4], e[2];
