@@ -38,10 +38,10 @@ namespace emo {
 namespace {
 
 constexpr int kZcThreads = 640;
-constexpr int kDhzZStages = 6;
+constexpr int kDhzZStages = 5;
 constexpr int kDhzOpStages = 3;                // w_out blocks come from L2: three in flight are enough
 constexpr int kZPrefetch = 8;                  // z K blocks pulled into L2 ahead of the shared-memory ring
-constexpr int kDrainBufBytes = 2048;           // [32 cells x 32 j] bf16, 64B swizzle; two per drain warp
+constexpr int kDrainBufBytes = 4096;           // per drain warp: [32 cells x 64 j] bf16, 128B swizzle
 constexpr int kDwzZStages = 5;
 constexpr int kDwzOpStages = 4;
 constexpr int kZBytes = 16384;                 // one z / dz stage: 128 x 64 (dhz) or 2 x [64 x 64] (dWz) 2-byte elements
@@ -145,7 +145,7 @@ struct __align__(16) ZcBarriers {
 __global__ void __launch_bounds__(kZcThreads, 1)
 joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,J), box [64 j x 64 v]
                  const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (rows,V), box [64 v x 128 cells]
-                 const __grid_constant__ CUtensorMap tmap_d,   // dh out, bf16 (rows,J), box [32 j x 32 cells], 64B swizzle
+                 const __grid_constant__ CUtensorMap tmap_d,   // dh out, bf16 (rows,J), box [64 j x 32 cells], 128B swizzle
                  const int* __restrict__ labels,
                  const int* __restrict__ tlen, const int* __restrict__ ulen, const float* __restrict__ lse,
                  const float* __restrict__ gamma2, const float* __restrict__ grad_cost, int B, int T, int U1,
@@ -377,8 +377,8 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
         const int G = J >> 6;              // 32-column groups per column half
         const int col_base = hf * (J >> 1);
         uint8_t* buf = sDst + (dw & 7) * kDrainBufBytes;
-        uint8_t* rowp = buf + lane * 64;
-        const int sw = (lane >> 1) & 3;
+        uint8_t* rowp = buf + lane * 128;
+        const int sw = lane & 7;
         uint32_t tl = 0;
         TileInfo ti;
         for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
@@ -417,25 +417,32 @@ joint_dhz_kernel(const __grid_constant__ CUtensorMap tmap_w,   // w_out bf16 (V,
             }
             if (grp == 1) {
                 // ---- drain: dh -> bf16, tile-major (rows of the h cache, J).  Each warp moves its
-                // [32 cells x 32 j] blocks through a private shared-memory buffer (64B swizzle, conflict-free
+                // [32 cells x 64 j] blocks through a private shared-memory buffer (128B swizzle, conflict-free
                 // 16-byte stores) and one TMA store per block; the factor (1 - h^2) is applied by the reduction
                 // kernel, which reads h with the same row index.
                 const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM + q * 32;
                 mbar_wait(smem_u32(&bars->acc_full), tl & 1);
                 tc_fence_after();
-                for (int g = 0; g < G; ++g) {
-                    uint32_t r[32];
-                    tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + g * 32, r);
+                for (int g = 0; g < G; g += 2) {     // two 32-column groups = one 128-byte row piece per TMA store
+                    uint32_t ra[32], rb[32];
+                    tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + g * 32, ra);
+                    tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + g * 32 + 32, rb);
                     tmem_wait_ld();
                     if (lane == 0) tma_store_wait_read<0>();   // the previous block has left the buffer
                     __syncwarp();
 #pragma unroll
-                    for (int j = 0; j < 4; ++j)
+                    for (int j = 0; j < 4; ++j) {
                         *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(
-                            pack_bf16x2(__uint_as_float(r[8 * j]), __uint_as_float(r[8 * j + 1])),
-                            pack_bf16x2(__uint_as_float(r[8 * j + 2]), __uint_as_float(r[8 * j + 3])),
-                            pack_bf16x2(__uint_as_float(r[8 * j + 4]), __uint_as_float(r[8 * j + 5])),
-                            pack_bf16x2(__uint_as_float(r[8 * j + 6]), __uint_as_float(r[8 * j + 7])));
+                            pack_bf16x2(__uint_as_float(ra[8 * j]), __uint_as_float(ra[8 * j + 1])),
+                            pack_bf16x2(__uint_as_float(ra[8 * j + 2]), __uint_as_float(ra[8 * j + 3])),
+                            pack_bf16x2(__uint_as_float(ra[8 * j + 4]), __uint_as_float(ra[8 * j + 5])),
+                            pack_bf16x2(__uint_as_float(ra[8 * j + 6]), __uint_as_float(ra[8 * j + 7])));
+                        *reinterpret_cast<uint4*>(rowp + (((4 + j) ^ sw) << 4)) = make_uint4(
+                            pack_bf16x2(__uint_as_float(rb[8 * j]), __uint_as_float(rb[8 * j + 1])),
+                            pack_bf16x2(__uint_as_float(rb[8 * j + 2]), __uint_as_float(rb[8 * j + 3])),
+                            pack_bf16x2(__uint_as_float(rb[8 * j + 4]), __uint_as_float(rb[8 * j + 5])),
+                            pack_bf16x2(__uint_as_float(rb[8 * j + 6]), __uint_as_float(rb[8 * j + 7])));
+                    }
                     fence_proxy_async_smem();
                     __syncwarp();
                     if (lane == 0) {
@@ -910,7 +917,7 @@ int joint_dhz_launch(const void* w_bf16, const void* hcache, const void* zcache,
     if (rc) return rc;
     rc = make_tmap_bf16_2d(&tmap_z, zcache, (uint64_t)V, rows, kBlockK, kTileM);
     if (rc) return rc;
-    rc = make_tmap_bf16_2d(&tmap_d, dh_ws, (uint64_t)J, rows, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+    rc = make_tmap_bf16_2d(&tmap_d, dh_ws, (uint64_t)J, rows, 64, 32);   // 128B swizzle
     if (rc) return rc;
     const size_t smem = dhz_smem_bytes(J);
     EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_bwd(bf16): shared memory (dhz)");
