@@ -9,14 +9,14 @@
 // from (t,u-1) is handed over by the neighbouring thread: inside a warp with one shuffle, across
 // warp boundaries through a double-buffered shared-memory slot.  The per-cell {blank,label}
 // log-prob pair is one 8-byte load that does not depend on the recursion, so it is prefetched
-// kPrefetch diagonals ahead in registers.
+// one block of kPrefetch diagonals ahead in registers.
 #include "common.cuh"
 
 namespace emo {
 
 namespace {
 
-constexpr int kPrefetch = 4;
+constexpr int kPrefetch = 8;
 
 template <bool kBackward>
 __device__ __forceinline__ void wavefront(const float2* __restrict__ lp2_b, int T_b, int U_b,
@@ -40,20 +40,25 @@ __device__ __forceinline__ void wavefront(const float2* __restrict__ lp2_b, int 
         return __ldg(&lp2_b[(size_t)t * U1 + u_ld]);
     };
 
-    float2 ring[kPrefetch];
+    // The pairs of the NEXT block of kPrefetch diagonals are loaded at the top of the current block (kPrefetch
+    // independent loads back to back), so every load has a whole block of diagonals to land.  (A per-diagonal
+    // ring "load diagonal i + kPrefetch while computing diagonal i" was scheduled by the compiler right in front
+    // of its use: a quarter of the kernel's stall samples sat on the load's scoreboard.)
+    float2 cur[kPrefetch], nxt[kPrefetch];
 #pragma unroll
-    for (int k = 0; k < kPrefetch; ++k) ring[k] = load(k);
+    for (int k = 0; k < kPrefetch; ++k) cur[k] = load(k);
 
     float keep = kNegInf;  // forward: alpha(t-1,u)+blank(t-1,u); backward: beta(t+1,u)
     float give = kNegInf;  // forward: alpha(t,u)+label(t,u) for thread u+1; backward: beta(t,u) for u-1
 
     for (int i0 = 0; i0 < n_diag; i0 += kPrefetch) {
 #pragma unroll
+        for (int k = 0; k < kPrefetch; ++k) nxt[k] = load(i0 + kPrefetch + k);
+#pragma unroll
         for (int k = 0; k < kPrefetch; ++k) {
             const int i = i0 + k;
             if (i >= n_diag) break;  // uniform across the CTA
-            const float2 lp = ring[k];
-            ring[k] = load(i + kPrefetch);
+            const float2 lp = cur[k];
             const int t = cell_t(i);
             const bool active = col_valid && t >= 0 && t < T_b;
 
@@ -92,6 +97,8 @@ __device__ __forceinline__ void wavefront(const float2* __restrict__ lp2_b, int 
             if (kBackward && lane == 0) edge[i & 1][warp] = give;
             __syncthreads();
         }
+#pragma unroll
+        for (int k = 0; k < kPrefetch; ++k) cur[k] = nxt[k];
     }
 }
 
