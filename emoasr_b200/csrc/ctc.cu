@@ -79,48 +79,9 @@ ctc_row_lse_kernel(const float* __restrict__ logits, const long long* __restrict
     const int lane = threadIdx.x & 31;
     const int warp_global = blockIdx.x * kLseWarps + (threadIdx.x >> 5);
     const int warp_stride = gridDim.x * kLseWarps;
-    for (int r = warp_global; r < rows; r += warp_stride) {
-        const int b = r / T, t = r - b * T;
-        if (t >= tlen[b]) {
-            if (lane == 0) lse[r] = 0.f;
-            continue;  // warp-uniform
-        }
-        const float* row = logits + (size_t)r * V;
-        float m = kNegInf, s = 0.f;
-        if ((V & 3) == 0) {
-            const float4* row4 = reinterpret_cast<const float4*>(row);
-            const int n4 = V >> 2;
-            for (int base = 0; base < n4; base += kRowVec * 32) {
-                float4 x[kRowVec];
-#pragma unroll
-                for (int k = 0; k < kRowVec; ++k) {
-                    const int i = base + k * 32 + lane;
-                    x[k] = i < n4 ? __ldg(row4 + i) : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
-                }
-                float mx = kNegInf;
-#pragma unroll
-                for (int k = 0; k < kRowVec; ++k)
-                    mx = fmaxf(mx, fmaxf(fmaxf(x[k].x, x[k].y), fmaxf(x[k].z, x[k].w)));
-                const float mn = fmaxf(m, mx);
-                if (mn > kNegInf) {
-                    float acc = 0.f;
-#pragma unroll
-                    for (int k = 0; k < kRowVec; ++k)
-                        acc += __expf(x[k].x - mn) + __expf(x[k].y - mn) + __expf(x[k].z - mn) + __expf(x[k].w - mn);
-                    s = s * __expf(m - mn) + acc;
-                    m = mn;
-                }
-            }
-        } else {
-            for (int i = lane; i < V; i += 32) {
-                const float x = __ldg(row + i);
-                const float mn = fmaxf(m, x);
-                if (mn > kNegInf) {
-                    s = s * __expf(m - mn) + __expf(x - mn);
-                    m = mn;
-                }
-            }
-        }
+    // end of a row: warp-reduce the online (max, sum exp), write lse, gather the emissions of the
+    // blank-extended label sequence (the row is L2-hot)
+    auto finish_row = [&](int r, int b, float m, float s) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             const float m2 = __shfl_xor_sync(0xffffffffu, m, o);
@@ -129,7 +90,7 @@ ctc_row_lse_kernel(const float* __restrict__ logits, const long long* __restrict
         }
         const float l = m + logf(s);
         if (lane == 0) lse[r] = l;
-        // gather the emissions of the blank-extended label sequence
+        const float* row = logits + (size_t)r * V;
         const long long U_bl = ulen[b];
         const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
         const int S_b = 2 * U_b + 1;
@@ -139,6 +100,92 @@ ctc_row_lse_kernel(const float* __restrict__ logits, const long long* __restrict
             lp_a[(size_t)r * S + st] = v;
             if (lp_b) lp_b[(size_t)r * S + st] = v;
         }
+    };
+    if ((V & 3) != 0) {
+        // scalar path (vocabulary not a multiple of 4)
+        for (int r = warp_global; r < rows; r += warp_stride) {
+            const int b = r / T, t = r - b * T;
+            if (t >= tlen[b]) {
+                if (lane == 0) lse[r] = 0.f;
+                continue;  // warp-uniform
+            }
+            const float* row = logits + (size_t)r * V;
+            float m = kNegInf, s = 0.f;
+            for (int i = lane; i < V; i += 32) {
+                const float x = __ldg(row + i);
+                const float mn = fmaxf(m, x);
+                if (mn > kNegInf) {
+                    s = s * __expf(m - mn) + __expf(x - mn);
+                    m = mn;
+                }
+            }
+            finish_row(r, b, m, s);
+        }
+        return;
+    }
+    // Vector path.  The (row, slab) sequence of this warp is one software pipeline: the loads of the NEXT slab --
+    // which may be the first slab of the next row -- are issued before the current slab is consumed, so the
+    // reduction / emission gather that ends a row runs with a slab of the next row in flight instead of an idle
+    // memory pipe.
+    const int n4 = V >> 2;
+    int nr = warp_global - warp_stride, nbase = n4;   // load cursor (row, first float4 of the slab)
+    auto advance = [&]() -> bool {                    // moves the cursor to the next slab; false at the end
+        nbase += kRowVec * 32;
+        while (nbase >= n4) {
+            nr += warp_stride;
+            if (nr >= rows) return false;
+            const int bb = nr / T;
+            if (nr - bb * T >= tlen[bb]) {            // padded frame: no log-probs needed
+                if (lane == 0) lse[nr] = 0.f;
+                continue;
+            }
+            nbase = 0;
+        }
+        return true;
+    };
+    auto issue = [&](float4 (&x)[kRowVec]) {
+        const float4* row4 = reinterpret_cast<const float4*>(logits + (size_t)nr * V);
+#pragma unroll
+        for (int k = 0; k < kRowVec; ++k) {
+            const int i = nbase + k * 32 + lane;
+            x[k] = i < n4 ? __ldg(row4 + i) : make_float4(kNegInf, kNegInf, kNegInf, kNegInf);
+        }
+    };
+    float4 xa[kRowVec], xb[kRowVec];
+    float m = kNegInf, s = 0.f;
+    auto consume = [&](const float4 (&x)[kRowVec], int r, int base) {
+        float mx = kNegInf;
+#pragma unroll
+        for (int k = 0; k < kRowVec; ++k)
+            mx = fmaxf(mx, fmaxf(fmaxf(x[k].x, x[k].y), fmaxf(x[k].z, x[k].w)));
+        const float mn = fmaxf(m, mx);
+        if (mn > kNegInf) {
+            float acc = 0.f;
+#pragma unroll
+            for (int k = 0; k < kRowVec; ++k)
+                acc += __expf(x[k].x - mn) + __expf(x[k].y - mn) + __expf(x[k].z - mn) + __expf(x[k].w - mn);
+            s = s * __expf(m - mn) + acc;
+            m = mn;
+        }
+        if (base + kRowVec * 32 >= n4) {   // last slab of the row
+            finish_row(r, r / T, m, s);
+            m = kNegInf;
+            s = 0.f;
+        }
+    };
+    bool va = advance();
+    int ra = nr, ba = nbase;
+    if (va) issue(xa);
+    while (va) {
+        const bool vb = advance();
+        const int rb = nr, bb = nbase;
+        if (vb) issue(xb);
+        consume(xa, ra, ba);
+        if (!vb) break;
+        va = advance();
+        ra = nr; ba = nbase;
+        if (va) issue(xa);
+        consume(xb, rb, bb);
     }
 }
 
