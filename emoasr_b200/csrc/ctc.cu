@@ -351,6 +351,119 @@ ctc_grad_kernel(const float* __restrict__ logits, const long long* __restrict__ 
     }
 }
 
+// Gradient, one WARP per row, no block barriers and no vocabulary-sized accumulator (V % 4 == 0):
+//   1. stream the row once:  grad[v] = g * softmax(z)[v]   (float4 loads / stores; the (row, slab) sequence of the
+//      warp is one software pipeline, as in ctc_row_lse_kernel: the next slab -- possibly of the next row -- is in
+//      flight while the current one is consumed and while a finished row is patched)
+//   2. patch the <= S_b entries that carry a posterior:  grad[l'_s] -= g * occ_t(s)   with atomics on the lines
+//      just written (L2 hits); the U_b + 1 blank states are summed in the warp first.
+// occ_t(s) = exp(alpha_t(s) + beta_t(s) - lp_t(l'_s) - ll) is formed here from the two lattices.
+__global__ void __launch_bounds__(kLseWarps * 32)
+ctc_grad_warp_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
+                     const long long* __restrict__ tlen, const long long* __restrict__ ulen,
+                     const float* __restrict__ lse, const float* __restrict__ alpha_ws,
+                     const float* __restrict__ beta_ws, const float* __restrict__ grad_nll, int B, int T,
+                     int V, int Umax, int blank, float* __restrict__ grad) {
+    const int rows = B * T;
+    const int S = 2 * Umax + 1;
+    const int lane = threadIdx.x & 31;
+    const int warp_global = blockIdx.x * kLseWarps + (threadIdx.x >> 5);
+    const int warp_stride = gridDim.x * kLseWarps;
+    const int n4 = V >> 2;
+    struct Meta { int r; float row_lse, g, l; };
+    int nr = warp_global - warp_stride, nbase = n4;   // load cursor (row, first float4 of the slab)
+    Meta nmeta = {0, 0.f, 0.f, 0.f};
+    auto advance = [&]() -> bool {
+        nbase += kRowVec * 32;
+        while (nbase >= n4) {
+            nr += warp_stride;
+            if (nr >= rows) return false;
+            const int b = nr / T, t = nr - b * T;
+            const long long T_bl = tlen[b], U_bl = ulen[b];
+            const int T_b = (int)(T_bl < 1 ? 1 : (T_bl > T ? T : T_bl));
+            const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
+            const int S_b = 2 * U_b + 1;
+            // feasibility of the utterance from the last alphas (same test as the forward kernel)
+            const float* alast = alpha_ws + ((size_t)b * T + (T_b - 1)) * S;
+            const float l = log_add_exp(alast[S_b - 1], S_b > 1 ? alast[S_b - 2] : kNegInf);
+            const bool feasible = l > kNegInf && l == l && l < INFINITY;
+            if (t >= T_b || !feasible) {  // warp-uniform: padded frame or infeasible utterance, zero gradient
+                float4* g4 = reinterpret_cast<float4*>(grad + (size_t)nr * V);
+                for (int i = lane; i < n4; i += 32) g4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                continue;
+            }
+            nmeta.r = nr; nmeta.row_lse = lse[nr]; nmeta.g = grad_nll[b]; nmeta.l = l;
+            nbase = 0;
+        }
+        return true;
+    };
+    auto issue = [&](float4 (&x)[kRowVec]) {
+        const float4* row4 = reinterpret_cast<const float4*>(logits + (size_t)nr * V);
+#pragma unroll
+        for (int k = 0; k < kRowVec; ++k) {
+            const int i = nbase + k * 32 + lane;
+            if (i < n4) x[k] = __ldg(row4 + i);
+        }
+    };
+    auto consume = [&](const float4 (&x)[kRowVec], const Meta& mt, int base) {
+        float4* g4 = reinterpret_cast<float4*>(grad + (size_t)mt.r * V);
+#pragma unroll
+        for (int k = 0; k < kRowVec; ++k) {
+            const int i = base + k * 32 + lane;
+            if (i < n4) {
+                float4 o;
+                o.x = mt.g * expf(x[k].x - mt.row_lse);
+                o.y = mt.g * expf(x[k].y - mt.row_lse);
+                o.z = mt.g * expf(x[k].z - mt.row_lse);
+                o.w = mt.g * expf(x[k].w - mt.row_lse);
+                g4[i] = o;
+            }
+        }
+        if (base + kRowVec * 32 < n4) return;
+        // ---- last slab of the row: patch the entries of the blank-extended label sequence
+        __syncwarp();   // the row is written (memory ordering among the lanes) before it is patched
+        const int b = mt.r / T;
+        const long long U_bl = ulen[b];
+        const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
+        const int S_b = 2 * U_b + 1;
+        const long long* y = labels + (size_t)b * Umax;
+        const float* row = logits + (size_t)mt.r * V;
+        const float* al = alpha_ws + (size_t)mt.r * S;
+        const float* be = beta_ws + (size_t)mt.r * S;
+        float* grow = grad + (size_t)mt.r * V;
+        float blank_occ = 0.f;
+        for (int st = lane; st < S_b; st += 32) {
+            const int lab = ext_state(y, st, S_b, blank, V).label;
+            const float a = al[st], bt = be[st];
+            if (a > kNegInf && bt > kNegInf) {
+                const float lp = __ldg(row + lab) - mt.row_lse;
+                const float occ = expf(a + bt - lp - mt.l);
+                if (lab == blank) blank_occ += occ;
+                else atomicAdd(grow + lab, -mt.g * occ);
+            }
+        }
+        blank_occ = warp_sum(blank_occ);
+        if (lane == 0 && blank_occ != 0.f) atomicAdd(grow + blank, -mt.g * blank_occ);
+    };
+    float4 xa[kRowVec], xb[kRowVec];
+    bool va = advance();
+    Meta ma = nmeta;
+    int ba = nbase;
+    if (va) issue(xa);
+    while (va) {
+        const bool vb = advance();
+        const Meta mb = nmeta;
+        const int bb = nbase;
+        if (vb) issue(xb);
+        consume(xa, ma, ba);
+        if (!vb) break;
+        va = advance();
+        ma = nmeta; ba = nbase;
+        if (va) issue(xa);
+        consume(xb, mb, bb);
+    }
+}
+
 // lp_ext gather alone (backward called without a forward that staged beta)
 __global__ void ctc_gather_kernel(const float* __restrict__ logits, const long long* __restrict__ labels,
                                   const long long* __restrict__ tlen, const long long* __restrict__ ulen,
@@ -431,6 +544,13 @@ extern "C" int emo_ctc_bwd(const float* logits, const long long* labels, const l
         ctc_lattice_kernel<<<dim3(B, 1), threads, 0, st>>>(labels, tlen, ulen, T, V, Umax, blank, zero_infinity, 1,
                                                            nullptr, beta_ws, nullptr);
         EMO_CHECK_LAUNCH("ctc_lattice_kernel<beta>");
+    }
+    if ((V & 3) == 0) {   // warp-per-row streaming version
+        const int rows = B * T;
+        ctc_grad_warp_kernel<<<min(ceil_div(rows, kLseWarps), sm_count() * 8), kLseWarps * 32, 0, st>>>(
+            logits, labels, tlen, ulen, lse, alpha_ws, beta_ws, grad_nll, B, T, V, Umax, blank, grad_logits);
+        EMO_CHECK_LAUNCH("ctc_grad_warp_kernel");
+        return EMO_OK;
     }
     size_t smem = (size_t)V * sizeof(float);
     if (smem > 48 * 1024)
