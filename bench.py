@@ -340,17 +340,61 @@ def run_ours_ctc(args, w, rank, world, dev):
 
 # ------------------------------------------------------------------------------------------------
 class ClockMonitor:
-    """Samples nvidia-smi clocks / throttle reasons during the timed region."""
+    """Samples SM clocks / throttle reasons DURING the timed region: NVML in a thread (a query takes well under a
+    millisecond, so even a 50 ms region gets several samples); `nvidia-smi -lms` as the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
     def __init__(self, index):
         self.index = index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []       # (sm_mhz, reasons bitmask)
+        self.max_mhz = None
+        self._stop = threading.Event()
+
+    def _nvml_loop(self, handle):
+        nv = self.nvml
+        while not self._stop.is_set():
+            try:
+                mhz = nv.nvmlDeviceGetClockInfo(handle, nv.NVML_CLOCK_SM)
+                try:
+                    bits = nv.nvmlDeviceGetCurrentClocksEventReasons(handle)
+                except Exception:
+                    bits = nv.nvmlDeviceGetCurrentClocksThrottleReasons(handle)
+                self.samples.append((float(mhz), int(bits)))
+            except Exception:
+                pass
+            time.sleep(0.004)
 
     def start(self):
+        try:
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: map torch's (CUDA_VISIBLE_DEVICES-relative) index through the UUID
+            uuid = torch.cuda.get_device_properties(self.index).uuid
+            handle = None
+            for cand in (f"GPU-{uuid}", str(uuid)):
+                try:
+                    handle = nv.nvmlDeviceGetHandleByUUID(cand.encode() if isinstance(cand, str) else cand)
+                    break
+                except Exception:
+                    continue
+            if handle is None:
+                handle = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.max_mhz = float(nv.nvmlDeviceGetMaxClockInfo(handle, nv.NVML_CLOCK_SM))
+            self.nvml = nv
+            # the launching thread holds the GIL almost continuously: let the sampler in every 0.5 ms
+            self._switch = sys.getswitchinterval()
+            sys.setswitchinterval(0.0005)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(handle,), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
@@ -365,6 +409,19 @@ class ClockMonitor:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self._stop.set()
+            self.thread.join(timeout=1)
+            sys.setswitchinterval(self._switch)
+            nv = self.nvml
+            masks = {"hw_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+            sm = [m for m, _ in self.samples]
+            reasons = sorted(n for n, bit in masks.items() if any(b & bit for _, b in self.samples))
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -374,7 +431,6 @@ class ClockMonitor:
         except subprocess.TimeoutExpired:
             self.proc.kill()
         sm, mx, reasons = [], None, set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.lines:
             f = [x.strip() for x in ln.split(",")]
             if len(f) < 7:
@@ -383,11 +439,11 @@ class ClockMonitor:
                 sm.append(float(f[0])); mx = float(f[1])
             except ValueError:
                 continue
-            for n, v in zip(names, f[3:7]):
+            for n, v in zip(self.NAMES, f[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "source": "nvidia-smi"}
 
 
 # ------------------------------------------------------------------------------------------------
