@@ -302,6 +302,7 @@ BF16_SHAPES = [
     (2, 20, 12, 288, 128),    # partial last vocab chunk (TMA out-of-bounds rows), 2 K blocks
     (3, 40, 15, 1024, 512),   # cfg-3 vocabulary / joint width, several tiles per CTA
     (2, 150, 30, 512, 256),   # many tiles
+    (1, 24, 10, 4096, 512),   # cfg-4 vocabulary: 16 vocab roles in the dW kernel, 64 K blocks per tile in dh
 ]
 
 
