@@ -451,9 +451,12 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             return true;
         };
         uint32_t wunit = 0, wtl = 0;                 // work cursor: same sequence, 2 * KB units per valid tile
+        EMO_PROF(long long q_wait = 0, q_work = 0, q_t0 = clock64(), q_c;)
         auto work = [&](const uint4 (&re)[4], const uint4 (&rd)[4]) {
             const uint32_t wkb = wunit >> 1, half = wunit & 1;
+            EMO_PROF(q_c = clock64();)
             if (!half) mbar_wait(smem_u32(&bars->a_empty[wkb]), (wtl & 1) ^ 1);
+            EMO_PROF(q_wait += clock64() - q_c; q_c = clock64();)
             produce_h_block16(re, rd, 2 * pw + (int)half, rsub, c, sA + (size_t)wkb * kABlockBytes);
             if (half) {
                 fence_proxy_async_smem();
@@ -461,6 +464,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 if (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->a_full[wkb]), 0));
                 else       mbar_arrive(smem_u32(&bars->a_full[wkb]));
             }
+            EMO_PROF(q_work += clock64() - q_c;)
             if (++wunit == 2u * (uint32_t)KB) { wunit = 0; ++wtl; }
         };
         uint4 e0[4], d0[4], e1[4], d1[4], e2[4], d2[4];
@@ -477,6 +481,10 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             work(e2, d2);
             v2 = v1 && issue(e2, d2);
         }
+        EMO_PROF(if (blockIdx.x == 0 && threadIdx.x == 12 * 32)
+                     printf("fwd producer warp 12: total %lld clk, %u tiles; wait a_empty %lld, produce (incl. load stalls) "
+                            "%lld, rest (issue) %lld\n", clock64() - q_t0, wtl, q_wait, q_work,
+                            clock64() - q_t0 - q_wait - q_work);)
     }
 
     tc_fence_before();
