@@ -149,14 +149,17 @@ def run_ours_rnnt(args, w, rank, world, dev):
     mods = torch.nn.ModuleList([wl.w_enc, wl.w_dec, wl.output]).to(dev)
     params = list(mods.parameters())
     crit = E.RNNTJointLoss(blank_id=0, precision=args.precision)
-    buckets = sharding.GradBuckets(params) if world > 1 else None
+    buckets = sharding.GradBuckets(params, own_grads=True) if world > 1 else None   # p.grad = views of flat buckets
     host = [t.pin_memory() for t in (wl.eouts, wl.douts, wl.ys.int(), wl.tlen.int(), wl.ulen.int())]
     resident = [t.to(dev) for t in host]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
 
     def step(eouts, douts, ys, tlen, ulen):
-        for p in params:
-            p.grad = None
+        if buckets is not None:
+            buckets.zero()          # in place: the gradients live inside the all-reduce buckets
+        else:
+            for p in params:
+                p.grad = None
         eouts = eouts.detach().requires_grad_()
         douts = douts.detach().requires_grad_()
         loss = crit(wl.w_enc(eouts), wl.w_dec(douts), wl.output.weight, wl.output.bias, ys, tlen, ulen)

@@ -32,11 +32,15 @@ class GradBuckets:
     """Flat gradient buckets (default ~25 MB) all-reduced asynchronously, then averaged.
 
     ``start()`` launches one all-reduce per bucket (they overlap with whatever the caller enqueues
-    next, e.g. the encoder backward); ``finish()`` waits, divides by the world size and scatters the
-    result back into ``p.grad``.
+    next, e.g. the encoder backward); ``finish()`` waits and leaves the averaged gradients in ``p.grad``.
+
+    With ``own_grads=True`` the buckets OWN the gradient storage: every ``p.grad`` is a view into its bucket's
+    flat buffer (autograd accumulates into it in place), so a step is one ``zero()`` (a memset per bucket) and one
+    in-place all-reduce per bucket -- no flatten / unflatten copies, and with NCCL the division by the world size
+    is the collective's own ``AVG``.
     """
 
-    def __init__(self, params, bucket_bytes=25 << 20, group=None):
+    def __init__(self, params, bucket_bytes=25 << 20, group=None, own_grads=False):
         self.params = [p for p in params if p.requires_grad]
         self.group = group
         self.buckets, cur, size = [], [], 0
@@ -50,20 +54,49 @@ class GradBuckets:
         if cur:
             self.buckets.append(cur)
         self._pending = []
+        self.flats = None
+        if own_grads:
+            self.flats = []
+            for bucket in self.buckets:
+                flat = torch.zeros(sum(p.numel() for p in bucket), dtype=bucket[0].dtype, device=bucket[0].device)
+                off = 0
+                for p in bucket:
+                    p.grad = flat[off:off + p.numel()].view_as(p)
+                    off += p.numel()
+                self.flats.append(flat)
+
+    def zero(self):
+        """own_grads mode: clears the gradients in place (instead of ``p.grad = None``)."""
+        for flat in self.flats:
+            flat.zero_()
+
+    def _avg_op(self):
+        backend = dist.get_backend(self.group)
+        return dist.ReduceOp.AVG if backend == "nccl" else None
 
     def start(self):
         self._pending = []
+        if self.flats is not None:
+            avg = self._avg_op()
+            for flat in self.flats:
+                work = dist.all_reduce(flat, op=avg if avg is not None else dist.ReduceOp.SUM, group=self.group,
+                                       async_op=True)
+                self._pending.append((None, None, flat, work, avg is not None))
+            return
         for bucket in self.buckets:
             grads = [p.grad if p.grad is not None else torch.zeros_like(p) for p in bucket]
             flat = torch._utils._flatten_dense_tensors(grads)
             work = dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=self.group, async_op=True)
-            self._pending.append((bucket, grads, flat, work))
+            self._pending.append((bucket, grads, flat, work, False))
 
     def finish(self):
         world = dist.get_world_size(self.group)
-        for bucket, grads, flat, work in self._pending:
+        for bucket, grads, flat, work, averaged in self._pending:
             work.wait()
-            flat.div_(world)
+            if not averaged:
+                flat.div_(world)
+            if bucket is None:
+                continue    # own_grads: p.grad already is the reduced buffer
             for p, g, r in zip(bucket, grads, torch._utils._unflatten_dense_tensors(flat, grads)):
                 if p.grad is None:
                     p.grad = r.clone()

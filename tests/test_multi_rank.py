@@ -57,15 +57,22 @@ def _loss(lin, eouts, douts, ys, tl, ul):
                                       lin[2].weight, lin[2].bias, ys, tl, ul, blank=0)
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, own_grads=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
     eouts, douts, ys, tl, ul, lin = _make_problem()
     batch = sharding.shard_batch({"eouts": eouts, "douts": douts, "ys": ys, "tl": tl, "ul": ul}, rank, world)
+    buckets = None
+    if own_grads:   # gradients accumulate straight into the flat all-reduce buffers
+        buckets = sharding.GradBuckets(lin.parameters(), bucket_bytes=256, own_grads=True)
+        for p in lin.parameters():
+            p.grad.fill_(123.0)     # stale values from a previous step ...
+        buckets.zero()              # ... are cleared in place
     loss = _loss(lin, batch["eouts"], batch["douts"], batch["ys"], batch["tl"], batch["ul"])
     loss.backward()
-    buckets = sharding.GradBuckets(lin.parameters(), bucket_bytes=256)   # tiny buckets: several all-reduces
+    if buckets is None:
+        buckets = sharding.GradBuckets(lin.parameters(), bucket_bytes=256)   # tiny buckets: several all-reduces
     assert len(buckets.buckets) > 1
     buckets.start()
     buckets.finish()
@@ -76,9 +83,10 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
-def test_two_rank_sharded_step_matches_single_process(tmp_path):
+@pytest.mark.parametrize("own_grads", [False, True], ids=["copy_buckets", "grads_in_buckets"])
+def test_two_rank_sharded_step_matches_single_process(tmp_path, own_grads):
     out = str(tmp_path / "rank0.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, own_grads), nprocs=2, join=True)
     got = torch.load(out)
     eouts, douts, ys, tl, ul, lin = _make_problem()
     loss = _loss(lin, eouts, douts, ys, tl, ul)      # global mean over the 4 utterances
