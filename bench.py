@@ -546,6 +546,9 @@ def main():
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
+        # stdout carries ONE JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) would be a second one
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     run = run_ours_rnnt if w["kind"] == "rnnt" else run_ours_ctc
     r = run(args, w, rank, world, dev)
