@@ -493,7 +493,21 @@ def cpu_reference_rate(w, sample_units, steps, warmup, threads=None):
     return Bc * steps / dt, dt / steps
 
 
+def emit(out):
+    """The ONE line of stdout.  File descriptor 1 is pointed at stderr for the rest of the process (main()), so
+    that banners printed by native libraries (e.g. "NCCL version ...") cannot add lines to it."""
+    _REAL_STDOUT.write(json.dumps(out) + "\n")
+    _REAL_STDOUT.flush()
+
+
+_REAL_STDOUT = sys.stdout
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -539,16 +553,13 @@ def main():
                                           "reference op sequence (oracle/torch_path.py: joint->log_softmax->"
                                           "torchaudio rnnt_loss CPU / torch ctc_loss CPU)"},
                "e2e": {"value": round(rate, 4), "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(out))
+        emit(out)
         return
 
     assert torch.cuda.is_available(), "bench.py --impl ours needs a CUDA device (no CPU fallback)"
     dev = torch.device("cuda", local_rank)
     torch.cuda.set_device(dev)
     if world > 1:
-        # stdout carries ONE JSON line: NCCL's "NCCL version ..." banner (NCCL_DEBUG=VERSION) would be a second one
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-            os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     run = run_ours_rnnt if w["kind"] == "rnnt" else run_ours_ctc
     r = run(args, w, rank, world, dev)
@@ -579,7 +590,7 @@ def main():
                                    "kind": "port", "host_cpus": os.cpu_count(),
                                    "sample": f"{sample} utterances of the same shape, 1 warm-up + 1 timed step "
                                              f"({sec:.1f} s/step)"}
-        print(json.dumps(out))
+        emit(out)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
