@@ -139,8 +139,8 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
 bool joint_zc_supported(int J);
 int joint_dhz_launch(const void* w_bf16, const void* hcache, const void* zcache, const int* labels, const int* tlen,
                      const int* ulen, const float* lse, const float* gamma2, const float* grad_cost, int B, int T,
-                     int U1, int J, int V, int blank, void* dh_ws, float* d_enc_proj, float* d_dec_proj,
-                     cudaStream_t st);
+                     int U1, int J, int V, int blank, void* dh_ws, const float* enc_proj, const float* dec_proj,
+                     float* d_enc_proj, float* d_dec_proj, cudaStream_t st);
 int joint_dwz_launch(const void* hcache, const void* zcache, const int* labels, const int* tlen, const int* ulen,
                      const float* lse, const float* gamma2, const float* grad_cost, int B, int T, int U1, int J,
                      int V, int blank, float* d_w_out, float* d_b_out, cudaStream_t st);

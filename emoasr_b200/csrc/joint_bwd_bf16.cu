@@ -1181,7 +1181,6 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
                    const void* hcache, size_t hcache_bytes, int B, int T,
                    int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
                    float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st) {
-    (void)enc_proj; (void)dec_proj;
     EMO_REQUIRE(w_out && b_out && labels && tlen && ulen && lse && gamma2 && grad_cost && d_enc_proj &&
                     d_dec_proj && d_w_out && d_b_out && ws,
                 EMO_BAD_ARG, "joint_bwd(bf16): null pointer");
@@ -1209,7 +1208,7 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
         hcache_bytes >= zcache_offset_for(B, T, U1, J) + zcache_bytes_for(B, T, U1, V)) {
         const void* zcache = (const char*)hcache + zcache_offset_for(B, T, U1, J);
         rc = joint_dhz_launch(w_bf16, hcache, zcache, labels, tlen, ulen, lse, gamma2, grad_cost, B, T, U1, J, V,
-                              blank, dpre, d_enc_proj, d_dec_proj, st);
+                              blank, dpre, enc_proj, dec_proj, d_enc_proj, d_dec_proj, st);
         if (rc) return rc;
         return joint_dwz_launch(hcache, zcache, labels, tlen, ulen, lse, gamma2, grad_cost, B, T, U1, J, V, blank,
                                 d_w_out, d_b_out, st);
