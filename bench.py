@@ -47,13 +47,13 @@ WORKLOADS = {
 # dram__bytes_read.sum + dram__bytes_write.sum per launch, from the ncu --set full captures under profiles/.
 # recompute route (profiles/r1c_ncu_full_metrics.txt): bwd = joint_dh_kernel + reduce_dpre_kernel +
 #   joint_dwt_kernel; algorithmic: h cache read twice, dpre written once and read once = 3.3 GB
-# z-cache route (profiles/r1i_ncu_full_metrics.txt): fwd writes h + z; bwd = joint_dhz_kernel (z + w_out read,
-#   dh written) + reduce_dh_kernel (dh + h read) + joint_dwz_kernel (z + h read); algorithmic:
-#   z read twice, h read twice, dh written and read once = 6.6 GB
+# z-cache route (profiles/r1l_ncu_full_metrics.txt): fwd writes h + z; bwd = joint_dhz_kernel (z + w_out read,
+#   dh written) + reduce_dh_tanh_kernel (dh read, h recomputed) + joint_dwz_kernel (z + h read); algorithmic:
+#   z read twice, h read once, dh written and read once = 5.8 GB
 NCU_DRAM_BYTES = {"rnnt_cfg3": {"fwd": 24.1e6 + 781.9e6,
                                 "bwd": (842.4e6 + 776.5e6) + (834.2e6 + 21.9e6) + (844.1e6 + 4.5e6)},
                   "rnnt_cfg3_zc": {"fwd": 13.6e6 + 2451.2e6,
-                                   "bwd": (1678.7e6 + 798.5e6) + (1661.4e6 + 25.3e6) + (2497.5e6 + 4.2e6)}}
+                                   "bwd": (1683.1e6 + 795.9e6) + (857.1e6 + 25.7e6) + (2498.1e6 + 3.9e6)}}
 
 
 def load_peaks():
