@@ -1,6 +1,6 @@
 // How many clusters of a 1-CTA/SM kernel (640 threads, ~220 KiB dynamic shared memory) can be co-resident
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -o tools/probe/cluster_probe tools/probe/cluster_probe.cu
 // for cluster sizes 1, 2, 4, 8?  (cudaOccupancyMaxActiveClusters; decides whether wider TMA multicast pays)
+// build: nvcc -gencode arch=compute_100a,code=sm_100a -o tools/probe/cluster_probe tools/probe/cluster_probe.cu
 #include <cstdio>
 #include <cuda_runtime.h>
 __global__ void __launch_bounds__(640, 1) probe_kernel(int* p) { extern __shared__ char s[]; if (p) p[0] = s[0]; }
