@@ -131,7 +131,9 @@ int emo_rnnt_joint_fwd(const float* enc_proj, const float* dec_proj,
  *   d_w_out (V,J) = sum dz^T h ; d_b_out (V) = sum dz ; dh = dz w_out ;
  *   dpre = dh (1-h^2) ; d_enc_proj[b,t] = sum_u dpre ; d_dec_proj[b,u] = sum_t dpre.
  * All four outputs are overwritten (not accumulated into).  hcache: what emo_rnnt_joint_fwd wrote
- * for the same inputs (required in EMO_PREC_BF16). */
+ * for the same inputs (required in EMO_PREC_BF16).  enc_proj, dec_proj, w_out, b_out, labels and the
+ * lengths must be the tensors the forward call saw (as autograd's saved tensors are): the backward re-reads
+ * them (h is recomputed from enc_proj / dec_proj in the axis reduction). */
 int emo_rnnt_joint_bwd(const float* enc_proj, const float* dec_proj,
                        const float* w_out, const float* b_out,
                        const int* labels, const int* tlen, const int* ulen,
