@@ -178,7 +178,7 @@ def run_ours_rnnt(args, w, rank, world, dev):
         step(*resident)
     barrier()
     # ---- device-resident timing: per-step CUDA events, L2 flushed (untimed) between steps
-    mon = ClockMonitor(dev.index if dev.index is not None else 0)
+    mon = ClockMonitor(dev.index if dev.index is not None else 0, enabled=rank == 0)
     mon.start()
     evs = []
     for _ in range(args.steps):
@@ -316,7 +316,7 @@ def run_ours_ctc(args, w, rank, world, dev):
     for _ in range(args.warmup):
         step(*resident)
     torch.cuda.synchronize()
-    mon = ClockMonitor(dev.index if dev.index is not None else 0)
+    mon = ClockMonitor(dev.index if dev.index is not None else 0, enabled=rank == 0)
     mon.start()
     evs = []
     for _ in range(args.steps):
@@ -350,7 +350,9 @@ class ClockMonitor:
          "clocks_event_reasons.sw_power_cap")
     NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
+    def __init__(self, index, enabled=True):
+        # rank 0 only: eight processes polling NVML contend on the driver's lock and slow every rank's launches
+        self.enabled = enabled
         self.index = index
         self.proc = None
         self.lines = []
@@ -371,9 +373,11 @@ class ClockMonitor:
                 self.samples.append((float(mhz), int(bits)))
             except Exception:
                 pass
-            time.sleep(0.004)
+            time.sleep(0.01)
 
     def start(self):
+        if not self.enabled:
+            return
         try:
             import pynvml as nv
             nv.nvmlInit()
@@ -412,6 +416,8 @@ class ClockMonitor:
             self.lines.append(line.strip())
 
     def stop(self):
+        if not self.enabled:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "rank 0 samples"}
         if self.nvml is not None:
             self._stop.set()
             self.thread.join(timeout=1)
