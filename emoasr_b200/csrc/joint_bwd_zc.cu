@@ -9,9 +9,10 @@
 // 2 bytes per (cell, vocab entry) of HBM.
 //
 //   dhz kernel  cell-stationary CTA pair (cta_group::2, 256 cells per pair tile); per 64-wide vocab block:
-//                  z tile [128 cells x 64 v] (TMA) -> dz (8 transform warps) -> dh[256 x J] += dz W[kb]
+//                  z tile [128 cells x 64 v] (TMA) -> dz (transform warps) -> dh[256 x J] += dz W[kb]
 //               with the full J-wide accumulator in TMEM (512 columns); dh leaves as bf16, tile-major (TMA
-//               stores); reduce_dh_kernel applies (1 - h^2) and forms the two axis sums.
+//               stores); reduce_dh_tanh_kernel applies (1 - h^2) (h recomputed from the projections) and forms
+//               the two axis sums.
 //               The tile, read with v contiguous, is the K-major A operand.
 //   dWz kernel  vocab-stationary CTA pair: role = 256 vocab rows (128 per CTA, TMEM lane == vocab row), all
 //               of J in the 512 TMEM columns, accumulated over ALL cells of the pair's share:
@@ -19,8 +20,11 @@
 //               The same bytes, read with v contiguous, are now the MN-major A operand (M = vocab, K = cells);
 //               h blocks from the h cache are the MN-major B operand.  d_b_out = column sums of dz, kept in
 //               registers of the transform threads (each owns an 8-wide vocab strip for the whole kernel).
-// Both: warp 0 TMA producer of the second operand (w_out / h), warp 1 MMA issuer, warp 2 TMEM allocator + z TMA
-// producer, warp 3 per-cell scalar stager (dWz), warps 4-11 transform, warps 12-19 accumulator drain / flush.
+// Both (640 threads): warp 0 TMA producer of the second operand (w_out / h), warp 1 MMA issuer, warp 2 TMEM
+// allocator + z TMA producer (with an L2 prefetch cursor ahead of the loads), warp 3 per-cell scalar stager (per tile
+// in dhz, per K block in dWz; its global loads stay in flight ahead of use), warps 4-19 transform in two groups of
+// 8 warps on alternate ring stages.  dhz: group 1 (warps 12-19) also drains the accumulator of a finished tile;
+// dWz: group 0 (warps 4-11) flushes the accumulator once at the end.
 #include "joint_tc.cuh"
 
 // -DEMO_ZC_PROF: clock64 accounting of the MMA issuer's mbarrier waits (printf from CTA 0) and the
