@@ -4,21 +4,24 @@
 //   lse[cell]  = log sum_v exp z ;  lp2[cell] = { z[blank]-lse, z[label]-lse }
 // (asr/modeling/decoders/rnn_transducer.py:147-156 + :102) without writing z anywhere.
 //
-// Persistent, warp-specialised CTAs, one 128-cell tile at a time (cells of one utterance,
-// flattened over its VALID (t,u) region, so padding costs nothing):
-//   warp 0      TMA producer   w_out (bf16, [V][J]) tiles [256 v x 64 j], 128B swizzle, ring of
-//                              kNumBStages, mbarrier complete_tx
-//   warp 1      MMA issuer     tcgen05.mma kind::f16, M=128, N<=256, K=16; accumulators in TMEM,
-//                              two 256-column buffers so the epilogue of vocab chunk n overlaps the
-//                              MMAs of chunk n+1
-//   warp 2      TMEM allocator
-//   warps 4-7   epilogue       tcgen05.ld 32 columns at a time (thread == lattice cell), bias add,
-//                              online (max, sum-exp) over the vocab chunks, capture of the blank and
-//                              label logits
-//   warps 8-11  A producers    h = tanh(enc+dec) -> bf16 -> shared memory in the canonical K-major
-//                              128B-swizzle layout, one 64-wide K block at a time so the MMAs of
-//                              the next tile start as soon as block 0 is rewritten
-// The h tile (128 x J bf16) stays resident in shared memory for all vocab chunks of the tile.
+// Persistent, warp-specialised CTA pairs (cluster of 2, cta_group::2), one 256-cell tile per pair at a time (cells of
+// one utterance, flattened over its VALID (t,u) region, so padding costs nothing); 512 threads, setmaxnreg budgets
+// per warpgroup:
+//   warp 0       TMA producer   w_out (bf16, [V][J]) tiles [128 v x 64 j] per CTA, 128B swizzle, mbarrier ring
+//                               (5 stages, 4 when the z cache is written), complete_tx
+//   warp 1       MMA issuer     tcgen05.mma kind::f16, M=256, N<=256, K=16; accumulators in TMEM, two 256-column
+//                               buffers so the epilogue of vocab chunk n overlaps the MMAs of chunk n+1
+//   warp 2       TMEM allocator
+//   warp 3       h-cache writer TMA store of every finished h block (bf16, tile-major) for the backward
+//   warps 4-11   epilogue       two warps per TMEM lane quadrant, each half of a chunk's columns: tcgen05.ld 32
+//                               columns at a time (thread == lattice cell), bias add, online (max, sum-exp) over the
+//                               vocab chunks, capture of the blank and label logits; optionally the logits go to the
+//                               z cache as fp16 through a per-warp staging buffer and one TMA store per block
+//   warps 12-15  A producers    h = tanh(enc+dec): fp16 gathers, packed-half add and tanh.approx, -> bf16 -> shared
+//                               memory in the canonical K-major 128B-swizzle layout, one 64-wide K block at a time so
+//                               the MMAs of the next tile start as soon as block 0 is rewritten
+// The h tile (128 x J bf16 per CTA) stays resident in shared memory for all vocab chunks of the tile.
+// (joint_fwd_kernel<1, .> is the single-CTA variant kept as a tuning switch, EMO_FWD_SINGLE_CTA.)
 #include "joint_tc.cuh"
 
 // -DEMO_ZC_PROF: clock64 accounting of the MMA issuer's mbarrier waits (printf from CTA 0); tools/gpu_zcprof.sh
