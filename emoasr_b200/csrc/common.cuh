@@ -131,13 +131,25 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
                    size_t hcache_bytes, void* ws, size_t ws_bytes, cudaStream_t st);
 int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
                    const float* b_out, const int* labels, const int* tlen, const int* ulen,
-                   const float* lse, const float* gamma2, const float* grad_cost,
+                   const float* lse, const float* lp2, const float* gamma2, const float* grad_cost,
                    const void* hcache, size_t hcache_bytes, int B, int T,
                    int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
                    float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st);
-// z-cache backward kernels (joint_bwd_zc.cu)
+// ring backward (joint_bwd_ring.cu): the default route
+bool joint_ring_supported(int B, int T, int U1, int J, int V);
+size_t joint_ring_workspace(int B, int T, int U1, int J, int V);
+int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec_h, const float* b_out,
+                          const int* labels, const int* tlen, const int* ulen, const float* lse, const float* lp2,
+                          const float* gamma2, const float* grad_cost, int B, int T, int U1, int J, int V, int blank,
+                          void* dh_ws, void* ring_ws, float* d_w_out, float* d_b_out, cudaStream_t st);
+int joint_bf16_casts(const float* enc_proj, const float* dec_proj, const float* w_out, int B, int T, int U1, int J,
+                     int V, void* ws, const void** w_bf16, const void** enc_h, const void** dec_h, cudaStream_t st);
+// z-cache backward kernels (joint_bwd_zc.cu): optional variant
 bool joint_zc_supported(int J);
-int joint_dhz_launch(const void* w_bf16, const void* hcache, const void* zcache, const int* labels, const int* tlen,
+int joint_reduce_dh_launch(const void* dh_ws, const float* enc_proj, const float* dec_proj, const int* tlen,
+                           const int* ulen, int B, int T, int U1, int J, float* d_enc_proj, float* d_dec_proj,
+                           cudaStream_t st);
+int joint_dhz_launch(const void* w_bf16, const void* zcache, const int* labels, const int* tlen,
                      const int* ulen, const float* lse, const float* gamma2, const float* grad_cost, int B, int T,
                      int U1, int J, int V, int blank, void* dh_ws, const float* enc_proj, const float* dec_proj,
                      float* d_enc_proj, float* d_dec_proj, cudaStream_t st);

@@ -2,7 +2,9 @@
 //
 //   z[cell, v] = sum_j tanh(enc[b,t,j] + dec[b,u,j]) * w_out[v,j] + b_out[v]
 //   lse[cell]  = log sum_v exp z ;  lp2[cell] = { z[blank]-lse, z[label]-lse }
-// (asr/modeling/decoders/rnn_transducer.py:147-156 + :102) without writing z anywhere.
+// (asr/modeling/decoders/rnn_transducer.py:147-156 + :102).  Default instantiation <2, false>: z lives only in TMEM
+// and registers.  <2, true> is the optional z-cache variant, which DOES write z (fp16, valid cells) and h (bf16)
+// to a caller-provided cache for the z-cache backward (joint_bwd_zc.cu).
 //
 // Persistent, warp-specialised CTA pairs (cluster of 2, cta_group::2), one 256-cell tile per pair at a time (cells of
 // one utterance, flattened over its VALID (t,u) region, so padding costs nothing); 512 threads, setmaxnreg budgets
@@ -21,7 +23,6 @@
 //                               memory in the canonical K-major 128B-swizzle layout, one 64-wide K block at a time so
 //                               the MMAs of the next tile start as soon as block 0 is rewritten
 // The h tile (128 x J bf16 per CTA) stays resident in shared memory for all vocab chunks of the tile.
-// (joint_fwd_kernel<1, .> is the single-CTA variant kept as a tuning switch, EMO_FWD_SINGLE_CTA.)
 #include "joint_tc.cuh"
 
 // -DEMO_ZC_PROF: clock64 accounting of the MMA issuer's mbarrier waits (printf from CTA 0); tools/gpu_zcprof.sh
@@ -513,48 +514,35 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     EMO_REQUIRE(((uintptr_t)ws & 255) == 0 && ((uintptr_t)enc_proj & 15) == 0 &&
                     ((uintptr_t)dec_proj & 15) == 0 && ((uintptr_t)w_out & 15) == 0,
                 EMO_BAD_ARG, "joint_fwd(bf16): pointers must be 16-byte (workspace 256-byte) aligned");
-    __nv_bfloat16* w_bf16 = reinterpret_cast<__nv_bfloat16*>(ws);
-    size_t nw = (size_t)V * J;
-    f32_to_bf16_kernel<<<ceil_div(nw, 4 * 256), 256, 0, st>>>(w_out, w_bf16, nw);
-    EMO_CHECK_LAUNCH("f32_to_bf16_kernel");
-    // fp16 copies of the two projected streams (11-bit mantissa, half the gather bytes of fp32)
-    const size_t ne = (size_t)B * T * J, nd = (size_t)B * U1 * J;
-    __half* enc_h = reinterpret_cast<__half*>((char*)ws + align_up(nw * sizeof(__nv_bfloat16), 256));
-    __half* dec_h = reinterpret_cast<__half*>((char*)enc_h + align_up(ne * sizeof(__half), 256));
-    f32_to_f16_kernel<<<ceil_div(ne, 4 * 256), 256, 0, st>>>(enc_proj, enc_h, ne);
-    f32_to_f16_kernel<<<ceil_div(nd, 4 * 256), 256, 0, st>>>(dec_proj, dec_h, nd);
-    EMO_CHECK_LAUNCH("f32_to_f16_kernel");
+    const void *w_bf16, *enc_h, *dec_h;
+    rc = joint_bf16_casts(enc_proj, dec_proj, w_out, B, T, U1, J, V, ws, &w_bf16, &enc_h, &dec_h, st);
+    if (rc) return rc;
 
     const int KB = J / kBlockK;
     const size_t a_bytes = (size_t)KB * kABlockBytes;
-    static const bool use_single = getenv("EMO_FWD_SINGLE_CTA") != nullptr;  // A/B switch while tuning
-    CUtensorMap tmap, tmap_h;
+    CUtensorMap tmap, tmap_h, tmap_z;
     const int store_h = hcache != nullptr;
-    __half* zcache = nullptr;
     if (store_h) {
-        EMO_REQUIRE(hcache_bytes >= hcache_bytes_for(B, T, U1, J) && ((uintptr_t)hcache & 255) == 0,
-                    EMO_WORKSPACE_TOO_SMALL, "joint_fwd(bf16): h cache too small or misaligned");
-        if (joint_zc_supported(J) &&
-            hcache_bytes >= zcache_offset_for(B, T, U1, J) + zcache_bytes_for(B, T, U1, V))
-            zcache = reinterpret_cast<__half*>((char*)hcache + zcache_offset_for(B, T, U1, J));
-        rc = make_tmap_bf16_2d(&tmap_h, hcache, (uint64_t)J,
-                               (uint64_t)B * tiles128_per_utt(T, U1) * kTileM, kBlockK, kTileM);
+        // optional z-cache variant: h (bf16) and the logits (fp16) of every valid cell go to the caller's cache
+        EMO_REQUIRE(joint_zc_supported(J) &&
+                        hcache_bytes >= zcache_offset_for(B, T, U1, J) + zcache_bytes_for(B, T, U1, V) &&
+                        ((uintptr_t)hcache & 255) == 0,
+                    EMO_WORKSPACE_TOO_SMALL,
+                    "joint_fwd(bf16): cache must be emo_workspace_bytes(EMO_OP_RNNT_JOINT_HZCACHE) bytes, 256-byte "
+                    "aligned (or NULL for the default route)");
+        const uint64_t rows = (uint64_t)B * tiles128_per_utt(T, U1) * kTileM;
+        rc = make_tmap_bf16_2d(&tmap_h, hcache, (uint64_t)J, rows, kBlockK, kTileM);
         if (rc) return rc;
-    }
-    CUtensorMap tmap_z;
-    if (zcache) {
-        rc = make_tmap_bf16_2d(&tmap_z, zcache, (uint64_t)V, (uint64_t)B * tiles128_per_utt(T, U1) * kTileM, 32, 32,
+        rc = make_tmap_bf16_2d(&tmap_z, (char*)hcache + zcache_offset_for(B, T, U1, J), (uint64_t)V, rows, 32, 32,
                                CU_TENSOR_MAP_SWIZZLE_64B);
         if (rc) return rc;
     }
-    const bool pair = !use_single;
-    const int b_rows = pair ? Cfg<2, false>::kBRows : Cfg<1, false>::kBRows;
+    const int b_rows = Cfg<2, false>::kBRows;
     rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, b_rows);
     if (rc) return rc;
-    if (!store_h) tmap_h = tmap;
-    if (!zcache) tmap_z = tmap;
-    const int tiles = B * ceil_div((size_t)T * U1, (pair ? 2 : 1) * kTileM);
-    const int ctas = pair ? 2 * min(tiles, sm_count() / 2) : min(tiles, sm_count());
+    if (!store_h) { tmap_h = tmap; tmap_z = tmap; }
+    const int tiles = B * ceil_div((size_t)T * U1, 2 * kTileM);
+    const int ctas = 2 * min(tiles, sm_count() / 2);
     auto launch = [&](auto kernel, int stages, size_t bars_bytes, bool store_z) -> int {
         const size_t smem = a_bytes + (size_t)stages * b_rows * kBlockK * 2 +
                             (store_z ? (kFwdEpiThreads / 32) * kZStageBytes : 0) + bars_bytes +
@@ -568,7 +556,7 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
         cfg.stream = st;
         cudaLaunchAttribute attr[1];
         attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = pair ? 2 : 1; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr;
         cfg.numAttrs = 1;
         EMO_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmap, tmap_h, tmap_z, store_h, (const __half*)enc_h,
@@ -576,12 +564,8 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
         EMO_CHECK_LAUNCH("joint_fwd_kernel");
         return EMO_OK;
     };
-    if (pair) {
-        if (zcache) return launch(joint_fwd_kernel<2, true>, Cfg<2, true>::kBStages, sizeof(FwdBarriers<2, true>), true);
-        return launch(joint_fwd_kernel<2, false>, Cfg<2, false>::kBStages, sizeof(FwdBarriers<2, false>), false);
-    }
-    if (zcache) return launch(joint_fwd_kernel<1, true>, Cfg<1, true>::kBStages, sizeof(FwdBarriers<1, true>), true);
-    return launch(joint_fwd_kernel<1, false>, Cfg<1, false>::kBStages, sizeof(FwdBarriers<1, false>), false);
+    if (store_h) return launch(joint_fwd_kernel<2, true>, Cfg<2, true>::kBStages, sizeof(FwdBarriers<2, true>), true);
+    return launch(joint_fwd_kernel<2, false>, Cfg<2, false>::kBStages, sizeof(FwdBarriers<2, false>), false);
 }
 
 }  // namespace emo

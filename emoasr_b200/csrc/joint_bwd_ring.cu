@@ -1,0 +1,1241 @@
+// EMO_PREC_BF16 backward of the fused joint WITHOUT any N x V tensor in HBM ("ring" route, the default).
+//
+//   dz[cell,v] = g_b * (gamma * exp(z - lse) - gamma_blank 1[v=blank] - gamma_label 1[v=label])
+//   dW = dz^T h      dh = dz W      (rnn_transducer.py:101-102,147-156 differentiated)
+//
+// The logits are RECOMPUTED tile by tile on the tensor cores (1 GEMM unit), turned into dz in the epilogue
+// and consumed by the two gradient GEMMs (1 unit each): 3 executed units for 2 algorithmic ones, against 6
+// for a design that recomputes z separately for every accumulator that does not fit next to it in TMEM
+// (a [128 cells x 512] fp32 accumulator IS the 512 TMEM columns of an SM, so neither dh nor dW can share an
+// SM with the logit accumulators).  The three GEMMs therefore run on DIFFERENT SMs of one persistent,
+// heterogeneous kernel and hand dz / h to each other through a small ring of tiles in global memory that is
+// sized to stay L2-resident (36 MB, independent of the problem size):
+//
+//   P pairs  (producer)   the forward's pipeline again: h = tanh(enc+dec) -> smem, z = h W^T in TMEM
+//                         (cta_group::2, 256 cells per pair tile); epilogue thread == lattice cell:
+//                         dz -> bf16 -> per-warp staging -> TMA store into the ring; h blocks -> ring.
+//   D pairs  (dh)         cell-stationary: dh[256 x J] += dz[256 x 64 v] W[64 v x J] over the vocabulary, dz
+//                         straight from the ring by TMA (K-major A operand); drain -> bf16 dh, tile-major
+//                         (HBM; the axis reduction kernel applies (1 - h^2) and forms d_enc / d_dec).
+//   W pairs  (dW)         vocab-stationary: role = 256 vocab rows, all of J in TMEM, accumulated over the
+//                         tiles of the pair's split: dW[256 v x J] += dz^T[256 v x 64 cells] h[64 cells x J];
+//                         dz (MN-major A) and h (MN-major B) from the ring; column sums of dz -> d_b_out.
+//
+// Ring protocol (global int counters, zeroed per launch by ring_prep_kernel): items are produced and consumed
+// in increasing order of the dense pair-tile index q (prefix sums over the utterances' valid cells), slot =
+// item mod slots.  A writer lane signals "ready" with red.release.gpu after its TMA stores have completed
+// (cp.async.bulk.wait_group 0); a consumer polls with ld.acquire.gpu before its TMA loads and signals "done"
+// once the loads have landed (mbarrier complete_tx observed); a producer polls "done" of the previous use of
+// the slot before overwriting it.  No role ever waits for a LATER item, all CTAs are co-resident (grid <=
+// resident clusters, checked on the host), hence no deadlock.
+#include "joint_tc.cuh"
+
+namespace emo {
+namespace {
+
+constexpr int kRingThreads = 640;
+constexpr int kVG = 1024;                      // vocab entries per ring item (one z slot = 256 cells x kVG)
+constexpr int kPairM = 2 * kTileM;             // cells per pair tile
+constexpr int kRingSlots = 48;                 // z slots (512 KiB each at V >= 1024) and h slots (256 KiB at J = 512)
+constexpr int kPBStages = 4;                   // P: w_out ring
+constexpr int kDZStages = 5, kDOpStages = 3;   // D: dz ring, w_out ring
+constexpr int kWZStages = 5, kWOpStages = 4;   // W: dz ring, h ring
+constexpr int kStageBytes = 16384;
+constexpr int kBoxBytes = 8192;                // [64 rows x 128 B]
+constexpr int kZStBytes = 2048;                // P epilogue staging per warp: [32 cells x 32 v] bf16, 64B swizzle
+constexpr int kDrainWarps = 8, kDrainBufBytes = 4096;
+constexpr int kColsumWarps = 8;
+constexpr int kMaxB = 1024;                    // utterances (prefix table lives in shared memory)
+constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO=1024, v1, SW128
+
+struct RingArgs {
+    const __half* enc;          // (B,T,J) fp16 copy of enc_proj
+    const __half* dec;          // (B,U1,J)
+    const float* b_out;
+    const int* labels;
+    const float* lse;
+    const float* lp2;
+    const float* gamma2;
+    const float* grad_cost;
+    const int* prefix;          // [B+1] dense pair-tile prefix, then [B] packed (T_b | U1b << 16)
+    int* flags;                 // z_ready[NZ] z_done[NZ] h_ready[NH] h_done[NH]
+    float* d_w_out;
+    float* d_b_out;
+    int B, T, U1, J, V, blank;
+    int nP, nD, nS;             // pairs: producers, dh consumers, dW splits (x roles_v pairs)
+    int NZ, NH, G;              // ring slots, vocab groups per tile
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+    int v;
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void red_release_gpu(int* p) {
+    asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(p) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async_all() {
+    asm volatile("fence.proxy.async;" ::: "memory");
+}
+// consumer / producer side of a ring flag: wait, then order the async-proxy accesses (TMA) that follow
+__device__ __forceinline__ void ring_wait(const int* p, int need) {
+    while (ld_acquire_gpu(p) < need) __nanosleep(32);
+    fence_proxy_async_all();
+}
+// after this lane's TMA stores have COMPLETED: publish
+__device__ __forceinline__ void ring_signal_stored(int* p) {
+    tma_store_wait_all<0>();
+    fence_proxy_async_all();
+    red_release_gpu(p);
+}
+__device__ __forceinline__ uint32_t desc_lo(uint32_t smem_addr, uint32_t lbo_bytes) {
+    return ((smem_addr & 0x3FFFFu) >> 4) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo) { return ((uint64_t)kDescHiSw128 << 32) | lo; }
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d)
+                 : "memory");
+}
+template <int N> __device__ __forceinline__ void reg_dec() {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
+}
+template <int N> __device__ __forceinline__ void reg_inc() {
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N));
+}
+
+// dense pair-tile index -> utterance / first cell (binary search in the shared-memory prefix table)
+struct PTile {
+    int b, first_cell, n_cells, U1b;
+};
+__device__ __forceinline__ void ptile(int q, const int* s_prefix, int B, PTile& t) {
+    int lo = 0, hi = B;
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if (s_prefix[mid] <= q) lo = mid; else hi = mid;
+    }
+    const int tu = s_prefix[B + 1 + lo];
+    t.b = lo;
+    t.U1b = tu >> 16;
+    t.n_cells = (tu & 0xffff) * t.U1b;
+    t.first_cell = (q - s_prefix[lo]) * kPairM;
+}
+// W roles of vocab group g (256-row slabs inside [g kVG, min(V, (g+1) kVG)))
+__device__ __forceinline__ int roles_in_group(int g, int V) {
+    return (min(V - g * kVG, kVG) + 255) >> 8;
+}
+
+// ---- prefix table + flag reset (one block) ------------------------------------------------------
+__global__ void __launch_bounds__(kMaxB) ring_prep_kernel(const int* __restrict__ tlen, const int* __restrict__ ulen,
+                                                          int B, int T, int U1, int* __restrict__ prefix,
+                                                          int* __restrict__ flags, int nflags) {
+    __shared__ int s_warp[32];
+    const int b = threadIdx.x, lane = b & 31, warp = b >> 5;
+    int n = 0, tu = 0;
+    if (b < B) {
+        const int T_b = min(max(tlen[b], 1), T), U1b = min(max(ulen[b], 0), U1 - 1) + 1;
+        n = (T_b * U1b + kPairM - 1) / kPairM;
+        tu = T_b | (U1b << 16);
+    }
+    int incl = n;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s_warp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += v;
+        }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    if (warp > 0) incl += s_warp[warp - 1];
+    if (b == 0) prefix[0] = 0;
+    if (b < B) {
+        prefix[b + 1] = incl;
+        prefix[B + 1 + b] = tu;
+    }
+    for (int i = b; i < nflags; i += blockDim.x) flags[i] = 0;
+}
+
+// =================================================================================================
+// P role: recompute z = h W^T tile by tile, emit dz and h into the ring
+// =================================================================================================
+struct __align__(16) PBars {
+    uint64_t b_full[kPBStages], b_empty[kPBStages];
+    uint64_t a_full[kMaxKBlocks], a_empty[kMaxKBlocks];
+    uint64_t h_ready[kMaxKBlocks];   // local: this CTA's producer warps have written block kb
+    uint64_t acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    uint32_t pad[3];
+};
+constexpr int kPEpiThreads = 256;    // warps 4-11
+constexpr int kPProdWarps = 8;       // warps 12-19
+
+// per-cell scalars of the dz epilogue (thread == cell)
+struct PCell {
+    float nl2;    // -lse * log2e (-1e30 for padding rows: exp2 -> 0)
+    float cs;     // g * (gamma_blank + gamma_label)
+    float dblk;   // dz at the blank column:  cs * p_blank - g * gamma_blank (- g * gamma_label if label == blank)
+    float dlab;   // dz at the label column:  cs * p_label - g * gamma_label
+    int lab;      // label of the cell's emit transition, -1 if none (or == blank)
+};
+struct PRaw {
+    float g, lse;
+    float2 gm, lp;
+    int lab, valid;
+};
+__device__ __forceinline__ void p_load_raw(PRaw& r, const PTile& ti, int m, const RingArgs& a) {
+    r.g = 0.f; r.lse = 0.f; r.gm = make_float2(0.f, 0.f); r.lp = make_float2(0.f, 0.f); r.lab = -1; r.valid = 0;
+    if (m < ti.n_cells) {
+        const int t = m / ti.U1b, u = m - t * ti.U1b;
+        const size_t cell = ((size_t)ti.b * a.T + t) * a.U1 + u;
+        r.valid = 1;
+        r.g = __ldg(a.grad_cost + ti.b);
+        r.gm = __ldg(reinterpret_cast<const float2*>(a.gamma2) + cell);
+        r.lp = __ldg(reinterpret_cast<const float2*>(a.lp2) + cell);
+        r.lse = __ldg(a.lse + cell);
+        if (u < ti.U1b - 1) r.lab = __ldg(a.labels + (size_t)ti.b * (a.U1 - 1) + u);
+    }
+}
+__device__ __forceinline__ PCell p_finish(const PRaw& r, int V, int blank) {
+    PCell s;
+    s.nl2 = r.valid ? -r.lse * kLog2e : -1e30f;
+    s.cs = r.g * (r.gm.x + r.gm.y);
+    const int lab = r.lab < 0 ? -1 : min(r.lab, V - 1);
+    const float cb = r.g * r.gm.x, cl = r.g * r.gm.y;
+    s.dblk = r.valid ? fmaf(s.cs, ex2_approx(r.lp.x * kLog2e), -cb) : 0.f;
+    s.dlab = (r.valid && lab >= 0) ? fmaf(s.cs, ex2_approx(r.lp.y * kLog2e), -cl) : 0.f;
+    if (lab == blank) { s.dblk -= cl; s.lab = -1; } else s.lab = lab;
+    return s;
+}
+
+// One 32-column group of this thread's row: z = acc + bias, dz = cs * exp2(z log2e - lse log2e) -> bf16 into
+// the warp's staging buffer ([32 cells x 32 v], 64B swizzle, conflict-free 16-byte stores); the blank / label
+// entries are overwritten with their exact fp32 values (from the forward's lp2) before the TMA store.
+// live == false: a 32-column group past the vocabulary (V % 64 == 32): zeros, so that the consumers' 64-wide K
+// blocks never see stale ring content.
+__device__ __forceinline__ void dz_group(const uint32_t (&r)[32], const float* __restrict__ bias, int v0,
+                                         const PCell& s, int blank, const CUtensorMap* tmap_z, uint8_t* zbuf,
+                                         int zcol, int zrow, int lane, bool live) {
+    uint32_t o[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) o[i] = 0u;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        if (!live) break;
+        const float4 bv = *reinterpret_cast<const float4*>(bias + i);
+        const float d0 = s.cs * ex2_approx(fmaf(__uint_as_float(r[i + 0]) + bv.x, kLog2e, s.nl2));
+        const float d1 = s.cs * ex2_approx(fmaf(__uint_as_float(r[i + 1]) + bv.y, kLog2e, s.nl2));
+        const float d2 = s.cs * ex2_approx(fmaf(__uint_as_float(r[i + 2]) + bv.z, kLog2e, s.nl2));
+        const float d3 = s.cs * ex2_approx(fmaf(__uint_as_float(r[i + 3]) + bv.w, kLog2e, s.nl2));
+        o[i >> 1] = pack_bf16x2(d0, d1);
+        o[(i >> 1) + 1] = pack_bf16x2(d2, d3);
+    }
+    if (lane == 0) tma_store_wait_read<0>();   // the previous block has left the staging buffer
+    __syncwarp();
+    uint8_t* rowp = zbuf + lane * 64;
+    const int sw = (lane >> 1) & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<uint4*>(rowp + ((i ^ sw) << 4)) = make_uint4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+    const int dl = s.lab - v0;
+    if (live && (unsigned)dl < 32u)
+        *reinterpret_cast<__nv_bfloat16*>(rowp + (((dl >> 3) ^ sw) << 4) + (dl & 7) * 2) = __float2bfloat16_rn(s.dlab);
+    const int db = blank - v0;
+    if (live && (unsigned)db < 32u)   // warp-uniform
+        *reinterpret_cast<__nv_bfloat16*>(rowp + (((db >> 3) ^ sw) << 4) + (db & 7) * 2) = __float2bfloat16_rn(s.dblk);
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(tmap_z, smem_u32(zbuf), zcol, zrow);
+        tma_store_commit();
+    }
+}
+
+// A-operand producer: this warp's 16 rows of the 128-row tile, one 64-wide K block (see joint_bf16.cu)
+__device__ __forceinline__ void produce_h16(const uint4 (&re)[4], const uint4 (&rd)[4], int pw, int rsub, int c,
+                                            uint8_t* blk) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        const int row = pw * 16 + p * 4 + rsub;
+        const uint32_t e[4] = {re[p].x, re[p].y, re[p].z, re[p].w};
+        const uint32_t d[4] = {rd[p].x, rd[p].y, rd[p].z, rd[p].w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            const float2 f = unpack_f16x2(tanh_f16x2(hadd2_u32(e[q], d[q])));
+            o[q] = pack_bf16x2(f.x, f.y);
+        }
+        uint8_t* dst = blk + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+}
+
+__device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMap* tm_w, const CUtensorMap* tm_hst,
+                                             const CUtensorMap* tm_zst, uint8_t* smem, int pidx) {
+    const int KB = a.J / kBlockK;
+    const int NC = (a.V + kChunkN - 1) / kChunkN;
+    uint8_t* sA = smem;
+    uint8_t* sB = sA + (size_t)KB * kABlockBytes;
+    uint8_t* sZst = sB + (size_t)kPBStages * kStageBytes;
+    PBars* bars = reinterpret_cast<PBars*>(sZst + (kPEpiThreads / 32) * kZStBytes);
+    float* s_bias = reinterpret_cast<float*>(bars + 1);               // [2][kChunkN]
+    int* s_prefix = reinterpret_cast<int*>(s_bias + 2 * kChunkN);    // [B+1] + [B]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    int* z_ready = a.flags;
+    int* z_done = a.flags + a.NZ;
+    int* h_ready_g = a.flags + 2 * a.NZ;
+    int* h_done = a.flags + 2 * a.NZ + a.NH;
+    const int roles_v = (a.V + 255) >> 8;
+
+    for (int i = threadIdx.x; i < 2 * a.B + 1; i += kRingThreads) s_prefix[i] = __ldg(a.prefix + i);
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kPBStages; ++i) {
+            mbar_init(smem_u32(&bars->b_full[i]), 2);
+            mbar_init(smem_u32(&bars->b_empty[i]), 1);
+        }
+        for (int i = 0; i < kMaxKBlocks; ++i) {
+            mbar_init(smem_u32(&bars->a_full[i]), 2 * kPProdWarps);
+            mbar_init(smem_u32(&bars->a_empty[i]), 2);   // MMA commit + h store done
+            mbar_init(smem_u32(&bars->h_ready[i]), kPProdWarps);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(smem_u32(&bars->acc_full[i]), 1);
+            mbar_init(smem_u32(&bars->acc_empty[i]), 2 * (kPEpiThreads / 32));
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(tm_w);
+        tma_prefetch_desc(tm_hst);
+        tma_prefetch_desc(tm_zst);
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(smem_u32(&bars->tmem_base), 512);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    const int Q = s_prefix[a.B];
+
+    // register budget per warpgroup (x128 threads): control 40, two epilogue groups 128, two producer groups 88
+    // = 472 of the 480 the CTA owns at launch (96 x 640); an exact fit deadlocks in setmaxnreg.inc
+    if (warp < 4) {
+        reg_dec<40>();
+        if (warp == 0) {
+            // ===================== TMA producer: w_out tiles [128 v x 64 j] per CTA =====================
+            if (lane == 0) {
+                uint32_t stage = 0, phase = 0;
+                for (int q = pidx; q < Q; q += a.nP) {
+                    for (int nc = 0; nc < NC; ++nc) {
+                        const int n = min(kChunkN, a.V - nc * kChunkN);
+                        const int y = nc * kChunkN + (int)rank * (n >> 1);
+                        for (int kb = 0; kb < KB; ++kb) {
+                            mbar_wait(smem_u32(&bars->b_empty[stage]), phase ^ 1);
+                            const uint32_t full = smem_u32(&bars->b_full[stage]);
+                            mbar_arrive_expect_tx_cluster(mapa_shared(full, 0), kStageBytes);
+                            tma_load_2d_pair(smem_u32(sB + (size_t)stage * kStageBytes), tm_w, kb * kBlockK, y, full);
+                            if (++stage == kPBStages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            // ===================== MMA issuer =====================
+            if (leader) {
+                uint32_t stage = 0, phase = 0, cc = 0, tl = 0;
+                const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
+                const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+                for (int q = pidx; q < Q; q += a.nP) {
+                    for (int nc = 0; nc < NC; ++nc, ++cc) {
+                        const uint32_t buf = cc & 1;
+                        mbar_wait(smem_u32(&bars->acc_empty[buf]), ((cc >> 1) & 1) ^ 1);
+                        const int n = min(kChunkN, a.V - nc * kChunkN);
+                        const uint32_t idesc = umma_idesc_bf16(kPairM, n);
+                        const uint32_t d_tmem = tmem_base + buf * kChunkN;
+                        for (int kb = 0; kb < KB; ++kb) {
+                            if (nc == 0) mbar_wait(smem_u32(&bars->a_full[kb]), tl & 1);
+                            mbar_wait(smem_u32(&bars->b_full[stage]), phase);
+                            tc_fence_after();
+                            if (elect_one_sync()) {
+                                const uint32_t a_lo = a_lo0 + kb * (kABlockBytes >> 4);
+                                const uint32_t b_lo = b_lo0 + stage * (kStageBytes >> 4);
+#pragma unroll
+                                for (int k16 = 0; k16 < kBlockK / 16; ++k16)
+                                    umma_bf16_pair(d_tmem, mk_desc(a_lo + 2 * k16), mk_desc(b_lo + 2 * k16), idesc,
+                                                   (kb | k16) != 0);
+                                umma_commit_pair(smem_u32(&bars->b_empty[stage]));
+                                if (nc == NC - 1) umma_commit_pair(smem_u32(&bars->a_empty[kb]));
+                                if (kb == KB - 1) umma_commit_pair(smem_u32(&bars->acc_full[buf]));
+                            }
+                            __syncwarp();
+                            if (++stage == kPBStages) { stage = 0; phase ^= 1; }
+                        }
+                    }
+                    ++tl;
+                }
+            }
+        } else if (warp == 3) {
+            // ===================== h writer: every finished h block -> ring =====================
+            if (lane == 0) {
+                uint32_t tl = 0;
+                for (int q = pidx; q < Q; q += a.nP) {
+                    const int hs = q % a.NH;
+                    ring_wait(h_done + hs, (q / a.NH) * roles_v);
+                    const int row0 = hs * kPairM + (int)rank * kTileM;
+                    for (int kb = 0; kb < KB; ++kb) {
+                        mbar_wait(smem_u32(&bars->h_ready[kb]), tl & 1);
+                        tma_store_2d(tm_hst, smem_u32(sA + (size_t)kb * kABlockBytes), kb * kBlockK, row0);
+                        tma_store_commit();
+                        tma_store_wait_read<0>();
+                        mbar_arrive(smem_u32(&bars->a_empty[kb]));
+                    }
+                    ring_signal_stored(h_ready_g + hs);
+                    ++tl;
+                }
+            }
+        }
+    } else if (warp < 12) {
+        reg_inc<128>();
+        // ===================== epilogue: z -> dz -> ring =====================
+        // Two warps per TMEM lane quadrant: warp (qd, hf) owns columns [128 hf, 128 hf + 128) of every 256-wide
+        // chunk for the rows of quadrant qd; thread == lattice cell.
+        const int qd = warp & 3, hf = (warp - 4) >> 2;
+        const int row = qd * 32 + lane;
+        const int etid = threadIdx.x - 128;   // 0..255
+        uint8_t* zbuf = sZst + (warp - 4) * kZStBytes;
+        const uint32_t acc_empty0 = mapa_shared(smem_u32(&bars->acc_empty[0]), 0);
+        uint32_t cc = 0;
+        int pending = -1;                      // z slot whose stores have been issued but not yet published
+        float nb = etid < a.V ? __ldg(a.b_out + etid) : 0.f;
+        PTile ti;
+        PRaw nxt;
+        if (pidx < Q) {
+            ptile(pidx, s_prefix, a.B, ti);
+            p_load_raw(nxt, ti, ti.first_cell + (int)rank * kTileM + row, a);
+        }
+        for (int q = pidx; q < Q; q += a.nP) {
+            const PCell cur = p_finish(nxt, a.V, a.blank);
+            if (q + a.nP < Q) {   // next tile's scalars stay in flight during this tile
+                ptile(q + a.nP, s_prefix, a.B, ti);
+                p_load_raw(nxt, ti, ti.first_cell + (int)rank * kTileM + row, a);
+            }
+            for (int nc = 0; nc < NC; ++nc, ++cc) {
+                const uint32_t buf = cc & 1;
+                const int n = min(kChunkN, a.V - nc * kChunkN);
+                float* bias = s_bias + buf * kChunkN;
+                bias[etid] = nb;
+                {   // prefetch the next chunk's bias (wraps to chunk 0 for the next tile)
+                    const int nn = (nc + 1 == NC) ? 0 : nc + 1;
+                    const int i0 = nn * kChunkN + etid;
+                    nb = i0 < a.V ? __ldg(a.b_out + i0) : 0.f;
+                }
+                named_bar_sync(1, kPEpiThreads);
+                mbar_wait(smem_u32(&bars->acc_full[buf]), (cc >> 1) & 1);
+                tc_fence_after();
+                const int item = q * a.G + (nc >> 2);
+                const int zs = item % a.NZ;
+                if ((nc & 3) == 0) {
+                    // first chunk of a ring item: publish the previous item (its stores were issued a chunk
+                    // ago), then make sure every consumer has released this slot's previous content
+                    if (lane == 0) {
+                        if (pending >= 0) ring_signal_stored(z_ready + pending);
+                        ring_wait(z_done + zs, (item / a.NZ) * (1 + roles_in_group(zs % a.G, a.V)));
+                    }
+                    pending = zs;
+                    __syncwarp();
+                }
+                const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + buf * kChunkN;
+                const int gl = n >> 5;                                  // live 32-column groups of the chunk
+                const int g0 = hf * 4, g1 = min(hf * 4 + 4, (gl + 1) & ~1);   // mine (padded to whole 64-wide K blocks)
+                const int zrow = zs * kPairM + (int)rank * kTileM + qd * 32;
+                const int zcol0 = (nc & 3) * kChunkN;
+                if (g0 < g1) {
+                    uint32_t ra[32], rb[32];
+                    tmem_ld_32x32b_x32(taddr + g0 * 32, ra);
+                    for (int g = g0; g < g1; g += 2) {
+                        tmem_wait_ld();
+                        if (g + 1 < g1) tmem_ld_32x32b_x32(taddr + (g + 1) * 32, rb);
+                        dz_group(ra, bias + g * 32, nc * kChunkN + g * 32, cur, a.blank, tm_zst, zbuf,
+                                 zcol0 + g * 32, zrow, lane, g < gl);
+                        if (g + 1 < g1) {
+                            tmem_wait_ld();
+                            if (g + 2 < g1) tmem_ld_32x32b_x32(taddr + (g + 2) * 32, ra);
+                            dz_group(rb, bias + (g + 1) * 32, nc * kChunkN + (g + 1) * 32, cur, a.blank, tm_zst, zbuf,
+                                     zcol0 + (g + 1) * 32, zrow, lane, g + 1 < gl);
+                        }
+                    }
+                }
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(acc_empty0 + buf * 8);
+            }
+        }
+        if (lane == 0) {
+            if (pending >= 0) ring_signal_stored(z_ready + pending);
+            else tma_store_wait_all<0>();
+        }
+    } else {
+        reg_dec<88>();
+        // ===================== A producers: h = tanh(enc + dec) -> bf16 -> K-major SW128 smem =====================
+        const int pw = warp - 12;      // 8 producer warps, 16 rows each
+        const int c = lane & 7;        // 16-byte chunk (8 hidden units) inside the 64-wide K block
+        const int rsub = lane >> 3;    // 4 rows per warp pass
+        // flattened (tile, K block) sequence with two units of loads in flight
+        int lq = pidx - a.nP, lunit = KB;
+        uint32_t eoff[4], doff[4];
+        auto issue = [&](uint4 (&re)[4], uint4 (&rd)[4]) -> bool {
+            if (lunit == KB) {
+                lq += a.nP;
+                if (lq >= Q) { lq = Q; return false; }
+                PTile t;
+                ptile(lq, s_prefix, a.B, t);
+#pragma unroll
+                for (int p = 0; p < 4; ++p) {
+                    const int row = pw * 16 + p * 4 + rsub;
+                    const int m = min(t.first_cell + (int)rank * kTileM + row, t.n_cells - 1);  // clamp padding rows
+                    const int tt = m / t.U1b, u = m - tt * t.U1b;
+                    eoff[p] = (uint32_t)(((size_t)t.b * a.T + tt) * a.J) + c * 8;
+                    doff[p] = (uint32_t)(((size_t)t.b * a.U1 + u) * a.J) + c * 8;
+                }
+                lunit = 0;
+            }
+#pragma unroll
+            for (int p = 0; p < 4; ++p) {
+                re[p] = __ldg(reinterpret_cast<const uint4*>(a.enc + eoff[p] + lunit * kBlockK));
+                rd[p] = __ldg(reinterpret_cast<const uint4*>(a.dec + doff[p] + lunit * kBlockK));
+            }
+            ++lunit;
+            return true;
+        };
+        uint32_t wkb = 0, wtl = 0;
+        const uint32_t a_full0 = mapa_shared(smem_u32(&bars->a_full[0]), 0);
+        auto work = [&](const uint4 (&re)[4], const uint4 (&rd)[4]) {
+            mbar_wait(smem_u32(&bars->a_empty[wkb]), (wtl & 1) ^ 1);
+            produce_h16(re, rd, pw, rsub, c, sA + (size_t)wkb * kABlockBytes);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&bars->h_ready[wkb]));
+                mbar_arrive_cluster(a_full0 + wkb * 8);
+            }
+            if (++wkb == (uint32_t)KB) { wkb = 0; ++wtl; }
+        };
+        uint4 e0[4], d0[4], e1[4], d1[4];
+        bool v0 = issue(e0, d0);
+        bool v1 = v0 && issue(e1, d1);
+        while (v0) {
+            work(e0, d0);
+            v0 = v1 && issue(e0, d0);
+            if (!v1) break;
+            work(e1, d1);
+            v1 = v0 && issue(e1, d1);
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+// =================================================================================================
+// D role: dh[256 cells x J] = dz W, dz from the ring
+// =================================================================================================
+struct __align__(16) DBars {
+    uint64_t dz_full[kDZStages], dz_empty[kDZStages];
+    uint64_t op_full[kDOpStages], op_empty[kDOpStages];
+    uint64_t acc_full, acc_empty;
+    uint32_t tmem_base;
+    uint32_t pad[3];
+};
+
+__device__ __forceinline__ void role_dh(const RingArgs& a, const CUtensorMap* tm_w, const CUtensorMap* tm_z,
+                                        const CUtensorMap* tm_d, uint8_t* smem, int didx) {
+    const int NKB = (a.V + kBlockK - 1) / kBlockK;
+    const int NMMA = (a.J + 255) / 256;
+    const uint32_t op_bytes = (uint32_t)a.J * 64;      // this CTA's half of a [64 v x J] w_out block
+    uint8_t* sZ = smem;
+    uint8_t* sW = sZ + (size_t)kDZStages * kStageBytes;
+    uint8_t* sDst = sW + (size_t)kDOpStages * op_bytes;
+    DBars* bars = reinterpret_cast<DBars*>(sDst + kDrainWarps * kDrainBufBytes);
+    int* s_prefix = reinterpret_cast<int*>(bars + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    int* z_ready = a.flags;
+    int* z_done = a.flags + a.NZ;
+    const int tpu = tiles128_per_utt(a.T, a.U1);
+
+    for (int i = threadIdx.x; i < 2 * a.B + 1; i += kRingThreads) s_prefix[i] = __ldg(a.prefix + i);
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kDZStages; ++i) {
+            mbar_init(smem_u32(&bars->dz_full[i]), 2);
+            mbar_init(smem_u32(&bars->dz_empty[i]), 1);
+        }
+        for (int i = 0; i < kDOpStages; ++i) {
+            mbar_init(smem_u32(&bars->op_full[i]), 2);
+            mbar_init(smem_u32(&bars->op_empty[i]), 1);
+        }
+        mbar_init(smem_u32(&bars->acc_full), 1);
+        mbar_init(smem_u32(&bars->acc_empty), 2 * kDrainWarps);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(tm_w);
+        tma_prefetch_desc(tm_z);
+        tma_prefetch_desc(tm_d);
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(smem_u32(&bars->tmem_base), 512);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    const int Q = s_prefix[a.B];
+
+    if (warp == 0) {
+        // ===================== TMA: w_out blocks [64 v x J/2] (this CTA's half of every MMA's N range) ==========
+        if (lane == 0) {
+            uint32_t slot = 0, ph = 0;
+            for (int q = didx; q < Q; q += a.nD) {
+                for (int kb = 0; kb < NKB; ++kb) {
+                    mbar_wait(smem_u32(&bars->op_empty[slot]), ph ^ 1);
+                    const uint32_t full = smem_u32(&bars->op_full[slot]);
+                    mbar_arrive_expect_tx_cluster(mapa_shared(full, 0), op_bytes);
+                    uint32_t dst = smem_u32(sW + (size_t)slot * op_bytes);
+                    for (int n = 0; n < NMMA; ++n) {
+                        const int half = min(256, a.J - n * 256) >> 1;
+                        for (int b = 0; b < half; b += kBlockK) {
+                            tma_load_2d_pair(dst, tm_w, n * 256 + (int)rank * half + b, kb * kBlockK, full);
+                            dst += kBoxBytes;
+                        }
+                    }
+                    if (++slot == kDOpStages) { slot = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== TMA: this CTA's dz blocks [128 cells x 64 v] from the ring =====================
+        if (lane == 0) {
+            uint32_t zs = 0, zph = 0;
+            for (int q = didx; q < Q; q += a.nD) {
+                for (int kb = 0; kb < NKB; ++kb) {
+                    const int item = q * a.G + kb / (kVG / kBlockK);
+                    const int rs = item % a.NZ;
+                    if (kb % (kVG / kBlockK) == 0) ring_wait(z_ready + rs, (item / a.NZ + 1) * 2 * (kPEpiThreads / 32));
+                    mbar_wait(smem_u32(&bars->dz_empty[zs]), zph ^ 1);
+                    const uint32_t full = smem_u32(&bars->dz_full[zs]);
+                    mbar_arrive_expect_tx_cluster(mapa_shared(full, 0), kStageBytes);
+                    tma_load_2d_pair(smem_u32(sZ + (size_t)zs * kStageBytes), tm_z, (kb % (kVG / kBlockK)) * kBlockK,
+                                     rs * kPairM + (int)rank * kTileM, full);
+                    if (++zs == kDZStages) { zs = 0; zph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA) =====================
+        if (leader) {
+            uint32_t zs = 0, zph = 0, slot = 0, ph = 0, tl = 0;
+            const uint32_t z_lo0 = desc_lo(smem_u32(sZ), 16);
+            const uint32_t w_lo0 = desc_lo(smem_u32(sW), kBoxBytes);
+            for (int q = didx; q < Q; q += a.nD) {
+                mbar_wait(smem_u32(&bars->acc_empty), (tl & 1) ^ 1);
+                for (int kb = 0; kb < NKB; ++kb) {
+                    mbar_wait(smem_u32(&bars->dz_full[zs]), zph);
+                    mbar_wait(smem_u32(&bars->op_full[slot]), ph);
+                    tc_fence_after();
+                    if (elect_one_sync()) {
+                        // the ring item has been read completely once its last K block has landed
+                        if ((kb + 1) % (kVG / kBlockK) == 0 || kb == NKB - 1)
+                            red_release_gpu(z_done + (q * a.G + kb / (kVG / kBlockK)) % a.NZ);
+                        const uint32_t a_lo = z_lo0 + zs * (kStageBytes >> 4);
+                        const uint32_t b_lo = w_lo0 + slot * (op_bytes >> 4);
+#pragma unroll
+                        for (int k16 = 0; k16 < kBlockK / 16; ++k16) {
+                            for (int n = 0; n < NMMA; ++n) {
+                                const int Nn = min(256, a.J - n * 256);
+                                umma_bf16_pair(tmem_base + n * 256, mk_desc(a_lo + 2 * k16),
+                                               mk_desc(b_lo + n * (2 * kBoxBytes >> 4) + k16 * (2048 >> 4)),
+                                               umma_idesc_bf16(kPairM, Nn, 0, 1), (kb | k16) != 0);
+                            }
+                        }
+                        umma_commit_pair(smem_u32(&bars->dz_empty[zs]));
+                        umma_commit_pair(smem_u32(&bars->op_empty[slot]));
+                        if (kb == NKB - 1) umma_commit_pair(smem_u32(&bars->acc_full));
+                    }
+                    __syncwarp();
+                    if (++zs == kDZStages) { zs = 0; zph ^= 1; }
+                    if (++slot == kDOpStages) { slot = 0; ph ^= 1; }
+                }
+                ++tl;
+            }
+        }
+    } else if (warp >= 20 - kDrainWarps) {
+        // ===================== drain: dh -> bf16, tile-major (rows of the h-cache layout, J) =====================
+        // Each warp moves its [32 cells x 64 j] blocks through a private shared-memory buffer (128B swizzle,
+        // conflict-free 16-byte stores) and one TMA store per block; the factor (1 - h^2) is applied by the
+        // reduction kernel.
+        const int dw = warp - (20 - kDrainWarps);
+        const int qd = warp & 3, hf = (dw >> 2) & 1;
+        const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+        const uint32_t acc_empty_addr = mapa_shared(smem_u32(&bars->acc_empty), 0);
+        const int G = a.J >> 6;              // 32-column groups per column half
+        const int col_base = hf * (a.J >> 1);
+        uint8_t* buf = sDst + dw * kDrainBufBytes;
+        uint8_t* rowp = buf + lane * 128;
+        const int sw = lane & 7;
+        uint32_t tl = 0;
+        PTile ti;
+        for (int q = didx; q < Q; q += a.nD) {
+            ptile(q, s_prefix, a.B, ti);
+            const int row0 = (ti.b * tpu + (ti.first_cell + (int)rank * kTileM) / kTileM) * kTileM + qd * 32;
+            mbar_wait(smem_u32(&bars->acc_full), tl & 1);
+            tc_fence_after();
+            for (int g = 0; g < G; g += 2) {     // two 32-column groups = one 128-byte row piece per TMA store
+                uint32_t ra[32], rb[32];
+                tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + g * 32, ra);
+                tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + g * 32 + 32, rb);
+                tmem_wait_ld();
+                if (lane == 0) tma_store_wait_read<0>();   // the previous block has left the buffer
+                __syncwarp();
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(
+                        pack_bf16x2(__uint_as_float(ra[8 * j]), __uint_as_float(ra[8 * j + 1])),
+                        pack_bf16x2(__uint_as_float(ra[8 * j + 2]), __uint_as_float(ra[8 * j + 3])),
+                        pack_bf16x2(__uint_as_float(ra[8 * j + 4]), __uint_as_float(ra[8 * j + 5])),
+                        pack_bf16x2(__uint_as_float(ra[8 * j + 6]), __uint_as_float(ra[8 * j + 7])));
+                    *reinterpret_cast<uint4*>(rowp + (((4 + j) ^ sw) << 4)) = make_uint4(
+                        pack_bf16x2(__uint_as_float(rb[8 * j]), __uint_as_float(rb[8 * j + 1])),
+                        pack_bf16x2(__uint_as_float(rb[8 * j + 2]), __uint_as_float(rb[8 * j + 3])),
+                        pack_bf16x2(__uint_as_float(rb[8 * j + 4]), __uint_as_float(rb[8 * j + 5])),
+                        pack_bf16x2(__uint_as_float(rb[8 * j + 6]), __uint_as_float(rb[8 * j + 7])));
+                }
+                fence_proxy_async_smem();
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(tm_d, smem_u32(buf), col_base + g * 32, row0);
+                    tma_store_commit();
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(acc_empty_addr);
+            ++tl;
+        }
+        if (lane == 0) tma_store_wait_all<0>();
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+// =================================================================================================
+// W role: dW[256 v x J] += dz^T h over the tiles of this pair's split; d_b_out = column sums of dz
+// =================================================================================================
+struct __align__(16) WBars {
+    uint64_t z_full[kWZStages];     // local: TMA bytes of this CTA's dz blocks
+    uint64_t dz_full[kWZStages];    // leader: column-sum warps of both CTAs have read the stage
+    uint64_t dz_empty[kWZStages];   // both CTAs (multicast commit): the MMAs have read the stage
+    uint64_t op_full[kWOpStages], op_empty[kWOpStages];
+    uint64_t acc_full;
+    uint32_t tmem_base;
+    uint32_t pad[1];
+};
+
+__device__ __forceinline__ void role_dw(const RingArgs& a, const CUtensorMap* tm_z, const CUtensorMap* tm_h,
+                                        uint8_t* smem, int widx) {
+    const int NMMA = (a.J + 255) / 256;
+    const uint32_t op_bytes = (uint32_t)a.J * 64;      // this CTA's half of a [64 cells x J] h block
+    uint8_t* sZ = smem;
+    uint8_t* sH = sZ + (size_t)kWZStages * kStageBytes;
+    WBars* bars = reinterpret_cast<WBars*>(sH + (size_t)kWOpStages * op_bytes);
+    int* s_prefix = reinterpret_cast<int*>(bars + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    int* z_ready = a.flags;
+    int* z_done = a.flags + a.NZ;
+    int* h_ready_g = a.flags + 2 * a.NZ;
+    int* h_done = a.flags + 2 * a.NZ + a.NH;
+    const int roles_v = (a.V + 255) >> 8;
+    const int role = widx % roles_v, split = widx / roles_v;
+    const int gr = (role * 256) / kVG;                       // vocab group of this role's slab
+    const int v0_cta = role * 256 + (int)rank * kTileM;      // first vocab row of this CTA
+    const int vloc = v0_cta - gr * kVG;                      // column inside the ring item
+
+    for (int i = threadIdx.x; i < 2 * a.B + 1; i += kRingThreads) s_prefix[i] = __ldg(a.prefix + i);
+    if (warp == 1 && lane == 0) {
+        for (int i = 0; i < kWZStages; ++i) {
+            mbar_init(smem_u32(&bars->z_full[i]), 1);
+            mbar_init(smem_u32(&bars->dz_full[i]), 2 * kColsumWarps);
+            mbar_init(smem_u32(&bars->dz_empty[i]), 1);
+        }
+        for (int i = 0; i < kWOpStages; ++i) {
+            mbar_init(smem_u32(&bars->op_full[i]), 2);
+            mbar_init(smem_u32(&bars->op_empty[i]), 1);
+        }
+        mbar_init(smem_u32(&bars->acc_full), 1);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(tm_z);
+        tma_prefetch_desc(tm_h);
+    }
+    if (warp == 2) {
+        tmem_alloc_pair(smem_u32(&bars->tmem_base), 512);
+        tmem_relinquish_pair();
+    }
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem_base = bars->tmem_base;
+    const int Q = s_prefix[a.B];
+    const int n_tiles = split < Q ? (Q - split + a.nS - 1) / a.nS : 0;
+    const int n_kb = 4 * n_tiles;    // 64-cell K blocks (padding rows of a tile carry dz = 0)
+
+    if (warp == 0) {
+        // ===================== TMA: h blocks [64 cells x J/2] from the ring =====================
+        if (lane == 0) {
+            uint32_t slot = 0, ph = 0;
+            for (int q = split; q < Q; q += a.nS) {
+                const int hs = q % a.NH;
+                ring_wait(h_ready_g + hs, (q / a.NH + 1) * 2);
+                for (int kh = 0; kh < 4; ++kh) {
+                    mbar_wait(smem_u32(&bars->op_empty[slot]), ph ^ 1);
+                    const uint32_t full = smem_u32(&bars->op_full[slot]);
+                    mbar_arrive_expect_tx_cluster(mapa_shared(full, 0), op_bytes);
+                    uint32_t dst = smem_u32(sH + (size_t)slot * op_bytes);
+                    for (int n = 0; n < NMMA; ++n) {
+                        const int half = min(256, a.J - n * 256) >> 1;
+                        for (int b = 0; b < half; b += kBlockK) {
+                            tma_load_2d_pair(dst, tm_h, n * 256 + (int)rank * half + b, hs * kPairM + kh * 64, full);
+                            dst += kBoxBytes;
+                        }
+                    }
+                    if (++slot == kWOpStages) { slot = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 2) {
+        // ===================== TMA: dz blocks [64 cells x 128 v] of this CTA's vocab rows =====================
+        if (lane == 0) {
+            uint32_t zs = 0, zph = 0;
+            for (int q = split; q < Q; q += a.nS) {
+                const int item = q * a.G + gr;
+                const int rs = item % a.NZ;
+                ring_wait(z_ready + rs, (item / a.NZ + 1) * 2 * (kPEpiThreads / 32));
+                for (int kh = 0; kh < 4; ++kh) {
+                    mbar_wait(smem_u32(&bars->dz_empty[zs]), zph ^ 1);
+                    const uint32_t full = smem_u32(&bars->z_full[zs]);
+                    mbar_arrive_expect_tx(full, kStageBytes);
+                    const uint32_t dst = smem_u32(sZ + (size_t)zs * kStageBytes);
+                    tma_load_2d(dst, tm_z, vloc, rs * kPairM + kh * 64, full);
+                    tma_load_2d(dst + kBoxBytes, tm_z, vloc + kBlockK, rs * kPairM + kh * 64, full);
+                    if (++zs == kWZStages) { zs = 0; zph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===================== MMA issuer (leader CTA) =====================
+        if (leader) {
+            uint32_t zs = 0, zph = 0, slot = 0, ph = 0;
+            const uint32_t z_lo0 = desc_lo(smem_u32(sZ), kBoxBytes);
+            const uint32_t h_lo0 = desc_lo(smem_u32(sH), kBoxBytes);
+            int q = split;
+            for (int kbi = 0; kbi < n_kb; ++kbi) {
+                mbar_wait(smem_u32(&bars->dz_full[zs]), zph);
+                mbar_wait(smem_u32(&bars->op_full[slot]), ph);
+                tc_fence_after();
+                if (elect_one_sync()) {
+                    if ((kbi & 3) == 3) {   // the tile's ring items have been read completely by this pair
+                        red_release_gpu(z_done + (q * a.G + gr) % a.NZ);
+                        red_release_gpu(h_done + q % a.NH);
+                    }
+                    const uint32_t a_lo = z_lo0 + zs * (kStageBytes >> 4);
+                    const uint32_t b_lo = h_lo0 + slot * (op_bytes >> 4);
+#pragma unroll
+                    for (int k16 = 0; k16 < 4; ++k16) {
+                        for (int n = 0; n < NMMA; ++n) {
+                            const int Nn = min(256, a.J - n * 256);
+                            umma_bf16_pair(tmem_base + n * 256, mk_desc(a_lo + k16 * (2048 >> 4)),
+                                           mk_desc(b_lo + n * (2 * kBoxBytes >> 4) + k16 * (2048 >> 4)),
+                                           umma_idesc_bf16(kPairM, Nn, 1, 1), (kbi | k16) != 0);
+                        }
+                    }
+                    umma_commit_pair(smem_u32(&bars->dz_empty[zs]));
+                    umma_commit_pair(smem_u32(&bars->op_empty[slot]));
+                }
+                __syncwarp();
+                if ((kbi & 3) == 3) q += a.nS;
+                if (++zs == kWZStages) { zs = 0; zph ^= 1; }
+                if (++slot == kWOpStages) { slot = 0; ph ^= 1; }
+            }
+            if (elect_one_sync()) umma_commit_pair(smem_u32(&bars->acc_full));
+            __syncwarp();
+        }
+    } else if (warp >= 4 && warp < 4 + kColsumWarps) {
+        // ===================== column sums of dz (d_b_out), then the flush of dW =====================
+        // thread = (64-wide vocab box, 16-byte chunk c = 8 vocab entries, 4 consecutive cells); each thread owns
+        // an 8-wide vocab strip for the whole kernel
+        const int tt = threadIdx.x - 128;
+        const int box = tt >> 7, t7 = tt & 127;
+        const int c = t7 & 7, r0 = (t7 >> 3) * 4;
+        const int vb = v0_cta + box * kBlockK + c * 8;
+        const uint32_t dz_full0 = mapa_shared(smem_u32(&bars->dz_full[0]), 0);
+        uint32_t off[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int row = r0 + i;
+            off[i] = box * kBoxBytes + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
+        }
+        float colsum[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) colsum[e] = 0.f;
+        uint32_t zs = 0, zph = 0;
+        for (int kbi = 0; kbi < n_kb; ++kbi) {
+            const uint8_t* st = sZ + (size_t)zs * kStageBytes;
+            mbar_wait(smem_u32(&bars->z_full[zs]), zph);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const uint4 v = *reinterpret_cast<const uint4*>(st + off[i]);
+                colsum[0] += __uint_as_float(v.x << 16); colsum[1] += __uint_as_float(v.x & 0xffff0000u);
+                colsum[2] += __uint_as_float(v.y << 16); colsum[3] += __uint_as_float(v.y & 0xffff0000u);
+                colsum[4] += __uint_as_float(v.z << 16); colsum[5] += __uint_as_float(v.z & 0xffff0000u);
+                colsum[6] += __uint_as_float(v.w << 16); colsum[7] += __uint_as_float(v.w & 0xffff0000u);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(dz_full0 + zs * 8);
+            if (++zs == kWZStages) { zs = 0; zph ^= 1; }
+        }
+        // ---- d_b_out: lanes with equal (lane & 7) hold the same vocab strip
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            colsum[e] += __shfl_xor_sync(0xffffffffu, colsum[e], 8);
+            colsum[e] += __shfl_xor_sync(0xffffffffu, colsum[e], 16);
+        }
+        if (lane < 8) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+                if (vb + e < a.V && colsum[e] != 0.f) atomicAdd(a.d_b_out + vb + e, colsum[e]);
+        }
+        // ---- flush dW: TMEM lane = vocab row, columns = hidden units
+        const int dw = warp - 4;
+        const int qd = warp & 3, hf = dw >> 2;
+        const int v = v0_cta + qd * 32 + lane;
+        const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
+        const int G = a.J >> 6;
+        const int col_base = hf * (a.J >> 1);
+        mbar_wait(smem_u32(&bars->acc_full), 0);
+        tc_fence_after();
+        if (n_kb > 0) {
+            for (int g = 0; g < G; ++g) {
+                uint32_t r[32];
+                tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + g * 32, r);
+                tmem_wait_ld();
+                if (v < a.V) {
+                    float* dst = a.d_w_out + (size_t)v * a.J + col_base + g * 32;
+#pragma unroll
+                    for (int i = 0; i < 32; i += 4)
+                        red_add_v4(dst + i, __uint_as_float(r[i]), __uint_as_float(r[i + 1]),
+                                   __uint_as_float(r[i + 2]), __uint_as_float(r[i + 3]));
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) {
+        tc_fence_after();
+        tmem_dealloc_pair(tmem_base, 512);
+    }
+}
+
+// =================================================================================================
+__global__ void __launch_bounds__(kRingThreads, 1)
+joint_bwd_ring_kernel(const __grid_constant__ CUtensorMap tm_w_p,    // w_out bf16 (V,J), box [64 j x 128 v]
+                      const __grid_constant__ CUtensorMap tm_w_d,    // w_out bf16 (V,J), box [64 j x 64 v]
+                      const __grid_constant__ CUtensorMap tm_h_st,   // ring h (NH*256, J), box [64 j x 128 cells]
+                      const __grid_constant__ CUtensorMap tm_h_ld,   // ring h, box [64 j x 64 cells]
+                      const __grid_constant__ CUtensorMap tm_z_st,   // ring dz (NZ*256, VGW), box [32 v x 32 cells], 64B swizzle
+                      const __grid_constant__ CUtensorMap tm_z_ld_d, // ring dz, box [64 v x 128 cells]
+                      const __grid_constant__ CUtensorMap tm_z_ld_w, // ring dz, box [64 v x 64 cells]
+                      const __grid_constant__ CUtensorMap tm_dh,     // dh out bf16 (rows,J), box [64 j x 32 cells]
+                      const RingArgs a) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    const int pair = blockIdx.x >> 1;
+    if (pair < a.nP) role_produce(a, &tm_w_p, &tm_h_st, &tm_z_st, smem, pair);
+    else if (pair < a.nP + a.nD) role_dh(a, &tm_w_d, &tm_z_ld_d, &tm_dh, smem, pair - a.nP);
+    else role_dw(a, &tm_z_ld_w, &tm_h_ld, smem, pair - a.nP - a.nD);
+}
+
+size_t ring_smem_bytes(int B, int J) {
+    const size_t prefix = (size_t)(2 * B + 1) * sizeof(int);
+    const size_t p = (size_t)(J / kBlockK) * kABlockBytes + (size_t)kPBStages * kStageBytes +
+                     (kPEpiThreads / 32) * kZStBytes + sizeof(PBars) + 2 * kChunkN * sizeof(float) + prefix;
+    const size_t d = (size_t)kDZStages * kStageBytes + (size_t)kDOpStages * J * 64 + kDrainWarps * kDrainBufBytes +
+                     sizeof(DBars) + prefix;
+    const size_t w = (size_t)kWZStages * kStageBytes + (size_t)kWOpStages * J * 64 + sizeof(WBars) + prefix;
+    return max(p, max(d, w));
+}
+
+struct RingGeom {
+    int vgw;            // columns of a z slot
+    int G;              // vocab groups per tile
+    int NZ, NH;
+    size_t z_bytes, h_bytes, flag_bytes, prefix_bytes;
+};
+RingGeom ring_geom(int B, int J, int V) {
+    RingGeom g;
+    g.vgw = (min(V, kVG) + 63) / 64 * 64;
+    g.G = ceil_div(V, kVG);
+    g.NZ = kRingSlots / g.G * g.G;      // a multiple of G: a slot always serves the same vocab group
+    g.NH = kRingSlots;
+    g.z_bytes = align_up((size_t)g.NZ * kPairM * g.vgw * 2, 1024);
+    g.h_bytes = align_up((size_t)g.NH * kPairM * J * 2, 1024);
+    g.flag_bytes = align_up((size_t)(2 * g.NZ + 2 * g.NH) * sizeof(int), 256);
+    g.prefix_bytes = align_up((size_t)(2 * B + 1) * sizeof(int), 256);
+    return g;
+}
+
+// resident CTA pairs of the ring kernel on the current device (cached per device)
+int ring_max_pairs(size_t smem) {
+    static thread_local int cached_dev = -1, cached = 0;
+    static thread_local size_t cached_smem = 0;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+    if (dev == cached_dev && smem == cached_smem) return cached;
+    if (cudaFuncSetAttribute(joint_bwd_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) !=
+        cudaSuccess)
+        return 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(sm_count() / 2 * 2);
+    cfg.blockDim = dim3(kRingThreads);
+    cfg.dynamicSmemBytes = smem;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, joint_bwd_ring_kernel, &cfg) != cudaSuccess) n = 0;
+    cached = min(n, sm_count() / 2);
+    cached_dev = dev;
+    cached_smem = smem;
+    return cached;
+}
+
+}  // namespace
+
+bool joint_ring_supported(int B, int T, int U1, int J, int V) {
+    return B <= kMaxB && T < 65536 && U1 < 65536 && J % 128 == 0 && J <= kMaxKBlocks * kBlockK && V % 32 == 0 &&
+           ring_smem_bytes(B, J) <= (size_t)kSmemLimit;
+}
+
+size_t joint_ring_workspace(int B, int T, int U1, int J, int V) {
+    const RingGeom g = ring_geom(B, J, V);
+    return g.z_bytes + g.h_bytes + g.flag_bytes + g.prefix_bytes;
+}
+
+// Role split of the resident pairs.  The three roles execute one GEMM unit each; the producer also does the
+// tanh / exp work, so it gets the larger share (measured: profiles/r2*_ring_split.txt).
+void ring_split(int pairs, int V, int& nP, int& nD, int& nS) {
+    const int roles_v = ceil_div(V, 256);
+    nS = max(1, (int)(pairs * 0.30f / roles_v + 0.5f));
+    while (nS > 1 && pairs - nS * roles_v < 2) --nS;
+    const int rest = pairs - nS * roles_v;
+    nD = max(1, (int)(rest * 0.46f + 0.5f));
+    nP = rest - nD;
+#ifdef EMO_TUNING
+    if (const char* e = getenv("EMO_RING_SPLIT")) {   // "nP,nD,nS": tuning builds only (tools/)
+        int p, d, s;
+        if (sscanf(e, "%d,%d,%d", &p, &d, &s) == 3 && p > 0 && d > 0 && s > 0 && p + d + s * roles_v <= pairs) {
+            nP = p; nD = d; nS = s;
+        }
+    }
+#endif
+}
+
+int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec_h, const float* b_out,
+                          const int* labels, const int* tlen, const int* ulen, const float* lse, const float* lp2,
+                          const float* gamma2, const float* grad_cost, int B, int T, int U1, int J, int V, int blank,
+                          void* dh_ws, void* ring_ws, float* d_w_out, float* d_b_out, cudaStream_t st) {
+    EMO_REQUIRE(joint_ring_supported(B, T, U1, J, V), EMO_UNSUPPORTED_SHAPE,
+                "joint_bwd(bf16, ring): needs B <= %d, J %% 128 == 0, J <= 512, V %% 32 == 0", kMaxB);
+    const RingGeom g = ring_geom(B, J, V);
+    char* zring = (char*)ring_ws;
+    char* hring = zring + g.z_bytes;
+    int* flags = reinterpret_cast<int*>(hring + g.h_bytes);
+    int* prefix = reinterpret_cast<int*>((char*)flags + g.flag_bytes);
+    const size_t smem = ring_smem_bytes(B, J);
+    const int pairs = ring_max_pairs(smem);
+    const int roles_v = ceil_div(V, 256);
+    EMO_REQUIRE(pairs >= roles_v + 2, EMO_UNSUPPORTED_SHAPE,
+                "joint_bwd(bf16, ring): %d resident CTA pairs cannot host %d vocabulary roles", pairs, roles_v);
+    RingArgs a;
+    a.enc = (const __half*)enc_h; a.dec = (const __half*)dec_h; a.b_out = b_out; a.labels = labels;
+    a.lse = lse; a.lp2 = lp2; a.gamma2 = gamma2; a.grad_cost = grad_cost; a.prefix = prefix; a.flags = flags;
+    a.d_w_out = d_w_out; a.d_b_out = d_b_out;
+    a.B = B; a.T = T; a.U1 = U1; a.J = J; a.V = V; a.blank = blank;
+    ring_split(pairs, V, a.nP, a.nD, a.nS);
+    a.NZ = g.NZ; a.NH = g.NH; a.G = g.G;
+
+    ring_prep_kernel<<<1, kMaxB, 0, st>>>(tlen, ulen, B, T, U1, prefix, flags, 2 * g.NZ + 2 * g.NH);
+    EMO_CHECK_LAUNCH("ring_prep_kernel");
+
+    CUtensorMap tm_w_p, tm_w_d, tm_h_st, tm_h_ld, tm_z_st, tm_z_ld_d, tm_z_ld_w, tm_dh;
+    int rc;
+    if ((rc = make_tmap_bf16_2d(&tm_w_p, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, kChunkN / 2))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm_w_d, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, 64))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm_h_st, hring, (uint64_t)J, (uint64_t)g.NH * kPairM, kBlockK, kTileM))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm_h_ld, hring, (uint64_t)J, (uint64_t)g.NH * kPairM, kBlockK, 64))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm_z_st, zring, (uint64_t)g.vgw, (uint64_t)g.NZ * kPairM, 32, 32,
+                                CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm_z_ld_d, zring, (uint64_t)g.vgw, (uint64_t)g.NZ * kPairM, kBlockK, kTileM))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm_z_ld_w, zring, (uint64_t)g.vgw, (uint64_t)g.NZ * kPairM, kBlockK, 64))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tm_dh, dh_ws, (uint64_t)J, (uint64_t)B * tiles128_per_utt(T, U1) * kTileM, 64, 32)))
+        return rc;
+
+    EMO_CUDA(cudaFuncSetAttribute(joint_bwd_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * (a.nP + a.nD + a.nS * roles_v));
+    cfg.blockDim = dim3(kRingThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    EMO_CUDA(cudaLaunchKernelEx(&cfg, joint_bwd_ring_kernel, tm_w_p, tm_w_d, tm_h_st, tm_h_ld, tm_z_st, tm_z_ld_d,
+                                tm_z_ld_w, tm_dh, a));
+    EMO_CHECK_LAUNCH("joint_bwd_ring_kernel");
+    return EMO_OK;
+}
+
+
+// ---- workspace / launch accounting of the bf16 joint (include/emoasr_b200.h) ---------------------
+static size_t casts_bytes(int B, int T, int U1, int J, int V) {
+    return align_up((size_t)V * J * sizeof(__nv_bfloat16), 256) + align_up((size_t)B * T * J * sizeof(__half), 256) +
+           align_up((size_t)B * U1 * J * sizeof(__half), 256);
+}
+
+size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V) {
+    if (op == EMO_OP_RNNT_JOINT_HZCACHE) {
+        if (!joint_zc_supported(J) || J % 128 != 0 || V % 32 != 0) return 0;
+        return zcache_offset_for(B, T, U1, J) + align_up(zcache_bytes_for(B, T, U1, V), 256);
+    }
+    if (op == EMO_OP_RNNT_JOINT_FWD) return casts_bytes(B, T, U1, J, V);
+    if (op == EMO_OP_RNNT_JOINT_BWD) {
+        // bf16 w_out + fp16 streams, tile-major dh (bf16, rows of the valid cells), the dz / h ring and its flags
+        size_t n = casts_bytes(B, T, U1, J, V) + align_up(hcache_bytes_for(B, T, U1, J), 1024);
+        if (joint_ring_supported(B, T, U1, J, V)) n += joint_ring_workspace(B, T, U1, J, V);
+        return n;
+    }
+    return 0;
+}
+
+int joint_bf16_launches(int op, int B, int T, int U1, int J, int V) {
+    (void)B; (void)T; (void)U1; (void)J; (void)V;
+    if (op == EMO_OP_RNNT_JOINT_BWD) return 6;  // 3 casts, ring prep, ring kernel, axis reductions
+    if (op == EMO_OP_RNNT_JOINT_HZCACHE) return 4;  // backward on the z-cache route: weight cast, dhz, axis reductions, dWz
+    return 4;                                    // weight cast, 2 stream casts, fused joint forward
+}
+
+// casts shared by forward and backward: w_out -> bf16, enc_proj / dec_proj -> fp16 (11-bit mantissa, half the
+// gather bytes of fp32); layout of the head of every bf16 workspace
+int joint_bf16_casts(const float* enc_proj, const float* dec_proj, const float* w_out, int B, int T, int U1, int J,
+                     int V, void* ws, const void** w_bf16, const void** enc_h, const void** dec_h, cudaStream_t st) {
+    const size_t nw = (size_t)V * J, ne = (size_t)B * T * J, nd = (size_t)B * U1 * J;
+    __nv_bfloat16* w = reinterpret_cast<__nv_bfloat16*>(ws);
+    __half* e = reinterpret_cast<__half*>((char*)ws + align_up(nw * sizeof(__nv_bfloat16), 256));
+    __half* d = reinterpret_cast<__half*>((char*)e + align_up(ne * sizeof(__half), 256));
+    f32_to_bf16_kernel<<<ceil_div(nw, 4 * 256), 256, 0, st>>>(w_out, w, nw);
+    EMO_CHECK_LAUNCH("f32_to_bf16_kernel");
+    if (enc_h) {
+        f32_to_f16_kernel<<<ceil_div(ne, 4 * 256), 256, 0, st>>>(enc_proj, e, ne);
+        f32_to_f16_kernel<<<ceil_div(nd, 4 * 256), 256, 0, st>>>(dec_proj, d, nd);
+        EMO_CHECK_LAUNCH("f32_to_f16_kernel");
+        *enc_h = e;
+        *dec_h = d;
+    }
+    *w_bf16 = w;
+    return EMO_OK;
+}
+
+int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
+                   const float* b_out, const int* labels, const int* tlen, const int* ulen,
+                   const float* lse, const float* lp2, const float* gamma2, const float* grad_cost,
+                   const void* hcache, size_t hcache_bytes, int B, int T,
+                   int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
+                   float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+    EMO_REQUIRE(enc_proj && dec_proj && w_out && b_out && labels && tlen && ulen && lse && gamma2 && grad_cost &&
+                    d_enc_proj && d_dec_proj && d_w_out && d_b_out && ws,
+                EMO_BAD_ARG, "joint_bwd(bf16): null pointer");
+    int rc = check_bf16_shape(B, T, U1, J, V, blank);
+    if (rc) return rc;
+    EMO_REQUIRE(ws_bytes >= joint_bf16_workspace(EMO_OP_RNNT_JOINT_BWD, B, T, U1, J, V),
+                EMO_WORKSPACE_TOO_SMALL, "joint_bwd(bf16): workspace too small");
+    EMO_REQUIRE(((uintptr_t)ws & 255) == 0 && ((uintptr_t)w_out & 15) == 0 && ((uintptr_t)d_w_out & 15) == 0 &&
+                    ((uintptr_t)enc_proj & 15) == 0 && ((uintptr_t)dec_proj & 15) == 0,
+                EMO_BAD_ARG, "joint_bwd(bf16): pointers must be 16-byte (workspace 256-byte) aligned");
+    const size_t nw = (size_t)V * J;
+    void* dh_ws = (char*)ws + casts_bytes(B, T, U1, J, V);
+    EMO_CUDA(cudaMemsetAsync(d_w_out, 0, nw * sizeof(float), st));
+    EMO_CUDA(cudaMemsetAsync(d_b_out, 0, (size_t)V * sizeof(float), st));
+    EMO_CUDA(cudaMemsetAsync(d_dec_proj, 0, (size_t)B * U1 * J * sizeof(float), st));
+
+    // ---- z-cache variant: the caller let the forward store the logits (fp16) behind an h cache
+    const bool zc = hcache && joint_zc_supported(J) &&
+                    hcache_bytes >= zcache_offset_for(B, T, U1, J) + zcache_bytes_for(B, T, U1, V);
+    const void *w_bf16, *enc_h = nullptr, *dec_h = nullptr;
+    if (zc) {
+        EMO_REQUIRE(((uintptr_t)hcache & 255) == 0, EMO_BAD_ARG, "joint_bwd(bf16): cache misaligned");
+        rc = joint_bf16_casts(enc_proj, dec_proj, w_out, B, T, U1, J, V, ws, &w_bf16, nullptr, nullptr, st);
+        if (rc) return rc;
+        const void* zcache = (const char*)hcache + zcache_offset_for(B, T, U1, J);
+        rc = joint_dhz_launch(w_bf16, zcache, labels, tlen, ulen, lse, gamma2, grad_cost, B, T, U1, J, V,
+                              blank, dh_ws, enc_proj, dec_proj, d_enc_proj, d_dec_proj, st);
+        if (rc) return rc;
+        return joint_dwz_launch(hcache, zcache, labels, tlen, ulen, lse, gamma2, grad_cost, B, T, U1, J, V, blank,
+                                d_w_out, d_b_out, st);
+    }
+
+    // ---- default: ring route, nothing of size N x V (or N x J, besides dh) ever reaches HBM
+    EMO_REQUIRE(lp2, EMO_BAD_ARG, "joint_bwd(bf16): lp2 (the forward's output) is required");
+    rc = joint_bf16_casts(enc_proj, dec_proj, w_out, B, T, U1, J, V, ws, &w_bf16, &enc_h, &dec_h, st);
+    if (rc) return rc;
+    void* ring_ws = (char*)dh_ws + align_up(hcache_bytes_for(B, T, U1, J), 1024);
+    rc = joint_bwd_ring_launch(w_bf16, enc_h, dec_h, b_out, labels, tlen, ulen, lse, lp2, gamma2, grad_cost, B, T, U1,
+                               J, V, blank, dh_ws, ring_ws, d_w_out, d_b_out, st);
+    if (rc) return rc;
+    return joint_reduce_dh_launch(dh_ws, enc_proj, dec_proj, tlen, ulen, B, T, U1, J, d_enc_proj, d_dec_proj, st);
+}
+
+}  // namespace emo

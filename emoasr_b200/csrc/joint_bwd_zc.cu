@@ -812,72 +812,10 @@ joint_dwz_kernel(const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (
 constexpr int kRedTG = 8;
 constexpr int kRedWarps = 8;
 constexpr int kRedCols = 128;   // columns per block: 4 per lane (one 8-byte load of 4 bf16)
-__global__ void __launch_bounds__(kRedWarps * 32)
-reduce_dh_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ h,
-                 const int* __restrict__ tlen, const int* __restrict__ ulen, int T, int U1, int J, int tpu,
-                 float* __restrict__ d_enc, float* __restrict__ d_dec) {
-    __shared__ float4 s_enc[kRedWarps][kRedTG][32];
-    const int b = blockIdx.z, j0 = blockIdx.x * kRedCols;
-    const int t0 = blockIdx.y * kRedTG;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int T_b = min(max(tlen[b], 1), T), U1b = min(max(ulen[b], 0), U1 - 1) + 1;
-    const int nt = max(0, min(kRedTG, T_b - t0));          // valid frames of this block
-    const size_t rs = (size_t)J / 4;                        // row stride in uint2
-    const size_t off = (((size_t)b * tpu * kTileM + (size_t)t0 * U1b) * J + j0) / 4 + lane;
-    const uint2* dbase = reinterpret_cast<const uint2*>(dh) + off;
-    const uint2* hbase = reinterpret_cast<const uint2*>(h) + off;
-    float e[kRedTG][4];
-#pragma unroll
-    for (int k = 0; k < kRedTG; ++k) e[k][0] = e[k][1] = e[k][2] = e[k][3] = 0.f;
-    auto load_u = [&](int u, uint2 (&dv)[kRedTG], uint2 (&hv)[kRedTG]) {
-#pragma unroll
-        for (int k = 0; k < kRedTG; ++k) {
-            const bool ok = k < nt && u < U1b;
-            const size_t i = ((size_t)k * U1b + u) * rs;
-            dv[k] = ok ? __ldg(dbase + i) : make_uint2(0u, 0u);
-            hv[k] = ok ? __ldg(hbase + i) : make_uint2(0u, 0u);
-        }
-    };
-    uint2 cd[kRedTG], ch[kRedTG], nd[kRedTG], nh[kRedTG];
-    load_u(warp, cd, ch);
-    for (int u = warp; u < U1b; u += kRedWarps) {
-        load_u(u + kRedWarps, nd, nh);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll
-        for (int k = 0; k < kRedTG; ++k) {
-            const float h0 = __uint_as_float(ch[k].x << 16), h1 = __uint_as_float(ch[k].x & 0xffff0000u);
-            const float h2 = __uint_as_float(ch[k].y << 16), h3 = __uint_as_float(ch[k].y & 0xffff0000u);
-            const float f0 = __uint_as_float(cd[k].x << 16) * fmaf(-h0, h0, 1.f);
-            const float f1 = __uint_as_float(cd[k].x & 0xffff0000u) * fmaf(-h1, h1, 1.f);
-            const float f2 = __uint_as_float(cd[k].y << 16) * fmaf(-h2, h2, 1.f);
-            const float f3 = __uint_as_float(cd[k].y & 0xffff0000u) * fmaf(-h3, h3, 1.f);
-            a0 += f0; a1 += f1; a2 += f2; a3 += f3;
-            e[k][0] += f0; e[k][1] += f1; e[k][2] += f2; e[k][3] += f3;
-        }
-        if (nt > 0) red_add_v4(d_dec + ((size_t)b * U1 + u) * J + j0 + lane * 4, a0, a1, a2, a3);
-#pragma unroll
-        for (int k = 0; k < kRedTG; ++k) { cd[k] = nd[k]; ch[k] = nh[k]; }
-    }
-#pragma unroll
-    for (int k = 0; k < kRedTG; ++k) s_enc[warp][k][lane] = make_float4(e[k][0], e[k][1], e[k][2], e[k][3]);
-    __syncthreads();
-    for (int i = threadIdx.x; i < kRedTG * 32; i += blockDim.x) {
-        const int k = i >> 5, l = i & 31;
-        if (t0 + k >= T) continue;
-        float4 a = s_enc[0][k][l];
-#pragma unroll
-        for (int w = 1; w < kRedWarps; ++w) {
-            const float4 x = s_enc[w][k][l];
-            a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
-        }
-        reinterpret_cast<float4*>(d_enc + ((size_t)b * T + t0 + k) * J + j0)[l] = a;
-    }
-}
-
-// Same reduction with h RECOMPUTED instead of read back: h = bf16(tanh.approx.f16x2(f16(enc) + f16(dec))) is the
-// exact instruction sequence of the forward's A producers on the same inputs, so it reproduces the h cache bit for
-// bit, and enc_proj / dec_proj (11 MB at cfg 3) are L2-resident -- the kernel reads 0.83 GB of dh from HBM instead
-// of 1.66 GB of dh + h.  The enc values of the block's kRedTG frames stay in registers for the whole u loop.
+// h is RECOMPUTED instead of read back: h = bf16(tanh.approx.f16x2(f16(enc) + f16(dec))) is the exact instruction
+// sequence of the forward's A producers on the same inputs, so it reproduces the forward's h bit for bit, and
+// enc_proj / dec_proj (11 MB at cfg 3) are L2-resident -- the kernel reads 0.83 GB of dh from HBM and nothing
+// else of that size.  The enc values of the block's kRedTG frames stay in registers for the whole u loop.
 __global__ void __launch_bounds__(kRedWarps * 32)
 reduce_dh_tanh_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ enc_proj,
                       const float* __restrict__ dec_proj, const int* __restrict__ tlen,
@@ -963,10 +901,15 @@ size_t dwz_smem_bytes(int J) {
            (size_t)kDwzZStages * 5 * 64 * sizeof(float);
 }
 
-// EMO_ZC_DEBUG=<flags>: kernel tuning switches (results are then WRONG; never set outside tools/)
+// EMO_ZC_DEBUG=<flags>: ablation switches of the -DEMO_ZC_PROF tuning build only (results are then WRONG);
+// the shipped library never reads the environment
 int zc_debug_flags() {
+#ifdef EMO_ZC_PROF
     static const int flags = getenv("EMO_ZC_DEBUG") ? atoi(getenv("EMO_ZC_DEBUG")) : 0;
     return flags;
+#else
+    return 0;
+#endif
 }
 
 int launch_pair_kernel(const void* fn, int ctas, size_t smem, cudaStream_t st, void** args) {
@@ -990,7 +933,7 @@ bool joint_zc_supported(int J) {
     return dhz_smem_bytes(J) <= (size_t)kSmemLimit && dwz_smem_bytes(J) <= (size_t)kSmemLimit;
 }
 
-int joint_dhz_launch(const void* w_bf16, const void* hcache, const void* zcache, const int* labels, const int* tlen,
+int joint_dhz_launch(const void* w_bf16, const void* zcache, const int* labels, const int* tlen,
                      const int* ulen, const float* lse, const float* gamma2, const float* grad_cost, int B, int T,
                      int U1, int J, int V, int blank, void* dh_ws, const float* enc_proj, const float* dec_proj,
                      float* d_enc_proj, float* d_dec_proj, cudaStream_t st) {
@@ -1014,18 +957,19 @@ int joint_dhz_launch(const void* w_bf16, const void* hcache, const void* zcache,
     rc = launch_pair_kernel((const void*)joint_dhz_kernel, 2 * pairs, smem, st, args);
     if (rc) return rc;
     EMO_CHECK_LAUNCH("joint_dhz_kernel");
-    static const bool read_h = getenv("EMO_REDUCE_READ_H") != nullptr;   // A/B switch: read h back instead
-    if (enc_proj && dec_proj && !read_h && ((uintptr_t)enc_proj & 15) == 0 && ((uintptr_t)dec_proj & 15) == 0) {
-        reduce_dh_tanh_kernel<<<dim3(J / kRedCols, ceil_div(T, kRedTG), B), kRedWarps * 32, 0, st>>>(
-            reinterpret_cast<const __nv_bfloat16*>(dh_ws), enc_proj, dec_proj, tlen, ulen, T, U1, J, tpu, d_enc_proj,
-            d_dec_proj);
-        EMO_CHECK_LAUNCH("reduce_dh_tanh_kernel");
-        return EMO_OK;
-    }
-    reduce_dh_kernel<<<dim3(J / kRedCols, ceil_div(T, kRedTG), B), kRedWarps * 32, 0, st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(dh_ws), reinterpret_cast<const __nv_bfloat16*>(hcache), tlen, ulen, T,
-        U1, J, tpu, d_enc_proj, d_dec_proj);
-    EMO_CHECK_LAUNCH("reduce_dh_kernel");
+    return joint_reduce_dh_launch(dh_ws, enc_proj, dec_proj, tlen, ulen, B, T, U1, J, d_enc_proj, d_dec_proj, st);
+}
+
+// d_enc_proj = sum_u dh (1 - h^2), d_dec_proj = sum_t dh (1 - h^2) from the tile-major bf16 dh (d_dec_proj pre-zeroed)
+int joint_reduce_dh_launch(const void* dh_ws, const float* enc_proj, const float* dec_proj, const int* tlen,
+                           const int* ulen, int B, int T, int U1, int J, float* d_enc_proj, float* d_dec_proj,
+                           cudaStream_t st) {
+    EMO_REQUIRE(enc_proj && dec_proj && ((uintptr_t)enc_proj & 15) == 0 && ((uintptr_t)dec_proj & 15) == 0, EMO_BAD_ARG,
+                "joint_bwd(bf16): enc_proj / dec_proj must be given and 16-byte aligned");
+    reduce_dh_tanh_kernel<<<dim3(J / kRedCols, ceil_div(T, kRedTG), B), kRedWarps * 32, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(dh_ws), enc_proj, dec_proj, tlen, ulen, T, U1, J,
+        tiles128_per_utt(T, U1), d_enc_proj, d_dec_proj);
+    EMO_CHECK_LAUNCH("reduce_dh_tanh_kernel");
     return EMO_OK;
 }
 

@@ -19,6 +19,17 @@ def _opt(params, name, default=0):
     return getattr(params, name) if hasattr(params, name) else default
 
 
+def _reference_forward(self, mixin):
+    """forward() of the first class behind `mixin` in the MRO that really implements one (the reference's
+    decoder when installed through dropin.install()), or None for the stand-alone classes."""
+    mro = type(self).__mro__
+    for cls in mro[mro.index(mixin) + 1:]:
+        fwd = cls.__dict__.get("forward")
+        if fwd is not None and cls is not nn.Module:
+            return fwd.__get__(self, type(self))
+    return None
+
+
 class FusedCTCForward:
     """forward() of ctc.py:87-174 with every ``ctc_loss_fn(logits.transpose(1,0).log_softmax(2), ...)
     / B`` site (:109-113, :139-141, :152-154) replaced by the fused op on raw logits."""
@@ -32,11 +43,11 @@ class FusedCTCForward:
         wants_kd = self.kd_weight > 0 and soft_labels is not None
         if wants_kd or _opt(self, "inter_kd_weight") > 0:
             # KD needs dense log-probs + the forced aligner: the reference's own path
-            base = super()
-            if not hasattr(base, "forward") or type(self).__mro__[1] is nn.Module:
+            ref_forward = _reference_forward(self, FusedCTCForward)
+            if ref_forward is None:
                 raise NotImplementedError("knowledge distillation needs the reference decoder "
                                           "(use emoasr_b200.dropin.install())")
-            return base.forward(eouts, elens, eouts_inter, ys, ylens, ys_in, ys_out, soft_labels, ps, plens)
+            return ref_forward(eouts, elens, eouts_inter, ys, ylens, ys_in, ys_out, soft_labels, ps, plens)
         loss = 0
         loss_dict = {}
         logits = self.output(eouts)  # (B, T, vocab)
@@ -62,19 +73,35 @@ class FusedCTCForward:
 
 class FusedRNNTForward:
     """forward() of rnn_transducer.py:81-145 with joint -> log_softmax -> warp_rnnt.rnnt_loss
-    (:101-115) replaced by one fused op.  The third return value is None (the (B,T,U+1,V) logits
-    are never formed; the only caller, asr/modeling/asr.py:65, discards it)."""
+    (:101-115) replaced by one fused op.  The third return value is None (with the default route the
+    (B,T,U+1,V) logits are never formed; the only caller, asr/modeling/asr.py:65, discards it).
+
+    ``fused_precision`` "bf16" runs the tensor-core kernels; shapes they do not support (see
+    ``emo_rnnt_joint_supported``) fall back to the fp32 kernels with a one-time warning.
+    ``fused_route``: "ring" (default, nothing of size N x V in HBM) or "zcache" (see functional)."""
 
     fused_precision = "bf16"
+    fused_route = "ring"
+    _warned_fallback = False
+
+    def _precision_for(self, B, T, U1, J, V):
+        if self.fused_precision != "bf16" or F.joint_supported("bf16", self.fused_route, B, T, U1, J, V):
+            return self.fused_precision
+        if not FusedRNNTForward._warned_fallback:
+            FusedRNNTForward._warned_fallback = True
+            import warnings
+            warnings.warn(f"emoasr_b200: joint shape J={J}, V={V}, B={B} is outside what the bf16 tensor-core "
+                          "kernels support; using the (much slower) fp32 kernels", RuntimeWarning)
+        return "fp32"
 
     def forward(self, eouts, elens, eouts_inter=None, ys=None, ylens=None, ys_in=None, ys_out=None,
                 soft_labels=None, ps=None, plens=None):
         if self.kd_weight > 0 and soft_labels is not None:
-            base = super()
-            if type(self).__mro__[1] is nn.Module or not hasattr(base, "forward"):
+            ref_forward = _reference_forward(self, FusedRNNTForward)
+            if ref_forward is None:
                 raise NotImplementedError("knowledge distillation needs the dense logits: use the "
                                           "reference decoder (emoasr_b200.dropin.install())")
-            return base.forward(eouts, elens, eouts_inter, ys, ylens, ys_in, ys_out, soft_labels, ps, plens)
+            return ref_forward(eouts, elens, eouts_inter, ys, ylens, ys_in, ys_out, soft_labels, ps, plens)
         loss = 0
         loss_dict = {}
         douts, _ = self.recurrency(ys_in, dstate=None)
@@ -83,7 +110,10 @@ class FusedRNNTForward:
         assert dec_proj.size(1) == ys.size(1) + 1
         loss_rnnt = F.rnnt_joint_loss(enc_proj, dec_proj, self.output.weight, self.output.bias,
                                       ys, elens, ylens, blank=self.blank_id, reduction="mean",
-                                      precision=self.fused_precision)
+                                      precision=self._precision_for(enc_proj.size(0), enc_proj.size(1),
+                                                                    dec_proj.size(1), enc_proj.size(2),
+                                                                    self.output.weight.size(0)),
+                                      route=self.fused_route)
         loss += loss_rnnt
         loss_dict["loss_rnnt"] = loss_rnnt
         if self.mtl_ctc_weight > 0:

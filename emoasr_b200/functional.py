@@ -5,9 +5,9 @@ rnnt_joint_loss  joint + log_softmax + transducer loss fused (rnn_transducer.py:
 ctc_loss         log_softmax + nn.CTCLoss(reduction="none") fused (asr/modeling/decoders/ctc.py:109-113)
 """
 import ctypes
-import os
 
 import torch
+from torch.autograd.function import once_differentiable
 
 from . import _lib
 
@@ -67,6 +67,7 @@ class _RNNTLattice(torch.autograd.Function):
         return cost
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_cost):
         (gamma2,) = ctx.saved_tensors
         return -gamma2 * grad_cost.view(-1, 1, 1, 1), None, None
@@ -85,6 +86,8 @@ class _RNNTDense(torch.autograd.Function):
         labels, tlen, ulen = _i32c(labels, dev), _i32c(tlen, dev), _i32c(ulen, dev)
         if labels.dim() != 2 or labels.size(0) != B or labels.size(1) != U1 - 1:
             raise RuntimeError(f"labels must be (B, U) = ({B}, {U1 - 1}); got {tuple(labels.shape)}")
+        if U1 == 1:   # no labels at all: the kernels still want a valid pointer
+            labels = torch.zeros(B, 1, dtype=torch.int32, device=dev)
         with torch.cuda.device(dev):
             lp2 = torch.empty(B, T, U1, 2, device=dev)
             alpha = torch.empty(B, T, U1, device=dev)
@@ -99,6 +102,7 @@ class _RNNTDense(torch.autograd.Function):
         return cost
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_cost):
         gamma2, labels, tlen, ulen = ctx.saved_tensors
         B, T, U1, V, blank = ctx.dims
@@ -126,13 +130,17 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=
               reduction=None, blank=0, gather=False):
     """Drop-in for ``warp_rnnt.rnnt_loss`` as called at rnn_transducer.py:106-115.
 
-    log_probs (B,T,U+1,V) fp32 log-softmax output (or (B,T,U+1,2) = {blank,label} pairs when
-    ``gather=True``), labels (B,U) int, lengths (B,) int.  Gradient w.r.t. log_probs has two
+    log_probs (B,T,U+1,V) fp32 log-softmax output, labels (B,U) int, lengths (B,) int.  ``gather`` is
+    warp_rnnt's memory switch (it gathers the {blank,label} pairs before the lattice): this implementation
+    always gathers, so the flag changes nothing for dense input; as an extension, ``gather=True`` with a
+    last dimension of 2 takes pre-gathered pairs (B,T,U+1,2).  Gradient w.r.t. log_probs has two
     non-zeros per valid lattice cell, exactly like warp_rnnt.
     """
-    if gather:
+    if gather and log_probs.size(-1) == 2:
+        # extension: already gathered {blank, label} pairs (B,T,U+1,2)
         costs = _RNNTLattice.apply(log_probs, frames_lengths, labels_lengths)
     else:
+        # dense log-probs: the kernel gathers the pairs itself (what warp_rnnt's gather=True does internally)
         costs = _RNNTDense.apply(log_probs, labels, frames_lengths, labels_lengths, int(blank))
     if average_frames:
         costs = costs / frames_lengths.to(costs)
@@ -140,36 +148,21 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=
 
 
 # ----------------------------------------------------------------------------------------------
-_CACHE_BYTES = {}
+ROUTES = ("ring", "zcache")
 
 
-def _joint_cache_bytes(precision, B, T, U1, J, V, dev):
-    """Size of the cache the fused forward leaves for its backward.  Preferred: h (bf16) + logits (fp16),
-    which lets the backward stream z instead of recomputing it (2 GEMMs instead of 6).  Falls back to the
-    h-only cache (recompute path) when the logit cache would not fit comfortably in free HBM, or when
-    EMO_NO_ZCACHE is set (A/B switch)."""
-    no_zc = bool(os.environ.get("EMO_NO_ZCACHE"))
-    key = (precision, B, T, U1, J, V, torch.device(dev).index, no_zc)
-    hit = _CACHE_BYTES.get(key)
-    if hit is not None:
-        return hit
-    hbytes = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HCACHE, precision, B, T, U1, J, V)
-    out = hbytes
-    if hbytes and not no_zc:
-        hz = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HZCACHE, precision, B, T, U1, J, V)
-        if hz:
-            free, _total = torch.cuda.mem_get_info(dev)
-            # the caching allocator may hold freed blocks that can serve the request
-            reusable = torch.cuda.memory_reserved(dev) - torch.cuda.memory_allocated(dev)
-            if hz <= 0.6 * (free + reusable):
-                out = hz
-    _CACHE_BYTES[key] = out          # decided once per shape: no driver query on the step path
-    return out
+def joint_supported(precision, route, B, T, U1, J, V):
+    """True if rnnt_joint_loss can run these sizes with this precision / route (host call, no CUDA work)."""
+    return bool(_lib.load().emo_rnnt_joint_supported(_PRECISIONS[precision], ROUTES.index(route), B, T, U1, J, V))
+
+
+def _zcache_bytes(precision, B, T, U1, J, V):
+    return _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HZCACHE, precision, B, T, U1, J, V)
 
 
 class _RNNTJoint(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, blank, precision):
+    def forward(ctx, enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, blank, precision, route):
         _require_cuda(enc_proj, dec_proj, w_out, b_out)
         lib = _lib.load()
         enc, dec, w, bo = _f32c(enc_proj), _f32c(dec_proj), _f32c(w_out), _f32c(b_out)
@@ -188,18 +181,23 @@ class _RNNTJoint(torch.autograd.Function):
                 labels = labels[:, : U1 - 1].contiguous()
         else:
             labels = torch.zeros(B, 1, dtype=torch.int32, device=dev)
+        need_grad = any(ctx.needs_input_grad[:4]) and torch.is_grad_enabled()
         with torch.cuda.device(dev):
             nbytes = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_FWD, precision, B, T, U1, J, V)
             ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
             lp2 = torch.empty(B, T, U1, 2, device=dev)
             lse = torch.empty(B, T, U1, device=dev)
-            # bf16 mode: tanh output of every valid cell, written by the forward kernel for the backward
-            hbytes = _joint_cache_bytes(precision, B, T, U1, J, V, dev)
-            need_h = hbytes > 0 and any(ctx.needs_input_grad[:4])
-            hcache = torch.empty(hbytes, dtype=torch.uint8, device=dev) if need_h else None
+            # route "zcache" (opt-in, bf16 only): the forward also stores h (bf16) and the logits (fp16) of the
+            # valid cells for the backward.  Default "ring": nothing is cached, the backward recomputes.
+            cache = None
+            if route == "zcache" and need_grad and precision == _lib.PREC_BF16:
+                cbytes = _zcache_bytes(precision, B, T, U1, J, V)
+                if cbytes == 0:
+                    raise RuntimeError(f"route='zcache' does not support J={J}, V={V}")
+                cache = torch.empty(cbytes, dtype=torch.uint8, device=dev)
             _lib.check(lib.emo_rnnt_joint_fwd(_p(enc), _p(dec), _p(w), _p(bo), _p(labels), _p(tlen), _p(ulen),
                                               B, T, U1, J, V, blank, precision, _p(lp2), _p(lse),
-                                              _p(hcache), hbytes if need_h else 0,
+                                              _p(cache), cache.numel() if cache is not None else 0,
                                               _p(ws), ws.numel(), _stream()), "emo_rnnt_joint_fwd")
             alpha = torch.empty(B, T, U1, device=dev)
             beta = torch.empty(B, T, U1, device=dev)
@@ -208,14 +206,18 @@ class _RNNTJoint(torch.autograd.Function):
             _lib.check(lib.emo_rnnt_lattice_fwd_bwd(_p(lp2), _p(tlen), _p(ulen), B, T, U1, _p(alpha),
                                                     _p(beta), _p(cost), _p(gamma2), _stream()),
                        "emo_rnnt_lattice_fwd_bwd")
-        ctx.save_for_backward(enc, dec, w, bo, labels, tlen, ulen, lse, gamma2)
-        ctx.hcache = hcache
+        if cache is not None:
+            ctx.save_for_backward(enc, dec, w, bo, labels, tlen, ulen, lse, lp2, gamma2, cache)
+        else:
+            ctx.save_for_backward(enc, dec, w, bo, labels, tlen, ulen, lse, lp2, gamma2)
         ctx.cfg = (blank, precision)
         return cost
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_cost):
-        enc, dec, w, bo, labels, tlen, ulen, lse, gamma2 = ctx.saved_tensors
+        enc, dec, w, bo, labels, tlen, ulen, lse, lp2, gamma2, *rest = ctx.saved_tensors
+        cache = rest[0] if rest else None
         blank, precision = ctx.cfg
         lib = _lib.load()
         B, T, J = enc.shape
@@ -229,27 +231,33 @@ class _RNNTJoint(torch.autograd.Function):
             d_dec = torch.empty_like(dec)
             d_w = torch.empty_like(w)
             d_b = torch.empty_like(bo)
-            hcache = ctx.hcache
             _lib.check(lib.emo_rnnt_joint_bwd(_p(enc), _p(dec), _p(w), _p(bo), _p(labels), _p(tlen), _p(ulen),
-                                              _p(lse), _p(gamma2), _p(g), _p(hcache),
-                                              hcache.numel() if hcache is not None else 0,
+                                              _p(lse), _p(lp2), _p(gamma2), _p(g), _p(cache),
+                                              cache.numel() if cache is not None else 0,
                                               B, T, U1, J, V, blank, precision,
                                               _p(d_enc), _p(d_dec), _p(d_w), _p(d_b), _p(ws), ws.numel(),
                                               _stream()), "emo_rnnt_joint_bwd")
-            ctx.hcache = None
-        return d_enc, d_dec, d_w, d_b, None, None, None, None, None
+        return d_enc, d_dec, d_w, d_b, None, None, None, None, None, None
 
 
 def rnnt_joint_loss(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths, labels_lengths,
-                    blank=0, reduction=None, precision="bf16"):
+                    blank=0, reduction=None, precision="bf16", route="ring"):
     """Per-utterance transducer cost straight from the two projected streams.
 
     enc_proj (B,T,J) = w_enc(eouts)+b, dec_proj (B,U+1,J) = w_dec(douts)+b, w_out (V,J), b_out (V).
     Equivalent to ``rnnt_loss(log_softmax(output(tanh(enc_proj[:,:,None]+dec_proj[:,None]))), ...)``
-    (rnn_transducer.py:101-115,147-156) without ever forming the (B,T,U+1,V) tensors.
+    (rnn_transducer.py:101-115,147-156).
+
+    route="ring" (default): the (B,T,U+1,V) logits / log-probs / gradient are never formed, neither by the
+    forward nor by the backward, which recomputes logit tiles on the tensor cores and hands ``dz`` to the
+    gradient GEMMs through an L2-resident ring of tiles.  route="zcache" (bf16 only, opt-in): the forward
+    stores the logits of the valid cells as fp16 (2 bytes per cell and vocabulary entry) and the backward
+    streams them -- fewer tensor-core flops, ~100x the HBM traffic.
     """
+    if route not in ROUTES:
+        raise ValueError(f"unknown route {route!r}; expected one of {ROUTES}")
     costs = _RNNTJoint.apply(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths,
-                             labels_lengths, int(blank), _PRECISIONS[precision])
+                             labels_lengths, int(blank), _PRECISIONS[precision], route)
     return _reduce(costs, reduction)
 
 
@@ -285,6 +293,7 @@ class _CTC(torch.autograd.Function):
         return nll
 
     @staticmethod
+    @once_differentiable
     def backward(ctx, grad_nll):
         z, labels, tlen, ulen, lse, alpha, nll = ctx.saved_tensors
         blank, zero_infinity = ctx.cfg
