@@ -30,11 +30,13 @@ def needs_build():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    if not force and not needs_build():
+def build_library(force=False, verbose=False, out=None, extra=()):
+    """out / extra: a differently-flagged copy (tuning builds, e.g. -DEMO_ZC_PROF) next to the product library;
+    load it with EMOASR_B200_LIB=<path> (tools/ only)."""
+    if out is None and not force and not needs_build():
         return LIB
     os.makedirs(os.path.dirname(LIB), exist_ok=True)
-    objdir = os.path.join(HERE, "lib", "obj")
+    objdir = os.path.join(HERE, "lib", "obj" if out is None else "obj_" + os.path.splitext(os.path.basename(out))[0])
     os.makedirs(objdir, exist_ok=True)
     nvcc = _nvcc()
     procs = []
@@ -42,20 +44,25 @@ def build_library(force=False, verbose=False):
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
         objs.append(obj)
-        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("EMO_NVCC_EXTRA", "").split() + (["-Xptxas", "-v"] if verbose else []) + [
+        cmd = [nvcc] + NVCC_FLAGS + os.environ.get("EMO_NVCC_EXTRA", "").split() + list(extra) + (["-Xptxas", "-v"] if verbose else []) + [
             "-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
     failed = False
     for src, p in procs:
-        out, _ = p.communicate()
+        log, _ = p.communicate()
         if p.returncode != 0 or verbose:
-            sys.stderr.write(f"--- {src} ---\n{out}\n")
+            sys.stderr.write(f"--- {src} ---\n{log}\n")
         failed |= p.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", LIB] + objs)
-    return LIB
+    target = LIB if out is None else out
+    subprocess.check_call([nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-o", target] + objs)
+    return target
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if "--prof" in sys.argv:   # instrumented copy: clock64 wait accounting + tuning switches
+        print(build_library(force=True, verbose="-v" in sys.argv,
+                            out=os.path.join(HERE, "lib", "libemoasr_b200_prof.so"), extra=["-DEMO_ZC_PROF"]))
+    else:
+        print(build_library(force="--force" in sys.argv, verbose="-v" in sys.argv))

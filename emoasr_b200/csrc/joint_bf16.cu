@@ -7,7 +7,7 @@
 // to a caller-provided cache for the z-cache backward (joint_bwd_zc.cu).
 //
 // Persistent, warp-specialised CTA pairs (cluster of 2, cta_group::2), one 256-cell tile per pair at a time (cells of
-// one utterance, flattened over its VALID (t,u) region, so padding costs nothing); 512 threads, setmaxnreg budgets
+// one utterance, flattened over its VALID (t,u) region, so padding costs nothing); 640 threads, setmaxnreg budgets
 // per warpgroup:
 //   warp 0       TMA producer   w_out (bf16, [V][J]) tiles [128 v x 64 j] per CTA, 128B swizzle, mbarrier ring
 //                               (5 stages, 4 when the z cache is written), complete_tx
@@ -19,9 +19,10 @@
 //                               columns at a time (thread == lattice cell), bias add, online (max, sum-exp) over the
 //                               vocab chunks, capture of the blank and label logits; optionally the logits go to the
 //                               z cache as fp16 through a per-warp staging buffer and one TMA store per block
-//   warps 12-15  A producers    h = tanh(enc+dec): fp16 gathers, packed-half add and tanh.approx, -> bf16 -> shared
+//   warps 12-19  A producers    h = tanh(enc+dec): fp16 gathers, packed-half add and tanh.approx, -> bf16 -> shared
 //                               memory in the canonical K-major 128B-swizzle layout, one 64-wide K block at a time so
-//                               the MMAs of the next tile start as soon as block 0 is rewritten
+//                               the MMAs of the next tile start as soon as block 0 is rewritten (8 warps, 16 rows
+//                               each: with 4 the MMA issuer spent a third of its time waiting for h)
 // The h tile (128 x J bf16 per CTA) stays resident in shared memory for all vocab chunks of the tile.
 #include "joint_tc.cuh"
 
@@ -37,10 +38,6 @@ namespace {
 
 // ---- per-variant constants ----
 template <int kCtas, bool kStoreZ> struct Cfg;
-template <bool kStoreZ> struct Cfg<1, kStoreZ> {
-    static constexpr int kBStages = 2;                // (tuning switch only; the pair kernel is the product path)
-    static constexpr int kBRows = kChunkN;            // vocab rows of a w_out tile held by this CTA
-};
 template <bool kStoreZ> struct Cfg<2, kStoreZ> {
     static constexpr int kBStages = kStoreZ ? 4 : 5;  // the z staging buffers take one stage's worth of shared memory
     static constexpr int kBRows = kChunkN / 2;
@@ -123,7 +120,8 @@ __device__ __forceinline__ void lse_group(const uint32_t (&r)[32], const float* 
 // stages only half (128 vocab rows) of every w_out tile.  Barrier topology for the pair:
 //   b_full / a_full / acc_empty live in the LEADER (arrivals from both CTAs, TMA bytes from both),
 //   b_empty / a_empty / acc_full are signalled in BOTH CTAs by a multicast tcgen05.commit.
-constexpr int kFwdThreads = 512;  // 4 control warps, 8 epilogue warps, 4 A-producer warps
+constexpr int kFwdThreads = 640;  // 4 control warps, 8 epilogue warps, 8 A-producer warps
+constexpr int kFwdProdWarps = 8;
 constexpr int kFwdEpiThreads = 256;
 template <int N> __device__ __forceinline__ void reg_dec() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
@@ -186,7 +184,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     const int total_tiles = B * tiles_per_utt;
     const int tile0 = blockIdx.x / kCtas, tile_stride = gridDim.x / kCtas;
     constexpr uint32_t kArrivals = (kFwdEpiThreads / 32) * kCtas;   // epilogue WARPS of the pair (one arrive each)
-    constexpr uint32_t kProducers = 128;                            // A-producer threads per CTA
+    constexpr uint32_t kProducers = kFwdProdWarps;                  // A-producer WARPS per CTA (one arrive each)
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kBStages; ++i) {
@@ -217,8 +215,9 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     if (kPair) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
-    // register budget per warpgroup (x128 threads): control 40, two epilogue groups 152, producers 152 (three units
-    // of gather loads in flight) -> 5120 + 2 * 19456 + 19456 = 63488 of 65536 (an exact fit deadlocks)
+    // register budget per warpgroup (x128 threads): control 40, two epilogue groups 128, two producer groups 88
+    // (two units of gather loads in flight) = 472 of the 480 the CTA owns at launch (96 x 640); an exact fit
+    // deadlocks in setmaxnreg.inc
     if (warp < 4) {
     reg_dec<40>();
     if (warp == 0) {
@@ -330,7 +329,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         }
     }
     } else if (warp < 12) {
-        reg_inc<152>();
+        reg_inc<128>();
         // ===================== epilogue: online LSE over vocab chunks =====================
         // Two warps per TMEM lane quadrant: warp (q, hf) owns columns [128 hf, 128 hf + 128) of every 256-wide
         // chunk for the rows of quadrant q.  The two partial (max, sum, blank, label) states of a row are
@@ -410,26 +409,26 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         }
         if (kStoreZ && lane == 0) tma_store_wait_all<0>();
     } else {
-        reg_inc<152>();
+        reg_dec<88>();
         // ===================== A producers =====================
-        const int pw = warp - 12;      // 4 producer warps, 32 rows each, produced as two 16-row halves
+        const int pw = warp - 12;      // 8 producer warps, 16 rows each
         const int c = lane & 7;        // 16-byte chunk (8 hidden units) inside the 64-wide K block
         const int rsub = lane >> 3;    // 4 rows per warp pass
-        // Flattened (tile, K block, half) sequence with THREE units of loads in flight: the loads of unit n+3
-        // are issued right after unit n has been written, so an L2 round trip (600-1500 clk under load) is hidden
-        // behind three unit periods (and, across tiles, behind the wait for the MMAs to release the slot).
-        int ltile = tile0 - tile_stride, lunit = 2 * KB;   // load cursor; unit = 2 * kb + half
-        uint32_t eoff[8], doff[8];
+        // Flattened (tile, K block) sequence with TWO units of loads in flight: the loads of unit n+2 are issued
+        // right after unit n has been written, so an L2 round trip is hidden behind two unit periods (and, across
+        // tiles, behind the wait for the MMAs to release the slot).
+        int ltile = tile0 - tile_stride, lunit = KB;   // load cursor; unit = kb
+        uint32_t eoff[4], doff[4];
         auto issue = [&](uint4 (&re)[4], uint4 (&rd)[4]) -> bool {
-            if (lunit == 2 * KB) {
+            if (lunit == KB) {
                 TileInfo ti;
                 do {
                     ltile += tile_stride;
                     if (ltile >= total_tiles) { ltile = total_tiles; return false; }
                 } while (!tile_info<kCtas>(ltile, tiles_per_utt, rank, tlen, ulen, T, U1, ti));
 #pragma unroll
-                for (int p = 0; p < 8; ++p) {
-                    const int row = pw * 32 + p * 4 + rsub;
+                for (int p = 0; p < 4; ++p) {
+                    const int row = pw * 16 + p * 4 + rsub;
                     const int m = min(ti.first_cell + row, ti.n_cells - 1);  // clamp padding rows
                     const int t = m / ti.U1b, u = m - t * ti.U1b;
                     eoff[p] = (uint32_t)(((size_t)ti.b * T + t) * J) + c * 8;
@@ -437,53 +436,41 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 }
                 lunit = 0;
             }
-            const int lkb = lunit >> 1;
-            if (lunit & 1) {
 #pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    re[p] = __ldg(reinterpret_cast<const uint4*>(enc + eoff[4 + p] + lkb * kBlockK));
-                    rd[p] = __ldg(reinterpret_cast<const uint4*>(dec + doff[4 + p] + lkb * kBlockK));
-                }
-            } else {
-#pragma unroll
-                for (int p = 0; p < 4; ++p) {
-                    re[p] = __ldg(reinterpret_cast<const uint4*>(enc + eoff[p] + lkb * kBlockK));
-                    rd[p] = __ldg(reinterpret_cast<const uint4*>(dec + doff[p] + lkb * kBlockK));
-                }
+            for (int p = 0; p < 4; ++p) {
+                re[p] = __ldg(reinterpret_cast<const uint4*>(enc + eoff[p] + lunit * kBlockK));
+                rd[p] = __ldg(reinterpret_cast<const uint4*>(dec + doff[p] + lunit * kBlockK));
             }
             ++lunit;
             return true;
         };
-        uint32_t wunit = 0, wtl = 0;                 // work cursor: same sequence, 2 * KB units per valid tile
+        uint32_t wkb = 0, wtl = 0;                 // work cursor: same sequence, KB units per valid tile
+        const uint32_t a_full0 = kPair ? mapa_shared(smem_u32(&bars->a_full[0]), 0) : smem_u32(&bars->a_full[0]);
         EMO_PROF(long long q_wait = 0, q_work = 0, q_t0 = clock64(), q_c;)
         auto work = [&](const uint4 (&re)[4], const uint4 (&rd)[4]) {
-            const uint32_t wkb = wunit >> 1, half = wunit & 1;
             EMO_PROF(q_c = clock64();)
-            if (!half) mbar_wait(smem_u32(&bars->a_empty[wkb]), (wtl & 1) ^ 1);
+            mbar_wait(smem_u32(&bars->a_empty[wkb]), (wtl & 1) ^ 1);
             EMO_PROF(q_wait += clock64() - q_c; q_c = clock64();)
-            produce_h_block16(re, rd, 2 * pw + (int)half, rsub, c, sA + (size_t)wkb * kABlockBytes);
-            if (half) {
-                fence_proxy_async_smem();
+            produce_h_block16(re, rd, pw, rsub, c, sA + (size_t)wkb * kABlockBytes);
+            fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) {
                 if (store_h) mbar_arrive(smem_u32(&bars->h_ready[wkb]));
-                if (kPair) mbar_arrive_cluster(mapa_shared(smem_u32(&bars->a_full[wkb]), 0));
-                else       mbar_arrive(smem_u32(&bars->a_full[wkb]));
+                if (kPair) mbar_arrive_cluster(a_full0 + wkb * 8);
+                else       mbar_arrive(a_full0 + wkb * 8);
             }
             EMO_PROF(q_work += clock64() - q_c;)
-            if (++wunit == 2u * (uint32_t)KB) { wunit = 0; ++wtl; }
+            if (++wkb == (uint32_t)KB) { wkb = 0; ++wtl; }
         };
-        uint4 e0[4], d0[4], e1[4], d1[4], e2[4], d2[4];
+        uint4 e0[4], d0[4], e1[4], d1[4];
         bool v0 = issue(e0, d0);
         bool v1 = v0 && issue(e1, d1);
-        bool v2 = v1 && issue(e2, d2);
         while (v0) {
             work(e0, d0);
-            v0 = v2 && issue(e0, d0);
+            v0 = v1 && issue(e0, d0);
             if (!v1) break;
             work(e1, d1);
             v1 = v0 && issue(e1, d1);
-            if (!v2) break;
-            work(e2, d2);
-            v2 = v1 && issue(e2, d2);
         }
         EMO_PROF(if (blockIdx.x == 0 && threadIdx.x == 12 * 32)
                      printf("fwd producer warp 12: total %lld clk, %u tiles; wait a_empty %lld, produce (incl. load stalls) "

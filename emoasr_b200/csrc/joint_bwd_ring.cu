@@ -30,6 +30,14 @@
 // resident clusters, checked on the host), hence no deadlock.
 #include "joint_tc.cuh"
 
+// -DEMO_ZC_PROF: clock64 accounting of what each role's MMA issuer / ring gate waits for (printf from the first
+// pair of each role); tools/gpu_ringprof.sh.  Never defined in the shipped library.
+#ifdef EMO_ZC_PROF
+#define EMO_PROF(...) __VA_ARGS__
+#else
+#define EMO_PROF(...)
+#endif
+
 namespace emo {
 namespace {
 
@@ -37,13 +45,14 @@ constexpr int kRingThreads = 640;
 constexpr int kVG = 1024;                      // vocab entries per ring item (one z slot = 256 cells x kVG)
 constexpr int kPairM = 2 * kTileM;             // cells per pair tile
 constexpr int kRingSlots = 48;                 // z slots (512 KiB each at V >= 1024) and h slots (256 KiB at J = 512)
-constexpr int kPBStages = 4;                   // P: w_out ring
+constexpr int kPBStages = 3;                   // P: w_out ring (the dz staging buffers take the fourth stage)
 constexpr int kDZStages = 5, kDOpStages = 3;   // D: dz ring, w_out ring
 constexpr int kWZStages = 5, kWOpStages = 4;   // W: dz ring, h ring
 constexpr int kStageBytes = 16384;
 constexpr int kBoxBytes = 8192;                // [64 rows x 128 B]
-constexpr int kZStBytes = 2048;                // P epilogue staging per warp: [32 cells x 32 v] bf16, 64B swizzle
-constexpr int kDrainWarps = 8, kDrainBufBytes = 4096;
+constexpr int kZStBytes = 2048;                // P epilogue staging block: [32 cells x 32 v] bf16, 64B swizzle
+constexpr int kZStBufs = 2;                    // blocks per epilogue warp: a TMA store in flight while the next is built
+constexpr int kDrainWarps = 16, kDrainBufBytes = 2048;   // D: warps 4-19, [32 cells x 32 j] bf16 blocks, 64B swizzle
 constexpr int kColsumWarps = 8;
 constexpr int kMaxB = 1024;                    // utterances (prefix table lives in shared memory)
 constexpr uint32_t kDescHiSw128 = (1024u >> 4) | (1u << 14) | (2u << 29);  // SBO=1024, v1, SW128
@@ -179,11 +188,12 @@ constexpr int kPProdWarps = 8;       // warps 12-19
 
 // per-cell scalars of the dz epilogue (thread == cell)
 struct PCell {
-    float nl2;    // -lse * log2e (-1e30 for padding rows: exp2 -> 0)
-    float cs;     // g * (gamma_blank + gamma_label)
-    float dblk;   // dz at the blank column:  cs * p_blank - g * gamma_blank (- g * gamma_label if label == blank)
-    float dlab;   // dz at the label column:  cs * p_label - g * gamma_label
-    int lab;      // label of the cell's emit transition, -1 if none (or == blank)
+    float c2;       // log2|cs| - lse * log2e with cs = g * (gamma_blank + gamma_label): dz = +-exp2(z log2e + c2)
+                    // (-1e30 for padding rows and cs == 0: exp2 -> 0)
+    uint32_t sgn;   // 0x80008000 if cs < 0 (a negative grad_cost), xor-ed into the packed bf16 pairs
+    float dblk;     // dz at the blank column:  cs * p_blank - g * gamma_blank (- g * gamma_label if label == blank)
+    float dlab;     // dz at the label column:  cs * p_label - g * gamma_label
+    int lab;        // label of the cell's emit transition, -1 if none (or == blank)
 };
 struct PRaw {
     float g, lse;
@@ -205,40 +215,53 @@ __device__ __forceinline__ void p_load_raw(PRaw& r, const PTile& ti, int m, cons
 }
 __device__ __forceinline__ PCell p_finish(const PRaw& r, int V, int blank) {
     PCell s;
-    s.nl2 = r.valid ? -r.lse * kLog2e : -1e30f;
-    s.cs = r.g * (r.gm.x + r.gm.y);
+    const float cs = r.g * (r.gm.x + r.gm.y);
+    s.c2 = (r.valid && cs != 0.f) ? fmaf(-r.lse, kLog2e, log2f(fabsf(cs))) : -1e30f;
+    s.sgn = cs < 0.f ? 0x80008000u : 0u;
     const int lab = r.lab < 0 ? -1 : min(r.lab, V - 1);
     const float cb = r.g * r.gm.x, cl = r.g * r.gm.y;
-    s.dblk = r.valid ? fmaf(s.cs, ex2_approx(r.lp.x * kLog2e), -cb) : 0.f;
-    s.dlab = (r.valid && lab >= 0) ? fmaf(s.cs, ex2_approx(r.lp.y * kLog2e), -cl) : 0.f;
+    s.dblk = r.valid ? fmaf(cs, ex2_approx(r.lp.x * kLog2e), -cb) : 0.f;
+    s.dlab = (r.valid && lab >= 0) ? fmaf(cs, ex2_approx(r.lp.y * kLog2e), -cl) : 0.f;
     if (lab == blank) { s.dblk -= cl; s.lab = -1; } else s.lab = lab;
     return s;
 }
 
-// One 32-column group of this thread's row: z = acc + bias, dz = cs * exp2(z log2e - lse log2e) -> bf16 into
-// the warp's staging buffer ([32 cells x 32 v], 64B swizzle, conflict-free 16-byte stores); the blank / label
-// entries are overwritten with their exact fp32 values (from the forward's lp2) before the TMA store.
+// One 32-column group of this thread's row: dz = +-exp2(acc log2e + (bias log2e + c2)) -> bf16 into the warp's
+// staging buffer ([32 cells x 32 v], 64B swizzle, conflict-free 16-byte stores); the blank / label entries are
+// overwritten with their exact fp32 values (from the forward's lp2) before the TMA store.  `bias` holds
+// b_out * log2e.  Packed fp32 pairs (FADD2 / FFMA2): 2.5 instructions per element with the MUFU and the bf16 pack.
+// (Tried: three of four exponentials as a polynomial on the FMA pipe, FlashAttention-4 style -- the producers' tanh
+// got faster but the epilogue, which is bound by issue latency with two warps per scheduler and not by the MUFU,
+// got slower: kernel 2.11 -> 2.25 ms.)
 // live == false: a 32-column group past the vocabulary (V % 64 == 32): zeros, so that the consumers' 64-wide K
 // blocks never see stale ring content.
 __device__ __forceinline__ void dz_group(const uint32_t (&r)[32], const float* __restrict__ bias, int v0,
-                                         const PCell& s, int blank, const CUtensorMap* tmap_z, uint8_t* zbuf,
-                                         int zcol, int zrow, int lane, bool live) {
+                                         const PCell& s, bool anyneg, int blank, const CUtensorMap* tmap_z,
+                                         uint8_t* zbuf, int zcol, int zrow, int lane, bool live
+                                         EMO_PROF(, long long& p_rd, long long& p_st)) {
     uint32_t o[16];
 #pragma unroll
     for (int i = 0; i < 16; ++i) o[i] = 0u;
+    const float2 c2 = make_float2(s.c2, s.c2), l2 = make_float2(kLog2e, kLog2e);
 #pragma unroll
     for (int i = 0; i < 32; i += 4) {
         if (!live) break;
         const float4 bv = *reinterpret_cast<const float4*>(bias + i);
-        const float d0 = s.cs * ex2_approx(fmaf(__uint_as_float(r[i + 0]) + bv.x, kLog2e, s.nl2));
-        const float d1 = s.cs * ex2_approx(fmaf(__uint_as_float(r[i + 1]) + bv.y, kLog2e, s.nl2));
-        const float d2 = s.cs * ex2_approx(fmaf(__uint_as_float(r[i + 2]) + bv.z, kLog2e, s.nl2));
-        const float d3 = s.cs * ex2_approx(fmaf(__uint_as_float(r[i + 3]) + bv.w, kLog2e, s.nl2));
-        o[i >> 1] = pack_bf16x2(d0, d1);
-        o[(i >> 1) + 1] = pack_bf16x2(d2, d3);
+        const float2 t0 = __ffma2_rn(make_float2(__uint_as_float(r[i + 0]), __uint_as_float(r[i + 1])), l2,
+                                     __fadd2_rn(make_float2(bv.x, bv.y), c2));
+        const float2 t1 = __ffma2_rn(make_float2(__uint_as_float(r[i + 2]), __uint_as_float(r[i + 3])), l2,
+                                     __fadd2_rn(make_float2(bv.z, bv.w), c2));
+        o[i >> 1] = pack_bf16x2(ex2_approx(t0.x), ex2_approx(t0.y));
+        o[(i >> 1) + 1] = pack_bf16x2(ex2_approx(t1.x), ex2_approx(t1.y));
     }
-    if (lane == 0) tma_store_wait_read<0>();   // the previous block has left the staging buffer
+    if (anyneg) {   // warp-uniform, false unless some utterance has a negative grad_cost
+#pragma unroll
+        for (int i = 0; i < 16; ++i) o[i] ^= s.sgn;
+    }
+    EMO_PROF(long long p_c = clock64();)
+    if (lane == 0) tma_store_wait_read<kZStBufs - 1>();   // the block before the previous one has left its buffer
     __syncwarp();
+    EMO_PROF(p_rd += clock64() - p_c; p_c = clock64();)
     uint8_t* rowp = zbuf + lane * 64;
     const int sw = (lane >> 1) & 3;
 #pragma unroll
@@ -256,6 +279,7 @@ __device__ __forceinline__ void dz_group(const uint32_t (&r)[32], const float* _
         tma_store_2d(tmap_z, smem_u32(zbuf), zcol, zrow);
         tma_store_commit();
     }
+    EMO_PROF(p_st += clock64() - p_c;)
 }
 
 // A-operand producer: this warp's 16 rows of the 128-row tile, one 64-wide K block (see joint_bf16.cu)
@@ -284,7 +308,7 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
     uint8_t* sA = smem;
     uint8_t* sB = sA + (size_t)KB * kABlockBytes;
     uint8_t* sZst = sB + (size_t)kPBStages * kStageBytes;
-    PBars* bars = reinterpret_cast<PBars*>(sZst + (kPEpiThreads / 32) * kZStBytes);
+    PBars* bars = reinterpret_cast<PBars*>(sZst + (kPEpiThreads / 32) * kZStBufs * kZStBytes);
     float* s_bias = reinterpret_cast<float*>(bars + 1);               // [2][kChunkN]
     int* s_prefix = reinterpret_cast<int*>(s_bias + 2 * kChunkN);    // [B+1] + [B]
 
@@ -358,16 +382,22 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
                 uint32_t stage = 0, phase = 0, cc = 0, tl = 0;
                 const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
                 const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
+                EMO_PROF(long long p_acc = 0, p_a = 0, p_b = 0, p_t0 = clock64(), p_c;)
                 for (int q = pidx; q < Q; q += a.nP) {
                     for (int nc = 0; nc < NC; ++nc, ++cc) {
                         const uint32_t buf = cc & 1;
+                        EMO_PROF(p_c = clock64();)
                         mbar_wait(smem_u32(&bars->acc_empty[buf]), ((cc >> 1) & 1) ^ 1);
+                        EMO_PROF(p_acc += clock64() - p_c;)
                         const int n = min(kChunkN, a.V - nc * kChunkN);
                         const uint32_t idesc = umma_idesc_bf16(kPairM, n);
                         const uint32_t d_tmem = tmem_base + buf * kChunkN;
                         for (int kb = 0; kb < KB; ++kb) {
+                            EMO_PROF(p_c = clock64();)
                             if (nc == 0) mbar_wait(smem_u32(&bars->a_full[kb]), tl & 1);
+                            EMO_PROF(p_a += clock64() - p_c; p_c = clock64();)
                             mbar_wait(smem_u32(&bars->b_full[stage]), phase);
+                            EMO_PROF(p_b += clock64() - p_c;)
                             tc_fence_after();
                             if (elect_one_sync()) {
                                 const uint32_t a_lo = a_lo0 + kb * (kABlockBytes >> 4);
@@ -386,6 +416,9 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
                     }
                     ++tl;
                 }
+                EMO_PROF(if (pidx == 0 && lane == 0)
+                             printf("ring P issuer: total %lld clk, %u tiles; wait acc_empty %lld a_full %lld b_full %lld\n",
+                                    clock64() - p_t0, tl, p_acc, p_a, p_b);)
             }
         } else if (warp == 3) {
             // ===================== h writer: every finished h block -> ring =====================
@@ -415,11 +448,12 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
         const int qd = warp & 3, hf = (warp - 4) >> 2;
         const int row = qd * 32 + lane;
         const int etid = threadIdx.x - 128;   // 0..255
-        uint8_t* zbuf = sZst + (warp - 4) * kZStBytes;
+        uint8_t* zbuf0 = sZst + (warp - 4) * kZStBufs * kZStBytes;   // alternating blocks (g & 1)
         const uint32_t acc_empty0 = mapa_shared(smem_u32(&bars->acc_empty[0]), 0);
         uint32_t cc = 0;
         int pending = -1;                      // z slot whose stores have been issued but not yet published
-        float nb = etid < a.V ? __ldg(a.b_out + etid) : 0.f;
+        EMO_PROF(long long p_sig = 0, p_gate = 0, p_accw = 0, p_t0 = clock64(), p_rd = 0, p_st = 0, p_bar = 0, p_ldw = 0;)
+        float nb = etid < a.V ? __ldg(a.b_out + etid) * kLog2e : 0.f;   // bias * log2e (see dz_group)
         PTile ti;
         PRaw nxt;
         if (pidx < Q) {
@@ -428,6 +462,7 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
         }
         for (int q = pidx; q < Q; q += a.nP) {
             const PCell cur = p_finish(nxt, a.V, a.blank);
+            const bool anyneg = __any_sync(0xffffffffu, cur.sgn != 0u);
             if (q + a.nP < Q) {   // next tile's scalars stay in flight during this tile
                 ptile(q + a.nP, s_prefix, a.B, ti);
                 p_load_raw(nxt, ti, ti.first_cell + (int)rank * kTileM + row, a);
@@ -440,10 +475,13 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
                 {   // prefetch the next chunk's bias (wraps to chunk 0 for the next tile)
                     const int nn = (nc + 1 == NC) ? 0 : nc + 1;
                     const int i0 = nn * kChunkN + etid;
-                    nb = i0 < a.V ? __ldg(a.b_out + i0) : 0.f;
+                    nb = i0 < a.V ? __ldg(a.b_out + i0) * kLog2e : 0.f;
                 }
+                EMO_PROF(const long long p_cb = clock64();)
                 named_bar_sync(1, kPEpiThreads);
+                EMO_PROF(const long long p_c0 = clock64(); p_bar += p_c0 - p_cb;)
                 mbar_wait(smem_u32(&bars->acc_full[buf]), (cc >> 1) & 1);
+                EMO_PROF(p_accw += clock64() - p_c0;)
                 tc_fence_after();
                 const int item = q * a.G + (nc >> 2);
                 const int zs = item % a.NZ;
@@ -451,8 +489,11 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
                     // first chunk of a ring item: publish the previous item (its stores were issued a chunk
                     // ago), then make sure every consumer has released this slot's previous content
                     if (lane == 0) {
+                        EMO_PROF(const long long p_c = clock64();)
                         if (pending >= 0) ring_signal_stored(z_ready + pending);
+                        EMO_PROF(p_sig += clock64() - p_c;)
                         ring_wait(z_done + zs, (item / a.NZ) * (1 + roles_in_group(zs % a.G, a.V)));
+                        EMO_PROF(p_gate += clock64() - p_c;)
                     }
                     pending = zs;
                     __syncwarp();
@@ -466,15 +507,17 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
                     uint32_t ra[32], rb[32];
                     tmem_ld_32x32b_x32(taddr + g0 * 32, ra);
                     for (int g = g0; g < g1; g += 2) {
+                        EMO_PROF(const long long p_cl = clock64();)
                         tmem_wait_ld();
+                        EMO_PROF(p_ldw += clock64() - p_cl;)
                         if (g + 1 < g1) tmem_ld_32x32b_x32(taddr + (g + 1) * 32, rb);
-                        dz_group(ra, bias + g * 32, nc * kChunkN + g * 32, cur, a.blank, tm_zst, zbuf,
-                                 zcol0 + g * 32, zrow, lane, g < gl);
+                        dz_group(ra, bias + g * 32, nc * kChunkN + g * 32, cur, anyneg, a.blank, tm_zst, zbuf0,
+                                 zcol0 + g * 32, zrow, lane, g < gl EMO_PROF(, p_rd, p_st));
                         if (g + 1 < g1) {
                             tmem_wait_ld();
                             if (g + 2 < g1) tmem_ld_32x32b_x32(taddr + (g + 2) * 32, ra);
-                            dz_group(rb, bias + (g + 1) * 32, nc * kChunkN + (g + 1) * 32, cur, a.blank, tm_zst, zbuf,
-                                     zcol0 + (g + 1) * 32, zrow, lane, g + 1 < gl);
+                            dz_group(rb, bias + (g + 1) * 32, nc * kChunkN + (g + 1) * 32, cur, anyneg, a.blank, tm_zst,
+                                     zbuf0 + kZStBytes, zcol0 + (g + 1) * 32, zrow, lane, g + 1 < gl EMO_PROF(, p_rd, p_st));
                         }
                     }
                 }
@@ -487,6 +530,10 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
             if (pending >= 0) ring_signal_stored(z_ready + pending);
             else tma_store_wait_all<0>();
         }
+        EMO_PROF(if (pidx == 0 && warp == 4 && lane == 0)
+                     printf("ring P epilogue warp 4: total %lld clk; wait acc_full %lld, publish %lld, publish + slot gate %lld, "
+                            "named barrier %lld, tmem ld wait (even groups) %lld, staging wait_read %lld, sts+fence+tma issue %lld\n",
+                            clock64() - p_t0, p_accw, p_sig, p_gate, p_bar, p_ldw, p_rd, p_st);)
     } else {
         reg_dec<88>();
         // ===================== A producers: h = tanh(enc + dec) -> bf16 -> K-major SW128 smem =====================
@@ -637,11 +684,14 @@ __device__ __forceinline__ void role_dh(const RingArgs& a, const CUtensorMap* tm
         // ===================== TMA: this CTA's dz blocks [128 cells x 64 v] from the ring =====================
         if (lane == 0) {
             uint32_t zs = 0, zph = 0;
+            EMO_PROF(long long p_ring = 0, p_t0 = clock64(), p_c;)
             for (int q = didx; q < Q; q += a.nD) {
                 for (int kb = 0; kb < NKB; ++kb) {
                     const int item = q * a.G + kb / (kVG / kBlockK);
                     const int rs = item % a.NZ;
+                    EMO_PROF(p_c = clock64();)
                     if (kb % (kVG / kBlockK) == 0) ring_wait(z_ready + rs, (item / a.NZ + 1) * 2 * (kPEpiThreads / 32));
+                    EMO_PROF(p_ring += clock64() - p_c;)
                     mbar_wait(smem_u32(&bars->dz_empty[zs]), zph ^ 1);
                     const uint32_t full = smem_u32(&bars->dz_full[zs]);
                     mbar_arrive_expect_tx_cluster(mapa_shared(full, 0), kStageBytes);
@@ -650,6 +700,8 @@ __device__ __forceinline__ void role_dh(const RingArgs& a, const CUtensorMap* tm
                     if (++zs == kDZStages) { zs = 0; zph ^= 1; }
                 }
             }
+            EMO_PROF(if (didx == 0 && leader)
+                         printf("ring D dz loader: total %lld clk; waiting for ring items %lld\n", clock64() - p_t0, p_ring);)
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA) =====================
@@ -657,11 +709,17 @@ __device__ __forceinline__ void role_dh(const RingArgs& a, const CUtensorMap* tm
             uint32_t zs = 0, zph = 0, slot = 0, ph = 0, tl = 0;
             const uint32_t z_lo0 = desc_lo(smem_u32(sZ), 16);
             const uint32_t w_lo0 = desc_lo(smem_u32(sW), kBoxBytes);
+            EMO_PROF(long long p_acc = 0, p_dz = 0, p_op = 0, p_t0 = clock64(), p_c;)
             for (int q = didx; q < Q; q += a.nD) {
+                EMO_PROF(p_c = clock64();)
                 mbar_wait(smem_u32(&bars->acc_empty), (tl & 1) ^ 1);
+                EMO_PROF(p_acc += clock64() - p_c;)
                 for (int kb = 0; kb < NKB; ++kb) {
+                    EMO_PROF(p_c = clock64();)
                     mbar_wait(smem_u32(&bars->dz_full[zs]), zph);
+                    EMO_PROF(p_dz += clock64() - p_c; p_c = clock64();)
                     mbar_wait(smem_u32(&bars->op_full[slot]), ph);
+                    EMO_PROF(p_op += clock64() - p_c;)
                     tc_fence_after();
                     if (elect_one_sync()) {
                         // the ring item has been read completely once its last K block has landed
@@ -688,21 +746,24 @@ __device__ __forceinline__ void role_dh(const RingArgs& a, const CUtensorMap* tm
                 }
                 ++tl;
             }
+            EMO_PROF(if (didx == 0 && lane == 0)
+                         printf("ring D issuer: total %lld clk, %u tiles; wait acc_empty %lld dz_full %lld op_full %lld\n",
+                                clock64() - p_t0, tl, p_acc, p_dz, p_op);)
         }
     } else if (warp >= 20 - kDrainWarps) {
-        // ===================== drain: dh -> bf16, tile-major (rows of the h-cache layout, J) =====================
-        // Each warp moves its [32 cells x 64 j] blocks through a private shared-memory buffer (128B swizzle,
-        // conflict-free 16-byte stores) and one TMA store per block; the factor (1 - h^2) is applied by the
-        // reduction kernel.
+        // ===================== drain: dh -> bf16, tile-major (rows of the valid cells, J) =====================
+        // 16 warps: TMEM lane quadrant qd = warp & 3, column quarter cq.  Each warp moves its [32 cells x 32 j]
+        // blocks through a private shared-memory buffer (64B swizzle, conflict-free 16-byte stores) and one TMA
+        // store per block; the factor (1 - h^2) is applied by the reduction kernel.
         const int dw = warp - (20 - kDrainWarps);
-        const int qd = warp & 3, hf = (dw >> 2) & 1;
+        const int qd = warp & 3, cq = dw >> 2;
         const uint32_t lane_base = (uint32_t)(qd * 32) << 16;
         const uint32_t acc_empty_addr = mapa_shared(smem_u32(&bars->acc_empty), 0);
-        const int G = a.J >> 6;              // 32-column groups per column half
-        const int col_base = hf * (a.J >> 1);
+        const int G = a.J >> 7;              // 32-column groups per column quarter
+        const int col_base = cq * (a.J >> 2);
         uint8_t* buf = sDst + dw * kDrainBufBytes;
-        uint8_t* rowp = buf + lane * 128;
-        const int sw = lane & 7;
+        uint8_t* rowp = buf + lane * 64;
+        const int sw = (lane >> 1) & 3;
         uint32_t tl = 0;
         PTile ti;
         for (int q = didx; q < Q; q += a.nD) {
@@ -710,31 +771,33 @@ __device__ __forceinline__ void role_dh(const RingArgs& a, const CUtensorMap* tm
             const int row0 = (ti.b * tpu + (ti.first_cell + (int)rank * kTileM) / kTileM) * kTileM + qd * 32;
             mbar_wait(smem_u32(&bars->acc_full), tl & 1);
             tc_fence_after();
-            for (int g = 0; g < G; g += 2) {     // two 32-column groups = one 128-byte row piece per TMA store
-                uint32_t ra[32], rb[32];
-                tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + g * 32, ra);
-                tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + g * 32 + 32, rb);
-                tmem_wait_ld();
+            auto put = [&](const uint32_t (&x)[32], int g) {
                 if (lane == 0) tma_store_wait_read<0>();   // the previous block has left the buffer
                 __syncwarp();
 #pragma unroll
-                for (int j = 0; j < 4; ++j) {
+                for (int j = 0; j < 4; ++j)
                     *reinterpret_cast<uint4*>(rowp + ((j ^ sw) << 4)) = make_uint4(
-                        pack_bf16x2(__uint_as_float(ra[8 * j]), __uint_as_float(ra[8 * j + 1])),
-                        pack_bf16x2(__uint_as_float(ra[8 * j + 2]), __uint_as_float(ra[8 * j + 3])),
-                        pack_bf16x2(__uint_as_float(ra[8 * j + 4]), __uint_as_float(ra[8 * j + 5])),
-                        pack_bf16x2(__uint_as_float(ra[8 * j + 6]), __uint_as_float(ra[8 * j + 7])));
-                    *reinterpret_cast<uint4*>(rowp + (((4 + j) ^ sw) << 4)) = make_uint4(
-                        pack_bf16x2(__uint_as_float(rb[8 * j]), __uint_as_float(rb[8 * j + 1])),
-                        pack_bf16x2(__uint_as_float(rb[8 * j + 2]), __uint_as_float(rb[8 * j + 3])),
-                        pack_bf16x2(__uint_as_float(rb[8 * j + 4]), __uint_as_float(rb[8 * j + 5])),
-                        pack_bf16x2(__uint_as_float(rb[8 * j + 6]), __uint_as_float(rb[8 * j + 7])));
-                }
+                        pack_bf16x2(__uint_as_float(x[8 * j]), __uint_as_float(x[8 * j + 1])),
+                        pack_bf16x2(__uint_as_float(x[8 * j + 2]), __uint_as_float(x[8 * j + 3])),
+                        pack_bf16x2(__uint_as_float(x[8 * j + 4]), __uint_as_float(x[8 * j + 5])),
+                        pack_bf16x2(__uint_as_float(x[8 * j + 6]), __uint_as_float(x[8 * j + 7])));
                 fence_proxy_async_smem();
                 __syncwarp();
                 if (lane == 0) {
                     tma_store_2d(tm_d, smem_u32(buf), col_base + g * 32, row0);
                     tma_store_commit();
+                }
+            };
+            uint32_t ra[32], rb[32];
+            tmem_ld_32x32b_x32(tmem_base + lane_base + col_base, ra);
+            for (int g = 0; g < G; g += 2) {
+                tmem_wait_ld();
+                if (g + 1 < G) tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + (g + 1) * 32, rb);
+                put(ra, g);
+                if (g + 1 < G) {
+                    tmem_wait_ld();
+                    if (g + 2 < G) tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + (g + 2) * 32, ra);
+                    put(rb, g + 1);
                 }
             }
             tc_fence_before();
@@ -846,10 +909,13 @@ __device__ __forceinline__ void role_dw(const RingArgs& a, const CUtensorMap* tm
         // ===================== TMA: dz blocks [64 cells x 128 v] of this CTA's vocab rows =====================
         if (lane == 0) {
             uint32_t zs = 0, zph = 0;
+            EMO_PROF(long long p_ring = 0, p_t0 = clock64(), p_c;)
             for (int q = split; q < Q; q += a.nS) {
                 const int item = q * a.G + gr;
                 const int rs = item % a.NZ;
+                EMO_PROF(p_c = clock64();)
                 ring_wait(z_ready + rs, (item / a.NZ + 1) * 2 * (kPEpiThreads / 32));
+                EMO_PROF(p_ring += clock64() - p_c;)
                 for (int kh = 0; kh < 4; ++kh) {
                     mbar_wait(smem_u32(&bars->dz_empty[zs]), zph ^ 1);
                     const uint32_t full = smem_u32(&bars->z_full[zs]);
@@ -860,6 +926,8 @@ __device__ __forceinline__ void role_dw(const RingArgs& a, const CUtensorMap* tm
                     if (++zs == kWZStages) { zs = 0; zph ^= 1; }
                 }
             }
+            EMO_PROF(if (widx == 0 && leader)
+                         printf("ring W dz loader: total %lld clk; waiting for ring items %lld\n", clock64() - p_t0, p_ring);)
         }
     } else if (warp == 1) {
         // ===================== MMA issuer (leader CTA) =====================
@@ -868,9 +936,13 @@ __device__ __forceinline__ void role_dw(const RingArgs& a, const CUtensorMap* tm
             const uint32_t z_lo0 = desc_lo(smem_u32(sZ), kBoxBytes);
             const uint32_t h_lo0 = desc_lo(smem_u32(sH), kBoxBytes);
             int q = split;
+            EMO_PROF(long long p_dz = 0, p_op = 0, p_t0 = clock64(), p_c;)
             for (int kbi = 0; kbi < n_kb; ++kbi) {
+                EMO_PROF(p_c = clock64();)
                 mbar_wait(smem_u32(&bars->dz_full[zs]), zph);
+                EMO_PROF(p_dz += clock64() - p_c; p_c = clock64();)
                 mbar_wait(smem_u32(&bars->op_full[slot]), ph);
+                EMO_PROF(p_op += clock64() - p_c;)
                 tc_fence_after();
                 if (elect_one_sync()) {
                     if ((kbi & 3) == 3) {   // the tile's ring items have been read completely by this pair
@@ -898,6 +970,9 @@ __device__ __forceinline__ void role_dw(const RingArgs& a, const CUtensorMap* tm
             }
             if (elect_one_sync()) umma_commit_pair(smem_u32(&bars->acc_full));
             __syncwarp();
+            EMO_PROF(if (widx == 0 && lane == 0)
+                         printf("ring W issuer: total %lld clk, %d K blocks; wait dz_full %lld op_full %lld\n",
+                                clock64() - p_t0, n_kb, p_dz, p_op);)
         }
     } else if (warp >= 4 && warp < 4 + kColsumWarps) {
         // ===================== column sums of dz (d_b_out), then the flush of dW =====================
@@ -986,7 +1061,7 @@ joint_bwd_ring_kernel(const __grid_constant__ CUtensorMap tm_w_p,    // w_out bf
                       const __grid_constant__ CUtensorMap tm_z_st,   // ring dz (NZ*256, VGW), box [32 v x 32 cells], 64B swizzle
                       const __grid_constant__ CUtensorMap tm_z_ld_d, // ring dz, box [64 v x 128 cells]
                       const __grid_constant__ CUtensorMap tm_z_ld_w, // ring dz, box [64 v x 64 cells]
-                      const __grid_constant__ CUtensorMap tm_dh,     // dh out bf16 (rows,J), box [64 j x 32 cells]
+                      const __grid_constant__ CUtensorMap tm_dh,     // dh out bf16 (rows,J), box [32 j x 32 cells], 64B swizzle
                       const RingArgs a) {
     extern __shared__ __align__(1024) uint8_t smem[];
     const int pair = blockIdx.x >> 1;
@@ -998,7 +1073,7 @@ joint_bwd_ring_kernel(const __grid_constant__ CUtensorMap tm_w_p,    // w_out bf
 size_t ring_smem_bytes(int B, int J) {
     const size_t prefix = (size_t)(2 * B + 1) * sizeof(int);
     const size_t p = (size_t)(J / kBlockK) * kABlockBytes + (size_t)kPBStages * kStageBytes +
-                     (kPEpiThreads / 32) * kZStBytes + sizeof(PBars) + 2 * kChunkN * sizeof(float) + prefix;
+                     (kPEpiThreads / 32) * kZStBufs * kZStBytes + sizeof(PBars) + 2 * kChunkN * sizeof(float) + prefix;
     const size_t d = (size_t)kDZStages * kStageBytes + (size_t)kDOpStages * J * 64 + kDrainWarps * kDrainBufBytes +
                      sizeof(DBars) + prefix;
     const size_t w = (size_t)kWZStages * kStageBytes + (size_t)kWOpStages * J * 64 + sizeof(WBars) + prefix;
@@ -1067,12 +1142,12 @@ size_t joint_ring_workspace(int B, int T, int U1, int J, int V) {
 // tanh / exp work, so it gets the larger share (measured: profiles/r2*_ring_split.txt).
 void ring_split(int pairs, int V, int& nP, int& nD, int& nS) {
     const int roles_v = ceil_div(V, 256);
-    nS = max(1, (int)(pairs * 0.30f / roles_v + 0.5f));
+    nS = max(1, (int)(pairs * 0.32f / roles_v + 0.5f));
     while (nS > 1 && pairs - nS * roles_v < 2) --nS;
     const int rest = pairs - nS * roles_v;
-    nD = max(1, (int)(rest * 0.46f + 0.5f));
-    nP = rest - nD;
-#ifdef EMO_TUNING
+    nD = max(1, (int)(rest * 0.42f + 0.5f));
+    nP = rest - nD;               // 74 pairs, V = 1024: 29 / 21 / 6 x 4
+#if defined(EMO_TUNING) || defined(EMO_ZC_PROF)
     if (const char* e = getenv("EMO_RING_SPLIT")) {   // "nP,nD,nS": tuning builds only (tools/)
         int p, d, s;
         if (sscanf(e, "%d,%d,%d", &p, &d, &s) == 3 && p > 0 && d > 0 && s > 0 && p + d + s * roles_v <= pairs) {
@@ -1119,8 +1194,8 @@ int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec
                                 CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
     if ((rc = make_tmap_bf16_2d(&tm_z_ld_d, zring, (uint64_t)g.vgw, (uint64_t)g.NZ * kPairM, kBlockK, kTileM))) return rc;
     if ((rc = make_tmap_bf16_2d(&tm_z_ld_w, zring, (uint64_t)g.vgw, (uint64_t)g.NZ * kPairM, kBlockK, 64))) return rc;
-    if ((rc = make_tmap_bf16_2d(&tm_dh, dh_ws, (uint64_t)J, (uint64_t)B * tiles128_per_utt(T, U1) * kTileM, 64, 32)))
-        return rc;
+    if ((rc = make_tmap_bf16_2d(&tm_dh, dh_ws, (uint64_t)J, (uint64_t)B * tiles128_per_utt(T, U1) * kTileM, 32, 32,
+                                CU_TENSOR_MAP_SWIZZLE_64B))) return rc;
 
     EMO_CUDA(cudaFuncSetAttribute(joint_bwd_ring_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     cudaLaunchConfig_t cfg = {};

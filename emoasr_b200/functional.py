@@ -162,7 +162,7 @@ def _zcache_bytes(precision, B, T, U1, J, V):
 
 class _RNNTJoint(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, blank, precision, route):
+    def forward(ctx, enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, blank, precision, route, grad_mode):
         _require_cuda(enc_proj, dec_proj, w_out, b_out)
         lib = _lib.load()
         enc, dec, w, bo = _f32c(enc_proj), _f32c(dec_proj), _f32c(w_out), _f32c(b_out)
@@ -181,7 +181,7 @@ class _RNNTJoint(torch.autograd.Function):
                 labels = labels[:, : U1 - 1].contiguous()
         else:
             labels = torch.zeros(B, 1, dtype=torch.int32, device=dev)
-        need_grad = any(ctx.needs_input_grad[:4]) and torch.is_grad_enabled()
+        need_grad = any(ctx.needs_input_grad[:4]) and grad_mode   # (grad mode is always off inside forward())
         with torch.cuda.device(dev):
             nbytes = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_FWD, precision, B, T, U1, J, V)
             ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
@@ -237,7 +237,7 @@ class _RNNTJoint(torch.autograd.Function):
                                               B, T, U1, J, V, blank, precision,
                                               _p(d_enc), _p(d_dec), _p(d_w), _p(d_b), _p(ws), ws.numel(),
                                               _stream()), "emo_rnnt_joint_bwd")
-        return d_enc, d_dec, d_w, d_b, None, None, None, None, None, None
+        return d_enc, d_dec, d_w, d_b, None, None, None, None, None, None, None
 
 
 def rnnt_joint_loss(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths, labels_lengths,
@@ -257,7 +257,7 @@ def rnnt_joint_loss(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths, la
     if route not in ROUTES:
         raise ValueError(f"unknown route {route!r}; expected one of {ROUTES}")
     costs = _RNNTJoint.apply(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths,
-                             labels_lengths, int(blank), _PRECISIONS[precision], route)
+                             labels_lengths, int(blank), _PRECISIONS[precision], route, torch.is_grad_enabled())
     return _reduce(costs, reduction)
 
 

@@ -109,6 +109,43 @@ def ctc_case(name, seed, B, T, U, V, He, tlens, ulens):
     print(name, float(loss))
 
 
+def ctc_mtl_case(name, seed, B, T, U, Up, V, Vp, He, tlens, ulens, plens, phone_w, hie, inter_w):
+    """Phone-CTC (ctc.py:129-148, final or intermediate layer) and intermediate-CTC (ctc.py:150-170) heads."""
+    from asr.modeling.decoders.ctc import CTCDecoder
+
+    base = _params(enc_hidden_size=He, vocab_size=V)._asdict()
+    base.update(mtl_phone_ctc_weight=phone_w, hie_mtl_phone=hie, phone_vocab_size=Vp, mtl_inter_ctc_weight=inter_w)
+    p = namedtuple("Params", base.keys())(**base)
+    torch.manual_seed(seed)
+    g = torch.Generator().manual_seed(seed)
+    dec = CTCDecoder(p)
+    eouts = torch.randn(B, T, He, generator=g).requires_grad_()
+    eouts_inter = torch.randn(B, T, He, generator=g).requires_grad_()
+    elens = torch.tensor(tlens, dtype=torch.long)
+    ylens = torch.tensor(ulens, dtype=torch.long)
+    pl = torch.tensor(plens, dtype=torch.long)
+    ys = _labels(g, B, U, V, ulens, p.eos_id)
+    ps = _labels(g, B, Up, Vp, plens, p.eos_id)
+    loss, loss_dict, logits = dec(eouts, elens, eouts_inter, ys, ylens, None, None, None, ps, pl)
+    loss.backward()
+    out = {
+        "eouts": _np(eouts), "eouts_inter": _np(eouts_inter), "elens": _np(elens), "ys": _np(ys), "ylens": _np(ylens),
+        "ps": _np(ps), "plens": _np(pl), "loss_total": _np(loss), "grad_eouts": _np(eouts.grad),
+        "grad_eouts_inter": _np(eouts_inter.grad) if eouts_inter.grad is not None else np.zeros(0),
+        "logits": _np(logits),
+    }
+    for k, v in loss_dict.items():
+        out["lossdict." + k] = _np(v)
+    for k, v in dec.state_dict().items():
+        out["param." + k] = _np(v)
+    for k, v in dec.named_parameters():
+        out["grad." + k] = _np(v.grad)
+    for k, v in p._asdict().items():
+        out["hp." + k] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, float(loss), {k: float(v) for k, v in loss_dict.items()})
+
+
 def smoke_fixtures():
     """Freeze the reference's two in-tree __main__ smoke inputs and what its CPU-runnable loss
     functions give on them, plus the warp-transducer known-answer vector."""
@@ -190,6 +227,18 @@ def main():
              tlens=[13, 9, 4, 13, 1], ulens=[6, 4, 6, 0, 1])
     ctc_case("ref_ctc_medium_ragged", 6, B=6, T=61, U=20, V=203, He=32,
              tlens=[61, 55, 50, 41, 30, 22], ulens=[20, 18, 20, 7, 11, 10])
+    # tensor-core-compatible joint shape (J % 128 == 0, V % 32 == 0): the drop-in decoder in bf16 mode is
+    # checked against the reference's own numbers at the stated bf16 tolerance
+    pt = _params(dec_num_layers=1, dec_hidden_size=32, embedding_size=16, joint_hidden_size=128,
+                 enc_hidden_size=24, vocab_size=64)
+    rnnt_case("ref_rnnt_tcshape_ragged", 7, B=4, T=21, U=9, p=pt, tlens=[21, 18, 12, 5], ulens=[9, 6, 9, 1])
+    rnnt_case("ref_rnnt_tcshape_auxctc", 8, B=3, T=17, U=6, p=pt, tlens=[17, 17, 10], ulens=[6, 2, 5],
+              mtl_ctc_weight=0.3)
+    # phone-CTC on the final layer, on the intermediate layer (hie_mtl_phone), and intermediate CTC
+    ctc_mtl_case("ref_ctc_phone_final", 9, B=4, T=19, U=5, Up=9, V=23, Vp=43, He=16, tlens=[19, 15, 12, 9],
+                 ulens=[5, 4, 2, 5], plens=[9, 7, 3, 8], phone_w=0.3, hie=False, inter_w=0.0)
+    ctc_mtl_case("ref_ctc_phone_hie_inter", 10, B=4, T=22, U=6, Up=10, V=29, Vp=43, He=16, tlens=[22, 20, 11, 6],
+                 ulens=[6, 5, 6, 1], plens=[10, 8, 9, 2], phone_w=0.3, hie=True, inter_w=0.5)
 
 
 if __name__ == "__main__":

@@ -7,7 +7,8 @@ import torch
 from conftest import load_golden, pred_net_douts, rel_err
 from oracle import clattice, ctc_dp, rnnt_dp, torch_path
 
-RNNT_CASES = ["ref_rnnt_small_full", "ref_rnnt_small_ragged", "ref_rnnt_small_auxctc", "ref_rnnt_medium_ragged"]
+RNNT_CASES = ["ref_rnnt_small_full", "ref_rnnt_small_ragged", "ref_rnnt_small_auxctc", "ref_rnnt_medium_ragged",
+              "ref_rnnt_tcshape_ragged", "ref_rnnt_tcshape_auxctc"]
 CTC_CASES = ["ref_ctc_small_full", "ref_ctc_small_ragged", "ref_ctc_medium_ragged"]
 
 
@@ -81,6 +82,39 @@ def test_ctc_dp_vs_reference_golden(name):
     assert rel_err(c["d_eouts"], g["grad_eouts"]) < 1e-4
     assert rel_err(c["d_w"], g["grad.output.weight"]) < 1e-4
     assert rel_err(c["d_b"], g["grad.output.bias"]) < 1e-4
+
+
+@pytest.mark.parametrize("name", ["ref_ctc_phone_final", "ref_ctc_phone_hie_inter"])
+def test_ctc_dp_vs_reference_golden_phone_and_inter_heads(name):
+    """Phone CTC (final / intermediate layer, ctc.py:129-148) and intermediate CTC (ctc.py:150-170): the same
+    head recipe on other inputs / weights; loss_total = ctc + w_p * phone + w_i * inter."""
+    g = load_golden(name)
+    blank = int(g["hp.blank_id"])
+    wp, wi, hie = float(g["hp.mtl_phone_ctc_weight"]), float(g["hp.mtl_inter_ctc_weight"]), bool(g["hp.hie_mtl_phone"])
+    main = ctc_dp.ctc_head_loss_and_grads(g["eouts"], g["param.output.weight"], g["param.output.bias"],
+                                          g["ys"], g["elens"], g["ylens"], blank=blank)
+    src = g["eouts_inter"] if hie else g["eouts"]
+    phone = ctc_dp.ctc_head_loss_and_grads(src, g["param.phone_output.weight"], g["param.phone_output.bias"],
+                                           g["ps"], g["elens"], g["plens"], blank=blank)
+    total = main["loss"] + wp * phone["loss"]
+    d_eouts = main["d_eouts"] + (0 if hie else wp * phone["d_eouts"])
+    d_inter = wp * phone["d_eouts"] if hie else 0
+    d_w = main["d_w"]
+    key = "lossdict.loss_phone_ctc(inter)" if hie else "lossdict.loss_phone_ctc"
+    assert abs(phone["loss"] - float(g[key])) <= 1e-5 * abs(phone["loss"])
+    if wi > 0:
+        inter = ctc_dp.ctc_head_loss_and_grads(g["eouts_inter"], g["param.output.weight"], g["param.output.bias"],
+                                               g["ys"], g["elens"], g["ylens"], blank=blank)
+        assert abs(inter["loss"] - float(g["lossdict.loss_inter_ctc"])) <= 1e-5 * abs(inter["loss"])
+        total += wi * inter["loss"]
+        d_inter = d_inter + wi * inter["d_eouts"]
+        d_w = d_w + wi * inter["d_w"]
+    assert abs(total - float(g["loss_total"])) <= 1e-5 * abs(total)
+    assert rel_err(d_eouts, g["grad_eouts"]) < 1e-4
+    if g["grad_eouts_inter"].size:
+        assert rel_err(d_inter, g["grad_eouts_inter"]) < 1e-4
+    assert rel_err(d_w, g["grad.output.weight"]) < 1e-4
+    assert rel_err(wp * phone["d_w"], g["grad.phone_output.weight"]) < 1e-4
 
 
 def test_ctc_aligner_smoke_fixture():
