@@ -3,16 +3,21 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload rnnt_cfg3|rnnt_cfg4|ctc_cfg2|ctc_cfg1] [--precision bf16|fp32]
-                    [--lengths full|ragged]
+                    [--route ring|zcache] [--lengths full|ragged] [--grad-payload-mb M] [--no-extras]
 
 A "step" is one pass of the hot path over one batch of synthetic input:
   RNN-T  enc_proj = w_enc(eouts), dec_proj = w_dec(douts)  (plain cuBLAS Linear, as in the
          reference's joint) -> fused joint + log-softmax + transducer loss -> backward to eouts,
          douts and every joint parameter   (asr/modeling/decoders/rnn_transducer.py:101-115,147-156)
-  CTC    logits -> fused log-softmax + CTC loss -> backward to logits (asr/modeling/decoders/ctc.py:109-113)
-Default workload (N=1): BASELINE cfg 3, "RNN-T(Cf.) 1kBPE 26M fused joint+loss, B=32 T=250 U=100 V=1024".
-For N>1 every rank processes its own batch of the same shape (weak scaling, batch-sharded) and the
-gradients of the path's parameters are all-reduced over NCCL inside the timed step.
+  CTC    eouts -> output Linear -> fused log-softmax + CTC loss -> backward to eouts and the Linear's
+         parameters                         (asr/modeling/decoders/ctc.py:103-113)
+Default workload (N=1): BASELINE cfg 3, "RNN-T(Cf.) 1kBPE 26M fused joint+loss, B=32 T=250 U=100 V=1024", on the
+default route "ring" (nothing of size N x V is written to HBM, forward or backward).  The default N=1 run also
+reports, under "extra", the opt-in z-cache route of the same workload, CTC cfg 2, and same-box GPU baselines
+(the reference's materialised op sequence on CUDA; torch's CUDA ctc_loss) -- `--no-extras` skips them.
+For N>1 every rank processes its own batch of the same shape (weak scaling, batch-sharded) and the gradients of
+the path's parameters (plus, with --grad-payload-mb, a stand-in for the rest of the model's gradients) are
+all-reduced over NCCL inside the timed step, launched from autograd hooks so that they overlap the backward.
 
 One JSON line is printed by rank 0 (see the driver contract in the task statement).
 """
@@ -42,18 +47,7 @@ WORKLOADS = {
     "ctc_cfg1": dict(kind="ctc", B=8, T=249, U=60, V=10872, He=256,
                      desc="CTC(Trf.) 20M (L1-style) CTC loss, batch 8, T=249, V=10872"),
 }
-
-
-# dram__bytes_read.sum + dram__bytes_write.sum per launch, from the ncu --set full captures under profiles/.
-# recompute route (profiles/r1c_ncu_full_metrics.txt): bwd = joint_dh_kernel + reduce_dpre_kernel +
-#   joint_dwt_kernel; algorithmic: h cache read twice, dpre written once and read once = 3.3 GB
-# z-cache route (profiles/r1l_ncu_full_metrics.txt): fwd writes h + z; bwd = joint_dhz_kernel (z + w_out read,
-#   dh written) + reduce_dh_tanh_kernel (dh read, h recomputed) + joint_dwz_kernel (z + h read); algorithmic:
-#   z read twice, h read once, dh written and read once = 5.8 GB
-NCU_DRAM_BYTES = {"rnnt_cfg3": {"fwd": 24.1e6 + 781.9e6,
-                                "bwd": (842.4e6 + 776.5e6) + (834.2e6 + 21.9e6) + (844.1e6 + 4.5e6)},
-                  "rnnt_cfg3_zc": {"fwd": 13.6e6 + 2451.2e6,
-                                   "bwd": (1683.1e6 + 795.9e6) + (857.1e6 + 25.7e6) + (2498.1e6 + 3.9e6)}}
+TRAFFIC_FILE = os.path.join(ROOT, "profiles", "dram_traffic.json")   # written by tools/ncu_traffic.py from ncu --set full
 
 
 def load_peaks():
@@ -63,6 +57,17 @@ def load_peaks():
         return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d.get("bf16_tflops_sustained"),
                     src="measured (MEASURED_PEAKS.json)")
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
+
+
+def load_traffic(workload, route):
+    """dram__bytes_read.sum + dram__bytes_write.sum per call, from the committed ncu --set full capture of this
+    workload (profiles/dram_traffic.json names the capture it came from).  None if there is no capture."""
+    try:
+        d = json.load(open(TRAFFIC_FILE))
+        e = d[workload][route]
+        return e, d.get("_source")
+    except (OSError, KeyError, ValueError):
+        return None, None
 
 
 # ------------------------------------------------------------------------------------------------
@@ -108,12 +113,30 @@ class RNNTWorkload:
         return 2.0 * self.n_valid * self.w["J"] * self.w["V"]
 
 
+class CTCWorkload:
+    """Synthetic cfg-1/cfg-2 CTC head inputs: eouts ~ N(0,1) (B,T,He), output Linear(He,V) default init."""
+
+    def __init__(self, w, seed, regime):
+        gen = torch.Generator().manual_seed(seed)
+        B, T, U, V = w["B"], w["T"], w["U"], w["V"]
+        self.w = w
+        self.eouts = torch.randn(B, T, w["He"], generator=gen)
+        self.tlen, _ = make_lengths(B, T, U, regime, gen)
+        self.ulen = torch.randint(U // 2, U + 1, (B,), generator=gen)
+        self.ys = make_labels(B, U, V, gen)
+        torch.manual_seed(1234)
+        self.output = torch.nn.Linear(w["He"], V)
+
+
 def run_e2e(step, host, dev, steps, first=lambda out: out):
     """`steps` steps through the public API with HOST inputs: every step's inputs are copied from pinned host
     memory (on a copy stream, issued while the previous step computes -- what a prefetching loader does) and
-    every step's loss is read back to the host.  Returns wall-clock seconds for exactly `steps` steps."""
+    every step's loss is copied back to pinned host memory and read by the host.  The read of step i's loss
+    happens after step i+1 has been enqueued (one step late, as a logging loop does), so the device never waits
+    for the host.  Returns wall-clock seconds for exactly `steps` steps, all losses read."""
     copy_stream = torch.cuda.Stream(device=dev)
     main = torch.cuda.current_stream(dev)
+    pinned = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
 
     def upload():
         with torch.cuda.stream(copy_stream):
@@ -125,17 +148,78 @@ def run_e2e(step, host, dev, steps, first=lambda out: out):
     torch.cuda.synchronize(dev)
     t0 = time.perf_counter()
     nxt = upload()
+    pending = None   # (pinned scalar, event) of the previous step
+    total = 0.0
     for i in range(steps):
         cur, ev = nxt
         main.wait_event(ev)
         for t in cur:
             t.record_stream(main)
         out = step(*cur)
+        buf = pinned[i & 1]
+        buf.copy_(first(out).detach().float(), non_blocking=True)
+        done = torch.cuda.Event()
+        done.record(main)
         if i + 1 < steps:
             nxt = upload()
-        float(first(out))
+        if pending is not None:
+            pending[1].synchronize()
+            total += float(pending[0])
+        pending = (buf, done)
+    pending[1].synchronize()
+    total += float(pending[0])
     torch.cuda.synchronize(dev)
     return time.perf_counter() - t0
+
+
+def timed_steps(step, resident, steps, flush, barrier):
+    """`steps` steps with device-resident inputs: per-step CUDA events, L2 flushed (untimed) between steps."""
+    evs = []
+    for _ in range(steps):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        step(*resident)
+        b.record()
+        evs.append((a, b))
+    barrier()
+    return sum(a.elapsed_time(b) for a, b in evs)
+
+
+def time_call(fn, flush, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    kev = []
+    for _ in range(iters):
+        flush.fill_(1)
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        kev.append((a, b))
+    torch.cuda.synchronize()
+    return statistics.mean(a.elapsed_time(b) for a, b in kev)
+
+
+# ------------------------------------------------------------------------------------------------
+def rnnt_step_fn(E, wl, route, precision, params, buckets, payload, world):
+    crit = E.RNNTJointLoss(blank_id=0, precision=precision, route=route)
+
+    def step(eouts, douts, ys, tlen, ulen):
+        if buckets is not None:
+            buckets.zero()          # in place: the gradients live inside the all-reduce buckets
+        else:
+            for p in params:
+                p.grad = None
+        eouts = eouts.detach().requires_grad_()
+        douts = douts.detach().requires_grad_()
+        loss = crit(wl.w_enc(eouts), wl.w_dec(douts), wl.output.weight, wl.output.bias, ys, tlen, ulen)
+        loss.backward()             # the buckets' all-reduces are launched from autograd hooks during this call
+        if world > 1:
+            if payload is not None:
+                buckets.start_extra(payload)   # stand-in for the rest of the model's gradients
+            buckets.finish()        # compute stream waits for the collectives (no host sync)
+        return loss
+    return step
 
 
 def run_ours_rnnt(args, w, rank, world, dev):
@@ -147,26 +231,19 @@ def run_ours_rnnt(args, w, rank, world, dev):
     torch.backends.cuda.matmul.allow_tf32 = args.precision == "bf16"
     wl = RNNTWorkload(w, seed=rank, regime=args.lengths)
     mods = torch.nn.ModuleList([wl.w_enc, wl.w_dec, wl.output]).to(dev)
-    params = list(mods.parameters())
-    crit = E.RNNTJointLoss(blank_id=0, precision=args.precision)
-    buckets = sharding.GradBuckets(params, own_grads=True) if world > 1 else None   # p.grad = views of flat buckets
+    # bucket order = order in which the gradients become final: output.* when the fused backward retires, then
+    # w_dec.*, w_enc.* (small GEMMs after the axis reductions)
+    params = [wl.output.weight, wl.output.bias, wl.w_dec.weight, wl.w_dec.bias, wl.w_enc.weight, wl.w_enc.bias]
+    buckets, payload = None, None
+    if world > 1:
+        buckets = sharding.GradBuckets(params, bucket_bytes=2200 << 10, own_grads=True)   # p.grad = views of flat buckets
+        buckets.attach_hooks()
+        if args.grad_payload_mb > 0:
+            payload = torch.zeros(int(args.grad_payload_mb * 1e6) // 4, device=dev)
     host = [t.pin_memory() for t in (wl.eouts, wl.douts, wl.ys.int(), wl.tlen.int(), wl.ulen.int())]
     resident = [t.to(dev) for t in host]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def step(eouts, douts, ys, tlen, ulen):
-        if buckets is not None:
-            buckets.zero()          # in place: the gradients live inside the all-reduce buckets
-        else:
-            for p in params:
-                p.grad = None
-        eouts = eouts.detach().requires_grad_()
-        douts = douts.detach().requires_grad_()
-        loss = crit(wl.w_enc(eouts), wl.w_dec(douts), wl.output.weight, wl.output.bias, ys, tlen, ulen)
-        loss.backward()
-        if world > 1:
-            buckets.allreduce()     # NCCL sum over ranks, / world (emoasr_b200/sharding.py)
-        return loss
+    step = rnnt_step_fn(E, wl, args.route, args.precision, params, buckets, payload, world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -177,168 +254,261 @@ def run_ours_rnnt(args, w, rank, world, dev):
     for _ in range(args.warmup):
         step(*resident)
     barrier()
-    # ---- device-resident timing: per-step CUDA events, L2 flushed (untimed) between steps
     mon = ClockMonitor(dev.index if dev.index is not None else 0, enabled=rank == 0)
     mon.start()
-    evs = []
-    for _ in range(args.steps):
-        flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        step(*resident)
-        b.record()
-        evs.append((a, b))
-    barrier()
+    ms_total = timed_steps(step, resident, args.steps, flush, barrier)
     clocks = mon.stop()
-    ms_total = sum(a.elapsed_time(b) for a, b in evs)
     # ---- end-to-end: host (pinned) buffers in, loss value out, wall clock
     run_e2e(step, host, dev, 2)
     barrier()
     e2e_s = run_e2e(step, host, dev, args.steps)
     barrier()
 
-    # ---- dominant kernel alone: the fused joint forward (tcgen05) through the C ABI, CUDA events
-    roof = None
-    if args.precision == "bf16":
-        import ctypes
-        lib = _lib.load()
-        with torch.no_grad():
-            enc_proj = wl.w_enc(resident[0]).contiguous()
-            dec_proj = wl.w_dec(resident[1]).contiguous()
-        B, T, J = enc_proj.shape
-        U1, V = dec_proj.size(1), w["V"]
-        ws = torch.empty(_lib.workspace_bytes(0, 1, B, T, U1, J, V), dtype=torch.uint8, device=dev)
-        lp2 = torch.empty(B, T, U1, 2, device=dev)
-        lse = torch.empty(B, T, U1, device=dev)
-        from emoasr_b200.functional import _joint_cache_bytes
-        cache_bytes = _joint_cache_bytes(1, B, T, U1, J, V, dev)       # same policy as the autograd path
-        zc = cache_bytes > _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HCACHE, 1, B, T, U1, J, V)
-        hc = torch.empty(cache_bytes, dtype=torch.uint8, device=dev)
-        wo, bo = wl.output.weight.detach().contiguous(), wl.output.bias.detach().contiguous()
-        p = lambda t: ctypes.c_void_p(t.data_ptr())
-        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-
-        def call():
-            rc = lib.emo_rnnt_joint_fwd(p(enc_proj), p(dec_proj), p(wo), p(bo), p(resident[2]), p(resident[3]),
-                                        p(resident[4]), B, T, U1, J, V, 0, 1, p(lp2), p(lse), p(hc), hc.numel(),
-                                        p(ws), ws.numel(), st)
-            _lib.check(rc, "emo_rnnt_joint_fwd")
-        # backward through the C ABI: lattice posteriors from the forward outputs, then emo_rnnt_joint_bwd
-        alpha = torch.empty(B, T, U1, device=dev); beta = torch.empty(B, T, U1, device=dev)
-        cost = torch.empty(B, device=dev); gamma2 = torch.empty(B, T, U1, 2, device=dev)
-        call()
-        _lib.check(lib.emo_rnnt_lattice_fwd_bwd(p(lp2), p(resident[3]), p(resident[4]), B, T, U1, p(alpha), p(beta),
-                                                p(cost), p(gamma2), st), "emo_rnnt_lattice_fwd_bwd")
-        gcost = torch.full((B,), 1.0 / B, device=dev)
-        wsb = torch.empty(_lib.workspace_bytes(1, 1, B, T, U1, J, V), dtype=torch.uint8, device=dev)
-        d_enc, d_dec = torch.empty_like(enc_proj), torch.empty_like(dec_proj)
-        d_w, d_b = torch.empty_like(wo), torch.empty_like(bo)
-
-        def call_bwd():
-            rc = lib.emo_rnnt_joint_bwd(p(enc_proj), p(dec_proj), p(wo), p(bo), p(resident[2]), p(resident[3]),
-                                        p(resident[4]), p(lse), p(gamma2), p(gcost), p(hc), hc.numel(), B, T, U1, J, V,
-                                        0, 1, p(d_enc), p(d_dec), p(d_w), p(d_b), p(wsb), wsb.numel(), st)
-            _lib.check(rc, "emo_rnnt_joint_bwd")
-
-        def time_call(fn):
-            for _ in range(3):
-                fn()
-            torch.cuda.synchronize()
-            kev = []
-            for _ in range(max(args.steps, 5)):
-                flush.fill_(1)
-                a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-                a.record(); fn(); b.record()
-                kev.append((a, b))
-            torch.cuda.synchronize()
-            return statistics.mean(a.elapsed_time(b) for a, b in kev)
-
-        f_ms, b_ms = time_call(call), time_call(call_bwd)
-        peaks = load_peaks()
-        unit = wl.joint_gemm_flops()
-
-        def roofline(kernel, flops, ms, extra):
-            ach = flops / (ms * 1e-3) / 1e12
-            r = {"bound": "tensor", "kernel": kernel, "achieved": round(ach, 1), "peak": peaks["tf_burst"],
-                 "unit": "TFLOP/s", "frac": round(ach / peaks["tf_burst"], 4), "traffic": None,
-                 "kernel_ms": round(ms, 4), "peak_source": peaks["src"] + ", burst",
-                 "algorithmic_flops_per_launch": flops}
-            r.update(extra)
-            return r
-        # dominant by time: the backward call (ncu launch list under profiles/ gives the per-kernel shares)
-        if zc:
-            roof = roofline("emo_rnnt_joint_bwd = joint_dhz_kernel + joint_dwz_kernel (+ weight cast, axis reductions)",
-                            2 * unit, b_ms, {"executed_flops_per_launch": 2 * unit,
-                                             "note": "algorithmic = executed = dh and dW GEMMs (2 x 2*N*J*V); the "
-                                                     "logits come from the fp16 z cache the forward wrote"})
-        else:
-            roof = roofline("emo_rnnt_joint_bwd = joint_dh_kernel + joint_dwt_kernel (+ weight cast, axis reductions)",
-                            2 * unit, b_ms, {"executed_flops_per_launch": 6 * unit,
-                                             "note": "algorithmic = dh and dW GEMMs (2 x 2*N*J*V); z is recomputed "
-                                                     "per J-part in both kernels (6 GEMM units executed)"})
-        roof["z_cache"] = bool(zc)
-        roof["forward"] = roofline("joint_fwd_kernel (+ weight / stream casts)", unit, f_ms, {})
-        # DRAM bytes per launch from the ncu --set full capture of this workload (profiles/, cfg 3 only)
-        if args.workload == "rnnt_cfg3" and args.lengths == "full":
-            key = "rnnt_cfg3_zc" if zc else "rnnt_cfg3"
-            roof["traffic"] = NCU_DRAM_BYTES[key]["bwd"]
-            roof["forward"]["traffic"] = NCU_DRAM_BYTES[key]["fwd"]
-
     prec = 1 if args.precision == "bf16" else 0
-    per_step = (_lib.launch_count(_lib.OP_RNNT_JOINT_FWD, prec, w["B"], w["T"], w["U"] + 1, w["J"], w["V"]) +
-                _lib.launch_count(_lib.OP_RNNT_JOINT_BWD, prec, w["B"], w["T"], w["U"] + 1, w["J"], w["V"]))
-    launches = per_step * args.steps
-    bytes_in = sum(t.numel() * t.element_size() for t in host)
-    return dict(ms_total=ms_total, e2e_s=e2e_s, units=w["B"], clocks=clocks, roofline=roof, launches=launches,
-                h2d=bytes_in, d2h=4, flops=wl.algorithmic_flops(), n_valid=wl.n_valid)
+    B, T, U1, J, V = w["B"], w["T"], w["U"] + 1, w["J"], w["V"]
+    bwd_op = _lib.OP_RNNT_JOINT_HZCACHE if (args.route == "zcache" and prec == 1) else _lib.OP_RNNT_JOINT_BWD
+    per_step = _lib.launch_count(_lib.OP_RNNT_JOINT_FWD, prec, B, T, U1, J, V) + _lib.launch_count(bwd_op, prec, B, T, U1, J, V)
+    out = dict(ms_total=ms_total, e2e_s=e2e_s, units=w["B"], clocks=clocks, roofline=None, launches=per_step * args.steps,
+               h2d=sum(t.numel() * t.element_size() for t in host), d2h=4, flops=wl.algorithmic_flops(),
+               n_valid=wl.n_valid, extra={})
+    if args.precision == "bf16" and rank == 0:
+        out["roofline"] = rnnt_kernel_roofline(args, w, wl, resident, flush, dev)
+    if rank == 0 and world == 1 and not args.no_extras and args.precision == "bf16":
+        # the other route of the same workload, a few steps
+        other = "zcache" if args.route == "ring" else "ring"
+        try:
+            ostep = rnnt_step_fn(E, wl, other, args.precision, params, None, None, 1)
+            for _ in range(3):
+                ostep(*resident)
+            torch.cuda.synchronize()
+            n = max(5, args.steps // 2)
+            oms = timed_steps(ostep, resident, n, flush, torch.cuda.synchronize) / n
+            out["extra"]["route_" + other] = {
+                "ms_per_step": round(oms, 4), "value": round(w["B"] / (oms * 1e-3), 2), "unit": "utt/s",
+                "note": ("opt-in variant: the forward stores the valid cells' logits as fp16 (1.66 GB at cfg 3) and the "
+                         "backward streams them; NOT the north-star design (it materialises N x V in HBM)")
+                if other == "zcache" else "default route"}
+        except RuntimeError as e:   # e.g. out of memory for the cache at cfg 4 on a busy device
+            out["extra"]["route_" + other] = {"unavailable": str(e)[:200]}
+        torch.cuda.empty_cache()
+    return out
+
+
+def rnnt_kernel_roofline(args, w, wl, resident, flush, dev):
+    """The dominant kernels alone, through the C ABI, timed with CUDA events: emo_rnnt_joint_bwd (ring route: one
+    persistent kernel executing 3 GEMM units for 2 algorithmic ones + casts, ring prep, axis reductions) and
+    emo_rnnt_joint_fwd."""
+    import ctypes
+    from emoasr_b200 import _lib
+    lib = _lib.load()
+    with torch.no_grad():
+        enc_proj = wl.w_enc(resident[0]).contiguous()
+        dec_proj = wl.w_dec(resident[1]).contiguous()
+    B, T, J = enc_proj.shape
+    U1, V = dec_proj.size(1), w["V"]
+    ws = torch.empty(_lib.workspace_bytes(_lib.OP_RNNT_JOINT_FWD, 1, B, T, U1, J, V), dtype=torch.uint8, device=dev)
+    lp2 = torch.empty(B, T, U1, 2, device=dev)
+    lse = torch.empty(B, T, U1, device=dev)
+    zc = args.route == "zcache"
+    cache = torch.empty(_lib.workspace_bytes(_lib.OP_RNNT_JOINT_HZCACHE, 1, B, T, U1, J, V), dtype=torch.uint8,
+                        device=dev) if zc else None
+    wo, bo = wl.output.weight.detach().contiguous(), wl.output.bias.detach().contiguous()
+    p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    nc = cache.numel() if zc else 0
+
+    def call():
+        rc = lib.emo_rnnt_joint_fwd(p(enc_proj), p(dec_proj), p(wo), p(bo), p(resident[2]), p(resident[3]),
+                                    p(resident[4]), B, T, U1, J, V, 0, 1, p(lp2), p(lse), p(cache), nc,
+                                    p(ws), ws.numel(), st)
+        _lib.check(rc, "emo_rnnt_joint_fwd")
+    alpha = torch.empty(B, T, U1, device=dev); beta = torch.empty(B, T, U1, device=dev)
+    cost = torch.empty(B, device=dev); gamma2 = torch.empty(B, T, U1, 2, device=dev)
+    call()
+    _lib.check(lib.emo_rnnt_lattice_fwd_bwd(p(lp2), p(resident[3]), p(resident[4]), B, T, U1, p(alpha), p(beta),
+                                            p(cost), p(gamma2), st), "emo_rnnt_lattice_fwd_bwd")
+    gcost = torch.full((B,), 1.0 / B, device=dev)
+    wsb = torch.empty(_lib.workspace_bytes(_lib.OP_RNNT_JOINT_BWD, 1, B, T, U1, J, V), dtype=torch.uint8, device=dev)
+    d_enc, d_dec = torch.empty_like(enc_proj), torch.empty_like(dec_proj)
+    d_w, d_b = torch.empty_like(wo), torch.empty_like(bo)
+
+    def call_bwd():
+        rc = lib.emo_rnnt_joint_bwd(p(enc_proj), p(dec_proj), p(wo), p(bo), p(resident[2]), p(resident[3]),
+                                    p(resident[4]), p(lse), p(lp2), p(gamma2), p(gcost), p(cache), nc, B, T, U1, J, V,
+                                    0, 1, p(d_enc), p(d_dec), p(d_w), p(d_b), p(wsb), wsb.numel(), st)
+        _lib.check(rc, "emo_rnnt_joint_bwd")
+
+    iters = max(args.steps, 5)
+    f_ms, b_ms = time_call(call, flush, iters), time_call(call_bwd, flush, iters)
+    peaks = load_peaks()
+    unit = wl.joint_gemm_flops()
+
+    def roofline(kernel, flops, ms, extra):
+        ach = flops / (ms * 1e-3) / 1e12
+        r = {"bound": "tensor", "kernel": kernel, "achieved": round(ach, 1), "peak": peaks["tf_burst"],
+             "unit": "TFLOP/s", "frac": round(ach / peaks["tf_burst"], 4), "traffic": None,
+             "kernel_ms": round(ms, 4), "peak_source": peaks["src"] + ", burst",
+             "algorithmic_flops_per_launch": flops}
+        r.update(extra)
+        return r
+    if zc:
+        roof = roofline("emo_rnnt_joint_bwd = joint_dhz_kernel + joint_dwz_kernel (+ weight cast, axis reductions)",
+                        2 * unit, b_ms, {"executed_flops_per_launch": 2 * unit,
+                                         "note": "z-cache variant: algorithmic = executed = dh and dW GEMMs; the logits "
+                                                 "come from the fp16 cache the forward wrote to HBM"})
+    else:
+        roof = roofline("emo_rnnt_joint_bwd = joint_bwd_ring_kernel (+ casts, ring prep, axis reductions)",
+                        2 * unit, b_ms,
+                        {"executed_flops_per_launch": 3 * unit,
+                         "executed_frac": round(3 * unit / (b_ms * 1e-3) / 1e12 / peaks["tf_burst"], 4),
+                         "note": "algorithmic = dh and dW GEMMs (2 x 2*N*J*V); the kernel also recomputes the logits "
+                                 "(3 GEMM units executed) and hands dz to the two gradient GEMMs through an "
+                                 "L2-resident ring: nothing of size N x V reaches HBM"})
+    roof["route"] = args.route
+    roof["forward"] = roofline("emo_rnnt_joint_fwd = joint_fwd_kernel (+ weight / stream casts)", unit, f_ms, {})
+    tr, src = load_traffic(args.workload, args.route)
+    if tr is not None and args.lengths == "full":
+        roof["traffic"] = tr.get("bwd")
+        roof["forward"]["traffic"] = tr.get("fwd")
+        roof["traffic_step"] = tr.get("step")
+        roof["traffic_source"] = src
+    return roof
+
+
+# ------------------------------------------------------------------------------------------------
+def ctc_step_fn(E, wl, B):
+    def step(eouts, ys, tlen, ulen):
+        wl.output.weight.grad = None
+        wl.output.bias.grad = None
+        eouts = eouts.detach().requires_grad_()
+        logits = wl.output(eouts)                                  # ctc.py:103
+        loss = E.ctc_loss(logits, ys, tlen, ulen, blank=0, reduction="sum") / B   # ctc.py:109-113
+        loss.backward()
+        return loss
+    return step
 
 
 def run_ours_ctc(args, w, rank, world, dev):
     import emoasr_b200 as E
     from emoasr_b200 import _lib
 
-    gen = torch.Generator().manual_seed(rank)
-    B, T, U, V = w["B"], w["T"], w["U"], w["V"]
-    logits_h = torch.randn(B, T, V, generator=gen).pin_memory()
-    tlen, _ = make_lengths(B, T, U, args.lengths, gen)
-    ulen = torch.randint(U // 2, U + 1, (B,), generator=gen)
-    ys = make_labels(B, U, V, gen)
-    host = [logits_h, ys.pin_memory(), tlen.pin_memory(), ulen.pin_memory()]
+    # the head's Linear(He,V) and its two backward GEMMs via cuBLAS in TF32 (as the RNN-T leg's projections); in
+    # true fp32 (SIMT) they alone take ~4 ms at cfg 2, ten times the loss kernels
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    wl = CTCWorkload(w, seed=rank, regime=args.lengths)
+    wl.output.to(dev)
+    B, T, V, He = w["B"], w["T"], w["V"], w["He"]
+    host = [t.pin_memory() for t in (wl.eouts, wl.ys, wl.tlen, wl.ulen)]
     resident = [t.to(dev) for t in host]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-
-    def step(logits, ys, tlen, ulen):
-        logits = logits.detach().requires_grad_()
-        loss = E.ctc_loss(logits, ys, tlen, ulen, blank=0, reduction="sum") / B
-        loss.backward()
-        return loss, logits.grad
-
+    step = ctc_step_fn(E, wl, B)
     for _ in range(args.warmup):
         step(*resident)
     torch.cuda.synchronize()
     mon = ClockMonitor(dev.index if dev.index is not None else 0, enabled=rank == 0)
     mon.start()
-    evs = []
-    for _ in range(args.steps):
-        flush.fill_(1)
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(); step(*resident); b.record()
-        evs.append((a, b))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+    ms_total = timed_steps(step, resident, args.steps, flush, barrier)
     clocks = mon.stop()
-    ms_total = sum(a.elapsed_time(b) for a, b in evs)
-    e2e_s = run_e2e(step, host, dev, args.steps, first=lambda out: out[0])
+    run_e2e(step, host, dev, 2)
+    e2e_s = run_e2e(step, host, dev, args.steps)
     peaks = load_peaks()
+    # algorithmic bytes of the step: the loss kernels read the logits twice and write their gradient once
+    # (SURVEY 8d: 3*B*T*V*4); the head's Linear adds one write of the logits and one read of the gradient
     alg_bytes = 3.0 * B * T * V * 4
     ach = alg_bytes / (ms_total / args.steps * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "ctc fwd+bwd (row_lse + lattice + grad kernels, whole step)",
+    roof = {"bound": "hbm", "kernel": "CTC head step: output Linear fwd/bwd (cuBLAS TF32) + row_lse + lattices + grad kernels",
             "achieved": round(ach, 1), "peak": peaks["hbm"], "unit": "GB/s", "frac": round(ach / peaks["hbm"], 4),
-            "traffic": None, "peak_source": peaks["src"], "algorithmic_bytes_per_step": alg_bytes}
+            "traffic": None, "peak_source": peaks["src"], "algorithmic_bytes_per_step": alg_bytes,
+            "note": "algorithmic bytes = 3*B*T*V*4 (the loss kernels' logits traffic); the step timed here also "
+                    "contains the Linear(He,V) forward and both of its backward GEMMs (cuBLAS, TF32)"}
+    tr, src = load_traffic(args.workload, "default")
+    if tr is not None:
+        roof["traffic"], roof["traffic_source"] = tr.get("step"), src
+    torch.backends.cuda.matmul.allow_tf32 = tf32
     return dict(ms_total=ms_total, e2e_s=e2e_s, units=B, clocks=clocks, roofline=roof,
                 launches=_lib.launch_count(_lib.OP_CTC, 0, B, T, 1, 1, V) * args.steps,
-                h2d=sum(t.numel() * t.element_size() for t in host), d2h=4, flops=None, n_valid=None)
+                h2d=sum(t.numel() * t.element_size() for t in host), d2h=4, flops=None, n_valid=None, extra={})
+
+
+# ------------------------------------------------------------------------------------------------
+def gpu_baselines(dev, steps=3):
+    """Same-box GPU comparators (rank 0, N=1): what the REFERENCE's op sequence costs on this B200.
+      rnnt_cfg3  joint -> log_softmax -> transducer loss with all three (B,T,U+1,V) fp32 tensors materialised
+                 (rnn_transducer.py:101-115); warp_rnnt is absent from the image, torchaudio's CUDA rnnt_loss
+                 (fused_log_softmax=False) has the same contract.
+      ctc_cfg2   output Linear -> transpose -> log_softmax -> torch's CUDA ctc_loss (ctc.py:103-113)."""
+    out = {}
+    tf32 = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = False     # the reference runs cuBLAS in fp32
+    # ---- CTC cfg 2
+    try:
+        w = WORKLOADS["ctc_cfg2"]
+        wl = CTCWorkload(w, 0, "full")
+        wl.output.to(dev)
+        e, ys, tl, ul = (t.to(dev) for t in (wl.eouts, wl.ys, wl.tlen, wl.ulen))
+        fn = torch.nn.CTCLoss(blank=0, reduction="sum", zero_infinity=True)
+
+        def ctc_step():
+            wl.output.zero_grad(set_to_none=True)
+            x = e.detach().requires_grad_()
+            logits = wl.output(x)
+            loss = fn(logits.transpose(1, 0).log_softmax(dim=2), ys, tl, ul) / logits.size(0)
+            loss.backward()
+        for _ in range(2):
+            ctc_step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            ctc_step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        out["ctc_cfg2"] = {"value": round(w["B"] / (ms * 1e-3), 1), "unit": "utt/s", "ms_per_step": round(ms, 3),
+                           "what": "torch CUDA: Linear -> log_softmax -> nn.CTCLoss -> backward (the reference's ops)"}
+    except Exception as ex:   # noqa: BLE001
+        out["ctc_cfg2"] = {"unavailable": repr(ex)[:200]}
+    torch.cuda.empty_cache()
+    # ---- RNN-T cfg 3, materialised
+    try:
+        import torchaudio
+        w = WORKLOADS["rnnt_cfg3"]
+        wl = RNNTWorkload(w, 0, "full")
+        mods = torch.nn.ModuleList([wl.w_enc, wl.w_dec, wl.output]).to(dev)
+        e, d, ys, tl, ul = (t.to(dev) for t in (wl.eouts, wl.douts, wl.ys.int(), wl.tlen.int(), wl.ulen.int()))
+
+        def rnnt_step():
+            mods.zero_grad(set_to_none=True)
+            x, y = e.detach().requires_grad_(), d.detach().requires_grad_()
+            logits = wl.output(torch.tanh(wl.w_enc(x).unsqueeze(2) + wl.w_dec(y).unsqueeze(1)))
+            lp = torch.log_softmax(logits, dim=-1)
+            loss = torchaudio.functional.rnnt_loss(lp, ys, tl, ul, blank=0, reduction="mean", fused_log_softmax=False)
+            loss.backward()
+        rnnt_step()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        for _ in range(steps):
+            rnnt_step()
+        b.record()
+        torch.cuda.synchronize()
+        ms = a.elapsed_time(b) / steps
+        out["rnnt_cfg3"] = {"value": round(w["B"] / (ms * 1e-3), 1), "unit": "utt/s", "ms_per_step": round(ms, 2),
+                            "peak_mem_gb": round(torch.cuda.max_memory_allocated(dev) / 1e9, 1),
+                            "what": "torch CUDA: joint (cuBLAS fp32) -> log_softmax -> torchaudio rnnt_loss "
+                                    "(fused_log_softmax=False, warp_rnnt's contract) -> backward, B=32, all "
+                                    "(B,T,U+1,V) tensors materialised"}
+    except Exception as ex:   # noqa: BLE001
+        out["rnnt_cfg3"] = {"unavailable": repr(ex)[:200]}
+    torch.cuda.empty_cache()
+    torch.backends.cuda.matmul.allow_tf32 = tf32
+    return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -481,13 +651,16 @@ def cpu_reference_rate(w, sample_units, steps, warmup, threads=None):
             loss.backward()
             return float(loss)
     else:
-        logits = torch.randn(Bc, w["T"], w["V"], generator=gen, requires_grad=True)
+        eouts = torch.randn(Bc, w["T"], w["He"], generator=gen, requires_grad=True)
         ys = make_labels(Bc, w["U"], w["V"], gen)
         tl = torch.full((Bc,), w["T"]); ul = torch.randint(w["U"] // 2, w["U"] + 1, (Bc,), generator=gen)
+        torch.manual_seed(1234)
+        head = torch.nn.Linear(w["He"], w["V"])
 
         def step():
-            logits.grad = None
-            loss = torch_path.ctc_loss_from_logits(logits, ys, tl, ul, blank=0)
+            eouts.grad = None
+            head.zero_grad(set_to_none=True)
+            loss = torch_path.ctc_head_loss(eouts, head.weight, head.bias, ys, tl, ul, blank=0)
             loss.backward()
             return float(loss)
     for _ in range(warmup):
@@ -521,8 +694,16 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="rnnt_cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--route", default="ring", choices=["ring", "zcache"])
     ap.add_argument("--lengths", default="full", choices=["full", "ragged"])
+    ap.add_argument("--grad-payload-mb", type=float, default=0.0,
+                    help="N>1: MB of stand-in gradients (the rest of the model: 99.4 for the 25.8 M-parameter cfg-3 "
+                         "model, 103 MB in total) all-reduced per step besides the path's own 3.7 MB.  They are "
+                         "launched after the path's backward and nothing of the hot path is left to hide them "
+                         "behind (in a training step they overlap the encoder backward), so this is the exposed "
+                         "cost of the collective; default 0 = the path's own parameters only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]
@@ -532,11 +713,19 @@ def main():
     metric = "RNN-T/CTC loss fwd+bwd utterances/s"
     config = {"workload": w["desc"], "name": args.workload, "lengths": args.lengths,
               "per_gpu_batch": w["B"], "global_batch": w["B"] * world,
-              "parallelism": f"batch-sharded x{world}, NCCL all-reduce of the path's parameter grads" if world > 1 else "single GPU",
+              "parallelism": (f"batch-sharded x{world}; NCCL all-reduce (AVG) of the path's parameter grads"
+                              + (f" + {args.grad_payload_mb:.1f} MB stand-in for the rest of the 25.8 M-parameter model's grads"
+                                 if args.grad_payload_mb > 0 and w["kind"] == "rnnt" else "")
+                              + ", launched from autograd hooks (overlaps the backward), stream-ordered wait")
+              if world > 1 else "single GPU",
               "l2": "L2 flushed (256 MiB write, untimed) between timed steps",
-              "projections": "w_enc/w_dec Linear via cuBLAS, " + ("TF32" if args.precision == "bf16" else "fp32"),
               "e2e": "per step: H2D of the step's inputs from pinned host memory on a copy stream (prefetched "
-                     "during the previous step) + D2H read of the loss, wall clock"}
+                     "during the previous step) + D2H of the loss, read by the host one step late; wall clock"}
+    if w["kind"] == "rnnt":
+        config["route"] = args.route
+        config["projections"] = "w_enc/w_dec Linear via cuBLAS, " + ("TF32" if args.precision == "bf16" else "fp32")
+    else:
+        config["head"] = "output Linear(He,V) forward + backward included in the step (cuBLAS TF32)"
 
     if args.impl == "reference":
         if rank != 0:
@@ -546,8 +735,9 @@ def main():
         threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else cores
         torch.set_num_threads(threads)
         config = dict(config, parallelism=f"host CPU, {threads} threads (rank 0 only)")
-        sample = 2 if w["kind"] == "rnnt" else w["B"]
-        steps = max(1, min(args.steps, 2 if w["kind"] == "rnnt" else 5))
+        config.pop("route", None)
+        sample = 4 if w["kind"] == "rnnt" else w["B"]
+        steps = max(1, min(args.steps, 3 if w["kind"] == "rnnt" else 5))
         warm = 1 if args.warmup > 0 else 0
         rate, sec = cpu_reference_rate(w, sample, steps, warm)
         out = {"impl": "reference", "metric": metric, "value": round(rate, 4), "unit": "utt/s", "n_gpus": args.gpus,
@@ -557,7 +747,7 @@ def main():
                                 "host_cpus": cores,
                                 "sample": f"{sample} utterances/step of the same T,U,V,J shape, {steps} timed steps; "
                                           "reference op sequence (oracle/torch_path.py: joint->log_softmax->"
-                                          "torchaudio rnnt_loss CPU / torch ctc_loss CPU)"},
+                                          "torchaudio rnnt_loss CPU / Linear->log_softmax->torch ctc_loss CPU)"},
                "e2e": {"value": round(rate, 4), "unit": "utt/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         emit(out)
         return
@@ -585,17 +775,38 @@ def main():
                "gpu_launches": r["launches"], "roofline": r["roofline"]}
         if r["flops"]:
             peaks = load_peaks()
-            step_tf = r["flops"] / (ms_total / args.steps * 1e-3) / 1e12 * 1.0
+            step_tf = r["flops"] / (ms_total / args.steps * 1e-3) / 1e12
             out["step_algorithmic_tflops"] = round(step_tf, 1)
+            out["step_frac_of_burst_peak"] = round(step_tf / peaks["tf_burst"], 4)
             out["step_frac_of_sustained_peak"] = round(step_tf / (peaks["tf_sust"] or peaks["tf_burst"]), 4)
+        extra = dict(r.get("extra") or {})
+        if world == 1 and not args.no_extras:
+            if args.workload == "rnnt_cfg3":
+                # CTC cfg 2 through the same harness (its own roofline), so that it has a driver-run number too
+                cargs = argparse.Namespace(**vars(args))
+                cargs.workload, cargs.steps, cargs.warmup = "ctc_cfg2", max(5, args.steps // 2), 3
+                c = run_ours_ctc(cargs, WORKLOADS["ctc_cfg2"], 0, 1, dev)
+                cu = c["units"] * cargs.steps
+                extra["ctc_cfg2"] = {"workload": WORKLOADS["ctc_cfg2"]["desc"],
+                                     "value": round(cu / (c["ms_total"] * 1e-3), 1), "unit": "utt/s",
+                                     "ms_per_step": round(c["ms_total"] / cargs.steps, 4),
+                                     "e2e": {"value": round(cu / c["e2e_s"], 1), "unit": "utt/s",
+                                             "h2d_bytes_per_step": c["h2d"], "d2h_bytes_per_step": c["d2h"]},
+                                     "roofline": c["roofline"], "dtype": "f32"}
+                torch.cuda.empty_cache()
+            out["gpu_baseline"] = gpu_baselines(dev)
+        if extra:
+            out["extra"] = extra
         if not args.no_cpu_baseline and world == 1:
-            sample = 2 if w["kind"] == "rnnt" else min(w["B"], 16)
+            # bounded sample of the same workload on the host cores: ~10-30 s of CPU work
+            sample, csteps = (4, 2) if w["kind"] == "rnnt" else (min(w["B"], 16), 3)
             nthreads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-            rate, sec = cpu_reference_rate(w, sample, 1, 1, threads=nthreads)
+            rate, sec = cpu_reference_rate(w, sample, csteps, 1, threads=nthreads)
             out["cpu_baseline"] = {"value": round(rate, 4), "unit": "utt/s", "cores": torch.get_num_threads(),
                                    "kind": "port", "host_cpus": os.cpu_count(),
-                                   "sample": f"{sample} utterances of the same shape, 1 warm-up + 1 timed step "
-                                             f"({sec:.1f} s/step)"}
+                                   "sample": f"{sample} utterances of the same shape per step, 1 warm-up + {csteps} "
+                                             f"timed steps ({sec:.1f} s/step); reference op sequence "
+                                             "(oracle/torch_path.py)"}
         emit(out)
     if world > 1:
         dist.barrier()

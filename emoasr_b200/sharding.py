@@ -108,6 +108,37 @@ class GradBuckets:
         self.start()
         self.finish()
 
+    # ---- overlap with the backward pass (what DistributedDataParallel does, for the process-per-GPU mode) ----
+    def attach_hooks(self):
+        """own_grads mode: every bucket's all-reduce is launched from an autograd hook as soon as the LAST of its
+        parameters has received its gradient, i.e. while the rest of the backward pass is still being enqueued /
+        executed.  NCCL runs it on its own stream behind an event of the compute stream, so the collective
+        overlaps the remaining backward kernels; ``finish()`` then only makes the compute stream wait for it
+        (``Work.wait()`` is a stream dependency with NCCL, not a host block).  Order the parameters so that a
+        bucket holds gradients that become ready together (here: output.* first, they are final when the fused
+        backward kernel retires)."""
+        assert self.flats is not None, "attach_hooks() needs own_grads=True"
+        self._ready = [0] * len(self.buckets)
+        self._hooked = True
+        avg = self._avg_op()
+        for bi, bucket in enumerate(self.buckets):
+            for p in bucket:
+                def hook(_p, bi=bi, n=len(bucket)):
+                    self._ready[bi] += 1
+                    if self._ready[bi] == n:
+                        self._ready[bi] = 0
+                        work = dist.all_reduce(self.flats[bi], op=avg if avg is not None else dist.ReduceOp.SUM,
+                                               group=self.group, async_op=True)
+                        self._pending.append((None, None, self.flats[bi], work, avg is not None))
+                p.register_post_accumulate_grad_hook(hook)
+
+    def start_extra(self, flat):
+        """All-reduce (average) of a flat buffer that is not tied to parameters of this process' graph (e.g. the
+        gradients of the rest of the model); joins the same pending list."""
+        avg = self._avg_op()
+        work = dist.all_reduce(flat, op=avg if avg is not None else dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self._pending.append((None, None, flat, work, avg is not None))
+
 
 def mean_over_replicas(value, group=None):
     """Logging-only scalar: mean of the per-replica values (train_asr.py:67-71)."""

@@ -57,7 +57,7 @@ def _loss(lin, eouts, douts, ys, tl, ul):
                                       lin[2].weight, lin[2].bias, ys, tl, ul, blank=0)
 
 
-def _worker(rank, world, port, out, own_grads=False):
+def _worker(rank, world, port, out, own_grads=False, hooks=False):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     torch.set_num_threads(1)
@@ -69,13 +69,22 @@ def _worker(rank, world, port, out, own_grads=False):
         for p in lin.parameters():
             p.grad.fill_(123.0)     # stale values from a previous step ...
         buckets.zero()              # ... are cleared in place
+        if hooks:                   # all-reduces launched from autograd hooks while backward() is still running
+            buckets.attach_hooks()
+    extra = torch.full((5,), float(rank + 1)) if hooks else None
     loss = _loss(lin, batch["eouts"], batch["douts"], batch["ys"], batch["tl"], batch["ul"])
     loss.backward()
     if buckets is None:
         buckets = sharding.GradBuckets(lin.parameters(), bucket_bytes=256)   # tiny buckets: several all-reduces
     assert len(buckets.buckets) > 1
-    buckets.start()
+    if hooks:
+        assert len(buckets._pending) == len(buckets.buckets)   # every bucket was launched during backward()
+        buckets.start_extra(extra)
+    else:
+        buckets.start()
     buckets.finish()
+    if hooks:
+        assert torch.allclose(extra, torch.full((5,), 1.5))    # mean of 1 and 2
     mean_loss = sharding.mean_over_replicas(loss)
     if rank == 0:
         torch.save({"loss": mean_loss, "grads": [p.grad.clone() for p in lin.parameters()]}, out)
@@ -83,10 +92,11 @@ def _worker(rank, world, port, out, own_grads=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("own_grads", [False, True], ids=["copy_buckets", "grads_in_buckets"])
-def test_two_rank_sharded_step_matches_single_process(tmp_path, own_grads):
+@pytest.mark.parametrize("own_grads,hooks", [(False, False), (True, False), (True, True)],
+                         ids=["copy_buckets", "grads_in_buckets", "overlap_hooks"])
+def test_two_rank_sharded_step_matches_single_process(tmp_path, own_grads, hooks):
     out = str(tmp_path / "rank0.pt")
-    mp.spawn(_worker, args=(2, _free_port(), out, own_grads), nprocs=2, join=True)
+    mp.spawn(_worker, args=(2, _free_port(), out, own_grads, hooks), nprocs=2, join=True)
     got = torch.load(out)
     eouts, douts, ys, tl, ul, lin = _make_problem()
     loss = _loss(lin, eouts, douts, ys, tl, ul)      # global mean over the 4 utterances
