@@ -3,7 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
                     [--workload rnnt_cfg3|rnnt_cfg4|ctc_cfg2|ctc_cfg1] [--precision bf16|fp32]
-                    [--route ring|zcache] [--lengths full|ragged] [--grad-payload-mb M] [--no-extras]
+                    [--lengths full|ragged] [--grad-payload-mb M] [--no-extras]
 
 A "step" is one pass of the hot path over one batch of synthetic input:
   RNN-T  enc_proj = w_enc(eouts), dec_proj = w_dec(douts)  (plain cuBLAS Linear, as in the
@@ -11,10 +11,10 @@ A "step" is one pass of the hot path over one batch of synthetic input:
          douts and every joint parameter   (asr/modeling/decoders/rnn_transducer.py:101-115,147-156)
   CTC    eouts -> output Linear -> fused log-softmax + CTC loss -> backward to eouts and the Linear's
          parameters                         (asr/modeling/decoders/ctc.py:103-113)
-Default workload (N=1): BASELINE cfg 3, "RNN-T(Cf.) 1kBPE 26M fused joint+loss, B=32 T=250 U=100 V=1024", on the
-default route "ring" (nothing of size N x V is written to HBM, forward or backward).  The default N=1 run also
-reports, under "extra", the opt-in z-cache route of the same workload, CTC cfg 2, and same-box GPU baselines
-(the reference's materialised op sequence on CUDA; torch's CUDA ctc_loss) -- `--no-extras` skips them.
+Default workload (N=1): BASELINE cfg 3, "RNN-T(Cf.) 1kBPE 26M fused joint+loss, B=32 T=250 U=100 V=1024"; nothing
+of size N x V is written to HBM, forward or backward.  The default N=1 run also reports, under "extra", CTC cfg 2,
+and under "gpu_baseline" same-box GPU comparators (the reference's materialised op sequence on CUDA; torch's CUDA
+ctc_loss) -- `--no-extras` skips them.
 For N>1 every rank processes its own batch of the same shape (weak scaling, batch-sharded) and the gradients of
 the path's parameters (plus, with --grad-payload-mb, a stand-in for the rest of the model's gradients) are
 all-reduced over NCCL inside the timed step, launched from autograd hooks so that they overlap the backward.
@@ -59,7 +59,7 @@ def load_peaks():
     return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback (B200_PROFILING.md)")
 
 
-def load_traffic(workload, route):
+def load_traffic(workload, route="ring"):
     """dram__bytes_read.sum + dram__bytes_write.sum per call, from the committed ncu --set full capture of this
     workload (profiles/dram_traffic.json names the capture it came from).  None if there is no capture."""
     try:
@@ -201,8 +201,8 @@ def time_call(fn, flush, iters):
 
 
 # ------------------------------------------------------------------------------------------------
-def rnnt_step_fn(E, wl, route, precision, params, buckets, payload, world):
-    crit = E.RNNTJointLoss(blank_id=0, precision=precision, route=route)
+def rnnt_step_fn(E, wl, precision, params, buckets, payload, world):
+    crit = E.RNNTJointLoss(blank_id=0, precision=precision)
 
     def step(eouts, douts, ys, tlen, ulen):
         if buckets is not None:
@@ -243,7 +243,7 @@ def run_ours_rnnt(args, w, rank, world, dev):
     host = [t.pin_memory() for t in (wl.eouts, wl.douts, wl.ys.int(), wl.tlen.int(), wl.ulen.int())]
     resident = [t.to(dev) for t in host]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    step = rnnt_step_fn(E, wl, args.route, args.precision, params, buckets, payload, world)
+    step = rnnt_step_fn(E, wl, args.precision, params, buckets, payload, world)
 
     def barrier():
         torch.cuda.synchronize()
@@ -266,31 +266,13 @@ def run_ours_rnnt(args, w, rank, world, dev):
 
     prec = 1 if args.precision == "bf16" else 0
     B, T, U1, J, V = w["B"], w["T"], w["U"] + 1, w["J"], w["V"]
-    bwd_op = _lib.OP_RNNT_JOINT_HZCACHE if (args.route == "zcache" and prec == 1) else _lib.OP_RNNT_JOINT_BWD
-    per_step = _lib.launch_count(_lib.OP_RNNT_JOINT_FWD, prec, B, T, U1, J, V) + _lib.launch_count(bwd_op, prec, B, T, U1, J, V)
+    per_step = (_lib.launch_count(_lib.OP_RNNT_JOINT_FWD, prec, B, T, U1, J, V)
+                + _lib.launch_count(_lib.OP_RNNT_JOINT_BWD, prec, B, T, U1, J, V))
     out = dict(ms_total=ms_total, e2e_s=e2e_s, units=w["B"], clocks=clocks, roofline=None, launches=per_step * args.steps,
                h2d=sum(t.numel() * t.element_size() for t in host), d2h=4, flops=wl.algorithmic_flops(),
                n_valid=wl.n_valid, extra={})
     if args.precision == "bf16" and rank == 0:
         out["roofline"] = rnnt_kernel_roofline(args, w, wl, resident, flush, dev)
-    if rank == 0 and world == 1 and not args.no_extras and args.precision == "bf16":
-        # the other route of the same workload, a few steps
-        other = "zcache" if args.route == "ring" else "ring"
-        try:
-            ostep = rnnt_step_fn(E, wl, other, args.precision, params, None, None, 1)
-            for _ in range(3):
-                ostep(*resident)
-            torch.cuda.synchronize()
-            n = max(5, args.steps // 2)
-            oms = timed_steps(ostep, resident, n, flush, torch.cuda.synchronize) / n
-            out["extra"]["route_" + other] = {
-                "ms_per_step": round(oms, 4), "value": round(w["B"] / (oms * 1e-3), 2), "unit": "utt/s",
-                "note": ("opt-in variant: the forward stores the valid cells' logits as fp16 (1.66 GB at cfg 3) and the "
-                         "backward streams them; NOT the north-star design (it materialises N x V in HBM)")
-                if other == "zcache" else "default route"}
-        except RuntimeError as e:   # e.g. out of memory for the cache at cfg 4 on a busy device
-            out["extra"]["route_" + other] = {"unavailable": str(e)[:200]}
-        torch.cuda.empty_cache()
     return out
 
 
@@ -309,18 +291,13 @@ def rnnt_kernel_roofline(args, w, wl, resident, flush, dev):
     ws = torch.empty(_lib.workspace_bytes(_lib.OP_RNNT_JOINT_FWD, 1, B, T, U1, J, V), dtype=torch.uint8, device=dev)
     lp2 = torch.empty(B, T, U1, 2, device=dev)
     lse = torch.empty(B, T, U1, device=dev)
-    zc = args.route == "zcache"
-    cache = torch.empty(_lib.workspace_bytes(_lib.OP_RNNT_JOINT_HZCACHE, 1, B, T, U1, J, V), dtype=torch.uint8,
-                        device=dev) if zc else None
     wo, bo = wl.output.weight.detach().contiguous(), wl.output.bias.detach().contiguous()
     p = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else ctypes.c_void_p(0)
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
-    nc = cache.numel() if zc else 0
 
     def call():
         rc = lib.emo_rnnt_joint_fwd(p(enc_proj), p(dec_proj), p(wo), p(bo), p(resident[2]), p(resident[3]),
-                                    p(resident[4]), B, T, U1, J, V, 0, 1, p(lp2), p(lse), p(cache), nc,
-                                    p(ws), ws.numel(), st)
+                                    p(resident[4]), B, T, U1, J, V, 0, 1, p(lp2), p(lse), p(ws), ws.numel(), st)
         _lib.check(rc, "emo_rnnt_joint_fwd")
     alpha = torch.empty(B, T, U1, device=dev); beta = torch.empty(B, T, U1, device=dev)
     cost = torch.empty(B, device=dev); gamma2 = torch.empty(B, T, U1, 2, device=dev)
@@ -334,7 +311,7 @@ def rnnt_kernel_roofline(args, w, wl, resident, flush, dev):
 
     def call_bwd():
         rc = lib.emo_rnnt_joint_bwd(p(enc_proj), p(dec_proj), p(wo), p(bo), p(resident[2]), p(resident[3]),
-                                    p(resident[4]), p(lse), p(lp2), p(gamma2), p(gcost), p(cache), nc, B, T, U1, J, V,
+                                    p(resident[4]), p(lse), p(lp2), p(gamma2), p(gcost), B, T, U1, J, V,
                                     0, 1, p(d_enc), p(d_dec), p(d_w), p(d_b), p(wsb), wsb.numel(), st)
         _lib.check(rc, "emo_rnnt_joint_bwd")
 
@@ -351,22 +328,15 @@ def rnnt_kernel_roofline(args, w, wl, resident, flush, dev):
              "algorithmic_flops_per_launch": flops}
         r.update(extra)
         return r
-    if zc:
-        roof = roofline("emo_rnnt_joint_bwd = joint_dhz_kernel + joint_dwz_kernel (+ weight cast, axis reductions)",
-                        2 * unit, b_ms, {"executed_flops_per_launch": 2 * unit,
-                                         "note": "z-cache variant: algorithmic = executed = dh and dW GEMMs; the logits "
-                                                 "come from the fp16 cache the forward wrote to HBM"})
-    else:
-        roof = roofline("emo_rnnt_joint_bwd = joint_bwd_ring_kernel (+ casts, ring prep, axis reductions)",
-                        2 * unit, b_ms,
-                        {"executed_flops_per_launch": 3 * unit,
-                         "executed_frac": round(3 * unit / (b_ms * 1e-3) / 1e12 / peaks["tf_burst"], 4),
-                         "note": "algorithmic = dh and dW GEMMs (2 x 2*N*J*V); the kernel also recomputes the logits "
-                                 "(3 GEMM units executed) and hands dz to the two gradient GEMMs through an "
-                                 "L2-resident ring: nothing of size N x V reaches HBM"})
-    roof["route"] = args.route
+    roof = roofline("emo_rnnt_joint_bwd = joint_bwd_ring_kernel (+ casts, ring prep, axis reductions)",
+                    2 * unit, b_ms,
+                    {"executed_flops_per_launch": 3 * unit,
+                     "executed_frac": round(3 * unit / (b_ms * 1e-3) / 1e12 / peaks["tf_burst"], 4),
+                     "note": "algorithmic = dh and dW GEMMs (2 x 2*N*J*V); the kernel also recomputes the logits "
+                             "(3 GEMM units executed) and hands dz to the two gradient GEMMs through an "
+                             "L2-resident ring: nothing of size N x V reaches HBM"})
     roof["forward"] = roofline("emo_rnnt_joint_fwd = joint_fwd_kernel (+ weight / stream casts)", unit, f_ms, {})
-    tr, src = load_traffic(args.workload, args.route)
+    tr, src = load_traffic(args.workload)
     if tr is not None and args.lengths == "full":
         roof["traffic"] = tr.get("bwd")
         roof["forward"]["traffic"] = tr.get("fwd")
@@ -694,7 +664,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="rnnt_cfg3", choices=sorted(WORKLOADS))
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--route", default="ring", choices=["ring", "zcache"])
     ap.add_argument("--lengths", default="full", choices=["full", "ragged"])
     ap.add_argument("--grad-payload-mb", type=float, default=0.0,
                     help="N>1: MB of stand-in gradients (the rest of the model: 99.4 for the 25.8 M-parameter cfg-3 "
@@ -722,7 +691,7 @@ def main():
               "e2e": "per step: H2D of the step's inputs from pinned host memory on a copy stream (prefetched "
                      "during the previous step) + D2H of the loss, read by the host one step late; wall clock"}
     if w["kind"] == "rnnt":
-        config["route"] = args.route
+        config["route"] = "logit tiles recomputed by the backward; dz through an L2-resident ring; no N x V tensor in HBM"
         config["projections"] = "w_enc/w_dec Linear via cuBLAS, " + ("TF32" if args.precision == "bf16" else "fp32")
     else:
         config["head"] = "output Linear(He,V) forward + backward included in the step (cuBLAS TF32)"

@@ -23,20 +23,18 @@ class RNNTLoss(nn.Module):
 
 class RNNTJointLoss(nn.Module):
     """Joint network + log-softmax + transducer loss in one fused op
-    (rnn_transducer.py:101-115 and :147-156).  With the default route="ring" the (B,T,U+1,V) tensors are
-    never formed (forward or backward); route="zcache" stores the valid cells' logits as fp16 instead."""
+    (rnn_transducer.py:101-115 and :147-156); the (B,T,U+1,V) tensors are never formed, forward or backward."""
 
-    def __init__(self, blank_id=0, precision="bf16", normalize_length=False, normalize_batch=True, route="ring"):
+    def __init__(self, blank_id=0, precision="bf16", normalize_length=False, normalize_batch=True):
         super().__init__()
         self.blank_id = blank_id
         self.precision = precision
-        self.route = route
         self.normalize_length = normalize_length
         self.normalize_batch = normalize_batch
 
     def forward(self, enc_proj, dec_proj, w_out, b_out, ys, elens, ylens):
         costs = F.rnnt_joint_loss(enc_proj, dec_proj, w_out, b_out, ys, elens, ylens,
-                                  blank=self.blank_id, precision=self.precision, route=self.route)
+                                  blank=self.blank_id, precision=self.precision)
         if self.normalize_length:
             costs = costs / elens.to(costs)
         return costs.mean() if self.normalize_batch else costs.sum()

@@ -43,19 +43,15 @@ extern "C" size_t emo_workspace_bytes(int op, int precision, int B, int T, int U
             if (U1 <= 0 || J <= 0 || V <= 0) return 0;
             return precision == EMO_PREC_BF16 ? joint_bf16_workspace(op, B, T, U1, J, V)
                                               : joint_f32_workspace(op, B, T, U1, J, V);
-        case EMO_OP_RNNT_JOINT_HZCACHE:
-            if (U1 <= 0 || J <= 0 || V <= 0) return 0;
-            return precision == EMO_PREC_BF16 ? joint_bf16_workspace(op, B, T, U1, J, V) : 0;
         default:
             return 0;  // CTC takes its scratch as explicit arguments
     }
 }
 
-extern "C" int emo_rnnt_joint_supported(int precision, int route, int B, int T, int U1, int J, int V) {
+extern "C" int emo_rnnt_joint_supported(int precision, int B, int T, int U1, int J, int V) {
     if (B <= 0 || T <= 0 || U1 <= 0 || J <= 0 || V <= 0) return 0;
     if (precision == EMO_PREC_FP32) return 1;
     if (precision != EMO_PREC_BF16) return 0;
-    if (route == 1) return joint_bf16_workspace(EMO_OP_RNNT_JOINT_HZCACHE, B, T, U1, J, V) != 0 && J <= 512;
     return joint_ring_supported(B, T, U1, J, V) ? 1 : 0;
 }
 
@@ -68,8 +64,6 @@ extern "C" int emo_launch_count(int op, int precision, int B, int T, int U1, int
         case EMO_OP_RNNT_JOINT_BWD:
             return precision == EMO_PREC_BF16 ? joint_bf16_launches(op, B, T, U1, J, V)
                                               : joint_f32_launches(op, B, T, U1, J, V);
-        case EMO_OP_RNNT_JOINT_HZCACHE:
-            return precision == EMO_PREC_BF16 ? joint_bf16_launches(op, B, T, U1, J, V) : 0;
         case EMO_OP_CTC:
             return 3;  // row lse + emission gather, alpha || beta lattices, gradient
         default:
@@ -80,15 +74,15 @@ extern "C" int emo_launch_count(int op, int precision, int B, int T, int U1, int
 extern "C" int emo_rnnt_joint_fwd(const float* enc_proj, const float* dec_proj, const float* w_out,
                                   const float* b_out, const int* labels, const int* tlen,
                                   const int* ulen, int B, int T, int U1, int J, int V, int blank,
-                                  int precision, float* lp2, float* lse, void* hcache,
-                                  size_t hcache_bytes, void* ws, size_t ws_bytes, void* stream) {
+                                  int precision, float* lp2, float* lse, void* ws, size_t ws_bytes,
+                                  void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == EMO_PREC_FP32)
         return joint_fwd_f32(enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, B, T, U1, J, V,
                              blank, lp2, lse, ws, ws_bytes, st);
     if (precision == EMO_PREC_BF16)
         return joint_fwd_bf16(enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, B, T, U1, J, V,
-                              blank, lp2, lse, hcache, hcache_bytes, ws, ws_bytes, st);
+                              blank, lp2, lse, ws, ws_bytes, st);
     set_error("joint_fwd: unknown precision %d", precision);
     return EMO_BAD_ARG;
 }
@@ -96,7 +90,7 @@ extern "C" int emo_rnnt_joint_fwd(const float* enc_proj, const float* dec_proj, 
 extern "C" int emo_rnnt_joint_bwd(const float* enc_proj, const float* dec_proj, const float* w_out,
                                   const float* b_out, const int* labels, const int* tlen,
                                   const int* ulen, const float* lse, const float* lp2, const float* gamma2,
-                                  const float* grad_cost, const void* hcache, size_t hcache_bytes,
+                                  const float* grad_cost,
                                   int B, int T, int U1, int J, int V, int blank, int precision, float* d_enc_proj, float* d_dec_proj,
                                   float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes,
                                   void* stream) {
@@ -107,7 +101,7 @@ extern "C" int emo_rnnt_joint_bwd(const float* enc_proj, const float* dec_proj, 
                              d_b_out, ws, ws_bytes, st);
     if (precision == EMO_PREC_BF16)
         return joint_bwd_bf16(enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, lse, lp2, gamma2,
-                              grad_cost, hcache, hcache_bytes, B, T, U1, J, V, blank, d_enc_proj, d_dec_proj, d_w_out,
+                              grad_cost, B, T, U1, J, V, blank, d_enc_proj, d_dec_proj, d_w_out,
                               d_b_out, ws, ws_bytes, st);
     set_error("joint_bwd: unknown precision %d", precision);
     return EMO_BAD_ARG;

@@ -127,12 +127,11 @@ int joint_f32_launches(int op, int B, int T, int U1, int J, int V);
 
 int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
                    const float* b_out, const int* labels, const int* tlen, const int* ulen, int B,
-                   int T, int U1, int J, int V, int blank, float* lp2, float* lse, void* hcache,
-                   size_t hcache_bytes, void* ws, size_t ws_bytes, cudaStream_t st);
+                   int T, int U1, int J, int V, int blank, float* lp2, float* lse, void* ws, size_t ws_bytes,
+                   cudaStream_t st);
 int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
                    const float* b_out, const int* labels, const int* tlen, const int* ulen,
-                   const float* lse, const float* lp2, const float* gamma2, const float* grad_cost,
-                   const void* hcache, size_t hcache_bytes, int B, int T,
+                   const float* lse, const float* lp2, const float* gamma2, const float* grad_cost, int B, int T,
                    int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
                    float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st);
 // ring backward (joint_bwd_ring.cu): the default route
@@ -144,18 +143,10 @@ int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec
                           void* dh_ws, void* ring_ws, float* d_w_out, float* d_b_out, cudaStream_t st);
 int joint_bf16_casts(const float* enc_proj, const float* dec_proj, const float* w_out, int B, int T, int U1, int J,
                      int V, void* ws, const void** w_bf16, const void** enc_h, const void** dec_h, cudaStream_t st);
-// z-cache backward kernels (joint_bwd_zc.cu): optional variant
-bool joint_zc_supported(int J);
+// axis reductions of dh (joint_reduce.cu)
 int joint_reduce_dh_launch(const void* dh_ws, const float* enc_proj, const float* dec_proj, const int* tlen,
                            const int* ulen, int B, int T, int U1, int J, float* d_enc_proj, float* d_dec_proj,
                            cudaStream_t st);
-int joint_dhz_launch(const void* w_bf16, const void* zcache, const int* labels, const int* tlen,
-                     const int* ulen, const float* lse, const float* gamma2, const float* grad_cost, int B, int T,
-                     int U1, int J, int V, int blank, void* dh_ws, const float* enc_proj, const float* dec_proj,
-                     float* d_enc_proj, float* d_dec_proj, cudaStream_t st);
-int joint_dwz_launch(const void* hcache, const void* zcache, const int* labels, const int* tlen, const int* ulen,
-                     const float* lse, const float* gamma2, const float* grad_cost, int B, int T, int U1, int J,
-                     int V, int blank, float* d_w_out, float* d_b_out, cudaStream_t st);
 size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V);
 int joint_bf16_launches(int op, int B, int T, int U1, int J, int V);
 

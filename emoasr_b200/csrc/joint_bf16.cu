@@ -2,28 +2,28 @@
 //
 //   z[cell, v] = sum_j tanh(enc[b,t,j] + dec[b,u,j]) * w_out[v,j] + b_out[v]
 //   lse[cell]  = log sum_v exp z ;  lp2[cell] = { z[blank]-lse, z[label]-lse }
-// (asr/modeling/decoders/rnn_transducer.py:147-156 + :102).  Default instantiation <2, false>: z lives only in TMEM
-// and registers.  <2, true> is the optional z-cache variant, which DOES write z (fp16, valid cells) and h (bf16)
-// to a caller-provided cache for the z-cache backward (joint_bwd_zc.cu).
+// (asr/modeling/decoders/rnn_transducer.py:147-156 + :102).  z lives only in TMEM and registers: nothing of size
+// N x V is written to memory.
 //
 // Persistent, warp-specialised CTA pairs (cluster of 2, cta_group::2), one 256-cell tile per pair at a time (cells of
 // one utterance, flattened over its VALID (t,u) region, so padding costs nothing); 640 threads, setmaxnreg budgets
 // per warpgroup:
-//   warp 0       TMA producer   w_out (bf16, [V][J]) tiles [128 v x 64 j] per CTA, 128B swizzle, mbarrier ring
-//                               (5 stages, 4 when the z cache is written), complete_tx
+//   warp 0       TMA producer   w_out (bf16, [V][J]) tiles [128 v x 64 j] per CTA, 128B swizzle, 5-stage mbarrier
+//                               ring, complete_tx
 //   warp 1       MMA issuer     tcgen05.mma kind::f16, M=256, N<=256, K=16; accumulators in TMEM, two 256-column
 //                               buffers so the epilogue of vocab chunk n overlaps the MMAs of chunk n+1
 //   warp 2       TMEM allocator
-//   warp 3       h-cache writer TMA store of every finished h block (bf16, tile-major) for the backward
 //   warps 4-11   epilogue       two warps per TMEM lane quadrant, each half of a chunk's columns: tcgen05.ld 32
 //                               columns at a time (thread == lattice cell), bias add, online (max, sum-exp) over the
-//                               vocab chunks, capture of the blank and label logits; optionally the logits go to the
-//                               z cache as fp16 through a per-warp staging buffer and one TMA store per block
+//                               vocab chunks, capture of the blank and label logits
 //   warps 12-19  A producers    h = tanh(enc+dec): fp16 gathers, packed-half add and tanh.approx, -> bf16 -> shared
 //                               memory in the canonical K-major 128B-swizzle layout, one 64-wide K block at a time so
 //                               the MMAs of the next tile start as soon as block 0 is rewritten (8 warps, 16 rows
 //                               each: with 4 the MMA issuer spent a third of its time waiting for h)
 // The h tile (128 x J bf16 per CTA) stays resident in shared memory for all vocab chunks of the tile.
+// (Round 1 also had a variant that stored z as fp16 and h as bf16 for a "z-cache" backward.  It materialised the
+// logits the design exists to avoid and its backward corrupted one tile in ~2.5 % of the runs at the cfg-4 shape
+// (tools/stress_repeat.py); removed in round 2 in favour of the ring backward, joint_bwd_ring.cu.)
 #include "joint_tc.cuh"
 
 // -DEMO_ZC_PROF: clock64 accounting of the MMA issuer's mbarrier waits (printf from CTA 0); tools/gpu_zcprof.sh
@@ -36,33 +36,23 @@
 namespace emo {
 namespace {
 
-// ---- per-variant constants ----
-template <int kCtas, bool kStoreZ> struct Cfg;
-template <bool kStoreZ> struct Cfg<2, kStoreZ> {
-    static constexpr int kBStages = kStoreZ ? 4 : 5;  // the z staging buffers take one stage's worth of shared memory
-    static constexpr int kBRows = kChunkN / 2;
-};
-constexpr int kZStageBytes = 2048;                    // per epilogue warp: [32 cells x 32 v] fp16, 64B swizzle
+constexpr int kCtas = 2;            // CTAs per tile (cluster of 2, cta_group::2)
+constexpr int kBStages = 5;         // w_out ring
+constexpr int kBRows = kChunkN / 2; // vocab rows of a w_out tile held by one CTA
 
-template <int kCtas, bool kStoreZ>
 struct __align__(16) FwdBarriers {
-    uint64_t b_full[Cfg<kCtas, kStoreZ>::kBStages], b_empty[Cfg<kCtas, kStoreZ>::kBStages];
+    uint64_t b_full[kBStages], b_empty[kBStages];
     uint64_t a_full[kMaxKBlocks], a_empty[kMaxKBlocks];
-    uint64_t h_ready[kMaxKBlocks];  // local: this CTA's producer threads have written block kb
     uint64_t acc_full[2], acc_empty[2];
     uint32_t tmem_base;
     uint32_t pad[3];
 };
 
 // One 32-column group of logits of this thread's row: bias add, online (max, sum exp2), capture of
-// the blank / label logit.  kStoreZ: the warp's [32 cells x 32 v] block of logits also goes to the z cache
-// as fp16: staged in this warp's shared-memory buffer (64B swizzle, conflict-free 16-byte stores) and
-// written with one TMA store (per-thread global stores of 64-byte row pieces cost 32 L1 wavefronts each).
-template <bool kStoreZ>
+// the blank / label logit.
 __device__ __forceinline__ void lse_group(const uint32_t (&r)[32], const float* __restrict__ bias,
                                           int v0, int lab, int blank, float& run_m, float& run_s,
-                                          float& zb, float& zl, const CUtensorMap* tmap_z, uint8_t* zbuf,
-                                          int zrow0, int lane) {
+                                          float& zb, float& zl) {
     float x[32];
     float m0 = kNegInf, m1 = kNegInf, m2 = kNegInf, m3 = kNegInf;
 #pragma unroll
@@ -76,22 +66,6 @@ __device__ __forceinline__ void lse_group(const uint32_t (&r)[32], const float* 
         m1 = fmaxf(m1, x[i + 1]);
         m2 = fmaxf(m2, x[i + 2]);
         m3 = fmaxf(m3, x[i + 3]);
-    }
-    if (kStoreZ) {
-        if (lane == 0) tma_store_wait_read<0>();   // the previous block has left the staging buffer
-        __syncwarp();
-        uint8_t* rowp = zbuf + lane * 64;
-#pragma unroll
-        for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<uint4*>(rowp + ((i ^ ((lane >> 1) & 3)) << 4)) =
-                make_uint4(pack_f16x2_sat(x[8 * i], x[8 * i + 1]), pack_f16x2_sat(x[8 * i + 2], x[8 * i + 3]),
-                           pack_f16x2_sat(x[8 * i + 4], x[8 * i + 5]), pack_f16x2_sat(x[8 * i + 6], x[8 * i + 7]));
-        fence_proxy_async_smem();
-        __syncwarp();
-        if (lane == 0) {
-            tma_store_2d(tmap_z, smem_u32(zbuf), v0, zrow0);
-            tma_store_commit();
-        }
     }
     const float new_m = fmaxf(run_m, fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)));
     const float neg_m2 = -new_m * kLog2e;
@@ -115,14 +89,14 @@ __device__ __forceinline__ void lse_group(const uint32_t (&r)[32], const float* 
 }
 
 // =================================================================================================
-// Fused joint forward.  See the file header for the role layout.  kCtas = 2 is the CTA-pair
-// (cta_group::2) version: the leader CTA issues M=256 MMAs over both CTAs' h tiles, and each CTA
-// stages only half (128 vocab rows) of every w_out tile.  Barrier topology for the pair:
+// Fused joint forward.  See the file header for the role layout.  The leader CTA of the pair issues M=256 MMAs over
+// both CTAs' h tiles, and each CTA stages only half (128 vocab rows) of every w_out tile.  Barrier topology:
 //   b_full / a_full / acc_empty live in the LEADER (arrivals from both CTAs, TMA bytes from both),
 //   b_empty / a_empty / acc_full are signalled in BOTH CTAs by a multicast tcgen05.commit.
 constexpr int kFwdThreads = 640;  // 4 control warps, 8 epilogue warps, 8 A-producer warps
-constexpr int kFwdProdWarps = 8;
 constexpr int kFwdEpiThreads = 256;
+constexpr int kFwdProdWarps = 8;
+constexpr int kBBytes = kBRows * kBlockK * 2;
 template <int N> __device__ __forceinline__ void reg_dec() {
     asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N));
 }
@@ -152,19 +126,13 @@ __device__ __forceinline__ void produce_h_block16(const uint4 (&re)[4], const ui
     }
 }
 
-template <int kCtas, bool kStoreZ>
 __global__ void __launch_bounds__(kFwdThreads, 1)
-joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_constant__ CUtensorMap tmap_h,
-                 const __grid_constant__ CUtensorMap tmap_z,   // z cache fp16 (rows,V), box [32 v x 32 cells], 64B swizzle
-                 int store_h, const __half* __restrict__ enc,
+joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __restrict__ enc,
                  const __half* __restrict__ dec, const float* __restrict__ b_out,
                  const int* __restrict__ labels, const int* __restrict__ tlen,
                  const int* __restrict__ ulen, int B, int T, int U1, int J, int V, int blank,
                  float* __restrict__ lp2, float* __restrict__ lse_out) {
-    constexpr bool kPair = kCtas == 2;
-    constexpr int kBStages = Cfg<kCtas, kStoreZ>::kBStages;
-    constexpr int kBBytes = Cfg<kCtas, kStoreZ>::kBRows * kBlockK * 2;
-    using Bars = FwdBarriers<kCtas, kStoreZ>;
+    using Bars = FwdBarriers;
     // 1024-byte alignment is required by the 128B swizzle atoms; the kernel has no static shared
     // memory, so the dynamic window starts at the CTA's (1 KiB-granular) shared-memory base.
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -172,19 +140,17 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     const int NC = (V + kChunkN - 1) / kChunkN;
     uint8_t* sA = smem;
     uint8_t* sB = sA + (size_t)KB * kABlockBytes;
-    uint8_t* sZst = sB + (size_t)kBStages * kBBytes;   // kStoreZ: one staging buffer per epilogue warp
-    Bars* bars = reinterpret_cast<Bars*>(sZst + (kStoreZ ? (kFwdEpiThreads / 32) * kZStageBytes : 0));
+    Bars* bars = reinterpret_cast<Bars*>(sB + (size_t)kBStages * kBBytes);
     float* s_bias = reinterpret_cast<float*>(bars + 1);  // [2][kChunkN]
     float4* s_part = reinterpret_cast<float4*>(s_bias + 2 * kChunkN);  // [kTileM] partial LSE state of column half 1
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = kPair ? cluster_ctarank() : 0;
+    const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int tiles_per_utt = (T * U1 + kCtas * kTileM - 1) / (kCtas * kTileM);
     const int total_tiles = B * tiles_per_utt;
     const int tile0 = blockIdx.x / kCtas, tile_stride = gridDim.x / kCtas;
     constexpr uint32_t kArrivals = (kFwdEpiThreads / 32) * kCtas;   // epilogue WARPS of the pair (one arrive each)
-    constexpr uint32_t kProducers = kFwdProdWarps;                  // A-producer WARPS per CTA (one arrive each)
 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < kBStages; ++i) {
@@ -192,9 +158,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             mbar_init(smem_u32(&bars->b_empty[i]), 1);
         }
         for (int i = 0; i < kMaxKBlocks; ++i) {
-            mbar_init(smem_u32(&bars->a_full[i]), kProducers * kCtas);
-            mbar_init(smem_u32(&bars->a_empty[i]), store_h ? 2 : 1);  // MMA commit (+ h store done)
-            mbar_init(smem_u32(&bars->h_ready[i]), kProducers);
+            mbar_init(smem_u32(&bars->a_full[i]), kFwdProdWarps * kCtas);   // producer WARPS of the pair
+            mbar_init(smem_u32(&bars->a_empty[i]), 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->acc_full[i]), 1);
@@ -202,17 +167,13 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         }
         fence_barrier_init();
     }
-    if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&tmap_w);
-        tma_prefetch_desc(&tmap_h);
-        if (kStoreZ) tma_prefetch_desc(&tmap_z);
-    }
+    if (warp == 0 && lane == 0) tma_prefetch_desc(&tmap_w);
     if (warp == 2) {
-        if (kPair) { tmem_alloc_pair(smem_u32(&bars->tmem_base), 512); tmem_relinquish_pair(); }
-        else       { tmem_alloc(smem_u32(&bars->tmem_base), 512); tmem_relinquish(); }
+        tmem_alloc_pair(smem_u32(&bars->tmem_base), 512);
+        tmem_relinquish_pair();
     }
     tc_fence_before();
-    if (kPair) cluster_sync_all(); else __syncthreads();
+    cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
     // register budget per warpgroup (x128 threads): control 40, two epilogue groups 128, two producer groups 88
@@ -229,18 +190,12 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 if (!tile_info<kCtas>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
                 for (int nc = 0; nc < NC; ++nc) {
                     const int n = min(kChunkN, V - nc * kChunkN);
-                    const int y = nc * kChunkN + (kPair ? (int)rank * (n >> 1) : 0);
+                    const int y = nc * kChunkN + (int)rank * (n >> 1);
                     for (int kb = 0; kb < KB; ++kb) {
                         mbar_wait(smem_u32(&bars->b_empty[stage]), phase ^ 1);
                         const uint32_t full = smem_u32(&bars->b_full[stage]);
-                        const uint32_t dst = smem_u32(sB + (size_t)stage * kBBytes);
-                        if (kPair) {
-                            mbar_arrive_expect_tx_cluster(mapa_shared(full, 0), kBBytes);
-                            tma_load_2d_pair(dst, &tmap_w, kb * kBlockK, y, full);
-                        } else {
-                            mbar_arrive_expect_tx(full, kBBytes);
-                            tma_load_2d(dst, &tmap_w, kb * kBlockK, y, full);
-                        }
+                        mbar_arrive_expect_tx_cluster(mapa_shared(full, 0), kBBytes);
+                        tma_load_2d_pair(smem_u32(sB + (size_t)stage * kBBytes), &tmap_w, kb * kBlockK, y, full);
                         if (++stage == kBStages) { stage = 0; phase ^= 1; }
                     }
                 }
@@ -260,21 +215,16 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 for (int nc = 0; nc < NC; ++nc, ++cc) {
                     const uint32_t buf = cc & 1;
                     EMO_PROF(p_c = clock64();)
-                    if (kPair) mbar_wait_cluster(smem_u32(&bars->acc_empty[buf]), ((cc >> 1) & 1) ^ 1);
-                    else       mbar_wait(smem_u32(&bars->acc_empty[buf]), ((cc >> 1) & 1) ^ 1);
+                    mbar_wait_cluster(smem_u32(&bars->acc_empty[buf]), ((cc >> 1) & 1) ^ 1);
                     EMO_PROF(p_acc += clock64() - p_c;)
                     const int n = min(kChunkN, V - nc * kChunkN);
                     const uint32_t idesc = umma_idesc_bf16(kCtas * kTileM, n);
                     const uint32_t d_tmem = tmem_base + buf * kChunkN;
                     for (int kb = 0; kb < KB; ++kb) {
                         EMO_PROF(p_c = clock64();)
-                        if (nc == 0) {
-                            if (kPair) mbar_wait_cluster(smem_u32(&bars->a_full[kb]), tl & 1);
-                            else       mbar_wait(smem_u32(&bars->a_full[kb]), tl & 1);
-                        }
+                        if (nc == 0) mbar_wait_cluster(smem_u32(&bars->a_full[kb]), tl & 1);
                         EMO_PROF(p_a += clock64() - p_c; p_c = clock64();)
-                        if (kPair) mbar_wait_cluster(smem_u32(&bars->b_full[stage]), phase);
-                        else       mbar_wait(smem_u32(&bars->b_full[stage]), phase);
+                        mbar_wait_cluster(smem_u32(&bars->b_full[stage]), phase);
                         EMO_PROF(p_b += clock64() - p_c;)
                         tc_fence_after();
                         if (elect_one_sync()) {
@@ -284,18 +234,11 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                             for (int k16 = 0; k16 < kBlockK / 16; ++k16) {
                                 const uint64_t ad = ((uint64_t)kDescHi << 32) | (a_lo + 2 * k16);
                                 const uint64_t bd = ((uint64_t)kDescHi << 32) | (b_lo + 2 * k16);
-                                if (kPair) umma_bf16_pair(d_tmem, ad, bd, idesc, (kb | k16) != 0);
-                                else       umma_bf16(d_tmem, ad, bd, idesc, (kb | k16) != 0);
+                                umma_bf16_pair(d_tmem, ad, bd, idesc, (kb | k16) != 0);
                             }
-                            if (kPair) {
-                                umma_commit_pair(smem_u32(&bars->b_empty[stage]));
-                                if (nc == NC - 1) umma_commit_pair(smem_u32(&bars->a_empty[kb]));
-                                if (kb == KB - 1) umma_commit_pair(smem_u32(&bars->acc_full[buf]));
-                            } else {
-                                umma_commit(smem_u32(&bars->b_empty[stage]));
-                                if (nc == NC - 1) umma_commit(smem_u32(&bars->a_empty[kb]));
-                                if (kb == KB - 1) umma_commit(smem_u32(&bars->acc_full[buf]));
-                            }
+                            umma_commit_pair(smem_u32(&bars->b_empty[stage]));
+                            if (nc == NC - 1) umma_commit_pair(smem_u32(&bars->a_empty[kb]));
+                            if (kb == KB - 1) umma_commit_pair(smem_u32(&bars->acc_full[buf]));
                         }
                         __syncwarp();
                         if (++stage == kBStages) { stage = 0; phase ^= 1; }
@@ -306,26 +249,6 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             EMO_PROF(if (blockIdx.x == 0 && lane == 0)
                          printf("fwd issuer: total %lld clk, %u tiles; wait acc_empty %lld a_full %lld b_full %lld\n",
                                 clock64() - p_t0, tl, p_acc, p_a, p_b);)
-        }
-    } else if (warp == 3) {
-        // ===================== h-cache writer: TMA store of every finished h block =====================
-        if (store_h && lane == 0) {
-            const int tpu = tiles128_per_utt(T, U1);
-            uint32_t tl = 0;
-            TileInfo ti;
-            for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
-                if (!tile_info<kCtas>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
-                const int row0 = (ti.b * tpu + ti.first_cell / kTileM) * kTileM;
-                for (int kb = 0; kb < KB; ++kb) {
-                    mbar_wait(smem_u32(&bars->h_ready[kb]), tl & 1);
-                    tma_store_2d(&tmap_h, smem_u32(sA + (size_t)kb * kABlockBytes), kb * kBlockK, row0);
-                    tma_store_commit();
-                    tma_store_wait_read<0>();
-                    mbar_arrive(smem_u32(&bars->a_empty[kb]));
-                }
-                ++tl;
-            }
-            tma_store_wait_all<0>();
         }
     }
     } else if (warp < 12) {
@@ -339,9 +262,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
         const int etid = threadIdx.x - 128;   // 0..255
         uint32_t cc = 0;
         TileInfo ti;
-        uint32_t acc_empty_addr[2];
-        acc_empty_addr[0] = kPair ? mapa_shared(smem_u32(&bars->acc_empty[0]), 0) : smem_u32(&bars->acc_empty[0]);
-        acc_empty_addr[1] = kPair ? mapa_shared(smem_u32(&bars->acc_empty[1]), 0) : smem_u32(&bars->acc_empty[1]);
+        const uint32_t acc_empty0 = mapa_shared(smem_u32(&bars->acc_empty[0]), 0);
         float nb = etid < V ? __ldg(b_out + etid) : 0.f;   // bias of the first chunk of the first tile
         for (int tile = tile0; tile < total_tiles; tile += tile_stride) {
             if (!tile_info<kCtas>(tile, tiles_per_utt, rank, tlen, ulen, T, U1, ti)) continue;
@@ -353,8 +274,6 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             if (valid && u < ti.U1b - 1)
                 lab = min(max(__ldg(labels + (size_t)ti.b * (U1 - 1) + u), 0), V - 1);
             float run_m = kNegInf, run_s = 0.f, zb = 0.f, zl = 0.f;
-            const int zrow0 = (ti.b * tiles128_per_utt(T, U1) + ti.first_cell / kTileM) * kTileM + q * 32;
-            uint8_t* zbuf = sZst + (warp - 4) * kZStageBytes;
             for (int nc = 0; nc < NC; ++nc, ++cc) {
                 const uint32_t buf = cc & 1;
                 const int n = min(kChunkN, V - nc * kChunkN);
@@ -376,22 +295,18 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                     for (int g = g0; g < g1; g += 2) {
                         tmem_wait_ld();
                         if (g + 1 < g1) tmem_ld_32x32b_x32(taddr + (g + 1) * 32, rb);
-                        lse_group<kStoreZ>(ra, bias + g * 32, nc * kChunkN + g * 32, lab, blank, run_m, run_s, zb, zl,
-                                           &tmap_z, zbuf, zrow0, lane);
+                        lse_group(ra, bias + g * 32, nc * kChunkN + g * 32, lab, blank, run_m, run_s, zb, zl);
                         if (g + 1 < g1) {
                             tmem_wait_ld();
                             if (g + 2 < g1) tmem_ld_32x32b_x32(taddr + (g + 2) * 32, ra);
-                            lse_group<kStoreZ>(rb, bias + (g + 1) * 32, nc * kChunkN + (g + 1) * 32, lab, blank,
-                                               run_m, run_s, zb, zl, &tmap_z, zbuf, zrow0, lane);
+                            lse_group(rb, bias + (g + 1) * 32, nc * kChunkN + (g + 1) * 32, lab, blank, run_m, run_s,
+                                      zb, zl);
                         }
                     }
                 }
                 tc_fence_before();
                 __syncwarp();
-                if (lane == 0) {
-                    if (kPair) mbar_arrive_cluster(acc_empty_addr[buf]);
-                    else       mbar_arrive(acc_empty_addr[buf]);
-                }
+                if (lane == 0) mbar_arrive_cluster(acc_empty0 + buf * 8);
             }
             // ---- merge the two column halves of the row (half 1 -> shared memory -> half 0)
             if (hf == 1) s_part[row] = make_float4(run_m, run_s, zb, zl);
@@ -407,7 +322,6 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
                 lse_out[cell] = l;
             }
         }
-        if (kStoreZ && lane == 0) tma_store_wait_all<0>();
     } else {
         reg_dec<88>();
         // ===================== A producers =====================
@@ -445,7 +359,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             return true;
         };
         uint32_t wkb = 0, wtl = 0;                 // work cursor: same sequence, KB units per valid tile
-        const uint32_t a_full0 = kPair ? mapa_shared(smem_u32(&bars->a_full[0]), 0) : smem_u32(&bars->a_full[0]);
+        const uint32_t a_full0 = mapa_shared(smem_u32(&bars->a_full[0]), 0);
         EMO_PROF(long long q_wait = 0, q_work = 0, q_t0 = clock64(), q_c;)
         auto work = [&](const uint4 (&re)[4], const uint4 (&rd)[4]) {
             EMO_PROF(q_c = clock64();)
@@ -454,11 +368,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
             produce_h_block16(re, rd, pw, rsub, c, sA + (size_t)wkb * kABlockBytes);
             fence_proxy_async_smem();
             __syncwarp();
-            if (lane == 0) {
-                if (store_h) mbar_arrive(smem_u32(&bars->h_ready[wkb]));
-                if (kPair) mbar_arrive_cluster(a_full0 + wkb * 8);
-                else       mbar_arrive(a_full0 + wkb * 8);
-            }
+            if (lane == 0) mbar_arrive_cluster(a_full0 + wkb * 8);
             EMO_PROF(q_work += clock64() - q_c;)
             if (++wkb == (uint32_t)KB) { wkb = 0; ++wtl; }
         };
@@ -479,10 +389,10 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
     }
 
     tc_fence_before();
-    if (kPair) cluster_sync_all(); else __syncthreads();
+    cluster_sync_all();
     if (warp == 2) {
         tc_fence_after();
-        if (kPair) tmem_dealloc_pair(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
+        tmem_dealloc_pair(tmem_base, 512);
     }
 }
 
@@ -490,8 +400,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __grid_consta
 
 int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
                    const float* b_out, const int* labels, const int* tlen, const int* ulen, int B,
-                   int T, int U1, int J, int V, int blank, float* lp2, float* lse, void* hcache,
-                   size_t hcache_bytes, void* ws, size_t ws_bytes, cudaStream_t st) {
+                   int T, int U1, int J, int V, int blank, float* lp2, float* lse, void* ws, size_t ws_bytes,
+                   cudaStream_t st) {
     EMO_REQUIRE(enc_proj && dec_proj && w_out && b_out && labels && tlen && ulen && lp2 && lse && ws,
                 EMO_BAD_ARG, "joint_fwd(bf16): null pointer");
     int rc = check_bf16_shape(B, T, U1, J, V, blank);
@@ -506,53 +416,29 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     if (rc) return rc;
 
     const int KB = J / kBlockK;
-    const size_t a_bytes = (size_t)KB * kABlockBytes;
-    CUtensorMap tmap, tmap_h, tmap_z;
-    const int store_h = hcache != nullptr;
-    if (store_h) {
-        // optional z-cache variant: h (bf16) and the logits (fp16) of every valid cell go to the caller's cache
-        EMO_REQUIRE(joint_zc_supported(J) &&
-                        hcache_bytes >= zcache_offset_for(B, T, U1, J) + zcache_bytes_for(B, T, U1, V) &&
-                        ((uintptr_t)hcache & 255) == 0,
-                    EMO_WORKSPACE_TOO_SMALL,
-                    "joint_fwd(bf16): cache must be emo_workspace_bytes(EMO_OP_RNNT_JOINT_HZCACHE) bytes, 256-byte "
-                    "aligned (or NULL for the default route)");
-        const uint64_t rows = (uint64_t)B * tiles128_per_utt(T, U1) * kTileM;
-        rc = make_tmap_bf16_2d(&tmap_h, hcache, (uint64_t)J, rows, kBlockK, kTileM);
-        if (rc) return rc;
-        rc = make_tmap_bf16_2d(&tmap_z, (char*)hcache + zcache_offset_for(B, T, U1, J), (uint64_t)V, rows, 32, 32,
-                               CU_TENSOR_MAP_SWIZZLE_64B);
-        if (rc) return rc;
-    }
-    const int b_rows = Cfg<2, false>::kBRows;
-    rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, b_rows);
+    CUtensorMap tmap;
+    rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, kBRows);
     if (rc) return rc;
-    if (!store_h) { tmap_h = tmap; tmap_z = tmap; }
-    const int tiles = B * ceil_div((size_t)T * U1, 2 * kTileM);
-    const int ctas = 2 * min(tiles, sm_count() / 2);
-    auto launch = [&](auto kernel, int stages, size_t bars_bytes, bool store_z) -> int {
-        const size_t smem = a_bytes + (size_t)stages * b_rows * kBlockK * 2 +
-                            (store_z ? (kFwdEpiThreads / 32) * kZStageBytes : 0) + bars_bytes +
-                            2 * kChunkN * sizeof(float) + kTileM * sizeof(float4);
-        EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_fwd(bf16): shared memory");
-        EMO_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = dim3(ctas);
-        cfg.blockDim = dim3(kFwdThreads);
-        cfg.dynamicSmemBytes = smem;
-        cfg.stream = st;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        EMO_CUDA(cudaLaunchKernelEx(&cfg, kernel, tmap, tmap_h, tmap_z, store_h, (const __half*)enc_h,
-                                    (const __half*)dec_h, b_out, labels, tlen, ulen, B, T, U1, J, V, blank, lp2, lse));
-        EMO_CHECK_LAUNCH("joint_fwd_kernel");
-        return EMO_OK;
-    };
-    if (store_h) return launch(joint_fwd_kernel<2, true>, Cfg<2, true>::kBStages, sizeof(FwdBarriers<2, true>), true);
-    return launch(joint_fwd_kernel<2, false>, Cfg<2, false>::kBStages, sizeof(FwdBarriers<2, false>), false);
+    const int tiles = B * ceil_div((size_t)T * U1, kCtas * kTileM);
+    const int ctas = kCtas * min(tiles, sm_count() / kCtas);
+    const size_t smem = (size_t)KB * kABlockBytes + (size_t)kBStages * kBBytes + sizeof(FwdBarriers) +
+                        2 * kChunkN * sizeof(float) + kTileM * sizeof(float4);
+    EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_fwd(bf16): shared memory");
+    EMO_CUDA(cudaFuncSetAttribute(joint_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(kFwdThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    EMO_CUDA(cudaLaunchKernelEx(&cfg, joint_fwd_kernel, tmap, (const __half*)enc_h, (const __half*)dec_h, b_out, labels,
+                                tlen, ulen, B, T, U1, J, V, blank, lp2, lse));
+    EMO_CHECK_LAUNCH("joint_fwd_kernel");
+    return EMO_OK;
 }
 
 }  // namespace emo

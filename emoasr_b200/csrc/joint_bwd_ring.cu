@@ -1222,14 +1222,10 @@ static size_t casts_bytes(int B, int T, int U1, int J, int V) {
 }
 
 size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V) {
-    if (op == EMO_OP_RNNT_JOINT_HZCACHE) {
-        if (!joint_zc_supported(J) || J % 128 != 0 || V % 32 != 0) return 0;
-        return zcache_offset_for(B, T, U1, J) + align_up(zcache_bytes_for(B, T, U1, V), 256);
-    }
     if (op == EMO_OP_RNNT_JOINT_FWD) return casts_bytes(B, T, U1, J, V);
     if (op == EMO_OP_RNNT_JOINT_BWD) {
         // bf16 w_out + fp16 streams, tile-major dh (bf16, rows of the valid cells), the dz / h ring and its flags
-        size_t n = casts_bytes(B, T, U1, J, V) + align_up(hcache_bytes_for(B, T, U1, J), 1024);
+        size_t n = casts_bytes(B, T, U1, J, V) + align_up(dh_bytes_for(B, T, U1, J), 1024);
         if (joint_ring_supported(B, T, U1, J, V)) n += joint_ring_workspace(B, T, U1, J, V);
         return n;
     }
@@ -1239,7 +1235,6 @@ size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V) {
 int joint_bf16_launches(int op, int B, int T, int U1, int J, int V) {
     (void)B; (void)T; (void)U1; (void)J; (void)V;
     if (op == EMO_OP_RNNT_JOINT_BWD) return 6;  // 3 casts, ring prep, ring kernel, axis reductions
-    if (op == EMO_OP_RNNT_JOINT_HZCACHE) return 4;  // backward on the z-cache route: weight cast, dhz, axis reductions, dWz
     return 4;                                    // weight cast, 2 stream casts, fused joint forward
 }
 
@@ -1266,12 +1261,11 @@ int joint_bf16_casts(const float* enc_proj, const float* dec_proj, const float* 
 
 int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
                    const float* b_out, const int* labels, const int* tlen, const int* ulen,
-                   const float* lse, const float* lp2, const float* gamma2, const float* grad_cost,
-                   const void* hcache, size_t hcache_bytes, int B, int T,
+                   const float* lse, const float* lp2, const float* gamma2, const float* grad_cost, int B, int T,
                    int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
                    float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st) {
-    EMO_REQUIRE(enc_proj && dec_proj && w_out && b_out && labels && tlen && ulen && lse && gamma2 && grad_cost &&
-                    d_enc_proj && d_dec_proj && d_w_out && d_b_out && ws,
+    EMO_REQUIRE(enc_proj && dec_proj && w_out && b_out && labels && tlen && ulen && lse && lp2 && gamma2 &&
+                    grad_cost && d_enc_proj && d_dec_proj && d_w_out && d_b_out && ws,
                 EMO_BAD_ARG, "joint_bwd(bf16): null pointer");
     int rc = check_bf16_shape(B, T, U1, J, V, blank);
     if (rc) return rc;
@@ -1282,31 +1276,13 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
                 EMO_BAD_ARG, "joint_bwd(bf16): pointers must be 16-byte (workspace 256-byte) aligned");
     const size_t nw = (size_t)V * J;
     void* dh_ws = (char*)ws + casts_bytes(B, T, U1, J, V);
+    void* ring_ws = (char*)dh_ws + align_up(dh_bytes_for(B, T, U1, J), 1024);
     EMO_CUDA(cudaMemsetAsync(d_w_out, 0, nw * sizeof(float), st));
     EMO_CUDA(cudaMemsetAsync(d_b_out, 0, (size_t)V * sizeof(float), st));
     EMO_CUDA(cudaMemsetAsync(d_dec_proj, 0, (size_t)B * U1 * J * sizeof(float), st));
-
-    // ---- z-cache variant: the caller let the forward store the logits (fp16) behind an h cache
-    const bool zc = hcache && joint_zc_supported(J) &&
-                    hcache_bytes >= zcache_offset_for(B, T, U1, J) + zcache_bytes_for(B, T, U1, V);
-    const void *w_bf16, *enc_h = nullptr, *dec_h = nullptr;
-    if (zc) {
-        EMO_REQUIRE(((uintptr_t)hcache & 255) == 0, EMO_BAD_ARG, "joint_bwd(bf16): cache misaligned");
-        rc = joint_bf16_casts(enc_proj, dec_proj, w_out, B, T, U1, J, V, ws, &w_bf16, nullptr, nullptr, st);
-        if (rc) return rc;
-        const void* zcache = (const char*)hcache + zcache_offset_for(B, T, U1, J);
-        rc = joint_dhz_launch(w_bf16, zcache, labels, tlen, ulen, lse, gamma2, grad_cost, B, T, U1, J, V,
-                              blank, dh_ws, enc_proj, dec_proj, d_enc_proj, d_dec_proj, st);
-        if (rc) return rc;
-        return joint_dwz_launch(hcache, zcache, labels, tlen, ulen, lse, gamma2, grad_cost, B, T, U1, J, V, blank,
-                                d_w_out, d_b_out, st);
-    }
-
-    // ---- default: ring route, nothing of size N x V (or N x J, besides dh) ever reaches HBM
-    EMO_REQUIRE(lp2, EMO_BAD_ARG, "joint_bwd(bf16): lp2 (the forward's output) is required");
+    const void *w_bf16, *enc_h, *dec_h;
     rc = joint_bf16_casts(enc_proj, dec_proj, w_out, B, T, U1, J, V, ws, &w_bf16, &enc_h, &dec_h, st);
     if (rc) return rc;
-    void* ring_ws = (char*)dh_ws + align_up(hcache_bytes_for(B, T, U1, J), 1024);
     rc = joint_bwd_ring_launch(w_bf16, enc_h, dec_h, b_out, labels, tlen, ulen, lse, lp2, gamma2, grad_cost, B, T, U1,
                                J, V, blank, dh_ws, ring_ws, d_w_out, d_b_out, st);
     if (rc) return rc;

@@ -1,4 +1,4 @@
-// Shared pieces of the tcgen05 joint kernels (forward: joint_bf16.cu, backward: joint_bwd_bf16.cu).
+// Shared pieces of the tcgen05 joint kernels (forward: joint_bf16.cu, backward: joint_bwd_ring.cu, joint_reduce.cu).
 #pragma once
 #include <stdlib.h>
 
@@ -24,26 +24,16 @@ struct TileInfo {
     int b, first_cell, n_cells, U1b;  // n_cells = valid cells of the utterance
 };
 
-// h cache: tanh output of every valid cell in bf16, written by the forward kernel and read by the
-// backward kernels.  Layout [B * tiles128_per_utt * 128, J], row = (b * tiles128_per_utt +
-// first_cell / 128) * 128 + row-in-tile; tiles128_per_utt is even so a CTA pair always owns two slots.
+// dh workspace of the backward (bf16, tile-major): layout [B * tiles128_per_utt * 128, J], row = (b *
+// tiles128_per_utt + first_cell / 128) * 128 + row-in-tile for the flattened valid cell m = t * (U_b+1) + u;
+// tiles128_per_utt is even so a CTA pair always owns two slots.
 __host__ __device__ inline int tiles128_per_utt(int T, int U1) { return 2 * ((T * U1 + 255) / 256); }
-inline size_t hcache_bytes_for(int B, int T, int U1, int J) {
+inline size_t dh_bytes_for(int B, int T, int U1, int J) {
     return (size_t)B * tiles128_per_utt(T, U1) * kTileM * J * sizeof(__nv_bfloat16);
 }
 
-// kCtas = 1: one CTA per 128-cell tile.  kCtas = 2: a CTA pair (cluster of 2, cta_group::2) per
-// 256-cell tile, 128 cells per CTA; `rank` selects this CTA's half.  Both CTAs of a pair get the
-// same answer.
-// z cache (optional, behind the h cache in the same buffer): fp16 logits z = h W^T + b of the same rows,
-// layout [B * tiles128_per_utt * 128, V].
-inline size_t zcache_offset_for(int B, int T, int U1, int J) {
-    return (hcache_bytes_for(B, T, U1, J) + 255) / 256 * 256;
-}
-inline size_t zcache_bytes_for(int B, int T, int U1, int V) {
-    return (size_t)B * tiles128_per_utt(T, U1) * kTileM * V * sizeof(__half);
-}
-
+// kCtas = 2: a CTA pair (cluster of 2, cta_group::2) per 256-cell tile, 128 cells per CTA; `rank` selects this
+// CTA's half.  Both CTAs of a pair get the same answer.  (kCtas = 1: one CTA per 128-cell tile.)
 template <int kCtas>
 __device__ __forceinline__ bool tile_info(int tile, int tiles_per_utt, uint32_t rank, const int* tlen,
                                           const int* ulen, int T, int U1, TileInfo& ti) {

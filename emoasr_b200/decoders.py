@@ -73,19 +73,17 @@ class FusedCTCForward:
 
 class FusedRNNTForward:
     """forward() of rnn_transducer.py:81-145 with joint -> log_softmax -> warp_rnnt.rnnt_loss
-    (:101-115) replaced by one fused op.  The third return value is None (with the default route the
-    (B,T,U+1,V) logits are never formed; the only caller, asr/modeling/asr.py:65, discards it).
+    (:101-115) replaced by one fused op.  The third return value is None (the (B,T,U+1,V) logits are never
+    formed; the only caller, asr/modeling/asr.py:65, discards it).
 
     ``fused_precision`` "bf16" runs the tensor-core kernels; shapes they do not support (see
-    ``emo_rnnt_joint_supported``) fall back to the fp32 kernels with a one-time warning.
-    ``fused_route``: "ring" (default, nothing of size N x V in HBM) or "zcache" (see functional)."""
+    ``emo_rnnt_joint_supported``) fall back to the fp32 kernels with a one-time warning."""
 
     fused_precision = "bf16"
-    fused_route = "ring"
     _warned_fallback = False
 
     def _precision_for(self, B, T, U1, J, V):
-        if self.fused_precision != "bf16" or F.joint_supported("bf16", self.fused_route, B, T, U1, J, V):
+        if self.fused_precision != "bf16" or F.joint_supported("bf16", B, T, U1, J, V):
             return self.fused_precision
         if not FusedRNNTForward._warned_fallback:
             FusedRNNTForward._warned_fallback = True
@@ -112,8 +110,7 @@ class FusedRNNTForward:
                                       ys, elens, ylens, blank=self.blank_id, reduction="mean",
                                       precision=self._precision_for(enc_proj.size(0), enc_proj.size(1),
                                                                     dec_proj.size(1), enc_proj.size(2),
-                                                                    self.output.weight.size(0)),
-                                      route=self.fused_route)
+                                                                    self.output.weight.size(0)))
         loss += loss_rnnt
         loss_dict["loss_rnnt"] = loss_rnnt
         if self.mtl_ctc_weight > 0:

@@ -17,7 +17,7 @@ import runpy
 import sys
 
 
-def install(reference_root=None, precision="bf16", route="ring"):
+def install(reference_root=None, precision="bf16"):
     compat = os.path.join(os.path.dirname(os.path.abspath(__file__)), "compat")
     if compat not in sys.path:
         sys.path.insert(0, compat)                       # S1
@@ -41,7 +41,6 @@ def install(reference_root=None, precision="bf16", route="ring"):
 
     class RNNTDecoder(FusedRNNTForward, ref_rnnt.RNNTDecoder):
         fused_precision = precision
-        fused_route = route
 
         def __init__(self, params, phase="train"):
             ref_rnnt.RNNTDecoder.__init__(self, params, phase)
@@ -59,11 +58,10 @@ def main(argv=None):
     ap = argparse.ArgumentParser(description=__doc__, formatter_class=argparse.RawDescriptionHelpFormatter)
     ap.add_argument("--reference", required=True, help="root of an emoASR checkout")
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
-    ap.add_argument("--route", default="ring", choices=["ring", "zcache"])
     ap.add_argument("script", help="reference script, e.g. asr/train_asr.py")
     ap.add_argument("args", nargs=argparse.REMAINDER)
     ns = ap.parse_args(argv)
-    install(ns.reference, ns.precision, ns.route)
+    install(ns.reference, ns.precision)
     script = ns.script if os.path.isabs(ns.script) else os.path.join(ns.reference, ns.script)
     sys.argv = [script] + [a for a in ns.args if a != "--"]
     runpy.run_path(script, run_name="__main__")

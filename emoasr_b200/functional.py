@@ -148,21 +148,14 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=
 
 
 # ----------------------------------------------------------------------------------------------
-ROUTES = ("ring", "zcache")
-
-
-def joint_supported(precision, route, B, T, U1, J, V):
-    """True if rnnt_joint_loss can run these sizes with this precision / route (host call, no CUDA work)."""
-    return bool(_lib.load().emo_rnnt_joint_supported(_PRECISIONS[precision], ROUTES.index(route), B, T, U1, J, V))
-
-
-def _zcache_bytes(precision, B, T, U1, J, V):
-    return _lib.workspace_bytes(_lib.OP_RNNT_JOINT_HZCACHE, precision, B, T, U1, J, V)
+def joint_supported(precision, B, T, U1, J, V):
+    """True if rnnt_joint_loss can run these sizes with this precision (host call, no CUDA work)."""
+    return bool(_lib.load().emo_rnnt_joint_supported(_PRECISIONS[precision], B, T, U1, J, V))
 
 
 class _RNNTJoint(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, blank, precision, route, grad_mode):
+    def forward(ctx, enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, blank, precision):
         _require_cuda(enc_proj, dec_proj, w_out, b_out)
         lib = _lib.load()
         enc, dec, w, bo = _f32c(enc_proj), _f32c(dec_proj), _f32c(w_out), _f32c(b_out)
@@ -181,23 +174,13 @@ class _RNNTJoint(torch.autograd.Function):
                 labels = labels[:, : U1 - 1].contiguous()
         else:
             labels = torch.zeros(B, 1, dtype=torch.int32, device=dev)
-        need_grad = any(ctx.needs_input_grad[:4]) and grad_mode   # (grad mode is always off inside forward())
         with torch.cuda.device(dev):
             nbytes = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_FWD, precision, B, T, U1, J, V)
             ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
             lp2 = torch.empty(B, T, U1, 2, device=dev)
             lse = torch.empty(B, T, U1, device=dev)
-            # route "zcache" (opt-in, bf16 only): the forward also stores h (bf16) and the logits (fp16) of the
-            # valid cells for the backward.  Default "ring": nothing is cached, the backward recomputes.
-            cache = None
-            if route == "zcache" and need_grad and precision == _lib.PREC_BF16:
-                cbytes = _zcache_bytes(precision, B, T, U1, J, V)
-                if cbytes == 0:
-                    raise RuntimeError(f"route='zcache' does not support J={J}, V={V}")
-                cache = torch.empty(cbytes, dtype=torch.uint8, device=dev)
             _lib.check(lib.emo_rnnt_joint_fwd(_p(enc), _p(dec), _p(w), _p(bo), _p(labels), _p(tlen), _p(ulen),
                                               B, T, U1, J, V, blank, precision, _p(lp2), _p(lse),
-                                              _p(cache), cache.numel() if cache is not None else 0,
                                               _p(ws), ws.numel(), _stream()), "emo_rnnt_joint_fwd")
             alpha = torch.empty(B, T, U1, device=dev)
             beta = torch.empty(B, T, U1, device=dev)
@@ -206,18 +189,15 @@ class _RNNTJoint(torch.autograd.Function):
             _lib.check(lib.emo_rnnt_lattice_fwd_bwd(_p(lp2), _p(tlen), _p(ulen), B, T, U1, _p(alpha),
                                                     _p(beta), _p(cost), _p(gamma2), _stream()),
                        "emo_rnnt_lattice_fwd_bwd")
-        if cache is not None:
-            ctx.save_for_backward(enc, dec, w, bo, labels, tlen, ulen, lse, lp2, gamma2, cache)
-        else:
-            ctx.save_for_backward(enc, dec, w, bo, labels, tlen, ulen, lse, lp2, gamma2)
+        # nothing of size N x V is kept for the backward: it recomputes the logit tiles
+        ctx.save_for_backward(enc, dec, w, bo, labels, tlen, ulen, lse, lp2, gamma2)
         ctx.cfg = (blank, precision)
         return cost
 
     @staticmethod
     @once_differentiable
     def backward(ctx, grad_cost):
-        enc, dec, w, bo, labels, tlen, ulen, lse, lp2, gamma2, *rest = ctx.saved_tensors
-        cache = rest[0] if rest else None
+        enc, dec, w, bo, labels, tlen, ulen, lse, lp2, gamma2 = ctx.saved_tensors
         blank, precision = ctx.cfg
         lib = _lib.load()
         B, T, J = enc.shape
@@ -232,32 +212,26 @@ class _RNNTJoint(torch.autograd.Function):
             d_w = torch.empty_like(w)
             d_b = torch.empty_like(bo)
             _lib.check(lib.emo_rnnt_joint_bwd(_p(enc), _p(dec), _p(w), _p(bo), _p(labels), _p(tlen), _p(ulen),
-                                              _p(lse), _p(lp2), _p(gamma2), _p(g), _p(cache),
-                                              cache.numel() if cache is not None else 0,
+                                              _p(lse), _p(lp2), _p(gamma2), _p(g),
                                               B, T, U1, J, V, blank, precision,
                                               _p(d_enc), _p(d_dec), _p(d_w), _p(d_b), _p(ws), ws.numel(),
                                               _stream()), "emo_rnnt_joint_bwd")
-        return d_enc, d_dec, d_w, d_b, None, None, None, None, None, None, None
+        return d_enc, d_dec, d_w, d_b, None, None, None, None, None
 
 
 def rnnt_joint_loss(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths, labels_lengths,
-                    blank=0, reduction=None, precision="bf16", route="ring"):
+                    blank=0, reduction=None, precision="bf16"):
     """Per-utterance transducer cost straight from the two projected streams.
 
     enc_proj (B,T,J) = w_enc(eouts)+b, dec_proj (B,U+1,J) = w_dec(douts)+b, w_out (V,J), b_out (V).
     Equivalent to ``rnnt_loss(log_softmax(output(tanh(enc_proj[:,:,None]+dec_proj[:,None]))), ...)``
-    (rnn_transducer.py:101-115,147-156).
-
-    route="ring" (default): the (B,T,U+1,V) logits / log-probs / gradient are never formed, neither by the
-    forward nor by the backward, which recomputes logit tiles on the tensor cores and hands ``dz`` to the
-    gradient GEMMs through an L2-resident ring of tiles.  route="zcache" (bf16 only, opt-in): the forward
-    stores the logits of the valid cells as fp16 (2 bytes per cell and vocabulary entry) and the backward
-    streams them -- fewer tensor-core flops, ~100x the HBM traffic.
+    (rnn_transducer.py:101-115,147-156).  The (B,T,U+1,V) logits / log-probs / gradient are never formed,
+    neither by the forward nor by the backward: precision="bf16" recomputes logit tiles on the tensor cores and
+    hands ``dz`` to the gradient GEMMs through an L2-resident ring of tiles; precision="fp32" (parity mode)
+    streams them through a bounded slab.
     """
-    if route not in ROUTES:
-        raise ValueError(f"unknown route {route!r}; expected one of {ROUTES}")
     costs = _RNNTJoint.apply(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths,
-                             labels_lengths, int(blank), _PRECISIONS[precision], route, torch.is_grad_enabled())
+                             labels_lengths, int(blank), _PRECISIONS[precision])
     return _reduce(costs, reduction)
 
 

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define EMO_ABI_VERSION 4
+#define EMO_ABI_VERSION 5
 
 enum emo_status {
     EMO_OK = 0,
@@ -53,10 +53,7 @@ enum emo_precision {
 enum emo_op {
     EMO_OP_RNNT_JOINT_FWD = 0,
     EMO_OP_RNNT_JOINT_BWD = 1,
-    EMO_OP_CTC = 2,
-    EMO_OP_RNNT_JOINT_HZCACHE = 4 /* emo_workspace_bytes: size of the OPTIONAL h + fp16 logit cache of the z-cache
-                                     variant (see emo_rnnt_joint_fwd); emo_launch_count: launches of that variant's
-                                     backward */
+    EMO_OP_CTC = 2
 };
 
 int emo_abi_version(void);
@@ -71,10 +68,9 @@ size_t emo_workspace_bytes(int op, int precision, int B, int T, int U1, int J, i
  * (J is ignored). */
 int emo_launch_count(int op, int precision, int B, int T, int U1, int J, int V);
 
-/* 1 if emo_rnnt_joint_fwd / _bwd support these sizes for this precision and route (0 = default ring route,
- * 1 = z-cache variant; ignored for EMO_PREC_FP32, which supports every shape), else 0.  Host call.
- * EMO_PREC_BF16 needs J % 128 == 0, J <= 512, V % 32 == 0 and (default route) B <= 1024. */
-int emo_rnnt_joint_supported(int precision, int route, int B, int T, int U1, int J, int V);
+/* 1 if emo_rnnt_joint_fwd / _bwd support these sizes for this precision, else 0.  Host call.  EMO_PREC_FP32
+ * supports every shape; EMO_PREC_BF16 needs J % 128 == 0, J <= 512, V % 32 == 0, B <= 1024, T and U1 < 65536. */
+int emo_rnnt_joint_supported(int precision, int B, int T, int U1, int J, int V);
 
 /* ---- RNN-T lattice on gathered pairs ---------------------------------------------------------
  * Replaces the alpha/beta/grad kernels of warp_rnnt.rnnt_loss (rnn_transducer.py:106-115).
@@ -111,34 +107,26 @@ int emo_rnnt_dense_bwd(const float* gamma2_ws, const int* labels, const int* tle
  * w_out (V,J) fp32 row-major (torch Linear weight), b_out (V)
  * For every valid cell: h = tanh(enc_proj[b,t] + dec_proj[b,u]); z = w_out h + b_out;
  *   lse[b,t,u] = logsumexp_v z;  lp2[b,t,u] = {z[blank]-lse, z[labels[b,u]]-lse (u < ulen[b])}.
- * EMO_PREC_BF16, default route (hcache == NULL): nothing of size N x V (N = valid lattice cells) is written to
- * memory by the forward, and the backward keeps it that way (see emo_rnnt_joint_bwd); the only per-cell outputs
- * are lp2 and lse.  EMO_PREC_FP32 streams the logits through a bounded slab inside `ws`.
- * OPTIONAL z-cache variant (EMO_PREC_BF16; a trade of HBM for tensor-core work that DOES materialise the logits
- * of the valid cells): if the caller passes a buffer of emo_workspace_bytes(EMO_OP_RNNT_JOINT_HZCACHE, ...) bytes
- * (non-zero for shapes that support it, 256-byte aligned) as hcache, the forward also leaves h = tanh(.) as bf16
- * and the logits z as fp16 (2 bytes per valid cell and vocabulary entry: 1.66 GB at B=32 T=250 U=100 V=1024) in
- * it, tile-major, and emo_rnnt_joint_bwd, given the same buffer and size, streams them instead of recomputing z.
- * hcache is ignored (may be NULL, 0) in EMO_PREC_FP32.
+ * EMO_PREC_BF16: nothing of size N x V (N = valid lattice cells) is written to memory by the forward, and the
+ * backward keeps it that way (see emo_rnnt_joint_bwd); the only per-cell outputs are lp2 and lse.
+ * EMO_PREC_FP32 streams the logits through a bounded slab inside `ws`.
  */
 int emo_rnnt_joint_fwd(const float* enc_proj, const float* dec_proj,
                        const float* w_out, const float* b_out,
                        const int* labels, const int* tlen, const int* ulen,
                        int B, int T, int U1, int J, int V, int blank, int precision,
-                       float* lp2, float* lse, void* hcache, size_t hcache_bytes,
-                       void* ws, size_t ws_bytes, void* stream);
+                       float* lp2, float* lse, void* ws, size_t ws_bytes, void* stream);
 
 /* Backward of cost (B) w.r.t. enc_proj, dec_proj, w_out, b_out given grad_cost (B):
  *   dz[b,t,u,v] = grad_cost[b] * ((g_blank+g_label) * exp(z[v]-lse) - g_blank 1[v=blank]
  *                                  - g_label 1[v=labels[b,u]])
  *   d_w_out (V,J) = sum dz^T h ; d_b_out (V) = sum dz ; dh = dz w_out ;
  *   dpre = dh (1-h^2) ; d_enc_proj[b,t] = sum_u dpre ; d_dec_proj[b,u] = sum_t dpre.
- * EMO_PREC_BF16, default route (hcache == NULL): z is RECOMPUTED tile by tile on the tensor cores by producer
- * CTA pairs of one persistent kernel, turned into dz in their epilogue and handed to the dh / dW consumer pairs
- * of the same kernel through a ring of tiles inside `ws` whose size (36 MB) does not depend on the problem
- * size and stays L2-resident; dz is never a tensor in HBM.  What does go through HBM is dh as bf16 (N x J),
- * read back once by the axis reductions.  With the z-cache buffer of the forward (see above) the logits are
- * streamed from it instead.
+ * EMO_PREC_BF16: z is RECOMPUTED tile by tile on the tensor cores by producer CTA pairs of one persistent
+ * kernel, turned into dz in their epilogue and handed to the dh / dW consumer pairs of the same kernel through
+ * a ring of tiles inside `ws` whose size (36 MB) does not depend on the problem size and stays L2-resident; dz
+ * is never a tensor in HBM.  What does go through HBM is dh as bf16 (N x J), read back once by the axis
+ * reductions.
  * All four outputs are overwritten (not accumulated into).  enc_proj, dec_proj, w_out, b_out, labels, the
  * lengths, lse and lp2 must be the tensors the forward call saw / produced (as autograd's saved tensors are):
  * the backward re-reads them (h is recomputed from enc_proj / dec_proj; lp2 gives the exact blank / label
@@ -147,7 +135,6 @@ int emo_rnnt_joint_bwd(const float* enc_proj, const float* dec_proj,
                        const float* w_out, const float* b_out,
                        const int* labels, const int* tlen, const int* ulen,
                        const float* lse, const float* lp2, const float* gamma2, const float* grad_cost,
-                       const void* hcache, size_t hcache_bytes,
                        int B, int T, int U1, int J, int V, int blank, int precision,
                        float* d_enc_proj, float* d_dec_proj, float* d_w_out, float* d_b_out,
                        void* ws, size_t ws_bytes, void* stream);

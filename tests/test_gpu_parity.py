@@ -267,7 +267,7 @@ BF16_LOSS_RTOL = 2e-3
 BF16_GRAD_RTOL = 2e-2
 
 
-def _joint_fwd_raw(enc, dec_, w_out, b_out, ys, tl, ul, precision, cache_op=None, return_cache=False):
+def _joint_fwd_raw(enc, dec_, w_out, b_out, ys, tl, ul, precision):
     """Calls emo_rnnt_joint_fwd directly; returns lp2 (B,T,U1,2) and lse (B,T,U1) as numpy."""
     import ctypes
     from emoasr_b200 import _lib
@@ -282,15 +282,11 @@ def _joint_fwd_raw(enc, dec_, w_out, b_out, ys, tl, ul, precision, cache_op=None
     lp2 = torch.zeros(B, T, U1, 2, device=dev())
     lse = torch.zeros(B, T, U1, device=dev())
     p = lambda t: ctypes.c_void_p(t.data_ptr())
-    hb = 0 if cache_op is None else _lib.workspace_bytes(cache_op, precision, B, T, U1, J, V)
-    hc = torch.empty(max(hb, 256), dtype=torch.uint8, device=dev())
     rc = lib.emo_rnnt_joint_fwd(p(te[0]), p(te[1]), p(te[2]), p(te[3]), p(lab), p(tlen), p(ulen), B, T, U1, J, V,
-                                0, precision, p(lp2), p(lse), p(hc) if hb else None, hb, p(ws), ws.numel(),
+                                0, precision, p(lp2), p(lse), p(ws), ws.numel(),
                                 ctypes.c_void_p(torch.cuda.current_stream().cuda_stream))
     _lib.check(rc, "emo_rnnt_joint_fwd")
     torch.cuda.synchronize()
-    if return_cache:
-        return lp2.cpu().numpy(), lse.cpu().numpy(), hc
     return lp2.cpu().numpy(), lse.cpu().numpy()
 
 
@@ -332,35 +328,12 @@ def test_joint_bf16_forward_values(B, T, U, V, J):
     # fp32 mode through the same raw call agrees tightly
     lp2f, lsef = _joint_fwd_raw(enc, dec_, w_out, b_out, ys, tl, ul, precision=0)
     assert np.abs(lsef[0, :, :] - lse_ref[0]).max() < 1e-4
-    # with the larger cache the forward also leaves h (bf16) and the logits (fp16) of every valid cell,
-    # tile-major: row (b * tiles128 + m // 128) * 128 + m % 128 for the flattened valid cell m = t * (U_b+1) + u
-    from emoasr_b200 import _lib
-    lp2z, lsez, hc = _joint_fwd_raw(enc, dec_, w_out, b_out, ys, tl, ul, precision=1,
-                                    cache_op=_lib.OP_RNNT_JOINT_HZCACHE, return_cache=True)
-    assert np.array_equal(lp2z, lp2) and np.array_equal(lsez, lse)
-    U1 = U + 1
-    tpu = 2 * ((T * U1 + 255) // 256)
-    rows = B * tpu * 128
-    hbytes = (rows * J * 2 + 255) // 256 * 256
-    hcache = hc[: rows * J * 2].view(torch.bfloat16).view(rows, J).float().cpu().numpy()
-    zcache = hc[hbytes: hbytes + rows * V * 2].view(torch.float16).view(rows, V).float().cpu().numpy()
-    for b in range(B):
-        Tb, U1b = tl[b], ul[b] + 1
-        m = np.arange(Tb * U1b)
-        t, u = m // U1b, m % U1b
-        r = b * tpu * 128 + m
-        assert np.abs(hcache[r] - np.tanh(enc[b, t] + dec_[b, u])).max() < 2e-2
-        assert np.abs(zcache[r] - z[b, t, u]).max() < 6e-2
 
 
-ROUTES = ["ring", "zcache"]
-
-
-@pytest.mark.parametrize("route", ROUTES)
 @pytest.mark.parametrize("B,T,U,V,J", BF16_SHAPES)
-def test_joint_bf16_loss_and_grads(B, T, U, V, J, route):
-    """Both backward routes: "ring" (default: logit tiles recomputed, dz handed to the gradient GEMMs through the
-    L2-resident ring, nothing N x V in HBM) and "zcache" (logits streamed from the forward's fp16 cache)."""
+def test_joint_bf16_loss_and_grads(B, T, U, V, J):
+    """Loss and all four gradients of the tensor-core path (logit tiles recomputed by the backward, dz handed to
+    the gradient GEMMs through the L2-resident ring, nothing N x V in HBM) vs the fp64 oracle."""
     import emoasr_b200 as E
     from oracle import rnnt_dp
     rng = np.random.default_rng(B * 77 + V)
@@ -373,7 +346,7 @@ def test_joint_bf16_loss_and_grads(B, T, U, V, J, route):
     eye = np.eye(J, dtype=np.float32)
     r = rnnt_dp.joint_loss_and_grads(enc, dec_, eye, np.zeros(J), eye, np.zeros(J), w_out, b_out, ys, tl, ul)
     te = [T_(a).requires_grad_() for a in (enc, dec_, w_out, b_out)]
-    loss = E.rnnt_joint_loss(*te, T_(ys), T_(tl), T_(ul), blank=0, reduction="mean", precision="bf16", route=route)
+    loss = E.rnnt_joint_loss(*te, T_(ys), T_(tl), T_(ul), blank=0, reduction="mean", precision="bf16")
     loss.backward()
     assert abs(float(loss) - r["loss"]) <= BF16_LOSS_RTOL * abs(r["loss"])
     for t, k in zip(te, ["d_enc_proj", "d_dec_proj", "d_w_out", "d_b_out"]):
@@ -412,8 +385,7 @@ def test_ctc_backward_without_staged_beta_matches_training_path():
     assert torch.allclose(grad, x.grad, rtol=GRAD_RTOL, atol=2e-5)
 
 
-@pytest.mark.parametrize("route", ROUTES)
-def test_joint_bf16_properties_full_size_cfg3(route):
+def test_joint_bf16_properties_full_size_cfg3():
     """BASELINE cfg 3 at full size (B=32,T=250,U=100,V=1024,J=512; the oracle would need 3.3 GB tensors):
     size-independent properties of the fused tensor-core path.
       * every dz row sums to zero (softmax - two one-hots)        =>  sum(d_b_out) ~ 0
@@ -432,7 +404,7 @@ def test_joint_bf16_properties_full_size_cfg3(route):
     r = torch.linspace(1.0, 0.6, B)
     tl, ul = (T * r).long().to(dev()), (U * r).long().to(dev())
     te = [t.clone().requires_grad_() for t in (enc, dec_, w, bo)]
-    loss = E.rnnt_joint_loss(*te, ys, tl, ul, blank=0, reduction="mean", precision="bf16", route=route)
+    loss = E.rnnt_joint_loss(*te, ys, tl, ul, blank=0, reduction="mean", precision="bf16")
     loss.backward()
     d_enc, d_dec, d_w, d_b = [t.grad for t in te]
     assert torch.isfinite(loss) and all(torch.isfinite(g).all() for g in (d_enc, d_dec, d_w, d_b))

@@ -14,7 +14,6 @@ pytestmark = pytest.mark.gpu
 
 LOSS_RTOL, GRAD_RTOL = 1e-5, 1e-4            # fp32 mode (north star)
 BF16_LOSS_RTOL, BF16_GRAD_RTOL = 2e-3, 2e-2  # stated bf16-operand tolerance
-ROUTES = ["ring", "zcache"]
 
 torch.backends.cudnn.allow_tf32 = False
 torch.backends.cuda.matmul.allow_tf32 = False
@@ -52,8 +51,7 @@ def test_lattice_cfg4_vs_c_oracle():
         assert np.all(g[b, tl[b]:] == 0) and np.all(g[b, :, ul[b] + 1:] == 0)
 
 
-@pytest.mark.parametrize("route", ROUTES)
-def test_joint_cfg4_shape_vs_fp32_mode(route):
+def test_joint_cfg4_shape_vs_fp32_mode():
     """One cfg-4-shaped joint step (T=1000, U=400, V=4096, J=512; B=2, second utterance shorter): loss and all
     four gradients of the tensor-core path against the fp32 mode (itself pinned to the reference at 1e-5 / 1e-4)."""
     import emoasr_b200 as E
@@ -66,9 +64,9 @@ def test_joint_cfg4_shape_vs_fp32_mode(route):
     ys = torch.randint(1, V, (B, U), generator=gen).to(dev())
     tl, ul = torch.tensor([T, 611], device=dev()), torch.tensor([U, 333], device=dev())
     out = {}
-    for prec, rt in (("fp32", "ring"), ("bf16", route)):
+    for prec in ("fp32", "bf16"):
         te = [t.clone().requires_grad_() for t in (enc, dec_, w, bo)]
-        loss = E.rnnt_joint_loss(*te, ys, tl, ul, blank=0, reduction="mean", precision=prec, route=rt)
+        loss = E.rnnt_joint_loss(*te, ys, tl, ul, blank=0, reduction="mean", precision=prec)
         loss.backward()
         out[prec] = (float(loss), [t.grad for t in te])
     assert abs(out["bf16"][0] - out["fp32"][0]) <= BF16_LOSS_RTOL * abs(out["fp32"][0])
@@ -107,10 +105,9 @@ def test_ctc_cfg1_vs_torch_fp64():
 
 
 # ---------------------------------------------------------------- peaked logits (the regime of a trained model)
-@pytest.mark.parametrize("route", ROUTES)
-def test_joint_bf16_peaked_logits(route):
+def test_joint_bf16_peaked_logits():
     """w_out scaled x8: |z| reaches ~40, softmax rows are close to one-hot.  Exercises exp2 of large negative
-    arguments, the exact blank / label entries of dz and (zcache) the fp16 range of the logit cache."""
+    arguments and the exact blank / label entries of dz."""
     import emoasr_b200 as E
     from oracle import rnnt_dp
     B, T, U, V, J = 3, 40, 15, 1024, 512
@@ -125,7 +122,7 @@ def test_joint_bf16_peaked_logits(route):
     assert np.abs(z).max() > 30
     r = rnnt_dp.joint_loss_and_grads(enc, dec_, eye, np.zeros(J), eye, np.zeros(J), w_out, b_out, ys, tl, ul)
     te = [T_(a).requires_grad_() for a in (enc, dec_, w_out, b_out)]
-    loss = E.rnnt_joint_loss(*te, T_(ys), T_(tl), T_(ul), blank=0, reduction="mean", precision="bf16", route=route)
+    loss = E.rnnt_joint_loss(*te, T_(ys), T_(tl), T_(ul), blank=0, reduction="mean", precision="bf16")
     loss.backward()
     # |z| ~ 40 with 8-bit-mantissa operands: the logits themselves carry ~0.1 absolute error, i.e. ~1e-3 of a
     # loss of ~1e3 -- still inside the stated tolerance
@@ -146,19 +143,16 @@ RNNT_KEYS = ["dec_num_layers", "dec_hidden_size", "embedding_size", "joint_hidde
              "dropout_dec_rate"]
 
 
-@pytest.mark.parametrize("route", ROUTES)
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 @pytest.mark.parametrize("name", ["ref_rnnt_tcshape_ragged", "ref_rnnt_tcshape_auxctc"])
-def test_rnnt_decoder_tensor_core_shape_vs_reference_golden(name, precision, route):
+def test_rnnt_decoder_tensor_core_shape_vs_reference_golden(name, precision):
     """Goldens of the UNMODIFIED reference at a shape the tensor-core kernels accept (J=128, V=64): the drop-in
     decoder must reproduce them at 1e-5 / 1e-4 in fp32 mode and at the stated bf16 tolerance in bf16 mode (the
     default of dropin.install())."""
     from emoasr_b200.decoders import RNNTDecoder
-    if precision == "fp32" and route == "zcache":
-        pytest.skip("fp32 mode has one route")
     g = load_golden(name)
     dec = RNNTDecoder(_params_from_golden(g, RNNT_KEYS), phase="test")
-    dec.fused_precision, dec.fused_route = precision, route
+    dec.fused_precision = precision
     dec.load_state_dict({k[len("param."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")})
     dec = dec.to(dev()).train()
     eouts = T_(g["eouts"]).requires_grad_()
@@ -203,12 +197,10 @@ def test_ctc_decoder_phone_and_inter_heads_vs_reference_golden(name):
 
 
 # ---------------------------------------------------------------- run-to-run determinism
-@pytest.mark.parametrize("route", ROUTES)
-def test_joint_bf16_repeatability(route):
+def test_joint_bf16_repeatability():
     """50 repeats of the same step: the forward outputs (cost) are bit-identical; the gradients are sums over
     CTAs combined with red.global.add in arrival order, so they may differ in the last bits only (<= 1e-6
-    relative).  A race between roles of the ring kernel / the z-cache kernels would show up here as a large or
-    growing difference."""
+    relative).  A race between roles of the ring kernel would show up here as a large or growing difference."""
     import emoasr_b200 as E
     gen = torch.Generator().manual_seed(3)
     B, T, U, V, J = 6, 120, 40, 1024, 512
@@ -222,7 +214,7 @@ def test_joint_bf16_repeatability(route):
     ref = None
     for it in range(50):
         te = [t.clone().requires_grad_() for t in (enc, dec_, w, bo)]
-        costs = E.rnnt_joint_loss(*te, ys, tl, ul, blank=0, precision="bf16", route=route)
+        costs = E.rnnt_joint_loss(*te, ys, tl, ul, blank=0, precision="bf16")
         costs.mean().backward()
         cur = (costs.detach().clone(), [t.grad.clone() for t in te])
         if ref is None:
@@ -233,23 +225,24 @@ def test_joint_bf16_repeatability(route):
             assert float((a - b_).norm() / b_.norm()) <= 1e-6, (it, k)
 
 
-def test_no_grad_forward_allocates_no_cache():
-    """Validation passes (torch.no_grad) must not allocate the z cache even when route='zcache' is requested."""
+def test_forward_and_backward_keep_nothing_of_size_N_x_V():
+    """Peak device memory of a whole training step stays far below one N x V tensor (even at 2 bytes per entry):
+    the logits are neither cached by the forward nor formed by the backward."""
     import emoasr_b200 as E
     gen = torch.Generator().manual_seed(5)
-    B, T, U, V, J = 4, 100, 30, 1024, 512
+    B, T, U, V, J = 8, 200, 60, 4096, 512
     enc = torch.randn(B, T, J, generator=gen).to(dev()).requires_grad_()
     dec_ = torch.randn(B, U + 1, J, generator=gen).to(dev()).requires_grad_()
     w = (torch.randn(V, J, generator=gen) / J ** 0.5).to(dev()).requires_grad_()
     bo = torch.zeros(V, device=dev(), requires_grad=True)
     ys = torch.randint(1, V, (B, U), generator=gen).to(dev())
     tl, ul = torch.full((B,), T, device=dev()), torch.full((B,), U, device=dev())
-    zbytes = B * 2 * ((T * (U + 1) + 255) // 256) * 128 * V * 2
+    zbytes = B * T * (U + 1) * V * 2
     torch.cuda.synchronize()
     torch.cuda.reset_peak_memory_stats()
     base = torch.cuda.memory_allocated()
-    with torch.no_grad():
-        loss = E.rnnt_joint_loss(enc, dec_, w, bo, ys, tl, ul, reduction="mean", precision="bf16", route="zcache")
+    loss = E.rnnt_joint_loss(enc, dec_, w, bo, ys, tl, ul, reduction="mean", precision="bf16")
+    loss.backward()
     torch.cuda.synchronize()
     assert torch.isfinite(loss)
     assert torch.cuda.max_memory_allocated() - base < zbytes // 2
