@@ -271,6 +271,19 @@ def run_ours_rnnt(args, w, rank, world, dev):
     out = dict(ms_total=ms_total, e2e_s=e2e_s, units=w["B"], clocks=clocks, roofline=None, launches=per_step * args.steps,
                h2d=sum(t.numel() * t.element_size() for t in host), d2h=4, flops=wl.algorithmic_flops(),
                n_valid=wl.n_valid, extra={})
+    if world > 1:
+        # diagnosis of the scaling loss: every rank's step WITHOUT the collective (same kernels, same inputs).  The
+        # synchronised step can never be faster than the slowest GPU's local step.
+        local = rnnt_step_fn(E, wl, args.precision, params, buckets, None, 1)
+        buckets.detach_hooks()
+        for _ in range(3):
+            local(*resident)
+        n = max(5, args.steps // 2)
+        lms = timed_steps(local, resident, n, flush, barrier) / n
+        t = torch.zeros(world, device=dev, dtype=torch.float64)
+        t[rank] = lms
+        dist.all_reduce(t)
+        out["extra"]["per_rank_local_step_ms"] = [round(float(x), 4) for x in t]
     if args.precision == "bf16" and rank == 0:
         out["roofline"] = rnnt_kernel_roofline(args, w, wl, resident, flush, dev)
     return out

@@ -139,10 +139,11 @@ bool joint_ring_supported(int B, int T, int U1, int J, int V);
 size_t joint_ring_workspace(int B, int T, int U1, int J, int V);
 int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec_h, const float* b_out,
                           const int* labels, const int* tlen, const int* ulen, const float* lse, const float* lp2,
-                          const float* gamma2, const float* grad_cost, int B, int T, int U1, int J, int V, int blank,
-                          void* dh_ws, void* ring_ws, float* d_w_out, float* d_b_out, cudaStream_t st);
-int joint_bf16_casts(const float* enc_proj, const float* dec_proj, const float* w_out, int B, int T, int U1, int J,
-                     int V, void* ws, const void** w_bf16, const void** enc_h, const void** dec_h, cudaStream_t st);
+                          const float* gamma2, const float* grad_cost, int B, int T, int U1, int J, int V, int Vout,
+                          int blank, void* dh_ws, void* ring_ws, float* d_w_out, float* d_b_out, cudaStream_t st);
+int joint_bf16_casts(const float* enc_proj, const float* dec_proj, const float* w_out, const float* b_out, int B, int T,
+                     int U1, int J, int V, void* ws, const void** w_bf16, const void** enc_h, const void** dec_h,
+                     const float** b_pad, cudaStream_t st);
 // axis reductions of dh (joint_reduce.cu)
 int joint_reduce_dh_launch(const void* dh_ws, const float* enc_proj, const float* dec_proj, const int* tlen,
                            const int* ulen, int B, int T, int U1, int J, float* d_enc_proj, float* d_dec_proj,

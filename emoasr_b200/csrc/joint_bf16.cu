@@ -412,12 +412,14 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
                     ((uintptr_t)dec_proj & 15) == 0 && ((uintptr_t)w_out & 15) == 0,
                 EMO_BAD_ARG, "joint_fwd(bf16): pointers must be 16-byte (workspace 256-byte) aligned");
     const void *w_bf16, *enc_h, *dec_h;
-    rc = joint_bf16_casts(enc_proj, dec_proj, w_out, B, T, U1, J, V, ws, &w_bf16, &enc_h, &dec_h, st);
+    const float* b_pad;
+    rc = joint_bf16_casts(enc_proj, dec_proj, w_out, b_out, B, T, U1, J, V, ws, &w_bf16, &enc_h, &dec_h, &b_pad, st);
     if (rc) return rc;
+    const int Vp = padded_vocab(V);   // pad columns: zero weights, bias -1e30 (contribute nothing to the LSE)
 
     const int KB = J / kBlockK;
     CUtensorMap tmap;
-    rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)V, kBlockK, kBRows);
+    rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)Vp, kBlockK, kBRows);
     if (rc) return rc;
     const int tiles = B * ceil_div((size_t)T * U1, kCtas * kTileM);
     const int ctas = kCtas * min(tiles, sm_count() / kCtas);
@@ -435,8 +437,8 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     attr[0].val.clusterDim.x = kCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    EMO_CUDA(cudaLaunchKernelEx(&cfg, joint_fwd_kernel, tmap, (const __half*)enc_h, (const __half*)dec_h, b_out, labels,
-                                tlen, ulen, B, T, U1, J, V, blank, lp2, lse));
+    EMO_CUDA(cudaLaunchKernelEx(&cfg, joint_fwd_kernel, tmap, (const __half*)enc_h, (const __half*)dec_h, b_pad, labels,
+                                tlen, ulen, B, T, U1, J, Vp, blank, lp2, lse));
     EMO_CHECK_LAUNCH("joint_fwd_kernel");
     return EMO_OK;
 }

@@ -70,7 +70,8 @@ struct RingArgs {
     int* flags;                 // z_ready[NZ] z_done[NZ] h_ready[NH] h_done[NH]
     float* d_w_out;
     float* d_b_out;
-    int B, T, U1, J, V, blank;
+    int B, T, U1, J, V, blank;   // V = vocabulary padded to a multiple of 32 (pad rows of w_out are 0, pad bias -1e30)
+    int Vout;                    // rows of d_w_out / entries of d_b_out (the caller's vocabulary)
     int nP, nD, nS;             // pairs: producers, dh consumers, dW splits (x roles_v pairs)
     int NZ, NH, G;              // ring slots, vocab groups per tile
 };
@@ -1017,7 +1018,7 @@ __device__ __forceinline__ void role_dw(const RingArgs& a, const CUtensorMap* tm
         if (lane < 8) {
 #pragma unroll
             for (int e = 0; e < 8; ++e)
-                if (vb + e < a.V && colsum[e] != 0.f) atomicAdd(a.d_b_out + vb + e, colsum[e]);
+                if (vb + e < a.Vout && colsum[e] != 0.f) atomicAdd(a.d_b_out + vb + e, colsum[e]);
         }
         // ---- flush dW: TMEM lane = vocab row, columns = hidden units
         const int dw = warp - 4;
@@ -1033,7 +1034,7 @@ __device__ __forceinline__ void role_dw(const RingArgs& a, const CUtensorMap* tm
                 uint32_t r[32];
                 tmem_ld_32x32b_x32(tmem_base + lane_base + col_base + g * 32, r);
                 tmem_wait_ld();
-                if (v < a.V) {
+                if (v < a.Vout) {
                     float* dst = a.d_w_out + (size_t)v * a.J + col_base + g * 32;
 #pragma unroll
                     for (int i = 0; i < 32; i += 4)
@@ -1129,12 +1130,12 @@ int ring_max_pairs(size_t smem) {
 }  // namespace
 
 bool joint_ring_supported(int B, int T, int U1, int J, int V) {
-    return B <= kMaxB && T < 65536 && U1 < 65536 && J % 128 == 0 && J <= kMaxKBlocks * kBlockK && V % 32 == 0 &&
+    return B <= kMaxB && T < 65536 && U1 < 65536 && J % 128 == 0 && J <= kMaxKBlocks * kBlockK && V > 0 &&
            ring_smem_bytes(B, J) <= (size_t)kSmemLimit;
 }
 
 size_t joint_ring_workspace(int B, int T, int U1, int J, int V) {
-    const RingGeom g = ring_geom(B, J, V);
+    const RingGeom g = ring_geom(B, J, padded_vocab(V));
     return g.z_bytes + g.h_bytes + g.flag_bytes + g.prefix_bytes;
 }
 
@@ -1159,10 +1160,10 @@ void ring_split(int pairs, int V, int& nP, int& nD, int& nS) {
 
 int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec_h, const float* b_out,
                           const int* labels, const int* tlen, const int* ulen, const float* lse, const float* lp2,
-                          const float* gamma2, const float* grad_cost, int B, int T, int U1, int J, int V, int blank,
-                          void* dh_ws, void* ring_ws, float* d_w_out, float* d_b_out, cudaStream_t st) {
+                          const float* gamma2, const float* grad_cost, int B, int T, int U1, int J, int V, int Vout,
+                          int blank, void* dh_ws, void* ring_ws, float* d_w_out, float* d_b_out, cudaStream_t st) {
     EMO_REQUIRE(joint_ring_supported(B, T, U1, J, V), EMO_UNSUPPORTED_SHAPE,
-                "joint_bwd(bf16, ring): needs B <= %d, J %% 128 == 0, J <= 512, V %% 32 == 0", kMaxB);
+                "joint_bwd(bf16, ring): needs B <= %d, J %% 128 == 0, J <= 512", kMaxB);
     const RingGeom g = ring_geom(B, J, V);
     char* zring = (char*)ring_ws;
     char* hring = zring + g.z_bytes;
@@ -1177,7 +1178,7 @@ int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec
     a.enc = (const __half*)enc_h; a.dec = (const __half*)dec_h; a.b_out = b_out; a.labels = labels;
     a.lse = lse; a.lp2 = lp2; a.gamma2 = gamma2; a.grad_cost = grad_cost; a.prefix = prefix; a.flags = flags;
     a.d_w_out = d_w_out; a.d_b_out = d_b_out;
-    a.B = B; a.T = T; a.U1 = U1; a.J = J; a.V = V; a.blank = blank;
+    a.B = B; a.T = T; a.U1 = U1; a.J = J; a.V = V; a.Vout = Vout; a.blank = blank;
     ring_split(pairs, V, a.nP, a.nD, a.nS);
     a.NZ = g.NZ; a.NH = g.NH; a.G = g.G;
 
@@ -1217,8 +1218,9 @@ int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec
 
 // ---- workspace / launch accounting of the bf16 joint (include/emoasr_b200.h) ---------------------
 static size_t casts_bytes(int B, int T, int U1, int J, int V) {
-    return align_up((size_t)V * J * sizeof(__nv_bfloat16), 256) + align_up((size_t)B * T * J * sizeof(__half), 256) +
-           align_up((size_t)B * U1 * J * sizeof(__half), 256);
+    const size_t Vp = (size_t)padded_vocab(V);
+    return align_up(Vp * J * sizeof(__nv_bfloat16), 256) + align_up((size_t)B * T * J * sizeof(__half), 256) +
+           align_up((size_t)B * U1 * J * sizeof(__half), 256) + align_up(Vp * sizeof(float), 256);
 }
 
 size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V) {
@@ -1233,21 +1235,43 @@ size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V) {
 }
 
 int joint_bf16_launches(int op, int B, int T, int U1, int J, int V) {
-    (void)B; (void)T; (void)U1; (void)J; (void)V;
-    if (op == EMO_OP_RNNT_JOINT_BWD) return 6;  // 3 casts, ring prep, ring kernel, axis reductions
-    return 4;                                    // weight cast, 2 stream casts, fused joint forward
+    (void)B; (void)T; (void)U1; (void)J;
+    const int pad = padded_vocab(V) != V;        // + vocabulary padding kernel
+    if (op == EMO_OP_RNNT_JOINT_BWD) return 6 + pad;  // 3 casts, ring prep, ring kernel, axis reductions
+    return 4 + pad;                                    // weight cast, 2 stream casts, fused joint forward
 }
 
 // casts shared by forward and backward: w_out -> bf16, enc_proj / dec_proj -> fp16 (11-bit mantissa, half the
 // gather bytes of fp32); layout of the head of every bf16 workspace
-int joint_bf16_casts(const float* enc_proj, const float* dec_proj, const float* w_out, int B, int T, int U1, int J,
-                     int V, void* ws, const void** w_bf16, const void** enc_h, const void** dec_h, cudaStream_t st) {
+// Vocabulary sizes that are not a multiple of 32 (e.g. the reference's 10872 / 9798 SentencePiece vocabularies) run
+// on a padded copy: pad rows of the bf16 w_out are zero and the pad entries of the bias copy are -1e30, so the pad
+// logits contribute exp2(-huge) = 0 to every log-sum-exp and get dz = 0.
+__global__ void pad_vocab_kernel(__nv_bfloat16* __restrict__ w_tail, size_t n_tail, const float* __restrict__ b_out,
+                                 float* __restrict__ b_pad, int V, int Vp) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tail) w_tail[i] = __float2bfloat16_rn(0.f);
+    if (i < (size_t)Vp) b_pad[i] = i < (size_t)V ? b_out[i] : -1e30f;
+}
+
+int joint_bf16_casts(const float* enc_proj, const float* dec_proj, const float* w_out, const float* b_out, int B, int T,
+                     int U1, int J, int V, void* ws, const void** w_bf16, const void** enc_h, const void** dec_h,
+                     const float** b_pad, cudaStream_t st) {
+    const int Vp = padded_vocab(V);
     const size_t nw = (size_t)V * J, ne = (size_t)B * T * J, nd = (size_t)B * U1 * J;
     __nv_bfloat16* w = reinterpret_cast<__nv_bfloat16*>(ws);
-    __half* e = reinterpret_cast<__half*>((char*)ws + align_up(nw * sizeof(__nv_bfloat16), 256));
+    __half* e = reinterpret_cast<__half*>((char*)ws + align_up((size_t)Vp * J * sizeof(__nv_bfloat16), 256));
     __half* d = reinterpret_cast<__half*>((char*)e + align_up(ne * sizeof(__half), 256));
+    float* bp = reinterpret_cast<float*>((char*)d + align_up(nd * sizeof(__half), 256));
     f32_to_bf16_kernel<<<ceil_div(nw, 4 * 256), 256, 0, st>>>(w_out, w, nw);
     EMO_CHECK_LAUNCH("f32_to_bf16_kernel");
+    if (Vp != V) {
+        const size_t n_tail = (size_t)(Vp - V) * J;
+        pad_vocab_kernel<<<ceil_div(max(n_tail, (size_t)Vp), 256), 256, 0, st>>>(w + nw, n_tail, b_out, bp, V, Vp);
+        EMO_CHECK_LAUNCH("pad_vocab_kernel");
+        *b_pad = bp;
+    } else {
+        *b_pad = b_out;
+    }
     if (enc_h) {
         f32_to_f16_kernel<<<ceil_div(ne, 4 * 256), 256, 0, st>>>(enc_proj, e, ne);
         f32_to_f16_kernel<<<ceil_div(nd, 4 * 256), 256, 0, st>>>(dec_proj, d, nd);
@@ -1281,10 +1305,11 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     EMO_CUDA(cudaMemsetAsync(d_b_out, 0, (size_t)V * sizeof(float), st));
     EMO_CUDA(cudaMemsetAsync(d_dec_proj, 0, (size_t)B * U1 * J * sizeof(float), st));
     const void *w_bf16, *enc_h, *dec_h;
-    rc = joint_bf16_casts(enc_proj, dec_proj, w_out, B, T, U1, J, V, ws, &w_bf16, &enc_h, &dec_h, st);
+    const float* b_pad;
+    rc = joint_bf16_casts(enc_proj, dec_proj, w_out, b_out, B, T, U1, J, V, ws, &w_bf16, &enc_h, &dec_h, &b_pad, st);
     if (rc) return rc;
-    rc = joint_bwd_ring_launch(w_bf16, enc_h, dec_h, b_out, labels, tlen, ulen, lse, lp2, gamma2, grad_cost, B, T, U1,
-                               J, V, blank, dh_ws, ring_ws, d_w_out, d_b_out, st);
+    rc = joint_bwd_ring_launch(w_bf16, enc_h, dec_h, b_pad, labels, tlen, ulen, lse, lp2, gamma2, grad_cost, B, T, U1,
+                               J, padded_vocab(V), V, blank, dh_ws, ring_ws, d_w_out, d_b_out, st);
     if (rc) return rc;
     return joint_reduce_dh_launch(dh_ws, enc_proj, dec_proj, tlen, ulen, B, T, U1, J, d_enc_proj, d_dec_proj, st);
 }

@@ -20,6 +20,9 @@ constexpr int kSmemLimit = 232448;                    // 227 KiB opt-in maximum 
 constexpr float kLog2e = 1.4426950408889634f;
 constexpr float kLn2 = 0.6931471805599453f;
 
+// the tensor-core kernels work on a vocabulary padded to a multiple of 32 (joint_bf16_casts)
+__host__ __device__ inline int padded_vocab(int V) { return (V + 31) / 32 * 32; }
+
 struct TileInfo {
     int b, first_cell, n_cells, U1b;  // n_cells = valid cells of the utterance
 };
@@ -126,8 +129,6 @@ int check_bf16_shape(int B, int T, int U1, int J, int V, int blank) {
     EMO_REQUIRE(J % 128 == 0 && J <= kMaxKBlocks * kBlockK, EMO_UNSUPPORTED_SHAPE,
                 "joint(bf16): joint_hidden_size %d must be a multiple of 128 and <= 512 "
                 "(use precision fp32 for other sizes)", J);
-    EMO_REQUIRE(V % 32 == 0, EMO_UNSUPPORTED_SHAPE,
-                "joint(bf16): vocab %d must be a multiple of 32 (use precision fp32)", V);
     EMO_REQUIRE((long long)B * T * J < (1ll << 31) && (long long)B * U1 * J < (1ll << 31),
                 EMO_UNSUPPORTED_SHAPE, "joint(bf16): projected streams exceed 2^31 elements");
     return EMO_OK;

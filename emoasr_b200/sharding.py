@@ -124,6 +124,8 @@ class GradBuckets:
         for bi, bucket in enumerate(self.buckets):
             for p in bucket:
                 def hook(_p, bi=bi, n=len(bucket)):
+                    if not self._hooked:
+                        return
                     self._ready[bi] += 1
                     if self._ready[bi] == n:
                         self._ready[bi] = 0
@@ -131,6 +133,10 @@ class GradBuckets:
                                                group=self.group, async_op=True)
                         self._pending.append((None, None, self.flats[bi], work, avg is not None))
                 p.register_post_accumulate_grad_hook(hook)
+
+    def detach_hooks(self):
+        """The hooks stay registered but stop launching collectives (rank-local steps)."""
+        self._hooked = False
 
     def start_extra(self, flat):
         """All-reduce (average) of a flat buffer that is not tied to parameters of this process' graph (e.g. the

@@ -69,7 +69,8 @@ size_t emo_workspace_bytes(int op, int precision, int B, int T, int U1, int J, i
 int emo_launch_count(int op, int precision, int B, int T, int U1, int J, int V);
 
 /* 1 if emo_rnnt_joint_fwd / _bwd support these sizes for this precision, else 0.  Host call.  EMO_PREC_FP32
- * supports every shape; EMO_PREC_BF16 needs J % 128 == 0, J <= 512, V % 32 == 0, B <= 1024, T and U1 < 65536. */
+ * supports every shape; EMO_PREC_BF16 needs J % 128 == 0, J <= 512, B <= 1024, T and U1 < 65536 (any vocabulary
+ * size: one that is not a multiple of 32 is padded inside the workspace, zero weights / -1e30 bias). */
 int emo_rnnt_joint_supported(int precision, int B, int T, int U1, int J, int V);
 
 /* ---- RNN-T lattice on gathered pairs ---------------------------------------------------------

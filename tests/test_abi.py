@@ -51,3 +51,18 @@ def test_ops_refuse_cpu_tensors():
         E.ctc_loss(torch.zeros(1, 2, 3), torch.zeros(1, 1, dtype=torch.long), torch.tensor([2]), torch.tensor([1]))
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         E.rnnt_loss(torch.zeros(1, 2, 2, 3), torch.zeros(1, 1, dtype=torch.int32), torch.tensor([2]), torch.tensor([1]))
+
+
+def test_shape_support_query():
+    """Host-only: the tensor-core mode accepts any vocabulary size (the reference's 10872 / 9798 are not multiples of
+    32: padded inside the workspace) but needs J % 128 == 0 and J <= 512; fp32 mode accepts everything."""
+    import emoasr_b200.functional as F
+    assert F.joint_supported("bf16", 8, 249, 61, 512, 10872)
+    assert F.joint_supported("bf16", 8, 249, 61, 256, 9798)
+    assert not F.joint_supported("bf16", 8, 249, 61, 640, 1024)
+    assert not F.joint_supported("bf16", 8, 249, 61, 320, 1024)
+    assert F.joint_supported("fp32", 8, 249, 61, 640, 1000)
+    # the padded vocabulary needs a slightly larger workspace than the next smaller multiple of 32
+    a = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_BWD, _lib.PREC_BF16, 2, 20, 8, 128, 96)
+    b = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_BWD, _lib.PREC_BF16, 2, 20, 8, 128, 100)
+    assert b > a

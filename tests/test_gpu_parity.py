@@ -299,6 +299,8 @@ BF16_SHAPES = [
     (3, 40, 15, 1024, 512),   # cfg-3 vocabulary / joint width, several tiles per CTA
     (2, 150, 30, 512, 256),   # many tiles
     (1, 24, 10, 4096, 512),   # cfg-4 vocabulary: 16 vocab roles in the dW kernel, 64 K blocks per tile in dh
+    (2, 12, 6, 100, 128),     # vocabulary not a multiple of 32: padded inside the workspace (zero weights, -1e30 bias)
+    (2, 14, 5, 1087, 256),    # odd vocabulary spanning several chunks (the reference's 10872 / 9798 are of this kind)
 ]
 
 

@@ -16,7 +16,6 @@ ap.add_argument("--V", type=int, default=1024)
 ap.add_argument("--J", type=int, default=512)
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--precision", default="bf16")
-ap.add_argument("--route", default="ring")
 ap.add_argument("--no-backward", action="store_true")
 ap.add_argument("--ctc", action="store_true")
 a = ap.parse_args()
@@ -41,7 +40,7 @@ else:
     tl = torch.full((a.B,), a.T, device=dev)
     ul = torch.full((a.B,), a.U, device=dev)
     for _ in range(a.iters):
-        loss = E.rnnt_joint_loss(enc, dec, w, b, ys, tl, ul, reduction="mean", precision=a.precision, route=a.route)
+        loss = E.rnnt_joint_loss(enc, dec, w, b, ys, tl, ul, reduction="mean", precision=a.precision)
         if not a.no_backward:
             loss.backward()
 torch.cuda.synchronize()
