@@ -67,3 +67,20 @@ class CTCLoss(nn.Module):
     def forward(self, log_probs, targets, input_lengths, target_lengths):
         """log_probs (T,B,V) as nn.CTCLoss takes them."""
         return self.from_logits(log_probs.transpose(0, 1), targets, input_lengths, target_lengths)
+
+
+class CTCHeadLoss(nn.Module):
+    """Output Linear + log_softmax + CTC loss in one fused op (asr/modeling/decoders/ctc.py:103-113: ``logits =
+    self.output(eouts)`` ... ``ctc_loss_fn(...) / B``); the (B,T,V) logits are never formed.  Takes the head's
+    parameters at call time so that the module owning them (``CTCDecoder.output``) keeps its state-dict keys."""
+
+    def __init__(self, blank=0, zero_infinity=True, normalize_batch=True):
+        super().__init__()
+        self.blank = blank
+        self.zero_infinity = zero_infinity
+        self.normalize_batch = normalize_batch   # the reference's "/ logits.size(0)" (ctc.py:111-113)
+
+    def forward(self, eouts, weight, bias, ys, elens, ylens):
+        nll = F.ctc_head_loss(eouts, weight, bias, ys, elens, ylens, blank=self.blank,
+                              zero_infinity=self.zero_infinity)
+        return nll.sum() / eouts.size(0) if self.normalize_batch else nll.sum()

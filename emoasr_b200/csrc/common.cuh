@@ -140,7 +140,11 @@ size_t joint_ring_workspace(int B, int T, int U1, int J, int V);
 int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec_h, const float* b_out,
                           const int* labels, const int* tlen, const int* ulen, const float* lse, const float* lp2,
                           const float* gamma2, const float* grad_cost, int B, int T, int U1, int J, int V, int Vout,
-                          int blank, void* dh_ws, void* ring_ws, float* d_w_out, float* d_b_out, cudaStream_t st);
+                          int blank, int plain, void* dh_ws, void* ring_ws, float* d_w_out, float* d_b_out,
+                          cudaStream_t st);
+int joint_fwd_launch(const void* w_bf16, const void* enc_h, const void* dec_h, const float* b_pad, const int* labels,
+                     const int* tlen, const int* ulen, int B, int T, int U1, int J, int Vp, int blank, float* lp2,
+                     float* lse, int plain, cudaStream_t st);
 int joint_bf16_casts(const float* enc_proj, const float* dec_proj, const float* w_out, const float* b_out, int B, int T,
                      int U1, int J, int V, void* ws, const void** w_bf16, const void** enc_h, const void** dec_h,
                      const float** b_pad, cudaStream_t st);
@@ -148,6 +152,9 @@ int joint_bf16_casts(const float* enc_proj, const float* dec_proj, const float* 
 int joint_reduce_dh_launch(const void* dh_ws, const float* enc_proj, const float* dec_proj, const int* tlen,
                            const int* ulen, int B, int T, int U1, int J, float* d_enc_proj, float* d_dec_proj,
                            cudaStream_t st);
+int ctc_lattice_launch(const long long* labels, const long long* tlen, const long long* ulen, int B, int T, int V,
+                       int Umax, int blank, int zero_infinity, float* alpha_ws, float* beta_ws, float* nll,
+                       cudaStream_t st);
 size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V);
 int joint_bf16_launches(int op, int B, int T, int U1, int J, int V);
 

@@ -105,7 +105,7 @@ ctc_row_lse_kernel(const float* __restrict__ logits, const long long* __restrict
         // scalar path (vocabulary not a multiple of 4)
         for (int r = warp_global; r < rows; r += warp_stride) {
             const int b = r / T, t = r - b * T;
-            if (t >= tlen[b]) {
+            if (t >= max(tlen[b], 1LL)) {   // same clamp as the lattice / gradient kernels (T_b >= 1)
                 if (lane == 0) lse[r] = 0.f;
                 continue;  // warp-uniform
             }
@@ -135,7 +135,7 @@ ctc_row_lse_kernel(const float* __restrict__ logits, const long long* __restrict
             nr += warp_stride;
             if (nr >= rows) return false;
             const int bb = nr / T;
-            if (nr - bb * T >= tlen[bb]) {            // padded frame: no log-probs needed
+            if (nr - bb * T >= max(tlen[bb], 1LL)) {  // padded frame: no log-probs needed (T_b clamped to >= 1)
                 if (lane == 0) lse[nr] = 0.f;
                 continue;
             }
@@ -478,7 +478,7 @@ __global__ void ctc_gather_kernel(const float* __restrict__ logits, const long l
         long long U_bl = ulen[b];
         const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
         const int S_b = 2 * U_b + 1;
-        if (t < tlen[b] && st < S_b)
+        if (t < max(tlen[b], 1LL) && st < S_b)
             lp_out[idx] = __ldg(logits + r * V + ext_state(labels + (size_t)b * Umax, st, S_b, blank, V).label) - lse[r];
     }
 }
@@ -496,6 +496,22 @@ int check_ctc_args(const void* logits, const void* labels, const void* tlen, con
 }
 
 }  // namespace
+}  // namespace emo
+
+namespace emo {
+// alpha (and, with beta_ws, beta) lattices over emissions already staged in alpha_ws / beta_ws (ctc_head.cu)
+int ctc_lattice_launch(const long long* labels, const long long* tlen, const long long* ulen, int B, int T, int V,
+                       int Umax, int blank, int zero_infinity, float* alpha_ws, float* beta_ws, float* nll,
+                       cudaStream_t st) {
+    EMO_REQUIRE(2 * Umax + 1 <= 1024, EMO_UNSUPPORTED_SHAPE, "ctc: 2*Umax+1 = %d exceeds 1024 extended states",
+                2 * Umax + 1);
+    const int S = 2 * Umax + 1;
+    const int threads = (S + 31) / 32 * 32;
+    ctc_lattice_kernel<<<dim3(B, beta_ws ? 2 : 1), threads, 0, st>>>(labels, tlen, ulen, T, V, Umax, blank,
+                                                                      zero_infinity, 0, alpha_ws, beta_ws, nll);
+    EMO_CHECK_LAUNCH("ctc_lattice_kernel");
+    return EMO_OK;
+}
 }  // namespace emo
 
 using namespace emo;

@@ -109,7 +109,7 @@ template <int N> __device__ __forceinline__ void reg_inc() {
 // with packed-half add and tanh.approx.f16x2, rounded to bf16 into the canonical K-major SW128 layout
 // (16-byte chunk index XOR (row mod 8)).
 __device__ __forceinline__ void produce_h_block16(const uint4 (&re)[4], const uint4 (&rd)[4], int pw, int rsub,
-                                                  int c, uint8_t* blk) {
+                                                  int c, uint8_t* blk, bool plain) {
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         const int row = pw * 16 + p * 4 + rsub;
@@ -118,7 +118,7 @@ __device__ __forceinline__ void produce_h_block16(const uint4 (&re)[4], const ui
         uint32_t o[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float2 f = unpack_f16x2(tanh_f16x2(hadd2_u32(e[q], d[q])));
+            const float2 f = unpack_f16x2(plain ? e[q] : tanh_f16x2(hadd2_u32(e[q], d[q])));
             o[q] = pack_bf16x2(f.x, f.y);
         }
         uint8_t* dst = blk + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
@@ -126,6 +126,9 @@ __device__ __forceinline__ void produce_h_block16(const uint4 (&re)[4], const ui
     }
 }
 
+// kPlain (the CTC head, ctc_head.cu): the A operand is the enc stream itself (h = enc, no dec stream, no tanh);
+// the caller passes U1 = 1 and ulen = 0, so a "cell" is a frame.
+template <bool kPlain>
 __global__ void __launch_bounds__(kFwdThreads, 1)
 joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __restrict__ enc,
                  const __half* __restrict__ dec, const float* __restrict__ b_out,
@@ -353,7 +356,8 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __res
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 re[p] = __ldg(reinterpret_cast<const uint4*>(enc + eoff[p] + lunit * kBlockK));
-                rd[p] = __ldg(reinterpret_cast<const uint4*>(dec + doff[p] + lunit * kBlockK));
+                rd[p] = kPlain ? make_uint4(0u, 0u, 0u, 0u)
+                               : __ldg(reinterpret_cast<const uint4*>(dec + doff[p] + lunit * kBlockK));
             }
             ++lunit;
             return true;
@@ -365,7 +369,7 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __res
             EMO_PROF(q_c = clock64();)
             mbar_wait(smem_u32(&bars->a_empty[wkb]), (wtl & 1) ^ 1);
             EMO_PROF(q_wait += clock64() - q_c; q_c = clock64();)
-            produce_h_block16(re, rd, pw, rsub, c, sA + (size_t)wkb * kABlockBytes);
+            produce_h_block16(re, rd, pw, rsub, c, sA + (size_t)wkb * kABlockBytes, kPlain);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) mbar_arrive_cluster(a_full0 + wkb * 8);
@@ -398,6 +402,37 @@ joint_fwd_kernel(const __grid_constant__ CUtensorMap tmap_w, const __half* __res
 
 }  // namespace
 
+// the kernel on prepared operands: bf16 w_out (Vp rows), fp16 streams, bias of Vp entries (joint_bf16_casts)
+int joint_fwd_launch(const void* w_bf16, const void* enc_h, const void* dec_h, const float* b_pad, const int* labels,
+                     const int* tlen, const int* ulen, int B, int T, int U1, int J, int Vp, int blank, float* lp2,
+                     float* lse, int plain, cudaStream_t st) {
+    const int KB = J / kBlockK;
+    CUtensorMap tmap;
+    int rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)Vp, kBlockK, kBRows);
+    if (rc) return rc;
+    const int tiles = B * ceil_div((size_t)T * U1, kCtas * kTileM);
+    const int ctas = kCtas * min(tiles, sm_count() / kCtas);
+    const size_t smem = (size_t)KB * kABlockBytes + (size_t)kBStages * kBBytes + sizeof(FwdBarriers) +
+                        2 * kChunkN * sizeof(float) + kTileM * sizeof(float4);
+    EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_fwd(bf16): shared memory");
+    auto kern = plain ? joint_fwd_kernel<true> : joint_fwd_kernel<false>;
+    EMO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctas);
+    cfg.blockDim = dim3(kFwdThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = kCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    EMO_CUDA(cudaLaunchKernelEx(&cfg, kern, tmap, (const __half*)enc_h, (const __half*)dec_h, b_pad, labels,
+                                tlen, ulen, B, T, U1, J, Vp, blank, lp2, lse));
+    EMO_CHECK_LAUNCH("joint_fwd_kernel");
+    return EMO_OK;
+}
+
 int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
                    const float* b_out, const int* labels, const int* tlen, const int* ulen, int B,
                    int T, int U1, int J, int V, int blank, float* lp2, float* lse, void* ws, size_t ws_bytes,
@@ -415,32 +450,9 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     const float* b_pad;
     rc = joint_bf16_casts(enc_proj, dec_proj, w_out, b_out, B, T, U1, J, V, ws, &w_bf16, &enc_h, &dec_h, &b_pad, st);
     if (rc) return rc;
-    const int Vp = padded_vocab(V);   // pad columns: zero weights, bias -1e30 (contribute nothing to the LSE)
-
-    const int KB = J / kBlockK;
-    CUtensorMap tmap;
-    rc = make_tmap_bf16_2d(&tmap, w_bf16, (uint64_t)J, (uint64_t)Vp, kBlockK, kBRows);
-    if (rc) return rc;
-    const int tiles = B * ceil_div((size_t)T * U1, kCtas * kTileM);
-    const int ctas = kCtas * min(tiles, sm_count() / kCtas);
-    const size_t smem = (size_t)KB * kABlockBytes + (size_t)kBStages * kBBytes + sizeof(FwdBarriers) +
-                        2 * kChunkN * sizeof(float) + kTileM * sizeof(float4);
-    EMO_REQUIRE(smem <= (size_t)kSmemLimit, EMO_UNSUPPORTED_SHAPE, "joint_fwd(bf16): shared memory");
-    EMO_CUDA(cudaFuncSetAttribute(joint_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(ctas);
-    cfg.blockDim = dim3(kFwdThreads);
-    cfg.dynamicSmemBytes = smem;
-    cfg.stream = st;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = kCtas; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr;
-    cfg.numAttrs = 1;
-    EMO_CUDA(cudaLaunchKernelEx(&cfg, joint_fwd_kernel, tmap, (const __half*)enc_h, (const __half*)dec_h, b_pad, labels,
-                                tlen, ulen, B, T, U1, J, Vp, blank, lp2, lse));
-    EMO_CHECK_LAUNCH("joint_fwd_kernel");
-    return EMO_OK;
+    // pad columns of the vocabulary: zero weights, bias -1e30 (contribute nothing to the LSE)
+    return joint_fwd_launch(w_bf16, enc_h, dec_h, b_pad, labels, tlen, ulen, B, T, U1, J, padded_vocab(V), blank, lp2,
+                            lse, 0, st);
 }
 
 }  // namespace emo

@@ -72,6 +72,7 @@ struct RingArgs {
     float* d_b_out;
     int B, T, U1, J, V, blank;   // V = vocabulary padded to a multiple of 32 (pad rows of w_out are 0, pad bias -1e30)
     int Vout;                    // rows of d_w_out / entries of d_b_out (the caller's vocabulary)
+    int plain;                   // CTC head (ctc_head.cu): h = enc (no dec stream, no tanh), dz = g softmax(z), no patches
     int nP, nD, nS;             // pairs: producers, dh consumers, dW splits (x roles_v pairs)
     int NZ, NH, G;              // ring slots, vocab groups per tile
 };
@@ -208,9 +209,13 @@ __device__ __forceinline__ void p_load_raw(PRaw& r, const PTile& ti, int m, cons
         const size_t cell = ((size_t)ti.b * a.T + t) * a.U1 + u;
         r.valid = 1;
         r.g = __ldg(a.grad_cost + ti.b);
+        r.lse = __ldg(a.lse + cell);
+        if (a.plain) {   // dz = g softmax(z): unit weight, the blank / label patches are switched off by the caller
+            r.gm = make_float2(1.f, 0.f);
+            return;
+        }
         r.gm = __ldg(reinterpret_cast<const float2*>(a.gamma2) + cell);
         r.lp = __ldg(reinterpret_cast<const float2*>(a.lp2) + cell);
-        r.lse = __ldg(a.lse + cell);
         if (u < ti.U1b - 1) r.lab = __ldg(a.labels + (size_t)ti.b * (a.U1 - 1) + u);
     }
 }
@@ -285,7 +290,7 @@ __device__ __forceinline__ void dz_group(const uint32_t (&r)[32], const float* _
 
 // A-operand producer: this warp's 16 rows of the 128-row tile, one 64-wide K block (see joint_bf16.cu)
 __device__ __forceinline__ void produce_h16(const uint4 (&re)[4], const uint4 (&rd)[4], int pw, int rsub, int c,
-                                            uint8_t* blk) {
+                                            uint8_t* blk, bool plain) {
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
         const int row = pw * 16 + p * 4 + rsub;
@@ -294,7 +299,7 @@ __device__ __forceinline__ void produce_h16(const uint4 (&re)[4], const uint4 (&
         uint32_t o[4];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-            const float2 f = unpack_f16x2(tanh_f16x2(hadd2_u32(e[q], d[q])));
+            const float2 f = unpack_f16x2(plain ? e[q] : tanh_f16x2(hadd2_u32(e[q], d[q])));
             o[q] = pack_bf16x2(f.x, f.y);
         }
         uint8_t* dst = blk + (row >> 3) * 1024 + (row & 7) * 128 + ((c ^ (row & 7)) << 4);
@@ -452,6 +457,7 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
         uint8_t* zbuf0 = sZst + (warp - 4) * kZStBufs * kZStBytes;   // alternating blocks (g & 1)
         const uint32_t acc_empty0 = mapa_shared(smem_u32(&bars->acc_empty[0]), 0);
         uint32_t cc = 0;
+        const int pblank = a.plain ? -1 : a.blank;   // plain: no blank patch
         int pending = -1;                      // z slot whose stores have been issued but not yet published
         EMO_PROF(long long p_sig = 0, p_gate = 0, p_accw = 0, p_t0 = clock64(), p_rd = 0, p_st = 0, p_bar = 0, p_ldw = 0;)
         float nb = etid < a.V ? __ldg(a.b_out + etid) * kLog2e : 0.f;   // bias * log2e (see dz_group)
@@ -512,12 +518,12 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
                         tmem_wait_ld();
                         EMO_PROF(p_ldw += clock64() - p_cl;)
                         if (g + 1 < g1) tmem_ld_32x32b_x32(taddr + (g + 1) * 32, rb);
-                        dz_group(ra, bias + g * 32, nc * kChunkN + g * 32, cur, anyneg, a.blank, tm_zst, zbuf0,
+                        dz_group(ra, bias + g * 32, nc * kChunkN + g * 32, cur, anyneg, pblank, tm_zst, zbuf0,
                                  zcol0 + g * 32, zrow, lane, g < gl EMO_PROF(, p_rd, p_st));
                         if (g + 1 < g1) {
                             tmem_wait_ld();
                             if (g + 2 < g1) tmem_ld_32x32b_x32(taddr + (g + 2) * 32, ra);
-                            dz_group(rb, bias + (g + 1) * 32, nc * kChunkN + (g + 1) * 32, cur, anyneg, a.blank, tm_zst,
+                            dz_group(rb, bias + (g + 1) * 32, nc * kChunkN + (g + 1) * 32, cur, anyneg, pblank, tm_zst,
                                      zbuf0 + kZStBytes, zcol0 + (g + 1) * 32, zrow, lane, g + 1 < gl EMO_PROF(, p_rd, p_st));
                         }
                     }
@@ -563,7 +569,8 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
 #pragma unroll
             for (int p = 0; p < 4; ++p) {
                 re[p] = __ldg(reinterpret_cast<const uint4*>(a.enc + eoff[p] + lunit * kBlockK));
-                rd[p] = __ldg(reinterpret_cast<const uint4*>(a.dec + doff[p] + lunit * kBlockK));
+                rd[p] = a.plain ? make_uint4(0u, 0u, 0u, 0u)
+                                : __ldg(reinterpret_cast<const uint4*>(a.dec + doff[p] + lunit * kBlockK));
             }
             ++lunit;
             return true;
@@ -572,7 +579,7 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
         const uint32_t a_full0 = mapa_shared(smem_u32(&bars->a_full[0]), 0);
         auto work = [&](const uint4 (&re)[4], const uint4 (&rd)[4]) {
             mbar_wait(smem_u32(&bars->a_empty[wkb]), (wtl & 1) ^ 1);
-            produce_h16(re, rd, pw, rsub, c, sA + (size_t)wkb * kABlockBytes);
+            produce_h16(re, rd, pw, rsub, c, sA + (size_t)wkb * kABlockBytes, a.plain != 0);
             fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) {
@@ -1161,7 +1168,8 @@ void ring_split(int pairs, int V, int& nP, int& nD, int& nS) {
 int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec_h, const float* b_out,
                           const int* labels, const int* tlen, const int* ulen, const float* lse, const float* lp2,
                           const float* gamma2, const float* grad_cost, int B, int T, int U1, int J, int V, int Vout,
-                          int blank, void* dh_ws, void* ring_ws, float* d_w_out, float* d_b_out, cudaStream_t st) {
+                          int blank, int plain, void* dh_ws, void* ring_ws, float* d_w_out, float* d_b_out,
+                          cudaStream_t st) {
     EMO_REQUIRE(joint_ring_supported(B, T, U1, J, V), EMO_UNSUPPORTED_SHAPE,
                 "joint_bwd(bf16, ring): needs B <= %d, J %% 128 == 0, J <= 512", kMaxB);
     const RingGeom g = ring_geom(B, J, V);
@@ -1178,7 +1186,7 @@ int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec
     a.enc = (const __half*)enc_h; a.dec = (const __half*)dec_h; a.b_out = b_out; a.labels = labels;
     a.lse = lse; a.lp2 = lp2; a.gamma2 = gamma2; a.grad_cost = grad_cost; a.prefix = prefix; a.flags = flags;
     a.d_w_out = d_w_out; a.d_b_out = d_b_out;
-    a.B = B; a.T = T; a.U1 = U1; a.J = J; a.V = V; a.Vout = Vout; a.blank = blank;
+    a.B = B; a.T = T; a.U1 = U1; a.J = J; a.V = V; a.Vout = Vout; a.blank = blank; a.plain = plain;
     ring_split(pairs, V, a.nP, a.nD, a.nS);
     a.NZ = g.NZ; a.NH = g.NH; a.G = g.G;
 
@@ -1243,16 +1251,6 @@ int joint_bf16_launches(int op, int B, int T, int U1, int J, int V) {
 
 // casts shared by forward and backward: w_out -> bf16, enc_proj / dec_proj -> fp16 (11-bit mantissa, half the
 // gather bytes of fp32); layout of the head of every bf16 workspace
-// Vocabulary sizes that are not a multiple of 32 (e.g. the reference's 10872 / 9798 SentencePiece vocabularies) run
-// on a padded copy: pad rows of the bf16 w_out are zero and the pad entries of the bias copy are -1e30, so the pad
-// logits contribute exp2(-huge) = 0 to every log-sum-exp and get dz = 0.
-__global__ void pad_vocab_kernel(__nv_bfloat16* __restrict__ w_tail, size_t n_tail, const float* __restrict__ b_out,
-                                 float* __restrict__ b_pad, int V, int Vp) {
-    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_tail) w_tail[i] = __float2bfloat16_rn(0.f);
-    if (i < (size_t)Vp) b_pad[i] = i < (size_t)V ? b_out[i] : -1e30f;
-}
-
 int joint_bf16_casts(const float* enc_proj, const float* dec_proj, const float* w_out, const float* b_out, int B, int T,
                      int U1, int J, int V, void* ws, const void** w_bf16, const void** enc_h, const void** dec_h,
                      const float** b_pad, cudaStream_t st) {
@@ -1309,7 +1307,7 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     rc = joint_bf16_casts(enc_proj, dec_proj, w_out, b_out, B, T, U1, J, V, ws, &w_bf16, &enc_h, &dec_h, &b_pad, st);
     if (rc) return rc;
     rc = joint_bwd_ring_launch(w_bf16, enc_h, dec_h, b_pad, labels, tlen, ulen, lse, lp2, gamma2, grad_cost, B, T, U1,
-                               J, padded_vocab(V), V, blank, dh_ws, ring_ws, d_w_out, d_b_out, st);
+                               J, padded_vocab(V), V, blank, 0, dh_ws, ring_ws, d_w_out, d_b_out, st);
     if (rc) return rc;
     return joint_reduce_dh_launch(dh_ws, enc_proj, dec_proj, tlen, ulen, B, T, U1, J, d_enc_proj, d_dec_proj, st);
 }

@@ -72,6 +72,16 @@ __global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restr
     }
 }
 
+// Vocabulary sizes that are not a multiple of 32 (e.g. the reference's 10872 / 9798 SentencePiece vocabularies) run
+// on a padded copy: pad rows of the bf16 w_out are zero and the pad entries of the bias copy are -1e30, so the pad
+// logits contribute exp2(-huge) = 0 to every log-sum-exp and get dz = 0.
+__global__ void pad_vocab_kernel(__nv_bfloat16* __restrict__ w_tail, size_t n_tail, const float* __restrict__ b_out,
+                                 float* __restrict__ b_pad, int V, int Vp) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_tail) w_tail[i] = __float2bfloat16_rn(0.f);
+    if (i < (size_t)Vp) b_pad[i] = i < (size_t)V ? b_out[i] : -1e30f;
+}
+
 // x[d] for a per-thread d in [0,32) without dynamic register indexing: five select levels
 __device__ __forceinline__ float mux32(const float (&x)[32], int d) {
     float a[16], b[8], c[4], e[2];

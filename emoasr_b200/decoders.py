@@ -32,11 +32,29 @@ def _reference_forward(self, mixin):
 
 class FusedCTCForward:
     """forward() of ctc.py:87-174 with every ``ctc_loss_fn(logits.transpose(1,0).log_softmax(2), ...)
-    / B`` site (:109-113, :139-141, :152-154) replaced by the fused op on raw logits."""
+    / B`` site (:109-113, :139-141, :152-154) replaced by a fused op.
+
+    ``fused_precision`` "fp32" (default of the stand-alone class): the Linear stays a cuBLAS call and the fused op
+    takes its raw logits (log_softmax + loss, exact fp32).  "bf16" (what ``dropin.install()`` selects by default):
+    Linear + log_softmax + loss + the Linear's backward run as ONE fused tensor-core op per head and the (B,T,V)
+    logits are never formed -- the third return value is then None, like the RNN-T decoder's (its only reader is
+    lm/modeling/p2w.py, outside this path); shapes the tensor-core path does not take fall back to the fp32 route."""
+
+    fused_precision = "fp32"
 
     def _fused_ctc(self, logits, ys, elens, ylens):
         nll = F.ctc_loss(logits, ys, elens, ylens, blank=self.blank_id, zero_infinity=True)
         return nll.sum() / logits.size(0)   # reduction="sum", then "/ B" (ctc.py:111-113)
+
+    def _head_loss(self, linear, eouts, ys, elens, ylens):
+        """(loss, logits or None) of one head (a Linear + CTC): fused from eouts when the tensor-core path takes it."""
+        if (self.fused_precision == "bf16" and eouts.is_cuda and linear.bias is not None and
+                F.ctc_head_supported(eouts.size(0), eouts.size(1), eouts.size(2), linear.weight.size(0), ys.size(1))):
+            nll = F.ctc_head_loss(eouts, linear.weight, linear.bias, ys, elens, ylens, blank=self.blank_id,
+                                  zero_infinity=True)
+            return nll.sum() / eouts.size(0), None
+        logits = linear(eouts)
+        return self._fused_ctc(logits, ys, elens, ylens), logits
 
     def forward(self, eouts, elens, eouts_inter=None, ys=None, ylens=None, ys_in=None, ys_out=None,
                 soft_labels=None, ps=None, plens=None):
@@ -50,21 +68,19 @@ class FusedCTCForward:
             return ref_forward(eouts, elens, eouts_inter, ys, ylens, ys_in, ys_out, soft_labels, ps, plens)
         loss = 0
         loss_dict = {}
-        logits = self.output(eouts)  # (B, T, vocab)
         if ys is None:
-            return logits
-        loss_ctc = self._fused_ctc(logits, ys, elens, ylens)
+            return self.output(eouts)  # (B, T, vocab): decode-time use (ctc.py:105-106)
+        loss_ctc, logits = self._head_loss(self.output, eouts, ys, elens, ylens)
         loss += loss_ctc
         loss_dict["loss_ctc"] = loss_ctc
         if self.mtl_phone_ctc_weight > 0:
-            logits_phone = self.phone_output(eouts_inter if self.hie_mtl_phone else eouts)
-            loss_phone_ctc = self._fused_ctc(logits_phone, ps, elens, plens)
+            loss_phone_ctc, _ = self._head_loss(self.phone_output, eouts_inter if self.hie_mtl_phone else eouts,
+                                                ps, elens, plens)
             loss += self.mtl_phone_ctc_weight * loss_phone_ctc
             key = "loss_phone_ctc(inter)" if self.hie_mtl_phone else "loss_phone_ctc"
             loss_dict[key] = loss_phone_ctc
         if self.mtl_inter_ctc_weight > 0:
-            logits_inter = self.output(eouts_inter)
-            loss_inter_ctc = self._fused_ctc(logits_inter, ys, elens, ylens)
+            loss_inter_ctc, _ = self._head_loss(self.output, eouts_inter, ys, elens, ylens)
             loss_dict["loss_inter_ctc"] = loss_inter_ctc
             loss += self.mtl_inter_ctc_weight * loss_inter_ctc
         loss_dict["loss_total"] = loss

@@ -35,6 +35,8 @@ def install(reference_root=None, precision="bf16"):
         return ref_asr
 
     class CTCDecoder(FusedCTCForward, ref_ctc.CTCDecoder):
+        fused_precision = precision
+
         def __init__(self, params):
             ref_ctc.CTCDecoder.__init__(self, params)
             self.ctc_loss_fn = CTCLoss(blank=self.blank_id, reduction="sum", zero_infinity=True)  # S3

@@ -3,6 +3,7 @@
 rnnt_loss        warp_rnnt.rnnt_loss signature (asr/modeling/decoders/rnn_transducer.py:106-115)
 rnnt_joint_loss  joint + log_softmax + transducer loss fused (rnn_transducer.py:101-115, 147-156)
 ctc_loss         log_softmax + nn.CTCLoss(reduction="none") fused (asr/modeling/decoders/ctc.py:109-113)
+ctc_head_loss    output Linear + log_softmax + CTC loss fused, logits never formed (ctc.py:103-113)
 """
 import ctypes
 
@@ -295,4 +296,80 @@ def ctc_loss(logits, labels, input_lengths, label_lengths, blank=0, reduction=No
     fused.  Feeding log-probs instead of logits gives the same value and torch's gradient.
     """
     nll = _CTC.apply(logits, labels, input_lengths, label_lengths, int(blank), bool(zero_infinity))
+    return _reduce(nll, reduction)
+
+
+# ----------------------------------------------------------------------------------------------
+def ctc_head_supported(B, T, He, V, Umax):
+    """True if ctc_head_loss can run these sizes on the tensor-core path (host call, no CUDA work)."""
+    return bool(_lib.load().emo_ctc_head_supported(B, T, He, V, max(Umax, 1)))
+
+
+class _CTCHead(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, eouts, weight, bias, labels, tlen, ulen, blank, zero_infinity):
+        _require_cuda(eouts, weight, bias)
+        lib = _lib.load()
+        e, w, bo = _f32c(eouts), _f32c(weight), _f32c(bias)
+        B, T, He = e.shape
+        V = w.size(0)
+        if w.size(1) != He or bo.numel() != V:
+            raise RuntimeError(f"ctc_head_loss: inconsistent shapes eouts {tuple(e.shape)} weight {tuple(w.shape)}")
+        dev = e.device
+        labels, tlen, ulen = _i64c(labels, dev), _i64c(tlen, dev), _i64c(ulen, dev)
+        if labels.dim() != 2 or labels.size(0) != B:
+            raise RuntimeError(f"labels must be (B, Umax); got {tuple(labels.shape)}")
+        Umax = labels.size(1)
+        if Umax == 0:
+            labels = torch.zeros(B, 1, dtype=torch.int64, device=dev)
+            Umax = 1
+        S = 2 * Umax + 1
+        need_grad = any(ctx.needs_input_grad[:3])
+        with torch.cuda.device(dev):
+            nbytes = int(lib.emo_ctc_head_workspace_bytes(0, B, T, He, V, Umax))
+            if nbytes == 0:
+                raise RuntimeError(f"ctc_head_loss: unsupported shape B={B} T={T} He={He} V={V} Umax={Umax} "
+                                   "(see emo_ctc_head_supported; use ctc_loss on the Linear's output)")
+            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            lse = torch.zeros(B, T, device=dev)
+            emis = torch.empty(B, T, Umax + 1, device=dev)
+            alpha = torch.empty(B, T, S, device=dev)
+            beta = torch.empty(B, T, S, device=dev) if need_grad else None
+            nll = torch.empty(B, device=dev)
+            _lib.check(lib.emo_ctc_head_fwd(_p(e), _p(w), _p(bo), _p(labels), _p(tlen), _p(ulen), B, T, He, V, Umax,
+                                            blank, int(zero_infinity), _p(lse), _p(emis), _p(alpha), _p(beta), _p(nll),
+                                            _p(ws), ws.numel(), _stream()), "emo_ctc_head_fwd")
+        if need_grad:
+            ctx.save_for_backward(e, w, bo, labels, tlen, ulen, lse, emis, alpha, beta)
+        ctx.blank = blank
+        return nll
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_nll):
+        e, w, bo, labels, tlen, ulen, lse, emis, alpha, beta = ctx.saved_tensors
+        lib = _lib.load()
+        B, T, He = e.shape
+        V, Umax = w.size(0), labels.size(1)
+        dev = e.device
+        with torch.cuda.device(dev):
+            g = _f32c(grad_nll)
+            ws = torch.empty(int(lib.emo_ctc_head_workspace_bytes(1, B, T, He, V, Umax)), dtype=torch.uint8, device=dev)
+            d_e, d_w, d_b = torch.empty_like(e), torch.empty_like(w), torch.empty_like(bo)
+            _lib.check(lib.emo_ctc_head_bwd(_p(e), _p(w), _p(bo), _p(labels), _p(tlen), _p(ulen), _p(lse), _p(emis),
+                                            _p(alpha), _p(beta), _p(g), B, T, He, V, Umax, ctx.blank,
+                                            _p(d_e), _p(d_w), _p(d_b), _p(ws), ws.numel(), _stream()),
+                       "emo_ctc_head_bwd")
+        return d_e, d_w, d_b, None, None, None, None, None
+
+
+def ctc_head_loss(eouts, weight, bias, labels, input_lengths, label_lengths, blank=0, reduction=None,
+                  zero_infinity=True):
+    """Per-utterance CTC negative log-likelihood straight from the encoder outputs and the head's parameters.
+
+    Equivalent to ``ctc_loss(linear(eouts, weight, bias), ...)`` (ctc.py:103-113) with the Linear, the log_softmax,
+    the loss and all three backward GEMMs fused: the (B,T,V) logits are never formed.  Tensor-core path (bf16
+    operands, fp32 accumulation); shapes outside ``ctc_head_supported`` raise.
+    """
+    nll = _CTCHead.apply(eouts, weight, bias, labels, input_lengths, label_lengths, int(blank), bool(zero_infinity))
     return _reduce(nll, reduction)

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define EMO_ABI_VERSION 5
+#define EMO_ABI_VERSION 6
 
 enum emo_status {
     EMO_OK = 0,
@@ -160,6 +160,32 @@ int emo_ctc_bwd(const float* logits, const long long* labels, const long long* t
                 const long long* ulen, const float* lse, const float* alpha_ws, const float* nll,
                 const float* grad_nll, int B, int T, int V, int Umax, int blank, int zero_infinity,
                 float* beta_ws, int beta_valid, float* grad_logits, void* stream);
+
+/* ---- fused CTC head: output Linear + log_softmax + CTC loss --------------------------------------
+ * Replaces asr/modeling/decoders/ctc.py:103-113 (`logits = self.output(eouts)`; `ctc_loss_fn(logits.transpose(1,0)
+ * .log_softmax(2), ys, elens, ylens)`) including the Linear's backward: the (B,T,V) logits, log-probs and their
+ * gradient are never written to memory.
+ * eouts (B,T,He) fp32, w (V,He) fp32 row-major (torch Linear weight), b (V); labels / lengths as emo_ctc_fwd.
+ * Tensor-core path (operands rounded to bf16, fp32 accumulation; loss <= 2e-3, gradients <= 2e-2 relative):
+ * needs He % 128 == 0, He <= 512, 2*Umax+1 <= 1024, B <= 1024 and a vocabulary of at most ~16 k entries
+ * (emo_ctc_head_supported; any V is padded to a multiple of 32 inside the workspace).
+ * emo_ctc_head_fwd: lse (B,T) log-sum-exp of every valid frame's logits; emis (B,T,Umax+1) emission log-probs
+ *                   {blank, y_0 .. y_{U_b-1}} per frame (kept for the backward); alpha_ws / beta_ws (B,T,2*Umax+1)
+ *                   lattices (beta_ws may be NULL when no gradient will be asked for); nll (B).
+ * emo_ctc_head_bwd: d_eouts (B,T,He), d_w (V,He), d_b (V) of sum_b grad_nll[b] * nll[b]; all three are overwritten.
+ *                   lse / emis / alpha_ws / beta_ws must be the forward's outputs.
+ * emo_ctc_head_workspace_bytes: op 0 = forward, 1 = backward; 0 for unsupported shapes.  Host calls. */
+int emo_ctc_head_supported(int B, int T, int He, int V, int Umax);
+size_t emo_ctc_head_workspace_bytes(int op, int B, int T, int He, int V, int Umax);
+int emo_ctc_head_fwd(const float* eouts, const float* w, const float* b, const long long* labels,
+                     const long long* tlen, const long long* ulen, int B, int T, int He, int V, int Umax,
+                     int blank, int zero_infinity, float* lse, float* emis, float* alpha_ws, float* beta_ws,
+                     float* nll, void* ws, size_t ws_bytes, void* stream);
+int emo_ctc_head_bwd(const float* eouts, const float* w, const float* b, const long long* labels,
+                     const long long* tlen, const long long* ulen, const float* lse, const float* emis,
+                     const float* alpha_ws, const float* beta_ws, const float* grad_nll, int B, int T, int He,
+                     int V, int Umax, int blank, float* d_eouts, float* d_w, float* d_b, void* ws, size_t ws_bytes,
+                     void* stream);
 
 #ifdef __cplusplus
 }

@@ -48,6 +48,8 @@ def _np(t):
 
 
 def rnnt_case(name, seed, B, T, U, p, tlens, ulens, mtl_ctc_weight=0.0):
+    if not _wanted(name):
+        return
     from asr.modeling.decoders.rnn_transducer import RNNTDecoder
 
     p = p._replace(mtl_ctc_weight=mtl_ctc_weight)
@@ -83,6 +85,8 @@ def rnnt_case(name, seed, B, T, U, p, tlens, ulens, mtl_ctc_weight=0.0):
 
 
 def ctc_case(name, seed, B, T, U, V, He, tlens, ulens):
+    if not _wanted(name):
+        return
     from asr.modeling.decoders.ctc import CTCDecoder
 
     p = _params(enc_hidden_size=He, vocab_size=V)
@@ -110,6 +114,8 @@ def ctc_case(name, seed, B, T, U, V, He, tlens, ulens):
 
 
 def ctc_mtl_case(name, seed, B, T, U, Up, V, Vp, He, tlens, ulens, plens, phone_w, hie, inter_w):
+    if not _wanted(name):
+        return
     """Phone-CTC (ctc.py:129-148, final or intermediate layer) and intermediate-CTC (ctc.py:150-170) heads."""
     from asr.modeling.decoders.ctc import CTCDecoder
 
@@ -202,7 +208,16 @@ def smoke_fixtures():
     print("known_answer", _np(cost))
 
 
+ONLY = None   # python oracle/gen_golden.py NAME ... : regenerate just these cases
+
+
+def _wanted(name):
+    return ONLY is None or name in ONLY
+
+
 def main():
+    global ONLY
+    ONLY = set(sys.argv[1:]) or None
     os.makedirs(OUT, exist_ok=True)
     sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
     from oracle import warp_rnnt_shim
@@ -211,7 +226,8 @@ def main():
     sys.path.insert(0, REF)
     torch.set_num_threads(4)
 
-    smoke_fixtures()
+    if ONLY is None:
+        smoke_fixtures()
     p = _params()
     rnnt_case("ref_rnnt_small_full", 0, B=3, T=9, U=5, p=p, tlens=[9, 9, 9], ulens=[5, 5, 5])
     rnnt_case("ref_rnnt_small_ragged", 1, B=4, T=12, U=6, p=p, tlens=[12, 10, 7, 1], ulens=[6, 3, 0, 2])
@@ -239,6 +255,13 @@ def main():
                  ulens=[5, 4, 2, 5], plens=[9, 7, 3, 8], phone_w=0.3, hie=False, inter_w=0.0)
     ctc_mtl_case("ref_ctc_phone_hie_inter", 10, B=4, T=22, U=6, Up=10, V=29, Vp=43, He=16, tlens=[22, 20, 11, 6],
                  ulens=[6, 5, 6, 1], plens=[10, 8, 9, 2], phone_w=0.3, hie=True, inter_w=0.5)
+    # enc_hidden_size the fused tensor-core CTC head accepts (He % 128 == 0): main head with an odd vocabulary, an
+    # infeasible utterance and an empty transcript; then all three heads (main, phone on the intermediate layer,
+    # intermediate CTC)
+    ctc_case("ref_ctc_tchead_ragged", 11, B=5, T=41, U=12, V=203, He=128,
+             tlens=[41, 37, 9, 41, 20], ulens=[12, 10, 12, 0, 5])
+    ctc_mtl_case("ref_ctc_tchead_phone_hie_inter", 12, B=4, T=33, U=8, Up=14, V=157, Vp=43, He=128,
+                 tlens=[33, 30, 21, 16], ulens=[8, 7, 8, 2], plens=[14, 11, 12, 3], phone_w=0.3, hie=True, inter_w=0.5)
 
 
 if __name__ == "__main__":

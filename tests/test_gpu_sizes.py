@@ -246,3 +246,95 @@ def test_forward_and_backward_keep_nothing_of_size_N_x_V():
     torch.cuda.synchronize()
     assert torch.isfinite(loss)
     assert torch.cuda.max_memory_allocated() - base < zbytes // 2
+
+
+# ---------------------------------------------------------------- fused CTC head (Linear + log_softmax + CTC)
+HEAD_SHAPES = [
+    # B, T, He, V, U
+    (3, 40, 128, 64, 9),       # one vocab chunk
+    (4, 61, 256, 1000, 17),    # vocabulary not a multiple of 32, several chunks
+    (2, 300, 256, 5000, 80),   # cfg-2 head, more than one 256-frame pair tile per utterance
+    (2, 37, 512, 2048, 12),    # widest supported hidden size
+]
+
+
+@pytest.mark.parametrize("B,T,He,V,U", HEAD_SHAPES)
+def test_ctc_head_vs_oracle(B, T, He, V, U):
+    """Fused head (tensor-core path) against the reference's op sequence Linear -> log_softmax -> nn.CTCLoss in
+    fp64 on the CPU (oracle/torch_path.py), ragged lengths, repeated labels, at the stated bf16 tolerance."""
+    import emoasr_b200 as E
+    from oracle import torch_path
+    gen = torch.Generator().manual_seed(B * 100 + V)
+    eouts = torch.randn(B, T, He, generator=gen)
+    w = torch.randn(V, He, generator=gen) * (2.0 / He ** 0.5)
+    bias = torch.randn(V, generator=gen) * 0.5
+    ys = torch.randint(1, V, (B, U), generator=gen)
+    ys[:, 3] = ys[:, 2]                                   # a repeated label (needs the blank between)
+    tl = torch.randint(max(2 * U + 2, T // 2), T + 1, (B,), generator=gen); tl[0] = T
+    ul = torch.randint(1, U + 1, (B,), generator=gen); ul[0] = U
+    ref_in = [t.double().requires_grad_() for t in (eouts, w, bias)]
+    ref = torch_path.ctc_head_loss(*ref_in, ys, tl, ul, blank=0)
+    ref.backward()
+    te = [t.to(dev()).requires_grad_() for t in (eouts, w, bias)]
+    nll = E.ctc_head_loss(*te, ys.to(dev()), tl.to(dev()), ul.to(dev()), blank=0)
+    loss = nll.sum() / B
+    loss.backward()
+    assert abs(float(loss) - float(ref)) <= BF16_LOSS_RTOL * abs(float(ref))
+    for got, want, k in zip(te, ref_in, ("d_eouts", "d_weight", "d_bias")):
+        assert rel_err(got.grad.cpu().numpy(), want.grad.numpy()) < BF16_GRAD_RTOL, k
+    b = int(torch.argmin(tl))
+    assert float(te[0].grad[b, int(tl[b]):].abs().sum()) == 0.0       # padded frames
+
+
+def test_ctc_head_infeasible_and_matches_unfused():
+    """zero_infinity: an utterance whose labels do not fit its frames contributes 0 loss and 0 gradient; the fused
+    head agrees with the unfused route (cuBLAS Linear + emo_ctc_fwd/bwd in fp32) on the rest."""
+    import emoasr_b200 as E
+    gen = torch.Generator().manual_seed(9)
+    B, T, He, V, U = 4, 50, 256, 512, 20
+    eouts = torch.randn(B, T, He, generator=gen).to(dev())
+    lin = torch.nn.Linear(He, V).to(dev())
+    ys = torch.randint(1, V, (B, U), generator=gen).to(dev())
+    tl = torch.tensor([50, 12, 50, 33], device=dev())     # utterance 1: 12 frames < 20 labels
+    ul = torch.tensor([20, 20, 0, 7], device=dev())       # utterance 2: empty transcript
+    out = {}
+    for name in ("fused", "unfused"):
+        lin.zero_grad(set_to_none=True)
+        x = eouts.clone().requires_grad_()
+        if name == "fused":
+            nll = E.ctc_head_loss(x, lin.weight, lin.bias, ys, tl, ul, blank=0)
+        else:
+            nll = E.ctc_loss(lin(x), ys, tl, ul, blank=0)
+        (nll.sum() / B).backward()
+        out[name] = (nll.detach().clone(), x.grad.clone(), lin.weight.grad.clone(), lin.bias.grad.clone())
+    f, u = out["fused"], out["unfused"]
+    assert float(f[0][1]) == 0.0 and float(f[1][1].abs().sum()) == 0.0
+    assert torch.allclose(f[0], u[0], rtol=BF16_LOSS_RTOL, atol=1e-3)
+    for a, b_, k in zip(f[1:], u[1:], ("d_eouts", "d_weight", "d_bias")):
+        assert float((a - b_).norm() / b_.norm()) < BF16_GRAD_RTOL, k
+
+
+@pytest.mark.parametrize("name", ["ref_ctc_tchead_ragged", "ref_ctc_tchead_phone_hie_inter"])
+def test_ctc_decoder_fused_head_vs_reference_golden(name):
+    """The drop-in CTCDecoder with fused_precision="bf16" (every head fused from eouts where the shape allows)
+    against the goldens of the unmodified reference, at the stated bf16 tolerance."""
+    from emoasr_b200.decoders import CTCDecoder
+    g = load_golden(name)
+    keys = ["enc_hidden_size", "vocab_size", "eos_id", "blank_id", "kd_weight", "mtl_phone_ctc_weight",
+            "hie_mtl_phone", "phone_vocab_size", "mtl_inter_ctc_weight"]
+    keys = [k for k in keys if "hp." + k in g]
+    dec = CTCDecoder(_params_from_golden(g, keys))
+    dec.fused_precision = "bf16"
+    dec.load_state_dict({k[len("param."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")})
+    dec = dec.to(dev())
+    eouts = T_(g["eouts"]).requires_grad_()
+    inter = T_(g["eouts_inter"]).requires_grad_() if "eouts_inter" in g and g["eouts_inter"].size else None
+    ps = T_(g["ps"]) if "ps" in g else None
+    plens = T_(g["plens"]) if "plens" in g else None
+    loss, loss_dict, logits = dec(eouts, T_(g["elens"]), inter, T_(g["ys"]), T_(g["ylens"]), None, None, None, ps, plens)
+    loss.backward()
+    assert logits is None                      # the fused head ran: no (B,T,V) tensor exists
+    assert abs(float(loss) - float(g["loss_total"])) <= BF16_LOSS_RTOL * abs(float(g["loss_total"]))
+    assert rel_err(eouts.grad.cpu().numpy(), g["grad_eouts"]) < BF16_GRAD_RTOL
+    for k, v in dec.named_parameters():
+        assert rel_err(v.grad.cpu().numpy(), g["grad." + k]) < BF16_GRAD_RTOL, k

@@ -9,7 +9,7 @@ from oracle import clattice, ctc_dp, rnnt_dp, torch_path
 
 RNNT_CASES = ["ref_rnnt_small_full", "ref_rnnt_small_ragged", "ref_rnnt_small_auxctc", "ref_rnnt_medium_ragged",
               "ref_rnnt_tcshape_ragged", "ref_rnnt_tcshape_auxctc"]
-CTC_CASES = ["ref_ctc_small_full", "ref_ctc_small_ragged", "ref_ctc_medium_ragged"]
+CTC_CASES = ["ref_ctc_small_full", "ref_ctc_small_ragged", "ref_ctc_medium_ragged", "ref_ctc_tchead_ragged"]
 
 
 def test_known_answer_dp():
@@ -84,7 +84,7 @@ def test_ctc_dp_vs_reference_golden(name):
     assert rel_err(c["d_b"], g["grad.output.bias"]) < 1e-4
 
 
-@pytest.mark.parametrize("name", ["ref_ctc_phone_final", "ref_ctc_phone_hie_inter"])
+@pytest.mark.parametrize("name", ["ref_ctc_phone_final", "ref_ctc_phone_hie_inter", "ref_ctc_tchead_phone_hie_inter"])
 def test_ctc_dp_vs_reference_golden_phone_and_inter_heads(name):
     """Phone CTC (final / intermediate layer, ctc.py:129-148) and intermediate CTC (ctc.py:150-170): the same
     head recipe on other inputs / weights; loss_total = ctc + w_p * phone + w_i * inter."""
