@@ -359,13 +359,20 @@ def rnnt_kernel_roofline(args, w, wl, resident, flush, dev):
 
 
 # ------------------------------------------------------------------------------------------------
-def ctc_step_fn(E, wl, B):
+def ctc_step_fn(E, wl, B, fused=True):
+    """fused: Linear + log_softmax + CTC + the Linear's backward as one tensor-core op per direction (no (B,T,V)
+    tensor in memory); unfused: cuBLAS Linear (TF32) around the fp32 loss kernels on raw logits."""
+    crit = E.CTCHeadLoss(blank=0)
+
     def step(eouts, ys, tlen, ulen):
         wl.output.weight.grad = None
         wl.output.bias.grad = None
         eouts = eouts.detach().requires_grad_()
-        logits = wl.output(eouts)                                  # ctc.py:103
-        loss = E.ctc_loss(logits, ys, tlen, ulen, blank=0, reduction="sum") / B   # ctc.py:109-113
+        if fused:
+            loss = crit(eouts, wl.output.weight, wl.output.bias, ys, tlen, ulen)      # ctc.py:103-113
+        else:
+            logits = wl.output(eouts)                                  # ctc.py:103
+            loss = E.ctc_loss(logits, ys, tlen, ulen, blank=0, reduction="sum") / B   # ctc.py:109-113
         loss.backward()
         return loss
     return step
@@ -385,7 +392,9 @@ def run_ours_ctc(args, w, rank, world, dev):
     host = [t.pin_memory() for t in (wl.eouts, wl.ys, wl.tlen, wl.ulen)]
     resident = [t.to(dev) for t in host]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
-    step = ctc_step_fn(E, wl, B)
+    from emoasr_b200 import functional as EF
+    fused = EF.ctc_head_supported(B, T, He, V, w["U"]) and not getattr(args, "ctc_unfused", False)
+    step = ctc_step_fn(E, wl, B, fused)
     for _ in range(args.warmup):
         step(*resident)
     torch.cuda.synchronize()
@@ -401,21 +410,47 @@ def run_ours_ctc(args, w, rank, world, dev):
     run_e2e(step, host, dev, 2)
     e2e_s = run_e2e(step, host, dev, args.steps)
     peaks = load_peaks()
-    # algorithmic bytes of the step: the loss kernels read the logits twice and write their gradient once
-    # (3*B*T*V*4); the head's Linear adds one write of the logits and one read of the gradient
+    # SURVEY 8d's per-step figure for the CTC path is the logits traffic of the unfused sequence, 3*B*T*V*4 bytes
+    # (read twice, gradient written once).  The fused head moves none of it: what bounds it is the tensor pipe on
+    # the head's three GEMMs (Linear forward, d_eouts, d_W: 6*B*T*He*V flop).  Both fractions are reported: the
+    # HBM one as "time the unfused byte stream would need at peak / step time" (> 1 is possible when fused).
+    n_frames = int(wl.tlen.sum())
     alg_bytes = 3.0 * B * T * V * 4
-    ach = alg_bytes / (ms_total / args.steps * 1e-3) / 1e9
-    roof = {"bound": "hbm", "kernel": "CTC head step: output Linear fwd/bwd (cuBLAS TF32) + row_lse + lattices + grad kernels",
-            "achieved": round(ach, 1), "peak": peaks["hbm"], "unit": "GB/s", "frac": round(ach / peaks["hbm"], 4),
-            "traffic": None, "peak_source": peaks["src"], "algorithmic_bytes_per_step": alg_bytes,
-            "note": "algorithmic bytes = 3*B*T*V*4 (the loss kernels' logits traffic); the step timed here also "
-                    "contains the Linear(He,V) forward and both of its backward GEMMs (cuBLAS, TF32)"}
-    tr, src = load_traffic(args.workload, "default")
+    ms = ms_total / args.steps
+    ach = alg_bytes / (ms * 1e-3) / 1e9
+    if fused:
+        flops = 6.0 * n_frames * He * V
+        tf = flops / (ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "fused CTC head step: joint_fwd_kernel<plain> + emissions + lattices + "
+                                             "joint_bwd_ring_kernel (plain) + sparse label kernels",
+                "achieved": round(tf, 1), "peak": peaks["tf_burst"], "unit": "TFLOP/s",
+                "frac": round(tf / peaks["tf_burst"], 4), "traffic": None, "peak_source": peaks["src"] + ", burst",
+                "algorithmic_flops_per_step": flops,
+                "hbm_equivalent": {"achieved": round(ach, 1), "peak": peaks["hbm"], "unit": "GB/s",
+                                   "frac": round(ach / peaks["hbm"], 4), "algorithmic_bytes_per_step": alg_bytes},
+                "note": "small-K GEMMs (K = He = 256) with an exp per logit: the step is bound by the lattice "
+                        "recursions' latency and the MUFU epilogues, not by the tensor pipe or HBM"}
+    else:
+        roof = {"bound": "hbm", "kernel": "CTC head step: output Linear fwd/bwd (cuBLAS TF32) + row_lse + lattices + grad kernels",
+                "achieved": round(ach, 1), "peak": peaks["hbm"], "unit": "GB/s", "frac": round(ach / peaks["hbm"], 4),
+                "traffic": None, "peak_source": peaks["src"], "algorithmic_bytes_per_step": alg_bytes,
+                "note": "algorithmic bytes = 3*B*T*V*4 (the loss kernels' logits traffic); the step timed here also "
+                        "contains the Linear(He,V) forward and both of its backward GEMMs (cuBLAS, TF32)"}
+    roof["head"] = "fused" if fused else "unfused"
+    tr, src = load_traffic(args.workload, "fused" if fused else "default")
     if tr is not None:
         roof["traffic"], roof["traffic_source"] = tr.get("step"), src
+    if fused and rank == 0:
+        ustep = ctc_step_fn(E, wl, B, False)
+        for _ in range(3):
+            ustep(*resident)
+        torch.cuda.synchronize()
+        n = max(5, args.steps // 2)
+        roof["unfused_ms_per_step"] = round(timed_steps(ustep, resident, n, flush, torch.cuda.synchronize) / n, 4)
     torch.backends.cuda.matmul.allow_tf32 = tf32
     return dict(ms_total=ms_total, e2e_s=e2e_s, units=B, clocks=clocks, roofline=roof,
-                launches=_lib.launch_count(_lib.OP_CTC, 0, B, T, 1, 1, V) * args.steps,
+                launches=(_lib.launch_count(_lib.OP_CTC_HEAD, 1, B, T, 1, He, V) if fused
+                          else _lib.launch_count(_lib.OP_CTC, 0, B, T, 1, 1, V)) * args.steps,
                 h2d=sum(t.numel() * t.element_size() for t in host), d2h=4, flops=None, n_valid=None, extra={})
 
 
@@ -686,6 +721,7 @@ def main():
                          "cost of the collective; default 0 = the path's own parameters only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--ctc-unfused", action="store_true", help="CTC workloads: cuBLAS Linear + loss kernels on logits")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]
@@ -707,7 +743,8 @@ def main():
         config["route"] = "logit tiles recomputed by the backward; dz through an L2-resident ring; no N x V tensor in HBM"
         config["projections"] = "w_enc/w_dec Linear via cuBLAS, " + ("TF32" if args.precision == "bf16" else "fp32")
     else:
-        config["head"] = "output Linear(He,V) forward + backward included in the step (cuBLAS TF32)"
+        config["head"] = ("output Linear(He,V) forward + backward included in the step: fused tensor-core head (no "
+                          "(B,T,V) tensor in memory) where the shape allows, else cuBLAS TF32 + fp32 loss kernels")
 
     if args.impl == "reference":
         if rank != 0:
@@ -750,7 +787,8 @@ def main():
         value = units / (ms_total * 1e-3)
         out = {"metric": metric, "value": round(value, 2), "unit": "utt/s", "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": round(ms_total / args.steps, 4), "higher_is_better": True,
-               "scaling": "weak", "vs_baseline": None, "dtype": args.precision if w["kind"] == "rnnt" else "f32",
+               "scaling": "weak", "vs_baseline": None,
+               "dtype": args.precision if w["kind"] == "rnnt" else ("bf16" if (r["roofline"] or {}).get("head") == "fused" else "f32"),
                "data": "synthetic", "config": config, "clocks": r["clocks"],
                "e2e": {"value": round(units / e2e_s, 2), "unit": "utt/s", "h2d_bytes_per_step": r["h2d"],
                        "d2h_bytes_per_step": r["d2h"]},
@@ -774,7 +812,7 @@ def main():
                                      "ms_per_step": round(c["ms_total"] / cargs.steps, 4),
                                      "e2e": {"value": round(cu / c["e2e_s"], 1), "unit": "utt/s",
                                              "h2d_bytes_per_step": c["h2d"], "d2h_bytes_per_step": c["d2h"]},
-                                     "roofline": c["roofline"], "dtype": "f32"}
+                                     "roofline": c["roofline"], "dtype": "bf16" if c["roofline"].get("head") == "fused" else "f32"}
                 torch.cuda.empty_cache()
             out["gpu_baseline"] = gpu_baselines(dev)
         if extra:

@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # EMOASR_B200_LIB: an instrumented copy of the library (python -m emoasr_b200.build --prof; tools/ only)
 LIB_PATH = os.environ.get("EMOASR_B200_LIB") or os.path.join(_HERE, "lib", "libemoasr_b200.so")
 
-OP_RNNT_JOINT_FWD, OP_RNNT_JOINT_BWD, OP_CTC = 0, 1, 2
+OP_RNNT_JOINT_FWD, OP_RNNT_JOINT_BWD, OP_CTC, OP_CTC_HEAD = 0, 1, 2, 3
 PREC_FP32, PREC_BF16 = 0, 1
 ABI_VERSION = 6
 

@@ -24,14 +24,32 @@ namespace {
 constexpr int kHeadFrames = 8;      // frames per block of the emission / d_eouts kernels
 constexpr int kHeadThreads = 128;
 
+// The joint kernels tile the cells of one utterance at a time (256 per CTA pair).  With one cell per frame that
+// would waste the tail of every utterance's last tile (T = 374 -> 512 rows), so the head presents the batch as Bs
+// "super-utterances" of Ts = (B / Bs) * T frames each (Bs = 1 whenever B * T < 65536): padded frames are ordinary
+// rows whose per-row gradient scale is 0.
+struct Super {
+    int Bs, Ts;
+};
+Super head_super(int B, int T) {
+    Super s;
+    s.Bs = B;
+    for (int d = 1; d <= B; ++d)
+        if (B % d == 0 && (long long)(B / d) * T < 65536) { s.Bs = d; break; }
+    s.Ts = B / s.Bs * T;
+    return s;
+}
+
 struct HeadWs {
     __nv_bfloat16* w_bf16;   // (Vp, He)
     __half* e16;             // (B, T, He)
     float* b_pad;            // (Vp)
     int* tlen32;             // (B)  clamp(tlen, 1, T)
     int* ulen32;             // (B)  0: one cell per frame
+    int* tsup32;             // (Bs) Ts: frames of a super-utterance
     float* lp2;              // fwd: (B, T, 2) blank log-prob from the joint forward
     float* geff;             // bwd: (B) grad_nll, 0 for infeasible utterances
+    float* grow;             // bwd: (B, T) per-frame gradient scale: geff[b] for t < T_b, else 0
     float* ll;               // bwd: (B) log-likelihood from the last alphas
     float* occg;             // bwd: (B, T, Umax + 1) g * occupancy per (frame, {blank, label u})
     void* dh;                // bwd: tile-major bf16 dh of the ring kernel
@@ -50,15 +68,19 @@ HeadWs head_ws_layout(void* base, int op, int B, int T, int He, int V, int Umax)
     w.b_pad = reinterpret_cast<float*>(take(Vp * sizeof(float)));
     w.tlen32 = reinterpret_cast<int*>(take((size_t)B * sizeof(int)));
     w.ulen32 = reinterpret_cast<int*>(take((size_t)B * sizeof(int)));
+    w.tsup32 = reinterpret_cast<int*>(take((size_t)B * sizeof(int)));
+    const Super su = head_super(B, T);
+    w.grow = nullptr;
     w.lp2 = nullptr; w.geff = nullptr; w.ll = nullptr; w.occg = nullptr; w.dh = nullptr; w.ring = nullptr;
     if (op == 0) {
         w.lp2 = reinterpret_cast<float*>(take((size_t)B * T * 2 * sizeof(float)));
     } else {
         w.geff = reinterpret_cast<float*>(take((size_t)B * sizeof(float)));
         w.ll = reinterpret_cast<float*>(take((size_t)B * sizeof(float)));
+        w.grow = reinterpret_cast<float*>(take((size_t)B * T * sizeof(float)));
         w.occg = reinterpret_cast<float*>(take((size_t)B * T * (Umax + 1) * sizeof(float)));
-        w.dh = take(align_up(dh_bytes_for(B, T, 1, He), 1024));
-        w.ring = take(joint_ring_workspace(B, T, 1, He, V));
+        w.dh = take(align_up(dh_bytes_for(su.Bs, su.Ts, 1, He), 1024));
+        w.ring = take(joint_ring_workspace(su.Bs, su.Ts, 1, He, V));
     }
     w.total = off;
     return w;
@@ -68,15 +90,16 @@ __device__ __forceinline__ int clamp_label(long long l, int V) { return (int)(l 
 
 // lengths for the joint kernels + (backward) feasibility and the per-utterance gradient scale
 __global__ void head_prep_kernel(const long long* __restrict__ tlen, const long long* __restrict__ ulen, int B, int T,
-                                 int Umax, int* __restrict__ tlen32, int* __restrict__ ulen32,
-                                 const float* __restrict__ alpha_ws, const float* __restrict__ grad_nll,
-                                 float* __restrict__ geff, float* __restrict__ ll) {
+                                 int Umax, int Ts, int* __restrict__ tlen32, int* __restrict__ ulen32,
+                                 int* __restrict__ tsup32, const float* __restrict__ alpha_ws,
+                                 const float* __restrict__ grad_nll, float* __restrict__ geff, float* __restrict__ ll) {
     const int b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B) return;
     const long long T_bl = tlen[b], U_bl = ulen[b];
     const int T_b = (int)(T_bl < 1 ? 1 : (T_bl > T ? T : T_bl));
     tlen32[b] = T_b;
     ulen32[b] = 0;
+    tsup32[b] = Ts;
     if (!alpha_ws) return;
     const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
     const int S = 2 * Umax + 1, S_b = 2 * U_b + 1;
@@ -85,6 +108,15 @@ __global__ void head_prep_kernel(const long long* __restrict__ tlen, const long 
     const bool feasible = l > kNegInf && l == l && l < INFINITY;
     geff[b] = feasible ? grad_nll[b] : 0.f;   // infeasible utterances: zero gradient (zero_infinity, ctc.py:38)
     ll[b] = feasible ? l : 0.f;
+}
+
+// per-frame gradient scale of the dense part
+__global__ void head_grow_kernel(const int* __restrict__ tlen32, const float* __restrict__ geff, int B, int T,
+                                 float* __restrict__ grow) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * T) return;
+    const int b = i / T, t = i - b * T;
+    grow[i] = t < tlen32[b] ? geff[b] : 0.f;
 }
 
 // e as the tensor cores see it: fp32 -> fp16 (the stream cast) -> bf16 (the A producers)
@@ -160,7 +192,7 @@ head_deouts_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict
                    const float* __restrict__ alpha_ws, const float* __restrict__ beta_ws,
                    const long long* __restrict__ labels, const int* __restrict__ tlen32,
                    const long long* __restrict__ ulen, const float* __restrict__ geff, const float* __restrict__ ll,
-                   int T, int He, int V, int Umax, int blank, int tpu, float* __restrict__ occg,
+                   int T, int He, int V, int Umax, int blank, int tpu, int per_super, float* __restrict__ occg,
                    float* __restrict__ d_eouts, float* __restrict__ d_b) {
     extern __shared__ float s_occ[];   // [Umax + 1][kHeadFrames]
     const int b = blockIdx.y, t0 = blockIdx.x * kHeadFrames;
@@ -231,8 +263,9 @@ head_deouts_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict
         if (t0 + f >= T) break;
         float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
         if (f < nf) {
-            // tile-major dh with one cell per frame: row = b * tpu * 128 + t
-            const uint2 dv = *reinterpret_cast<const uint2*>(dh + ((size_t)b * tpu * kTileM + t0 + f) * He + c4);
+            // tile-major dh with one cell per frame: row = super-utterance * tpu * 128 + frame inside it
+            const size_t row = (size_t)(b / per_super) * tpu * kTileM + (size_t)(b % per_super) * T + t0 + f;
+            const uint2 dv = *reinterpret_cast<const uint2*>(dh + row * He + c4);
             out.x = __uint_as_float(dv.x << 16) - acc[f][0];
             out.y = __uint_as_float(dv.x & 0xffff0000u) - acc[f][1];
             out.z = __uint_as_float(dv.y << 16) - acc[f][2];
@@ -297,8 +330,8 @@ int head_check(const void* eouts, const void* w, const void* b, const void* labe
                 2 * Umax + 1);
     EMO_REQUIRE(He % 128 == 0 && He <= kMaxKBlocks * kBlockK, EMO_UNSUPPORTED_SHAPE,
                 "ctc_head: enc_hidden_size %d must be a multiple of 128 and <= 512 (use the unfused CTC loss)", He);
-    EMO_REQUIRE(joint_ring_supported(B, T, 1, He, V) && He / 4 <= kHeadThreads, EMO_UNSUPPORTED_SHAPE,
-                "ctc_head: unsupported shape (B <= 1024, T < 65536)");
+    EMO_REQUIRE(joint_ring_supported(head_super(B, T).Bs, head_super(B, T).Ts, 1, He, V) && He / 4 <= kHeadThreads,
+                EMO_UNSUPPORTED_SHAPE, "ctc_head: unsupported shape (B <= 1024, T < 65536)");
     EMO_REQUIRE((long long)B * T * He < (1ll << 31), EMO_UNSUPPORTED_SHAPE, "ctc_head: eouts exceeds 2^31 elements");
     EMO_REQUIRE(((uintptr_t)eouts & 15) == 0 && ((uintptr_t)w & 15) == 0, EMO_BAD_ARG,
                 "ctc_head: eouts / weight must be 16-byte aligned");
@@ -330,7 +363,7 @@ extern "C" int emo_ctc_head_supported(int B, int T, int He, int V, int Umax) {
     if (B <= 0 || T <= 0 || He <= 0 || V <= 0 || Umax < 1) return 0;
     if (2 * Umax + 1 > 1024 || He % 128 != 0 || He > kMaxKBlocks * kBlockK) return 0;
     if ((long long)B * T * He >= (1ll << 31)) return 0;
-    if (!joint_ring_supported(B, T, 1, He, V)) return 0;
+    if (T >= 65536 || !joint_ring_supported(head_super(B, T).Bs, head_super(B, T).Ts, 1, He, V)) return 0;
     // the ring kernel needs a resident CTA pair for every 256-row slab of the vocabulary plus producers / dh pairs
     return ceil_div(padded_vocab(V), 256) + 8 <= sm_count() / 2 ? 1 : 0;
 }
@@ -351,16 +384,18 @@ extern "C" int emo_ctc_head_fwd(const float* eouts, const float* w, const float*
     EMO_REQUIRE(ws_bytes >= L.total && ((uintptr_t)ws & 255) == 0, EMO_WORKSPACE_TOO_SMALL,
                 "ctc_head_fwd: workspace too small or not 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    head_prep_kernel<<<ceil_div(B, 128), 128, 0, st>>>(tlen, ulen, B, T, Umax, L.tlen32, L.ulen32, nullptr, nullptr,
-                                                       nullptr, nullptr);
+    const Super su = head_super(B, T);
+    head_prep_kernel<<<ceil_div(B, 128), 128, 0, st>>>(tlen, ulen, B, T, Umax, su.Ts, L.tlen32, L.ulen32, L.tsup32,
+                                                       nullptr, nullptr, nullptr, nullptr);
     EMO_CHECK_LAUNCH("head_prep_kernel");
     rc = head_casts(eouts, w, b, B, T, He, V, L, st);
     if (rc) return rc;
     const int Vp = padded_vocab(V);
     const float* bias = Vp != V ? L.b_pad : b;
     // dense part: lse[b,t] and the blank log-prob (lp2[..., 0]); labels are unused with one cell per frame
-    rc = joint_fwd_launch(L.w_bf16, L.e16, nullptr, bias, L.ulen32, L.tlen32, L.ulen32, B, T, 1, He, Vp, blank, L.lp2,
-                          lse, 1, st);
+    // (padded frames are ordinary rows here: their lse / blank log-prob are computed and never read)
+    rc = joint_fwd_launch(L.w_bf16, L.e16, nullptr, bias, L.ulen32, L.tsup32, L.ulen32, su.Bs, su.Ts, 1, He, Vp, blank,
+                          L.lp2, lse, 1, st);
     if (rc) return rc;
     const size_t smem = (size_t)kHeadFrames * He * sizeof(float);
     head_emission_kernel<<<dim3(ceil_div(T, kHeadFrames), B), kHeadThreads, smem, st>>>(
@@ -384,9 +419,12 @@ extern "C" int emo_ctc_head_bwd(const float* eouts, const float* w, const float*
     EMO_REQUIRE(ws_bytes >= L.total && ((uintptr_t)ws & 255) == 0, EMO_WORKSPACE_TOO_SMALL,
                 "ctc_head_bwd: workspace too small or not 256-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    head_prep_kernel<<<ceil_div(B, 128), 128, 0, st>>>(tlen, ulen, B, T, Umax, L.tlen32, L.ulen32, alpha_ws, grad_nll,
-                                                       L.geff, L.ll);
+    const Super su = head_super(B, T);
+    head_prep_kernel<<<ceil_div(B, 128), 128, 0, st>>>(tlen, ulen, B, T, Umax, su.Ts, L.tlen32, L.ulen32, L.tsup32,
+                                                       alpha_ws, grad_nll, L.geff, L.ll);
     EMO_CHECK_LAUNCH("head_prep_kernel");
+    head_grow_kernel<<<ceil_div((size_t)B * T, 256), 256, 0, st>>>(L.tlen32, L.geff, B, T, L.grow);
+    EMO_CHECK_LAUNCH("head_grow_kernel");
     rc = head_casts(eouts, w, b, B, T, He, V, L, st);
     if (rc) return rc;
     const int Vp = padded_vocab(V);
@@ -394,14 +432,14 @@ extern "C" int emo_ctc_head_bwd(const float* eouts, const float* w, const float*
     EMO_CUDA(cudaMemsetAsync(d_w, 0, (size_t)V * He * sizeof(float), st));
     EMO_CUDA(cudaMemsetAsync(d_b, 0, (size_t)V * sizeof(float), st));
     // dense part: dz = g softmax(z) -> d_W, d_b, dh (bf16, tile-major)
-    rc = joint_bwd_ring_launch(L.w_bf16, L.e16, nullptr, bias, L.ulen32, L.tlen32, L.ulen32, lse, nullptr, nullptr,
-                               L.geff, B, T, 1, He, Vp, V, blank, 1, L.dh, L.ring, d_w, d_b, st);
+    rc = joint_bwd_ring_launch(L.w_bf16, L.e16, nullptr, bias, L.ulen32, L.tsup32, L.ulen32, lse, nullptr, nullptr,
+                               L.grow, su.Bs, su.Ts, 1, He, Vp, V, blank, 1, L.dh, L.ring, d_w, d_b, st);
     if (rc) return rc;
     // sparse part: the entries of the blank-extended label sequence
     const size_t smem = (size_t)(Umax + 1) * kHeadFrames * sizeof(float);
     head_deouts_kernel<<<dim3(ceil_div(T, kHeadFrames), B), kHeadThreads, smem, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(L.dh), w, emis, alpha_ws, beta_ws, labels, L.tlen32, ulen, L.geff, L.ll, T,
-        He, V, Umax, blank, tiles128_per_utt(T, 1), L.occg, d_eouts, d_b);
+        He, V, Umax, blank, tiles128_per_utt(su.Ts, 1), B / su.Bs, L.occg, d_eouts, d_b);
     EMO_CHECK_LAUNCH("head_deouts_kernel");
     head_dw_kernel<<<dim3(ceil_div(Umax + 1, kHeadCols), B), kHeadThreads, 0, st>>>(
         eouts, L.occg, labels, L.tlen32, ulen, L.geff, T, He, V, Umax, blank, d_w);

@@ -72,7 +72,8 @@ struct RingArgs {
     float* d_b_out;
     int B, T, U1, J, V, blank;   // V = vocabulary padded to a multiple of 32 (pad rows of w_out are 0, pad bias -1e30)
     int Vout;                    // rows of d_w_out / entries of d_b_out (the caller's vocabulary)
-    int plain;                   // CTC head (ctc_head.cu): h = enc (no dec stream, no tanh), dz = g softmax(z), no patches
+    int plain;                   // CTC head (ctc_head.cu): h = enc (no dec stream, no tanh), dz = g softmax(z) with a
+                                 // PER-CELL grad_cost (B,T,U1), no blank / label patches
     int nP, nD, nS;             // pairs: producers, dh consumers, dW splits (x roles_v pairs)
     int NZ, NH, G;              // ring slots, vocab groups per tile
 };
@@ -208,12 +209,13 @@ __device__ __forceinline__ void p_load_raw(PRaw& r, const PTile& ti, int m, cons
         const int t = m / ti.U1b, u = m - t * ti.U1b;
         const size_t cell = ((size_t)ti.b * a.T + t) * a.U1 + u;
         r.valid = 1;
-        r.g = __ldg(a.grad_cost + ti.b);
         r.lse = __ldg(a.lse + cell);
-        if (a.plain) {   // dz = g softmax(z): unit weight, the blank / label patches are switched off by the caller
+        if (a.plain) {   // dz = g softmax(z): grad_cost is PER CELL here, unit weight, no blank / label patches
+            r.g = __ldg(a.grad_cost + cell);
             r.gm = make_float2(1.f, 0.f);
             return;
         }
+        r.g = __ldg(a.grad_cost + ti.b);
         r.gm = __ldg(reinterpret_cast<const float2*>(a.gamma2) + cell);
         r.lp = __ldg(reinterpret_cast<const float2*>(a.lp2) + cell);
         if (u < ti.U1b - 1) r.lab = __ldg(a.labels + (size_t)ti.b * (a.U1 - 1) + u);
@@ -358,7 +360,12 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
     cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = bars->tmem_base;
-    const int Q = s_prefix[a.B];
+    // Work unit of a producer pair = ring item = (pair tile q, vocab group g): units are dealt round-robin in item
+    // order, so the nP units in production at any time are CONSECUTIVE items and fit the ring whatever V is (a pair
+    // that kept a whole tile -- G items -- to itself would need nP * G slots to keep every producer busy).  For
+    // G > 1 the h tile is rebuilt per unit (cheap next to 4 vocab chunks of MMAs); G == 1 is one unit per tile.
+    constexpr int kCPG = kVG / kChunkN;        // vocab chunks per ring item
+    const int NI = s_prefix[a.B] * a.G;
 
     // register budget per warpgroup (x128 threads): control 40, two epilogue groups 128, two producer groups 88
     // = 472 of the 480 the CTA owns at launch (96 x 640); an exact fit deadlocks in setmaxnreg.inc
@@ -368,8 +375,9 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
             // ===================== TMA producer: w_out tiles [128 v x 64 j] per CTA =====================
             if (lane == 0) {
                 uint32_t stage = 0, phase = 0;
-                for (int q = pidx; q < Q; q += a.nP) {
-                    for (int nc = 0; nc < NC; ++nc) {
+                for (int it = pidx; it < NI; it += a.nP) {
+                    const int nc0 = (it % a.G) * kCPG, nc1 = min(nc0 + kCPG, NC);
+                    for (int nc = nc0; nc < nc1; ++nc) {
                         const int n = min(kChunkN, a.V - nc * kChunkN);
                         const int y = nc * kChunkN + (int)rank * (n >> 1);
                         for (int kb = 0; kb < KB; ++kb) {
@@ -389,8 +397,9 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
                 const uint32_t a_lo0 = ((smem_u32(sA) & 0x3FFFFu) >> 4) | (1u << 16);
                 const uint32_t b_lo0 = ((smem_u32(sB) & 0x3FFFFu) >> 4) | (1u << 16);
                 EMO_PROF(long long p_acc = 0, p_a = 0, p_b = 0, p_t0 = clock64(), p_c;)
-                for (int q = pidx; q < Q; q += a.nP) {
-                    for (int nc = 0; nc < NC; ++nc, ++cc) {
+                for (int it = pidx; it < NI; it += a.nP) {
+                    const int nc0 = (it % a.G) * kCPG, nc1 = min(nc0 + kCPG, NC);
+                    for (int nc = nc0; nc < nc1; ++nc, ++cc) {
                         const uint32_t buf = cc & 1;
                         EMO_PROF(p_c = clock64();)
                         mbar_wait(smem_u32(&bars->acc_empty[buf]), ((cc >> 1) & 1) ^ 1);
@@ -400,7 +409,7 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
                         const uint32_t d_tmem = tmem_base + buf * kChunkN;
                         for (int kb = 0; kb < KB; ++kb) {
                             EMO_PROF(p_c = clock64();)
-                            if (nc == 0) mbar_wait(smem_u32(&bars->a_full[kb]), tl & 1);
+                            if (nc == nc0) mbar_wait(smem_u32(&bars->a_full[kb]), tl & 1);
                             EMO_PROF(p_a += clock64() - p_c; p_c = clock64();)
                             mbar_wait(smem_u32(&bars->b_full[stage]), phase);
                             EMO_PROF(p_b += clock64() - p_c;)
@@ -413,7 +422,7 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
                                     umma_bf16_pair(d_tmem, mk_desc(a_lo + 2 * k16), mk_desc(b_lo + 2 * k16), idesc,
                                                    (kb | k16) != 0);
                                 umma_commit_pair(smem_u32(&bars->b_empty[stage]));
-                                if (nc == NC - 1) umma_commit_pair(smem_u32(&bars->a_empty[kb]));
+                                if (nc == nc1 - 1) umma_commit_pair(smem_u32(&bars->a_empty[kb]));
                                 if (kb == KB - 1) umma_commit_pair(smem_u32(&bars->acc_full[buf]));
                             }
                             __syncwarp();
@@ -430,7 +439,15 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
             // ===================== h writer: every finished h block -> ring =====================
             if (lane == 0) {
                 uint32_t tl = 0;
-                for (int q = pidx; q < Q; q += a.nP) {
+                for (int it = pidx; it < NI; it += a.nP, ++tl) {
+                    const int q = it / a.G;
+                    if (it % a.G != 0) {   // the tile's h goes to the ring with its first vocab group only
+                        for (int kb = 0; kb < KB; ++kb) {
+                            mbar_wait(smem_u32(&bars->h_ready[kb]), tl & 1);
+                            mbar_arrive(smem_u32(&bars->a_empty[kb]));
+                        }
+                        continue;
+                    }
                     const int hs = q % a.NH;
                     ring_wait(h_done + hs, (q / a.NH) * roles_v);
                     const int row0 = hs * kPairM + (int)rank * kTileM;
@@ -442,7 +459,6 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
                         mbar_arrive(smem_u32(&bars->a_empty[kb]));
                     }
                     ring_signal_stored(h_ready_g + hs);
-                    ++tl;
                 }
             }
         }
@@ -460,27 +476,33 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
         const int pblank = a.plain ? -1 : a.blank;   // plain: no blank patch
         int pending = -1;                      // z slot whose stores have been issued but not yet published
         EMO_PROF(long long p_sig = 0, p_gate = 0, p_accw = 0, p_t0 = clock64(), p_rd = 0, p_st = 0, p_bar = 0, p_ldw = 0;)
-        float nb = etid < a.V ? __ldg(a.b_out + etid) * kLog2e : 0.f;   // bias * log2e (see dz_group)
+        float nb;                              // bias * log2e of the chunk about to be processed (see dz_group)
         PTile ti;
         PRaw nxt;
-        if (pidx < Q) {
-            ptile(pidx, s_prefix, a.B, ti);
+        if (pidx < NI) {
+            ptile(pidx / a.G, s_prefix, a.B, ti);
             p_load_raw(nxt, ti, ti.first_cell + (int)rank * kTileM + row, a);
         }
-        for (int q = pidx; q < Q; q += a.nP) {
+        {   // bias of the first chunk of this pair's first unit
+            const int i0 = (pidx % a.G) * kCPG * kChunkN + etid;
+            nb = i0 < a.V ? __ldg(a.b_out + i0) * kLog2e : 0.f;
+        }
+        for (int it = pidx; it < NI; it += a.nP) {
+            const int nc0 = (it % a.G) * kCPG, nc1 = min(nc0 + kCPG, NC);
             const PCell cur = p_finish(nxt, a.V, a.blank);
             const bool anyneg = __any_sync(0xffffffffu, cur.sgn != 0u);
-            if (q + a.nP < Q) {   // next tile's scalars stay in flight during this tile
-                ptile(q + a.nP, s_prefix, a.B, ti);
+            if (it + a.nP < NI) {   // next unit's scalars stay in flight during this one
+                ptile((it + a.nP) / a.G, s_prefix, a.B, ti);
                 p_load_raw(nxt, ti, ti.first_cell + (int)rank * kTileM + row, a);
             }
-            for (int nc = 0; nc < NC; ++nc, ++cc) {
+            const int nnc0 = ((it + a.nP) % a.G) * kCPG;   // first chunk of the next unit
+            for (int nc = nc0; nc < nc1; ++nc, ++cc) {
                 const uint32_t buf = cc & 1;
                 const int n = min(kChunkN, a.V - nc * kChunkN);
                 float* bias = s_bias + buf * kChunkN;
                 bias[etid] = nb;
-                {   // prefetch the next chunk's bias (wraps to chunk 0 for the next tile)
-                    const int nn = (nc + 1 == NC) ? 0 : nc + 1;
+                {   // prefetch the next chunk's bias (the first chunk of the next unit after the last one of this)
+                    const int nn = (nc + 1 == nc1) ? nnc0 : nc + 1;
                     const int i0 = nn * kChunkN + etid;
                     nb = i0 < a.V ? __ldg(a.b_out + i0) * kLog2e : 0.f;
                 }
@@ -490,9 +512,9 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
                 mbar_wait(smem_u32(&bars->acc_full[buf]), (cc >> 1) & 1);
                 EMO_PROF(p_accw += clock64() - p_c0;)
                 tc_fence_after();
-                const int item = q * a.G + (nc >> 2);
+                const int item = it;               // == q * G + nc / kCPG
                 const int zs = item % a.NZ;
-                if ((nc & 3) == 0) {
+                if (nc == nc0) {
                     // first chunk of a ring item: publish the previous item (its stores were issued a chunk
                     // ago), then make sure every consumer has released this slot's previous content
                     if (lane == 0) {
@@ -548,14 +570,14 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
         const int c = lane & 7;        // 16-byte chunk (8 hidden units) inside the 64-wide K block
         const int rsub = lane >> 3;    // 4 rows per warp pass
         // flattened (tile, K block) sequence with two units of loads in flight
-        int lq = pidx - a.nP, lunit = KB;
+        int lq = pidx - a.nP, lunit = KB;      // lq: unit (tile, vocab group) index
         uint32_t eoff[4], doff[4];
         auto issue = [&](uint4 (&re)[4], uint4 (&rd)[4]) -> bool {
             if (lunit == KB) {
                 lq += a.nP;
-                if (lq >= Q) { lq = Q; return false; }
+                if (lq >= NI) { lq = NI; return false; }
                 PTile t;
-                ptile(lq, s_prefix, a.B, t);
+                ptile(lq / a.G, s_prefix, a.B, t);
 #pragma unroll
                 for (int p = 0; p < 4; ++p) {
                     const int row = pw * 16 + p * 4 + rsub;
@@ -1147,14 +1169,17 @@ size_t joint_ring_workspace(int B, int T, int U1, int J, int V) {
 }
 
 // Role split of the resident pairs.  The three roles execute one GEMM unit each; the producer also does the
-// tanh / exp work, so it gets the larger share (measured: profiles/r2*_ring_split.txt).
-void ring_split(int pairs, int V, int& nP, int& nD, int& nS) {
+// tanh / exp work, whose cost per logit does not depend on J, so its share grows when J shrinks.  Weights measured
+// at J = 512 (29 / 21 / 24 of 74 pairs at V = 1024; tools/gpu_ringprof.sh), the two gradient GEMMs scaled by J / 512.
+void ring_split(int pairs, int V, int J, int& nP, int& nD, int& nS) {
     const int roles_v = ceil_div(V, 256);
-    nS = max(1, (int)(pairs * 0.32f / roles_v + 0.5f));
+    const float j = (float)J / 512.f;
+    const float wP = 0.392f, wD = 0.284f * j, wW = 0.324f * j;
+    nS = max(1, (int)(pairs * wW / (wP + wD + wW) / roles_v + 0.5f));
     while (nS > 1 && pairs - nS * roles_v < 2) --nS;
     const int rest = pairs - nS * roles_v;
-    nD = max(1, (int)(rest * 0.42f + 0.5f));
-    nP = rest - nD;               // 74 pairs, V = 1024: 29 / 21 / 6 x 4
+    nD = min(rest - 1, max(1, (int)(rest * wD / (wP + wD) + 0.5f)));
+    nP = rest - nD;               // 74 pairs, V = 1024, J = 512: 29 / 21 / 6 x 4
 #if defined(EMO_TUNING) || defined(EMO_ZC_PROF)
     if (const char* e = getenv("EMO_RING_SPLIT")) {   // "nP,nD,nS": tuning builds only (tools/)
         int p, d, s;
@@ -1187,7 +1212,7 @@ int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec
     a.lse = lse; a.lp2 = lp2; a.gamma2 = gamma2; a.grad_cost = grad_cost; a.prefix = prefix; a.flags = flags;
     a.d_w_out = d_w_out; a.d_b_out = d_b_out;
     a.B = B; a.T = T; a.U1 = U1; a.J = J; a.V = V; a.Vout = Vout; a.blank = blank; a.plain = plain;
-    ring_split(pairs, V, a.nP, a.nD, a.nS);
+    ring_split(pairs, V, J, a.nP, a.nD, a.nS);
     a.NZ = g.NZ; a.NH = g.NH; a.G = g.G;
 
     ring_prep_kernel<<<1, kMaxB, 0, st>>>(tlen, ulen, B, T, U1, prefix, flags, 2 * g.NZ + 2 * g.NH);

@@ -53,7 +53,8 @@ enum emo_precision {
 enum emo_op {
     EMO_OP_RNNT_JOINT_FWD = 0,
     EMO_OP_RNNT_JOINT_BWD = 1,
-    EMO_OP_CTC = 2
+    EMO_OP_CTC = 2,
+    EMO_OP_CTC_HEAD = 3 /* emo_launch_count only: forward + backward of the fused CTC head (J = He) */
 };
 
 int emo_abi_version(void);

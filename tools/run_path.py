@@ -18,10 +18,23 @@ ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--precision", default="bf16")
 ap.add_argument("--no-backward", action="store_true")
 ap.add_argument("--ctc", action="store_true")
+ap.add_argument("--ctc-head", action="store_true", help="fused CTC head from eouts (J = enc hidden size)")
 a = ap.parse_args()
 dev = torch.device("cuda:0")
 g = torch.Generator().manual_seed(0)
-if a.ctc:
+if a.ctc_head:
+    He = a.J
+    eouts = torch.randn(a.B, a.T, He, generator=g).to(dev).requires_grad_()
+    lin = torch.nn.Linear(He, a.V).to(dev)
+    ys = torch.randint(4, a.V, (a.B, a.U), generator=g).to(dev)
+    tl = torch.full((a.B,), a.T, device=dev)
+    ul = torch.full((a.B,), a.U, device=dev)
+    for _ in range(a.iters):
+        lin.zero_grad(set_to_none=True)
+        loss = E.ctc_head_loss(eouts, lin.weight, lin.bias, ys, tl, ul, reduction="sum") / a.B
+        if not a.no_backward:
+            loss.backward()
+elif a.ctc:
     logits = torch.randn(a.B, a.T, a.V, generator=g).to(dev).requires_grad_()
     ys = torch.randint(4, a.V, (a.B, a.U), generator=g).to(dev)
     tl = torch.full((a.B,), a.T, device=dev)
