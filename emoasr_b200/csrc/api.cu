@@ -66,9 +66,10 @@ extern "C" int emo_launch_count(int op, int precision, int B, int T, int U1, int
                                               : joint_f32_launches(op, B, T, U1, J, V);
         case EMO_OP_CTC:
             return 3;  // row lse + emission gather, alpha || beta lattices, gradient
-        case EMO_OP_CTC_HEAD:   // J = He.  fwd: prep, 2 casts, joint forward, emissions, lattices; bwd: prep, 2 casts,
-                                // per-frame scale, ring prep, ring kernel, d_eouts, d_W (+ the vocabulary padding kernel in each)
-            return 14 + ((V + 31) / 32 * 32 != V ? 2 : 0);
+        case EMO_OP_CTC_HEAD:   // J = He.  fwd: prep, 2 casts, label-row gather, joint forward, emissions, lattices; bwd: prep,
+                                // 2 casts, gather, per-frame scale, ring prep, ring kernel, occupancies, d_eouts, d_W
+                                // (+ the vocabulary padding kernel in each)
+            return 17 + ((V + 31) / 32 * 32 != V ? 2 : 0);
         default:
             return 0;
     }

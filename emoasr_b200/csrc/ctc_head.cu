@@ -16,6 +16,8 @@
 //   head_dw_kernel         d_W[row_j,:] -= sum_t (g occ_j)[t] e[b,t,:]
 // with row_0 = blank (all blank states of a frame summed) and row_{1+u} = y_u.  The alpha / beta recursions are the
 // kernels of ctc.cu (ctc_lattice_launch).
+#include <mma.h>
+
 #include "joint_tc.cuh"
 
 namespace emo {
@@ -43,6 +45,9 @@ Super head_super(int B, int T) {
 struct HeadWs {
     __nv_bfloat16* w_bf16;   // (Vp, He)
     __half* e16;             // (B, T, He)
+    __nv_bfloat16* e_bf;     // (B * T + 16, He)  bf16(f16(e)): the A operand as the MMAs see it; 16 zero tail rows
+    __nv_bfloat16* wy;       // (B, Up, He) gathered weight rows {blank, y_0 ..}, Up = Umax + 1 rounded up to 16
+    float* bias_y;           // (B, Up)
     float* b_pad;            // (Vp)
     int* tlen32;             // (B)  clamp(tlen, 1, T)
     int* ulen32;             // (B)  0: one cell per frame
@@ -51,7 +56,7 @@ struct HeadWs {
     float* geff;             // bwd: (B) grad_nll, 0 for infeasible utterances
     float* grow;             // bwd: (B, T) per-frame gradient scale: geff[b] for t < T_b, else 0
     float* ll;               // bwd: (B) log-likelihood from the last alphas
-    float* occg;             // bwd: (B, T, Umax + 1) g * occupancy per (frame, {blank, label u})
+    __nv_bfloat16* occg;     // bwd: (B, Tp, Up) g * occupancy per (frame, {blank, label u}), Tp = T rounded up to 16
     void* dh;                // bwd: tile-major bf16 dh of the ring kernel
     void* ring;              // bwd: dz / h ring + flags
     size_t total;
@@ -69,6 +74,10 @@ HeadWs head_ws_layout(void* base, int op, int B, int T, int He, int V, int Umax)
     w.tlen32 = reinterpret_cast<int*>(take((size_t)B * sizeof(int)));
     w.ulen32 = reinterpret_cast<int*>(take((size_t)B * sizeof(int)));
     w.tsup32 = reinterpret_cast<int*>(take((size_t)B * sizeof(int)));
+    const size_t Up = (size_t)(Umax + 1 + 15) / 16 * 16, Tp = (size_t)(T + 15) / 16 * 16;
+    w.e_bf = reinterpret_cast<__nv_bfloat16*>(take(((size_t)B * T + 16) * He * sizeof(__nv_bfloat16)));
+    w.wy = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * Up * He * sizeof(__nv_bfloat16)));
+    w.bias_y = reinterpret_cast<float*>(take((size_t)B * Up * sizeof(float)));
     const Super su = head_super(B, T);
     w.grow = nullptr;
     w.lp2 = nullptr; w.geff = nullptr; w.ll = nullptr; w.occg = nullptr; w.dh = nullptr; w.ring = nullptr;
@@ -78,7 +87,7 @@ HeadWs head_ws_layout(void* base, int op, int B, int T, int He, int V, int Umax)
         w.geff = reinterpret_cast<float*>(take((size_t)B * sizeof(float)));
         w.ll = reinterpret_cast<float*>(take((size_t)B * sizeof(float)));
         w.grow = reinterpret_cast<float*>(take((size_t)B * T * sizeof(float)));
-        w.occg = reinterpret_cast<float*>(take((size_t)B * T * (Umax + 1) * sizeof(float)));
+        w.occg = reinterpret_cast<__nv_bfloat16*>(take((size_t)B * Tp * Up * sizeof(__nv_bfloat16)));
         w.dh = take(align_up(dh_bytes_for(su.Bs, su.Ts, 1, He), 1024));
         w.ring = take(joint_ring_workspace(su.Bs, su.Ts, 1, He, V));
     }
@@ -119,97 +128,129 @@ __global__ void head_grow_kernel(const int* __restrict__ tlen32, const float* __
     grow[i] = t < tlen32[b] ? geff[b] : 0.f;
 }
 
-// e as the tensor cores see it: fp32 -> fp16 (the stream cast) -> bf16 (the A producers)
-__device__ __forceinline__ float round_like_a_operand(__half x) { return __bfloat162float(__float2bfloat16_rn(__half2float(x))); }
+// ---- operands of the sparse (label) GEMMs ------------------------------------------------------------------------
+// e16 (fp16, the joint kernels' enc stream) and e_bf = bf16(f16(e)) -- the value the tensor-core A producers feed
+// the MMAs -- in one pass; padded frames (t >= T_b) are written as ZEROS in both, so that their rows contribute
+// exactly nothing (0 * h, also when the caller's padding holds Inf / NaN).
+__global__ void head_cast_e_kernel(const float* __restrict__ eouts, const int* __restrict__ tlen32, int T, int He,
+                                   size_t n, __half* __restrict__ e16, __nv_bfloat16* __restrict__ e_bf) {
+    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (i >= n) return;
+    const size_t row = i / He;
+    const int b = (int)(row / T), t = (int)(row - (size_t)b * T);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t < tlen32[b]) v = *reinterpret_cast<const float4*>(eouts + i);
+    const uint2 h = make_uint2(pack_f16x2(v.x, v.y), pack_f16x2(v.z, v.w));
+    *reinterpret_cast<uint2*>(e16 + i) = h;
+    const float2 a = unpack_f16x2(h.x), c = unpack_f16x2(h.y);
+    *reinterpret_cast<uint2*>(e_bf + i) = make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(c.x, c.y));
+}
 
-// emissions of the labels: block = (tile of kHeadFrames frames, utterance); thread = label u (stride blockDim)
-__global__ void __launch_bounds__(kHeadThreads)
-head_emission_kernel(const __half* __restrict__ e16, const __nv_bfloat16* __restrict__ w_bf16,
-                     const float* __restrict__ b_out, const float* __restrict__ lse, const float* __restrict__ lp2,
-                     const long long* __restrict__ labels, const int* __restrict__ tlen32,
-                     const long long* __restrict__ ulen, int T, int He, int V, int Umax, int blank,
-                     float* __restrict__ emis, float* __restrict__ lp_a, float* __restrict__ lp_b) {
-    extern __shared__ float s_e[];   // [kHeadFrames][He]
-    const int b = blockIdx.y, t0 = blockIdx.x * kHeadFrames;
+// wy[b][j][:] = w_bf16[row_j] (row_0 = blank, row_{1+u} = y_u, zero rows for j > U_b); bias_y[b][j] = b[row_j]
+__global__ void head_gather_kernel(const __nv_bfloat16* __restrict__ w_bf16, const float* __restrict__ b_out,
+                                   const long long* __restrict__ labels, const long long* __restrict__ ulen, int He,
+                                   int V, int Umax, int Up, int blank, __nv_bfloat16* __restrict__ wy,
+                                   float* __restrict__ bias_y) {
+    const int b = blockIdx.y, j = blockIdx.x;
+    const long long U_bl = ulen[b];
+    const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
+    const bool live = j <= U_b;
+    const int row = !live ? 0 : (j == 0 ? blank : clamp_label(labels[(size_t)b * Umax + j - 1], V));
+    uint4* dst = reinterpret_cast<uint4*>(wy + ((size_t)b * Up + j) * He);
+    const uint4* src = reinterpret_cast<const uint4*>(w_bf16 + (size_t)row * He);
+    for (int i = threadIdx.x; i < He / 8; i += blockDim.x) dst[i] = live ? __ldg(src + i) : make_uint4(0u, 0u, 0u, 0u);
+    if (threadIdx.x == 0) bias_y[(size_t)b * Up + j] = live ? b_out[row] : 0.f;
+}
+
+namespace wm = nvcuda::wmma;
+using FragA = wm::fragment<wm::matrix_a, 16, 16, 16, __nv_bfloat16, wm::row_major>;
+using FragAT = wm::fragment<wm::matrix_a, 16, 16, 16, __nv_bfloat16, wm::col_major>;
+using FragBT = wm::fragment<wm::matrix_b, 16, 16, 16, __nv_bfloat16, wm::col_major>;
+using FragB = wm::fragment<wm::matrix_b, 16, 16, 16, __nv_bfloat16, wm::row_major>;
+using FragC = wm::fragment<wm::accumulator, 16, 16, 16, float>;
+
+constexpr int kHeadWarps = 4;
+constexpr int kHeadNT = 8;   // 16-wide output tiles a warp keeps in registers
+
+// Emissions: C[frames x Up] = e_bf[frames x He] wy[b]^T + bias_y - lse, staged as the lattices' input.
+// Block = (16-frame tile, utterance); the 4 warps take the 16-wide label tiles round-robin (short dependent chains:
+// the kernel is bound by the latency of its fragment loads, not by their volume); warp-level bf16 MMAs on the
+// tensor-core path's own operand roundings, fp32 accumulation.
+__global__ void __launch_bounds__(kHeadWarps * 32)
+head_emission_kernel(const __nv_bfloat16* __restrict__ e_bf, const __nv_bfloat16* __restrict__ wy,
+                     const float* __restrict__ bias_y, const float* __restrict__ lse, const int* __restrict__ tlen32,
+                     const long long* __restrict__ ulen, int T, int He, int Umax, int Up, float* __restrict__ emis,
+                     float* __restrict__ lp_a, float* __restrict__ lp_b) {
+    __shared__ __align__(32) float s_c[kHeadWarps][16 * 16];
+    __shared__ float s_blank[16];
+    const int b = blockIdx.y, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = blockIdx.x * 16;
     const int T_b = tlen32[b];
     if (t0 >= T_b) return;
     const long long U_bl = ulen[b];
     const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
     const int S = 2 * Umax + 1;
-    const int nf = min(kHeadFrames, T_b - t0);
-    for (int i = threadIdx.x; i < kHeadFrames * He; i += blockDim.x) {
-        const int f = i / He, k = i - f * He;
-        s_e[i] = f < nf ? round_like_a_operand(e16[((size_t)b * T + t0 + f) * He + k]) : 0.f;
+    const __nv_bfloat16* arow = e_bf + ((size_t)b * T + t0) * He;
+    const __nv_bfloat16* wyb = wy + (size_t)b * Up * He;
+    const int ntiles = (U_b + 1 + 15) / 16;
+    for (int nt = warp; nt < ntiles; nt += kHeadWarps) {
+        FragC acc;
+        wm::fill_fragment(acc, 0.f);
+        const __nv_bfloat16* brow = wyb + (size_t)nt * 16 * He;
+#pragma unroll 4
+        for (int k0 = 0; k0 < He; k0 += 16) {
+            FragA fa;
+            FragBT fb;
+            wm::load_matrix_sync(fa, arow + k0, He);
+            wm::load_matrix_sync(fb, brow + k0, He);
+            wm::mma_sync(acc, fa, fb, acc);
+        }
+        wm::store_matrix_sync(s_c[warp], acc, 16, wm::mem_row_major);
+        __syncwarp();
+        for (int e = lane; e < 256; e += 32) {
+            const int f = e >> 4, j = nt * 16 + (e & 15);
+            if (t0 + f >= T_b || j > U_b) continue;
+            const size_t r = (size_t)b * T + t0 + f;
+            const float v = s_c[warp][e] + bias_y[(size_t)b * Up + j] - lse[r];
+            emis[r * (Umax + 1) + j] = v;
+            if (j > 0) {
+                lp_a[r * S + 2 * j - 1] = v;
+                if (lp_b) lp_b[r * S + 2 * j - 1] = v;
+            } else {
+                s_blank[f] = v;
+            }
+        }
+        __syncwarp();
     }
     __syncthreads();
-    const long long* y = labels + (size_t)b * Umax;
-    // blank states: the log-prob comes from the joint forward
-    for (int i = threadIdx.x; i < nf * (U_b + 1); i += blockDim.x) {
-        const int f = i / (U_b + 1), u = i - f * (U_b + 1);
+    // blank states (even s): the emission of column 0
+    for (int e = threadIdx.x; e < 16 * (U_b + 1); e += blockDim.x) {
+        const int f = e / (U_b + 1), u = e - f * (U_b + 1);
+        if (t0 + f >= T_b) continue;
         const size_t r = (size_t)b * T + t0 + f;
-        const float v = lp2[2 * r];
-        if (u == 0) emis[r * (Umax + 1)] = v;
+        const float v = s_blank[f];
         lp_a[r * S + 2 * u] = v;
         if (lp_b) lp_b[r * S + 2 * u] = v;
     }
-    for (int u = threadIdx.x; u < U_b; u += blockDim.x) {
-        const int lab = clamp_label(y[u], V);
-        const uint4* wrow = reinterpret_cast<const uint4*>(w_bf16 + (size_t)lab * He);
-        float acc[kHeadFrames];
-#pragma unroll
-        for (int f = 0; f < kHeadFrames; ++f) acc[f] = 0.f;
-        for (int k8 = 0; k8 < He / 8; ++k8) {
-            const uint4 wv = __ldg(wrow + k8);
-            const float w0 = __uint_as_float(wv.x << 16), w1 = __uint_as_float(wv.x & 0xffff0000u);
-            const float w2 = __uint_as_float(wv.y << 16), w3 = __uint_as_float(wv.y & 0xffff0000u);
-            const float w4 = __uint_as_float(wv.z << 16), w5 = __uint_as_float(wv.z & 0xffff0000u);
-            const float w6 = __uint_as_float(wv.w << 16), w7 = __uint_as_float(wv.w & 0xffff0000u);
-#pragma unroll
-            for (int f = 0; f < kHeadFrames; ++f) {
-                const float4 ea = *reinterpret_cast<const float4*>(s_e + f * He + k8 * 8);
-                const float4 eb = *reinterpret_cast<const float4*>(s_e + f * He + k8 * 8 + 4);
-                acc[f] = fmaf(ea.x, w0, fmaf(ea.y, w1, fmaf(ea.z, w2, fmaf(ea.w, w3, acc[f]))));
-                acc[f] = fmaf(eb.x, w4, fmaf(eb.y, w5, fmaf(eb.z, w6, fmaf(eb.w, w7, acc[f]))));
-            }
-        }
-        const float bias = __ldg(b_out + lab);
-#pragma unroll
-        for (int f = 0; f < kHeadFrames; ++f) {
-            if (f >= nf) break;
-            const size_t r = (size_t)b * T + t0 + f;
-            const float v = acc[f] + bias - lse[r];
-            emis[r * (Umax + 1) + 1 + u] = v;
-            lp_a[r * S + 2 * u + 1] = v;
-            if (lp_b) lp_b[r * S + 2 * u + 1] = v;
-        }
-    }
 }
 
-// d_eouts = dense part (dh, bf16, from the ring kernel) - g sum_j occ_j W[row_j]; g occ kept for the dW pass;
-// d_b[row_j] -= g sum_t occ_j.  Block = (tile of kHeadFrames frames, utterance); thread = 4 columns of He.
+// g * occupancy per (frame, {blank, label u}) as bf16 [B][Tp][Up], Tp = T rounded up to 16 (zeros for padded frames /
+// columns, so that the 16-frame MMA steps of the consumers never mix utterances), and the bias gradient of the sparse
+// part.  Block = (tile of kHeadFrames frames, utterance).
 __global__ void __launch_bounds__(kHeadThreads)
-head_deouts_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict__ w, const float* __restrict__ emis,
-                   const float* __restrict__ alpha_ws, const float* __restrict__ beta_ws,
-                   const long long* __restrict__ labels, const int* __restrict__ tlen32,
-                   const long long* __restrict__ ulen, const float* __restrict__ geff, const float* __restrict__ ll,
-                   int T, int He, int V, int Umax, int blank, int tpu, int per_super, float* __restrict__ occg,
-                   float* __restrict__ d_eouts, float* __restrict__ d_b) {
-    extern __shared__ float s_occ[];   // [Umax + 1][kHeadFrames]
+head_occ_kernel(const float* __restrict__ emis, const float* __restrict__ alpha_ws, const float* __restrict__ beta_ws,
+                const long long* __restrict__ labels, const int* __restrict__ tlen32, const long long* __restrict__ ulen,
+                const float* __restrict__ geff, const float* __restrict__ ll, int T, int Tp, int V, int Umax, int Up,
+                int blank, __nv_bfloat16* __restrict__ occg, float* __restrict__ d_b) {
+    extern __shared__ float s_occ[];   // [Up][kHeadFrames]
     const int b = blockIdx.y, t0 = blockIdx.x * kHeadFrames;
     const int T_b = tlen32[b];
-    const int c4 = threadIdx.x * 4;
-    if (t0 >= T_b) {   // padded frames: zero gradient
-        for (int f = 0; f < kHeadFrames && t0 + f < T; ++f)
-            if (c4 < He) *reinterpret_cast<float4*>(d_eouts + ((size_t)b * T + t0 + f) * He + c4) = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
-    }
     const long long U_bl = ulen[b];
     const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
     const int S = 2 * Umax + 1, S_b = 2 * U_b + 1;
-    const int nf = min(kHeadFrames, T_b - t0);
+    const int nf = max(0, min(kHeadFrames, T_b - t0));
     const float g = geff[b], l = ll[b];
-    const long long* y = labels + (size_t)b * Umax;
-    for (int i = threadIdx.x; i < (Umax + 1) * kHeadFrames; i += blockDim.x) s_occ[i] = 0.f;
+    for (int i = threadIdx.x; i < Up * kHeadFrames; i += blockDim.x) s_occ[i] = 0.f;
     __syncthreads();
     if (g != 0.f) {
         for (int i = threadIdx.x; i < S_b * kHeadFrames; i += blockDim.x) {
@@ -225,12 +266,12 @@ head_deouts_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict
         }
     }
     __syncthreads();
-    // keep g occ for the dW pass; bias gradient
-    for (int i = threadIdx.x; i < (U_b + 1) * kHeadFrames; i += blockDim.x) {
-        const int j = i / kHeadFrames, f = i - j * kHeadFrames;
-        if (f < nf) occg[((size_t)b * T + t0 + f) * (Umax + 1) + j] = s_occ[i];
+    for (int i = threadIdx.x; i < Up * kHeadFrames; i += blockDim.x) {
+        const int f = i / Up, j = i - f * Up;
+        if (t0 + f < Tp) occg[((size_t)b * Tp + t0 + f) * Up + j] = __float2bfloat16_rn(s_occ[j * kHeadFrames + f]);
     }
     if (g != 0.f) {
+        const long long* y = labels + (size_t)b * Umax;
         for (int j = threadIdx.x; j <= U_b; j += blockDim.x) {
             float sum = 0.f;
 #pragma unroll
@@ -238,86 +279,108 @@ head_deouts_kernel(const __nv_bfloat16* __restrict__ dh, const float* __restrict
             if (sum != 0.f) atomicAdd(d_b + (j == 0 ? blank : clamp_label(y[j - 1], V)), -sum);
         }
     }
-    if (c4 >= He) return;
-    float acc[kHeadFrames][4];
+}
+
+// d_eouts[frames x He] = dh (dense part, bf16, from the ring kernel) - occg[frames x Up] wy[b][Up x He].
+// Block = (16-frame tile, 256-column slab, utterance); warp = 16 frames x 64 columns.
+constexpr int kDeNT = 4;
+__global__ void __launch_bounds__(kHeadWarps * 32)
+head_deouts_kernel(const __nv_bfloat16* __restrict__ dh, const __nv_bfloat16* __restrict__ occg,
+                   const __nv_bfloat16* __restrict__ wy, const int* __restrict__ tlen32,
+                   const long long* __restrict__ ulen, const float* __restrict__ geff, int T, int Tp, int He, int Umax,
+                   int Up, int tpu, int per_super, float* __restrict__ d_eouts) {
+    __shared__ __align__(32) float s_c[kHeadWarps][16 * kDeNT * 16];
+    const int b = blockIdx.z, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int t0 = blockIdx.x * 16;
+    const int c0 = (blockIdx.y * kHeadWarps + warp) * (kDeNT * 16);
+    if (c0 >= He) return;
+    const int T_b = tlen32[b];
+    const long long U_bl = ulen[b];
+    const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
+    FragC acc[kDeNT];
 #pragma unroll
-    for (int f = 0; f < kHeadFrames; ++f) acc[f][0] = acc[f][1] = acc[f][2] = acc[f][3] = 0.f;
-    if (g != 0.f) {
-        for (int j = 0; j <= U_b; ++j) {
-            const int row = j == 0 ? blank : clamp_label(y[j - 1], V);
-            const float4 wv = __ldg(reinterpret_cast<const float4*>(w + (size_t)row * He + c4));
-            const float4 oa = *reinterpret_cast<const float4*>(s_occ + j * kHeadFrames);
-            const float4 ob = *reinterpret_cast<const float4*>(s_occ + j * kHeadFrames + 4);
-            const float o[8] = {oa.x, oa.y, oa.z, oa.w, ob.x, ob.y, ob.z, ob.w};
+    for (int i = 0; i < kDeNT; ++i) wm::fill_fragment(acc[i], 0.f);
+    if (t0 < T_b && geff[b] != 0.f) {
+        const __nv_bfloat16* arow = occg + ((size_t)b * Tp + t0) * Up;
+        const __nv_bfloat16* wyb = wy + (size_t)b * Up * He + c0;
+        for (int k0 = 0; k0 <= U_b; k0 += 16) {
+            FragA fa;
+            wm::load_matrix_sync(fa, arow + k0, Up);
 #pragma unroll
-            for (int f = 0; f < kHeadFrames; ++f) {
-                acc[f][0] = fmaf(o[f], wv.x, acc[f][0]);
-                acc[f][1] = fmaf(o[f], wv.y, acc[f][1]);
-                acc[f][2] = fmaf(o[f], wv.z, acc[f][2]);
-                acc[f][3] = fmaf(o[f], wv.w, acc[f][3]);
+            for (int i = 0; i < kDeNT; ++i) {
+                FragB fb;
+                wm::load_matrix_sync(fb, wyb + (size_t)k0 * He + i * 16, He);
+                wm::mma_sync(acc[i], fa, fb, acc[i]);
             }
         }
     }
 #pragma unroll
-    for (int f = 0; f < kHeadFrames; ++f) {
-        if (t0 + f >= T) break;
-        float4 out = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (f < nf) {
+    for (int i = 0; i < kDeNT; ++i) wm::store_matrix_sync(s_c[warp] + i * 16, acc[i], kDeNT * 16, wm::mem_row_major);
+    __syncwarp();
+    // lane -> (frame f = lane / 2 .. , 8 consecutive columns): 16-byte dh loads, two 16-byte stores
+#pragma unroll
+    for (int it = 0; it < (16 * kDeNT * 16) / (32 * 8); ++it) {
+        const int e8 = it * 32 + lane;               // index of an 8-column group of the 16 x 64 tile
+        const int f = e8 / (kDeNT * 2), cc = (e8 % (kDeNT * 2)) * 8;
+        if (t0 + f >= T) continue;
+        float4 o0 = make_float4(0.f, 0.f, 0.f, 0.f), o1 = o0;
+        if (t0 + f < T_b) {
             // tile-major dh with one cell per frame: row = super-utterance * tpu * 128 + frame inside it
             const size_t row = (size_t)(b / per_super) * tpu * kTileM + (size_t)(b % per_super) * T + t0 + f;
-            const uint2 dv = *reinterpret_cast<const uint2*>(dh + row * He + c4);
-            out.x = __uint_as_float(dv.x << 16) - acc[f][0];
-            out.y = __uint_as_float(dv.x & 0xffff0000u) - acc[f][1];
-            out.z = __uint_as_float(dv.y << 16) - acc[f][2];
-            out.w = __uint_as_float(dv.y & 0xffff0000u) - acc[f][3];
+            const uint4 dv = *reinterpret_cast<const uint4*>(dh + row * He + c0 + cc);
+            const float* sc = s_c[warp] + f * (kDeNT * 16) + cc;
+            o0.x = __uint_as_float(dv.x << 16) - sc[0]; o0.y = __uint_as_float(dv.x & 0xffff0000u) - sc[1];
+            o0.z = __uint_as_float(dv.y << 16) - sc[2]; o0.w = __uint_as_float(dv.y & 0xffff0000u) - sc[3];
+            o1.x = __uint_as_float(dv.z << 16) - sc[4]; o1.y = __uint_as_float(dv.z & 0xffff0000u) - sc[5];
+            o1.z = __uint_as_float(dv.w << 16) - sc[6]; o1.w = __uint_as_float(dv.w & 0xffff0000u) - sc[7];
         }
-        *reinterpret_cast<float4*>(d_eouts + ((size_t)b * T + t0 + f) * He + c4) = out;
+        float4* dst = reinterpret_cast<float4*>(d_eouts + ((size_t)b * T + t0 + f) * He + c0 + cc);
+        dst[0] = o0;
+        dst[1] = o1;
     }
 }
 
-// d_W[row_j,:] -= sum_t (g occ_j)[t] e[b,t,:].  Block = (8 columns j of the utterance's {blank, labels}, utterance);
-// thread = 4 columns of He.
-constexpr int kHeadCols = 8;
-__global__ void __launch_bounds__(kHeadThreads)
-head_dw_kernel(const float* __restrict__ eouts, const float* __restrict__ occg, const long long* __restrict__ labels,
-               const int* __restrict__ tlen32, const long long* __restrict__ ulen, const float* __restrict__ geff,
-               int T, int He, int V, int Umax, int blank, float* __restrict__ d_w) {
-    const int b = blockIdx.y, j0 = blockIdx.x * kHeadCols;
+// d_W[row_j,:] -= sum_t occg[t][j] e_bf[b,t,:]:  C[16 j x 128 cols] = occg^T[16 x T_b] e_bf[T_b x 128].
+// Block = (16 columns j of the utterance's {blank, labels}, 128-column slab, utterance); the 4 warps split the frames
+// and are summed through shared memory before the scatter.
+__global__ void __launch_bounds__(kHeadWarps * 32)
+head_dw_kernel(const __nv_bfloat16* __restrict__ e_bf, const __nv_bfloat16* __restrict__ occg,
+               const long long* __restrict__ labels, const int* __restrict__ tlen32, const long long* __restrict__ ulen,
+               const float* __restrict__ geff, int T, int Tp, int He, int V, int Umax, int Up, int blank,
+               float* __restrict__ d_w) {
+    __shared__ __align__(32) float s_c[kHeadWarps][16 * kHeadNT * 16];
+    const int b = blockIdx.z, j0 = blockIdx.x * 16, c0 = blockIdx.y * (kHeadNT * 16);
     const long long U_bl = ulen[b];
     const int U_b = (int)(U_bl < 0 ? 0 : (U_bl > Umax ? Umax : U_bl));
     if (j0 > U_b || geff[b] == 0.f) return;
-    const int c4 = threadIdx.x * 4;
-    if (c4 >= He) return;
+    const int warp = threadIdx.x >> 5;
     const int T_b = tlen32[b];
-    const int nj = min(kHeadCols, U_b + 1 - j0);
-    float acc[kHeadCols][4];
+    FragC acc[kHeadNT];
 #pragma unroll
-    for (int j = 0; j < kHeadCols; ++j) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f;
-    const float* ob = occg + (size_t)b * T * (Umax + 1) + j0;
-    const float* eb = eouts + (size_t)b * T * He + c4;
-#pragma unroll 4
-    for (int t = 0; t < T_b; ++t) {
-        const float4 ev = __ldg(reinterpret_cast<const float4*>(eb + (size_t)t * He));
-        const float* o = ob + (size_t)t * (Umax + 1);
+    for (int i = 0; i < kHeadNT; ++i) wm::fill_fragment(acc[i], 0.f);
+    // frames past T_b inside the last 16-frame step: the occg rows are zero there (own padded rows, [B][Tp][Up]); the
+    // e_bf rows are zero (padded frames), the next utterance's first frames or the buffer's zeroed tail -- all finite
+    for (int k0 = warp * 16; k0 < T_b; k0 += kHeadWarps * 16) {
+        FragAT fa;
+        wm::load_matrix_sync(fa, occg + ((size_t)b * Tp + k0) * Up + j0, Up);
+        const __nv_bfloat16* brow = e_bf + ((size_t)b * T + k0) * He + c0;
 #pragma unroll
-        for (int j = 0; j < kHeadCols; ++j) {
-            const float ov = j < nj ? __ldg(o + j) : 0.f;
-            acc[j][0] = fmaf(ov, ev.x, acc[j][0]);
-            acc[j][1] = fmaf(ov, ev.y, acc[j][1]);
-            acc[j][2] = fmaf(ov, ev.z, acc[j][2]);
-            acc[j][3] = fmaf(ov, ev.w, acc[j][3]);
+        for (int i = 0; i < kHeadNT; ++i) {
+            FragB fb;
+            wm::load_matrix_sync(fb, brow + i * 16, He);
+            wm::mma_sync(acc[i], fa, fb, acc[i]);
         }
     }
-    const long long* y = labels + (size_t)b * Umax;
 #pragma unroll
-    for (int j = 0; j < kHeadCols; ++j) {
-        if (j >= nj) break;
-        const int jj = j0 + j;
+    for (int i = 0; i < kHeadNT; ++i) wm::store_matrix_sync(s_c[warp] + i * 16, acc[i], kHeadNT * 16, wm::mem_row_major);
+    __syncthreads();
+    const long long* y = labels + (size_t)b * Umax;
+    for (int e = threadIdx.x; e < 16 * kHeadNT * 16; e += blockDim.x) {
+        const int jj = j0 + e / (kHeadNT * 16), c = c0 + e % (kHeadNT * 16);
+        if (jj > U_b) continue;
+        const float v = s_c[0][e] + s_c[1][e] + s_c[2][e] + s_c[3][e];
         const int row = jj == 0 ? blank : clamp_label(y[jj - 1], V);
-        float* dst = d_w + (size_t)row * He + c4;
-        asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(-acc[j][0]), "f"(-acc[j][1]),
-                     "f"(-acc[j][2]), "f"(-acc[j][3])
-                     : "memory");
+        if (v != 0.f) atomicAdd(d_w + (size_t)row * He + c, -v);
     }
 }
 
@@ -330,7 +393,7 @@ int head_check(const void* eouts, const void* w, const void* b, const void* labe
                 2 * Umax + 1);
     EMO_REQUIRE(He % 128 == 0 && He <= kMaxKBlocks * kBlockK, EMO_UNSUPPORTED_SHAPE,
                 "ctc_head: enc_hidden_size %d must be a multiple of 128 and <= 512 (use the unfused CTC loss)", He);
-    EMO_REQUIRE(joint_ring_supported(head_super(B, T).Bs, head_super(B, T).Ts, 1, He, V) && He / 4 <= kHeadThreads,
+    EMO_REQUIRE(joint_ring_supported(head_super(B, T).Bs, head_super(B, T).Ts, 1, He, V) && He % (kHeadNT * 16) == 0,
                 EMO_UNSUPPORTED_SHAPE, "ctc_head: unsupported shape (B <= 1024, T < 65536)");
     EMO_REQUIRE((long long)B * T * He < (1ll << 31), EMO_UNSUPPORTED_SHAPE, "ctc_head: eouts exceeds 2^31 elements");
     EMO_REQUIRE(((uintptr_t)eouts & 15) == 0 && ((uintptr_t)w & 15) == 0, EMO_BAD_ARG,
@@ -338,19 +401,23 @@ int head_check(const void* eouts, const void* w, const void* b, const void* labe
     return EMO_OK;
 }
 
-int head_casts(const float* eouts, const float* w, const float* b, int B, int T, int He, int V, const HeadWs& ws,
-               cudaStream_t st) {
+int head_casts(const float* eouts, const float* w, const float* b, const long long* labels, const long long* ulen,
+               int B, int T, int He, int V, int Umax, int blank, const HeadWs& ws, cudaStream_t st) {
     const int Vp = padded_vocab(V);
+    const int Up = (Umax + 1 + 15) / 16 * 16;
     const size_t nw = (size_t)V * He, ne = (size_t)B * T * He;
     f32_to_bf16_kernel<<<ceil_div(nw, 4 * 256), 256, 0, st>>>(w, ws.w_bf16, nw);
     EMO_CHECK_LAUNCH("f32_to_bf16_kernel");
-    f32_to_f16_kernel<<<ceil_div(ne, 4 * 256), 256, 0, st>>>(eouts, ws.e16, ne);
-    EMO_CHECK_LAUNCH("f32_to_f16_kernel");
+    head_cast_e_kernel<<<ceil_div(ne, 4 * 256), 256, 0, st>>>(eouts, ws.tlen32, T, He, ne, ws.e16, ws.e_bf);
+    EMO_CHECK_LAUNCH("head_cast_e_kernel");
+    EMO_CUDA(cudaMemsetAsync(ws.e_bf + ne, 0, (size_t)16 * He * sizeof(__nv_bfloat16), st));
     if (Vp != V) {
         const size_t n_tail = (size_t)(Vp - V) * He;
         pad_vocab_kernel<<<ceil_div(max(n_tail, (size_t)Vp), 256), 256, 0, st>>>(ws.w_bf16 + nw, n_tail, b, ws.b_pad, V, Vp);
         EMO_CHECK_LAUNCH("pad_vocab_kernel");
     }
+    head_gather_kernel<<<dim3(Up, B), 32, 0, st>>>(ws.w_bf16, b, labels, ulen, He, V, Umax, Up, blank, ws.wy, ws.bias_y);
+    EMO_CHECK_LAUNCH("head_gather_kernel");
     return EMO_OK;
 }
 
@@ -388,7 +455,7 @@ extern "C" int emo_ctc_head_fwd(const float* eouts, const float* w, const float*
     head_prep_kernel<<<ceil_div(B, 128), 128, 0, st>>>(tlen, ulen, B, T, Umax, su.Ts, L.tlen32, L.ulen32, L.tsup32,
                                                        nullptr, nullptr, nullptr, nullptr);
     EMO_CHECK_LAUNCH("head_prep_kernel");
-    rc = head_casts(eouts, w, b, B, T, He, V, L, st);
+    rc = head_casts(eouts, w, b, labels, ulen, B, T, He, V, Umax, blank, L, st);
     if (rc) return rc;
     const int Vp = padded_vocab(V);
     const float* bias = Vp != V ? L.b_pad : b;
@@ -397,9 +464,9 @@ extern "C" int emo_ctc_head_fwd(const float* eouts, const float* w, const float*
     rc = joint_fwd_launch(L.w_bf16, L.e16, nullptr, bias, L.ulen32, L.tsup32, L.ulen32, su.Bs, su.Ts, 1, He, Vp, blank,
                           L.lp2, lse, 1, st);
     if (rc) return rc;
-    const size_t smem = (size_t)kHeadFrames * He * sizeof(float);
-    head_emission_kernel<<<dim3(ceil_div(T, kHeadFrames), B), kHeadThreads, smem, st>>>(
-        L.e16, L.w_bf16, b, lse, L.lp2, labels, L.tlen32, ulen, T, He, V, Umax, blank, emis, alpha_ws, beta_ws);
+    const int Up = (Umax + 1 + 15) / 16 * 16;
+    head_emission_kernel<<<dim3(ceil_div(T, 16), B), kHeadWarps * 32, 0, st>>>(
+        L.e_bf, L.wy, L.bias_y, lse, L.tlen32, ulen, T, He, Umax, Up, emis, alpha_ws, beta_ws);
     EMO_CHECK_LAUNCH("head_emission_kernel");
     return ctc_lattice_launch(labels, tlen, ulen, B, T, V, Umax, blank, zero_infinity, alpha_ws, beta_ws, nll, st);
 }
@@ -425,7 +492,7 @@ extern "C" int emo_ctc_head_bwd(const float* eouts, const float* w, const float*
     EMO_CHECK_LAUNCH("head_prep_kernel");
     head_grow_kernel<<<ceil_div((size_t)B * T, 256), 256, 0, st>>>(L.tlen32, L.geff, B, T, L.grow);
     EMO_CHECK_LAUNCH("head_grow_kernel");
-    rc = head_casts(eouts, w, b, B, T, He, V, L, st);
+    rc = head_casts(eouts, w, b, labels, ulen, B, T, He, V, Umax, blank, L, st);
     if (rc) return rc;
     const int Vp = padded_vocab(V);
     const float* bias = Vp != V ? L.b_pad : b;
@@ -436,13 +503,16 @@ extern "C" int emo_ctc_head_bwd(const float* eouts, const float* w, const float*
                                L.grow, su.Bs, su.Ts, 1, He, Vp, V, blank, 1, L.dh, L.ring, d_w, d_b, st);
     if (rc) return rc;
     // sparse part: the entries of the blank-extended label sequence
-    const size_t smem = (size_t)(Umax + 1) * kHeadFrames * sizeof(float);
-    head_deouts_kernel<<<dim3(ceil_div(T, kHeadFrames), B), kHeadThreads, smem, st>>>(
-        reinterpret_cast<const __nv_bfloat16*>(L.dh), w, emis, alpha_ws, beta_ws, labels, L.tlen32, ulen, L.geff, L.ll, T,
-        He, V, Umax, blank, tiles128_per_utt(su.Ts, 1), B / su.Bs, L.occg, d_eouts, d_b);
+    const int Up = (Umax + 1 + 15) / 16 * 16, Tp = (T + 15) / 16 * 16;
+    head_occ_kernel<<<dim3(Tp / kHeadFrames, B), kHeadThreads, (size_t)Up * kHeadFrames * sizeof(float), st>>>(
+        emis, alpha_ws, beta_ws, labels, L.tlen32, ulen, L.geff, L.ll, T, Tp, V, Umax, Up, blank, L.occg, d_b);
+    EMO_CHECK_LAUNCH("head_occ_kernel");
+    head_deouts_kernel<<<dim3(ceil_div(T, 16), ceil_div(He, kHeadWarps * kDeNT * 16), B), kHeadWarps * 32, 0, st>>>(
+        reinterpret_cast<const __nv_bfloat16*>(L.dh), L.occg, L.wy, L.tlen32, ulen, L.geff, T, Tp, He, Umax, Up,
+        tiles128_per_utt(su.Ts, 1), B / su.Bs, d_eouts);
     EMO_CHECK_LAUNCH("head_deouts_kernel");
-    head_dw_kernel<<<dim3(ceil_div(Umax + 1, kHeadCols), B), kHeadThreads, 0, st>>>(
-        eouts, L.occg, labels, L.tlen32, ulen, L.geff, T, He, V, Umax, blank, d_w);
+    head_dw_kernel<<<dim3(Up / 16, He / (kHeadNT * 16), B), kHeadWarps * 32, 0, st>>>(
+        L.e_bf, L.occg, labels, L.tlen32, ulen, L.geff, T, Tp, He, V, Umax, Up, blank, d_w);
     EMO_CHECK_LAUNCH("head_dw_kernel");
     return EMO_OK;
 }
