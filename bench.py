@@ -393,7 +393,9 @@ def run_ours_ctc(args, w, rank, world, dev):
     resident = [t.to(dev) for t in host]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     from emoasr_b200 import functional as EF
-    fused = EF.ctc_head_supported(B, T, He, V, w["U"]) and not getattr(args, "ctc_unfused", False)
+    # the drop-in decoder's rule (decoders.FusedCTCForward): fused head from 8192 frames per batch upwards
+    fused = (EF.ctc_head_supported(B, T, He, V, w["U"]) and not getattr(args, "ctc_unfused", False)
+             and (B * T >= 8192 or getattr(args, "ctc_fused", False)))
     step = ctc_step_fn(E, wl, B, fused)
     for _ in range(args.warmup):
         step(*resident)
@@ -722,6 +724,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
     ap.add_argument("--ctc-unfused", action="store_true", help="CTC workloads: cuBLAS Linear + loss kernels on logits")
+    ap.add_argument("--ctc-fused", action="store_true", help="CTC workloads: fused head also below 8192 frames")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     w = WORKLOADS[args.workload]

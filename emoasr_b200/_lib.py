@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("EMOASR_B200_LIB") or os.path.join(_HERE, "lib", "libe
 
 OP_RNNT_JOINT_FWD, OP_RNNT_JOINT_BWD, OP_CTC, OP_CTC_HEAD = 0, 1, 2, 3
 PREC_FP32, PREC_BF16 = 0, 1
-ABI_VERSION = 6
+ABI_VERSION = 7
 
 _c = ctypes
 _P = _c.c_void_p
@@ -35,6 +35,9 @@ _SIGNATURES = {
     "emo_ctc_head_workspace_bytes": (_SZ, [_I] * 6),
     "emo_ctc_head_fwd": (_I, [_P] * 6 + [_I] * 7 + [_P] * 6 + [_SZ, _P]),
     "emo_ctc_head_bwd": (_I, [_P] * 11 + [_I] * 6 + [_P] * 4 + [_SZ, _P]),
+    "emo_rnnt_step_workspace_bytes": (_SZ, [_I]),
+    "emo_rnnt_joint_step": (_I, [_P] * 5 + [_I] * 3 + [_P] * 3 + [_SZ, _P]),
+    "emo_rnnt_greedy_step": (_I, [_P] * 5 + [_I] * 6 + [_P] * 5 + [_I] + [_P] * 4 + [_SZ, _P]),
 }
 EXPORTS = tuple(_SIGNATURES)
 

@@ -41,6 +41,9 @@ class FusedCTCForward:
     lm/modeling/p2w.py, outside this path); shapes the tensor-core path does not take fall back to the fp32 route."""
 
     fused_precision = "fp32"
+    # below this many frames per batch the persistent tensor-core kernels cannot fill the GPU (a 256-frame tile per
+    # CTA pair, 74 pairs) and the cuBLAS Linear + loss kernels are faster: cfg 1 (B=8, T=249) 0.33 vs 0.53 ms
+    fused_head_min_frames = 8192
 
     def _fused_ctc(self, logits, ys, elens, ylens):
         nll = F.ctc_loss(logits, ys, elens, ylens, blank=self.blank_id, zero_infinity=True)
@@ -49,6 +52,7 @@ class FusedCTCForward:
     def _head_loss(self, linear, eouts, ys, elens, ylens):
         """(loss, logits or None) of one head (a Linear + CTC): fused from eouts when the tensor-core path takes it."""
         if (self.fused_precision == "bf16" and eouts.is_cuda and linear.bias is not None and
+                eouts.size(0) * eouts.size(1) >= self.fused_head_min_frames and
                 F.ctc_head_supported(eouts.size(0), eouts.size(1), eouts.size(2), linear.weight.size(0), ys.size(1))):
             nll = F.ctc_head_loss(eouts, linear.weight, linear.bias, ys, elens, ylens, blank=self.blank_id,
                                   zero_infinity=True)
@@ -137,6 +141,75 @@ class FusedRNNTForward:
         return loss, loss_dict, None
 
 
+class FusedRNNTSearch:
+    """Decode-time side of the RNN-T decoder: the joint of the search loops
+    (rnn_transducer.py:194-325) as one launch per step instead of (1,1,.) cuBLAS calls + tanh + argmax + .item().
+
+    * ``joint()`` keeps the reference's signature; single-cell calls on CUDA without autograd -- what ``_greedy``
+      and ``_beam_search`` make -- go through ``emo_rnnt_joint_step`` (the beam's hypotheses are the rows).
+    * ``_greedy()`` is replaced by a batched search: all utterances advance together, the per-step joint + argmax +
+      bookkeeping is ``emo_rnnt_greedy_step`` (no token is read back inside the loop), the prediction network runs
+      batched for the rows that emitted.  Returns the reference's ``(hyps, scores, logits, aligns)``."""
+
+    greedy_poll = 32   # steps between host polls of the "rows still active" counter
+
+    def joint(self, eouts, douts):
+        J = self.w_enc.weight.size(0)
+        if (eouts.is_cuda and eouts.size(1) == 1 and douts.size(1) == 1 and J % 4 == 0 and
+                not (torch.is_grad_enabled() and (eouts.requires_grad or douts.requires_grad or
+                                                  self.output.weight.requires_grad)) and
+                (eouts.size(0) == douts.size(0) or eouts.size(0) == 1 or douts.size(0) == 1)):
+            with torch.no_grad():
+                enc_proj = self.w_enc(eouts[:, 0])               # (Be, J)
+                dec_proj = self.w_dec(douts[:, 0])               # (Bd, J)
+                N = max(enc_proj.size(0), dec_proj.size(0))
+                row = None
+                if enc_proj.size(0) == 1 and N > 1:              # one frame against a beam of hypotheses
+                    row = torch.zeros(N, dtype=torch.int32, device=eouts.device)
+                if dec_proj.size(0) == 1 and N > 1:
+                    dec_proj = dec_proj.expand(N, -1)
+                logits, _ = F.joint_step(enc_proj, dec_proj, self.output.weight, self.output.bias, enc_row=row)
+            return logits.view(N, 1, 1, -1)
+        return self._dense_joint(eouts, douts)
+
+    def _dense_joint(self, eouts, douts):
+        mro = type(self).__mro__
+        for cls in mro[mro.index(FusedRNNTSearch) + 1:]:       # the reference's own joint when installed over it
+            j = cls.__dict__.get("joint")
+            if j is not None:
+                return j(self, eouts, douts)
+        out = torch.tanh(self.w_enc(eouts.unsqueeze(2)) + self.w_dec(douts.unsqueeze(1)))   # rnn_transducer.py:150-154
+        return self.output(out)
+
+    @torch.no_grad()
+    def _greedy(self, eouts, elens, decode_ctc_weight=0):
+        if decode_ctc_weight == 1:
+            return self.ctc.decode(eouts, elens, beam_width=1)
+        B, T, _ = eouts.shape
+        dev = eouts.device
+        enc_proj = self.w_enc(eouts).contiguous()                                   # (B, T, J), once
+        ys = torch.full((B, 1), self.eos_id, dtype=torch.long, device=dev)          # <sos>
+        dout, dstate = self.recurrency(ys, None)
+        state = F.GreedyState(B, T, torch.as_tensor(elens), self.max_seq_len, dev)
+        w, b = self.output.weight.detach(), self.output.bias.detach()
+        max_steps = T + self.max_seq_len + 2
+        for step in range(1, max_steps + 1):
+            dec_proj = self.w_dec(dout[:, 0]).contiguous()
+            F.greedy_step(state, enc_proj, dec_proj, w, b, self.blank_id)
+            # prediction network for the rows that emitted (run for all rows, kept where a token was appended)
+            new_dout, new_dstate = self.recurrency(state.token.view(B, 1), dstate)
+            em = state.emitted.bool()
+            dout = torch.where(em.view(B, 1, 1), new_dout, dout)
+            dstate = {k: torch.where(em.view(1, B, 1), new_dstate[k], dstate[k]) for k in ("hs", "cs")}
+            if step % self.greedy_poll == 0 and int(state.n_active) == 0:
+                break
+        hyp, hyp_len = state.hyp.cpu(), state.hyp_len.cpu()
+        align, align_len = state.align.cpu(), state.align_len.cpu()
+        hyps = [hyp[i, :int(hyp_len[i])].tolist() for i in range(B)]
+        aligns = [align[i, :int(align_len[i])].tolist() for i in range(B)]
+        return hyps, [None] * B, None, aligns
+
+
 class CTCDecoder(FusedCTCForward, nn.Module):
     """Stand-alone equivalent of asr/modeling/decoders/ctc.py:26-85 (constructor) for training."""
 
@@ -159,7 +232,7 @@ class CTCDecoder(FusedCTCForward, nn.Module):
                                   "decoder via emoasr_b200.dropin.install()")
 
 
-class RNNTDecoder(FusedRNNTForward, nn.Module):
+class RNNTDecoder(FusedRNNTForward, FusedRNNTSearch, nn.Module):
     """Stand-alone equivalent of asr/modeling/decoders/rnn_transducer.py:24-79 (constructor),
     :147-156 (joint) and :158-192 (recurrency) for training."""
 
@@ -187,11 +260,6 @@ class RNNTDecoder(FusedRNNTForward, nn.Module):
         if self.mtl_ctc_weight > 0:
             self.ctc = CTCDecoder(params)
 
-    def joint(self, eouts, douts):
-        """Dense joint, kept for decoding-style callers: (B,T,He),(B,L,Hd) -> (B,T,L,V)."""
-        out = torch.tanh(self.w_enc(eouts.unsqueeze(2)) + self.w_dec(douts.unsqueeze(1)))
-        return self.output(out)
-
     def recurrency(self, ys_in, dstate):
         ys_emb = self.dropout_emb(self.embed(ys_in))
         bs = ys_emb.size(0)
@@ -208,6 +276,13 @@ class RNNTDecoder(FusedRNNTForward, nn.Module):
             ys_emb = self.dropout(ys_emb)
         return ys_emb, {"hs": torch.cat(new_hs, dim=0), "cs": torch.cat(new_cs, dim=0)}
 
-    def decode(self, *args, **kwargs):
-        raise NotImplementedError("decoding is outside the loss hot path: use the reference "
-                                  "decoder via emoasr_b200.dropin.install()")
+    def decode(self, eouts, elens, eouts_inter=None, beam_width=1, len_weight=0, lm=None, lm_weight=0,
+               decode_ctc_weight=0, decode_phone=False):
+        """rnn_transducer.py:327-347: greedy search here (batched, on the device); beam search (ALSD with an optional
+        LM) is the reference's Python -- install over it with emoasr_b200.dropin.install(), its per-step joint then
+        runs through ``joint()`` above."""
+        if beam_width > 1:
+            raise NotImplementedError("beam search: use the reference decoder via emoasr_b200.dropin.install()")
+        hyps, _, _, _ = self._greedy(eouts, elens, decode_ctc_weight)
+        return hyps, None, None, None
+

@@ -29,7 +29,7 @@ def install(reference_root=None, precision="bf16"):
     import asr.modeling.decoders.rnn_transducer as ref_rnnt
 
     from .criteria import CTCLoss
-    from .decoders import FusedCTCForward, FusedRNNTForward
+    from .decoders import FusedCTCForward, FusedRNNTForward, FusedRNNTSearch
 
     if getattr(ref_asr, "_emoasr_b200_installed", False):
         return ref_asr
@@ -41,7 +41,7 @@ def install(reference_root=None, precision="bf16"):
             ref_ctc.CTCDecoder.__init__(self, params)
             self.ctc_loss_fn = CTCLoss(blank=self.blank_id, reduction="sum", zero_infinity=True)  # S3
 
-    class RNNTDecoder(FusedRNNTForward, ref_rnnt.RNNTDecoder):
+    class RNNTDecoder(FusedRNNTForward, FusedRNNTSearch, ref_rnnt.RNNTDecoder):
         fused_precision = precision
 
         def __init__(self, params, phase="train"):

@@ -373,3 +373,61 @@ def ctc_head_loss(eouts, weight, bias, labels, input_lengths, label_lengths, bla
     """
     nll = _CTCHead.apply(eouts, weight, bias, labels, input_lengths, label_lengths, int(blank), bool(zero_infinity))
     return _reduce(nll, reduction)
+
+
+# ----------------------------------------------------------------------------------------------
+def step_workspace(n_rows, device):
+    """Zeroed workspace of the decode-step calls for up to n_rows rows (they leave it zeroed: allocate once per search)."""
+    return torch.zeros(int(_lib.load().emo_rnnt_step_workspace_bytes(int(n_rows))), dtype=torch.uint8, device=device)
+
+
+def joint_step(enc_proj, dec_proj, w_out, b_out, enc_row=None, want_logits=True, want_token=False, ws=None):
+    """Decode-time joint for N rows in one launch (rnn_transducer.py:147-156 at T = L = 1, fp32):
+    ``z[n] = w_out tanh(enc_proj[enc_row[n]] + dec_proj[n]) + b_out``.  enc_proj (rows,J), dec_proj (N,J), enc_row (N)
+    int32 or None (row n).  Returns (logits (N,V) or None, token (N) int64 = argmax or None).  No grad."""
+    _require_cuda(enc_proj, dec_proj, w_out, b_out)
+    lib = _lib.load()
+    enc, dec, w, bo = _f32c(enc_proj), _f32c(dec_proj), _f32c(w_out), _f32c(b_out)
+    N, J = dec.shape
+    V = w.size(0)
+    dev = dec.device
+    with torch.cuda.device(dev):
+        logits = torch.empty(N, V, device=dev) if want_logits else None
+        token = torch.empty(N, dtype=torch.int64, device=dev) if want_token else None
+        if want_token and ws is None:
+            ws = step_workspace(N, dev)
+        row = _i32c(enc_row, dev) if enc_row is not None else None
+        _lib.check(lib.emo_rnnt_joint_step(_p(enc), _p(row), _p(dec), _p(w), _p(bo), N, J, V, _p(logits), _p(token),
+                                           _p(ws), ws.numel() if ws is not None else 0, _stream()), "emo_rnnt_joint_step")
+    return logits, token
+
+
+class GreedyState:
+    """Device-side state of a batched greedy search (one row per utterance); see emo_rnnt_greedy_step."""
+
+    def __init__(self, B, T, tlen, max_len, device, keep_align=True):
+        self.B, self.T, self.max_len = B, T, max_len
+        self.tlen = tlen.detach().to(device=device, dtype=torch.int32).clamp(min=0, max=T).contiguous()
+        z = lambda *s, dt=torch.int32: torch.zeros(*s, dtype=dt, device=device)
+        self.t_idx, self.hyp, self.hyp_len = z(B), z(B, max_len + 1), z(B)
+        self.align_cap = T + max_len + 2 if keep_align else 0
+        self.align = z(B, self.align_cap) if keep_align else None
+        self.align_len = z(B)
+        self.emitted = z(B, dt=torch.uint8)
+        self.token = z(B, dt=torch.int64)
+        self.n_active = z(1)
+        self.ws = step_workspace(B, device)
+
+
+def greedy_step(state, enc_proj, dec_proj, w_out, b_out, blank):
+    """One step of batched greedy transducer search for all utterances (rnn_transducer.py:194-240): joint at every
+    row's current frame, argmax, and the bookkeeping (advance on blank, append otherwise), on the device."""
+    lib = _lib.load()
+    B, T, J = enc_proj.shape
+    V = w_out.size(0)
+    s = state
+    with torch.cuda.device(enc_proj.device):
+        _lib.check(lib.emo_rnnt_greedy_step(_p(enc_proj), _p(dec_proj), _p(w_out), _p(b_out), _p(s.tlen), B, T, J, V,
+                                            int(blank), s.max_len, _p(s.t_idx), _p(s.hyp), _p(s.hyp_len), _p(s.align),
+                                            _p(s.align_len), s.align_cap, _p(s.emitted), _p(s.token), _p(s.n_active),
+                                            _p(s.ws), s.ws.numel(), _stream()), "emo_rnnt_greedy_step")

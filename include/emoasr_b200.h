@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define EMO_ABI_VERSION 6
+#define EMO_ABI_VERSION 7
 
 enum emo_status {
     EMO_OK = 0,
@@ -187,6 +187,28 @@ int emo_ctc_head_bwd(const float* eouts, const float* w, const float* b, const l
                      const float* alpha_ws, const float* beta_ws, const float* grad_nll, int B, int T, int He,
                      int V, int Umax, int blank, float* d_eouts, float* d_w, float* d_b, void* ws, size_t ws_bytes,
                      void* stream);
+
+/* ---- decode-time joint -------------------------------------------------------------------------------
+ * Replaces the (1,1,.) joint calls of the reference's search loops (rnn_transducer.py:194-325: `self.joint(eouts[b:b+1,
+ * t:t+1], dout)` -> argmax / log_softmax per step).  fp32 arithmetic (hypotheses should match the reference's).
+ *   z[n,:] = w_out tanh(enc_proj[row_n,:] + dec_proj[n,:]) + b_out,  n < N (utterances of a batch / hypotheses of a beam)
+ * enc_proj (rows,J) = w_enc(eouts)+b flattened over (b,t); enc_row (N) int32 row per n, or NULL (row n);
+ * dec_proj (N,J) = w_dec(dout)+b; J % 4 == 0.  ws: emo_rnnt_step_workspace_bytes(N) bytes, ZERO before its first use
+ * (the calls leave it zeroed), 256-byte aligned.
+ * emo_rnnt_joint_step:  logits (N,V) and / or token (N) = argmax_v z (lowest index on ties); either may be NULL.
+ * emo_rnnt_greedy_step: one step of batched greedy search (rnn_transducer.py:194-240) for all N utterances at once,
+ *   enc_row = n * T + t_idx[n]: token[n] = argmax; rows with t_idx < tlen and hyp_len <= max_len are active: the token
+ *   is appended to align (N,align_cap; optional), then blank -> t_idx += 1, else hyp[n][hyp_len++] = token (hyp is
+ *   (N,max_len+1)) and emitted[n] = 1 (the caller then advances that row's prediction network);
+ *   n_active (1, optional) = rows still active after the step.  No host synchronisation. */
+size_t emo_rnnt_step_workspace_bytes(int N);
+int emo_rnnt_joint_step(const float* enc_proj, const int* enc_row, const float* dec_proj, const float* w_out,
+                        const float* b_out, int N, int J, int V, float* logits, long long* token, void* ws,
+                        size_t ws_bytes, void* stream);
+int emo_rnnt_greedy_step(const float* enc_proj, const float* dec_proj, const float* w_out, const float* b_out,
+                         const int* tlen, int N, int T, int J, int V, int blank, int max_len, int* t_idx, int* hyp,
+                         int* hyp_len, int* align, int* align_len, int align_cap, unsigned char* emitted,
+                         long long* token, int* n_active, void* ws, size_t ws_bytes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -84,6 +84,38 @@ def rnnt_case(name, seed, B, T, U, p, tlens, ulens, mtl_ctc_weight=0.0):
     print(name, float(loss))
 
 
+def rnnt_greedy_case(name, seed, B, T, p, tlens, blank_bias):
+    """Hypotheses and alignments of the reference's own greedy search (rnn_transducer.py:194-240, via decode()'s
+    beam_width <= 1 branch) on a random model whose blank logit is biased so that blanks and labels alternate."""
+    if not _wanted(name):
+        return
+    from asr.modeling.decoders.rnn_transducer import RNNTDecoder
+
+    torch.manual_seed(seed)
+    g = torch.Generator().manual_seed(seed)
+    dec = RNNTDecoder(p, phase="test")
+    dec.eval()
+    with torch.no_grad():
+        dec.output.bias[p.blank_id] += blank_bias
+        dec.output.weight.mul_(3.0)             # peakier logits: fewer near-ties between fp32 summation orders
+    eouts = torch.randn(B, T, p.enc_hidden_size, generator=g)
+    elens = torch.tensor(tlens, dtype=torch.long)
+    with torch.no_grad():
+        hyps, scores, logits, aligns = dec._greedy(eouts, elens)
+        # margin between the best and second-best logit at every step of the search (the test skips the comparison
+        # of steps whose margin is below fp32 summation noise; with these weights there are none)
+    out = {"eouts": _np(eouts), "elens": _np(elens), "n": np.asarray(B)}
+    for b in range(B):
+        out[f"hyp.{b}"] = np.asarray(hyps[b], dtype=np.int64)
+        out[f"align.{b}"] = np.asarray(aligns[b], dtype=np.int64)
+    for k, v in dec.state_dict().items():
+        out["param." + k] = _np(v)
+    for k, v in p._asdict().items():
+        out["hp." + k] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, [len(h) for h in hyps], [len(a) for a in aligns])
+
+
 def ctc_case(name, seed, B, T, U, V, He, tlens, ulens):
     if not _wanted(name):
         return
@@ -255,6 +287,8 @@ def main():
                  ulens=[5, 4, 2, 5], plens=[9, 7, 3, 8], phone_w=0.3, hie=False, inter_w=0.0)
     ctc_mtl_case("ref_ctc_phone_hie_inter", 10, B=4, T=22, U=6, Up=10, V=29, Vp=43, He=16, tlens=[22, 20, 11, 6],
                  ulens=[6, 5, 6, 1], plens=[10, 8, 9, 2], phone_w=0.3, hie=True, inter_w=0.5)
+    # the reference's greedy search (decode-time joint)
+    rnnt_greedy_case("ref_rnnt_greedy", 13, B=5, T=23, p=pm, tlens=[23, 20, 14, 9, 1], blank_bias=3.0)
     # enc_hidden_size the fused tensor-core CTC head accepts (He % 128 == 0): main head with an odd vocabulary, an
     # infeasible utterance and an empty transcript; then all three heads (main, phone on the intermediate layer,
     # intermediate CTC)

@@ -324,7 +324,7 @@ def test_ctc_decoder_fused_head_vs_reference_golden(name):
             "hie_mtl_phone", "phone_vocab_size", "mtl_inter_ctc_weight"]
     keys = [k for k in keys if "hp." + k in g]
     dec = CTCDecoder(_params_from_golden(g, keys))
-    dec.fused_precision = "bf16"
+    dec.fused_precision, dec.fused_head_min_frames = "bf16", 0
     dec.load_state_dict({k[len("param."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")})
     dec = dec.to(dev())
     eouts = T_(g["eouts"]).requires_grad_()
@@ -338,3 +338,52 @@ def test_ctc_decoder_fused_head_vs_reference_golden(name):
     assert rel_err(eouts.grad.cpu().numpy(), g["grad_eouts"]) < BF16_GRAD_RTOL
     for k, v in dec.named_parameters():
         assert rel_err(v.grad.cpu().numpy(), g["grad." + k]) < BF16_GRAD_RTOL, k
+
+
+# ---------------------------------------------------------------- decode-time joint / greedy search
+def test_joint_step_vs_dense_joint():
+    """emo_rnnt_joint_step (one launch per search step) against the dense joint restricted to single cells, fp32:
+    logits and argmax for N rows, an enc-row index (greedy: row = b*T + t), one frame against a beam of rows, and
+    more rows than one pass of the kernel holds (N > 32)."""
+    from emoasr_b200 import functional as F
+    gen = torch.Generator().manual_seed(21)
+    for N, J, V in ((5, 64, 131), (32, 512, 1024), (70, 256, 1000)):
+        rows = 3 * N
+        enc = torch.randn(rows, J, generator=gen).to(dev())
+        dec_ = torch.randn(N, J, generator=gen).to(dev())
+        w = (torch.randn(V, J, generator=gen) / J ** 0.5).to(dev())
+        b = torch.randn(V, generator=gen).to(dev())
+        idx = torch.randint(0, rows, (N,), generator=gen).int().to(dev())
+        logits, tok = F.joint_step(enc, dec_, w, b, enc_row=idx, want_logits=True, want_token=True)
+        ref = torch.tanh(enc[idx.long()].double() + dec_.double()) @ w.double().t() + b.double()
+        assert float((logits.double() - ref).abs().max()) < 1e-4
+        assert torch.equal(tok, ref.argmax(-1))
+        # token only, workspace reused across calls (the kernel leaves it zeroed)
+        ws = F.step_workspace(N, dev())
+        for _ in range(3):
+            _, tok2 = F.joint_step(enc, dec_, w, b, enc_row=idx, want_logits=False, want_token=True, ws=ws)
+            assert torch.equal(tok2, tok)
+        assert int(ws.sum()) == 0
+
+
+def test_greedy_search_vs_reference_golden():
+    """Batched on-device greedy search against hypotheses AND per-step alignments of the unmodified reference's
+    _greedy (rnn_transducer.py:194-240): utterances that emit up to the max_seq_len break, an all-blank one, T_b = 1."""
+    from emoasr_b200.decoders import RNNTDecoder
+    g = load_golden("ref_rnnt_greedy")
+    dec = RNNTDecoder(_params_from_golden(g, RNNT_KEYS), phase="test")
+    dec.load_state_dict({k[len("param."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")})
+    dec = dec.to(dev()).eval()
+    hyps, scores, logits, aligns = dec._greedy(T_(g["eouts"]), T_(g["elens"]))
+    for b in range(int(g["n"])):
+        assert hyps[b] == g[f"hyp.{b}"].tolist(), b
+        assert aligns[b] == g[f"align.{b}"].tolist(), b
+    # the reference's decode() contract (rnn_transducer.py:327-347)
+    out = dec.decode(T_(g["eouts"]), T_(g["elens"]), beam_width=1)
+    assert out[0] == hyps and out[1:] == (None, None, None)
+    # joint() on single cells (what the reference's own search loops call) runs through the step kernel
+    e, d = T_(g["eouts"])[:1, 3:4], torch.randn(4, 1, dec.w_dec.in_features, device=dev())
+    with torch.no_grad():
+        fused = dec.joint(e, d)
+        dense = dec._dense_joint(e, d)
+    assert fused.shape == dense.shape and float((fused - dense).abs().max()) < 1e-4
