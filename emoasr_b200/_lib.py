@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("EMOASR_B200_LIB") or os.path.join(_HERE, "lib", "libe
 
 OP_RNNT_JOINT_FWD, OP_RNNT_JOINT_BWD, OP_CTC, OP_CTC_HEAD = 0, 1, 2, 3
 PREC_FP32, PREC_BF16 = 0, 1
-ABI_VERSION = 7
+ABI_VERSION = 8
 
 _c = ctypes
 _P = _c.c_void_p
@@ -28,7 +28,8 @@ _SIGNATURES = {
     "emo_rnnt_dense_fwd": (_I, [_P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P]),
     "emo_rnnt_dense_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "emo_rnnt_joint_fwd": (_I, [_P] * 7 + [_I] * 7 + [_P, _P, _P, _SZ, _P]),
-    "emo_rnnt_joint_bwd": (_I, [_P] * 11 + [_I] * 7 + [_P, _P, _P, _P, _P, _SZ, _P]),
+    "emo_rnnt_joint_bwd": (_I, [_P] * 12 + [_I] * 7 + [_P, _P, _P, _P, _P, _SZ, _P]),
+    "emo_rnnt_align": (_I, [_P] * 4 + [_I] * 3 + [_P, _P]),
     "emo_ctc_fwd": (_I, [_P] * 4 + [_I] * 6 + [_P, _P, _P, _P, _P]),
     "emo_ctc_bwd": (_I, [_P] * 8 + [_I] * 6 + [_P, _I, _P, _P]),
     "emo_ctc_head_supported": (_I, [_I] * 5),

@@ -84,3 +84,76 @@ class CTCHeadLoss(nn.Module):
         nll = F.ctc_head_loss(eouts, weight, bias, ys, elens, ylens, blank=self.blank,
                               zero_infinity=self.zero_infinity)
         return nll.sum() / eouts.size(0) if self.normalize_batch else nll.sum()
+
+
+class RNNTForcedAligner:
+    """Call-compatible with asr/modeling/decoders/rnnt_aligner.py:155-198 (``aligner(log_probs, elens, ys, ylens)``
+    -> best_aligns (B,U) int32): the Numba spin-lock alpha / beta kernels and the per-utterance Python walk become
+    the wavefront lattice kernel and one on-device walk.  With the fused joint the alignment comes from the same
+    lattice as the loss (``functional.rnnt_joint_outputs(..., aligns=True)``) and no dense tensor is needed."""
+
+    def __init__(self, blank_id=0):
+        self.blank_id = blank_id
+
+    def __call__(self, log_probs, elens, ys, ylens):
+        return F.rnnt_forced_align(log_probs.detach(), ys, elens, ylens, blank=self.blank_id)
+
+
+class RNNTWordDistillLoss(nn.Module):
+    """asr/criteria.py:218-249 without the dense (B,T,U+1,V) logits:
+    ``-sum_{t<xlen,u<ylen} sum_v q[u,v] log_softmax(z[t,u])[v]`` with ``sum_v q log p = (q W).h + q.b - (sum q) lse``:
+    ``lse`` is the fused joint's (differentiable) per-cell log-sum-exp, ``h = tanh(enc+dec)`` is formed one utterance
+    at a time ((xlen, ylen, J): the reference keeps (B,T,U+1,J) AND three (B,T,U+1,V) tensors)."""
+
+    def __init__(self, normalize_length=True, normalize_batch=True):
+        super().__init__()
+        self.normalize_length = normalize_length
+        self.normalize_batch = normalize_batch
+
+    def forward(self, enc_proj, dec_proj, w_out, b_out, lse, soft_labels, xlens, ylens):
+        bs = enc_proj.size(0)
+        loss = 0
+        for b in range(bs):
+            xlen, ylen = int(xlens[b]), int(ylens[b])
+            q = soft_labels[b, :ylen].to(w_out.dtype)                    # (L, V)
+            r = q @ w_out                                                # (L, J)
+            h = torch.tanh(enc_proj[b, :xlen].unsqueeze(1) + dec_proj[b, :ylen].unsqueeze(0))   # (xlen, L, J)
+            loss_b = (torch.einsum("tuj,uj->", h, r) + xlen * (q @ b_out).sum()
+                      - (lse[b, :xlen, :ylen] * q.sum(-1).unsqueeze(0)).sum())
+            if self.normalize_length:
+                loss_b = loss_b / (xlen * ylen)
+            loss = loss - loss_b
+        if self.normalize_batch:
+            loss = loss / bs
+        return loss
+
+
+class RNNTAlignDistillLoss(nn.Module):
+    """asr/criteria.py:252-288 without the dense logits.  The reference's loop keeps only the LAST label's term
+    (``loss_u`` is overwritten for u = 0 .. ylen-1 and subtracted once after the loop, :272-282); that is what its
+    training runs optimise, so it is what this computes: one lattice cell (aligns[b, ylen-1], ylen-1) per utterance,
+    whose logits are a (B,J) x (J,V) product."""
+
+    def __init__(self, normalize_length=True, normalize_batch=True):
+        super().__init__()
+        self.normalize_length = normalize_length
+        self.normalize_batch = normalize_batch
+
+    def forward(self, enc_proj, dec_proj, w_out, b_out, soft_labels, aligns, xlens, ylens):
+        bs = enc_proj.size(0)
+        dev = enc_proj.device
+        ylens = ylens.to(dev).long()
+        if int(ylens.min()) < 1:
+            raise RuntimeError("RNNTAlignDistillLoss: every utterance needs at least one label (as the reference)")
+        bi = torch.arange(bs, device=dev)
+        u = ylens - 1
+        t = aligns.to(dev).long()[bi, u]
+        h = torch.tanh(enc_proj[bi, t] + dec_proj[bi, u])                                 # (B, J)
+        lp = torch.log_softmax(torch.nn.functional.linear(h, w_out, b_out), dim=-1)        # (B, V)
+        loss_u = (soft_labels.to(dev)[bi, u].to(lp.dtype) * lp).sum(-1)
+        if self.normalize_length:
+            loss_u = loss_u / ylens.to(lp.dtype)
+        loss = -loss_u.sum()
+        if self.normalize_batch:
+            loss = loss / bs
+        return loss

@@ -94,18 +94,18 @@ extern "C" int emo_rnnt_joint_fwd(const float* enc_proj, const float* dec_proj, 
 extern "C" int emo_rnnt_joint_bwd(const float* enc_proj, const float* dec_proj, const float* w_out,
                                   const float* b_out, const int* labels, const int* tlen,
                                   const int* ulen, const float* lse, const float* lp2, const float* gamma2,
-                                  const float* grad_cost,
+                                  const float* grad_cost, const float* grad_lse,
                                   int B, int T, int U1, int J, int V, int blank, int precision, float* d_enc_proj, float* d_dec_proj,
                                   float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes,
                                   void* stream) {
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == EMO_PREC_FP32)
         return joint_bwd_f32(enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, lse, gamma2,
-                             grad_cost, B, T, U1, J, V, blank, d_enc_proj, d_dec_proj, d_w_out,
+                             grad_cost, grad_lse, B, T, U1, J, V, blank, d_enc_proj, d_dec_proj, d_w_out,
                              d_b_out, ws, ws_bytes, st);
     if (precision == EMO_PREC_BF16)
         return joint_bwd_bf16(enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, lse, lp2, gamma2,
-                              grad_cost, B, T, U1, J, V, blank, d_enc_proj, d_dec_proj, d_w_out,
+                              grad_cost, grad_lse, B, T, U1, J, V, blank, d_enc_proj, d_dec_proj, d_w_out,
                               d_b_out, ws, ws_bytes, st);
     set_error("joint_bwd: unknown precision %d", precision);
     return EMO_BAD_ARG;

@@ -119,8 +119,8 @@ int joint_fwd_f32(const float* enc_proj, const float* dec_proj, const float* w_o
                   size_t ws_bytes, cudaStream_t st);
 int joint_bwd_f32(const float* enc_proj, const float* dec_proj, const float* w_out,
                   const float* b_out, const int* labels, const int* tlen, const int* ulen,
-                  const float* lse, const float* gamma2, const float* grad_cost, int B, int T,
-                  int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
+                  const float* lse, const float* gamma2, const float* grad_cost, const float* grad_lse, int B,
+                  int T, int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
                   float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t joint_f32_workspace(int op, int B, int T, int U1, int J, int V);
 int joint_f32_launches(int op, int B, int T, int U1, int J, int V);
@@ -131,16 +131,16 @@ int joint_fwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
                    cudaStream_t st);
 int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
                    const float* b_out, const int* labels, const int* tlen, const int* ulen,
-                   const float* lse, const float* lp2, const float* gamma2, const float* grad_cost, int B, int T,
-                   int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
-                   float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st);
+                   const float* lse, const float* lp2, const float* gamma2, const float* grad_cost,
+                   const float* grad_lse, int B, int T, int U1, int J, int V, int blank, float* d_enc_proj,
+                   float* d_dec_proj, float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st);
 // ring backward (joint_bwd_ring.cu): the default route
 bool joint_ring_supported(int B, int T, int U1, int J, int V);
 size_t joint_ring_workspace(int B, int T, int U1, int J, int V);
 int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec_h, const float* b_out,
                           const int* labels, const int* tlen, const int* ulen, const float* lse, const float* lp2,
-                          const float* gamma2, const float* grad_cost, int B, int T, int U1, int J, int V, int Vout,
-                          int blank, int plain, void* dh_ws, void* ring_ws, float* d_w_out, float* d_b_out,
+                          const float* gamma2, const float* grad_cost, const float* grad_lse, int B, int T, int U1,
+                          int J, int V, int Vout, int blank, int plain, void* dh_ws, void* ring_ws, float* d_w_out, float* d_b_out,
                           cudaStream_t st);
 int joint_fwd_launch(const void* w_bf16, const void* enc_h, const void* dec_h, const float* b_pad, const int* labels,
                      const int* tlen, const int* ulen, int B, int T, int U1, int J, int Vp, int blank, float* lp2,

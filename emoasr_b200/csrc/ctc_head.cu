@@ -500,7 +500,7 @@ extern "C" int emo_ctc_head_bwd(const float* eouts, const float* w, const float*
     EMO_CUDA(cudaMemsetAsync(d_b, 0, (size_t)V * sizeof(float), st));
     // dense part: dz = g softmax(z) -> d_W, d_b, dh (bf16, tile-major)
     rc = joint_bwd_ring_launch(L.w_bf16, L.e16, nullptr, bias, L.ulen32, L.tsup32, L.ulen32, lse, nullptr, nullptr,
-                               L.grow, su.Bs, su.Ts, 1, He, Vp, V, blank, 1, L.dh, L.ring, d_w, d_b, st);
+                               L.grow, nullptr, su.Bs, su.Ts, 1, He, Vp, V, blank, 1, L.dh, L.ring, d_w, d_b, st);
     if (rc) return rc;
     // sparse part: the entries of the blank-extended label sequence
     const int Up = (Umax + 1 + 15) / 16 * 16, Tp = (T + 15) / 16 * 16;

@@ -66,6 +66,7 @@ struct RingArgs {
     const float* lp2;
     const float* gamma2;
     const float* grad_cost;
+    const float* grad_lse;      // (B,T,U1) gradient w.r.t. the forward's lse output, or NULL: adds grad_lse * softmax(z) to dz
     const int* prefix;          // [B+1] dense pair-tile prefix, then [B] packed (T_b | U1b << 16)
     int* flags;                 // z_ready[NZ] z_done[NZ] h_ready[NH] h_done[NH]
     float* d_w_out;
@@ -199,12 +200,12 @@ struct PCell {
     int lab;        // label of the cell's emit transition, -1 if none (or == blank)
 };
 struct PRaw {
-    float g, lse;
+    float g, lse, gl;
     float2 gm, lp;
     int lab, valid;
 };
 __device__ __forceinline__ void p_load_raw(PRaw& r, const PTile& ti, int m, const RingArgs& a) {
-    r.g = 0.f; r.lse = 0.f; r.gm = make_float2(0.f, 0.f); r.lp = make_float2(0.f, 0.f); r.lab = -1; r.valid = 0;
+    r.g = 0.f; r.lse = 0.f; r.gl = 0.f; r.gm = make_float2(0.f, 0.f); r.lp = make_float2(0.f, 0.f); r.lab = -1; r.valid = 0;
     if (m < ti.n_cells) {
         const int t = m / ti.U1b, u = m - t * ti.U1b;
         const size_t cell = ((size_t)ti.b * a.T + t) * a.U1 + u;
@@ -216,6 +217,7 @@ __device__ __forceinline__ void p_load_raw(PRaw& r, const PTile& ti, int m, cons
             return;
         }
         r.g = __ldg(a.grad_cost + ti.b);
+        if (a.grad_lse) r.gl = __ldg(a.grad_lse + cell);
         r.gm = __ldg(reinterpret_cast<const float2*>(a.gamma2) + cell);
         r.lp = __ldg(reinterpret_cast<const float2*>(a.lp2) + cell);
         if (u < ti.U1b - 1) r.lab = __ldg(a.labels + (size_t)ti.b * (a.U1 - 1) + u);
@@ -223,7 +225,7 @@ __device__ __forceinline__ void p_load_raw(PRaw& r, const PTile& ti, int m, cons
 }
 __device__ __forceinline__ PCell p_finish(const PRaw& r, int V, int blank) {
     PCell s;
-    const float cs = r.g * (r.gm.x + r.gm.y);
+    const float cs = fmaf(r.g, r.gm.x + r.gm.y, r.gl);   // coefficient of softmax(z) in dz
     s.c2 = (r.valid && cs != 0.f) ? fmaf(-r.lse, kLog2e, log2f(fabsf(cs))) : -1e30f;
     s.sgn = cs < 0.f ? 0x80008000u : 0u;
     const int lab = r.lab < 0 ? -1 : min(r.lab, V - 1);
@@ -1192,8 +1194,8 @@ void ring_split(int pairs, int V, int J, int& nP, int& nD, int& nS) {
 
 int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec_h, const float* b_out,
                           const int* labels, const int* tlen, const int* ulen, const float* lse, const float* lp2,
-                          const float* gamma2, const float* grad_cost, int B, int T, int U1, int J, int V, int Vout,
-                          int blank, int plain, void* dh_ws, void* ring_ws, float* d_w_out, float* d_b_out,
+                          const float* gamma2, const float* grad_cost, const float* grad_lse, int B, int T, int U1,
+                          int J, int V, int Vout, int blank, int plain, void* dh_ws, void* ring_ws, float* d_w_out, float* d_b_out,
                           cudaStream_t st) {
     EMO_REQUIRE(joint_ring_supported(B, T, U1, J, V), EMO_UNSUPPORTED_SHAPE,
                 "joint_bwd(bf16, ring): needs B <= %d, J %% 128 == 0, J <= 512", kMaxB);
@@ -1209,7 +1211,7 @@ int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec
                 "joint_bwd(bf16, ring): %d resident CTA pairs cannot host %d vocabulary roles", pairs, roles_v);
     RingArgs a;
     a.enc = (const __half*)enc_h; a.dec = (const __half*)dec_h; a.b_out = b_out; a.labels = labels;
-    a.lse = lse; a.lp2 = lp2; a.gamma2 = gamma2; a.grad_cost = grad_cost; a.prefix = prefix; a.flags = flags;
+    a.lse = lse; a.lp2 = lp2; a.gamma2 = gamma2; a.grad_cost = grad_cost; a.grad_lse = grad_lse; a.prefix = prefix; a.flags = flags;
     a.d_w_out = d_w_out; a.d_b_out = d_b_out;
     a.B = B; a.T = T; a.U1 = U1; a.J = J; a.V = V; a.Vout = Vout; a.blank = blank; a.plain = plain;
     ring_split(pairs, V, J, a.nP, a.nD, a.nS);
@@ -1308,9 +1310,9 @@ int joint_bf16_casts(const float* enc_proj, const float* dec_proj, const float* 
 
 int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_out,
                    const float* b_out, const int* labels, const int* tlen, const int* ulen,
-                   const float* lse, const float* lp2, const float* gamma2, const float* grad_cost, int B, int T,
-                   int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
-                   float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st) {
+                   const float* lse, const float* lp2, const float* gamma2, const float* grad_cost,
+                   const float* grad_lse, int B, int T, int U1, int J, int V, int blank, float* d_enc_proj,
+                   float* d_dec_proj, float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st) {
     EMO_REQUIRE(enc_proj && dec_proj && w_out && b_out && labels && tlen && ulen && lse && lp2 && gamma2 &&
                     grad_cost && d_enc_proj && d_dec_proj && d_w_out && d_b_out && ws,
                 EMO_BAD_ARG, "joint_bwd(bf16): null pointer");
@@ -1331,8 +1333,8 @@ int joint_bwd_bf16(const float* enc_proj, const float* dec_proj, const float* w_
     const float* b_pad;
     rc = joint_bf16_casts(enc_proj, dec_proj, w_out, b_out, B, T, U1, J, V, ws, &w_bf16, &enc_h, &dec_h, &b_pad, st);
     if (rc) return rc;
-    rc = joint_bwd_ring_launch(w_bf16, enc_h, dec_h, b_pad, labels, tlen, ulen, lse, lp2, gamma2, grad_cost, B, T, U1,
-                               J, padded_vocab(V), V, blank, 0, dh_ws, ring_ws, d_w_out, d_b_out, st);
+    rc = joint_bwd_ring_launch(w_bf16, enc_h, dec_h, b_pad, labels, tlen, ulen, lse, lp2, gamma2, grad_cost, grad_lse, B, T,
+                               U1, J, padded_vocab(V), V, blank, 0, dh_ws, ring_ws, d_w_out, d_b_out, st);
     if (rc) return rc;
     return joint_reduce_dh_launch(dh_ws, enc_proj, dec_proj, tlen, ulen, B, T, U1, J, d_enc_proj, d_dec_proj, st);
 }

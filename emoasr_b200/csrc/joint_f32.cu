@@ -160,10 +160,11 @@ row_lse_gather_kernel(const float* __restrict__ z, const int* __restrict__ label
 // dz in place + column sums.  CTA = 64 cell rows x all columns (thread per column, strided).
 __global__ void __launch_bounds__(256)
 dz_kernel(float* __restrict__ z, const int* __restrict__ labels, const float* __restrict__ lse,
-          const float* __restrict__ gamma2, const float* __restrict__ grad_cost, int r0, int rows,
+          const float* __restrict__ gamma2, const float* __restrict__ grad_cost,
+          const float* __restrict__ grad_lse, int r0, int rows,
           int T, int U1, int V, int blank, float* __restrict__ d_b_out) {
     constexpr int R = 64;
-    __shared__ float s_lse[R], s_gb[R], s_gl[R], s_g[R];
+    __shared__ float s_lse[R], s_gb[R], s_gl[R], s_g[R], s_gs[R];
     __shared__ int s_lab[R];
     int ncell = rows * U1;
     int c0 = blockIdx.x * R;
@@ -178,6 +179,7 @@ dz_kernel(float* __restrict__ z, const int* __restrict__ labels, const float* __
             s_gb[i] = g.x;
             s_gl[i] = g.y;
             s_g[i] = grad_cost[b];
+            s_gs[i] = grad_lse ? grad_lse[cell] : 0.f;   // d lse / d z = softmax(z)
             s_lab[i] = (u < U1 - 1) ? min(max(labels[(size_t)b * (U1 - 1) + u], 0), V - 1) : -1;
         }
     }
@@ -187,13 +189,14 @@ dz_kernel(float* __restrict__ z, const int* __restrict__ labels, const float* __
         float colsum = 0.f;
         for (int i = 0; i < nr; ++i) {
             float* p = z + (size_t)(c0 + i) * V + v;
-            float gb = s_gb[i], gl = s_gl[i];
+            float gb = s_gb[i], gl = s_gl[i], gs = s_gs[i];
             float d = 0.f;
-            if (gb != 0.f || gl != 0.f) {
-                d = (gb + gl) * expf(*p - s_lse[i]);
+            if (gb != 0.f || gl != 0.f || gs != 0.f) {
+                const float pr = expf(*p - s_lse[i]);
+                d = (gb + gl) * pr;
                 if (v == blank) d -= gb;
                 if (v == s_lab[i]) d -= gl;
-                d *= s_g[i];
+                d = fmaf(d, s_g[i], gs * pr);
             }
             *p = d;
             colsum += d;
@@ -297,8 +300,8 @@ int joint_fwd_f32(const float* enc_proj, const float* dec_proj, const float* w_o
 
 int joint_bwd_f32(const float* enc_proj, const float* dec_proj, const float* w_out,
                   const float* b_out, const int* labels, const int* tlen, const int* ulen,
-                  const float* lse, const float* gamma2, const float* grad_cost, int B, int T,
-                  int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
+                  const float* lse, const float* gamma2, const float* grad_cost, const float* grad_lse, int B,
+                  int T, int U1, int J, int V, int blank, float* d_enc_proj, float* d_dec_proj,
                   float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, cudaStream_t st) {
     int rc = check_joint_args(enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, B, T, U1, J, V, blank);
     if (rc) return rc;
@@ -321,7 +324,7 @@ int joint_bwd_f32(const float* enc_proj, const float* dec_proj, const float* w_o
         hidden_slab_kernel<<<min(ceil_div((size_t)nc * J, 256), sm_count() * 16), 256, 0, st>>>(
             enc_proj, dec_proj, r0, rows, T, U1, J, h);
         sgemm<true, true, false, true>(h, w_out, z, b_out, nc, V, J, J, J, V, st);
-        dz_kernel<<<ceil_div(nc, 64), 256, 0, st>>>(z, labels, lse, gamma2, grad_cost, r0, rows, T,
+        dz_kernel<<<ceil_div(nc, 64), 256, 0, st>>>(z, labels, lse, gamma2, grad_cost, grad_lse, r0, rows, T,
                                                     U1, V, blank, d_b_out);
         // d_w_out[v,j] += sum_c dz[c,v] h[c,j]
         sgemm<false, false, true, false>(z, h, d_w_out, nullptr, V, J, nc, V, J, J, st);

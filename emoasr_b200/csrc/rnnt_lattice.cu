@@ -197,6 +197,32 @@ __global__ void rnnt_scatter_grad_kernel(const float* __restrict__ gamma2,
     row[blank] = gb;
 }
 
+// Forced alignment on the lattice (asr/modeling/decoders/rnnt_aligner.py:176-196): walk from (0,0), at every cell
+// compare the path mass alpha + beta of the two successors -- (t+1,u) consumes a frame, (t,u+1) emits y_u at frame t.
+// One thread per utterance: T_b + U_b dependent steps on L2-resident values; entries for labels the walk does not
+// reach (it stops at the last frame) keep the reference's initial 0.
+__global__ void rnnt_align_kernel(const float* __restrict__ alpha, const float* __restrict__ beta,
+                                  const int* __restrict__ tlen, const int* __restrict__ ulen, int B, int T, int U1,
+                                  int* __restrict__ aligns) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B) return;
+    const int T_b = min(max(tlen[b], 1), T), U_b = min(max(ulen[b], 0), U1 - 1);
+    const float* a = alpha + (size_t)b * T * U1;
+    const float* bt = beta + (size_t)b * T * U1;
+    int* out = aligns + (size_t)b * (U1 - 1);
+    for (int u = 0; u < U1 - 1; ++u) out[u] = 0;
+    int t = 0, u = 0;
+    while (t + 1 < T_b && u < U_b) {
+        const size_t down = (size_t)(t + 1) * U1 + u, right = (size_t)t * U1 + u + 1;
+        if (a[down] + bt[down] > a[right] + bt[right]) {
+            ++t;
+        } else {
+            out[u] = t;
+            ++u;
+        }
+    }
+}
+
 }  // namespace
 
 int rnnt_lattice_launch(const float* lp2, const int* tlen, const int* ulen, int B, int T, int U1,
@@ -227,6 +253,16 @@ extern "C" int emo_rnnt_lattice_fwd_bwd(const float* lp2, const int* tlen, const
                                         float* cost, float* gamma2, void* stream) {
     return rnnt_lattice_launch(lp2, tlen, ulen, B, T, U1, alpha_ws, beta_ws, cost, gamma2,
                                (cudaStream_t)stream);
+}
+
+extern "C" int emo_rnnt_align(const float* alpha_ws, const float* beta_ws, const int* tlen, const int* ulen, int B,
+                              int T, int U1, int* aligns, void* stream) {
+    EMO_REQUIRE(alpha_ws && beta_ws && tlen && ulen && (aligns || U1 == 1), EMO_BAD_ARG, "rnnt_align: null pointer");
+    EMO_REQUIRE(B > 0 && T > 0 && U1 > 0, EMO_BAD_ARG, "rnnt_align: B,T,U1 must be positive");
+    if (U1 == 1) return EMO_OK;
+    rnnt_align_kernel<<<ceil_div(B, 32), 32, 0, (cudaStream_t)stream>>>(alpha_ws, beta_ws, tlen, ulen, B, T, U1, aligns);
+    EMO_CHECK_LAUNCH("rnnt_align_kernel");
+    return EMO_OK;
 }
 
 extern "C" int emo_rnnt_dense_fwd(const float* log_probs, const int* labels, const int* tlen,

@@ -12,7 +12,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as F
-from .criteria import CTCLoss
+from .criteria import CTCLoss, RNNTAlignDistillLoss, RNNTWordDistillLoss
 
 
 def _opt(params, name, default=0):
@@ -114,29 +114,42 @@ class FusedRNNTForward:
 
     def forward(self, eouts, elens, eouts_inter=None, ys=None, ylens=None, ys_in=None, ys_out=None,
                 soft_labels=None, ps=None, plens=None):
-        if self.kd_weight > 0 and soft_labels is not None:
-            ref_forward = _reference_forward(self, FusedRNNTForward)
-            if ref_forward is None:
-                raise NotImplementedError("knowledge distillation needs the dense logits: use the "
-                                          "reference decoder (emoasr_b200.dropin.install())")
-            return ref_forward(eouts, elens, eouts_inter, ys, ylens, ys_in, ys_out, soft_labels, ps, plens)
         loss = 0
         loss_dict = {}
         douts, _ = self.recurrency(ys_in, dstate=None)
         enc_proj = self.w_enc(eouts)   # (B, T, J)
         dec_proj = self.w_dec(douts)   # (B, L+1, J)
         assert dec_proj.size(1) == ys.size(1) + 1
-        loss_rnnt = F.rnnt_joint_loss(enc_proj, dec_proj, self.output.weight, self.output.bias,
-                                      ys, elens, ylens, blank=self.blank_id, reduction="mean",
-                                      precision=self._precision_for(enc_proj.size(0), enc_proj.size(1),
-                                                                    dec_proj.size(1), enc_proj.size(2),
-                                                                    self.output.weight.size(0)))
+        precision = self._precision_for(enc_proj.size(0), enc_proj.size(1), dec_proj.size(1), enc_proj.size(2),
+                                        self.output.weight.size(0))
+        wants_kd = self.kd_weight > 0 and soft_labels is not None
+        kd_type = getattr(self, "kd_type", None) if wants_kd else None
+        costs, lse, aligns = F.rnnt_joint_outputs(enc_proj, dec_proj, self.output.weight, self.output.bias, ys, elens,
+                                                  ylens, blank=self.blank_id, precision=precision,
+                                                  aligns=kd_type == "align")
+        loss_rnnt = costs.mean()
         loss += loss_rnnt
         loss_dict["loss_rnnt"] = loss_rnnt
         if self.mtl_ctc_weight > 0:
             loss_ctc, _, _ = self.ctc(eouts=eouts, elens=elens, ys=ys, ylens=ylens, soft_labels=None)
             loss += self.mtl_ctc_weight * loss_ctc
             loss_dict["loss_ctc"] = loss_ctc
+        if wants_kd:
+            # rnn_transducer.py:127-141 on the fused lattice: the per-cell lse (word) / the forced alignment (align)
+            # come out of the same fused forward as the loss; no (B,T,U+1,V) tensor is formed
+            if kd_type == "word":
+                loss_kd = RNNTWordDistillLoss()(enc_proj, dec_proj, self.output.weight, self.output.bias, lse,
+                                                soft_labels, elens, ylens)
+            elif kd_type == "align":
+                loss_kd = RNNTAlignDistillLoss()(enc_proj, dec_proj, self.output.weight, self.output.bias, soft_labels,
+                                                 aligns, elens, ylens)
+            else:
+                raise NotImplementedError(f"kd_type {kd_type!r} (the reference knows 'word' and 'align')")
+            loss_dict["loss_kd"] = loss_kd
+            if self.reduce_main_loss_kd:
+                loss = (1 - self.kd_weight) * loss + self.kd_weight * loss_kd
+            else:
+                loss += self.kd_weight * loss_kd
         loss_dict["loss_total"] = loss
         return loss, loss_dict, None
 
@@ -245,6 +258,9 @@ class RNNTDecoder(FusedRNNTForward, FusedRNNTSearch, nn.Module):
         self.max_seq_len = 256
         self.mtl_ctc_weight = params.mtl_ctc_weight
         self.kd_weight = params.kd_weight
+        if self.kd_weight > 0 and phase == "train":          # rnn_transducer.py:66-79
+            self.kd_type = params.kd_type
+            self.reduce_main_loss_kd = params.reduce_main_loss_kd
         self.embed = nn.Embedding(params.vocab_size, params.embedding_size)
         self.dropout_emb = nn.Dropout(p=params.dropout_emb_rate)
         self.dropout = nn.Dropout(p=params.dropout_dec_rate)

@@ -155,8 +155,12 @@ def joint_supported(precision, B, T, U1, J, V):
 
 
 class _RNNTJoint(torch.autograd.Function):
+    """Outputs: cost (B); lse (B,T,U1), the log-sum-exp of every valid cell's logits (0 elsewhere) -- differentiable,
+    so that losses built on log_softmax(z) without the dense tensor can be added (distillation: sum_v q log p =
+    q.z - (sum q) lse); aligns (B,U) int32 forced alignment on the same lattice (only when asked for)."""
+
     @staticmethod
-    def forward(ctx, enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, blank, precision):
+    def forward(ctx, enc_proj, dec_proj, w_out, b_out, labels, tlen, ulen, blank, precision, want_aligns):
         _require_cuda(enc_proj, dec_proj, w_out, b_out)
         lib = _lib.load()
         enc, dec, w, bo = _f32c(enc_proj), _f32c(dec_proj), _f32c(w_out), _f32c(b_out)
@@ -179,7 +183,7 @@ class _RNNTJoint(torch.autograd.Function):
             nbytes = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_FWD, precision, B, T, U1, J, V)
             ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
             lp2 = torch.empty(B, T, U1, 2, device=dev)
-            lse = torch.empty(B, T, U1, device=dev)
+            lse = torch.zeros(B, T, U1, device=dev)
             _lib.check(lib.emo_rnnt_joint_fwd(_p(enc), _p(dec), _p(w), _p(bo), _p(labels), _p(tlen), _p(ulen),
                                               B, T, U1, J, V, blank, precision, _p(lp2), _p(lse),
                                               _p(ws), ws.numel(), _stream()), "emo_rnnt_joint_fwd")
@@ -190,14 +194,20 @@ class _RNNTJoint(torch.autograd.Function):
             _lib.check(lib.emo_rnnt_lattice_fwd_bwd(_p(lp2), _p(tlen), _p(ulen), B, T, U1, _p(alpha),
                                                     _p(beta), _p(cost), _p(gamma2), _stream()),
                        "emo_rnnt_lattice_fwd_bwd")
+            aligns = torch.zeros(B, max(U1 - 1, 0), dtype=torch.int32, device=dev)
+            if want_aligns and U1 > 1:
+                _lib.check(lib.emo_rnnt_align(_p(alpha), _p(beta), _p(tlen), _p(ulen), B, T, U1, _p(aligns), _stream()),
+                           "emo_rnnt_align")
         # nothing of size N x V is kept for the backward: it recomputes the logit tiles
         ctx.save_for_backward(enc, dec, w, bo, labels, tlen, ulen, lse, lp2, gamma2)
         ctx.cfg = (blank, precision)
-        return cost
+        ctx.set_materialize_grads(False)
+        ctx.mark_non_differentiable(aligns)
+        return cost, lse, aligns
 
     @staticmethod
     @once_differentiable
-    def backward(ctx, grad_cost):
+    def backward(ctx, grad_cost, grad_lse, _grad_aligns):
         enc, dec, w, bo, labels, tlen, ulen, lse, lp2, gamma2 = ctx.saved_tensors
         blank, precision = ctx.cfg
         lib = _lib.load()
@@ -205,7 +215,13 @@ class _RNNTJoint(torch.autograd.Function):
         U1, V = dec.size(1), w.size(0)
         dev = enc.device
         with torch.cuda.device(dev):
-            g = _f32c(grad_cost)
+            g = _f32c(grad_cost) if grad_cost is not None else torch.zeros(B, device=dev)
+            gl = None
+            if grad_lse is not None:
+                # only valid cells carry an lse: mask what autograd sends for the rest
+                t_ok = torch.arange(T, device=dev).view(1, T, 1) < tlen.clamp(min=1).view(B, 1, 1)
+                u_ok = torch.arange(U1, device=dev).view(1, 1, U1) <= ulen.clamp(min=0, max=U1 - 1).view(B, 1, 1)
+                gl = (_f32c(grad_lse) * (t_ok & u_ok)).contiguous()
             nbytes = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_BWD, precision, B, T, U1, J, V)
             ws = torch.empty(max(nbytes, 256), dtype=torch.uint8, device=dev)
             d_enc = torch.empty_like(enc)
@@ -213,11 +229,11 @@ class _RNNTJoint(torch.autograd.Function):
             d_w = torch.empty_like(w)
             d_b = torch.empty_like(bo)
             _lib.check(lib.emo_rnnt_joint_bwd(_p(enc), _p(dec), _p(w), _p(bo), _p(labels), _p(tlen), _p(ulen),
-                                              _p(lse), _p(lp2), _p(gamma2), _p(g),
+                                              _p(lse), _p(lp2), _p(gamma2), _p(g), _p(gl),
                                               B, T, U1, J, V, blank, precision,
                                               _p(d_enc), _p(d_dec), _p(d_w), _p(d_b), _p(ws), ws.numel(),
                                               _stream()), "emo_rnnt_joint_bwd")
-        return d_enc, d_dec, d_w, d_b, None, None, None, None, None
+        return d_enc, d_dec, d_w, d_b, None, None, None, None, None, None
 
 
 def rnnt_joint_loss(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths, labels_lengths,
@@ -231,9 +247,45 @@ def rnnt_joint_loss(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths, la
     hands ``dz`` to the gradient GEMMs through an L2-resident ring of tiles; precision="fp32" (parity mode)
     streams them through a bounded slab.
     """
-    costs = _RNNTJoint.apply(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths,
-                             labels_lengths, int(blank), _PRECISIONS[precision])
+    costs, _, _ = _RNNTJoint.apply(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths,
+                                   labels_lengths, int(blank), _PRECISIONS[precision], False)
     return _reduce(costs, reduction)
+
+
+def rnnt_joint_outputs(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths, labels_lengths, blank=0,
+                       precision="bf16", aligns=False):
+    """The fused op with all its outputs: ``(costs (B), lse (B,T,U+1), aligns (B,U) int32 or None)``.
+
+    ``lse[b,t,u] = logsumexp_v z[b,t,u,v]`` for valid cells (0 elsewhere) is differentiable: together with a few
+    per-cell dot products it gives any ``sum_v q[v] log_softmax(z)[v] = q.z - (sum q) lse`` without the dense
+    tensor (knowledge distillation, asr/criteria.py:218-288).  ``aligns`` is the forced alignment of
+    asr/modeling/decoders/rnnt_aligner.py:155-198 computed on the same lattice."""
+    costs, lse, al = _RNNTJoint.apply(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths,
+                                      labels_lengths, int(blank), _PRECISIONS[precision], bool(aligns))
+    return costs, lse, (al if aligns else None)
+
+
+def rnnt_forced_align(log_probs, labels, frames_lengths, labels_lengths, blank=0):
+    """Drop-in for ``RNNTForcedAligner(blank_id)(log_probs, elens, ys, ylens)`` (rnnt_aligner.py:155-198) on dense
+    log-probs (B,T,U+1,V): gathers the {blank,label} pairs, runs the lattice and walks it on the device.
+    Returns best_aligns (B,U) int32."""
+    _require_cuda(log_probs)
+    lib = _lib.load()
+    lp = _f32c(log_probs)
+    B, T, U1, V = lp.shape
+    dev = lp.device
+    labels, tlen, ulen = _i32c(labels, dev), _i32c(frames_lengths, dev), _i32c(labels_lengths, dev)
+    labels = labels[:, : U1 - 1].contiguous() if U1 > 1 else torch.zeros(B, 1, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        lp2 = torch.empty(B, T, U1, 2, device=dev)
+        alpha, beta = torch.empty(B, T, U1, device=dev), torch.empty(B, T, U1, device=dev)
+        cost, gamma2 = torch.empty(B, device=dev), torch.empty(B, T, U1, 2, device=dev)
+        _lib.check(lib.emo_rnnt_dense_fwd(_p(lp), _p(labels), _p(tlen), _p(ulen), B, T, U1, V, int(blank), _p(lp2),
+                                          _p(alpha), _p(beta), _p(cost), _p(gamma2), _stream()), "emo_rnnt_dense_fwd")
+        aligns = torch.zeros(B, max(U1 - 1, 0), dtype=torch.int32, device=dev)
+        _lib.check(lib.emo_rnnt_align(_p(alpha), _p(beta), _p(tlen), _p(ulen), B, T, U1, _p(aligns), _stream()),
+                   "emo_rnnt_align")
+    return aligns
 
 
 # ----------------------------------------------------------------------------------------------

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define EMO_ABI_VERSION 7
+#define EMO_ABI_VERSION 8
 
 enum emo_status {
     EMO_OK = 0,
@@ -88,6 +88,14 @@ int emo_rnnt_lattice_fwd_bwd(const float* lp2, const int* tlen, const int* ulen,
                              float* alpha_ws, float* beta_ws,
                              float* cost, float* gamma2, void* stream);
 
+/* ---- forced alignment on the lattice ----------------------------------------------------------
+ * Replaces RNNTForcedAligner.__call__ (asr/modeling/decoders/rnnt_aligner.py:155-198: two Numba spin-lock kernels
+ * + a Python walk per utterance): given alpha_ws / beta_ws of emo_rnnt_lattice_fwd_bwd (or emo_rnnt_dense_fwd),
+ * aligns (B,U1-1) int32: aligns[b,u] = frame at which y_u is emitted on the greedy walk through alpha + beta
+ * (0 for labels the walk does not reach -- the reference's behaviour). */
+int emo_rnnt_align(const float* alpha_ws, const float* beta_ws, const int* tlen, const int* ulen, int B, int T,
+                   int U1, int* aligns, void* stream);
+
 /* ---- warp_rnnt module seam: dense log-probs in, sparse gradient out --------------------------
  * Same contract as warp_rnnt.rnnt_loss(log_probs, labels, frames_lengths, labels_lengths,
  * average_frames=False, reduction=None, blank, gather=False).
@@ -129,6 +137,9 @@ int emo_rnnt_joint_fwd(const float* enc_proj, const float* dec_proj,
  * a ring of tiles inside `ws` whose size (36 MB) does not depend on the problem size and stays L2-resident; dz
  * is never a tensor in HBM.  What does go through HBM is dh as bf16 (N x J), read back once by the axis
  * reductions.
+ * grad_lse (B,T,U1), optional (NULL = none): gradient w.r.t. the forward's `lse` output, for losses that use it
+ * next to the transducer cost (the distillation losses of asr/criteria.py:218-288 need sum_v q log_softmax(z) =
+ * q.z - (sum q) lse); it adds grad_lse * softmax(z) to dz.  Must be 0 for cells outside the valid lattice.
  * All four outputs are overwritten (not accumulated into).  enc_proj, dec_proj, w_out, b_out, labels, the
  * lengths, lse and lp2 must be the tensors the forward call saw / produced (as autograd's saved tensors are):
  * the backward re-reads them (h is recomputed from enc_proj / dec_proj; lp2 gives the exact blank / label
@@ -137,6 +148,7 @@ int emo_rnnt_joint_bwd(const float* enc_proj, const float* dec_proj,
                        const float* w_out, const float* b_out,
                        const int* labels, const int* tlen, const int* ulen,
                        const float* lse, const float* lp2, const float* gamma2, const float* grad_cost,
+                       const float* grad_lse,
                        int B, int T, int U1, int J, int V, int blank, int precision,
                        float* d_enc_proj, float* d_dec_proj, float* d_w_out, float* d_b_out,
                        void* ws, size_t ws_bytes, void* stream);

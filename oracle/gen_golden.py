@@ -84,6 +84,51 @@ def rnnt_case(name, seed, B, T, U, p, tlens, ulens, mtl_ctc_weight=0.0):
     print(name, float(loss))
 
 
+def rnnt_kd_case(name, seed, B, T, U, p, tlens, ulens, kd_type, reduce_main):
+    """RNNTDecoder.forward with knowledge distillation (rnn_transducer.py:127-141): kd_type "word"
+    (RNNTWordDistillLoss, criteria.py:218-249) or "align" (RNNTForcedAligner + RNNTAlignDistillLoss,
+    rnnt_aligner.py:155-198, criteria.py:252-288).  The aligner's Numba CUDA kernels run on the CPU under
+    NUMBA_ENABLE_CUDASIM=1 (set by main())."""
+    if not _wanted(name):
+        return
+    from asr.modeling.decoders.rnn_transducer import RNNTDecoder
+
+    p = p._replace(kd_weight=0.3)
+    p = namedtuple("Params", p._fields + ("kd_type", "reduce_main_loss_kd"))(*p, kd_type, reduce_main)
+    torch.manual_seed(seed)
+    g = torch.Generator().manual_seed(seed)
+    dec = RNNTDecoder(p, phase="train")
+    dec.train()
+    eouts = torch.randn(B, T, p.enc_hidden_size, generator=g).requires_grad_()
+    elens = torch.tensor(tlens, dtype=torch.long)
+    ylens = torch.tensor(ulens, dtype=torch.long)
+    ys = _labels(g, B, U, p.vocab_size, ulens, p.eos_id)
+    eos = torch.full((B, 1), p.eos_id, dtype=torch.long)
+    ys_in = torch.cat([eos, ys], dim=1)
+    ys_out = torch.cat([ys, eos], dim=1)
+    soft_labels = torch.softmax(2.0 * torch.randn(B, U, p.vocab_size, generator=g), dim=-1)   # teacher posteriors
+    loss, loss_dict, logits = dec(eouts, elens, None, ys, ylens, ys_in, ys_out, soft_labels)
+    loss.backward()
+    out = {
+        "eouts": _np(eouts), "elens": _np(elens), "ys": _np(ys), "ylens": _np(ylens),
+        "ys_in": _np(ys_in), "ys_out": _np(ys_out), "soft_labels": _np(soft_labels),
+        "loss_total": _np(loss), "grad_eouts": _np(eouts.grad),
+    }
+    if kd_type == "align":
+        with torch.no_grad():
+            out["aligns"] = _np(dec.forced_aligner(torch.log_softmax(logits, dim=-1), elens, ys, ylens))
+    for k, v in loss_dict.items():
+        out["lossdict." + k] = _np(v)
+    for k, v in dec.state_dict().items():
+        out["param." + k] = _np(v)
+    for k, v in dec.named_parameters():
+        out["grad." + k] = _np(v.grad) if v.grad is not None else np.zeros(0)
+    for k, v in p._asdict().items():
+        out["hp." + k] = np.asarray(v)
+    np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
+    print(name, float(loss), {k: float(v) for k, v in loss_dict.items()})
+
+
 def rnnt_greedy_case(name, seed, B, T, p, tlens, blank_bias):
     """Hypotheses and alignments of the reference's own greedy search (rnn_transducer.py:194-240, via decode()'s
     beam_width <= 1 branch) on a random model whose blank logit is biased so that blanks and labels alternate."""
@@ -197,9 +242,13 @@ def smoke_fixtures():
     U = torch.tensor([4, 5], dtype=torch.int32)
     costs = warp_rnnt.rnnt_loss(lp, labels, T, U, reduction=None, blank=0)
     costs.sum().backward()
+    # the reference's forced aligner on the same input (Numba CUDA simulator on the CPU)
+    from asr.modeling.decoders.rnnt_aligner import RNNTForcedAligner
+    aligns = RNNTForcedAligner(blank_id=0)(lp.detach(), T, labels, U)
     np.savez_compressed(
         os.path.join(OUT, "ref_rnnt_aligner_smoke.npz"),
         log_probs=_np(lp), labels=_np(labels), T=_np(T), U=_np(U), costs=_np(costs), grad=_np(lp.grad),
+        aligns=_np(aligns),
     )
     print("ref_rnnt_aligner_smoke", _np(costs))
 
@@ -248,6 +297,7 @@ def _wanted(name):
 
 
 def main():
+    os.environ.setdefault("NUMBA_ENABLE_CUDASIM", "1")   # rnnt_aligner.py's @cuda.jit kernels on the CPU
     global ONLY
     ONLY = set(sys.argv[1:]) or None
     os.makedirs(OUT, exist_ok=True)
@@ -258,7 +308,7 @@ def main():
     sys.path.insert(0, REF)
     torch.set_num_threads(4)
 
-    if ONLY is None:
+    if ONLY is None or "smoke" in ONLY:
         smoke_fixtures()
     p = _params()
     rnnt_case("ref_rnnt_small_full", 0, B=3, T=9, U=5, p=p, tlens=[9, 9, 9], ulens=[5, 5, 5])
@@ -287,6 +337,11 @@ def main():
                  ulens=[5, 4, 2, 5], plens=[9, 7, 3, 8], phone_w=0.3, hie=False, inter_w=0.0)
     ctc_mtl_case("ref_ctc_phone_hie_inter", 10, B=4, T=22, U=6, Up=10, V=29, Vp=43, He=16, tlens=[22, 20, 11, 6],
                  ulens=[6, 5, 6, 1], plens=[10, 8, 9, 2], phone_w=0.3, hie=True, inter_w=0.5)
+    # knowledge distillation on the transducer (word / align), both ways of combining it with the main loss
+    rnnt_kd_case("ref_rnnt_kd_word", 14, B=3, T=13, U=5, p=pm, tlens=[13, 11, 8], ulens=[5, 3, 4],
+                 kd_type="word", reduce_main=True)
+    rnnt_kd_case("ref_rnnt_kd_align", 15, B=3, T=12, U=5, p=pm, tlens=[12, 12, 7], ulens=[5, 4, 2],
+                 kd_type="align", reduce_main=False)
     # the reference's greedy search (decode-time joint)
     rnnt_greedy_case("ref_rnnt_greedy", 13, B=5, T=23, p=pm, tlens=[23, 20, 14, 9, 1], blank_bias=3.0)
     # enc_hidden_size the fused tensor-core CTC head accepts (He % 128 == 0): main head with an odd vocabulary, an

@@ -172,3 +172,50 @@ def joint_loss_and_grads(eouts, douts, w_enc, b_enc, w_dec, b_dec, w_out, b_out,
         "d_w_dec": d_w_dec, "d_b_dec": d_b_dec,
         "d_w_out": d_w_out, "d_b_out": d_b_out,
     }
+
+
+def forced_align(log_probs, labels, tlens, ulens, blank=0):
+    """RNNTForcedAligner.__call__ (asr/modeling/decoders/rnnt_aligner.py:155-198): best_aligns (B, U1max-1) int32.
+    Walk from (0,0); at each cell compare alpha+beta of (t+1,u) and (t,u+1) (:188-196); labels the walk does not
+    reach keep the initial 0."""
+    B, Tm, U1m, _ = log_probs.shape
+    out = np.zeros((B, U1m - 1), dtype=np.int32)
+    for b in range(B):
+        T, U = int(tlens[b]), int(ulens[b])
+        lp = log_probs[b].astype(np.float64)
+        lpb = lp[..., blank]
+        lpl = np.zeros((Tm, U1m))
+        if U > 0:
+            lpl[:, :U] = lp[:, np.arange(U), np.asarray(labels[b, :U], dtype=np.int64)]
+        alpha, beta, _ = lattice(lpb, lpl, T, U)
+        ab = alpha + beta
+        t = u = 0
+        while t + 1 < T and u < U:
+            if ab[t + 1, u] > ab[t, u + 1]:
+                t += 1
+            else:
+                out[b, u] = t
+                u += 1
+    return out
+
+
+def word_distill_loss(logits, soft_labels, xlens, ylens):
+    """RNNTWordDistillLoss.forward (asr/criteria.py:218-249), normalize_length = normalize_batch = True."""
+    loss = 0.0
+    for b in range(logits.shape[0]):
+        x, y = int(xlens[b]), int(ylens[b])
+        lp = log_softmax(logits[b, :x, :y].astype(np.float64))
+        loss -= float((soft_labels[b, :y][None] * lp).sum()) / (x * y)
+    return loss / logits.shape[0]
+
+
+def align_distill_loss(logits, soft_labels, aligns, xlens, ylens):
+    """RNNTAlignDistillLoss.forward (asr/criteria.py:252-288) AS WRITTEN: `loss_u` is overwritten inside the loop over
+    u (:272-278) and subtracted once after it (:280-282), so only the last label's cell contributes."""
+    loss = 0.0
+    for b in range(logits.shape[0]):
+        y = int(ylens[b])
+        u = y - 1
+        lp = log_softmax(logits[b, int(aligns[b][u]), u].astype(np.float64))
+        loss -= float((soft_labels[b, u] * lp).sum()) / y
+    return loss / logits.shape[0]

@@ -387,3 +387,79 @@ def test_greedy_search_vs_reference_golden():
         fused = dec.joint(e, d)
         dense = dec._dense_joint(e, d)
     assert fused.shape == dense.shape and float((fused - dense).abs().max()) < 1e-4
+
+
+# ---------------------------------------------------------------- forced aligner + distillation on the fused lattice
+def test_forced_aligner_vs_reference_smoke_fixture():
+    """emoasr_b200.RNNTForcedAligner (dense log-probs in, like rnnt_aligner.py:155-198) against what the unmodified
+    Numba aligner returned on its own smoke input (rnnt_aligner.py:201-208)."""
+    import emoasr_b200 as E
+    g = load_golden("ref_rnnt_aligner_smoke")
+    al = E.RNNTForcedAligner(blank_id=0)(T_(g["log_probs"]), T_(g["T"]), T_(g["labels"]), T_(g["U"]))
+    assert al.dtype == torch.int32 and np.array_equal(al.cpu().numpy(), g["aligns"])
+
+
+KD_KEYS = RNNT_KEYS + ["kd_type", "reduce_main_loss_kd"]
+
+
+@pytest.mark.parametrize("name", ["ref_rnnt_kd_word", "ref_rnnt_kd_align"])
+def test_rnnt_decoder_distillation_vs_reference_golden(name):
+    """kd_weight > 0 (rnn_transducer.py:127-141) WITHOUT the dense logits: the word loss from the fused joint's
+    differentiable per-cell lse, the align loss from the forced alignment computed on the loss's own lattice.
+    fp32 mode against the unmodified reference: loss 1e-5, gradients 1e-4."""
+    from emoasr_b200.decoders import RNNTDecoder
+    g = load_golden(name)
+    dec = RNNTDecoder(_params_from_golden(g, KD_KEYS), phase="train")
+    dec.fused_precision = "fp32"
+    dec.load_state_dict({k[len("param."):]: torch.from_numpy(v) for k, v in g.items() if k.startswith("param.")})
+    dec = dec.to(dev()).train()
+    eouts = T_(g["eouts"]).requires_grad_()
+    loss, loss_dict, logits = dec(eouts, T_(g["elens"]), None, T_(g["ys"]), T_(g["ylens"]), T_(g["ys_in"]),
+                                  T_(g["ys_out"]), T_(g["soft_labels"]))
+    loss.backward()
+    assert logits is None
+    for k in ("loss_rnnt", "loss_kd", "loss_total"):
+        assert abs(float(loss_dict[k]) - float(g["lossdict." + k])) <= LOSS_RTOL * abs(float(g["lossdict." + k])), k
+    assert rel_err(eouts.grad.cpu().numpy(), g["grad_eouts"]) < GRAD_RTOL
+    for k, v in dec.named_parameters():
+        ref = g["grad." + k]
+        if ref.size == 0:
+            continue
+        assert rel_err(v.grad.cpu().numpy(), ref) < GRAD_RTOL, k
+    if "aligns" in g:
+        from emoasr_b200 import functional as F
+        with torch.no_grad():
+            douts, _ = dec.recurrency(T_(g["ys_in"]), None)
+            _, _, al = F.rnnt_joint_outputs(dec.w_enc(T_(g["eouts"])), dec.w_dec(douts), dec.output.weight,
+                                            dec.output.bias, T_(g["ys"]), T_(g["elens"]), T_(g["ylens"]),
+                                            precision="fp32", aligns=True)
+        assert np.array_equal(al.cpu().numpy(), g["aligns"])
+
+
+def test_lse_output_gradient_bf16_vs_fp32_mode():
+    """The tensor-core backward with a gradient on the lse output (grad_lse * softmax(z) added to dz in the ring
+    kernel's epilogue) against the fp32 mode, plus a finite-difference-free identity: with cost weight 0 and
+    grad_lse = 1 on valid cells, d_b_out = sum over valid cells of softmax(z) -> sums to the number of valid cells."""
+    from emoasr_b200 import functional as F
+    gen = torch.Generator().manual_seed(31)
+    B, T, U, V, J = 3, 30, 11, 512, 256
+    enc = torch.randn(B, T, J, generator=gen).to(dev())
+    dec_ = torch.randn(B, U + 1, J, generator=gen).to(dev())
+    w = (torch.randn(V, J, generator=gen) / J ** 0.5).to(dev())
+    bo = (0.1 * torch.randn(V, generator=gen)).to(dev())
+    ys = torch.randint(1, V, (B, U), generator=gen).to(dev())
+    tl, ul = torch.tensor([30, 21, 9], device=dev()), torch.tensor([11, 6, 11], device=dev())
+    wgt = torch.rand(B, T, U + 1, generator=gen).to(dev())
+    out = {}
+    for prec in ("fp32", "bf16"):
+        te = [t.clone().requires_grad_() for t in (enc, dec_, w, bo)]
+        costs, lse, _ = F.rnnt_joint_outputs(*te, ys, tl, ul, precision=prec)
+        (costs.mean() + (wgt * lse).sum() / 50).backward()
+        out[prec] = [t.grad for t in te]
+    for a, b_, k in zip(out["bf16"], out["fp32"], ("d_enc", "d_dec", "d_w_out", "d_b_out")):
+        assert float((a - b_).norm() / b_.norm()) < BF16_GRAD_RTOL, k
+    te = [t.clone().requires_grad_() for t in (enc, dec_, w, bo)]
+    costs, lse, _ = F.rnnt_joint_outputs(*te, ys, tl, ul, precision="bf16")
+    lse.sum().backward()
+    n_valid = float((tl * (ul + 1)).sum())
+    assert abs(float(te[3].grad.sum()) - n_valid) < 2e-2 * n_valid

@@ -156,3 +156,34 @@ def test_torch_path_matches_dp_random():
     assert abs(float(loss) - r["loss"]) < 1e-5 * r["loss"]
     for t, k in zip(te, ["d_eouts", "d_douts", "d_w_enc", "d_b_enc", "d_w_dec", "d_b_dec", "d_w_out", "d_b_out"]):
         assert rel_err(t.grad.numpy(), r[k]) < 1e-4, k
+
+
+def test_forced_align_restatement_vs_reference():
+    """oracle.rnnt_dp.forced_align against alignments the UNMODIFIED RNNTForcedAligner produced (its Numba CUDA
+    kernels run under the CUDA simulator in oracle/gen_golden.py): the in-tree smoke input of rnnt_aligner.py:201-208
+    and the kd_type="align" decoder case."""
+    g = load_golden("ref_rnnt_aligner_smoke")
+    assert np.array_equal(rnnt_dp.forced_align(g["log_probs"], g["labels"], g["T"], g["U"]), g["aligns"])
+    g = load_golden("ref_rnnt_kd_align")
+    P = {k[len("param."):]: v.astype(np.float64) for k, v in g.items() if k.startswith("param.")}
+    douts = pred_net_douts(g)
+    _, _, _, z = rnnt_dp.joint_logits(g["eouts"], douts, P["w_enc.weight"], P["w_enc.bias"], P["w_dec.weight"],
+                                      P["w_dec.bias"], P["output.weight"], P["output.bias"])
+    al = rnnt_dp.forced_align(rnnt_dp.log_softmax(z), g["ys"], g["elens"], g["ylens"])
+    assert np.array_equal(al, g["aligns"])
+    kd = rnnt_dp.align_distill_loss(z, g["soft_labels"], al, g["elens"], g["ylens"])
+    assert abs(kd - float(g["lossdict.loss_kd"])) <= 1e-5 * abs(kd)
+
+
+def test_word_distill_restatement_vs_reference():
+    g = load_golden("ref_rnnt_kd_word")
+    P = {k[len("param."):]: v.astype(np.float64) for k, v in g.items() if k.startswith("param.")}
+    douts = pred_net_douts(g)
+    _, _, _, z = rnnt_dp.joint_logits(g["eouts"], douts, P["w_enc.weight"], P["w_enc.bias"], P["w_dec.weight"],
+                                      P["w_dec.bias"], P["output.weight"], P["output.bias"])
+    kd = rnnt_dp.word_distill_loss(z, g["soft_labels"], g["elens"], g["ylens"])
+    assert abs(kd - float(g["lossdict.loss_kd"])) <= 1e-5 * abs(kd)
+    # loss_total = (1 - w) * loss_rnnt + w * loss_kd  (reduce_main_loss_kd, rnn_transducer.py:138-139)
+    w = float(g["hp.kd_weight"])
+    total = (1 - w) * float(g["lossdict.loss_rnnt"]) + w * kd
+    assert abs(total - float(g["loss_total"])) <= 1e-5 * abs(total)
