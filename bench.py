@@ -324,7 +324,7 @@ def rnnt_kernel_roofline(args, w, wl, resident, flush, dev):
 
     def call_bwd():
         rc = lib.emo_rnnt_joint_bwd(p(enc_proj), p(dec_proj), p(wo), p(bo), p(resident[2]), p(resident[3]),
-                                    p(resident[4]), p(lse), p(lp2), p(gamma2), p(gcost), B, T, U1, J, V,
+                                    p(resident[4]), p(lse), p(lp2), p(gamma2), p(gcost), p(None), B, T, U1, J, V,
                                     0, 1, p(d_enc), p(d_dec), p(d_w), p(d_b), p(wsb), wsb.numel(), st)
         _lib.check(rc, "emo_rnnt_joint_bwd")
 
