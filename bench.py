@@ -201,23 +201,20 @@ def time_call(fn, flush, iters):
 
 
 # ------------------------------------------------------------------------------------------------
-def rnnt_step_fn(E, wl, precision, params, buckets, payload, world):
+def rnnt_step_fn(E, wl, precision, params, reducer, payload, world):
     crit = E.RNNTJointLoss(blank_id=0, precision=precision)
 
     def step(eouts, douts, ys, tlen, ulen):
-        if buckets is not None:
-            buckets.zero()          # in place: the gradients live inside the all-reduce buckets
-        else:
-            for p in params:
-                p.grad = None
+        for p in params:
+            p.grad = None           # optimizer.zero_grad(): autograd assigns the new gradients
         eouts = eouts.detach().requires_grad_()
         douts = douts.detach().requires_grad_()
         loss = crit(wl.w_enc(eouts), wl.w_dec(douts), wl.output.weight, wl.output.bias, ys, tlen, ulen)
-        loss.backward()             # the buckets' all-reduces are launched from autograd hooks during this call
+        loss.backward()             # every gradient's all-reduce is launched from an autograd hook during this call
         if world > 1:
             if payload is not None:
-                buckets.start_extra(payload)   # stand-in for the rest of the model's gradients
-            buckets.finish()        # compute stream waits for the collectives (no host sync)
+                reducer.start_extra(payload)   # stand-in for the rest of the model's gradients
+            reducer.finish()        # compute stream waits for the collectives (no host sync)
         return loss
     return step
 
@@ -231,13 +228,10 @@ def run_ours_rnnt(args, w, rank, world, dev):
     torch.backends.cuda.matmul.allow_tf32 = args.precision == "bf16"
     wl = RNNTWorkload(w, seed=rank, regime=args.lengths)
     mods = torch.nn.ModuleList([wl.w_enc, wl.w_dec, wl.output]).to(dev)
-    # bucket order = order in which the gradients become final: output.* when the fused backward retires, then
-    # w_dec.*, w_enc.* (small GEMMs after the axis reductions)
     params = [wl.output.weight, wl.output.bias, wl.w_dec.weight, wl.w_dec.bias, wl.w_enc.weight, wl.w_enc.bias]
     buckets, payload = None, None
     if world > 1:
-        buckets = sharding.GradBuckets(params, bucket_bytes=2200 << 10, own_grads=True)   # p.grad = views of flat buckets
-        buckets.attach_hooks()
+        buckets = sharding.GradReducer(params)   # per-gradient all-reduce from autograd hooks, in place
         if args.grad_payload_mb > 0:
             payload = torch.zeros(int(args.grad_payload_mb * 1e6) // 4, device=dev)
     host = [t.pin_memory() for t in (wl.eouts, wl.douts, wl.ys.int(), wl.tlen.int(), wl.ulen.int())]
@@ -274,8 +268,8 @@ def run_ours_rnnt(args, w, rank, world, dev):
     if world > 1:
         # diagnosis of the scaling loss: every rank's step WITHOUT the collective (same kernels, same inputs).  The
         # synchronised step can never be faster than the slowest GPU's local step.
-        local = rnnt_step_fn(E, wl, args.precision, params, buckets, None, 1)
-        buckets.detach_hooks()
+        local = rnnt_step_fn(E, wl, args.precision, params, None, None, 1)
+        buckets.enabled = False
         for _ in range(3):
             local(*resident)
         n = max(5, args.steps // 2)
@@ -737,7 +731,7 @@ def main():
               "parallelism": (f"batch-sharded x{world}; NCCL all-reduce (AVG) of the path's parameter grads"
                               + (f" + {args.grad_payload_mb:.1f} MB stand-in for the rest of the 25.8 M-parameter model's grads"
                                  if args.grad_payload_mb > 0 and w["kind"] == "rnnt" else "")
-                              + ", launched from autograd hooks (overlaps the backward), stream-ordered wait")
+                              + ", every gradient reduced in place from its autograd hook (overlaps the backward), stream-ordered wait")
               if world > 1 else "single GPU",
               "l2": "L2 flushed (256 MiB write, untimed) between timed steps",
               "e2e": "per step: H2D of the step's inputs from pinned host memory on a copy stream (prefetched "

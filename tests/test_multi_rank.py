@@ -63,6 +63,25 @@ def _worker(rank, world, port, out, own_grads=False, hooks=False):
     torch.set_num_threads(1)
     eouts, douts, ys, tl, ul, lin = _make_problem()
     batch = sharding.shard_batch({"eouts": eouts, "douts": douts, "ys": ys, "tl": tl, "ul": ul}, rank, world)
+    if hooks == "reducer":   # bench.py's N > 1 mode: per-gradient all-reduce from hooks, gradients assigned by autograd
+        red = sharding.GradReducer(lin.parameters(), small_numel=16)
+        extra = torch.full((5,), float(rank + 1))
+        for step in range(2):                      # two steps: the hooks must re-arm
+            for p in lin.parameters():
+                p.grad = None
+            loss = _loss(lin, batch["eouts"], batch["douts"], batch["ys"], batch["tl"], batch["ul"])
+            loss.backward()
+            assert len(red._pending) >= 3          # launched during backward()
+            if step == 1:
+                red.start_extra(extra)
+            red.finish()
+        assert torch.allclose(extra, torch.full((5,), 1.5))
+        mean_loss = sharding.mean_over_replicas(loss)
+        if rank == 0:
+            torch.save({"loss": mean_loss, "grads": [p.grad.clone() for p in lin.parameters()]}, out)
+        dist.barrier()
+        dist.destroy_process_group()
+        return
     buckets = None
     if own_grads:   # gradients accumulate straight into the flat all-reduce buffers
         buckets = sharding.GradBuckets(lin.parameters(), bucket_bytes=256, own_grads=True)
@@ -92,8 +111,8 @@ def _worker(rank, world, port, out, own_grads=False, hooks=False):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("own_grads,hooks", [(False, False), (True, False), (True, True)],
-                         ids=["copy_buckets", "grads_in_buckets", "overlap_hooks"])
+@pytest.mark.parametrize("own_grads,hooks", [(False, False), (True, False), (True, True), (False, "reducer")],
+                         ids=["copy_buckets", "grads_in_buckets", "overlap_hooks", "per_gradient_reducer"])
 def test_two_rank_sharded_step_matches_single_process(tmp_path, own_grads, hooks):
     out = str(tmp_path / "rank0.pt")
     mp.spawn(_worker, args=(2, _free_port(), out, own_grads, hooks), nprocs=2, join=True)
