@@ -201,15 +201,25 @@ def time_call(fn, flush, iters):
 
 
 # ------------------------------------------------------------------------------------------------
-def rnnt_step_fn(E, wl, precision, params, reducer, payload, world):
+def rnnt_step_fn(E, wl, precision, params, reducer, payload, world, folded=None):
+    """folded (default: whenever the tensor-core mode takes the shape): the w_enc / w_dec projections and their backward
+    run inside the library (emo_rnnt_joint_full_*); otherwise plain cuBLAS Linear around the fused joint."""
     crit = E.RNNTJointLoss(blank_id=0, precision=precision)
+    w = wl.w
+    if folded is None:
+        from emoasr_b200 import functional as EF
+        folded = precision == "bf16" and EF.joint_full_supported(w["B"], w["T"], w["U"] + 1, w["He"], w["Hd"], w["J"], w["V"])
+    full = E.RNNTJointFullLoss(blank_id=0)
 
     def step(eouts, douts, ys, tlen, ulen):
         for p in params:
             p.grad = None           # optimizer.zero_grad(): autograd assigns the new gradients
         eouts = eouts.detach().requires_grad_()
         douts = douts.detach().requires_grad_()
-        loss = crit(wl.w_enc(eouts), wl.w_dec(douts), wl.output.weight, wl.output.bias, ys, tlen, ulen)
+        if folded:
+            loss = full(eouts, douts, wl.w_enc, wl.w_dec, wl.output, ys, tlen, ulen)
+        else:
+            loss = crit(wl.w_enc(eouts), wl.w_dec(douts), wl.output.weight, wl.output.bias, ys, tlen, ulen)
         loss.backward()             # every gradient's all-reduce is launched from an autograd hook during this call
         if world > 1:
             if payload is not None:
@@ -237,7 +247,7 @@ def run_ours_rnnt(args, w, rank, world, dev):
     host = [t.pin_memory() for t in (wl.eouts, wl.douts, wl.ys.int(), wl.tlen.int(), wl.ulen.int())]
     resident = [t.to(dev) for t in host]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)  # > 126 MB L2
-    step = rnnt_step_fn(E, wl, args.precision, params, buckets, payload, world)
+    step = rnnt_step_fn(E, wl, args.precision, params, buckets, payload, world, folded=False if args.unfolded else None)
 
     def barrier():
         torch.cuda.synchronize()
@@ -260,7 +270,10 @@ def run_ours_rnnt(args, w, rank, world, dev):
 
     prec = 1 if args.precision == "bf16" else 0
     B, T, U1, J, V = w["B"], w["T"], w["U"] + 1, w["J"], w["V"]
-    per_step = (_lib.launch_count(_lib.OP_RNNT_JOINT_FWD, prec, B, T, U1, J, V)
+    from emoasr_b200 import functional as EF
+    folded = prec == 1 and EF.joint_full_supported(B, T, U1, w["He"], w["Hd"], J, V) and not args.unfolded
+    per_step = (_lib.launch_count(_lib.OP_RNNT_JOINT_FULL, prec, B, T, U1, J, V) if folded else
+                _lib.launch_count(_lib.OP_RNNT_JOINT_FWD, prec, B, T, U1, J, V)
                 + _lib.launch_count(_lib.OP_RNNT_JOINT_BWD, prec, B, T, U1, J, V))
     out = dict(ms_total=ms_total, e2e_s=e2e_s, units=w["B"], clocks=clocks, roofline=None, launches=per_step * args.steps,
                h2d=sum(t.numel() * t.element_size() for t in host), d2h=4, flops=wl.algorithmic_flops(),
@@ -268,7 +281,7 @@ def run_ours_rnnt(args, w, rank, world, dev):
     if world > 1:
         # diagnosis of the scaling loss: every rank's step WITHOUT the collective (same kernels, same inputs).  The
         # synchronised step can never be faster than the slowest GPU's local step.
-        local = rnnt_step_fn(E, wl, args.precision, params, None, None, 1)
+        local = rnnt_step_fn(E, wl, args.precision, params, None, None, 1, folded=False if args.unfolded else None)
         buckets.enabled = False
         for _ in range(3):
             local(*resident)
@@ -717,6 +730,8 @@ def main():
                          "cost of the collective; default 0 = the path's own parameters only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--unfolded", action="store_true",
+                    help="RNN-T workloads: w_enc / w_dec as cuBLAS Linear around the fused joint instead of inside the library")
     ap.add_argument("--ctc-unfused", action="store_true", help="CTC workloads: cuBLAS Linear + loss kernels on logits")
     ap.add_argument("--ctc-fused", action="store_true", help="CTC workloads: fused head also below 8192 frames")
     args = ap.parse_args()
@@ -738,7 +753,9 @@ def main():
                      "during the previous step) + D2H of the loss, read by the host one step late; wall clock"}
     if w["kind"] == "rnnt":
         config["route"] = "logit tiles recomputed by the backward; dz through an L2-resident ring; no N x V tensor in HBM"
-        config["projections"] = "w_enc/w_dec Linear via cuBLAS, " + ("TF32" if args.precision == "bf16" else "fp32")
+        config["projections"] = ("w_enc/w_dec (+ their backward) inside the library: tcgen05 GEMMs, bf16 operands"
+                                 if args.precision == "bf16" and not args.unfolded else
+                                 "w_enc/w_dec Linear via cuBLAS, " + ("TF32" if args.precision == "bf16" else "fp32"))
     else:
         config["head"] = ("output Linear(He,V) forward + backward included in the step: fused tensor-core head (no "
                           "(B,T,V) tensor in memory) where the shape allows, else cuBLAS TF32 + fp32 loss kernels")

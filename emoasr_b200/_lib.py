@@ -9,9 +9,9 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # EMOASR_B200_LIB: an instrumented copy of the library (python -m emoasr_b200.build --prof; tools/ only)
 LIB_PATH = os.environ.get("EMOASR_B200_LIB") or os.path.join(_HERE, "lib", "libemoasr_b200.so")
 
-OP_RNNT_JOINT_FWD, OP_RNNT_JOINT_BWD, OP_CTC, OP_CTC_HEAD = 0, 1, 2, 3
+OP_RNNT_JOINT_FWD, OP_RNNT_JOINT_BWD, OP_CTC, OP_CTC_HEAD, OP_RNNT_JOINT_FULL = 0, 1, 2, 3, 4
 PREC_FP32, PREC_BF16 = 0, 1
-ABI_VERSION = 8
+ABI_VERSION = 9
 
 _c = ctypes
 _P = _c.c_void_p
@@ -29,6 +29,10 @@ _SIGNATURES = {
     "emo_rnnt_dense_bwd": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P, _P]),
     "emo_rnnt_joint_fwd": (_I, [_P] * 7 + [_I] * 7 + [_P, _P, _P, _SZ, _P]),
     "emo_rnnt_joint_bwd": (_I, [_P] * 12 + [_I] * 7 + [_P, _P, _P, _P, _P, _SZ, _P]),
+    "emo_rnnt_joint_full_supported": (_I, [_I] * 7),
+    "emo_rnnt_joint_full_workspace_bytes": (_SZ, [_I] * 8),
+    "emo_rnnt_joint_full_fwd": (_I, [_P] * 11 + [_I] * 8 + [_P, _P, _P, _SZ, _P]),
+    "emo_rnnt_joint_full_bwd": (_I, [_P] * 10 + [_I] * 8 + [_P] * 9 + [_SZ, _P]),
     "emo_rnnt_align": (_I, [_P] * 4 + [_I] * 3 + [_P, _P]),
     "emo_ctc_fwd": (_I, [_P] * 4 + [_I] * 6 + [_P, _P, _P, _P, _P]),
     "emo_ctc_bwd": (_I, [_P] * 8 + [_I] * 6 + [_P, _I, _P, _P]),

@@ -40,6 +40,22 @@ class RNNTJointLoss(nn.Module):
         return costs.mean() if self.normalize_batch else costs.sum()
 
 
+class RNNTJointFullLoss(nn.Module):
+    """RNNTJointLoss with the ``w_enc`` / ``w_dec`` projections (rnn_transducer.py:57-58,153), their backward and every
+    cast inside the library: takes the encoder / prediction-network outputs and the three Linear layers' parameters.
+    Tensor-core mode only."""
+
+    def __init__(self, blank_id=0, normalize_batch=True):
+        super().__init__()
+        self.blank_id = blank_id
+        self.normalize_batch = normalize_batch
+
+    def forward(self, eouts, douts, w_enc, w_dec, output, ys, elens, ylens):
+        costs = F.rnnt_joint_loss_from_outputs(eouts, douts, w_enc.weight, w_enc.bias, w_dec.weight, w_dec.bias,
+                                               output.weight, output.bias, ys, elens, ylens, blank=self.blank_id)
+        return costs.mean() if self.normalize_batch else costs.sum()
+
+
 class CTCLoss(nn.Module):
     """Call-compatible with the ``nn.CTCLoss`` instance the reference keeps in
     ``CTCDecoder.ctc_loss_fn`` (asr/modeling/decoders/ctc.py:36-38, called at :109-110 as

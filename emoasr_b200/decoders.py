@@ -117,16 +117,24 @@ class FusedRNNTForward:
         loss = 0
         loss_dict = {}
         douts, _ = self.recurrency(ys_in, dstate=None)
-        enc_proj = self.w_enc(eouts)   # (B, T, J)
-        dec_proj = self.w_dec(douts)   # (B, L+1, J)
-        assert dec_proj.size(1) == ys.size(1) + 1
-        precision = self._precision_for(enc_proj.size(0), enc_proj.size(1), dec_proj.size(1), enc_proj.size(2),
-                                        self.output.weight.size(0))
+        assert douts.size(1) == ys.size(1) + 1
+        B, T, U1 = eouts.size(0), eouts.size(1), douts.size(1)
+        J, V = self.output.weight.size(1), self.output.weight.size(0)
+        precision = self._precision_for(B, T, U1, J, V)
         wants_kd = self.kd_weight > 0 and soft_labels is not None
         kd_type = getattr(self, "kd_type", None) if wants_kd else None
-        costs, lse, aligns = F.rnnt_joint_outputs(enc_proj, dec_proj, self.output.weight, self.output.bias, ys, elens,
-                                                  ylens, blank=self.blank_id, precision=precision,
-                                                  aligns=kd_type == "align")
+        if (precision == "bf16" and not wants_kd and eouts.is_cuda and self.w_enc.bias is not None and
+                F.joint_full_supported(B, T, U1, eouts.size(2), douts.size(2), J, V)):
+            # projections + joint + loss as two library calls (rnn_transducer.py:57-58,101-115,147-156)
+            costs = F.rnnt_joint_loss_from_outputs(eouts, douts, self.w_enc.weight, self.w_enc.bias, self.w_dec.weight,
+                                                   self.w_dec.bias, self.output.weight, self.output.bias, ys, elens,
+                                                   ylens, blank=self.blank_id)
+        else:
+            enc_proj = self.w_enc(eouts)   # (B, T, J)
+            dec_proj = self.w_dec(douts)   # (B, L+1, J)
+            costs, lse, aligns = F.rnnt_joint_outputs(enc_proj, dec_proj, self.output.weight, self.output.bias, ys,
+                                                      elens, ylens, blank=self.blank_id, precision=precision,
+                                                      aligns=kd_type == "align")
         loss_rnnt = costs.mean()
         loss += loss_rnnt
         loss_dict["loss_rnnt"] = loss_rnnt

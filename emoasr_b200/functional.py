@@ -265,6 +265,83 @@ def rnnt_joint_outputs(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths,
     return costs, lse, (al if aligns else None)
 
 
+def joint_full_supported(B, T, U1, He, Hd, J, V):
+    """True if rnnt_joint_loss_from_outputs can run these sizes (host call, no CUDA work)."""
+    return bool(_lib.load().emo_rnnt_joint_full_supported(B, T, U1, He, Hd, J, V))
+
+
+class _RNNTJointFull(torch.autograd.Function):
+    """The fused joint with the w_enc / w_dec projections (and their backward) inside the library: two C calls per
+    training step, working from the encoder / prediction-network outputs."""
+
+    @staticmethod
+    def forward(ctx, eouts, douts, w_enc, b_enc, w_dec, b_dec, w_out, b_out, labels, tlen, ulen, blank):
+        _require_cuda(eouts, douts, w_enc, w_dec, w_out)
+        lib = _lib.load()
+        e, d = _f32c(eouts), _f32c(douts)
+        we, be, wd, bd, wo, bo = (_f32c(t) for t in (w_enc, b_enc, w_dec, b_dec, w_out, b_out))
+        B, T, He = e.shape
+        U1, Hd = d.size(1), d.size(2)
+        J, V = we.size(0), wo.size(0)
+        dev = e.device
+        labels, tlen, ulen = _i32c(labels, dev), _i32c(tlen, dev), _i32c(ulen, dev)
+        if U1 > 1:
+            labels = labels[:, : U1 - 1].contiguous()
+        else:
+            labels = torch.zeros(B, 1, dtype=torch.int32, device=dev)
+        with torch.cuda.device(dev):
+            nbytes = int(lib.emo_rnnt_joint_full_workspace_bytes(0, B, T, U1, He, Hd, J, V))
+            if nbytes == 0:
+                raise RuntimeError(f"rnnt_joint_loss_from_outputs: unsupported shape B={B} T={T} U1={U1} He={He} Hd={Hd} "
+                                   f"J={J} V={V} (see emo_rnnt_joint_full_supported)")
+            fws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            lp2 = torch.empty(B, T, U1, 2, device=dev)
+            lse = torch.zeros(B, T, U1, device=dev)
+            _lib.check(lib.emo_rnnt_joint_full_fwd(_p(e), _p(d), _p(we), _p(be), _p(wd), _p(bd), _p(wo), _p(bo), _p(labels),
+                                                   _p(tlen), _p(ulen), B, T, U1, He, Hd, J, V, blank, _p(lp2), _p(lse),
+                                                   _p(fws), fws.numel(), _stream()), "emo_rnnt_joint_full_fwd")
+            alpha = torch.empty(B, T, U1, device=dev)
+            beta = torch.empty(B, T, U1, device=dev)
+            cost = torch.empty(B, device=dev)
+            gamma2 = torch.empty(B, T, U1, 2, device=dev)
+            _lib.check(lib.emo_rnnt_lattice_fwd_bwd(_p(lp2), _p(tlen), _p(ulen), B, T, U1, _p(alpha), _p(beta), _p(cost),
+                                                    _p(gamma2), _stream()), "emo_rnnt_lattice_fwd_bwd")
+        ctx.save_for_backward(bo, labels, tlen, ulen, lse, lp2, gamma2, fws)
+        ctx.dims = (B, T, U1, He, Hd, J, V, blank)
+        return cost
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_cost):
+        bo, labels, tlen, ulen, lse, lp2, gamma2, fws = ctx.saved_tensors
+        B, T, U1, He, Hd, J, V, blank = ctx.dims
+        lib = _lib.load()
+        dev = lse.device
+        with torch.cuda.device(dev):
+            g = _f32c(grad_cost)
+            ws = torch.empty(int(lib.emo_rnnt_joint_full_workspace_bytes(1, B, T, U1, He, Hd, J, V)), dtype=torch.uint8,
+                             device=dev)
+            mk = lambda *s: torch.empty(*s, device=dev)
+            d_e, d_d = mk(B, T, He), mk(B, U1, Hd)
+            d_we, d_be, d_wd, d_bd, d_wo, d_bo = mk(J, He), mk(J), mk(J, Hd), mk(J), mk(V, J), mk(V)
+            _lib.check(lib.emo_rnnt_joint_full_bwd(_p(bo), _p(labels), _p(tlen), _p(ulen), _p(lse), _p(lp2), _p(gamma2),
+                                                   _p(g), _p(None), _p(fws), B, T, U1, He, Hd, J, V, blank,
+                                                   _p(d_e), _p(d_d), _p(d_we), _p(d_be), _p(d_wd), _p(d_bd), _p(d_wo),
+                                                   _p(d_bo), _p(ws), ws.numel(), _stream()), "emo_rnnt_joint_full_bwd")
+        return d_e, d_d, d_we, d_be, d_wd, d_bd, d_wo, d_bo, None, None, None, None
+
+
+def rnnt_joint_loss_from_outputs(eouts, douts, w_enc, b_enc, w_dec, b_dec, w_out, b_out, labels, frames_lengths,
+                                 labels_lengths, blank=0, reduction=None):
+    """Per-utterance transducer cost from the encoder outputs (B,T,He) and the prediction-network outputs (B,U+1,Hd):
+    ``rnnt_joint_loss(linear(eouts, w_enc, b_enc), linear(douts, w_dec, b_dec), w_out, b_out, ...)`` with the two
+    projections, their weight / bias gradients and every cast inside the library (rnn_transducer.py:57-58,101-115,
+    147-156).  Tensor-core mode (bf16 operands, fp32 accumulation); shapes outside ``joint_full_supported`` raise."""
+    costs = _RNNTJointFull.apply(eouts, douts, w_enc, b_enc, w_dec, b_dec, w_out, b_out, labels, frames_lengths,
+                                 labels_lengths, int(blank))
+    return _reduce(costs, reduction)
+
+
 def rnnt_forced_align(log_probs, labels, frames_lengths, labels_lengths, blank=0):
     """Drop-in for ``RNNTForcedAligner(blank_id)(log_probs, elens, ys, ylens)`` (rnnt_aligner.py:155-198) on dense
     log-probs (B,T,U+1,V): gathers the {blank,label} pairs, runs the lattice and walks it on the device.

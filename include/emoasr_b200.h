@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define EMO_ABI_VERSION 8
+#define EMO_ABI_VERSION 9
 
 enum emo_status {
     EMO_OK = 0,
@@ -54,7 +54,8 @@ enum emo_op {
     EMO_OP_RNNT_JOINT_FWD = 0,
     EMO_OP_RNNT_JOINT_BWD = 1,
     EMO_OP_CTC = 2,
-    EMO_OP_CTC_HEAD = 3 /* emo_launch_count only: forward + backward of the fused CTC head (J = He) */
+    EMO_OP_CTC_HEAD = 3,       /* emo_launch_count only: forward + backward of the fused CTC head (J = He) */
+    EMO_OP_RNNT_JOINT_FULL = 4 /* emo_launch_count only: emo_rnnt_joint_full_fwd + lattice + _bwd */
 };
 
 int emo_abi_version(void);
@@ -152,6 +153,26 @@ int emo_rnnt_joint_bwd(const float* enc_proj, const float* dec_proj,
                        int B, int T, int U1, int J, int V, int blank, int precision,
                        float* d_enc_proj, float* d_dec_proj, float* d_w_out, float* d_b_out,
                        void* ws, size_t ws_bytes, void* stream);
+
+/* ---- fused joint from the encoder / prediction-network outputs (projections folded in) -----------
+ * emo_rnnt_joint_fwd / _bwd plus `enc_proj = w_enc(eouts) + b_enc`, `dec_proj = w_dec(douts) + b_dec`
+ * (rnn_transducer.py:57-58,153) and their backward, tensor-core mode only.  The projected streams exist only as the
+ * fp16 copies the joint kernels gather from.  eouts (B,T,He), douts (B,U1,Hd), w_enc (J,He), w_dec (J,Hd) fp32.
+ * The forward's workspace `fws` (emo_rnnt_joint_full_workspace_bytes(0, ...), 256-byte aligned) holds the bf16 / fp16
+ * operand copies and must be handed UNCHANGED to the backward, which reads them instead of casting again; the
+ * backward's own workspace is op 1.  All eight gradient outputs are overwritten.  He, Hd multiples of 16; J, B, T, U1
+ * as emo_rnnt_joint_supported. */
+int emo_rnnt_joint_full_supported(int B, int T, int U1, int He, int Hd, int J, int V);
+size_t emo_rnnt_joint_full_workspace_bytes(int op, int B, int T, int U1, int He, int Hd, int J, int V);
+int emo_rnnt_joint_full_fwd(const float* eouts, const float* douts, const float* w_enc, const float* b_enc,
+                            const float* w_dec, const float* b_dec, const float* w_out, const float* b_out,
+                            const int* labels, const int* tlen, const int* ulen, int B, int T, int U1, int He, int Hd,
+                            int J, int V, int blank, float* lp2, float* lse, void* fws, size_t fws_bytes, void* stream);
+int emo_rnnt_joint_full_bwd(const float* b_out, const int* labels, const int* tlen, const int* ulen, const float* lse,
+                            const float* lp2, const float* gamma2, const float* grad_cost, const float* grad_lse,
+                            const void* fws, int B, int T, int U1, int He, int Hd, int J, int V, int blank,
+                            float* d_eouts, float* d_douts, float* d_w_enc, float* d_b_enc, float* d_w_dec,
+                            float* d_b_dec, float* d_w_out, float* d_b_out, void* ws, size_t ws_bytes, void* stream);
 
 /* ---- CTC (ctc.py:109-113; torch.nn.CTCLoss semantics) ----------------------------------------
  * logits (B,T,V) fp32 contiguous -- the log_softmax of ctc.py:110 is fused: the kernels read raw

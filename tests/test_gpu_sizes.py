@@ -463,3 +463,36 @@ def test_lse_output_gradient_bf16_vs_fp32_mode():
     lse.sum().backward()
     n_valid = float((tl * (ul + 1)).sum())
     assert abs(float(te[3].grad.sum()) - n_valid) < 2e-2 * n_valid
+
+
+# ---------------------------------------------------------------- projections folded into the library
+FULL_SHAPES = [
+    # B, T, U, He, Hd, J, V
+    (2, 20, 7, 64, 48, 128, 96),        # one output tile everywhere, K tails (48 = 0.75 K block)
+    (3, 40, 15, 256, 512, 512, 1024),   # cfg-3 layer sizes: two 256-column tiles in the forward projections
+    (2, 150, 30, 144, 320, 256, 1000),  # hidden sizes that are not multiples of 64, odd vocabulary, split-K weight grads
+]
+
+
+@pytest.mark.parametrize("B,T,U,He,Hd,J,V", FULL_SHAPES)
+def test_joint_from_outputs_vs_oracle(B, T, U, He, Hd, J, V):
+    """emo_rnnt_joint_full_fwd / _bwd (w_enc / w_dec projections, their weight and bias gradients and all casts inside
+    the library) against the fp64 oracle of the whole joint: loss and all eight gradients."""
+    import emoasr_b200 as E
+    from oracle import rnnt_dp
+    rng = np.random.default_rng(B * 31 + V)
+    f = lambda *s: rng.standard_normal(s).astype(np.float32)
+    eouts, douts = f(B, T, He), np.tanh(f(B, U + 1, Hd))
+    w_enc, b_enc = f(J, He) / np.sqrt(He), f(J) * 0.1
+    w_dec, b_dec = f(J, Hd) / np.sqrt(Hd), f(J) * 0.1
+    w_out, b_out = f(V, J) * (2.0 / np.sqrt(J)), f(V) * 0.5
+    ys = rng.integers(1, V, (B, U))
+    tl = rng.integers(1, T + 1, B); tl[0] = T
+    ul = rng.integers(0, U + 1, B); ul[0] = U
+    r = rnnt_dp.joint_loss_and_grads(eouts, douts, w_enc, b_enc, w_dec, b_dec, w_out, b_out, ys, tl, ul)
+    te = [T_(a).requires_grad_() for a in (eouts, douts, w_enc, b_enc, w_dec, b_dec, w_out, b_out)]
+    loss = E.rnnt_joint_loss_from_outputs(*te, T_(ys), T_(tl), T_(ul), blank=0, reduction="mean")
+    loss.backward()
+    assert abs(float(loss) - r["loss"]) <= BF16_LOSS_RTOL * abs(r["loss"])
+    for t, k in zip(te, ["d_eouts", "d_douts", "d_w_enc", "d_b_enc", "d_w_dec", "d_b_dec", "d_w_out", "d_b_out"]):
+        assert rel_err(t.grad.cpu().numpy(), r[k]) < BF16_GRAD_RTOL, k
