@@ -1120,10 +1120,14 @@ struct RingGeom {
 };
 RingGeom ring_geom(int B, int J, int V) {
     RingGeom g;
+    int slots = kRingSlots;
+#if defined(EMO_TUNING) || defined(EMO_ZC_PROF)
+    if (const char* e = getenv("EMO_RING_SLOTS")) slots = max(8, atoi(e));   // tuning builds only (tools/)
+#endif
     g.vgw = (min(V, kVG) + 63) / 64 * 64;
     g.G = ceil_div(V, kVG);
-    g.NZ = kRingSlots / g.G * g.G;      // a multiple of G: a slot always serves the same vocab group
-    g.NH = kRingSlots;
+    g.NZ = slots / g.G * g.G;      // a multiple of G: a slot always serves the same vocab group
+    g.NH = slots;
     g.z_bytes = align_up((size_t)g.NZ * kPairM * g.vgw * 2, 1024);
     g.h_bytes = align_up((size_t)g.NH * kPairM * J * 2, 1024);
     g.flag_bytes = align_up((size_t)(2 * g.NZ + 2 * g.NH) * sizeof(int), 256);
