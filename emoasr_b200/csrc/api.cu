@@ -66,9 +66,10 @@ extern "C" int emo_launch_count(int op, int precision, int B, int T, int U1, int
                                               : joint_f32_launches(op, B, T, U1, J, V);
         case EMO_OP_CTC:
             return 3;  // row lse + emission gather, alpha || beta lattices, gradient
-        case EMO_OP_RNNT_JOINT_FULL:   // fwd: casts, 2 projections, joint forward, lattice + posteriors; bwd: ring prep,
-                                       // ring kernel, axis reductions, 2 casts, 2 bias sums, 4 projection GEMMs
-            return 17 + ((V + 31) / 32 * 32 != V ? 1 : 0);
+        case EMO_OP_RNNT_JOINT_FULL:   // fwd: casts, both projections, joint forward, lattice, posteriors; bwd: ring prep,
+                                       // ring kernel, axis reductions (+ d_enc copy / bias sums), d_dec copy + bias sums,
+                                       // both d_x GEMMs, both d_W GEMMs
+            return 11 + ((V + 31) / 32 * 32 != V ? 1 : 0);
         case EMO_OP_CTC_HEAD:   // J = He.  fwd: prep, 2 casts, label-row gather, joint forward, emissions, lattices; bwd: prep,
                                 // 2 casts, gather, per-frame scale, ring prep, ring kernel, occupancies, d_eouts, d_W
                                 // (+ the vocabulary padding kernel in each)

@@ -156,7 +156,8 @@ int ctc_lattice_launch(const long long* labels, const long long* tlen, const lon
                        int Umax, int blank, int zero_infinity, float* alpha_ws, float* beta_ws, float* nll,
                        cudaStream_t st);
 int joint_reduce_dh_launch_f16(const void* dh_ws, const void* enc16, const void* dec16, const int* tlen, const int* ulen,
-                               int B, int T, int U1, int J, float* d_enc_proj, float* d_dec_proj, cudaStream_t st);
+                               int B, int T, int U1, int J, float* d_enc_proj, float* d_dec_proj, void* d_enc_bf,
+                               cudaStream_t st);
 size_t joint_bf16_workspace(int op, int B, int T, int U1, int J, int V);
 int joint_bf16_launches(int op, int B, int T, int U1, int J, int V);
 

@@ -54,7 +54,7 @@ __global__ void __launch_bounds__(kRedWarps * 32, 4)
 reduce_dh_tanh_kernel(const __nv_bfloat16* __restrict__ dh, const TIn* __restrict__ enc_proj,
                       const TIn* __restrict__ dec_proj, const int* __restrict__ tlen,
                       const int* __restrict__ ulen, int T, int U1, int J, int tpu, float* __restrict__ d_enc,
-                      float* __restrict__ d_dec) {
+                      float* __restrict__ d_dec, __nv_bfloat16* __restrict__ d_enc_bf) {
     __shared__ float4 s_enc[kRedWarps][kRedTG][32];
     const int b = blockIdx.z, j0 = blockIdx.x * kRedCols;
     const int t0 = blockIdx.y * kRedTG;
@@ -121,6 +121,9 @@ reduce_dh_tanh_kernel(const __nv_bfloat16* __restrict__ dh, const TIn* __restric
             a.x += x.x; a.y += x.y; a.z += x.z; a.w += x.w;
         }
         reinterpret_cast<float4*>(d_enc + ((size_t)b * T + t0 + k) * J + j0)[l] = a;
+        if (d_enc_bf)   // bf16 copy for the projection backward (emo_rnnt_joint_full_bwd)
+            reinterpret_cast<uint2*>(d_enc_bf + ((size_t)b * T + t0 + k) * J + j0)[l] =
+                make_uint2(pack_bf16x2(a.x, a.y), pack_bf16x2(a.z, a.w));
     }
 }
 
@@ -134,17 +137,19 @@ int joint_reduce_dh_launch(const void* dh_ws, const float* enc_proj, const float
                 "joint_bwd(bf16): enc_proj / dec_proj must be given and 16-byte aligned");
     reduce_dh_tanh_kernel<float><<<dim3(J / kRedCols, ceil_div(T, kRedTG), B), kRedWarps * 32, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(dh_ws), enc_proj, dec_proj, tlen, ulen, T, U1, J,
-        tiles128_per_utt(T, U1), d_enc_proj, d_dec_proj);
+        tiles128_per_utt(T, U1), d_enc_proj, d_dec_proj, nullptr);
     EMO_CHECK_LAUNCH("reduce_dh_tanh_kernel");
     return EMO_OK;
 }
 
-// same from the fp16 streams (emo_rnnt_joint_full_bwd)
+// same from the fp16 streams (emo_rnnt_joint_full_bwd); also leaves a bf16 copy of d_enc_proj
 int joint_reduce_dh_launch_f16(const void* dh_ws, const void* enc16, const void* dec16, const int* tlen, const int* ulen,
-                               int B, int T, int U1, int J, float* d_enc_proj, float* d_dec_proj, cudaStream_t st) {
+                               int B, int T, int U1, int J, float* d_enc_proj, float* d_dec_proj, void* d_enc_bf,
+                               cudaStream_t st) {
     reduce_dh_tanh_kernel<__half><<<dim3(J / kRedCols, ceil_div(T, kRedTG), B), kRedWarps * 32, 0, st>>>(
         reinterpret_cast<const __nv_bfloat16*>(dh_ws), reinterpret_cast<const __half*>(enc16),
-        reinterpret_cast<const __half*>(dec16), tlen, ulen, T, U1, J, tiles128_per_utt(T, U1), d_enc_proj, d_dec_proj);
+        reinterpret_cast<const __half*>(dec16), tlen, ulen, T, U1, J, tiles128_per_utt(T, U1), d_enc_proj, d_dec_proj,
+        reinterpret_cast<__nv_bfloat16*>(d_enc_bf));
     EMO_CHECK_LAUNCH("reduce_dh_tanh_kernel");
     return EMO_OK;
 }

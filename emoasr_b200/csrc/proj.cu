@@ -28,9 +28,13 @@ enum { EPI_F16_BIAS = 0, EPI_F32 = 1, EPI_F32_ADD = 2 };
 
 struct ProjArgs {
     int M, N, K;          // C is M x N; K = contraction length
-    int kchunk;           // k-blocks (of 64) per CTA along blockIdx.z
+    int kchunk;           // k-blocks (of 64) per CTA of one output tile (split over K)
+    int mt, nt, kt;       // CTAs along M, N and K
     const float* bias;    // EPI_F16_BIAS: (N)
     void* out;            // row-major (M, N): __half (EPI_F16_BIAS) or float
+};
+struct ProjArgs2 {        // the enc and the dec instance of a form share one launch
+    ProjArgs p[2];
 };
 
 struct __align__(16) ProjBars {
@@ -44,16 +48,25 @@ __device__ __forceinline__ uint64_t pdesc(uint32_t lo) { return ((uint64_t)kPDes
 
 template <int FORM, int EPI>
 __global__ void __launch_bounds__(kPThreads, 1)
-proj_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_b, const ProjArgs a) {
+proj_gemm_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_b0,
+                 const __grid_constant__ CUtensorMap tm_a1, const __grid_constant__ CUtensorMap tm_b1,
+                 const ProjArgs2 args) {
     extern __shared__ __align__(1024) uint8_t smem[];
+    const int n0ctas = args.p[0].mt * args.p[0].nt * args.p[0].kt;
+    const bool second = (int)blockIdx.x >= n0ctas;
+    const ProjArgs& a = args.p[second ? 1 : 0];
+    const CUtensorMap& tm_a = second ? tm_a1 : tm_a0;
+    const CUtensorMap& tm_b = second ? tm_b1 : tm_b0;
+    const int cta = (int)blockIdx.x - (second ? n0ctas : 0);
+    const int bx = cta % a.mt, by = (cta / a.mt) % a.nt, bz = cta / (a.mt * a.nt);
     uint8_t* sA = smem;
     uint8_t* sB = sA + (size_t)kPStages * kPABytes;
     ProjBars* bars = reinterpret_cast<ProjBars*>(sB + (size_t)kPStages * kPBBytes);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int m0 = blockIdx.x * kTileM, n0 = blockIdx.y * kPNT;
+    const int m0 = bx * kTileM, n0 = by * kPNT;
     const int nt = min(kPNT, a.N - n0);                     // live columns of this tile (multiple of 16)
     const int nkb_all = (a.K + kBlockK - 1) / kBlockK;
-    const int kb0 = blockIdx.z * a.kchunk, kb1 = min(nkb_all, kb0 + a.kchunk);
+    const int kb0 = bz * a.kchunk, kb1 = min(nkb_all, kb0 + a.kchunk);
     if (kb0 >= kb1) return;
 
     if (warp == 1 && lane == 0) {
@@ -174,27 +187,42 @@ proj_gemm_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     }
 }
 
+struct ProjProblem {
+    const void* A;
+    const void* B;
+    int M, N, K;
+    const float* bias;
+    void* out;
+    int ksplit;
+};
+
 template <int FORM, int EPI>
-int proj_gemm(const void* A, const void* Bm, int M, int N, int K, const float* bias, void* out, int ksplit,
-              cudaStream_t st) {
-    // tensor maps: (inner, outer, box_inner, box_outer)
-    CUtensorMap tm_a, tm_b;
-    int rc;
-    if (FORM == FORM_H) rc = make_tmap_bf16_2d(&tm_a, A, (uint64_t)M, (uint64_t)K, 64, 64);
-    else rc = make_tmap_bf16_2d(&tm_a, A, (uint64_t)K, (uint64_t)M, kBlockK, kTileM);
-    if (rc) return rc;
-    if (FORM == FORM_F) rc = make_tmap_bf16_2d(&tm_b, Bm, (uint64_t)K, (uint64_t)N, kBlockK, min(N, kPNT));
-    else rc = make_tmap_bf16_2d(&tm_b, Bm, (uint64_t)N, (uint64_t)K, 64, 64);
-    if (rc) return rc;
-    ProjArgs a;
-    a.M = M; a.N = N; a.K = K; a.bias = bias; a.out = out;
-    const int nkb = ceil_div(K, kBlockK);
-    ksplit = max(1, min(ksplit, nkb));
-    a.kchunk = ceil_div(nkb, ksplit);
+int proj_gemm2(const ProjProblem& q0, const ProjProblem& q1, cudaStream_t st) {
+    CUtensorMap tm[4];
+    ProjArgs2 args;
+    int total = 0;
+    for (int i = 0; i < 2; ++i) {
+        const ProjProblem& q = i ? q1 : q0;
+        int rc;
+        // tensor maps: (inner, outer, box_inner, box_outer)
+        if (FORM == FORM_H) rc = make_tmap_bf16_2d(&tm[2 * i], q.A, (uint64_t)q.M, (uint64_t)q.K, 64, 64);
+        else rc = make_tmap_bf16_2d(&tm[2 * i], q.A, (uint64_t)q.K, (uint64_t)q.M, kBlockK, kTileM);
+        if (rc) return rc;
+        if (FORM == FORM_F) rc = make_tmap_bf16_2d(&tm[2 * i + 1], q.B, (uint64_t)q.K, (uint64_t)q.N, kBlockK, min(q.N, kPNT));
+        else rc = make_tmap_bf16_2d(&tm[2 * i + 1], q.B, (uint64_t)q.N, (uint64_t)q.K, 64, 64);
+        if (rc) return rc;
+        ProjArgs& a = args.p[i];
+        a.M = q.M; a.N = q.N; a.K = q.K; a.bias = q.bias; a.out = q.out;
+        const int nkb = ceil_div(q.K, kBlockK);
+        const int ks = max(1, min(q.ksplit, nkb));
+        a.kchunk = ceil_div(nkb, ks);
+        a.mt = ceil_div(q.M, kTileM); a.nt = ceil_div(q.N, kPNT); a.kt = ceil_div(nkb, a.kchunk);
+        total += a.mt * a.nt * a.kt;
+    }
     const size_t smem = (size_t)kPStages * (kPABytes + kPBBytes) + sizeof(ProjBars);
     auto kern = proj_gemm_kernel<FORM, EPI>;
     EMO_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    kern<<<dim3(ceil_div(M, kTileM), ceil_div(N, kPNT), ceil_div(nkb, a.kchunk)), kPThreads, smem, st>>>(tm_a, tm_b, a);
+    kern<<<total, kPThreads, smem, st>>>(tm[0], tm[1], tm[2], tm[3], args);
     EMO_CHECK_LAUNCH("proj_gemm_kernel");
     return EMO_OK;
 }
@@ -221,13 +249,18 @@ __global__ void multi_cast_kernel(const CastArgs a) {
     }
 }
 
-// column sums of an (M, N) fp32 matrix (bias gradients): block = 32 columns x 8 row lanes
-__global__ void colsum_kernel(const float* __restrict__ x, int M, int N, float* __restrict__ out) {
+// bf16 copy + column sums (bias gradient) of an (M, N) fp32 matrix in one pass: block = 32 columns x 8 row lanes
+__global__ void cast_colsum_kernel(const float* __restrict__ x, int M, int N, __nv_bfloat16* __restrict__ xb,
+                                   float* __restrict__ out, float* __restrict__ out2) {
     __shared__ float s[8][33];
     const int c = blockIdx.x * 32 + threadIdx.x;
     float acc = 0.f;
     if (c < N)
-        for (int r = blockIdx.y * 8 + threadIdx.y; r < M; r += gridDim.y * 8) acc += x[(size_t)r * N + c];
+        for (int r = blockIdx.y * 8 + threadIdx.y; r < M; r += gridDim.y * 8) {
+            const float v = x[(size_t)r * N + c];
+            xb[(size_t)r * N + c] = __float2bfloat16_rn(v);
+            acc += v;
+        }
     s[threadIdx.y][threadIdx.x] = acc;
     __syncthreads();
     if (threadIdx.y == 0 && c < N) {
@@ -235,16 +268,7 @@ __global__ void colsum_kernel(const float* __restrict__ x, int M, int N, float* 
 #pragma unroll
         for (int i = 0; i < 8; ++i) t += s[i][threadIdx.x];
         atomicAdd(out + c, t);
-    }
-}
-
-__global__ void f32_to_bf16_plain_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, size_t n) {
-    const size_t i = ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 4;
-    if (i + 3 < n) {
-        const float4 v = *reinterpret_cast<const float4*>(src + i);
-        *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16x2(v.x, v.y), pack_bf16x2(v.z, v.w));
-    } else {
-        for (size_t j = i; j < n; ++j) dst[j] = __float2bfloat16_rn(src[j]);
+        atomicAdd(out2 + c, t);
     }
 }
 
@@ -362,8 +386,9 @@ extern "C" int emo_rnnt_joint_full_fwd(const float* eouts, const float* douts, c
         bias = L.b_pad;
     }
     // projections straight to the fp16 streams the joint kernels gather from
-    if ((rc = proj_gemm<FORM_F, EPI_F16_BIAS>(L.e_bf, L.wenc_bf, B * T, J, He, b_enc, L.enc16, 1, st))) return rc;
-    if ((rc = proj_gemm<FORM_F, EPI_F16_BIAS>(L.d_bf, L.wdec_bf, B * U1, J, Hd, b_dec, L.dec16, 1, st))) return rc;
+    const ProjProblem pe = {L.e_bf, L.wenc_bf, B * T, J, He, b_enc, L.enc16, 1};
+    const ProjProblem pd = {L.d_bf, L.wdec_bf, B * U1, J, Hd, b_dec, L.dec16, 1};
+    if ((rc = proj_gemm2<FORM_F, EPI_F16_BIAS>(pe, pd, st))) return rc;
     return joint_fwd_launch(L.w_out_bf, L.enc16, L.dec16, bias, labels, tlen, ulen, B, T, U1, J, Vp, blank, lp2, lse, 0, st);
 }
 
@@ -395,20 +420,20 @@ extern "C" int emo_rnnt_joint_full_bwd(const float* b_out, const int* labels, co
     rc = joint_bwd_ring_launch(F.w_out_bf, F.enc16, F.dec16, bias, labels, tlen, ulen, lse, lp2, gamma2, grad_cost,
                                grad_lse, B, T, U1, J, Vp, V, blank, 0, L.dh, L.ring, d_w_out, d_b_out, st);
     if (rc) return rc;
-    rc = joint_reduce_dh_launch_f16(L.dh, F.enc16, F.dec16, tlen, ulen, B, T, U1, J, L.d_enc, L.d_dec, st);
+    // axis reductions; the bf16 copy of d_enc_proj (operand of the projection backward) comes out of the same pass
+    rc = joint_reduce_dh_launch_f16(L.dh, F.enc16, F.dec16, tlen, ulen, B, T, U1, J, L.d_enc, L.d_dec, L.d_enc_bf, st);
     if (rc) return rc;
-    // gradients of the projected streams -> bf16 operands of the projection backward, bias gradients
-    const size_t ne = (size_t)B * T * J, nd = (size_t)B * U1 * J;
-    f32_to_bf16_plain_kernel<<<ceil_div(ne, 4 * 256), 256, 0, st>>>(L.d_enc, L.d_enc_bf, ne);
-    f32_to_bf16_plain_kernel<<<ceil_div(nd, 4 * 256), 256, 0, st>>>(L.d_dec, L.d_dec_bf, nd);
-    EMO_CHECK_LAUNCH("f32_to_bf16_plain_kernel");
-    colsum_kernel<<<dim3(ceil_div(J, 32), 64), dim3(32, 8), 0, st>>>(L.d_enc, B * T, J, d_b_enc);
-    colsum_kernel<<<dim3(ceil_div(J, 32), 32), dim3(32, 8), 0, st>>>(L.d_dec, B * U1, J, d_b_dec);
-    EMO_CHECK_LAUNCH("colsum_kernel");
+    // d_dec_proj was accumulated with atomics over the frame blocks: its bf16 copy needs a second pass, which also forms
+    // the bias gradients.  d_b_enc = sum_{b,t} d_enc_proj and d_b_dec = sum_{b,u} d_dec_proj are the SAME vector (both are
+    // the sum of dpre over all lattice cells), so one set of column sums of the smaller matrix serves both.
+    cast_colsum_kernel<<<dim3(ceil_div(J, 32), 32), dim3(32, 8), 0, st>>>(L.d_dec, B * U1, J, L.d_dec_bf, d_b_dec, d_b_enc);
+    EMO_CHECK_LAUNCH("cast_colsum_kernel");
     // d_x = d_proj W   (A K-major, B MN-major);  d_W = d_proj^T x   (both MN-major, split over the rows)
-    if ((rc = proj_gemm<FORM_G, EPI_F32>(L.d_enc_bf, F.wenc_bf, B * T, He, J, nullptr, d_eouts, 1, st))) return rc;
-    if ((rc = proj_gemm<FORM_G, EPI_F32>(L.d_dec_bf, F.wdec_bf, B * U1, Hd, J, nullptr, d_douts, 1, st))) return rc;
-    if ((rc = proj_gemm<FORM_H, EPI_F32_ADD>(L.d_enc_bf, F.e_bf, J, He, B * T, nullptr, d_w_enc, 32, st))) return rc;
-    if ((rc = proj_gemm<FORM_H, EPI_F32_ADD>(L.d_dec_bf, F.d_bf, J, Hd, B * U1, nullptr, d_w_dec, 16, st))) return rc;
+    const ProjProblem ge = {L.d_enc_bf, F.wenc_bf, B * T, He, J, nullptr, d_eouts, 1};
+    const ProjProblem gd = {L.d_dec_bf, F.wdec_bf, B * U1, Hd, J, nullptr, d_douts, 1};
+    if ((rc = proj_gemm2<FORM_G, EPI_F32>(ge, gd, st))) return rc;
+    const ProjProblem he = {L.d_enc_bf, F.e_bf, J, He, B * T, nullptr, d_w_enc, 32};
+    const ProjProblem hd = {L.d_dec_bf, F.d_bf, J, Hd, B * U1, nullptr, d_w_dec, 16};
+    if ((rc = proj_gemm2<FORM_H, EPI_F32_ADD>(he, hd, st))) return rc;
     return EMO_OK;
 }

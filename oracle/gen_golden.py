@@ -332,6 +332,11 @@ def main():
     rnnt_case("ref_rnnt_tcshape_ragged", 7, B=4, T=21, U=9, p=pt, tlens=[21, 18, 12, 5], ulens=[9, 6, 9, 1])
     rnnt_case("ref_rnnt_tcshape_auxctc", 8, B=3, T=17, U=6, p=pt, tlens=[17, 17, 10], ulens=[6, 2, 5],
               mtl_ctc_weight=0.3)
+    # shape the FOLDED op takes (projections inside the library: He, Hd multiples of 16), with the auxiliary CTC head
+    pf = _params(dec_num_layers=1, dec_hidden_size=32, embedding_size=16, joint_hidden_size=128,
+                 enc_hidden_size=32, vocab_size=70)
+    rnnt_case("ref_rnnt_tcfull_auxctc", 16, B=4, T=19, U=7, p=pf, tlens=[19, 19, 13, 6], ulens=[7, 4, 7, 2],
+              mtl_ctc_weight=0.3)
     # phone-CTC on the final layer, on the intermediate layer (hie_mtl_phone), and intermediate CTC
     ctc_mtl_case("ref_ctc_phone_final", 9, B=4, T=19, U=5, Up=9, V=23, Vp=43, He=16, tlens=[19, 15, 12, 9],
                  ulens=[5, 4, 2, 5], plens=[9, 7, 3, 8], phone_w=0.3, hie=False, inter_w=0.0)

@@ -144,7 +144,7 @@ RNNT_KEYS = ["dec_num_layers", "dec_hidden_size", "embedding_size", "joint_hidde
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-@pytest.mark.parametrize("name", ["ref_rnnt_tcshape_ragged", "ref_rnnt_tcshape_auxctc"])
+@pytest.mark.parametrize("name", ["ref_rnnt_tcshape_ragged", "ref_rnnt_tcshape_auxctc", "ref_rnnt_tcfull_auxctc"])
 def test_rnnt_decoder_tensor_core_shape_vs_reference_golden(name, precision):
     """Goldens of the UNMODIFIED reference at a shape the tensor-core kernels accept (J=128, V=64): the drop-in
     decoder must reproduce them at 1e-5 / 1e-4 in fp32 mode and at the stated bf16 tolerance in bf16 mode (the

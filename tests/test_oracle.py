@@ -8,7 +8,7 @@ from conftest import load_golden, pred_net_douts, rel_err
 from oracle import clattice, ctc_dp, rnnt_dp, torch_path
 
 RNNT_CASES = ["ref_rnnt_small_full", "ref_rnnt_small_ragged", "ref_rnnt_small_auxctc", "ref_rnnt_medium_ragged",
-              "ref_rnnt_tcshape_ragged", "ref_rnnt_tcshape_auxctc"]
+              "ref_rnnt_tcshape_ragged", "ref_rnnt_tcshape_auxctc", "ref_rnnt_tcfull_auxctc"]
 CTC_CASES = ["ref_ctc_small_full", "ref_ctc_small_ragged", "ref_ctc_medium_ragged", "ref_ctc_tchead_ragged"]
 
 
