@@ -4,14 +4,18 @@
 // The kernels read raw logits (B,T,V) once in the forward (row log-sum-exp) and once in the
 // backward (softmax - occupancy), never materialising the (T,B,V) log-prob tensor.
 //
-//   ctc_row_lse_kernel   HBM-bound: one warp-group per (b,t) row, float4 loads, online (max,sum).
-//   ctc_lattice_kernel<false>  alpha: one CTA per utterance, thread s owns extended state s; serial
-//                        over t, previous frame in double-buffered shared memory; gathered logits
-//                        are prefetched kPrefetch frames ahead in registers.
-//   ctc_lattice_kernel<true>   beta, same backwards; writes the state posterior occ_t(s) in place
-//                        of beta.
-//   ctc_grad_kernel      HBM-bound: per row, scatter the <= S posteriors into a shared-memory
-//                        vocabulary accumulator, then stream softmax - occ with float4 stores.
+//   ctc_row_lse_kernel   HBM-bound: one warp per (b,t) row streams the logits through registers (float4 loads, online
+//                        max / sum exp, the (row, slab) sequence of a warp is one software pipeline) and gathers the
+//                        2U+1 emission log-probs into the alpha / beta work arrays.
+//   ctc_lattice_kernel   grid (B, 2): alpha and beta side by side, one CTA per (utterance, direction), thread s owns
+//                        extended state s; serial over t, previous frame in double-buffered shared memory; emissions
+//                        prefetched one block of 8 frames ahead, results written 8 frames at a time.
+//   ctc_grad_warp_kernel HBM-bound (V % 4 == 0): one warp per row, grad = g softmax(z) streamed with float4 loads /
+//                        stores, then the <= 2U+1 entries that carry a posterior are patched with atomics on the lines
+//                        just written.  ctc_grad_kernel: the same per CTA with a shared-memory vocabulary accumulator,
+//                        for vocabularies that are not a multiple of 4.
+//   ctc_gather_kernel    emissions alone (backward called without a forward that staged beta).
+// The fused head (Linear + log_softmax + CTC without any (B,T,V) tensor) is ctc_head.cu.
 #include "common.cuh"
 
 namespace emo {

@@ -1,4 +1,4 @@
-"""Times forward and backward of the fused joint at a BASELINE shape (CUDA events, L2 flushed)."""
+"""Times forward and backward of the fused joint (enc_proj / dec_proj in) at a BASELINE shape (CUDA events, L2 flushed)."""
 import argparse
 import os
 import statistics
@@ -29,7 +29,7 @@ ul = torch.full((a.B,), a.U, device=dev)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 unit = 2.0 * a.B * a.T * (a.U + 1) * a.J * a.V
 res = {}
-for route in ("ring",):
+for route in ("joint",):
     f_ms, b_ms = [], []
     for it in range(a.iters + 3):
         for t in (enc, dec, w, b):
@@ -47,7 +47,7 @@ for route in ("ring",):
             b_ms.append(e1.elapsed_time(e2))
     fm, bm = statistics.median(f_ms), statistics.median(b_ms)
     res[route] = (float(loss), [t.grad.clone() for t in (enc, dec, w, b)])
-    print(f"route={route:7s} loss={float(loss):.6f} fwd {fm:.3f} ms  bwd {bm:.3f} ms  step {fm + bm:.3f} ms "
+    print(f"{route} loss={float(loss):.6f} fwd {fm:.3f} ms  bwd {bm:.3f} ms  step {fm + bm:.3f} ms "
           f"-> {a.B / (fm + bm) * 1e3:.0f} utt/s; algorithmic {3 * unit / (fm + bm) / 1e9:.0f} TFLOP/s")
 if len(res) == 2:
     (l0, g0), (l1, g1) = res.values()
