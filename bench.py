@@ -22,6 +22,7 @@ all-reduced over NCCL inside the timed step, launched from autograd hooks so tha
 One JSON line is printed by rank 0 (see the driver contract in the task statement).
 """
 import argparse
+import gc
 import json
 import os
 import statistics
@@ -134,9 +135,12 @@ def run_e2e(step, host, dev, steps, first=lambda out: out):
     every step's loss is copied back to pinned host memory and read by the host.  The read of step i's loss
     happens after step i+1 has been enqueued (one step late, as a logging loop does), so the device never waits
     for the host.  Returns wall-clock seconds for exactly `steps` steps, all losses read."""
-    copy_stream = torch.cuda.Stream(device=dev)
+    key = (dev.index, "copy")
+    if key not in _E2E_STATE:   # one copy stream / one pair of result buffers per process: the allocator's pool of
+        _E2E_STATE[key] = (torch.cuda.Stream(device=dev),                      # upload blocks is per stream
+                           [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)])
+    copy_stream, pinned = _E2E_STATE[key]
     main = torch.cuda.current_stream(dev)
-    pinned = [torch.empty((), dtype=torch.float32).pin_memory() for _ in range(2)]
 
     def upload():
         with torch.cuda.stream(copy_stream):
@@ -170,6 +174,26 @@ def run_e2e(step, host, dev, steps, first=lambda out: out):
     total += float(pending[0])
     torch.cuda.synchronize(dev)
     return time.perf_counter() - t0
+
+
+_E2E_STATE = {}
+
+
+def e2e_regions(step, host, dev, steps, barrier, reps=3):
+    """The end-to-end number: 2 untimed steps, then `reps` regions of exactly `steps` steps each; returns the MEDIAN
+    region's seconds and all of them.  Long-lived Python objects are moved out of the garbage collector's reach
+    first (gc.freeze, what a training loop does once its model is built): a full collection of a process with
+    torch loaded takes ~100 ms, more than a whole 20-step region, and one landing inside it was measured to
+    triple the per-step time (tools/diag_e2e.py)."""
+    run_e2e(step, host, dev, 2)
+    gc.collect()
+    gc.freeze()
+    secs = []
+    for _ in range(reps):
+        barrier()
+        secs.append(run_e2e(step, host, dev, steps))
+    barrier()
+    return statistics.median(secs), secs
 
 
 def timed_steps(step, resident, steps, flush, barrier):
@@ -258,15 +282,14 @@ def run_ours_rnnt(args, w, rank, world, dev):
     for _ in range(args.warmup):
         step(*resident)
     barrier()
+    gc.collect()
+    gc.freeze()     # see e2e_regions: no full collection of torch's long-lived objects inside a timed region
     mon = ClockMonitor(dev.index if dev.index is not None else 0, enabled=rank == 0)
     mon.start()
     ms_total = timed_steps(step, resident, args.steps, flush, barrier)
     clocks = mon.stop()
     # ---- end-to-end: host (pinned) buffers in, loss value out, wall clock
-    run_e2e(step, host, dev, 2)
-    barrier()
-    e2e_s = run_e2e(step, host, dev, args.steps)
-    barrier()
+    e2e_s, e2e_all = e2e_regions(step, host, dev, args.steps, barrier)
 
     prec = 1 if args.precision == "bf16" else 0
     B, T, U1, J, V = w["B"], w["T"], w["U"] + 1, w["J"], w["V"]
@@ -275,7 +298,7 @@ def run_ours_rnnt(args, w, rank, world, dev):
     per_step = (_lib.launch_count(_lib.OP_RNNT_JOINT_FULL, prec, B, T, U1, J, V) if folded else
                 _lib.launch_count(_lib.OP_RNNT_JOINT_FWD, prec, B, T, U1, J, V)
                 + _lib.launch_count(_lib.OP_RNNT_JOINT_BWD, prec, B, T, U1, J, V))
-    out = dict(ms_total=ms_total, e2e_s=e2e_s, units=w["B"], clocks=clocks, roofline=None, launches=per_step * args.steps,
+    out = dict(ms_total=ms_total, e2e_s=e2e_s, e2e_all=e2e_all, units=w["B"], clocks=clocks, roofline=None, launches=per_step * args.steps,
                h2d=sum(t.numel() * t.element_size() for t in host), d2h=4, flops=wl.algorithmic_flops(),
                n_valid=wl.n_valid, extra={})
     if world > 1:
@@ -407,6 +430,8 @@ def run_ours_ctc(args, w, rank, world, dev):
     for _ in range(args.warmup):
         step(*resident)
     torch.cuda.synchronize()
+    gc.collect()
+    gc.freeze()
     mon = ClockMonitor(dev.index if dev.index is not None else 0, enabled=rank == 0)
     mon.start()
 
@@ -416,8 +441,7 @@ def run_ours_ctc(args, w, rank, world, dev):
             dist.barrier()
     ms_total = timed_steps(step, resident, args.steps, flush, barrier)
     clocks = mon.stop()
-    run_e2e(step, host, dev, 2)
-    e2e_s = run_e2e(step, host, dev, args.steps)
+    e2e_s, e2e_all = e2e_regions(step, host, dev, args.steps, barrier)
     peaks = load_peaks()
     # SURVEY 8d's per-step figure for the CTC path is the logits traffic of the unfused sequence, 3*B*T*V*4 bytes
     # (read twice, gradient written once).  The fused head moves none of it: what bounds it is the tensor pipe on
@@ -457,7 +481,7 @@ def run_ours_ctc(args, w, rank, world, dev):
         n = max(5, args.steps // 2)
         roof["unfused_ms_per_step"] = round(timed_steps(ustep, resident, n, flush, torch.cuda.synchronize) / n, 4)
     torch.backends.cuda.matmul.allow_tf32 = tf32
-    return dict(ms_total=ms_total, e2e_s=e2e_s, units=B, clocks=clocks, roofline=roof,
+    return dict(ms_total=ms_total, e2e_s=e2e_s, e2e_all=e2e_all, units=B, clocks=clocks, roofline=roof,
                 launches=(_lib.launch_count(_lib.OP_CTC_HEAD, 1, B, T, 1, He, V) if fused
                           else _lib.launch_count(_lib.OP_CTC, 0, B, T, 1, 1, V)) * args.steps,
                 h2d=sum(t.numel() * t.element_size() for t in host), d2h=4, flops=None, n_valid=None, extra={})
@@ -676,7 +700,7 @@ def cpu_reference_rate(w, sample_units, steps, warmup, threads=None):
             loss = torch_path.rnnt_joint_loss(eouts, douts, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias,
                                               lin[2].weight, lin[2].bias, ys, tl, ul, blank=0)
             loss.backward()
-            return float(loss)
+            return float(loss.detach())
     else:
         eouts = torch.randn(Bc, w["T"], w["He"], generator=gen, requires_grad=True)
         ys = make_labels(Bc, w["U"], w["V"], gen)
@@ -689,7 +713,7 @@ def cpu_reference_rate(w, sample_units, steps, warmup, threads=None):
             head.zero_grad(set_to_none=True)
             loss = torch_path.ctc_head_loss(eouts, head.weight, head.bias, ys, tl, ul, blank=0)
             loss.backward()
-            return float(loss)
+            return float(loss.detach())
     for _ in range(warmup):
         step()
     t0 = time.perf_counter()
@@ -750,7 +774,8 @@ def main():
               if world > 1 else "single GPU",
               "l2": "L2 flushed (256 MiB write, untimed) between timed steps",
               "e2e": "per step: H2D of the step's inputs from pinned host memory on a copy stream (prefetched "
-                     "during the previous step) + D2H of the loss, read by the host one step late; wall clock"}
+                     "during the previous step) + D2H of the loss, read by the host one step late; wall clock; median of 3 "
+                     "regions of `steps` steps each (all three under e2e.regions_utt_s_rank0), Python gc frozen first"}
     if w["kind"] == "rnnt":
         config["route"] = "logit tiles recomputed by the backward; dz through an L2-resident ring; no N x V tensor in HBM"
         config["projections"] = ("w_enc/w_dec (+ their backward) inside the library: tcgen05 GEMMs, bf16 operands"
@@ -805,7 +830,8 @@ def main():
                "dtype": args.precision if w["kind"] == "rnnt" else ("bf16" if (r["roofline"] or {}).get("head") == "fused" else "f32"),
                "data": "synthetic", "config": config, "clocks": r["clocks"],
                "e2e": {"value": round(units / e2e_s, 2), "unit": "utt/s", "h2d_bytes_per_step": r["h2d"],
-                       "d2h_bytes_per_step": r["d2h"]},
+                       "d2h_bytes_per_step": r["d2h"],
+                       "regions_utt_s_rank0": [round(units / x, 1) for x in r["e2e_all"]]},
                "gpu_launches": r["launches"], "roofline": r["roofline"]}
         if r["flops"]:
             peaks = load_peaks()
@@ -825,7 +851,8 @@ def main():
                                      "value": round(cu / (c["ms_total"] * 1e-3), 1), "unit": "utt/s",
                                      "ms_per_step": round(c["ms_total"] / cargs.steps, 4),
                                      "e2e": {"value": round(cu / c["e2e_s"], 1), "unit": "utt/s",
-                                             "h2d_bytes_per_step": c["h2d"], "d2h_bytes_per_step": c["d2h"]},
+                                             "h2d_bytes_per_step": c["h2d"], "d2h_bytes_per_step": c["d2h"],
+                                             "regions_utt_s_rank0": [round(cu / x, 1) for x in c["e2e_all"]]},
                                      "roofline": c["roofline"], "dtype": "bf16" if c["roofline"].get("head") == "fused" else "f32"}
                 torch.cuda.empty_cache()
             out["gpu_baseline"] = gpu_baselines(dev)
