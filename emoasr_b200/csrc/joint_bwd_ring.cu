@@ -90,9 +90,24 @@ __device__ __forceinline__ void red_release_gpu(int* p) {
 __device__ __forceinline__ void fence_proxy_async_all() {
     asm volatile("fence.proxy.async;" ::: "memory");
 }
-// consumer / producer side of a ring flag: wait, then order the async-proxy accesses (TMA) that follow
+__device__ __forceinline__ int ld_relaxed_gpu(const int* p) {
+    int v;
+    asm volatile("ld.relaxed.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// consumer / producer side of a ring flag: wait, then order the async-proxy accesses (TMA) that follow.  The poll
+// itself is a relaxed load: an acquire load per iteration invalidates the SM's L1 every time (CCTL.IVALL, 8.4 M of
+// them per launch in the first version -- the epilogue's register spills and the producers' gathers then miss L1);
+// one acquire load of the value that passed does the synchronisation.
+__device__ __forceinline__ bool ring_try(const int* p, int need) {
+    if (ld_relaxed_gpu(p) < need) return false;
+    (void)ld_acquire_gpu(p);
+    fence_proxy_async_all();
+    return true;
+}
 __device__ __forceinline__ void ring_wait(const int* p, int need) {
-    while (ld_acquire_gpu(p) < need) __nanosleep(32);
+    while (ld_relaxed_gpu(p) < need) __nanosleep(32);
+    (void)ld_acquire_gpu(p);
     fence_proxy_async_all();
 }
 // after this lane's TMA stores have COMPLETED: publish
@@ -184,6 +199,8 @@ struct __align__(16) PBars {
     uint64_t a_full[kMaxKBlocks], a_empty[kMaxKBlocks];
     uint64_t h_ready[kMaxKBlocks];   // local: this CTA's producer warps have written block kb
     uint64_t acc_full[2], acc_empty[2];
+    uint64_t slot_free[2];           // local: the ring manager (warp 2) has seen the item's z slot released
+    uint64_t stored[2];              // local: every epilogue warp's TMA stores of the item have completed
     uint32_t tmem_base;
     uint32_t pad[3];
 };
@@ -345,6 +362,8 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
         for (int i = 0; i < 2; ++i) {
             mbar_init(smem_u32(&bars->acc_full[i]), 1);
             mbar_init(smem_u32(&bars->acc_empty[i]), 2 * (kPEpiThreads / 32));
+            mbar_init(smem_u32(&bars->slot_free[i]), 1);
+            mbar_init(smem_u32(&bars->stored[i]), kPEpiThreads / 32);
         }
         fence_barrier_init();
     }
@@ -437,6 +456,32 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
                              printf("ring P issuer: total %lld clk, %u tiles; wait acc_empty %lld a_full %lld b_full %lld\n",
                                     clock64() - p_t0, tl, p_acc, p_a, p_b);)
             }
+        } else if (warp == 2) {
+            // ===================== ring manager: slot gate + publication of this CTA's dz items =====================
+            // The global-scope release (fence + red.release.gpu, ~800 clk) and the polling of the slot gate used to
+            // sit in lane 0 of every epilogue warp: 14 % of the epilogue's time (ncu stall_membar + the poll), on the
+            // role's critical path.  Here: the epilogue warps only wait for their own TMA stores and arrive on
+            // `stored`; this lane publishes the item (one arrival per CTA) and opens `slot_free` for the next one.
+            // Both are tried in turn without blocking (the gate of item k may depend on other pairs' publications,
+            // the publication of item k-1 must never wait for it); at most one item is gated ahead.
+            if (lane == 0) {
+                const int n_it = pidx < NI ? (NI - pidx + a.nP - 1) / a.nP : 0;
+                int kg = 0, kp = 0;
+                while (kp < n_it) {
+                    if (kg < n_it && kg <= kp + 1) {
+                        const int item = pidx + kg * a.nP, zs = item % a.NZ;
+                        if (ring_try(z_done + zs, (item / a.NZ) * (1 + roles_in_group(zs % a.G, a.V)))) {
+                            mbar_arrive(smem_u32(&bars->slot_free[kg & 1]));
+                            ++kg;
+                        }
+                    }
+                    if (kp < kg && mbar_try_wait(smem_u32(&bars->stored[kp & 1]), (kp >> 1) & 1)) {
+                        fence_proxy_async_all();
+                        red_release_gpu(z_ready + (pidx + kp * a.nP) % a.NZ);
+                        ++kp;
+                    }
+                }
+            }
         } else if (warp == 3) {
             // ===================== h writer: every finished h block -> ring =====================
             if (lane == 0) {
@@ -474,9 +519,9 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
         const int etid = threadIdx.x - 128;   // 0..255
         uint8_t* zbuf0 = sZst + (warp - 4) * kZStBufs * kZStBytes;   // alternating blocks (g & 1)
         const uint32_t acc_empty0 = mapa_shared(smem_u32(&bars->acc_empty[0]), 0);
-        uint32_t cc = 0;
+        uint32_t cc = 0, kit = 0;              // kit: index of the item in this pair's sequence
         const int pblank = a.plain ? -1 : a.blank;   // plain: no blank patch
-        int pending = -1;                      // z slot whose stores have been issued but not yet published
+        int pending = -1;                      // z slot whose stores have been issued but not yet handed to the manager
         EMO_PROF(long long p_sig = 0, p_gate = 0, p_accw = 0, p_t0 = clock64(), p_rd = 0, p_st = 0, p_bar = 0, p_ldw = 0;)
         float nb;                              // bias * log2e of the chunk about to be processed (see dz_group)
         PTile ti;
@@ -517,16 +562,20 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
                 const int item = it;               // == q * G + nc / kCPG
                 const int zs = item % a.NZ;
                 if (nc == nc0) {
-                    // first chunk of a ring item: publish the previous item (its stores were issued a chunk
-                    // ago), then make sure every consumer has released this slot's previous content
+                    // first chunk of a ring item: hand the previous item to the ring manager (its stores were issued
+                    // a chunk ago), then wait until the manager has seen this slot's previous content released
                     if (lane == 0) {
                         EMO_PROF(const long long p_c = clock64();)
-                        if (pending >= 0) ring_signal_stored(z_ready + pending);
+                        if (pending >= 0) {
+                            tma_store_wait_all<0>();
+                            mbar_arrive(smem_u32(&bars->stored[(kit - 1) & 1]));
+                        }
                         EMO_PROF(p_sig += clock64() - p_c;)
-                        ring_wait(z_done + zs, (item / a.NZ) * (1 + roles_in_group(zs % a.G, a.V)));
+                        mbar_wait(smem_u32(&bars->slot_free[kit & 1]), (kit >> 1) & 1);
                         EMO_PROF(p_gate += clock64() - p_c;)
                     }
                     pending = zs;
+                    ++kit;
                     __syncwarp();
                 }
                 const uint32_t taddr = tmem_base + ((uint32_t)(qd * 32) << 16) + buf * kChunkN;
@@ -558,8 +607,8 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
             }
         }
         if (lane == 0) {
-            if (pending >= 0) ring_signal_stored(z_ready + pending);
-            else tma_store_wait_all<0>();
+            tma_store_wait_all<0>();
+            if (pending >= 0) mbar_arrive(smem_u32(&bars->stored[(kit - 1) & 1]));
         }
         EMO_PROF(if (pidx == 0 && warp == 4 && lane == 0)
                      printf("ring P epilogue warp 4: total %lld clk; wait acc_full %lld, publish %lld, publish + slot gate %lld, "
@@ -722,7 +771,7 @@ __device__ __forceinline__ void role_dh(const RingArgs& a, const CUtensorMap* tm
                     const int item = q * a.G + kb / (kVG / kBlockK);
                     const int rs = item % a.NZ;
                     EMO_PROF(p_c = clock64();)
-                    if (kb % (kVG / kBlockK) == 0) ring_wait(z_ready + rs, (item / a.NZ + 1) * 2 * (kPEpiThreads / 32));
+                    if (kb % (kVG / kBlockK) == 0) ring_wait(z_ready + rs, (item / a.NZ + 1) * 2);
                     EMO_PROF(p_ring += clock64() - p_c;)
                     mbar_wait(smem_u32(&bars->dz_empty[zs]), zph ^ 1);
                     const uint32_t full = smem_u32(&bars->dz_full[zs]);
@@ -946,7 +995,7 @@ __device__ __forceinline__ void role_dw(const RingArgs& a, const CUtensorMap* tm
                 const int item = q * a.G + gr;
                 const int rs = item % a.NZ;
                 EMO_PROF(p_c = clock64();)
-                ring_wait(z_ready + rs, (item / a.NZ + 1) * 2 * (kPEpiThreads / 32));
+                ring_wait(z_ready + rs, (item / a.NZ + 1) * 2);
                 EMO_PROF(p_ring += clock64() - p_c;)
                 for (int kh = 0; kh < 4; ++kh) {
                     mbar_wait(smem_u32(&bars->dz_empty[zs]), zph ^ 1);
