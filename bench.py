@@ -207,7 +207,23 @@ def timed_steps(step, resident, steps, flush, barrier):
         b.record()
         evs.append((a, b))
     barrier()
-    return sum(a.elapsed_time(b) for a, b in evs)
+    ms = [a.elapsed_time(b) for a, b in evs]
+    LAST_STEP_MS[:] = ms
+    if os.environ.get("EMO_BENCH_TRACE"):
+        sys.stderr.write("rank %s step ms: %s\n" % (os.environ.get("RANK", "0"), " ".join("%.3f" % x for x in ms)))
+    return sum(ms)
+
+
+LAST_STEP_MS = []   # per-step device times of the most recent timed_steps() call (this rank)
+
+
+def step_spread(ms):
+    """first / median / last-quarter mean of the per-step device times: the GPU leaves its burst clocks after
+    ~0.1 s of sustained tensor load (power cap), so late steps of a long region run several per cent slower."""
+    q = max(1, len(ms) // 4)
+    return {"first": round(ms[0], 4), "median": round(statistics.median(ms), 4), "min": round(min(ms), 4),
+            "max": round(max(ms), 4), "first_quarter_mean": round(statistics.mean(ms[:q]), 4),
+            "last_quarter_mean": round(statistics.mean(ms[-q:]), 4)}
 
 
 def time_call(fn, flush, iters):
@@ -281,13 +297,19 @@ def run_ours_rnnt(args, w, rank, world, dev):
 
     for _ in range(args.warmup):
         step(*resident)
-    barrier()
     gc.collect()
     gc.freeze()     # see e2e_regions: no full collection of torch's long-lived objects inside a timed region
+    # Everything rank-specific happens BEFORE the barrier that opens the timed region.  Rank 0 alone starts the clock
+    # sampler (NVML initialisation: ~10 ms on the host); started after the barrier, that delay sat inside every other
+    # rank's first timed step (they wait for rank 0 in the first collective: 13.5 ms instead of 3.3 -- measured with
+    # EMO_BENCH_TRACE=1), i.e. +0.5 ms per step on a 20-step region, the larger part of the "scaling loss" of
+    # earlier rounds.
     mon = ClockMonitor(dev.index if dev.index is not None else 0, enabled=rank == 0)
     mon.start()
+    barrier()
     ms_total = timed_steps(step, resident, args.steps, flush, barrier)
     clocks = mon.stop()
+    spread = step_spread(LAST_STEP_MS)
     # ---- end-to-end: host (pinned) buffers in, loss value out, wall clock
     e2e_s, e2e_all = e2e_regions(step, host, dev, args.steps, barrier)
 
@@ -300,7 +322,7 @@ def run_ours_rnnt(args, w, rank, world, dev):
                 + _lib.launch_count(_lib.OP_RNNT_JOINT_BWD, prec, B, T, U1, J, V))
     out = dict(ms_total=ms_total, e2e_s=e2e_s, e2e_all=e2e_all, units=w["B"], clocks=clocks, roofline=None, launches=per_step * args.steps,
                h2d=sum(t.numel() * t.element_size() for t in host), d2h=4, flops=wl.algorithmic_flops(),
-               n_valid=wl.n_valid, extra={})
+               n_valid=wl.n_valid, extra={"step_ms_rank0": spread})
     if world > 1:
         # diagnosis of the scaling loss: every rank's step WITHOUT the collective (same kernels, same inputs).  The
         # synchronised step can never be faster than the slowest GPU's local step.
@@ -439,6 +461,7 @@ def run_ours_ctc(args, w, rank, world, dev):
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
+    barrier()
     ms_total = timed_steps(step, resident, args.steps, flush, barrier)
     clocks = mon.stop()
     e2e_s, e2e_all = e2e_regions(step, host, dev, args.steps, barrier)

@@ -7,6 +7,8 @@ ctc_head_loss    output Linear + log_softmax + CTC loss fused, logits never form
 """
 import ctypes
 
+import math
+
 import torch
 from torch.autograd.function import once_differentiable
 
@@ -323,12 +325,25 @@ class _RNNTJointFull(torch.autograd.Function):
                              device=dev)
             mk = lambda *s: torch.empty(*s, device=dev)
             d_e, d_d = mk(B, T, He), mk(B, U1, Hd)
-            d_we, d_be, d_wd, d_bd, d_wo, d_bo = mk(J, He), mk(J), mk(J, Hd), mk(J), mk(V, J), mk(V)
+            # the six parameter gradients are views of ONE flat buffer (16-byte aligned pieces): a data-parallel
+            # reducer that sees them share a base all-reduces that buffer once (sharding.GradReducer)
+            d_wo, d_bo, d_wd, d_bd, d_we, d_be = flat_views(dev, (V, J), (V,), (J, Hd), (J,), (J, He), (J,))
             _lib.check(lib.emo_rnnt_joint_full_bwd(_p(bo), _p(labels), _p(tlen), _p(ulen), _p(lse), _p(lp2), _p(gamma2),
                                                    _p(g), _p(None), _p(fws), B, T, U1, He, Hd, J, V, blank,
                                                    _p(d_e), _p(d_d), _p(d_we), _p(d_be), _p(d_wd), _p(d_bd), _p(d_wo),
                                                    _p(d_bo), _p(ws), ws.numel(), _stream()), "emo_rnnt_joint_full_bwd")
         return d_e, d_d, d_we, d_be, d_wd, d_bd, d_wo, d_bo, None, None, None, None
+
+
+def flat_views(dev, *shapes):
+    """fp32 tensors of the given shapes carved out of one flat allocation, every piece 16-byte aligned."""
+    sizes = [(math.prod(sh) + 3) // 4 * 4 for sh in shapes]
+    flat = torch.empty(sum(sizes), device=dev)
+    out, off = [], 0
+    for sh, n in zip(shapes, sizes):
+        out.append(flat[off:off + math.prod(sh)].view(*sh))
+        off += n
+    return out
 
 
 def rnnt_joint_loss_from_outputs(eouts, douts, w_enc, b_enc, w_dec, b_dec, w_out, b_out, labels, frames_lengths,

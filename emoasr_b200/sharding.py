@@ -155,7 +155,9 @@ class GradReducer:
     ``optimizer.zero_grad()`` does), so there is no zero-fill, no accumulate kernel and no flatten / unflatten copy
     around the collective.  Measured on B200 at cfg 3: the bucket variant (gradients accumulated into flat buffers)
     costs 0.10 ms of device time per step in a single process and 0.25-0.4 ms per rank under torchrun; this one
-    costs none.  Tiny tensors (biases) ride in one small flat buffer to save launches."""
+    costs none.  Tiny tensors (biases) ride in one small flat buffer to save launches.  Gradients that their producer
+    wrote side by side into one flat buffer (the folded joint's six parameter gradients, ``functional.flat_views``) are
+    reduced with a single collective on that buffer."""
 
     def __init__(self, params, group=None, small_numel=8192):
         self.params = [p for p in params if p.requires_grad]
@@ -164,6 +166,7 @@ class GradReducer:
         self._pending = []
         self._small_ready = 0
         self._small_flat = None
+        self._groups = {}       # flat gradient buffers whose pieces are still arriving: storage data_ptr -> [numel seen, grads]
         self.enabled = True
         for p in self.params:
             p.register_post_accumulate_grad_hook(self._hook)
@@ -178,6 +181,19 @@ class GradReducer:
 
     def _hook(self, p):
         if not self.enabled:
+            return
+        g = p.grad
+        st = g.untyped_storage()
+        n_al = (g.numel() + 3) // 4 * 4
+        if g.element_size() == 4 and g.is_contiguous() and st.nbytes() > 4 * n_al:
+            # the producer of this gradient wrote it into a flat buffer next to others (functional.flat_views: 16-byte
+            # aligned pieces of one allocation): once every piece has arrived, ONE collective on the buffer itself
+            grp = self._groups.setdefault(st.data_ptr(), [0, []])
+            grp[0] += n_al
+            grp[1].append(g)
+            if 4 * grp[0] >= st.nbytes():
+                del self._groups[st.data_ptr()]
+                self._launch(torch.empty(0, dtype=g.dtype, device=g.device).set_(st))
             return
         if p.numel() > 0 and not any(p is q for q in self.small):
             self._launch(p.grad)
@@ -194,6 +210,10 @@ class GradReducer:
 
     def finish(self):
         world = dist.get_world_size(self.group)
+        for _, grads in self._groups.values():   # flat buffers that never filled up (a frozen parameter): piecewise
+            for g in grads:
+                self._launch(g)
+        self._groups = {}
         for t, work, averaged in self._pending:
             work.wait()
             if not averaged:

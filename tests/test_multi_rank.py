@@ -123,3 +123,62 @@ def test_two_rank_sharded_step_matches_single_process(tmp_path, own_grads, hooks
     assert abs(float(got["loss"]) - float(loss)) < 1e-5 * abs(float(loss))
     for p, g in zip(lin.parameters(), got["grads"]):
         assert np.allclose(g.numpy(), p.grad.numpy(), rtol=1e-4, atol=1e-6)
+
+
+class _FlatLinear(torch.autograd.Function):
+    """y = x W^T + b whose backward writes d_W and d_b side by side into one flat buffer, the way the folded joint's
+    backward does on the GPU (functional.flat_views)."""
+
+    @staticmethod
+    def forward(ctx, x, w, b):
+        ctx.save_for_backward(x, w)
+        return x @ w.t() + b
+
+    @staticmethod
+    def backward(ctx, gy):
+        from emoasr_b200.functional import flat_views
+        x, w = ctx.saved_tensors
+        d_w, d_b = flat_views(x.device, tuple(w.shape), (w.size(0),))
+        d_w.copy_(gy.t() @ x)
+        d_b.copy_(gy.sum(0))
+        return gy @ w, d_w, d_b
+
+
+def _flat_worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.manual_seed(3)
+    w = torch.randn(5, 7, requires_grad=True)      # 35 elements: the bias piece starts at the padded offset 36
+    b = torch.randn(5, requires_grad=True)
+    other = torch.randn(3, requires_grad=True)     # a gradient that is NOT part of a flat buffer
+    x = torch.randn(4, 7, generator=torch.Generator().manual_seed(10 + rank))
+    red = sharding.GradReducer([w, b, other], small_numel=0)
+    for step in range(2):
+        for p in (w, b, other):
+            p.grad = None
+        ((_FlatLinear.apply(x, w, b) ** 2).sum() + (other * (rank + 1.0)).sum()).backward()
+        assert w.grad.untyped_storage().data_ptr() == b.grad.untyped_storage().data_ptr()
+        assert len(red._pending) == 2              # one collective for the flat buffer, one for `other`
+        red.finish()
+    if rank == 0:
+        torch.save({"w": w.grad.clone(), "b": b.grad.clone(), "other": other.grad.clone()}, out)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_reducer_allreduces_a_flat_gradient_buffer_once(tmp_path):
+    out = str(tmp_path / "rank0.pt")
+    mp.spawn(_flat_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    got = torch.load(out)
+    torch.manual_seed(3)
+    w = torch.randn(5, 7, requires_grad=True)
+    b = torch.randn(5, requires_grad=True)
+    gw, gb = torch.zeros_like(w), torch.zeros_like(b)
+    for rank in range(2):
+        x = torch.randn(4, 7, generator=torch.Generator().manual_seed(10 + rank))
+        y = x @ w.t() + b
+        a, c = torch.autograd.grad((y ** 2).sum(), (w, b))
+        gw += a / 2
+        gb += c / 2
+    assert torch.allclose(got["w"], gw, rtol=1e-5, atol=1e-6) and torch.allclose(got["b"], gb, rtol=1e-5, atol=1e-6)
+    assert torch.allclose(got["other"], torch.full((3,), 1.5))
