@@ -468,18 +468,22 @@ __device__ __forceinline__ void role_produce(const RingArgs& a, const CUtensorMa
                 const int n_it = pidx < NI ? (NI - pidx + a.nP - 1) / a.nP : 0;
                 int kg = 0, kp = 0;
                 while (kp < n_it) {
+                    bool moved = false;
                     if (kg < n_it && kg <= kp + 1) {
                         const int item = pidx + kg * a.nP, zs = item % a.NZ;
                         if (ring_try(z_done + zs, (item / a.NZ) * (1 + roles_in_group(zs % a.G, a.V)))) {
                             mbar_arrive(smem_u32(&bars->slot_free[kg & 1]));
                             ++kg;
+                            moved = true;
                         }
                     }
                     if (kp < kg && mbar_try_wait(smem_u32(&bars->stored[kp & 1]), (kp >> 1) & 1)) {
                         fence_proxy_async_all();
                         red_release_gpu(z_ready + (pidx + kp * a.nP) % a.NZ);
                         ++kp;
+                        moved = true;
                     }
+                    if (!moved) __nanosleep(32);
                 }
             }
         } else if (warp == 3) {

@@ -71,42 +71,57 @@ reduce_dh_tanh_kernel(const __nv_bfloat16* __restrict__ dh, const TIn* __restric
         e2[k][0] = e2[k][1] = 0u;
         if (k < nt) load4_f16x2<TIn>(enc_proj + ((size_t)b * T + t0 + k) * J + j0 + lane * 4, e2[k][0], e2[k][1]);
     }
-    const TIn* decb = dec_proj + (size_t)b * U1 * J + j0 + lane * 4;
+    // Every address of the u loop is a pointer that advances by a constant: the first version recomputed the 64-bit
+    // row offsets of all five loads and of the red in every iteration (ncu source page: ~200 of the loop's 320
+    // instructions were integer address arithmetic; the kernel was issue-bound at 3.7 TB/s).  Loads are unconditional
+    // (clamped to rows that exist), frames past T_b are masked with a select.
     float e[kRedTG][4];
 #pragma unroll
     for (int k = 0; k < kRedTG; ++k) e[k][0] = e[k][1] = e[k][2] = e[k][3] = 0.f;
-    auto load_u = [&](int u, uint2 (&dv)[kRedTG], uint2& dc) {
-        const bool uok = u < U1b;
-        dc = make_uint2(0u, 0u);
-        if (uok) load4_f16x2<TIn>(decb + (size_t)u * J, dc.x, dc.y);
+    if (nt > 0) {
+        const int w0 = min(warp, U1b - 1);
+        const uint2* dp[kRedTG];
 #pragma unroll
-        for (int k = 0; k < kRedTG; ++k)
-            dv[k] = (k < nt && uok) ? __ldg(dbase + ((size_t)k * U1b + u) * rs) : make_uint2(0u, 0u);
-    };
-    uint2 cd[kRedTG], nd[kRedTG];
-    uint2 cdec, ndec;
-    load_u(warp, cd, cdec);
-    for (int u = warp; u < U1b; u += kRedWarps) {
-        load_u(u + kRedWarps, nd, ndec);
-        const uint32_t d2a = cdec.x, d2b = cdec.y;
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+        for (int k = 0; k < kRedTG; ++k) dp[k] = dbase + ((size_t)(k < nt ? k : 0) * U1b + w0) * rs;
+        const TIn* decp = dec_proj + ((size_t)b * U1 + w0) * J + j0 + lane * 4;
+        float* ddp = d_dec + ((size_t)b * U1 + w0) * J + j0 + lane * 4;
+        const size_t ustep = (size_t)kRedWarps * rs, jstep = (size_t)kRedWarps * J;
+        uint2 cd[kRedTG], nd[kRedTG];
+        uint2 cdec, ndec;
+        load4_f16x2<TIn>(decp, cdec.x, cdec.y);
 #pragma unroll
-        for (int k = 0; k < kRedTG; ++k) {
-            // 1 - h^2 in packed half precision (h = tanh.approx.f16x2 of the forward's own sum; the factor is in
-            // [0,1], 11 mantissa bits), then two FMAs per element: 5.5 instructions per element instead of 9 -- the
-            // kernel is issue-bound, not HBM-bound (ncu: 195 M warp instructions for 413 M elements before this)
-            const float2 ga = unpack_f16x2(one_minus_sq_f16x2(tanh_f16x2(hadd2_u32(e2[k][0], d2a))));
-            const float2 gb = unpack_f16x2(one_minus_sq_f16x2(tanh_f16x2(hadd2_u32(e2[k][1], d2b))));
-            const float q0 = __uint_as_float(cd[k].x << 16), q1 = __uint_as_float(cd[k].x & 0xffff0000u);
-            const float q2 = __uint_as_float(cd[k].y << 16), q3 = __uint_as_float(cd[k].y & 0xffff0000u);
-            a0 = fmaf(q0, ga.x, a0); a1 = fmaf(q1, ga.y, a1); a2 = fmaf(q2, gb.x, a2); a3 = fmaf(q3, gb.y, a3);
-            e[k][0] = fmaf(q0, ga.x, e[k][0]); e[k][1] = fmaf(q1, ga.y, e[k][1]);
-            e[k][2] = fmaf(q2, gb.x, e[k][2]); e[k][3] = fmaf(q3, gb.y, e[k][3]);
+        for (int k = 0; k < kRedTG; ++k) cd[k] = __ldg(dp[k]);
+        for (int u = warp; u < U1b; u += kRedWarps) {
+            const bool more = u + kRedWarps < U1b;      // warp-uniform
+            if (more) {
+                decp += jstep;
+#pragma unroll
+                for (int k = 0; k < kRedTG; ++k) dp[k] += ustep;
+            }
+            load4_f16x2<TIn>(decp, ndec.x, ndec.y);     // the row after the last one is never used: reload the last
+#pragma unroll
+            for (int k = 0; k < kRedTG; ++k) nd[k] = __ldg(dp[k]);
+            const uint32_t d2a = cdec.x, d2b = cdec.y;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll
+            for (int k = 0; k < kRedTG; ++k) {
+                // 1 - h^2 in packed half precision (h = tanh.approx.f16x2 of the forward's own sum; the factor is in
+                // [0,1], 11 mantissa bits), then two FMAs per element
+                const float2 ga = unpack_f16x2(one_minus_sq_f16x2(tanh_f16x2(hadd2_u32(e2[k][0], d2a))));
+                const float2 gb = unpack_f16x2(one_minus_sq_f16x2(tanh_f16x2(hadd2_u32(e2[k][1], d2b))));
+                const uint32_t x = k < nt ? cd[k].x : 0u, y = k < nt ? cd[k].y : 0u;
+                const float q0 = __uint_as_float(x << 16), q1 = __uint_as_float(x & 0xffff0000u);
+                const float q2 = __uint_as_float(y << 16), q3 = __uint_as_float(y & 0xffff0000u);
+                a0 = fmaf(q0, ga.x, a0); a1 = fmaf(q1, ga.y, a1); a2 = fmaf(q2, gb.x, a2); a3 = fmaf(q3, gb.y, a3);
+                e[k][0] = fmaf(q0, ga.x, e[k][0]); e[k][1] = fmaf(q1, ga.y, e[k][1]);
+                e[k][2] = fmaf(q2, gb.x, e[k][2]); e[k][3] = fmaf(q3, gb.y, e[k][3]);
+            }
+            red_add_v4(ddp, a0, a1, a2, a3);
+            ddp += jstep;
+#pragma unroll
+            for (int k = 0; k < kRedTG; ++k) cd[k] = nd[k];
+            cdec = ndec;
         }
-        if (nt > 0) red_add_v4(d_dec + ((size_t)b * U1 + u) * J + j0 + lane * 4, a0, a1, a2, a3);
-#pragma unroll
-        for (int k = 0; k < kRedTG; ++k) cd[k] = nd[k];
-        cdec = ndec;
     }
 #pragma unroll
     for (int k = 0; k < kRedTG; ++k) s_enc[warp][k][lane] = make_float4(e[k][0], e[k][1], e[k][2], e[k][3]);
