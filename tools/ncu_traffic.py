@@ -31,7 +31,8 @@ for r in rows[2:]:
         to_bytes(r[c["dram__bytes_write.sum"]], unit["dram__bytes_write.sum"])
     per.setdefault(short, []).append(b)
 kern = {k: sum(v) / len(v) for k, v in per.items()}
-fwd_names = ("joint_fwd_kernel", "rnnt_alpha_beta_kernel", "rnnt_gamma_kernel", "ctc_row", "ctc_lattice")
+fwd_names = ("joint_fwd_kernel", "rnnt_alpha_beta_kernel", "rnnt_gamma_kernel", "ctc_row", "ctc_lattice",
+             "multi_cast_kernel", "proj_gemm_kernel<0, 0>")   # folded path: the call's casts and the forward projections
 fwd = sum(v for k, v in kern.items() if k.startswith(fwd_names))
 bwd = sum(v for k, v in kern.items() if not k.startswith(fwd_names))
 path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "profiles", "dram_traffic.json")
