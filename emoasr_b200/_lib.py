@@ -11,7 +11,7 @@ LIB_PATH = os.environ.get("EMOASR_B200_LIB") or os.path.join(_HERE, "lib", "libe
 
 OP_RNNT_JOINT_FWD, OP_RNNT_JOINT_BWD, OP_CTC, OP_CTC_HEAD, OP_RNNT_JOINT_FULL = 0, 1, 2, 3, 4
 PREC_FP32, PREC_BF16 = 0, 1
-ABI_VERSION = 9
+ABI_VERSION = 10
 
 _c = ctypes
 _P = _c.c_void_p
@@ -36,6 +36,8 @@ _SIGNATURES = {
     "emo_rnnt_align": (_I, [_P] * 4 + [_I] * 3 + [_P, _P]),
     "emo_ctc_fwd": (_I, [_P] * 4 + [_I] * 6 + [_P, _P, _P, _P, _P]),
     "emo_ctc_bwd": (_I, [_P] * 8 + [_I] * 6 + [_P, _I, _P, _P]),
+    "emo_ctc_align_workspace_bytes": (_SZ, [_I] * 3),
+    "emo_ctc_align": (_I, [_P] * 4 + [_I] * 5 + [_P, _P, _SZ, _P]),
     "emo_ctc_head_supported": (_I, [_I] * 5),
     "emo_ctc_head_workspace_bytes": (_SZ, [_I] * 6),
     "emo_ctc_head_fwd": (_I, [_P] * 6 + [_I] * 7 + [_P] * 6 + [_SZ, _P]),

@@ -7,7 +7,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "lib", "libemoasr_b200.so")
-SOURCES = ["api.cu", "rnnt_lattice.cu", "ctc.cu", "joint_f32.cu", "joint_bf16.cu", "joint_bwd_ring.cu", "joint_reduce.cu", "ctc_head.cu", "joint_decode.cu", "proj.cu"]
+SOURCES = ["api.cu", "rnnt_lattice.cu", "ctc.cu", "joint_f32.cu", "joint_bf16.cu", "joint_bwd_ring.cu", "joint_reduce.cu", "ctc_head.cu", "joint_decode.cu", "proj.cu", "ctc_align.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

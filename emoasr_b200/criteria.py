@@ -115,6 +115,19 @@ class RNNTForcedAligner:
         return F.rnnt_forced_align(log_probs.detach(), ys, elens, ylens, blank=self.blank_id)
 
 
+class CTCForcedAligner:
+    """Call-compatible with asr/modeling/decoders/ctc_aligner.py:88-221 (``aligner(log_probs, elens, ys, ylens)`` ->
+    best_aligns (B,T) int64): the three Python loops over the frames (forward, backward, greedy pick with a per-frame
+    argmax read back to the host) are one kernel launch for the batch.  ``dropin.install()`` puts it in place of every
+    ``CTCDecoder.forced_aligner`` (the CTC distillation path, ctc.py:117-120,158-161)."""
+
+    def __init__(self, blank_id=0):
+        self.blank_id = blank_id
+
+    def __call__(self, log_probs, elens, ys, ylens):
+        return F.ctc_forced_align(log_probs, ys, elens, ylens, blank=self.blank_id)
+
+
 class RNNTWordDistillLoss(nn.Module):
     """asr/criteria.py:218-249 without the dense (B,T,U+1,V) logits:
     ``-sum_{t<xlen,u<ylen} sum_v q[u,v] log_softmax(z[t,u])[v]`` with ``sum_v q log p = (q W).h + q.b - (sum q) lse``:

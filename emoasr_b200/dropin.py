@@ -10,7 +10,8 @@ S1 module seam  ``warp_rnnt`` -> emoasr_b200.compat.warp_rnnt (mandatory: the im
 S2 class seam   asr.modeling.asr.RNNTDecoder / CTCDecoder and
                 asr.modeling.decoders.rnn_transducer.CTCDecoder are rebound to subclasses of the
                 reference's own classes whose forward() is the fused one.
-S3 attribute    every CTCDecoder gets ``ctc_loss_fn`` = emoasr_b200.criteria.CTCLoss.
+S3 attribute    every CTCDecoder gets ``ctc_loss_fn`` = emoasr_b200.criteria.CTCLoss and, where the reference built
+                one (distillation), ``forced_aligner`` = emoasr_b200.criteria.CTCForcedAligner.
 """
 import os
 import runpy
@@ -28,7 +29,7 @@ def install(reference_root=None, precision="bf16"):
     import asr.modeling.decoders.ctc as ref_ctc
     import asr.modeling.decoders.rnn_transducer as ref_rnnt
 
-    from .criteria import CTCLoss
+    from .criteria import CTCForcedAligner, CTCLoss
     from .decoders import FusedCTCForward, FusedRNNTForward, FusedRNNTSearch
 
     if getattr(ref_asr, "_emoasr_b200_installed", False):
@@ -40,6 +41,8 @@ def install(reference_root=None, precision="bf16"):
         def __init__(self, params):
             ref_ctc.CTCDecoder.__init__(self, params)
             self.ctc_loss_fn = CTCLoss(blank=self.blank_id, reduction="sum", zero_infinity=True)  # S3
+            if hasattr(self, "forced_aligner"):                                                   # S3 (ctc.py:67,85)
+                self.forced_aligner = CTCForcedAligner(blank_id=self.blank_id)
 
     class RNNTDecoder(FusedRNNTForward, FusedRNNTSearch, ref_rnnt.RNNTDecoder):
         fused_precision = precision

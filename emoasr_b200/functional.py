@@ -443,6 +443,30 @@ def ctc_loss(logits, labels, input_lengths, label_lengths, blank=0, reduction=No
     return _reduce(nll, reduction)
 
 
+def ctc_forced_align(log_probs, labels, input_lengths, label_lengths, blank=0):
+    """Drop-in for ``CTCForcedAligner(blank_id)(log_probs, elens, ys, ylens)`` (ctc_aligner.py:138-221): log_probs
+    (B,T,V) = log_softmax(logits); returns best_aligns (B,T) int64 on the same device (the label or blank chosen for
+    every frame, 0 past the utterance).  One launch; the argument is not modified (the reference zeroes its padded
+    frames in place, which never influences the result)."""
+    _require_cuda(log_probs)
+    lib = _lib.load()
+    lp = _f32c(log_probs.detach())
+    B, T, V = lp.shape
+    dev = lp.device
+    labels, tlen, ulen = _i64c(labels, dev), _i64c(input_lengths, dev), _i64c(label_lengths, dev)
+    if labels.dim() != 2 or labels.size(0) != B:
+        raise RuntimeError(f"labels must be (B, Umax); got {tuple(labels.shape)}")
+    if labels.size(1) == 0:
+        labels = torch.zeros(B, 1, dtype=torch.int64, device=dev)
+    Umax = labels.size(1)
+    with torch.cuda.device(dev):
+        aligns = torch.empty(B, T, dtype=torch.int64, device=dev)
+        ws = torch.empty(int(lib.emo_ctc_align_workspace_bytes(B, T, Umax)), dtype=torch.uint8, device=dev)
+        _lib.check(lib.emo_ctc_align(_p(lp), _p(labels), _p(tlen), _p(ulen), B, T, V, Umax, int(blank), _p(aligns),
+                                     _p(ws), ws.numel(), _stream()), "emo_ctc_align")
+    return aligns
+
+
 # ----------------------------------------------------------------------------------------------
 def ctc_head_supported(B, T, He, V, Umax):
     """True if ctc_head_loss can run these sizes on the tensor-core path (host call, no CUDA work)."""

@@ -32,7 +32,7 @@
 extern "C" {
 #endif
 
-#define EMO_ABI_VERSION 9
+#define EMO_ABI_VERSION 10
 
 enum emo_status {
     EMO_OK = 0,
@@ -194,6 +194,19 @@ int emo_ctc_bwd(const float* logits, const long long* labels, const long long* t
                 const long long* ulen, const float* lse, const float* alpha_ws, const float* nll,
                 const float* grad_nll, int B, int T, int V, int Umax, int blank, int zero_infinity,
                 float* beta_ws, int beta_valid, float* grad_logits, void* stream);
+
+/* ---- CTC forced alignment ---------------------------------------------------------------------------
+ * Replaces CTCForcedAligner.__call__ (asr/modeling/decoders/ctc_aligner.py:138-221; used by the CTC distillation
+ * path, ctc.py:117-120,158-161): forward / backward over the blank-extended label path and the reference's greedy
+ * pick through the state posteriors, one launch for the batch instead of three Python loops over the frames with a
+ * host read per frame.  log_probs (B,T,V) fp32 = log_softmax(logits) as the reference passes it (NOT modified: the
+ * reference zeroes the padded frames of its argument in place, :144-147; they never reach the result); labels /
+ * lengths as emo_ctc_fwd; aligns (B,T) int64: the label (or blank) chosen for every frame t < tlen[b], 0 after it.
+ * ws: emo_ctc_align_workspace_bytes(B,T,Umax) bytes.  2*Umax+1 <= 1024, Umax >= 1. */
+size_t emo_ctc_align_workspace_bytes(int B, int T, int Umax);
+int emo_ctc_align(const float* log_probs, const long long* labels, const long long* tlen, const long long* ulen,
+                  int B, int T, int V, int Umax, int blank, long long* aligns, void* ws, size_t ws_bytes,
+                  void* stream);
 
 /* ---- fused CTC head: output Linear + log_softmax + CTC loss --------------------------------------
  * Replaces asr/modeling/decoders/ctc.py:103-113 (`logits = self.output(eouts)`; `ctc_loss_fn(logits.transpose(1,0)

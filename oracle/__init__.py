@@ -14,6 +14,8 @@ rnnt_dp.py     fp64 numpy restatement of the RNN-T joint + transducer loss and i
 ctc_dp.py      fp64 numpy restatement of Linear -> log_softmax -> CTCLoss(sum, zero_infinity)/B
                (asr/modeling/decoders/ctc.py:103-115; blank-extended path as
                asr/modeling/decoders/ctc_aligner.py:19-22).
+ctc_align.py   float32 numpy restatement of the CTC forced aligner
+               (asr/modeling/decoders/ctc_aligner.py:138-221), pinned by ref_ctc_forced_align.npz.
 torch_path.py  the reference's own op sequence in torch fp32 on CPU
                (joint -> log_softmax -> rnnt_loss ; Linear -> log_softmax -> nn.CTCLoss).
                ``warp_rnnt`` (1ytic/warp-rnnt, version unpinned by the reference, CUDA-only,

@@ -289,6 +289,35 @@ def smoke_fixtures():
     print("known_answer", _np(cost))
 
 
+def ctc_align_cases():
+    """asr/modeling/decoders/ctc_aligner.py: the unmodified CTCForcedAligner on its own smoke input (:224-236) and on
+    random ragged batches (repeated labels, empty label sequences, one infeasible utterance, peaked posteriors)."""
+    from asr.modeling.decoders.ctc_aligner import CTCForcedAligner
+    aligner = CTCForcedAligner(blank_id=0)
+    out = {}
+
+    def add(i, logits, elens, ys, ylens):
+        lp = torch.log_softmax(logits, dim=-1)
+        aligns = aligner(lp.clone(), elens, ys, ylens)      # the aligner zeroes padded frames of its argument
+        out.update({f"c{i}_log_probs": _np(lp), f"c{i}_elens": _np(elens), f"c{i}_ys": _np(ys),
+                    f"c{i}_ylens": _np(ylens), f"c{i}_aligns": _np(aligns)})
+
+    torch.manual_seed(1)                                       # :225-233
+    add(0, torch.rand((2, 8, 3)) * 10.0, torch.tensor([7, 8]), torch.tensor([[1, 2, 0], [1, 2, 1]]), torch.tensor([2, 3]))
+    g = torch.Generator().manual_seed(21)
+    add(1, torch.randn(4, 23, 11, generator=g) * 3.0, torch.tensor([23, 17, 9, 23]),
+        torch.randint(1, 11, (4, 6), generator=g), torch.tensor([6, 4, 0, 2]))
+    add(2, torch.randn(3, 40, 5, generator=g) * 6.0, torch.tensor([40, 31, 12]),       # 4 labels: many repeats
+        torch.randint(1, 5, (3, 9), generator=g), torch.tensor([9, 9, 5]))
+    add(3, torch.randn(3, 14, 29, generator=g), torch.tensor([14, 3, 14]),            # utterance 1: 3 frames, 5 labels
+        torch.randint(1, 29, (3, 5), generator=g), torch.tensor([5, 5, 1]))
+    add(4, torch.randn(5, 61, 203, generator=g) * 2.0, torch.tensor([61, 55, 50, 41, 30]),
+        torch.randint(1, 203, (5, 20), generator=g), torch.tensor([20, 18, 20, 7, 11]))
+    out["n_cases"] = np.int64(5)
+    np.savez_compressed(os.path.join(OUT, "ref_ctc_forced_align.npz"), **out)
+    print("ref_ctc_forced_align", [out[f"c{i}_aligns"].shape for i in range(5)])
+
+
 ONLY = None   # python oracle/gen_golden.py NAME ... : regenerate just these cases
 
 
@@ -310,6 +339,10 @@ def main():
 
     if ONLY is None or "smoke" in ONLY:
         smoke_fixtures()
+    if ONLY is None or "ctc_align" in ONLY:
+        ctc_align_cases()
+    if ONLY is not None and ONLY <= {"smoke", "ctc_align"}:
+        return
     p = _params()
     rnnt_case("ref_rnnt_small_full", 0, B=3, T=9, U=5, p=p, tlens=[9, 9, 9], ulens=[5, 5, 5])
     rnnt_case("ref_rnnt_small_ragged", 1, B=4, T=12, U=6, p=p, tlens=[12, 10, 7, 1], ulens=[6, 3, 0, 2])

@@ -72,3 +72,14 @@ def test_fused_forward_has_no_cpu_fallback(seams):
     ys_in = torch.cat([torch.full((B, 1), p.eos_id), ys], dim=1)
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         dec(eouts, torch.tensor([T, T - 1]), None, ys, torch.tensor([U, U]), ys_in, None)
+
+
+def test_attribute_seam_replaces_the_ctc_forced_aligner(seams):
+    """ctc.py:58-68: a distilling CTCDecoder builds a CTCForcedAligner; the seam swaps in the one-launch device version."""
+    from emoasr_b200.criteria import CTCForcedAligner
+    p = _params(decoder_type="ctc", kd_weight=0.5, lsm_prob=0.0, reduce_main_loss_kd=False)
+    dec = seams.CTCDecoder(p)
+    assert isinstance(dec.forced_aligner, CTCForcedAligner) and dec.forced_aligner.blank_id == p.blank_id
+    assert not hasattr(seams.CTCDecoder(_params(decoder_type="ctc")), "forced_aligner")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dec.forced_aligner(torch.zeros(1, 4, 5), torch.tensor([4]), torch.tensor([[1]]), torch.tensor([1]))

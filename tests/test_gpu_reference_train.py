@@ -128,3 +128,44 @@ def test_train_step_fp32_matches_cpu_reference_to_1e5():
         assert abs(outs["gpu"][0][k] - outs["cpu"][0][k]) <= 1e-5 * abs(outs["cpu"][0][k]), (k, outs["gpu"][0], outs["cpu"][0])
     for g, c in zip(outs["gpu"][1:], outs["cpu"][1:]):
         assert abs(g["loss_total"] - c["loss_total"]) <= 1e-3 * abs(c["loss_total"]), (g, c)
+
+
+def test_ctc_distillation_through_the_seams_matches_the_reference_classes():
+    """CTC knowledge distillation (ctc.py:117-127): the reference's forward with soft labels, once with its own
+    nn.CTCLoss + Python forced aligner, once with the attribute seams (CUDA CTC loss, one-launch forced aligner,
+    ctc_aligner.py:138-221) -- same loss_dict and gradients."""
+    from collections import namedtuple
+    ref = _reference_root()
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    sys.path.insert(0, ref)
+    from emoasr_b200 import dropin
+    from emoasr_b200.criteria import CTCForcedAligner
+    ref_asr = dropin.install(ref, precision="fp32")
+    import asr.modeling.decoders.ctc as ref_ctc
+    base = dict(enc_hidden_size=32, vocab_size=47, blank_id=0, eos_id=2, kd_weight=0.4, lsm_prob=0.1,
+                reduce_main_loss_kd=False, mtl_phone_ctc_weight=0, mtl_inter_ctc_weight=0)
+    p = namedtuple("Params", base.keys())(**base)
+    dev = torch.device("cuda:0")
+    torch.manual_seed(3)
+    plain = ref_ctc.CTCDecoder(p).to(dev)
+    fused = ref_asr.CTCDecoder(p).to(dev)
+    fused.load_state_dict(plain.state_dict())
+    assert isinstance(fused.forced_aligner, CTCForcedAligner)
+    B, T, U = 4, 31, 7
+    g = torch.Generator().manual_seed(4)
+    eouts = torch.randn(B, T, 32, generator=g).to(dev)
+    elens = torch.tensor([31, 26, 19, 31], device=dev)
+    ys = torch.randint(4, 47, (B, U), generator=g)     # labels stay on the host: the reference's to_onehot (criteria.py:5-6)
+    ylens = torch.tensor([7, 5, 7, 2])                # indexes a CPU identity matrix with them
+    soft = torch.softmax(torch.randn(B, U, 47, generator=g), dim=-1).to(dev)
+    outs = {}
+    for name, dec in (("plain", plain), ("fused", fused)):
+        x = eouts.clone().requires_grad_()
+        loss, loss_dict, _ = dec(x, elens, None, ys, ylens, None, None, soft)
+        loss.backward()
+        outs[name] = ({k: float(v) for k, v in loss_dict.items()}, x.grad.clone(), dec.output.weight.grad.clone())
+    for k, v in outs["plain"][0].items():
+        assert abs(outs["fused"][0][k] - v) <= 1e-5 * abs(v), (k, outs)
+    for a, b in zip(outs["fused"][1:], outs["plain"][1:]):
+        assert float((a - b).norm() / b.norm()) < 1e-4

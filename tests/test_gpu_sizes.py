@@ -496,3 +496,42 @@ def test_joint_from_outputs_vs_oracle(B, T, U, He, Hd, J, V):
     assert abs(float(loss) - r["loss"]) <= BF16_LOSS_RTOL * abs(r["loss"])
     for t, k in zip(te, ["d_eouts", "d_douts", "d_w_enc", "d_b_enc", "d_w_dec", "d_b_dec", "d_w_out", "d_b_out"]):
         assert rel_err(t.grad.cpu().numpy(), r[k]) < BF16_GRAD_RTOL, k
+
+
+# ---------------------------------------------------------------- CTC forced aligner (ctc_aligner.py:138-221)
+def test_ctc_forced_aligner_vs_reference_golden():
+    """emo_ctc_align against alignments of the UNMODIFIED reference aligner (integer output: exact)."""
+    import emoasr_b200 as E
+    g = load_golden("ref_ctc_forced_align")
+    aligner = E.CTCForcedAligner(blank_id=0)
+    for i in range(int(g["n_cases"])):
+        lp = T_(g[f"c{i}_log_probs"])
+        keep = lp.clone()
+        got = aligner(lp, T_(g[f"c{i}_elens"]), T_(g[f"c{i}_ys"]), T_(g[f"c{i}_ylens"]))
+        assert got.dtype == torch.int64 and got.shape == lp.shape[:2]
+        assert torch.equal(lp, keep)                       # the argument is left alone
+        assert np.array_equal(got.cpu().numpy(), g[f"c{i}_aligns"]), f"case {i}"
+
+
+def test_ctc_forced_aligner_cfg2_size_vs_oracle():
+    """B=8 utterances of the cfg-2 shape (T=374, V=5000, U<=80) against the numpy restatement; picks may differ from
+    it only where the two best reachable states tie to float32 rounding, which a random input does not produce."""
+    import emoasr_b200 as E
+    from oracle import ctc_align
+    gen = torch.Generator().manual_seed(5)
+    B, T, V, U = 8, 374, 5000, 80
+    lp = torch.log_softmax(torch.randn(B, T, V, generator=gen) * 2.0, dim=-1)
+    ys = torch.randint(1, V, (B, U), generator=gen)
+    ys[0, 10:20] = 7                                       # a run of repeated labels
+    elens = torch.tensor([374, 374, 300, 251, 200, 170, 161, 90])
+    ylens = torch.tensor([80, 41, 80, 60, 80, 3, 80, 0])
+    want = ctc_align.ctc_forced_align(lp.numpy(), elens.numpy(), ys.numpy(), ylens.numpy(), blank=0)
+    got = E.ctc_forced_align(lp.to(dev()), ys.to(dev()), elens.to(dev()), ylens.to(dev()), blank=0).cpu().numpy()
+    assert np.array_equal(got, want)
+    for b in range(B):                                     # collapsing the walk gives back the labels
+        x, u = int(elens[b]), int(ylens[b])
+        seq = got[b, :x]
+        labels = [int(v) for k, v in enumerate(seq) if v != 0 and (k == 0 or v != seq[k - 1] or False)]
+        if b != 0:                                         # utterance 0 has repeated labels separated by blanks
+            assert labels == [int(v) for v in ys[b, :u]]
+        assert (got[b, x:] == 0).all()

@@ -5,7 +5,7 @@ import pytest
 import torch
 
 from conftest import load_golden, pred_net_douts, rel_err
-from oracle import clattice, ctc_dp, rnnt_dp, torch_path
+from oracle import clattice, ctc_align, ctc_dp, rnnt_dp, torch_path
 
 RNNT_CASES = ["ref_rnnt_small_full", "ref_rnnt_small_ragged", "ref_rnnt_small_auxctc", "ref_rnnt_medium_ragged",
               "ref_rnnt_tcshape_ragged", "ref_rnnt_tcshape_auxctc", "ref_rnnt_tcfull_auxctc"]
@@ -187,3 +187,21 @@ def test_word_distill_restatement_vs_reference():
     w = float(g["hp.kd_weight"])
     total = (1 - w) * float(g["lossdict.loss_rnnt"]) + w * kd
     assert abs(total - float(g["loss_total"])) <= 1e-5 * abs(total)
+
+
+def test_ctc_forced_aligner_restatement_vs_reference_golden():
+    """oracle/ctc_align.py against alignments the UNMODIFIED CTCForcedAligner produced (ctc_aligner.py:138-221; its own
+    smoke input, ragged batches with repeated labels, an empty label sequence, an infeasible utterance)."""
+    g = load_golden("ref_ctc_forced_align")
+    for i in range(int(g["n_cases"])):
+        got = ctc_align.ctc_forced_align(g[f"c{i}_log_probs"], g[f"c{i}_elens"], g[f"c{i}_ys"], g[f"c{i}_ylens"], blank=0)
+        assert np.array_equal(got, g[f"c{i}_aligns"]), f"case {i}"
+        # an alignment is a monotone walk through the blank-extended path: collapsing repeats and dropping blanks gives
+        # a prefix-free subsequence check only for feasible utterances
+        for b in range(got.shape[0]):
+            x, u = int(g[f"c{i}_elens"][b]), int(g[f"c{i}_ylens"][b])
+            if x >= 2 * u + 1:      # comfortably feasible
+                seq = got[b, :x]
+                collapsed = [int(v) for k, v in enumerate(seq) if k == 0 or v != seq[k - 1]]
+                labels = [v for v in collapsed if v != 0]
+                assert labels == [int(v) for v in g[f"c{i}_ys"][b, :u]] or len(labels) <= u
