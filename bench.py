@@ -6,18 +6,23 @@
                     [--lengths full|ragged] [--grad-payload-mb M] [--no-extras]
 
 A "step" is one pass of the hot path over one batch of synthetic input:
-  RNN-T  enc_proj = w_enc(eouts), dec_proj = w_dec(douts)  (plain cuBLAS Linear, as in the
-         reference's joint) -> fused joint + log-softmax + transducer loss -> backward to eouts,
-         douts and every joint parameter   (asr/modeling/decoders/rnn_transducer.py:101-115,147-156)
-  CTC    eouts -> output Linear -> fused log-softmax + CTC loss -> backward to eouts and the Linear's
-         parameters                         (asr/modeling/decoders/ctc.py:103-113)
+  RNN-T  enc_proj = w_enc(eouts), dec_proj = w_dec(douts) -> fused joint + log-softmax + transducer loss ->
+         backward to eouts, douts and every joint parameter (asr/modeling/decoders/rnn_transducer.py:57-58,101-115,
+         147-156); by default the projections and their backward run inside the library too (two C calls + the
+         lattice per step), --unfolded keeps them as cuBLAS Linear around the fused joint
+  CTC    eouts -> output Linear -> log-softmax + CTC loss -> backward to eouts and the Linear's parameters
+         (asr/modeling/decoders/ctc.py:103-113): the fused tensor-core head from 8192 frames per batch upwards,
+         else cuBLAS Linear + the fused loss kernels on logits
 Default workload (N=1): BASELINE cfg 3, "RNN-T(Cf.) 1kBPE 26M fused joint+loss, B=32 T=250 U=100 V=1024"; nothing
 of size N x V is written to HBM, forward or backward.  The default N=1 run also reports, under "extra", CTC cfg 2,
 and under "gpu_baseline" same-box GPU comparators (the reference's materialised op sequence on CUDA; torch's CUDA
 ctc_loss) -- `--no-extras` skips them.
 For N>1 every rank processes its own batch of the same shape (weak scaling, batch-sharded) and the gradients of
 the path's parameters (plus, with --grad-payload-mb, a stand-in for the rest of the model's gradients) are
-all-reduced over NCCL inside the timed step, launched from autograd hooks so that they overlap the backward.
+all-reduced over NCCL inside the timed step, launched from autograd hooks (the fused joint's six parameter gradients
+arrive in one flat buffer: one collective).
+The end-to-end number is the median of three regions of `--steps` steps fed from pinned host buffers; EMO_BENCH_TRACE=1
+prints every timed step's device time to stderr.
 
 One JSON line is printed by rank 0 (see the driver contract in the task statement).
 """

@@ -23,10 +23,12 @@
 //
 // Ring protocol (global int counters, zeroed per launch by ring_prep_kernel): items are produced and consumed
 // in increasing order of the dense pair-tile index q (prefix sums over the utterances' valid cells), slot =
-// item mod slots.  A writer lane signals "ready" with red.release.gpu after its TMA stores have completed
-// (cp.async.bulk.wait_group 0); a consumer polls with ld.acquire.gpu before its TMA loads and signals "done"
-// once the loads have landed (mbarrier complete_tx observed); a producer polls "done" of the previous use of
-// the slot before overwriting it.  No role ever waits for a LATER item, all CTAs are co-resident (grid <=
+// item mod slots.  A writer signals "ready" with red.release.gpu after its TMA stores have completed
+// (cp.async.bulk.wait_group 0); a consumer polls (relaxed loads, then one ld.acquire.gpu) before its TMA loads and
+// signals "done" once the loads have landed (mbarrier complete_tx observed); a producer waits for "done" of the
+// previous use of the slot before overwriting it.  In a producer CTA both global-memory sides of the protocol
+// belong to one "ring manager" lane (warp 2): the epilogue warps hand it finished items / receive free slots
+// through shared-memory mbarriers.  No role ever waits for a LATER item, all CTAs are co-resident (grid <=
 // resident clusters, checked on the host), hence no deadlock.
 #include "joint_tc.cuh"
 
