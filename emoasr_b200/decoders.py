@@ -91,6 +91,22 @@ class FusedCTCForward:
         return loss, loss_dict, logits
 
 
+    def _greedy(self, eouts, elens, decode_phone=False):
+        """ctc.py:176-200 with ONE device-to-host copy of the best path per batch instead of one ``.item()`` per
+        frame and utterance (24 k host synchronisations at B=64, T=374); same return values."""
+        from itertools import groupby
+        logits = self.phone_output(eouts) if decode_phone else self.output(eouts)
+        best_paths = logits.argmax(-1).cpu()
+        lens = [int(n) for n in elens]
+        hyps, scores, aligns = [], [], []
+        for b in range(eouts.size(0)):
+            indices = best_paths[b, :lens[b]].tolist()
+            hyps.append([x for x, _ in groupby(indices) if x != self.blank_id])
+            scores.append(None)
+            aligns.append(indices)
+        return hyps, scores, logits, aligns
+
+
 class FusedRNNTForward:
     """forward() of rnn_transducer.py:81-145 with joint -> log_softmax -> warp_rnnt.rnnt_loss
     (:101-115) replaced by one fused op.  The third return value is None (the (B,T,U+1,V) logits are never

@@ -83,3 +83,19 @@ def test_attribute_seam_replaces_the_ctc_forced_aligner(seams):
     assert not hasattr(seams.CTCDecoder(_params(decoder_type="ctc")), "forced_aligner")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         dec.forced_aligner(torch.zeros(1, 4, 5), torch.tensor([4]), torch.tensor([[1]]), torch.tensor([1]))
+
+
+def test_ctc_greedy_decode_keeps_the_reference_results(seams):
+    """ctc.py:176-200: the seam's _greedy (one host copy per batch) against the reference's per-frame .item() loop."""
+    import asr.modeling.decoders.ctc as ref_ctc
+    p = _params(decoder_type="ctc")
+    torch.manual_seed(1)
+    fused = seams.CTCDecoder(p)
+    plain_cls = [c for c in type(fused).__mro__ if c.__module__ == ref_ctc.__name__][0]
+    plain = plain_cls(p)
+    plain.load_state_dict(fused.state_dict())
+    eouts = torch.randn(3, 17, p.enc_hidden_size) * 3
+    elens = torch.tensor([17, 11, 1])
+    h0, s0, l0, a0 = plain._greedy(eouts, elens)
+    h1, s1, l1, a1 = fused._greedy(eouts, elens)
+    assert h0 == h1 and s0 == s1 and a0 == a1 and torch.equal(l0, l1)
