@@ -535,3 +535,26 @@ def test_ctc_forced_aligner_cfg2_size_vs_oracle():
         if b != 0:                                         # utterance 0 has repeated labels separated by blanks
             assert labels == [int(v) for v in ys[b, :u]]
         assert (got[b, x:] == 0).all()
+
+
+def test_ctc_forced_aligner_edges():
+    """empty label matrix, an utterance without frames, labels outside the vocabulary are clamped, too long a label
+    matrix is refused (2*Umax+1 > 1024 threads), CPU tensors are refused."""
+    import emoasr_b200 as E
+    from oracle import ctc_align
+    gen = torch.Generator().manual_seed(9)
+    lp = torch.log_softmax(torch.randn(3, 12, 6, generator=gen), dim=-1)
+    elens = torch.tensor([12, 0, 5])
+    got = E.ctc_forced_align(lp.to(dev()), torch.zeros(3, 0, dtype=torch.long, device=dev()), elens.to(dev()),
+                             torch.zeros(3, dtype=torch.long, device=dev()), blank=0).cpu().numpy()
+    assert (got == 0).all()                                      # only blanks can be aligned
+    ys = torch.tensor([[1, 2, 3], [4, 5, 1], [2, 2, 2]])
+    ylens = torch.tensor([3, 2, 3])
+    want = ctc_align.ctc_forced_align(lp.numpy(), elens.numpy(), ys.numpy(), ylens.numpy(), blank=0)
+    got = E.ctc_forced_align(lp.to(dev()), ys.to(dev()), elens.to(dev()), ylens.to(dev()), blank=0).cpu().numpy()
+    assert np.array_equal(got, want) and (got[1] == 0).all()
+    with pytest.raises(RuntimeError, match="1024"):
+        E.ctc_forced_align(lp.to(dev()), torch.ones(3, 600, dtype=torch.long, device=dev()), elens.to(dev()),
+                           ylens.to(dev()), blank=0)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        E.ctc_forced_align(lp, ys, elens, ylens)
