@@ -498,6 +498,39 @@ def test_joint_from_outputs_vs_oracle(B, T, U, He, Hd, J, V):
         assert rel_err(t.grad.cpu().numpy(), r[k]) < BF16_GRAD_RTOL, k
 
 
+def test_folded_path_full_size_cfg3_vs_fp32_mode():
+    """The configuration bench.py times by default -- BASELINE cfg 3 at full size (B=32, T=250, U=100, V=1024, He=256,
+    Hd=512, J=512) through emo_rnnt_joint_full_fwd / _bwd -- against the fp32 mode (fp32 cuBLAS projections around the
+    fp32 joint kernels, itself pinned to the reference at 1e-5 / 1e-4): loss and all eight gradients within the stated
+    bf16 tolerance, exact zeros for padded frames / labels."""
+    import emoasr_b200 as E
+    gen = torch.Generator().manual_seed(3)
+    B, T, U, He, Hd, J, V = 32, 250, 100, 256, 512, 512, 1024
+    eouts = torch.randn(B, T, He, generator=gen).to(dev())
+    douts = torch.tanh(torch.randn(B, U + 1, Hd, generator=gen)).to(dev())
+    torch.manual_seed(1234)
+    lin = [torch.nn.Linear(He, J), torch.nn.Linear(Hd, J), torch.nn.Linear(J, V)]
+    ps = [p.detach().to(dev()) for l in lin for p in (l.weight, l.bias)]      # w_enc b_enc w_dec b_dec w_out b_out
+    ys = torch.randint(1, V, (B, U), generator=gen).to(dev())
+    r = torch.linspace(1.0, 0.6, B)
+    tl, ul = (T * r).long().to(dev()), (U * r).long().to(dev())
+    a = [t.clone().requires_grad_() for t in [eouts, douts] + ps]
+    loss = E.rnnt_joint_loss_from_outputs(*a, ys, tl, ul, blank=0, reduction="mean")
+    loss.backward()
+    b = [t.clone().requires_grad_() for t in [eouts, douts] + ps]
+    enc_proj = torch.nn.functional.linear(b[0], b[2], b[3])
+    dec_proj = torch.nn.functional.linear(b[1], b[4], b[5])
+    loss32 = E.rnnt_joint_loss(enc_proj, dec_proj, b[6], b[7], ys, tl, ul, blank=0, reduction="mean", precision="fp32")
+    loss32.backward()
+    assert abs(float(loss) - float(loss32)) <= BF16_LOSS_RTOL * abs(float(loss32))
+    names = ["d_eouts", "d_douts", "d_w_enc", "d_b_enc", "d_w_dec", "d_b_dec", "d_w_out", "d_b_out"]
+    for got, ref, k in zip(a, b, names):
+        assert float((got.grad - ref.grad).norm() / ref.grad.norm()) < BF16_GRAD_RTOL, k
+    last = B - 1
+    assert float(a[0].grad[last, int(tl[last]):].abs().sum()) == 0.0
+    assert float(a[1].grad[last, int(ul[last]) + 1:].abs().sum()) == 0.0
+
+
 # ---------------------------------------------------------------- CTC forced aligner (ctc_aligner.py:138-221)
 def test_ctc_forced_aligner_vs_reference_golden():
     """emo_ctc_align against alignments of the UNMODIFIED reference aligner (integer output: exact)."""
