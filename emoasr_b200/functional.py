@@ -151,9 +151,26 @@ def rnnt_loss(log_probs, labels, frames_lengths, labels_lengths, average_frames=
 
 
 # ----------------------------------------------------------------------------------------------
+def _padded_hidden(J):
+    return (J + 127) // 128 * 128
+
+
 def joint_supported(precision, B, T, U1, J, V):
-    """True if rnnt_joint_loss can run these sizes with this precision (host call, no CUDA work)."""
-    return bool(_lib.load().emo_rnnt_joint_supported(_PRECISIONS[precision], B, T, U1, J, V))
+    """True if rnnt_joint_loss can run these sizes with this precision (host call, no CUDA work).  The tensor-core
+    kernels need J % 128 == 0: a joint size that is not is zero-padded to the next multiple by rnnt_joint_loss /
+    rnnt_joint_outputs (see _pad_hidden), so what counts here is the padded size."""
+    prec = _PRECISIONS[precision]
+    return bool(_lib.load().emo_rnnt_joint_supported(prec, B, T, U1, _padded_hidden(J) if prec == _lib.PREC_BF16 else J, V))
+
+
+def _pad_hidden(enc_proj, dec_proj, w_out):
+    """Zero-pads the joint dimension to a multiple of 128 (tensor-core mode): tanh(0 + 0) = 0 meets zero columns of
+    w_out, so logits, loss and the gradients of the real columns are unchanged; autograd slices the padding off."""
+    pad = -enc_proj.size(-1) % 128
+    if pad == 0:
+        return enc_proj, dec_proj, w_out
+    P = torch.nn.functional.pad
+    return P(enc_proj, (0, pad)), P(dec_proj, (0, pad)), P(w_out, (0, pad))
 
 
 class _RNNTJoint(torch.autograd.Function):
@@ -249,6 +266,8 @@ def rnnt_joint_loss(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths, la
     hands ``dz`` to the gradient GEMMs through an L2-resident ring of tiles; precision="fp32" (parity mode)
     streams them through a bounded slab.
     """
+    if _PRECISIONS[precision] == _lib.PREC_BF16:
+        enc_proj, dec_proj, w_out = _pad_hidden(enc_proj, dec_proj, w_out)
     costs, _, _ = _RNNTJoint.apply(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths,
                                    labels_lengths, int(blank), _PRECISIONS[precision], False)
     return _reduce(costs, reduction)
@@ -262,6 +281,8 @@ def rnnt_joint_outputs(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths,
     per-cell dot products it gives any ``sum_v q[v] log_softmax(z)[v] = q.z - (sum q) lse`` without the dense
     tensor (knowledge distillation, asr/criteria.py:218-288).  ``aligns`` is the forced alignment of
     asr/modeling/decoders/rnnt_aligner.py:155-198 computed on the same lattice."""
+    if _PRECISIONS[precision] == _lib.PREC_BF16:
+        enc_proj, dec_proj, w_out = _pad_hidden(enc_proj, dec_proj, w_out)
     costs, lse, al = _RNNTJoint.apply(enc_proj, dec_proj, w_out, b_out, labels, frames_lengths,
                                       labels_lengths, int(blank), _PRECISIONS[precision], bool(aligns))
     return costs, lse, (al if aligns else None)

@@ -302,6 +302,10 @@ BF16_SHAPES = [
     (2, 12, 6, 100, 128),     # vocabulary not a multiple of 32: padded inside the workspace (zero weights, -1e30 bias)
     (2, 14, 5, 1087, 256),    # odd vocabulary spanning several chunks (the reference's 10872 / 9798 are of this kind)
 ]
+BF16_PADDED_J_SHAPES = [      # joint size not a multiple of 128: zero-padded by functional.rnnt_joint_loss (not by the C ABI)
+    (3, 17, 6, 100, 72),
+    (2, 30, 11, 300, 320),    # -> 384
+]
 
 
 @pytest.mark.parametrize("B,T,U,V,J", BF16_SHAPES)
@@ -332,7 +336,7 @@ def test_joint_bf16_forward_values(B, T, U, V, J):
     assert np.abs(lsef[0, :, :] - lse_ref[0]).max() < 1e-4
 
 
-@pytest.mark.parametrize("B,T,U,V,J", BF16_SHAPES)
+@pytest.mark.parametrize("B,T,U,V,J", BF16_SHAPES + BF16_PADDED_J_SHAPES)
 def test_joint_bf16_loss_and_grads(B, T, U, V, J):
     """Loss and all four gradients of the tensor-core path (logit tiles recomputed by the backward, dz handed to
     the gradient GEMMs through the L2-resident ring, nothing N x V in HBM) vs the fp64 oracle."""
