@@ -491,7 +491,7 @@ def ctc_forced_align(log_probs, labels, input_lengths, label_lengths, blank=0):
 # ----------------------------------------------------------------------------------------------
 def ctc_head_supported(B, T, He, V, Umax):
     """True if ctc_head_loss can run these sizes on the tensor-core path (host call, no CUDA work)."""
-    return bool(_lib.load().emo_ctc_head_supported(B, T, He, V, max(Umax, 1)))
+    return bool(_lib.load().emo_ctc_head_supported(B, T, _padded_hidden(He), V, max(Umax, 1)))   # see ctc_head_loss
 
 
 class _CTCHead(torch.autograd.Function):
@@ -558,8 +558,13 @@ def ctc_head_loss(eouts, weight, bias, labels, input_lengths, label_lengths, bla
 
     Equivalent to ``ctc_loss(linear(eouts, weight, bias), ...)`` (ctc.py:103-113) with the Linear, the log_softmax,
     the loss and all three backward GEMMs fused: the (B,T,V) logits are never formed.  Tensor-core path (bf16
-    operands, fp32 accumulation); shapes outside ``ctc_head_supported`` raise.
+    operands, fp32 accumulation); shapes outside ``ctc_head_supported`` raise.  ``He`` is zero-padded to a multiple of
+    128 here when it is not one.
     """
+    pad = -eouts.size(-1) % 128
+    if pad:   # an encoder width that is not a multiple of 128: zero columns on both operands leave the logits unchanged
+        eouts = torch.nn.functional.pad(eouts, (0, pad))
+        weight = torch.nn.functional.pad(weight, (0, pad))
     nll = _CTCHead.apply(eouts, weight, bias, labels, input_lengths, label_lengths, int(blank), bool(zero_infinity))
     return _reduce(nll, reduction)
 

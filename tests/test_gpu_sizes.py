@@ -255,6 +255,7 @@ HEAD_SHAPES = [
     (4, 61, 256, 1000, 17),    # vocabulary not a multiple of 32, several chunks
     (2, 300, 256, 5000, 80),   # cfg-2 head, more than one 256-frame pair tile per utterance
     (2, 37, 512, 2048, 12),    # widest supported hidden size
+    (3, 50, 144, 300, 11),     # encoder width not a multiple of 128: zero-padded to 256 by functional.ctc_head_loss
 ]
 
 
