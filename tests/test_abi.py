@@ -55,12 +55,15 @@ def test_ops_refuse_cpu_tensors():
 
 def test_shape_support_query():
     """Host-only: the tensor-core mode accepts any vocabulary size (the reference's 10872 / 9798 are not multiples of
-    32: padded inside the workspace) but needs J % 128 == 0 and J <= 512; fp32 mode accepts everything."""
+    32: padded inside the workspace) and any joint size up to 512 (the C ABI itself wants J % 128 == 0; the Python layer
+    zero-pads other sizes); fp32 mode accepts everything."""
     import emoasr_b200.functional as F
     assert F.joint_supported("bf16", 8, 249, 61, 512, 10872)
     assert F.joint_supported("bf16", 8, 249, 61, 256, 9798)
     assert not F.joint_supported("bf16", 8, 249, 61, 640, 1024)
-    assert not F.joint_supported("bf16", 8, 249, 61, 320, 1024)
+    assert F.joint_supported("bf16", 8, 249, 61, 320, 1024)            # run as J = 384 (functional._pad_hidden)
+    assert not _lib.load().emo_rnnt_joint_supported(_lib.PREC_BF16, 8, 249, 61, 320, 1024)   # the raw entry point
+    assert F.ctc_head_supported(8, 249, 144, 5000, 60) and not _lib.load().emo_ctc_head_supported(8, 249, 144, 5000, 60)
     assert F.joint_supported("fp32", 8, 249, 61, 640, 1000)
     # the padded vocabulary needs a slightly larger workspace than the next smaller multiple of 32
     a = _lib.workspace_bytes(_lib.OP_RNNT_JOINT_BWD, _lib.PREC_BF16, 2, 20, 8, 128, 96)
