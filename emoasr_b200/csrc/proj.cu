@@ -15,7 +15,7 @@
 namespace emo {
 namespace {
 
-constexpr int kPStages = 4;
+constexpr int kPStages = 2;      // 96 KiB of stages: two CTAs per SM, so the 178 tiles of the cfg-3 forward run as one wave
 constexpr int kPNT = 256;                 // output columns per CTA
 constexpr int kPThreads = 192;
 constexpr int kPABytes = kTileM * kBlockK * 2;     // 16 KiB
@@ -47,7 +47,7 @@ struct __align__(16) ProjBars {
 __device__ __forceinline__ uint64_t pdesc(uint32_t lo) { return ((uint64_t)kPDescHi << 32) | lo; }
 
 template <int FORM, int EPI>
-__global__ void __launch_bounds__(kPThreads, 1)
+__global__ void __launch_bounds__(kPThreads, 2)
 proj_gemm_kernel(const __grid_constant__ CUtensorMap tm_a0, const __grid_constant__ CUtensorMap tm_b0,
                  const __grid_constant__ CUtensorMap tm_a1, const __grid_constant__ CUtensorMap tm_b1,
                  const ProjArgs2 args) {
