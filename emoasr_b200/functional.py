@@ -319,7 +319,7 @@ class _RNNTJointFull(torch.autograd.Function):
                                    f"J={J} V={V} (see emo_rnnt_joint_full_supported)")
             fws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
             lp2 = torch.empty(B, T, U1, 2, device=dev)
-            lse = torch.zeros(B, T, U1, device=dev)
+            lse = torch.empty(B, T, U1, device=dev)     # internal here: only valid cells are written and read back
             _lib.check(lib.emo_rnnt_joint_full_fwd(_p(e), _p(d), _p(we), _p(be), _p(wd), _p(bd), _p(wo), _p(bo), _p(labels),
                                                    _p(tlen), _p(ulen), B, T, U1, He, Hd, J, V, blank, _p(lp2), _p(lse),
                                                    _p(fws), fws.numel(), _stream()), "emo_rnnt_joint_full_fwd")
