@@ -1313,11 +1313,16 @@ int joint_bwd_ring_launch(const void* w_bf16, const void* enc_h, const void* dec
     cfg.blockDim = dim3(kRingThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute attr[1];
+    // Cooperative launch: the roles wait for each other through the ring, so every CTA must be resident at the same
+    // time.  The grid is sized to the resident clusters (ring_max_pairs); the attribute makes the driver guarantee it
+    // -- the kernel does not start until all of it fits -- also when another stream's kernels hold SMs at that moment.
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeCooperative;
+    attr[1].val.cooperative = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     EMO_CUDA(cudaLaunchKernelEx(&cfg, joint_bwd_ring_kernel, tm_w_p, tm_w_d, tm_h_st, tm_h_ld, tm_z_st, tm_z_ld_d,
                                 tm_z_ld_w, tm_dh, a));
     EMO_CHECK_LAUNCH("joint_bwd_ring_kernel");
