@@ -225,6 +225,42 @@ def test_joint_bf16_repeatability():
             assert float((a - b_).norm() / b_.norm()) <= 1e-6, (it, k)
 
 
+@pytest.mark.timeout(180, method="thread")
+def test_two_steps_on_two_streams_at_once():
+    """The ring kernel's roles wait for each other, so all of its CTAs must be resident together; two instances
+    enqueued on two streams at the same time must not be interleaved on the SMs (cooperative launch).  Results equal
+    the sequential runs; a deadlock would trip the timeout."""
+    import emoasr_b200 as E
+    gen = torch.Generator().manual_seed(0)
+    B, T, U, V, J = 4, 120, 40, 1024, 512
+    tl, ul = torch.full((B,), T, device=dev()), torch.full((B,), U, device=dev())
+
+    def make():
+        return [torch.randn(B, T, J, generator=gen).to(dev()), torch.randn(B, U + 1, J, generator=gen).to(dev()),
+                (torch.randn(V, J, generator=gen) / J ** 0.5).to(dev()), torch.zeros(V, device=dev()),
+                torch.randint(1, V, (B, U), generator=gen).to(dev())]
+
+    def step(d):
+        te = [t.clone().requires_grad_() for t in d[:4]]
+        loss = E.rnnt_joint_loss(*te, d[4], tl, ul, blank=0, reduction="mean", precision="bf16")
+        loss.backward()
+        return [loss.detach()] + [t.grad for t in te]
+
+    a, b = make(), make()
+    ref_a, ref_b = step(a), step(b)
+    torch.cuda.synchronize()
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    for _ in range(10):
+        with torch.cuda.stream(s1):
+            ra = step(a)
+        with torch.cuda.stream(s2):
+            rb = step(b)
+        torch.cuda.synchronize()
+        for got, ref in ((ra, ref_a), (rb, ref_b)):
+            for x, y in zip(got, ref):
+                assert float((x - y).norm() / y.norm().clamp_min(1e-30)) < 1e-5
+
+
 def test_forward_and_backward_keep_nothing_of_size_N_x_V():
     """Peak device memory of a whole training step stays far below one N x V tensor (even at 2 bytes per entry):
     the logits are neither cached by the forward nor formed by the backward."""
